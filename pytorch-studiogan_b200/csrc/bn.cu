@@ -1,0 +1,361 @@
+// Batch-norm family on NHWC bf16 activations (HBM-bound streaming kernels, 16-byte vector accesses).
+//   stats      : per-channel sum / sum-of-squares                         (F.batch_norm training statistics)
+//   finalize   : mean / rstd, running-stat update, per-(image,channel) scale & shift for cBN or affine BN
+//   apply      : y = [relu](x*scale + shift), optional fused nearest x2 upsample of the result
+//   bwd_reduce : per-(image,channel) sums of dz and dz*xhat (+ channel totals weighted by the cBN gain)
+//   bwd_apply  : dx = a*dz - k1 - k2*xhat
+// Reference arithmetic: src/utils/ops.py:14-28 (ConditionalBatchNorm2d), :227-228 (batchnorm_2d, eps 1e-4,
+// momentum 0.1), torch F.batch_norm; cross-rank reduction points follow torch/nn/modules/_functions.py:7-212.
+#include "common.cuh"
+
+namespace sgb {
+
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xFFFF0000u);
+  f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xFFFF0000u);
+  f[4] = __uint_as_float(r.z << 16); f[5] = __uint_as_float(r.z & 0xFFFF0000u);
+  f[6] = __uint_as_float(r.w << 16); f[7] = __uint_as_float(r.w & 0xFFFF0000u);
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack2(f[0], f[1]); o.y = pack2(f[2], f[3]); o.z = pack2(f[4], f[5]); o.w = pack2(f[6], f[7]);
+  return o;
+}
+
+static constexpr int kChunkC = 2048;  // channels handled per blockIdx.y
+
+// ---------------------------------------------------------------------------------------------- stats
+__global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ x, long long npix, int C, long long cstride,
+                                                        float* __restrict__ sum, float* __restrict__ sumsq,
+                                                        long long pix_per_block) {
+  __shared__ float s_sum[kChunkC];
+  __shared__ float s_sq[kChunkC];
+  const int c_base = blockIdx.y * kChunkC;
+  const int cc = min(C - c_base, kChunkC);
+  const int VG = cc >> 3;
+  for (int i = threadIdx.x; i < cc; i += 256) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
+  __syncthreads();
+  const int VGb = VG < 256 ? VG : 256;
+  const int nrows = 256 / VGb;
+  const int g = threadIdx.x % VGb, prow = threadIdx.x / VGb;
+  if (prow < nrows) {
+    float a[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] = 0.f; q[j] = 0.f; }
+    const long long p0 = (long long)blockIdx.x * pix_per_block;
+    const long long p1 = min(p0 + pix_per_block, npix);
+    for (long long p = p0 + prow; p < p1; p += nrows) {
+      const uint4 r = __ldg(reinterpret_cast<const uint4*>(x + p * cstride + c_base) + g);
+      float f[8];
+      unpack8(r, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { atomicAdd(&s_sum[g * 8 + j], a[j]); atomicAdd(&s_sq[g * 8 + j], q[j]); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cc; i += 256) {
+    atomicAdd(sum + c_base + i, s_sum[i]);
+    atomicAdd(sumsq + c_base + i, s_sq[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- finalize
+// mode 0: cBN     scale[b,c] = rstd*(1+gain[b,c]),  shift[b,c] = bias[b,c] - mean*scale[b,c]   (nb = B rows)
+// mode 1: affine  scale[c]   = rstd*weight[c],      shift[c]   = bias[c]   - mean*scale[c]     (nb = 1 row)
+// mode 2: plain   scale[c]   = rstd,                shift[c]   = -mean*rstd                    (nb = 1 row)
+// use_batch_stats: 1 -> mean/var from sum/sumsq/count (and running stats updated if track), 0 -> running stats.
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, float count,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+                                   float eps, int use_batch_stats, int track, int mode, const float* __restrict__ gain,
+                                   const float* __restrict__ bias, int nb, int C, float* __restrict__ mean_out,
+                                   float* __restrict__ rstd_out, float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, var;
+  if (use_batch_stats) {
+    mean = sum[c] / count;
+    var = fmaxf(sumsq[c] / count - mean * mean, 0.f);
+    if (track && running_mean) {
+      const float unbiased = count > 1.f ? var * (count / (count - 1.f)) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const float rstd = rsqrtf(var + eps);
+  mean_out[c] = mean;
+  rstd_out[c] = rstd;
+  for (int b = 0; b < nb; ++b) {
+    float g = 1.f, be = 0.f;
+    if (mode == 0) { g = 1.f + gain[(size_t)b * C + c]; be = bias[(size_t)b * C + c]; }
+    else if (mode == 1) { g = gain[c]; be = bias[c]; }
+    const float sc = rstd * g;
+    scale[(size_t)b * C + c] = sc;
+    shift[(size_t)b * C + c] = be - mean * sc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- apply
+// One thread = 8 channels of one input pixel.  bstride = C for per-image scale/shift, 0 for per-channel.
+__global__ void __launch_bounds__(256) scale_shift_act_kernel(const bf16* __restrict__ x, int B, int H, int W, int C,
+                                                               long long x_cstride, const float* __restrict__ scale,
+                                                               const float* __restrict__ shift, int bstride, int relu,
+                                                               int up2, bf16* __restrict__ y, long long y_cstride) {
+  const int VG = C >> 3;
+  const long long total = (long long)B * H * W * VG;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int g = (int)(i % VG);
+    const long long p = i / VG;
+    const int b = (int)(p / ((long long)H * W));
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(x + p * x_cstride) + g);
+    float f[8];
+    unpack8(r, f);
+    const float4* sp = reinterpret_cast<const float4*>(scale + (size_t)b * bstride + g * 8);
+    const float4* hp = reinterpret_cast<const float4*>(shift + (size_t)b * bstride + g * 8);
+    const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), h0 = __ldg(hp), h1 = __ldg(hp + 1);
+    f[0] = fmaf(f[0], s0.x, h0.x); f[1] = fmaf(f[1], s0.y, h0.y); f[2] = fmaf(f[2], s0.z, h0.z); f[3] = fmaf(f[3], s0.w, h0.w);
+    f[4] = fmaf(f[4], s1.x, h1.x); f[5] = fmaf(f[5], s1.y, h1.y); f[6] = fmaf(f[6], s1.z, h1.z); f[7] = fmaf(f[7], s1.w, h1.w);
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    const uint4 o = pack8(f);
+    if (!up2) {
+      reinterpret_cast<uint4*>(y + p * y_cstride)[g] = o;
+    } else {
+      const int hw = (int)(p % ((long long)H * W));
+      const int h = hw / W, w = hw % W;
+      const long long q = ((long long)b * (2 * H) + 2 * h) * (2 * W) + 2 * w;
+      reinterpret_cast<uint4*>(y + q * y_cstride)[g] = o;
+      reinterpret_cast<uint4*>(y + (q + 1) * y_cstride)[g] = o;
+      reinterpret_cast<uint4*>(y + (q + 2 * W) * y_cstride)[g] = o;
+      reinterpret_cast<uint4*>(y + (q + 2 * W + 1) * y_cstride)[g] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- backward
+__device__ __forceinline__ void load_dz(const bf16* __restrict__ dy, long long dy_cstride, int b, int h, int w, int H, int W,
+                                        int g, int up2, long long p, float (&dz)[8]) {
+  if (!up2) {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + p * dy_cstride) + g), dz);
+  } else {
+    const long long q = ((long long)b * (2 * H) + 2 * h) * (2 * W) + 2 * w;
+    float t[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + q * dy_cstride) + g), dz);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (q + 1) * dy_cstride) + g), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dz[j] += t[j];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (q + 2 * W) * dy_cstride) + g), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dz[j] += t[j];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (q + 2 * W + 1) * dy_cstride) + g), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dz[j] += t[j];
+  }
+}
+
+// grid = (pixel chunks, B, channel chunks).  s1[b,c] += sum dz, s2[b,c] += sum dz*xhat; S1[c] += g1[b,c]*part etc.
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restrict__ dy, long long dy_cstride,
+                                                             const bf16* __restrict__ x, long long x_cstride, int H, int W, int C,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift,
+                                                             int bstride, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, int relu, int up2,
+                                                             float* __restrict__ s1, float* __restrict__ s2,
+                                                             float* __restrict__ S1, float* __restrict__ S2, int pix_per_block) {
+  __shared__ float a1[kChunkC];
+  __shared__ float a2[kChunkC];
+  const int b = blockIdx.y;
+  const int c_base = blockIdx.z * kChunkC;
+  const int cc = min(C - c_base, kChunkC);
+  const int VG = cc >> 3;
+  for (int i = threadIdx.x; i < cc; i += 256) { a1[i] = 0.f; a2[i] = 0.f; }
+  __syncthreads();
+  const int VGb = VG < 256 ? VG : 256;
+  const int nrows = 256 / VGb;
+  const int g = threadIdx.x % VGb, prow = threadIdx.x / VGb;
+  if (prow < nrows) {
+    float t1[8], t2[8], sc[8], sh[8], mu[8], rs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      t1[j] = 0.f; t2[j] = 0.f;
+      const int c = c_base + g * 8 + j;
+      sc[j] = scale[(size_t)b * bstride + c]; sh[j] = shift[(size_t)b * bstride + c];
+      mu[j] = mean[c]; rs[j] = rstd[c];
+    }
+    const int HW = H * W;
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, HW);
+    const int gg = (c_base >> 3) + g;
+    for (int hw = p0 + prow; hw < p1; hw += nrows) {
+      const long long p = (long long)b * HW + hw;
+      float xv[8], dz[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * x_cstride) + gg), xv);
+      load_dz(dy, dy_cstride, b, hw / W, hw % W, H, W, gg, up2, p, dz);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(xv[j], sc[j], sh[j]);
+        const float d = (relu && !(z > 0.f)) ? 0.f : dz[j];
+        t1[j] += d;
+        t2[j] = fmaf(d, (xv[j] - mu[j]) * rs[j], t2[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { atomicAdd(&a1[g * 8 + j], t1[j]); atomicAdd(&a2[g * 8 + j], t2[j]); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cc; i += 256) {
+    const int c = c_base + i;
+    const float v1 = a1[i], v2 = a2[i];
+    atomicAdd(s1 + (size_t)b * C + c, v1);
+    atomicAdd(s2 + (size_t)b * C + c, v2);
+    // d(xhat) = dz * g1 with g1 = scale / rstd (cBN: 1+gain, affine: weight, plain: 1)
+    const float g1 = scale[(size_t)b * bstride + c] / rstd[c];
+    atomicAdd(S1 + c, g1 * v1);
+    atomicAdd(S2 + c, g1 * v2);
+  }
+}
+
+// dx = scale[b,c]*dz - rstd*(S1/N) - rstd*(S2/N)*xhat   (train) ;   dx = scale[b,c]*dz   (eval: use_batch_stats = 0)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_cstride,
+                                                            const bf16* __restrict__ x, long long x_cstride, int B, int H, int W,
+                                                            int C, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                            int bstride, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, const float* __restrict__ S1,
+                                                            const float* __restrict__ S2, float inv_count, int relu, int up2,
+                                                            int use_batch_stats, bf16* __restrict__ dx, long long dx_cstride) {
+  const int VG = C >> 3;
+  const long long total = (long long)B * H * W * VG;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int g = (int)(i % VG);
+    const long long p = i / VG;
+    const int HW = H * W;
+    const int b = (int)(p / HW);
+    const int hw = (int)(p % HW);
+    float xv[8], dz[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * x_cstride) + g), xv);
+    load_dz(dy, dy_cstride, b, hw / W, hw % W, H, W, g, up2, p, dz);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      const float sc = __ldg(scale + (size_t)b * bstride + c), sh = __ldg(shift + (size_t)b * bstride + c);
+      const float z = fmaf(xv[j], sc, sh);
+      const float d = (relu && !(z > 0.f)) ? 0.f : dz[j];
+      float r = sc * d;
+      if (use_batch_stats) {
+        const float rs = __ldg(rstd + c);
+        const float xh = (xv[j] - __ldg(mean + c)) * rs;
+        r -= rs * inv_count * (__ldg(S1 + c) + xh * __ldg(S2 + c));
+      }
+      o[j] = r;
+    }
+    reinterpret_cast<uint4*>(dx + p * dx_cstride)[g] = pack8(o);
+  }
+}
+
+}  // namespace sgb
+
+using namespace sgb;
+
+static inline int ew_blocks(long long total_threads) {
+  long long b = (total_threads + 255) / 256;
+  const long long cap = 16LL * sm_count();
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+extern "C" int sgb_bn_stats(const void* x, int64_t npix, int32_t C, int64_t x_cstride, float* sum, float* sumsq,
+                            sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(x && sum && sumsq && npix > 0 && C > 0 && C % 8 == 0 && x_cstride % 8 == 0);
+  SGB_CUDA(cudaMemsetAsync(sum, 0, sizeof(float) * C, stream));
+  SGB_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * C, stream));
+  const int chunks = (C + kChunkC - 1) / kChunkC;
+  long long target_blocks = 8LL * sm_count() / chunks;
+  if (target_blocks < 1) target_blocks = 1;
+  long long ppb = (npix + target_blocks - 1) / target_blocks;
+  if (ppb < 64) ppb = 64;
+  dim3 grid((unsigned)((npix + ppb - 1) / ppb), chunks);
+  bn_stats_kernel<<<grid, 256, 0, stream>>>((const bf16*)x, npix, C, x_cstride, sum, sumsq, ppb);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_bn_finalize(const float* sum, const float* sumsq, float count, float* running_mean, float* running_var,
+                               float momentum, float eps, int32_t use_batch_stats, int32_t track, int32_t mode,
+                               const float* gain, const float* bias, int32_t nb, int32_t C, float* mean, float* rstd,
+                               float* scale, float* shift, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(C > 0 && nb > 0 && mean && rstd && scale && shift);
+  SGB_REQUIRE(use_batch_stats ? (sum && sumsq && count > 0.f) : (running_mean && running_var));
+  SGB_REQUIRE(mode == 2 || (gain && bias));
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sum, sumsq, count, running_mean, running_var, momentum, eps,
+                                                          use_batch_stats, track, mode, gain, bias, nb, C, mean, rstd, scale,
+                                                          shift);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_scale_shift_act(const void* x, int32_t B, int32_t H, int32_t W, int32_t C, int64_t x_cstride,
+                                   const float* scale, const float* shift, int32_t per_image, int32_t relu, int32_t up2,
+                                   void* y, int64_t y_cstride, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(x && y && scale && shift && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0);
+  SGB_REQUIRE(x_cstride % 8 == 0 && y_cstride % 8 == 0);
+  SGB_REQUIRE(((uintptr_t)scale & 15) == 0 && ((uintptr_t)shift & 15) == 0);
+  const long long total = (long long)B * H * W * (C / 8);
+  scale_shift_act_kernel<<<ew_blocks(total), 256, 0, stream>>>((const bf16*)x, B, H, W, C, x_cstride, scale, shift,
+                                                              per_image ? C : 0, relu, up2, (bf16*)y, y_cstride);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_bn_bwd_reduce(const void* dy, int64_t dy_cstride, const void* x, int64_t x_cstride, int32_t B, int32_t H,
+                                 int32_t W, int32_t C, const float* scale, const float* shift, int32_t per_image,
+                                 const float* mean, const float* rstd, int32_t relu, int32_t up2, float* s1, float* s2,
+                                 float* S1, float* S2, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(dy && x && scale && shift && mean && rstd && s1 && s2 && S1 && S2);
+  SGB_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && dy_cstride % 8 == 0 && x_cstride % 8 == 0);
+  SGB_CUDA(cudaMemsetAsync(s1, 0, sizeof(float) * (size_t)B * C, stream));
+  SGB_CUDA(cudaMemsetAsync(s2, 0, sizeof(float) * (size_t)B * C, stream));
+  SGB_CUDA(cudaMemsetAsync(S1, 0, sizeof(float) * C, stream));
+  SGB_CUDA(cudaMemsetAsync(S2, 0, sizeof(float) * C, stream));
+  const int chunks = (C + kChunkC - 1) / kChunkC;
+  const int HW = H * W;
+  long long target = 8LL * sm_count() / ((long long)B * chunks);
+  if (target < 1) target = 1;
+  int ppb = (int)((HW + target - 1) / target);
+  if (ppb < 32) ppb = 32;
+  dim3 grid((HW + ppb - 1) / ppb, B, chunks);
+  bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>((const bf16*)dy, dy_cstride, (const bf16*)x, x_cstride, H, W, C, scale, shift,
+                                                per_image ? C : 0, mean, rstd, relu, up2, s1, s2, S1, S2, ppb);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_bn_bwd_apply(const void* dy, int64_t dy_cstride, const void* x, int64_t x_cstride, int32_t B, int32_t H,
+                                int32_t W, int32_t C, const float* scale, const float* shift, int32_t per_image,
+                                const float* mean, const float* rstd, const float* S1, const float* S2, float count,
+                                int32_t relu, int32_t up2, int32_t use_batch_stats, void* dx, int64_t dx_cstride,
+                                sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(dy && x && dx && scale && shift && mean && rstd);
+  SGB_REQUIRE(!use_batch_stats || (S1 && S2 && count > 0.f));
+  SGB_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && dy_cstride % 8 == 0 && x_cstride % 8 == 0 && dx_cstride % 8 == 0);
+  const long long total = (long long)B * H * W * (C / 8);
+  bn_bwd_apply_kernel<<<ew_blocks(total), 256, 0, stream>>>((const bf16*)dy, dy_cstride, (const bf16*)x, x_cstride, B, H, W, C, scale,
+                                                           shift, per_image ? C : 0, mean, rstd, S1, S2,
+                                                           use_batch_stats ? 1.f / count : 0.f, relu, up2, use_batch_stats, (bf16*)dx,
+                                                           dx_cstride);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}

@@ -1,0 +1,226 @@
+// Spectral normalisation: one power iteration, sigma, and emission of the tensor-core weight packs.
+//
+// Reference arithmetic (torch/nn/utils/spectral_norm.py:62-114, used by src/utils/ops.py:195-224 with eps=1e-6,
+// n_power_iterations=1, dim=0):   v <- normalize(W^T u);  u <- normalize(W v);  sigma = u . (W v);  W_sn = W / sigma
+// where W is the weight viewed as [R = out_channels, K = in_channels*kh*kw] and normalize(x) = x / max(||x||_2, eps).
+// HBM-bound: two streaming passes over the fp32 weight for the iteration and one for the packs.
+#include "common.cuh"
+
+namespace sgb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) r = warp_sum(r);
+  if (threadIdx.x == 0) sh[0] = r;
+  __syncthreads();
+  r = sh[0];
+  return r;
+}
+
+// ws layout (floats): [0..K) t = W^T u accumulator, [K..K+R) s = W v, [K+R] ticket A, [K+R+1] ticket B
+// Pass 1: t += W^T u over a (rows_per_block x 256-column) tile; the last block normalises t into v and clears t.
+__global__ void __launch_bounds__(256) sn_wtu_kernel(const float* __restrict__ W, const float* __restrict__ u,
+                                                      float* __restrict__ v, float* __restrict__ ws, int R, int K,
+                                                      int rows_per_block, float eps) {
+  __shared__ float sh[32];
+  __shared__ bool last;
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, R);
+  if (c < K) {
+    float acc = 0.f;
+    const float* wp = W + (size_t)r0 * K + c;
+    for (int r = r0; r < r1; ++r, wp += K) acc = fmaf(__ldg(wp), __ldg(u + r), acc);
+    atomicAdd(ws + c, acc);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* ticket = reinterpret_cast<unsigned*>(ws + K + R);
+    const unsigned total = gridDim.x * gridDim.y;
+    last = (atomicAdd(ticket, 1u) == total - 1);
+    if (last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < K; i += 256) { const float t = __ldcg(ws + i); ss = fmaf(t, t, ss); }
+  ss = block_sum(ss, sh);
+  const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+  for (int i = threadIdx.x; i < K; i += 256) {
+    v[i] = __ldcg(ws + i) * inv;
+    ws[i] = 0.f;
+  }
+}
+
+// Pass 2: s = W v (one warp per row); the last block forms u = normalize(s), sigma = u . s.
+__global__ void __launch_bounds__(256) sn_wv_kernel(const float* __restrict__ W, float* __restrict__ u,
+                                                     const float* __restrict__ v, float* __restrict__ ws,
+                                                     float* __restrict__ sigma, int R, int K, float eps, int update_u) {
+  __shared__ float sh[32];
+  __shared__ bool last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s = ws + K;
+  for (int r = blockIdx.x * 8 + warp; r < R; r += gridDim.x * 8) {
+    const float* wp = W + (size_t)r * K;
+    float acc = 0.f;
+    for (int i = lane; i < K; i += 32) acc = fmaf(__ldg(wp + i), __ldg(v + i), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) s[r] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* ticket = reinterpret_cast<unsigned*>(ws + K + R + 1);
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    if (last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (update_u) {
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < R; i += 256) { const float t = __ldcg(s + i); ss = fmaf(t, t, ss); }
+    ss = block_sum(ss, sh);
+    const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+    for (int i = threadIdx.x; i < R; i += 256) u[i] = __ldcg(s + i) * inv;
+    if (threadIdx.x == 0) *sigma = ss * inv;  // u . s = ||s||^2 / max(||s||, eps)
+  } else {
+    float d = 0.f;
+    for (int i = threadIdx.x; i < R; i += 256) d = fmaf(__ldcg(s + i), u[i], d);
+    d = block_sum(d, sh);
+    if (threadIdx.x == 0) *sigma = d;
+  }
+}
+
+// Packs: W is the module's weight [R = Cout][Cin][taps] (taps = kh*kw, row-major OIHW).
+//   fprop pack  Wf[co][tap][ci]            = W[co][ci][tap] / sigma
+//   dgrad pack  Wd[ci][taps-1-tap][co]     = W[co][ci][tap] / sigma     (180-degree rotated, in/out swapped)
+// rows_perm > 1 re-orders output rows for linear0, whose output is viewed as [C, S] by the reference
+// (src/models/big_resnet_deep_legacy.py:167-168) but consumed here as NHWC [S, C]: packed row s*C + c <- row c*S + s.
+__global__ void __launch_bounds__(256) sn_pack_kernel(const float* __restrict__ W, const float* __restrict__ sigma,
+                                                       bf16* __restrict__ wf, bf16* __restrict__ wd, int Cout, int Cin,
+                                                       int taps, int perm_S) {
+  const size_t total = (size_t)Cout * Cin * taps;
+  const float inv = sigma ? 1.f / __ldg(sigma) : 1.f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int tap = (int)(i % taps);
+    const int ci = (int)((i / taps) % Cin);
+    int co = (int)(i / ((size_t)taps * Cin));
+    const float val = __ldg(W + i) * inv;
+    if (perm_S > 1) {
+      const int C = Cout / perm_S;
+      co = (co % perm_S) * C + co / perm_S;
+    }
+    const bf16 b = __float2bfloat16_rn(val);
+    if (wf) wf[((size_t)co * taps + tap) * Cin + ci] = b;
+    if (wd) wd[((size_t)ci * taps + (taps - 1 - tap)) * Cout + co] = b;
+  }
+}
+
+// Backward of W_sn = W / sigma with u, v held constant (they are detached buffers in the reference):
+//   dL/dW = (G - <G, W_sn> u v^T) / sigma,  G given in the fprop pack layout [co][tap][ci] (fp32, from wgrad).
+__global__ void __launch_bounds__(256) sn_bwd_dot_kernel(const float* __restrict__ G, const float* __restrict__ W,
+                                                          float* __restrict__ dot, int Cout, int Cin, int taps, int perm_S) {
+  __shared__ float sh[32];
+  const size_t total = (size_t)Cout * Cin * taps;
+  float acc = 0.f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int tap = (int)(i % taps);
+    const int ci = (int)((i / taps) % Cin);
+    int co = (int)(i / ((size_t)taps * Cin));
+    if (perm_S > 1) { const int C = Cout / perm_S; co = (co % perm_S) * C + co / perm_S; }
+    acc = fmaf(__ldg(G + ((size_t)co * taps + tap) * Cin + ci), __ldg(W + i), acc);
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(dot, acc);
+}
+
+__global__ void __launch_bounds__(256) sn_bwd_apply_kernel(const float* __restrict__ G, const float* __restrict__ u,
+                                                            const float* __restrict__ v, const float* __restrict__ sigma,
+                                                            const float* __restrict__ dot, float* __restrict__ dW, int Cout,
+                                                            int Cin, int taps, int perm_S, int accumulate) {
+  const size_t total = (size_t)Cout * Cin * taps;
+  float inv = 1.f, coef = 0.f;
+  if (sigma) {
+    inv = 1.f / __ldg(sigma);
+    coef = __ldg(dot) * inv;  // <G, W> / sigma = <G, W_sn>
+  }
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int tap = (int)(i % taps);
+    const int ci = (int)((i / taps) % Cin);
+    const int co_orig = (int)(i / ((size_t)taps * Cin));
+    int co = co_orig;
+    if (perm_S > 1) { const int C = Cout / perm_S; co = (co % perm_S) * C + co / perm_S; }
+    float g = __ldg(G + ((size_t)co * taps + tap) * Cin + ci);
+    if (sigma) g = (g - coef * __ldg(u + co_orig) * __ldg(v + (size_t)ci * taps + tap)) * inv;
+    dW[i] = accumulate ? dW[i] + g : g;
+  }
+}
+
+}  // namespace sgb
+
+using namespace sgb;
+
+extern "C" int64_t sgb_sn_workspace_floats(int32_t R, int32_t K) { return (int64_t)R + K + 4; }
+
+extern "C" int sgb_sn_power_iter(const float* W, float* u, float* v, float* sigma, float* ws, int32_t R, int32_t K,
+                                 float eps, int32_t do_power_iteration, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(W && u && v && sigma && ws && R > 0 && K > 0);
+  if (do_power_iteration) {
+    int rows_per_block = 64;
+    dim3 grid((K + 255) / 256, (R + rows_per_block - 1) / rows_per_block);
+    sn_wtu_kernel<<<grid, 256, 0, stream>>>(W, u, v, ws, R, K, rows_per_block, eps);
+    SGB_LAUNCH_CHECK();
+  }
+  int blocks = (R + 7) / 8;
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  sn_wv_kernel<<<blocks, 256, 0, stream>>>(W, u, v, ws, sigma, R, K, eps, do_power_iteration);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_weight_pack(const float* W, const float* sigma, void* w_fprop, void* w_dgrad, int32_t Cout, int32_t Cin,
+                               int32_t taps, int32_t perm_S, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(W && (w_fprop || w_dgrad) && Cout > 0 && Cin > 0 && taps > 0);
+  SGB_REQUIRE(perm_S <= 1 || Cout % perm_S == 0);
+  const size_t total = (size_t)Cout * Cin * taps;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+  sn_pack_kernel<<<blocks, 256, 0, stream>>>(W, sigma, (bf16*)w_fprop, (bf16*)w_dgrad, Cout, Cin, taps, perm_S);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_sn_backward(const float* G, const float* W, const float* u, const float* v, const float* sigma,
+                               float* scratch_dot, float* dW, int32_t Cout, int32_t Cin, int32_t taps, int32_t perm_S,
+                               int32_t accumulate, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(G && dW && Cout > 0 && Cin > 0 && taps > 0);
+  SGB_REQUIRE(!sigma || (W && u && v && scratch_dot));
+  const size_t total = (size_t)Cout * Cin * taps;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  if (sigma) {
+    SGB_CUDA(cudaMemsetAsync(scratch_dot, 0, sizeof(float), stream));
+    sn_bwd_dot_kernel<<<blocks, 256, 0, stream>>>(G, W, scratch_dot, Cout, Cin, taps, perm_S);
+    SGB_LAUNCH_CHECK();
+  }
+  sn_bwd_apply_kernel<<<blocks, 256, 0, stream>>>(G, u, v, sigma, scratch_dot, dW, Cout, Cin, taps, perm_S, accumulate);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}

@@ -1,0 +1,567 @@
+// Implicit-GEMM convolution / linear / dgrad / wgrad on Blackwell tensor cores.
+//
+//   fprop : D[pixel, co]   = sum_{tap, ci}  X[pixel + tap, ci] * Wp[co, tap, ci]
+//           A = X  tile, TMA 4-D box (64 ch, tw, th, nb) over NHWC   -> smem [128 px][64 ch], K-major, SWIZZLE_128B
+//           B = Wp tile, TMA 3-D box (64 ci, 1 tap, BN co)           -> smem [BN co][64 ci],  K-major, SWIZZLE_128B
+//           padding = TMA out-of-bounds zero fill (negative / overflowing box coordinates).
+//   wgrad : D[co, ci]      = sum_{pixel}    dY[pixel, co] * X[pixel + tap, ci]           (one tap per work item)
+//           A = dY tile(s), B = X tile(s): same boxes, consumed as MN-major operands (the pixel axis is K).
+//
+// One persistent CTA per SM, 6 warps: warp 0 = TMA producer (one lane), warp 1 = tcgen05.mma issuer (one lane) and
+// TMEM owner, warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global).  Two TMEM accumulator stages so
+// the epilogue of tile i overlaps the main loop of tile i+1.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sgb {
+
+static constexpr int kThreads = 192;
+static constexpr int kTileM = 128;          // pixels (fprop) or output channels (wgrad) per tile = TMEM lanes
+static constexpr int kBlockK = 64;          // bf16 elements per 128-byte swizzle row
+static constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB
+
+struct FpropArgs {
+  int B, H, W, Cin, Cout, taps, KW, pad_h, pad_w;
+  int tw, th, nb;                 // tile box: tw*th*nb == 128
+  int tiles_w, tiles_h, tiles_b, tiles_n, num_tiles;
+  int kblocks;                    // ceil(Cin / 64)
+  int BN;                         // output-channel tile (multiple of 16, <= 256)
+  int stages;
+  uint32_t tmem_cols;
+  float alpha;
+  const float* bias;
+  const bf16* residual; long long res_cstride; int res_up2;
+  const bf16* mask; long long mask_cstride;
+  int relu;
+  void* y; long long y_cstride; int y_fp32;
+};
+
+__device__ __forceinline__ float bf16_bits_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_bits_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)p.BN * kBlockK * 2;
+  const uint32_t stage_bytes = kABytes + b_bytes;  // multiple of 1024 because BN % 8 == 0 -> b_bytes % 1024 == 0
+  const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
+  const uint32_t holder = bar_base + 8u * (2 * p.stages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(holder, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(holder));
+
+  const int kiters = p.taps * p.kblocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------- TMA producer
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int nt = t % p.tiles_n; t /= p.tiles_n;
+        const int wt = t % p.tiles_w; t /= p.tiles_w;
+        const int ht = t % p.tiles_h; t /= p.tiles_h;
+        const int bt = t;
+        const int n0 = nt * p.BN, w0 = wt * p.tw, h0 = ht * p.th, b0 = bt * p.nb;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dh = tap / p.KW - p.pad_h, dw = tap % p.KW - p.pad_w;
+          for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            mbar_wait(empty_bar(s), ph ^ 1);
+            mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+            const uint32_t sa = smem_base + s * stage_bytes;
+            tma_load_4d(sa, &tmA, full_bar(s), kb * kBlockK, w0 + dw, h0 + dh, b0);
+            tma_load_3d(sa + kABytes, &tmB, full_bar(s), kb * kBlockK, tap, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------- MMA issuer
+      const uint32_t idesc = make_idesc_bf16(kTileM, p.BN, 0, 0);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(tempty_bar(a), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * p.BN;
+        for (int k = 0; k < kiters; ++k, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * stage_bytes;
+          const uint64_t adesc = make_sdesc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = make_sdesc_sw128(sa + kABytes, 16, 1024);
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / 16; ++kk) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+            umma_f16_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));  // smem slot reusable once these MMAs retire
+        }
+        umma_commit(tfull_bar(a));    // accumulator complete
+      }
+    }
+  } else {
+    // --------------------------------------------------------------- epilogue warps (TMEM lane quadrant = warp % 4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int wi = row % p.tw, hi = (row / p.tw) % p.th, bi = row / (p.tw * p.th);
+    const bool vec_ok = (p.Cout % 8 == 0) && (p.y_cstride % 8 == 0) &&
+                        (p.residual == nullptr || p.res_cstride % 8 == 0) && (p.mask == nullptr || p.mask_cstride % 8 == 0);
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+      int t = tile;
+      const int nt = t % p.tiles_n; t /= p.tiles_n;
+      const int wt = t % p.tiles_w; t /= p.tiles_w;
+      const int ht = t % p.tiles_h; t /= p.tiles_h;
+      const int bt = t;
+      const int n0 = nt * p.BN;
+      const int w = wt * p.tw + wi, h = ht * p.th + hi, b = bt * p.nb + bi;
+      const bool valid = (w < p.W) && (h < p.H) && (b < p.B);
+      const long long pix = ((long long)b * p.H + h) * p.W + w;
+      const long long rpix = p.res_up2 ? (((long long)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) : pix;
+
+      const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+      mbar_wait(tfull_bar(a), aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + a * p.BN;
+
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(t_row + c0, v);
+        tmem_ld_wait();
+        const int n = n0 + c0;
+        if (!valid || n >= p.Cout) continue;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        if (vec_ok && n + 16 <= p.Cout) {
+          if (p.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 bb = __ldg(bp + j);
+              f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+            }
+          }
+          if (p.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.res_cstride + n);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint4 r = __ldg(rp + j);
+              f[8 * j + 0] += bf16_bits_lo(r.x); f[8 * j + 1] += bf16_bits_hi(r.x);
+              f[8 * j + 2] += bf16_bits_lo(r.y); f[8 * j + 3] += bf16_bits_hi(r.y);
+              f[8 * j + 4] += bf16_bits_lo(r.z); f[8 * j + 5] += bf16_bits_hi(r.z);
+              f[8 * j + 6] += bf16_bits_lo(r.w); f[8 * j + 7] += bf16_bits_hi(r.w);
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.mask) {
+            const uint4* mp = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_cstride + n);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint4 m = __ldg(mp + j);
+              f[8 * j + 0] = bf16_bits_lo(m.x) > 0.f ? f[8 * j + 0] : 0.f;
+              f[8 * j + 1] = bf16_bits_hi(m.x) > 0.f ? f[8 * j + 1] : 0.f;
+              f[8 * j + 2] = bf16_bits_lo(m.y) > 0.f ? f[8 * j + 2] : 0.f;
+              f[8 * j + 3] = bf16_bits_hi(m.y) > 0.f ? f[8 * j + 3] : 0.f;
+              f[8 * j + 4] = bf16_bits_lo(m.z) > 0.f ? f[8 * j + 4] : 0.f;
+              f[8 * j + 5] = bf16_bits_hi(m.z) > 0.f ? f[8 * j + 5] : 0.f;
+              f[8 * j + 6] = bf16_bits_lo(m.w) > 0.f ? f[8 * j + 6] : 0.f;
+              f[8 * j + 7] = bf16_bits_hi(m.w) > 0.f ? f[8 * j + 7] : 0.f;
+            }
+          }
+          if (p.y_fp32) {
+            float4* yp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + pix * p.y_cstride + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) yp[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.y) + pix * p.y_cstride + n);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+              o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              yp[j] = o;
+            }
+          }
+        } else {
+          // ragged / unaligned channel tail (e.g. Cout = 3): scalar path
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int nn = n + j;
+            if (nn < p.Cout) {
+              float x = f[j];
+              if (p.bias) x += __ldg(p.bias + nn);
+              if (p.residual) x += __bfloat162float(p.residual[rpix * p.res_cstride + nn]);
+              if (p.relu) x = fmaxf(x, 0.f);
+              if (p.mask) x = __bfloat162float(p.mask[pix * p.mask_cstride + nn]) > 0.f ? x : 0.f;
+              if (p.y_fp32) reinterpret_cast<float*>(p.y)[pix * p.y_cstride + nn] = x;
+              else reinterpret_cast<bf16*>(p.y)[pix * p.y_cstride + nn] = __float2bfloat16_rn(x);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(a));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+struct WgradArgs {
+  int B, H, W, Cin, Cout, taps, KW, pad_h, pad_w;
+  int tw, th, nb;
+  int tiles_w, tiles_h, tiles_b, pix_tiles;  // pix_tiles = tiles_w*tiles_h*tiles_b
+  int tiles_m, tiles_n;                      // over Cout (128) and Cin (BN)
+  int BN;                                    // 64 or 128 (input-channel tile)
+  int splits, tiles_per_split;
+  int num_items;                             // tiles_m*tiles_n*taps*splits
+  int stages;
+  uint32_t tmem_cols;
+  float* dw;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgradArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = 2 * kABytes;                       // two 64-channel boxes -> M = 128
+  const uint32_t b_bytes = (uint32_t)(p.BN / 64) * kABytes;   // BN/64 boxes
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
+  const uint32_t holder = bar_base + 8u * (2 * p.stages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(holder, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(holder));
+
+  // work item -> (m tile, n tile, tap, split); n fastest so neighbouring CTAs share the dY tiles in L2
+  auto decode = [&](int item, int& mt, int& nt, int& tap, int& pt_begin, int& pt_end) {
+    int t = item;
+    nt = t % p.tiles_n; t /= p.tiles_n;
+    tap = t % p.taps; t /= p.taps;
+    mt = t % p.tiles_m; t /= p.tiles_m;
+    const int sp = t;
+    pt_begin = sp * p.tiles_per_split;
+    pt_end = min(pt_begin + p.tiles_per_split, p.pix_tiles);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        int mt, nt, tap, pb, pe;
+        decode(item, mt, nt, tap, pb, pe);
+        const int dh = tap / p.KW - p.pad_h, dw = tap % p.KW - p.pad_w;
+        for (int pt = pb; pt < pe; ++pt, ++it) {
+          int t = pt;
+          const int wt = t % p.tiles_w; t /= p.tiles_w;
+          const int ht = t % p.tiles_h; t /= p.tiles_h;
+          const int bt = t;
+          const int w0 = wt * p.tw, h0 = ht * p.th, b0 = bt * p.nb;
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+          const uint32_t sa = smem_base + s * stage_bytes;
+          tma_load_4d(sa, &tmDY, full_bar(s), mt * 128, w0, h0, b0);
+          tma_load_4d(sa + kABytes, &tmDY, full_bar(s), mt * 128 + 64, w0, h0, b0);
+          for (int j = 0; j < p.BN / 64; ++j)
+            tma_load_4d(sa + a_bytes + j * kABytes, &tmX, full_bar(s), nt * p.BN + j * 64, w0 + dw, h0 + dh, b0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kTileM, p.BN, 1, 1);  // both operands MN-major
+      uint32_t it = 0, tcount = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++tcount) {
+        int mt, nt, tap, pb, pe;
+        decode(item, mt, nt, tap, pb, pe);
+        const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(tempty_bar(a), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * p.BN;
+        for (int pt = pb; pt < pe; ++pt, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * stage_bytes;
+          // MN-major: 64-wide MN atoms are kABytes apart (LBO), 8-row K groups are 1024 B apart (SBO)
+          const uint64_t adesc = make_sdesc_sw128(sa, kABytes, 1024);
+          const uint64_t bdesc = make_sdesc_sw128(sa + a_bytes, kABytes, 1024);
+#pragma unroll
+          for (int kk = 0; kk < kTileM / 16; ++kk) {
+            // 16 pixels (K) = two 8-row groups = 2048 bytes -> +128 in the (addr >> 4) field
+            umma_f16_ss(d_tmem, adesc + 128 * kk, bdesc + 128 * kk, idesc, (pt > pb || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(a));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t tcount = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++tcount) {
+      int mt, nt, tap, pb, pe;
+      decode(item, mt, nt, tap, pb, pe);
+      const int co = mt * 128 + row;
+      const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+      mbar_wait(tfull_bar(a), aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + a * p.BN;
+      float* dst = p.dw + ((long long)co * p.taps + tap) * p.Cin;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(t_row + c0, v);
+        tmem_ld_wait();
+        if (pe <= pb || co >= p.Cout) continue;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int ci = nt * p.BN + c0 + j;
+          if (ci < p.Cin) atomicAdd(dst + ci, __uint_as_float(v[j]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(a));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static inline uint32_t pow2_cols(int need) {
+  uint32_t c = 32;
+  while ((int)c < need) c <<= 1;
+  return c;
+}
+
+// Tile box over (W, H, B) with tw*th*nb == 128. Power-of-two splits; edges are masked / zero-filled.
+static void pick_tile(int H, int W, int B, int& tw, int& th, int& nb) {
+  tw = 1;
+  while (tw < W && tw < 128) tw <<= 1;   // smallest power of two >= W, capped at 128
+  if (tw > 16 && (W % tw) != 0) {        // ragged widths (Inception): prefer narrower tiles to limit waste
+    while (tw > 16 && (W % tw) != 0) tw >>= 1;
+  }
+  th = 1;
+  while (th < H && tw * th < 128) th <<= 1;
+  nb = 128 / (tw * th);
+  (void)B;
+}
+
+static int make_act_tmap(CUtensorMap* m, const void* base, int B, int H, int W, int C, long long cstride, int tw, int th,
+                         int nb) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)cstride * 2, (uint64_t)cstride * 2 * W, (uint64_t)cstride * 2 * W * H};
+  uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, (uint32_t)nb};
+  return make_tmap_bf16(m, base, 4, dims, strides, box);
+}
+
+}  // namespace sgb
+
+using namespace sgb;
+
+extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(d && d->x && d->w && d->y);
+  SGB_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0 && d->KH > 0 && d->KW > 0);
+  SGB_REQUIRE(d->Cin % 8 == 0 && d->x_cstride % 8 == 0 && d->x_cstride >= d->Cin);
+  SGB_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->w & 15) == 0 && ((uintptr_t)d->y & 15) == 0);
+  SGB_REQUIRE(!d->res_up2 || (d->H % 2 == 0 && d->W % 2 == 0));
+  SGB_REQUIRE(((uintptr_t)d->bias & 15) == 0 && ((uintptr_t)d->residual & 15) == 0 && ((uintptr_t)d->mask & 15) == 0);
+
+  FpropArgs p;
+  p.B = d->B; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
+  p.taps = d->KH * d->KW; p.KW = d->KW; p.pad_h = d->pad_h; p.pad_w = d->pad_w;
+  pick_tile(d->H, d->W, d->B, p.tw, p.th, p.nb);
+  p.tiles_w = (d->W + p.tw - 1) / p.tw;
+  p.tiles_h = (d->H + p.th - 1) / p.th;
+  p.tiles_b = (d->B + p.nb - 1) / p.nb;
+  int BN;
+  if (d->Cout <= 16) BN = 16;
+  else if (d->Cout <= 32) BN = 32;
+  else if (d->Cout <= 64) BN = 64;
+  else if (d->Cout <= 128 || d->Cout % 256 != 0) BN = 128;
+  else BN = 256;
+  // keep enough tiles in flight: prefer 128-wide N tiles when the grid would otherwise underfill the SMs
+  {
+    long long tiles256 = (long long)p.tiles_w * p.tiles_h * p.tiles_b * ((d->Cout + 255) / 256);
+    if (BN == 256 && tiles256 < 2LL * sm_count()) BN = 128;
+  }
+  p.BN = BN;
+  p.tiles_n = (d->Cout + BN - 1) / BN;
+  p.num_tiles = p.tiles_n * p.tiles_w * p.tiles_h * p.tiles_b;
+  p.kblocks = (d->Cin + kBlockK - 1) / kBlockK;
+  const uint32_t stage_bytes = kABytes + BN * kBlockK * 2;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  p.tmem_cols = pow2_cols(2 * BN);
+  p.alpha = d->alpha;
+  p.bias = d->bias;
+  p.residual = (const bf16*)d->residual; p.res_cstride = d->res_cstride; p.res_up2 = d->res_up2;
+  p.mask = (const bf16*)d->mask; p.mask_cstride = d->mask_cstride;
+  p.relu = d->relu;
+  p.y = d->y; p.y_cstride = d->y_cstride; p.y_fp32 = d->y_fp32;
+
+  CUtensorMap tmA, tmB;
+  int rc = make_act_tmap(&tmA, d->x, d->B, d->H, d->W, d->Cin, d->x_cstride, p.tw, p.th, p.nb);
+  if (rc) return rc;
+  {
+    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)p.taps, (uint64_t)d->Cout};
+    uint64_t strides[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cin * 2 * p.taps};
+    uint32_t box[3] = {64, 1, (uint32_t)BN};
+    rc = make_tmap_bf16(&tmB, d->w, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 4) + 16;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    SGB_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    smem_set = 227 * 1024;
+  }
+  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  conv_fprop_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(d && d->x && d->dy && d->dw);
+  SGB_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0 && d->KH > 0 && d->KW > 0);
+  SGB_REQUIRE(d->Cin % 8 == 0 && d->x_cstride % 8 == 0 && d->Cout % 8 == 0 && d->dy_cstride % 8 == 0);
+  SGB_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->dy & 15) == 0);
+
+  WgradArgs p;
+  p.B = d->B; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
+  p.taps = d->KH * d->KW; p.KW = d->KW; p.pad_h = d->pad_h; p.pad_w = d->pad_w;
+  pick_tile(d->H, d->W, d->B, p.tw, p.th, p.nb);
+  p.tiles_w = (d->W + p.tw - 1) / p.tw;
+  p.tiles_h = (d->H + p.th - 1) / p.th;
+  p.tiles_b = (d->B + p.nb - 1) / p.nb;
+  p.pix_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+  p.BN = (d->Cin <= 64) ? 64 : 128;
+  p.tiles_m = (d->Cout + 127) / 128;
+  p.tiles_n = (d->Cin + p.BN - 1) / p.BN;
+  const int base_items = p.tiles_m * p.tiles_n * p.taps;
+  int splits = (2 * sm_count() + base_items - 1) / base_items;
+  if (splits > p.pix_tiles) splits = p.pix_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = (p.pix_tiles + splits - 1) / splits;
+  p.splits = (p.pix_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.num_items = base_items * p.splits;
+  const uint32_t stage_bytes = 2 * kABytes + (p.BN / 64) * kABytes;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 6) stages = 6;
+  p.stages = stages;
+  p.tmem_cols = pow2_cols(2 * p.BN);
+  p.dw = d->dw;
+
+  if (!d->accumulate)
+    SGB_CUDA(cudaMemsetAsync(d->dw, 0, sizeof(float) * (size_t)d->Cout * p.taps * d->Cin, stream));
+
+  CUtensorMap tmDY, tmX;
+  int rc = make_act_tmap(&tmDY, d->dy, d->B, d->H, d->W, d->Cout, d->dy_cstride, p.tw, p.th, p.nb);
+  if (rc) return rc;
+  rc = make_act_tmap(&tmX, d->x, d->B, d->H, d->W, d->Cin, d->x_cstride, p.tw, p.th, p.nb);
+  if (rc) return rc;
+
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 4) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SGB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int grid = p.num_items < sm_count() ? p.num_items : sm_count();
+  conv_wgrad_kernel<<<grid, kThreads, smem, stream>>>(tmDY, tmX, p);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
