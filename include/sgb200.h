@@ -46,12 +46,16 @@ typedef struct sgb_conv_desc {
   int32_t KH, KW, pad_h, pad_w;
   const void* x;       /* bf16 NHWC input */
   int64_t x_cstride;   /* elements between consecutive pixels (>= Cin, multiple of 8) */
-  const void* w;       /* bf16 packed weights [Cout][KH*KW][Cin] */
+  const void* w;       /* bf16 packed weights [Cout][KH*KW][Cin] (w_mode 0) */
+  int32_t w_mode;      /* 0: shared weights; 1: per-image B operand [B][Cout][Cin]; 2: per-image, Cout-contiguous
+                          [B][Cin][Cout] (MN-major).  Modes 1/2 (batched GEMM for attention) need KH=KW=1, H*W >= 128 */
   float alpha;         /* accumulator scale */
+  const float* alpha_ptr; /* optional device scalar multiplied into alpha */
   const float* bias;   /* fp32 [Cout] or NULL */
   const void* residual;/* bf16 NHWC or NULL; added after bias */
   int64_t res_cstride;
   int32_t res_up2;     /* 1: residual is at half resolution, read at (h/2, w/2) (nearest x2 upsample) */
+  int32_t res_after_mask; /* 0: residual added before relu/mask; 1: added last (skip-branch gradient in dgrad) */
   const void* mask;    /* bf16 NHWC or NULL; output is zeroed where mask <= 0 (ReLU backward) */
   int64_t mask_cstride;
   int32_t relu;        /* 1: ReLU applied last (before mask) */
@@ -73,11 +77,101 @@ typedef struct sgb_wgrad_desc {
   int64_t x_cstride;
   const void* dy;
   int64_t dy_cstride;
-  float* dw;          /* fp32 [Cout][KH*KW][Cin] */
+  float* dw;          /* fp32 [Cout][KH*KW][Cin]  (per_image: [B][Cout][KH*KW][Cin]) */
   int32_t accumulate; /* 0: dw is zeroed first */
+  int32_t per_image;  /* 1: one gradient per image (attention dK/dV); needs H*W >= 128 */
 } sgb_wgrad_desc;
 
 int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Spectral normalisation (power iteration + sigma) and tensor-core weight packs.
+ * Replaces: torch.nn.utils.spectral_norm forward-pre-hook (torch/nn/utils/spectral_norm.py:62-114)
+ *   installed by src/utils/ops.py:195-224 (eps = 1e-6, one iteration, dim = 0).
+ * W is the module weight viewed as [R = out_channels][K = in_channels*kh*kw], fp32.
+ * ws: caller-owned fp32 workspace of sgb_sn_workspace_floats(R, K) floats, ZERO-initialised once.
+ * ------------------------------------------------------------------------------------------ */
+int64_t sgb_sn_workspace_floats(int32_t R, int32_t K);
+/* do_power_iteration=1: v <- normalize(W^T u), u <- normalize(W v) in place; always: *sigma = u.(W v). */
+int sgb_sn_power_iter(const float* W, float* u, float* v, float* sigma, float* ws, int32_t R, int32_t K, float eps,
+                      int32_t do_power_iteration, sgb_stream_t stream);
+/* Packs W[Cout][Cin][taps] / sigma (sigma may be NULL = 1) into bf16:
+ *   w_fprop[Cout][taps][Cin] and/or w_dgrad[Cin][taps (rotated 180 deg)][Cout].
+ * perm_S > 1: output rows re-ordered (row c*S+s -> s*C+c) so that linear0's result is NHWC
+ *   (src/models/big_resnet_deep_legacy.py:167-168 views it as [C, 4, 4]). */
+/* Cout_p / Cin_p >= Cout / Cin are the (zero-padded, caller-zeroed) pack extents, e.g. 3 -> 8 for image convs. */
+int sgb_weight_pack(const float* W, const float* sigma, void* w_fprop, void* w_dgrad, int32_t Cout, int32_t Cin,
+                    int32_t taps, int32_t perm_S, int32_t Cout_p, int32_t Cin_p, sgb_stream_t stream);
+/* dW[Cout][Cin][taps] (=|+=) (G - <G, W/sigma> u v^T) / sigma with G in the fprop-pack layout (fp32, from
+ * sgb_conv_wgrad).  sigma NULL: plain re-layout of G (layers without spectral norm). */
+int sgb_sn_backward(const float* G, const float* W, const float* u, const float* v, const float* sigma,
+                    float* scratch_dot, float* dW, int32_t Cout, int32_t Cin, int32_t taps, int32_t perm_S,
+                    int32_t Cin_p, int32_t accumulate, sgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batch-norm family (NHWC bf16 activations, fp32 statistics).
+ * Replaces: ops.ConditionalBatchNorm2d.forward (src/utils/ops.py:24-28), ops.batchnorm_2d (:227-228),
+ *   F.batch_norm fwd/bwd; the [sum, sumsq, count] / [S1, S2] vectors are the cross-rank reduction points of
+ *   torch.nn.SyncBatchNorm (torch/nn/modules/_functions.py:7-212) and src/sync_batchnorm/batchnorm.py:94-175.
+ * ------------------------------------------------------------------------------------------ */
+int sgb_bn_stats(const void* x, int64_t npix, int32_t C, int64_t x_cstride, float* sum, float* sumsq, sgb_stream_t stream);
+/* mode 0: cBN (gain/bias [nb=B][C], scale = rstd*(1+gain)); 1: affine (gain=weight[C], bias[C], nb=1); 2: plain (nb=1). */
+int sgb_bn_finalize(const float* sum, const float* sumsq, float count, float* running_mean, float* running_var,
+                    float momentum, float eps, int32_t use_batch_stats, int32_t track, int32_t mode, const float* gain,
+                    const float* bias, int32_t nb, int32_t C, float* mean, float* rstd, float* scale, float* shift,
+                    sgb_stream_t stream);
+/* y = [relu](x*scale + shift); per_image: scale/shift are [B][C] else [C]; up2: y is the nearest x2 upsample. */
+int sgb_scale_shift_act(const void* x, int32_t B, int32_t H, int32_t W, int32_t C, int64_t x_cstride, const float* scale,
+                        const float* shift, int32_t per_image, int32_t relu, int32_t up2, void* y, int64_t y_cstride,
+                        sgb_stream_t stream);
+/* s1[b,c] = sum dz, s2[b,c] = sum dz*xhat, S1[c] = sum_b g1*s1, S2[c] = sum_b g1*s2 (g1 = scale/rstd). */
+int sgb_bn_bwd_reduce(const void* dy, int64_t dy_cstride, const void* x, int64_t x_cstride, int32_t B, int32_t H, int32_t W,
+                      int32_t C, const float* scale, const float* shift, int32_t per_image, const float* mean,
+                      const float* rstd, int32_t relu, int32_t up2, float* s1, float* s2, float* S1, float* S2,
+                      sgb_stream_t stream);
+int sgb_bn_bwd_apply(const void* dy, int64_t dy_cstride, const void* x, int64_t x_cstride, int32_t B, int32_t H, int32_t W,
+                     int32_t C, const float* scale, const float* shift, int32_t per_image, const float* mean,
+                     const float* rstd, const float* S1, const float* S2, float count, int32_t relu, int32_t up2,
+                     int32_t use_batch_stats, void* dx, int64_t dx_cstride, sgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Element-wise / small reductions (NHWC bf16 unless noted).  Reference call sites: ReLU, AvgPool2d(2),
+ * F.interpolate(nearest), residual adds in src/models/big_resnet_deep_legacy.py:49-73,210-229,334-345;
+ * MaxPool2d / Softmax / sigma*attn_g in src/utils/ops.py:79-103; nn.Tanh at big_resnet_deep_legacy.py:183.
+ * ------------------------------------------------------------------------------------------ */
+/* out = act(a*[*a_dev]*x + b*y), then masked by (mask > 0) if mask; act 0 none / 1 relu. */
+int sgb_axpby(const void* x, int64_t xs, const void* y, int64_t ys, const void* mask, int64_t ms, void* out, int64_t os,
+              int64_t npix, int32_t C, float a, const float* a_dev, float b, int32_t act, sgb_stream_t stream);
+/* 2x2 pooling to [B,Ho,Wo,C]; mode 0 average, 1 max. */
+int sgb_pool2_fwd(const void* x, int64_t xs, void* y, int64_t ys, int32_t B, int32_t Ho, int32_t Wo, int32_t C, int32_t mode,
+                  sgb_stream_t stream);
+/* dx = pool2 backward of dy (+ add) (masked by relu_src > 0); x needed for max (first max in scan order wins). */
+int sgb_pool2_bwd(const void* dy, int64_t dys, const void* x, int64_t xs, const void* add, int64_t adds, const void* relu_src,
+                  int64_t rs, void* dx, int64_t dxs, int32_t B, int32_t Ho, int32_t Wo, int32_t C, int32_t mode,
+                  sgb_stream_t stream);
+int sgb_softmax_rows(const void* s, void* p, int64_t rows, int32_t n, sgb_stream_t stream);
+int sgb_softmax_bwd_rows(const void* p, const void* dp, void* ds, int64_t rows, int32_t n, sgb_stream_t stream);
+int sgb_dot(const void* x, const void* y, int64_t n, float* out, sgb_stream_t stream);
+/* h[b,c] = sum_hw act(x) (fp32): discriminator head sum-pool (big_resnet_deep_legacy.py:344-345). */
+int sgb_sum_hw(const void* x, int64_t xs, int32_t B, int32_t HW, int32_t C, int32_t relu, float* h, sgb_stream_t stream);
+int sgb_sum_hw_bwd(const float* dh, const void* x, int64_t xs, void* dx, int64_t dxs, int32_t B, int32_t HW, int32_t C,
+                   int32_t relu, sgb_stream_t stream);
+/* image layout converters: NCHW fp32 <-> NHWC bf16 (channels zero-padded to Cp); act 1 = tanh. */
+int sgb_img_to_nhwc(const float* img, void* out, int32_t B, int32_t C, int32_t HW, int32_t Cp, sgb_stream_t stream);
+int sgb_nhwc_to_img(const void* in, int32_t in_fp32, int64_t cs, float* img, int32_t B, int32_t C, int32_t HW, int32_t act,
+                    sgb_stream_t stream);
+int sgb_img_grad_to_nhwc(const float* dimg, const float* y, void* out, int32_t B, int32_t C, int32_t HW, int32_t Cp,
+                         sgb_stream_t stream);
+int sgb_cast_f32_to_bf16(const float* in, void* out, int64_t n, float scale, sgb_stream_t stream);
+int sgb_cast_bf16_to_f32(const void* in, float* out, int64_t n, sgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser: fused Adam (torch.optim.Adam, eps 1e-6 at src/config.py:541-563) + EMA lerp
+ * (src/utils/ema.py:27-40) over a flat fp32 parameter arena.  ema may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+int sgb_adam_ema_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                      int32_t step, float* ema, float ema_decay, float grad_scale, sgb_stream_t stream);
+int sgb_ema_lerp(float* ema, const float* p, int64_t n, float decay, sgb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,331 @@
+"""ORACLE — test infrastructure only.  Nothing under sgb200/ (the product) may import this file.
+
+A CPU restatement, in plain PyTorch fp32/fp64 tensor algebra and numpy, of the arithmetic on StudioGAN's BigGAN /
+BigGAN-Deep hot path.  It is *state-dict driven*: every function takes the flat ``{key: tensor}`` dictionary that the
+reference modules (and the sgb200 modules, which keep the same keys) produce, so the same oracle checks both sides.
+Each function cites the reference lines it restates (paths relative to the reference checkout; ``torch/`` = PyTorch).
+
+Pinning: tests/golden/make_golden.py imports the real reference in the build container, runs it on seeded inputs and
+stores inputs/outputs in tests/golden/*.npz; tests/test_oracle_golden.py (CPU) checks this file against those vectors.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+SN_EPS = 1e-6
+BN_EPS = 1e-4
+BN_MOMENTUM = 0.1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# spectral norm  (torch/nn/utils/spectral_norm.py:62-114; installed by src/utils/ops.py:195-224, eps 1e-6, 1 iteration)
+# ---------------------------------------------------------------------------------------------------------------------
+def sn_weight(sd, prefix, training=True, update=True):
+    """Returns W / sigma (differentiable w.r.t. sd[prefix+'weight_orig']); updates u, v in ``sd`` like the hook does."""
+    W = sd[prefix + "weight_orig"]
+    u, v = sd[prefix + "weight_u"], sd[prefix + "weight_v"]
+    Wm = W.reshape(W.shape[0], -1)
+    if training:
+        with torch.no_grad():
+            v = F.normalize(torch.mv(Wm.t(), u), dim=0, eps=SN_EPS)
+            u = F.normalize(torch.mv(Wm, v), dim=0, eps=SN_EPS)
+        if update:
+            sd[prefix + "weight_u"], sd[prefix + "weight_v"] = u.clone(), v.clone()
+    sigma = torch.dot(u, torch.mv(Wm, v))
+    return W / sigma
+
+
+def weight(sd, prefix, training=True):
+    """Weight of a (possibly spectrally-normalised) layer."""
+    if prefix + "weight_orig" in sd:
+        return sn_weight(sd, prefix, training)
+    return sd[prefix + "weight"]
+
+
+def conv(sd, prefix, x, padding, training=True):
+    return F.conv2d(x, weight(sd, prefix, training), sd.get(prefix + "bias"), stride=1, padding=padding)
+
+
+def linear(sd, prefix, x, training=True):
+    return F.linear(x, weight(sd, prefix, training), sd.get(prefix + "bias"))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# batch norm  (src/utils/ops.py:227-228 -> nn.BatchNorm2d eps 1e-4 momentum 0.1; F.batch_norm semantics)
+# ---------------------------------------------------------------------------------------------------------------------
+def batch_norm(sd, prefix, x, training=True, track=True, affine=False):
+    if training:
+        mean = x.mean(dim=(0, 2, 3))
+        var = x.var(dim=(0, 2, 3), unbiased=False)
+        if track:
+            n = x.numel() / x.shape[1]
+            with torch.no_grad():
+                sd[prefix + "running_mean"] = (1 - BN_MOMENTUM) * sd[prefix + "running_mean"] + BN_MOMENTUM * mean
+                sd[prefix + "running_var"] = (1 - BN_MOMENTUM) * sd[prefix + "running_var"] + BN_MOMENTUM * var * n / (n - 1)
+                if prefix + "num_batches_tracked" in sd:
+                    sd[prefix + "num_batches_tracked"] = sd[prefix + "num_batches_tracked"] + 1
+    else:
+        mean, var = sd[prefix + "running_mean"], sd[prefix + "running_var"]
+    y = (x - mean[None, :, None, None]) * torch.rsqrt(var[None, :, None, None] + BN_EPS)
+    if affine:
+        y = y * sd[prefix + "weight"][None, :, None, None] + sd[prefix + "bias"][None, :, None, None]
+    return y
+
+
+def cbn(sd, prefix, x, y, training=True, track=True):
+    """ops.ConditionalBatchNorm2d.forward (src/utils/ops.py:24-28)."""
+    gain = (1 + linear(sd, prefix + "gain.", y, training)).view(y.size(0), -1, 1, 1)
+    bias = linear(sd, prefix + "bias.", y, training).view(y.size(0), -1, 1, 1)
+    return batch_norm(sd, prefix + "bn.", x, training, track) * gain + bias
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# self attention  (src/utils/ops.py:83-103)
+# ---------------------------------------------------------------------------------------------------------------------
+def self_attention(sd, prefix, x, training=True):
+    B, ch, h, w = x.shape
+    theta = conv(sd, prefix + "conv1x1_theta.", x, 0, training).view(-1, ch // 8, h * w)
+    phi = F.max_pool2d(conv(sd, prefix + "conv1x1_phi.", x, 0, training), 2, 2).view(-1, ch // 8, h * w // 4)
+    attn = torch.softmax(torch.bmm(theta.permute(0, 2, 1), phi), dim=-1)
+    g = F.max_pool2d(conv(sd, prefix + "conv1x1_g.", x, 0, training), 2, 2).view(-1, ch // 2, h * w // 4)
+    attn_g = torch.bmm(g, attn.permute(0, 2, 1)).view(-1, ch // 2, h, w)
+    attn_g = conv(sd, prefix + "conv1x1_attn.", attn_g, 0, training)
+    return x + sd[prefix + "sigma"] * attn_g
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BigGAN-Deep (legacy)  (src/models/big_resnet_deep_legacy.py)
+# ---------------------------------------------------------------------------------------------------------------------
+G_IN = {"32": [4, 4, 4], "64": [16, 8, 4, 2], "128": [16, 16, 8, 4, 2], "256": [16, 16, 8, 8, 4, 2]}
+G_OUT = {"32": [4, 4, 4], "64": [8, 4, 2, 1], "128": [16, 8, 4, 2, 1], "256": [16, 8, 8, 4, 2, 1]}
+D_IN = {"32": [4, 4, 4], "64": [1, 2, 4, 8], "128": [1, 2, 4, 8, 16], "256": [1, 2, 4, 8, 8, 16]}
+D_OUT = {"32": [4, 4, 4], "64": [2, 4, 8, 16], "128": [2, 4, 8, 16, 16], "256": [2, 4, 8, 8, 16, 16]}
+D_DOWN = {"32": [True, True, False, False], "64": [True, True, True, True, False],
+          "128": [True, True, True, True, True, False], "256": [True, True, True, True, True, True, False]}
+
+
+def deep_gen_block(sd, p, x, affine, out_channels, upsample, training=True, track=True):
+    """GenBlock.forward (src/models/big_resnet_deep_legacy.py:49-73)."""
+    x0 = x[:, :out_channels] if x.shape[1] != out_channels else x
+    h = conv(sd, p + "conv2d1.", F.relu(cbn(sd, p + "bn1.", x, affine, training, track)), 0, training)
+    h = F.relu(cbn(sd, p + "bn2.", h, affine, training, track))
+    if upsample:
+        h = F.interpolate(h, scale_factor=2, mode="nearest")
+    h = conv(sd, p + "conv2d2.", h, 1, training)
+    h = conv(sd, p + "conv2d3.", F.relu(cbn(sd, p + "bn3.", h, affine, training, track)), 1, training)
+    h = conv(sd, p + "conv2d4.", F.relu(cbn(sd, p + "bn4.", h, affine, training, track)), 0, training)
+    if upsample:
+        x0 = F.interpolate(x0, scale_factor=2, mode="nearest")
+    return h + x0
+
+
+def deep_generator(sd, z, label, img_size, g_conv_dim, g_depth, attn_g_loc=(), apply_attn=False, training=True, track=True,
+                   conditional=True):
+    """Generator.forward (src/models/big_resnet_deep_legacy.py:153-184); ``sd`` is mutated like module buffers are."""
+    key = str(img_size)
+    in_dims = [g_conv_dim * m for m in G_IN[key]]
+    out_dims = [g_conv_dim * m for m in G_OUT[key]]
+    if conditional:
+        z = torch.cat([F.embedding(label, sd["shared.weight"]), z], 1)
+    affine = z
+    act = linear(sd, "linear0.", z, training).view(-1, in_dims[0], 4, 4)
+    bi = 0
+    for index in range(len(in_dims)):
+        for g_index in range(g_depth):
+            oc = in_dims[index] if g_index == 0 else out_dims[index]
+            act = deep_gen_block(sd, "blocks.%d.0." % bi, act, affine, oc, g_index == g_depth - 1, training, track)
+            bi += 1
+        if (index + 1) in attn_g_loc and apply_attn:
+            act = self_attention(sd, "blocks.%d.0." % bi, act, training)
+            bi += 1
+    act = F.relu(batch_norm(sd, "bn4.", act, training, track, affine=True))
+    return torch.tanh(conv(sd, "conv2d5.", act, 1, training))
+
+
+def deep_disc_block(sd, p, x, downsample, training=True):
+    """DiscBlock.forward (src/models/big_resnet_deep_legacy.py:210-229).
+
+    NOTE the reference quirk: MODULES.d_act_fn is nn.ReLU(inplace=True) (src/config.py:486), so ``self.activation(x)``
+    at :213 also rectifies ``x0`` (same storage).  The skip path therefore carries relu(x), not x."""
+    x = F.relu(x)
+    x0 = x
+    h = conv(sd, p + "conv2d1.", x, 0, training)
+    h = conv(sd, p + "conv2d2.", F.relu(h), 1, training)
+    h = conv(sd, p + "conv2d3.", F.relu(h), 1, training)
+    h = F.relu(h)
+    if downsample:
+        h = F.avg_pool2d(h, 2)
+    h = conv(sd, p + "conv2d4.", h, 0, training)
+    if downsample:
+        x0 = F.avg_pool2d(x0, 2)
+    if (p + "conv2d0.weight_orig") in sd or (p + "conv2d0.weight") in sd:
+        x0 = torch.cat([x0, conv(sd, p + "conv2d0.", x0, 0, training)], 1)
+    return h + x0
+
+
+def disc_head_pd(sd, h, label, training=True, cond="PD"):
+    """Sum-pooled features -> adversarial logit (+ projection) (src/models/big_resnet_deep_legacy.py:344-372)."""
+    adv = torch.squeeze(linear(sd, "linear1.", h, training))
+    if cond == "PD":
+        adv = adv + torch.sum(F.embedding(label, weight(sd, "embedding.", training)) * h, 1)
+    return adv
+
+
+def deep_discriminator(sd, x, label, img_size, d_conv_dim, d_depth, attn_d_loc=(), apply_attn=False, training=True,
+                       cond="PD"):
+    """Discriminator.forward (src/models/big_resnet_deep_legacy.py:334-413); returns (adv_output, h)."""
+    key = str(img_size)
+    in_dims = [d_conv_dim * m for m in D_IN[key]]
+    down = D_DOWN[key]
+    h = conv(sd, "input_conv.", x, 1, training)
+    bi = 0
+    for index in range(len(in_dims)):
+        for d_index in range(d_depth):
+            h = deep_disc_block(sd, "blocks.%d.0." % bi, h, bool(down[index] and d_index == 0), training)
+            bi += 1
+        if (index + 1) in attn_d_loc and apply_attn:
+            h = self_attention(sd, "blocks.%d.0." % bi, h, training)
+            bi += 1
+    h = torch.sum(F.relu(h), dim=[2, 3])
+    return disc_head_pd(sd, h, label, training, cond), h
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# losses  (src/utils/losses.py:197-239, 268-275, 301-316)
+# ---------------------------------------------------------------------------------------------------------------------
+def d_hinge(d_logit_real, d_logit_fake, DDP=False):
+    return torch.mean(F.relu(1. - d_logit_real)) + torch.mean(F.relu(1. + d_logit_fake))
+
+
+def g_hinge(d_logit_fake, DDP=False):
+    return -torch.mean(d_logit_fake)
+
+
+def d_wasserstein(d_logit_real, d_logit_fake, DDP=False):
+    return torch.mean(d_logit_fake - d_logit_real)
+
+
+def g_wasserstein(d_logit_fake, DDP=False):
+    return -torch.mean(d_logit_fake)
+
+
+def d_vanilla(d_logit_real, d_logit_fake, DDP=False):
+    return torch.mean(F.softplus(-d_logit_real)) + torch.mean(F.softplus(d_logit_fake))
+
+
+def g_vanilla(d_logit_fake, DDP=False):
+    return torch.mean(F.softplus(-d_logit_fake))
+
+
+def grad_penalty(disc_fn, real, fake, alpha):
+    """cal_grad_penalty (src/utils/losses.py:301-316) with the CPU-drawn alpha passed in ([B,1] uniform)."""
+    B, c, h, w = real.shape
+    a = alpha.expand(B, real.nelement() // B).contiguous().view(B, c, h, w)
+    interp = (a * real + (1 - a) * fake).detach().requires_grad_(True)
+    out = disc_fn(interp)
+    grads = torch.autograd.grad(outputs=out, inputs=interp, grad_outputs=torch.ones_like(out), create_graph=True,
+                                retain_graph=True, only_inputs=True)[0]
+    grads = grads.view(len(grads), -1)
+    return ((grads.norm(2, dim=1) - 1) ** 2).mean() + interp[:, 0, 0, 0].mean() * 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# EMA / Adam  (src/utils/ema.py:27-40; src/config.py:541-563 -> torch.optim.Adam, eps 1e-6)
+# ---------------------------------------------------------------------------------------------------------------------
+def ema_update(src_sd, ema_sd, decay, step, start_iter):
+    d = 0.0 if step < start_iter else decay
+    for k in src_sd:
+        if k.endswith("num_batches_tracked"):
+            ema_sd[k] = src_sd[k].clone()
+        else:
+            ema_sd[k] = src_sd[k] + d * (ema_sd[k] - src_sd[k])   # torch.lerp(src, ema, d)
+
+
+def adam_step(p, g, m, v, step, lr, beta1, beta2, eps=1e-6):
+    m = beta1 * m + (1 - beta1) * g
+    v = beta2 * v + (1 - beta2) * g * g
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    p = p - (lr / bc1) * m / (v.sqrt() / math.sqrt(bc2) + eps)
+    return p, m, v
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# evaluation arithmetic  (src/utils/ops.py:251-263, src/utils/resize.py:83-91, src/metrics/{fid,ins,prdc}.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def quantize_images(x):
+    """ops.quantize_images (src/utils/ops.py:251-255): float [-1,1] -> uint8 with +0.5 and truncation."""
+    x = (x + 1) / 2
+    x = (255.0 * x + 0.5).clamp(0.0, 255.0)
+    return x.detach().cpu().numpy().astype(np.uint8)
+
+
+def resize_legacy(x_uint8_nchw, size=299):
+    """'legacy' resizer (src/utils/resize.py:83-91): per-image F.interpolate bilinear align_corners=False, clip 0..255."""
+    x = torch.from_numpy(x_uint8_nchw.astype(np.float32))
+    x = F.interpolate(x, size=(size, size), mode="bilinear", align_corners=False)
+    return x.clamp(0, 255)
+
+
+def normalize_for_inception(x255):
+    """resize_images tail (src/utils/ops.py:262): x/255, (x-0.5)/0.5 for InceptionV3_tf."""
+    return (x255 / 255.0 - 0.5) / 0.5
+
+
+def calculate_kl_div(ps, splits=1):
+    """ins.calculate_kl_div (src/metrics/ins.py:28-42)."""
+    ps = np.asarray(ps, dtype=np.float64)
+    scores = []
+    n = ps.shape[0]
+    for j in range(splits):
+        part = ps[(j * n // splits):((j + 1) * n // splits), :]
+        kl = part * (np.log(part) - np.log(np.mean(part, 0, keepdims=True)))
+        scores.append(np.exp(np.mean(np.sum(kl, 1))))
+    with np.errstate(all="ignore"):
+        std = float(np.std(scores, ddof=1)) if len(scores) > 1 else float("nan")   # torch.std is unbiased: NaN for splits=1
+    return float(np.mean(scores)), std
+
+
+def moments(feats):
+    """fid.calculate_moments tail (src/metrics/fid.py:96-97): mean and np.cov(rowvar=False)."""
+    feats = np.asarray(feats)
+    return np.mean(feats, axis=0), np.cov(feats, rowvar=False)
+
+
+def frechet_distance(mu1, sigma1, mu2, sigma2, eps=1e-6):
+    """fid.frechet_inception_distance (src/metrics/fid.py:34-62)."""
+    from scipy import linalg
+    mu1, mu2 = np.atleast_1d(mu1), np.atleast_1d(mu2)
+    sigma1, sigma2 = np.atleast_2d(sigma1), np.atleast_2d(sigma2)
+    diff = mu1 - mu2
+    covmean = linalg.sqrtm(sigma1.dot(sigma2))
+    if not np.isfinite(covmean).all():
+        offset = np.eye(sigma1.shape[0]) * eps
+        covmean = linalg.sqrtm((sigma1 + offset).dot(sigma2 + offset))
+    if np.iscomplexobj(covmean):
+        if not np.allclose(np.diagonal(covmean).imag, 0, atol=1e-3):
+            raise ValueError("Imaginary component {}".format(np.max(np.abs(covmean.imag))))
+        covmean = covmean.real
+    return float(diff.dot(diff) + np.trace(sigma1) + np.trace(sigma2) - 2 * np.trace(covmean))
+
+
+def prdc(real, fake, nearest_k=5):
+    """prdc.compute_prdc (src/metrics/prdc.py:129-168): euclidean distances, k-th NN radii (self included)."""
+    real, fake = np.asarray(real, dtype=np.float64), np.asarray(fake, dtype=np.float64)
+
+    def dist(a, b):
+        d2 = (a * a).sum(1)[:, None] + (b * b).sum(1)[None, :] - 2 * a @ b.T
+        return np.sqrt(np.maximum(d2, 0))
+
+    def kth(d, k):
+        return np.partition(d, k, axis=-1)[:, k]     # (k+1)-th smallest, k = nearest_k because self-distance is 0
+
+    rr, ff, rf = dist(real, real), dist(fake, fake), dist(real, fake)
+    r_real, r_fake = kth(rr, nearest_k), kth(ff, nearest_k)
+    precision = (rf < r_real[:, None]).any(axis=0).mean()
+    recall = (rf < r_fake[None, :]).any(axis=1).mean()
+    density = (1. / float(nearest_k)) * (rf < r_real[:, None]).sum(axis=0).mean()
+    coverage = (rf.min(axis=1) < r_real).mean()
+    return dict(precision=float(precision), recall=float(recall), density=float(density), coverage=float(coverage))

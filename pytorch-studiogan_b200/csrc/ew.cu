@@ -1,0 +1,529 @@
+// Streaming element-wise / small-reduction kernels around the conv engine (all HBM-bound, 16-byte vectors on NHWC bf16).
+// Reference call sites: ReLU / AvgPool2d / nearest-upsample / residual add in src/models/big_resnet_deep_legacy.py:49-73,
+// 210-229,334-345; MaxPool2d + Softmax + sigma*attn in src/utils/ops.py:79-103; tanh at big_resnet_deep_legacy.py:183;
+// Adam (src/config.py:541-563, eps 1e-6) and Ema.update (src/utils/ema.py:27-40).
+#include "common.cuh"
+
+namespace sgb {
+
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xFFFF0000u);
+  f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xFFFF0000u);
+  f[4] = __uint_as_float(r.z << 16); f[5] = __uint_as_float(r.z & 0xFFFF0000u);
+  f[6] = __uint_as_float(r.w << 16); f[7] = __uint_as_float(r.w & 0xFFFF0000u);
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack2(f[0], f[1]); o.y = pack2(f[2], f[3]); o.z = pack2(f[4], f[5]); o.w = pack2(f[6], f[7]);
+  return o;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// out = act(a*x + b*y) over [npix][C] with per-tensor channel strides; a may come from a device scalar.
+// act: 0 none, 1 relu.  y may be null (b ignored).  mask (optional): out = mask > 0 ? out : 0.
+__global__ void __launch_bounds__(256) axpby_kernel(const bf16* __restrict__ x, long long xs, const bf16* __restrict__ y,
+                                                     long long ys, const bf16* __restrict__ mask, long long ms,
+                                                     bf16* __restrict__ out, long long os, long long npix, int C, float a,
+                                                     const float* __restrict__ a_dev, float b, int act) {
+  const int VG = C >> 3;
+  if (a_dev) a *= __ldg(a_dev);
+  const long long total = npix * VG;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int g = (int)(i % VG);
+    const long long p = i / VG;
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * xs) + g), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= a;
+    if (y) {
+      float t[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(y + p * ys) + g), t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(b, t[j], f[j]);
+    }
+    if (act == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (mask) {
+      float t[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(mask + p * ms) + g), t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = t[j] > 0.f ? f[j] : 0.f;
+    }
+    reinterpret_cast<uint4*>(out + p * os)[g] = pack8(f);
+  }
+}
+
+// 2x2 pooling.  mode 0: average, 1: max.  One thread = 8 channels of one OUTPUT pixel.
+__global__ void __launch_bounds__(256) pool2_fwd_kernel(const bf16* __restrict__ x, long long xs, bf16* __restrict__ y,
+                                                         long long ys, int B, int Ho, int Wo, int C, int mode) {
+  const int VG = C >> 3;
+  const long long total = (long long)B * Ho * Wo * VG;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int g = (int)(i % VG);
+    const long long p = i / VG;
+    const int wo = (int)(p % Wo), ho = (int)((p / Wo) % Ho), b = (int)(p / ((long long)Wo * Ho));
+    const long long q = ((long long)b * (2 * Ho) + 2 * ho) * (2 * Wo) + 2 * wo;
+    float f0[8], f1[8], f2[8], f3[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + q * xs) + g), f0);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + (q + 1) * xs) + g), f1);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + (q + 2 * Wo) * xs) + g), f2);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + (q + 2 * Wo + 1) * xs) + g), f3);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = mode == 1 ? fmaxf(fmaxf(f0[j], f1[j]), fmaxf(f2[j], f3[j]))
+                       : (mode == 0 ? 0.25f : 1.0f) * (f0[j] + f1[j] + f2[j] + f3[j]);  // 0 average, 2 sum
+    reinterpret_cast<uint4*>(y + p * ys)[g] = pack8(o);
+  }
+}
+
+// Backward of 2x2 pooling, one thread = 8 channels of one OUTPUT-resolution pixel, writes the 4 input-resolution pixels.
+// mode 0 (avg): dx = 0.25*dy; mode 1 (max): dy routed to the first maximum in (h,w) scan order (torch MaxPool2d).
+// Optional: add (same layout as dx) is summed in, relu_src masks the result where relu_src <= 0.
+__global__ void __launch_bounds__(256) pool2_bwd_kernel(const bf16* __restrict__ dy, long long dys, const bf16* __restrict__ x,
+                                                         long long xs, const bf16* __restrict__ add, long long adds,
+                                                         const bf16* __restrict__ relu_src, long long rs, bf16* __restrict__ dx,
+                                                         long long dxs, int B, int Ho, int Wo, int C, int mode) {
+  const int VG = C >> 3;
+  const long long total = (long long)B * Ho * Wo * VG;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int g = (int)(i % VG);
+    const long long p = i / VG;
+    const int wo = (int)(p % Wo), ho = (int)((p / Wo) % Ho), b = (int)(p / ((long long)Wo * Ho));
+    const long long q0 = ((long long)b * (2 * Ho) + 2 * ho) * (2 * Wo) + 2 * wo;
+    const long long qs[4] = {q0, q0 + 1, q0 + 2 * Wo, q0 + 2 * Wo + 1};
+    float d[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + p * dys) + g), d);
+    float o[4][8];
+    if (mode == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[k][j] = 0.25f * d[j];
+    } else {
+      float f[4][8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) unpack8(__ldg(reinterpret_cast<const uint4*>(x + qs[k] * xs) + g), f[k]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int arg = 0;
+        float m = f[0][j];
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+          if (f[k][j] > m) { m = f[k][j]; arg = k; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k][j] = (k == arg) ? d[j] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (add) {
+        float t[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(add + qs[k] * adds) + g), t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[k][j] += t[j];
+      }
+      if (relu_src) {
+        float t[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(relu_src + qs[k] * rs) + g), t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[k][j] = t[j] > 0.f ? o[k][j] : 0.f;
+      }
+      reinterpret_cast<uint4*>(dx + qs[k] * dxs)[g] = pack8(o[k]);
+    }
+  }
+}
+
+// Row softmax over the last dim (bf16 in/out, fp32 math), one warp per row, in place allowed.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const bf16* __restrict__ s, bf16* __restrict__ p, long long rows, int n) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const uint4* sp = reinterpret_cast<const uint4*>(s + row * n);
+  uint4* pp = reinterpret_cast<uint4*>(p + row * n);
+  const int nv = n >> 3;
+  float m = -INFINITY;
+  for (int i = lane; i < nv; i += 32) {
+    float f[8];
+    unpack8(__ldg(sp + i), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m = fmaxf(m, f[j]);
+  }
+  m = warp_max(m);
+  float z = 0.f;
+  for (int i = lane; i < nv; i += 32) {
+    float f[8];
+    unpack8(__ldg(sp + i), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z += __expf(f[j] - m);
+  }
+  z = warp_sum(z);
+  const float inv = 1.f / z;
+  for (int i = lane; i < nv; i += 32) {
+    float f[8];
+    unpack8(__ldg(sp + i), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = __expf(f[j] - m) * inv;
+    pp[i] = pack8(f);
+  }
+}
+
+// dS = P * (dP - sum_j dP_j P_j), rowwise; writes into ds (may alias dp).
+__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const bf16* __restrict__ p, const bf16* __restrict__ dp,
+                                                                bf16* __restrict__ ds, long long rows, int n) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const uint4* pp = reinterpret_cast<const uint4*>(p + row * n);
+  const uint4* dpp = reinterpret_cast<const uint4*>(dp + row * n);
+  uint4* dsp = reinterpret_cast<uint4*>(ds + row * n);
+  const int nv = n >> 3;
+  float dot = 0.f;
+  for (int i = lane; i < nv; i += 32) {
+    float a[8], b[8];
+    unpack8(__ldg(pp + i), a);
+    unpack8(__ldg(dpp + i), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dot = fmaf(a[j], b[j], dot);
+  }
+  dot = warp_sum(dot);
+  for (int i = lane; i < nv; i += 32) {
+    float a[8], b[8];
+    unpack8(__ldg(pp + i), a);
+    unpack8(dpp[i], b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = a[j] * (b[j] - dot);
+    dsp[i] = pack8(b);
+  }
+}
+
+// sum over a contiguous bf16 buffer of x*y -> fp32 scalar (atomic).
+__global__ void __launch_bounds__(256) dot_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, long long nvec,
+                                                   float* __restrict__ out) {
+  __shared__ float sh[8];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long long)gridDim.x * 256) {
+    float a[8], b[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(a[j], b[j], acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float r = sh[threadIdx.x];
+    r += __shfl_xor_sync(0xffu, r, 4);
+    r += __shfl_xor_sync(0xffu, r, 2);
+    r += __shfl_xor_sync(0xffu, r, 1);
+    if (threadIdx.x == 0) atomicAdd(out, r);
+  }
+}
+
+// h[b,c] = sum_{hw} act(x[b,hw,c]) (fp32), act = relu if relu.  grid = (pixel chunks, B).
+__global__ void __launch_bounds__(256) sum_hw_kernel(const bf16* __restrict__ x, long long xs, int HW, int C, int relu,
+                                                      float* __restrict__ h, int pix_per_block) {
+  extern __shared__ float acc_s[];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < C; i += 256) acc_s[i] = 0.f;
+  __syncthreads();
+  const int VG = C >> 3;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, HW);
+  for (int g = threadIdx.x; g < VG; g += 256) {
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int hw = p0; hw < p1; ++hw) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((long long)b * HW + hw) * xs) + g), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += relu ? fmaxf(f[j], 0.f) : f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc_s[g * 8 + j] += a[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) atomicAdd(h + (size_t)b * C + i, acc_s[i]);
+}
+
+// dx[b,hw,c] = dh[b,c] * (relu ? x > 0 : 1)
+__global__ void __launch_bounds__(256) sum_hw_bwd_kernel(const float* __restrict__ dh, const bf16* __restrict__ x, long long xs,
+                                                          bf16* __restrict__ dx, long long dxs, int B, int HW, int C, int relu) {
+  const int VG = C >> 3;
+  const long long total = (long long)B * HW * VG;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int g = (int)(i % VG);
+    const long long p = i / VG;
+    const int b = (int)(p / HW);
+    float f[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * xs) + g), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = __ldg(dh + (size_t)b * C + g * 8 + j);
+      o[j] = (!relu || f[j] > 0.f) ? d : 0.f;
+    }
+    reinterpret_cast<uint4*>(dx + p * dxs)[g] = pack8(o);
+  }
+}
+
+// NCHW fp32 image -> NHWC bf16 with the channel dim zero-padded to Cp (multiple of 8).
+__global__ void __launch_bounds__(256) img_to_nhwc_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int C,
+                                                           int HW, int Cp) {
+  const long long total = (long long)B * HW;
+  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < total; p += (long long)gridDim.x * 256) {
+    const int b = (int)(p / HW), hw = (int)(p % HW);
+    for (int c0 = 0; c0 < Cp; c0 += 8) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = (c0 + j < C) ? __ldg(img + ((size_t)b * C + c0 + j) * HW + hw) : 0.f;
+      reinterpret_cast<uint4*>(out + p * Cp + c0)[0] = pack8(f);
+    }
+  }
+}
+
+// NHWC (fp32 or bf16, channel stride cs) -> NCHW fp32 for the first C channels; act: 0 none, 1 tanh.
+__global__ void __launch_bounds__(256) nhwc_to_img_kernel(const void* __restrict__ in, int in_fp32, long long cs,
+                                                           float* __restrict__ img, int B, int C, int HW, int act) {
+  const long long total = (long long)B * HW;
+  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < total; p += (long long)gridDim.x * 256) {
+    const int b = (int)(p / HW), hw = (int)(p % HW);
+    for (int c = 0; c < C; ++c) {
+      float v = in_fp32 ? reinterpret_cast<const float*>(in)[p * cs + c]
+                        : __bfloat162float(reinterpret_cast<const bf16*>(in)[p * cs + c]);
+      if (act == 1) v = tanhf(v);
+      img[((size_t)b * C + c) * HW + hw] = v;
+    }
+  }
+}
+
+// d(pre-tanh) in NHWC bf16 (padded to Cp) from d(image) and the tanh output, both NCHW fp32:  d * (1 - y^2).
+// With y == null it is a plain NCHW fp32 -> NHWC bf16 gradient re-layout.
+__global__ void __launch_bounds__(256) img_grad_to_nhwc_kernel(const float* __restrict__ dimg, const float* __restrict__ y,
+                                                                bf16* __restrict__ out, int B, int C, int HW, int Cp) {
+  const long long total = (long long)B * HW;
+  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < total; p += (long long)gridDim.x * 256) {
+    const int b = (int)(p / HW), hw = (int)(p % HW);
+    for (int c0 = 0; c0 < Cp; c0 += 8) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = 0.f;
+        if (c0 + j < C) {
+          const size_t idx = ((size_t)b * C + c0 + j) * HW + hw;
+          v = __ldg(dimg + idx);
+          if (y) { const float t = __ldg(y + idx); v *= (1.f - t * t); }
+        }
+        f[j] = v;
+      }
+      reinterpret_cast<uint4*>(out + p * Cp + c0)[0] = pack8(f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n,
+                                                             float scale) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+    out[i] = __float2bfloat16_rn(__ldg(in + i) * scale);
+}
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+    out[i] = __bfloat162float(in[i]);
+}
+
+// Fused Adam (torch.optim.Adam semantics, no weight decay / amsgrad) + optional EMA lerp of the updated weights:
+//   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+//   ema = p + decay * (ema - p)                       (torch lerp: p.lerp(p_ema, decay), src/utils/ema.py:33-36)
+__global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, long long n, float lr, float b1, float b2,
+                                                        float eps, float bc1, float bc2_sqrt, float* __restrict__ ema,
+                                                        float decay, float grad_scale) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float gi = g[i] * grad_scale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    const float pi = p[i] - (lr / bc1) * (mi / denom);
+    p[i] = pi;
+    if (ema) ema[i] = pi + decay * (ema[i] - pi);
+  }
+}
+__global__ void __launch_bounds__(256) lerp_kernel(float* __restrict__ ema, const float* __restrict__ p, long long n, float decay) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float pi = p[i];
+    ema[i] = pi + decay * (ema[i] - pi);
+  }
+}
+
+}  // namespace sgb
+
+using namespace sgb;
+
+static inline int ew_blocks(long long total_threads) {
+  long long b = (total_threads + 255) / 256;
+  const long long cap = 16LL * sm_count();
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+extern "C" int sgb_axpby(const void* x, int64_t xs, const void* y, int64_t ys, const void* mask, int64_t ms, void* out,
+                         int64_t os, int64_t npix, int32_t C, float a, const float* a_dev, float b, int32_t act,
+                         sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(x && out && npix > 0 && C > 0 && C % 8 == 0 && xs % 8 == 0 && os % 8 == 0);
+  SGB_REQUIRE((!y || ys % 8 == 0) && (!mask || ms % 8 == 0));
+  axpby_kernel<<<ew_blocks(npix * (C / 8)), 256, 0, stream>>>((const bf16*)x, xs, (const bf16*)y, ys, (const bf16*)mask, ms,
+                                                             (bf16*)out, os, npix, C, a, a_dev, b, act);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_pool2_fwd(const void* x, int64_t xs, void* y, int64_t ys, int32_t B, int32_t Ho, int32_t Wo, int32_t C,
+                             int32_t mode, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(x && y && B > 0 && Ho > 0 && Wo > 0 && C > 0 && C % 8 == 0 && xs % 8 == 0 && ys % 8 == 0);
+  pool2_fwd_kernel<<<ew_blocks((long long)B * Ho * Wo * (C / 8)), 256, 0, stream>>>((const bf16*)x, xs, (bf16*)y, ys, B, Ho, Wo, C,
+                                                                                  mode);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_pool2_bwd(const void* dy, int64_t dys, const void* x, int64_t xs, const void* add, int64_t adds,
+                             const void* relu_src, int64_t rs, void* dx, int64_t dxs, int32_t B, int32_t Ho, int32_t Wo,
+                             int32_t C, int32_t mode, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(dy && dx && B > 0 && Ho > 0 && Wo > 0 && C > 0 && C % 8 == 0 && dys % 8 == 0 && dxs % 8 == 0);
+  SGB_REQUIRE(mode == 0 || (x && xs % 8 == 0));
+  SGB_REQUIRE((!add || adds % 8 == 0) && (!relu_src || rs % 8 == 0));
+  pool2_bwd_kernel<<<ew_blocks((long long)B * Ho * Wo * (C / 8)), 256, 0, stream>>>(
+      (const bf16*)dy, dys, (const bf16*)x, xs, (const bf16*)add, adds, (const bf16*)relu_src, rs, (bf16*)dx, dxs, B, Ho, Wo, C, mode);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_softmax_rows(const void* s, void* p, int64_t rows, int32_t n, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(s && p && rows > 0 && n > 0 && n % 8 == 0);
+  softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>((const bf16*)s, (bf16*)p, rows, n);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_softmax_bwd_rows(const void* p, const void* dp, void* ds, int64_t rows, int32_t n, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(p && dp && ds && rows > 0 && n > 0 && n % 8 == 0);
+  softmax_bwd_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>((const bf16*)p, (const bf16*)dp, (bf16*)ds, rows, n);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_dot(const void* x, const void* y, int64_t n, float* out, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(x && y && out && n > 0 && n % 8 == 0);
+  SGB_CUDA(cudaMemsetAsync(out, 0, sizeof(float), stream));
+  dot_kernel<<<ew_blocks(n / 8), 256, 0, stream>>>((const bf16*)x, (const bf16*)y, n / 8, out);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_sum_hw(const void* x, int64_t xs, int32_t B, int32_t HW, int32_t C, int32_t relu, float* h,
+                          sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(x && h && B > 0 && HW > 0 && C > 0 && C % 8 == 0 && xs % 8 == 0 && C <= 8192);
+  SGB_CUDA(cudaMemsetAsync(h, 0, sizeof(float) * (size_t)B * C, stream));
+  int chunks = (4 * sm_count() + B - 1) / B;
+  if (chunks > HW) chunks = HW;
+  if (chunks < 1) chunks = 1;
+  const int ppb = (HW + chunks - 1) / chunks;
+  dim3 grid((HW + ppb - 1) / ppb, B);
+  sum_hw_kernel<<<grid, 256, sizeof(float) * C, stream>>>((const bf16*)x, xs, HW, C, relu, h, ppb);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_sum_hw_bwd(const float* dh, const void* x, int64_t xs, void* dx, int64_t dxs, int32_t B, int32_t HW,
+                              int32_t C, int32_t relu, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(dh && x && dx && B > 0 && HW > 0 && C > 0 && C % 8 == 0 && xs % 8 == 0 && dxs % 8 == 0);
+  sum_hw_bwd_kernel<<<ew_blocks((long long)B * HW * (C / 8)), 256, 0, stream>>>(dh, (const bf16*)x, xs, (bf16*)dx, dxs, B, HW, C,
+                                                                              relu);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_img_to_nhwc(const float* img, void* out, int32_t B, int32_t C, int32_t HW, int32_t Cp, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(img && out && B > 0 && C > 0 && HW > 0 && Cp >= C && Cp % 8 == 0);
+  img_to_nhwc_kernel<<<ew_blocks((long long)B * HW), 256, 0, stream>>>(img, (bf16*)out, B, C, HW, Cp);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_nhwc_to_img(const void* in, int32_t in_fp32, int64_t cs, float* img, int32_t B, int32_t C, int32_t HW,
+                               int32_t act, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(in && img && B > 0 && C > 0 && HW > 0 && cs >= C);
+  nhwc_to_img_kernel<<<ew_blocks((long long)B * HW), 256, 0, stream>>>(in, in_fp32, cs, img, B, C, HW, act);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_img_grad_to_nhwc(const float* dimg, const float* y, void* out, int32_t B, int32_t C, int32_t HW, int32_t Cp,
+                                    sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(dimg && out && B > 0 && C > 0 && HW > 0 && Cp >= C && Cp % 8 == 0);
+  img_grad_to_nhwc_kernel<<<ew_blocks((long long)B * HW), 256, 0, stream>>>(dimg, y, (bf16*)out, B, C, HW, Cp);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_cast_f32_to_bf16(const float* in, void* out, int64_t n, float scale, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(in && out && n > 0);
+  cast_f32_bf16_kernel<<<ew_blocks(n), 256, 0, stream>>>(in, (bf16*)out, n, scale);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_cast_bf16_to_f32(const void* in, float* out, int64_t n, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(in && out && n > 0);
+  cast_bf16_f32_kernel<<<ew_blocks(n), 256, 0, stream>>>((const bf16*)in, out, n);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_adam_ema_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                                 float eps, int32_t step, float* ema, float ema_decay, float grad_scale, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(p && g && m && v && n > 0 && step >= 1);
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  adam_ema_kernel<<<ew_blocks(n), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), ema, ema_decay,
+                                                   grad_scale);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_ema_lerp(float* ema, const float* p, int64_t n, float decay, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(ema && p && n > 0);
+  lerp_kernel<<<ew_blocks(n), 256, 0, stream>>>(ema, p, n, decay);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) sn_wv_kernel(const float* __restrict__ W,
 // (src/models/big_resnet_deep_legacy.py:167-168) but consumed here as NHWC [S, C]: packed row s*C + c <- row c*S + s.
 __global__ void __launch_bounds__(256) sn_pack_kernel(const float* __restrict__ W, const float* __restrict__ sigma,
                                                        bf16* __restrict__ wf, bf16* __restrict__ wd, int Cout, int Cin,
-                                                       int taps, int perm_S) {
+                                                       int taps, int perm_S, int Cout_p, int Cin_p) {
   const size_t total = (size_t)Cout * Cin * taps;
   const float inv = sigma ? 1.f / __ldg(sigma) : 1.f;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
@@ -125,15 +125,16 @@ __global__ void __launch_bounds__(256) sn_pack_kernel(const float* __restrict__ 
       co = (co % perm_S) * C + co / perm_S;
     }
     const bf16 b = __float2bfloat16_rn(val);
-    if (wf) wf[((size_t)co * taps + tap) * Cin + ci] = b;
-    if (wd) wd[((size_t)ci * taps + (taps - 1 - tap)) * Cout + co] = b;
+    if (wf) wf[((size_t)co * taps + tap) * Cin_p + ci] = b;
+    if (wd) wd[((size_t)ci * taps + (taps - 1 - tap)) * Cout_p + co] = b;
   }
 }
 
 // Backward of W_sn = W / sigma with u, v held constant (they are detached buffers in the reference):
 //   dL/dW = (G - <G, W_sn> u v^T) / sigma,  G given in the fprop pack layout [co][tap][ci] (fp32, from wgrad).
 __global__ void __launch_bounds__(256) sn_bwd_dot_kernel(const float* __restrict__ G, const float* __restrict__ W,
-                                                          float* __restrict__ dot, int Cout, int Cin, int taps, int perm_S) {
+                                                          float* __restrict__ dot, int Cout, int Cin, int taps, int perm_S,
+                                                          int Cin_p) {
   __shared__ float sh[32];
   const size_t total = (size_t)Cout * Cin * taps;
   float acc = 0.f;
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(256) sn_bwd_dot_kernel(const float* __restrict
     const int ci = (int)((i / taps) % Cin);
     int co = (int)(i / ((size_t)taps * Cin));
     if (perm_S > 1) { const int C = Cout / perm_S; co = (co % perm_S) * C + co / perm_S; }
-    acc = fmaf(__ldg(G + ((size_t)co * taps + tap) * Cin + ci), __ldg(W + i), acc);
+    acc = fmaf(__ldg(G + ((size_t)co * taps + tap) * Cin_p + ci), __ldg(W + i), acc);
   }
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) atomicAdd(dot, acc);
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(256) sn_bwd_dot_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) sn_bwd_apply_kernel(const float* __restrict__ G, const float* __restrict__ u,
                                                             const float* __restrict__ v, const float* __restrict__ sigma,
                                                             const float* __restrict__ dot, float* __restrict__ dW, int Cout,
-                                                            int Cin, int taps, int perm_S, int accumulate) {
+                                                            int Cin, int taps, int perm_S, int accumulate, int Cin_p) {
   const size_t total = (size_t)Cout * Cin * taps;
   float inv = 1.f, coef = 0.f;
   if (sigma) {
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(256) sn_bwd_apply_kernel(const float* __restri
     const int co_orig = (int)(i / ((size_t)taps * Cin));
     int co = co_orig;
     if (perm_S > 1) { const int C = Cout / perm_S; co = (co % perm_S) * C + co / perm_S; }
-    float g = __ldg(G + ((size_t)co * taps + tap) * Cin + ci);
+    float g = __ldg(G + ((size_t)co * taps + tap) * Cin_p + ci);
     if (sigma) g = (g - coef * __ldg(u + co_orig) * __ldg(v + (size_t)ci * taps + tap)) * inv;
     dW[i] = accumulate ? dW[i] + g : g;
   }
@@ -194,33 +195,35 @@ extern "C" int sgb_sn_power_iter(const float* W, float* u, float* v, float* sigm
 }
 
 extern "C" int sgb_weight_pack(const float* W, const float* sigma, void* w_fprop, void* w_dgrad, int32_t Cout, int32_t Cin,
-                               int32_t taps, int32_t perm_S, sgb_stream_t stream_) {
+                               int32_t taps, int32_t perm_S, int32_t Cout_p, int32_t Cin_p, sgb_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SGB_REQUIRE(W && (w_fprop || w_dgrad) && Cout > 0 && Cin > 0 && taps > 0);
   SGB_REQUIRE(perm_S <= 1 || Cout % perm_S == 0);
+  SGB_REQUIRE(Cout_p >= Cout && Cin_p >= Cin);
   const size_t total = (size_t)Cout * Cin * taps;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
-  sn_pack_kernel<<<blocks, 256, 0, stream>>>(W, sigma, (bf16*)w_fprop, (bf16*)w_dgrad, Cout, Cin, taps, perm_S);
+  sn_pack_kernel<<<blocks, 256, 0, stream>>>(W, sigma, (bf16*)w_fprop, (bf16*)w_dgrad, Cout, Cin, taps, perm_S, Cout_p, Cin_p);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }
 
 extern "C" int sgb_sn_backward(const float* G, const float* W, const float* u, const float* v, const float* sigma,
                                float* scratch_dot, float* dW, int32_t Cout, int32_t Cin, int32_t taps, int32_t perm_S,
-                               int32_t accumulate, sgb_stream_t stream_) {
+                               int32_t Cin_p, int32_t accumulate, sgb_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SGB_REQUIRE(G && dW && Cout > 0 && Cin > 0 && taps > 0);
   SGB_REQUIRE(!sigma || (W && u && v && scratch_dot));
+  SGB_REQUIRE(Cin_p >= Cin);
   const size_t total = (size_t)Cout * Cin * taps;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
   if (sigma) {
     SGB_CUDA(cudaMemsetAsync(scratch_dot, 0, sizeof(float), stream));
-    sn_bwd_dot_kernel<<<blocks, 256, 0, stream>>>(G, W, scratch_dot, Cout, Cin, taps, perm_S);
+    sn_bwd_dot_kernel<<<blocks, 256, 0, stream>>>(G, W, scratch_dot, Cout, Cin, taps, perm_S, Cin_p);
     SGB_LAUNCH_CHECK();
   }
-  sn_bwd_apply_kernel<<<blocks, 256, 0, stream>>>(G, u, v, sigma, scratch_dot, dW, Cout, Cin, taps, perm_S, accumulate);
+  sn_bwd_apply_kernel<<<blocks, 256, 0, stream>>>(G, u, v, sigma, scratch_dot, dW, Cout, Cin, taps, perm_S, accumulate, Cin_p);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }

@@ -26,11 +26,13 @@ struct FpropArgs {
   int tiles_w, tiles_h, tiles_b, tiles_n, num_tiles;
   int kblocks;                    // ceil(Cin / 64)
   int BN;                         // output-channel tile (multiple of 16, <= 256)
+  int w_mode;                     // 0: shared weights [Cout][taps][Cin]; 1: per-image [B][N][K]; 2: per-image MN-major [B][K][N]
   int stages;
   uint32_t tmem_cols;
   float alpha;
+  const float* alpha_ptr;
   const float* bias;
-  const bf16* residual; long long res_cstride; int res_up2;
+  const bf16* residual; long long res_cstride; int res_up2; int res_after;
   const bf16* mask; long long mask_cstride;
   int relu;
   void* y; long long y_cstride; int y_fp32;
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_bytes = (uint32_t)p.BN * kBlockK * 2;
+  const uint32_t b_bytes = (uint32_t)p.BN * kBlockK * 2;  // same size for K-major [BN][64] and MN-major (BN/64) x [64][64]
   const uint32_t stage_bytes = kABytes + b_bytes;  // multiple of 1024 because BN % 8 == 0 -> b_bytes % 1024 == 0
   const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -104,7 +106,14 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_arrive_expect_tx(full_bar(s), stage_bytes);
             const uint32_t sa = smem_base + s * stage_bytes;
             tma_load_4d(sa, &tmA, full_bar(s), kb * kBlockK, w0 + dw, h0 + dh, b0);
-            tma_load_3d(sa + kABytes, &tmB, full_bar(s), kb * kBlockK, tap, n0);
+            if (p.w_mode == 0) {
+              tma_load_3d(sa + kABytes, &tmB, full_bar(s), kb * kBlockK, tap, n0);
+            } else if (p.w_mode == 1) {
+              tma_load_3d(sa + kABytes, &tmB, full_bar(s), kb * kBlockK, b0, n0);
+            } else {
+              for (int j = 0; j < p.BN / 64; ++j)
+                tma_load_3d(sa + kABytes + j * 8192, &tmB, full_bar(s), n0 + j * 64, kb * kBlockK, b0);
+            }
           }
         }
       }
@@ -112,7 +121,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------------------------------------- MMA issuer
-      const uint32_t idesc = make_idesc_bf16(kTileM, p.BN, 0, 0);
+      const bool b_mn = (p.w_mode == 2);
+      const uint32_t idesc = make_idesc_bf16(kTileM, p.BN, 0, b_mn ? 1 : 0);
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
@@ -126,11 +136,14 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_fence_after();
           const uint32_t sa = smem_base + s * stage_bytes;
           const uint64_t adesc = make_sdesc_sw128(sa, 16, 1024);
-          const uint64_t bdesc = make_sdesc_sw128(sa + kABytes, 16, 1024);
+          // K-major B: rows = output channels, +32 B per 16-wide K step.
+          // MN-major B: (BN/64) atoms of [64 k-rows][64 n] 8 KiB apart (LBO), 8-row groups 1 KiB apart (SBO), +2 KiB per K step.
+          const uint64_t bdesc = b_mn ? make_sdesc_sw128(sa + kABytes, 8192, 1024) : make_sdesc_sw128(sa + kABytes, 16, 1024);
+          const uint32_t bstep = b_mn ? 128u : 2u;
 #pragma unroll
           for (int kk = 0; kk < kBlockK / 16; ++kk) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            umma_f16_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+            // A: advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+            umma_f16_ss(d_tmem, adesc + 2 * kk, bdesc + bstep * kk, idesc, (k > 0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(s));  // smem slot reusable once these MMAs retire
         }
@@ -144,6 +157,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int wi = row % p.tw, hi = (row / p.tw) % p.th, bi = row / (p.tw * p.th);
     const bool vec_ok = (p.Cout % 8 == 0) && (p.y_cstride % 8 == 0) &&
                         (p.residual == nullptr || p.res_cstride % 8 == 0) && (p.mask == nullptr || p.mask_cstride % 8 == 0);
+    const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
+    const bool res_pre = p.residual != nullptr && !p.res_after;
+    const bool res_post = p.residual != nullptr && p.res_after;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
       int t = tile;
@@ -171,7 +187,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (!valid || n >= p.Cout) continue;
         float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * alpha;
         if (vec_ok && n + 16 <= p.Cout) {
           if (p.bias) {
             const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
@@ -181,7 +197,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
             }
           }
-          if (p.residual) {
+          if (res_pre) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.res_cstride + n);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -211,6 +227,17 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               f[8 * j + 7] = bf16_bits_hi(m.w) > 0.f ? f[8 * j + 7] : 0.f;
             }
           }
+          if (res_post) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.res_cstride + n);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint4 r = __ldg(rp + j);
+              f[8 * j + 0] += bf16_bits_lo(r.x); f[8 * j + 1] += bf16_bits_hi(r.x);
+              f[8 * j + 2] += bf16_bits_lo(r.y); f[8 * j + 3] += bf16_bits_hi(r.y);
+              f[8 * j + 4] += bf16_bits_lo(r.z); f[8 * j + 5] += bf16_bits_hi(r.z);
+              f[8 * j + 6] += bf16_bits_lo(r.w); f[8 * j + 7] += bf16_bits_hi(r.w);
+            }
+          }
           if (p.y_fp32) {
             float4* yp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + pix * p.y_cstride + n);
 #pragma unroll
@@ -235,9 +262,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (nn < p.Cout) {
               float x = f[j];
               if (p.bias) x += __ldg(p.bias + nn);
-              if (p.residual) x += __bfloat162float(p.residual[rpix * p.res_cstride + nn]);
+              if (res_pre) x += __bfloat162float(p.residual[rpix * p.res_cstride + nn]);
               if (p.relu) x = fmaxf(x, 0.f);
               if (p.mask) x = __bfloat162float(p.mask[pix * p.mask_cstride + nn]) > 0.f ? x : 0.f;
+              if (res_post) x += __bfloat162float(p.residual[rpix * p.res_cstride + nn]);
               if (p.y_fp32) reinterpret_cast<float*>(p.y)[pix * p.y_cstride + nn] = x;
               else reinterpret_cast<bf16*>(p.y)[pix * p.y_cstride + nn] = __float2bfloat16_rn(x);
             }
@@ -264,11 +292,13 @@ struct WgradArgs {
   int tiles_w, tiles_h, tiles_b, pix_tiles;  // pix_tiles = tiles_w*tiles_h*tiles_b
   int tiles_m, tiles_n;                      // over Cout (128) and Cin (BN)
   int BN;                                    // 64 or 128 (input-channel tile)
-  int splits, tiles_per_split;
-  int num_items;                             // tiles_m*tiles_n*taps*splits
+  int groups, tiles_per_group;               // independent pixel groups (1, or B for per-image outputs)
+  int splits, tiles_per_split;               // K-splits inside a group
+  int num_items;                             // tiles_m*tiles_n*taps*groups*splits
   int stages;
   uint32_t tmem_cols;
   float* dw;
+  long long dw_group_stride;
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -312,22 +342,24 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(holder));
 
   // work item -> (m tile, n tile, tap, split); n fastest so neighbouring CTAs share the dY tiles in L2
-  auto decode = [&](int item, int& mt, int& nt, int& tap, int& pt_begin, int& pt_end) {
+  auto decode = [&](int item, int& mt, int& nt, int& tap, int& grp, int& pt_begin, int& pt_end) {
     int t = item;
     nt = t % p.tiles_n; t /= p.tiles_n;
     tap = t % p.taps; t /= p.taps;
     mt = t % p.tiles_m; t /= p.tiles_m;
-    const int sp = t;
-    pt_begin = sp * p.tiles_per_split;
-    pt_end = min(pt_begin + p.tiles_per_split, p.pix_tiles);
+    const int sp = t % p.splits; t /= p.splits;
+    grp = t;
+    const int g0 = grp * p.tiles_per_group;
+    pt_begin = g0 + sp * p.tiles_per_split;
+    pt_end = min(pt_begin + p.tiles_per_split, g0 + p.tiles_per_group);
   };
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        int mt, nt, tap, pb, pe;
-        decode(item, mt, nt, tap, pb, pe);
+        int mt, nt, tap, grp, pb, pe;
+        decode(item, mt, nt, tap, grp, pb, pe);
         const int dh = tap / p.KW - p.pad_h, dw = tap % p.KW - p.pad_w;
         for (int pt = pb; pt < pe; ++pt, ++it) {
           int t = pt;
@@ -352,8 +384,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       const uint32_t idesc = make_idesc_bf16(kTileM, p.BN, 1, 1);  // both operands MN-major
       uint32_t it = 0, tcount = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++tcount) {
-        int mt, nt, tap, pb, pe;
-        decode(item, mt, nt, tap, pb, pe);
+        int mt, nt, tap, grp, pb, pe;
+        decode(item, mt, nt, tap, grp, pb, pe);
         const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(tempty_bar(a), aph ^ 1);
         tc_fence_after();
@@ -382,14 +414,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     const int row = q * 32 + lane;
     uint32_t tcount = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++tcount) {
-      int mt, nt, tap, pb, pe;
-      decode(item, mt, nt, tap, pb, pe);
+      int mt, nt, tap, grp, pb, pe;
+      decode(item, mt, nt, tap, grp, pb, pe);
       const int co = mt * 128 + row;
       const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + a * p.BN;
-      float* dst = p.dw + ((long long)co * p.taps + tap) * p.Cin;
+      float* dst = p.dw + grp * p.dw_group_stride + ((long long)co * p.taps + tap) * p.Cin;
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         uint32_t v[16];
         __syncwarp();
@@ -454,6 +486,9 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   SGB_REQUIRE(d->Cin % 8 == 0 && d->x_cstride % 8 == 0 && d->x_cstride >= d->Cin);
   SGB_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->w & 15) == 0 && ((uintptr_t)d->y & 15) == 0);
   SGB_REQUIRE(!d->res_up2 || (d->H % 2 == 0 && d->W % 2 == 0));
+  SGB_REQUIRE(d->w_mode >= 0 && d->w_mode <= 2);
+  SGB_REQUIRE(d->w_mode == 0 || (d->KH == 1 && d->KW == 1 && d->H * d->W >= 128));
+  SGB_REQUIRE(d->w_mode != 2 || d->Cout % 8 == 0);
   SGB_REQUIRE(((uintptr_t)d->bias & 15) == 0 && ((uintptr_t)d->residual & 15) == 0 && ((uintptr_t)d->mask & 15) == 0);
 
   FpropArgs p;
@@ -474,7 +509,9 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
     long long tiles256 = (long long)p.tiles_w * p.tiles_h * p.tiles_b * ((d->Cout + 255) / 256);
     if (BN == 256 && tiles256 < 2LL * sm_count()) BN = 128;
   }
+  if (d->w_mode == 2 && BN < 64) BN = 64;  // MN-major B is staged in 64-wide atoms
   p.BN = BN;
+  p.w_mode = d->w_mode;
   p.tiles_n = (d->Cout + BN - 1) / BN;
   p.num_tiles = p.tiles_n * p.tiles_w * p.tiles_h * p.tiles_b;
   p.kblocks = (d->Cin + kBlockK - 1) / kBlockK;
@@ -485,8 +522,10 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * BN);
   p.alpha = d->alpha;
+  p.alpha_ptr = d->alpha_ptr;
   p.bias = d->bias;
   p.residual = (const bf16*)d->residual; p.res_cstride = d->res_cstride; p.res_up2 = d->res_up2;
+  p.res_after = d->res_after_mask;
   p.mask = (const bf16*)d->mask; p.mask_cstride = d->mask_cstride;
   p.relu = d->relu;
   p.y = d->y; p.y_cstride = d->y_cstride; p.y_fp32 = d->y_fp32;
@@ -494,13 +533,23 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   CUtensorMap tmA, tmB;
   int rc = make_act_tmap(&tmA, d->x, d->B, d->H, d->W, d->Cin, d->x_cstride, p.tw, p.th, p.nb);
   if (rc) return rc;
-  {
+  if (d->w_mode == 0) {
     uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)p.taps, (uint64_t)d->Cout};
     uint64_t strides[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cin * 2 * p.taps};
     uint32_t box[3] = {64, 1, (uint32_t)BN};
     rc = make_tmap_bf16(&tmB, d->w, 3, dims, strides, box);
-    if (rc) return rc;
+  } else if (d->w_mode == 1) {  // per-image [B][N = Cout][K = Cin]
+    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->B, (uint64_t)d->Cout};
+    uint64_t strides[2] = {(uint64_t)d->Cin * 2 * d->Cout, (uint64_t)d->Cin * 2};
+    uint32_t box[3] = {64, 1, (uint32_t)BN};
+    rc = make_tmap_bf16(&tmB, d->w, 3, dims, strides, box);
+  } else {                      // per-image [B][K = Cin][N = Cout], N contiguous
+    uint64_t dims[3] = {(uint64_t)d->Cout, (uint64_t)d->Cin, (uint64_t)d->B};
+    uint64_t strides[2] = {(uint64_t)d->Cout * 2, (uint64_t)d->Cout * 2 * d->Cin};
+    uint32_t box[3] = {64, 64, 1};
+    rc = make_tmap_bf16(&tmB, d->w, 3, dims, strides, box);
   }
+  if (rc) return rc;
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 4) + 16;
   static size_t smem_set = 0;
   if (smem > smem_set) {
@@ -531,12 +580,16 @@ extern "C" int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream_) {
   p.BN = (d->Cin <= 64) ? 64 : 128;
   p.tiles_m = (d->Cout + 127) / 128;
   p.tiles_n = (d->Cin + p.BN - 1) / p.BN;
-  const int base_items = p.tiles_m * p.tiles_n * p.taps;
+  p.groups = d->per_image ? d->B : 1;
+  SGB_REQUIRE(!d->per_image || (p.nb == 1));
+  p.tiles_per_group = p.pix_tiles / p.groups;
+  p.dw_group_stride = (long long)d->Cout * p.taps * d->Cin;
+  const int base_items = p.tiles_m * p.tiles_n * p.taps * p.groups;
   int splits = (2 * sm_count() + base_items - 1) / base_items;
-  if (splits > p.pix_tiles) splits = p.pix_tiles;
+  if (splits > p.tiles_per_group) splits = p.tiles_per_group;
   if (splits < 1) splits = 1;
-  p.tiles_per_split = (p.pix_tiles + splits - 1) / splits;
-  p.splits = (p.pix_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.tiles_per_split = (p.tiles_per_group + splits - 1) / splits;
+  p.splits = (p.tiles_per_group + p.tiles_per_split - 1) / p.tiles_per_split;
   p.num_items = base_items * p.splits;
   const uint32_t stage_bytes = 2 * kABytes + (p.BN / 64) * kABytes;
   int stages = (int)((200 * 1024) / stage_bytes);
@@ -546,7 +599,7 @@ extern "C" int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream_) {
   p.dw = d->dw;
 
   if (!d->accumulate)
-    SGB_CUDA(cudaMemsetAsync(d->dw, 0, sizeof(float) * (size_t)d->Cout * p.taps * d->Cin, stream));
+    SGB_CUDA(cudaMemsetAsync(d->dw, 0, sizeof(float) * (size_t)d->Cout * p.taps * d->Cin * (d->per_image ? d->B : 1), stream));
 
   CUtensorMap tmDY, tmX;
   int rc = make_act_tmap(&tmDY, d->dy, d->B, d->H, d->W, d->Cout, d->dy_cstride, p.tw, p.th, p.nb);

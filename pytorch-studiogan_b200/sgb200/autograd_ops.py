@@ -1,0 +1,460 @@
+"""torch.autograd.Function wrappers: the forward/backward of every hot-path op is a sequence of libsgb200 calls.
+
+Conventions
+* activations: NHWC-in-memory bf16 tensors of logical shape [B, C, H, W] (see kernels.py)
+* "premasked" protocol for ReLU chains in the discriminators: a conv with ``relu=True`` stores its post-ReLU
+  output; whoever consumes that output is responsible for delivering a gradient already masked by (output > 0)
+  (the consumer's dgrad epilogue does it for free via ``mask_input=True``).  That gradient is therefore the
+  gradient w.r.t. the pre-activation and is used as is.
+"""
+import torch
+import torch.distributed as dist
+from torch.autograd import Function
+
+from . import kernels as K
+
+bf16 = torch.bfloat16
+
+
+class SpectralNormState:
+    """u / v buffers + workspace of one spectrally-normalised weight (torch/nn/utils/spectral_norm.py semantics)."""
+
+    def __init__(self, module, eps):
+        self.module = module
+        self.eps = eps
+        self.ws = None
+
+    def tensors(self):
+        m = self.module
+        W = m.weight_orig
+        if self.ws is None or self.ws.device != W.device:
+            R = W.shape[0]
+            self.ws = K.sn_workspace(R, W.numel() // R, W.device)
+        return m.weight_u, m.weight_v, self.ws
+
+
+def _grad_bf16(dy):
+    """Incoming gradient as NHWC bf16 (fp32 grads appear only on the tiny [B,C,1,1] cBN gain/bias branches)."""
+    if dy.dtype == torch.float32:
+        B, C, H, W = dy.shape
+        out = K.empty_nhwc(B, C, H, W, dy.device)
+        if H * W == 1:
+            K.cast_f32_to_bf16(dy.contiguous(), out=out)
+        else:
+            K.cast_f32_to_bf16(dy.permute(0, 2, 3, 1).contiguous(), out=out)
+        return out
+    return K.as_nhwc(dy)
+
+
+class ConvFn(Function):
+    """y = [relu](conv(x, W / sigma) + bias [+ residual])  — conv2d (stride 1) or linear (H = W = 1).
+
+    cfg keys: KH, KW, pad, relu, premasked, mask_input, res_up2, res_channels, out_fp32, perm_S, sn (SpectralNormState|None),
+    do_power_iteration.
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, cfg):
+        KH, KW, pad = cfg["KH"], cfg["KW"], cfg["pad"]
+        Cout = weight.shape[0]
+        Cin = weight.numel() // (Cout * KH * KW)
+        taps = KH * KW
+        sn = cfg.get("sn")
+        sigma = u_saved = v_saved = None
+        if sn is not None:
+            u, v, ws = sn.tensors()
+            sigma = torch.empty(1, device=weight.device, dtype=torch.float32)
+            K.sn_power_iter(weight, u, v, sigma, ws, sn.eps, cfg.get("do_power_iteration", True))
+        need_dx = ctx.needs_input_grad[0]
+        need_dw = ctx.needs_input_grad[1]
+        wf, wd = K.weight_pack(weight, sigma, Cout, Cin, taps, True, need_dx, cfg.get("perm_S", 1))
+        Cout_p = K.pad8(Cout)
+        res = residual
+        y = K.conv_fprop(x, wf, Cout_p, KH, KW, pad, pad, bias=bias if Cout_p == Cout else _pad_bias(bias, Cout_p),
+                         residual=res, res_up2=cfg.get("res_up2", False), relu=cfg.get("relu", False),
+                         out_fp32=cfg.get("out_fp32", False))
+        if need_dw and sn is not None:
+            u_saved, v_saved = u.clone(), v.clone()
+        ctx.cfg = cfg
+        ctx.dims = (Cout, Cin, taps)
+        ctx.has_res = residual is not None
+        ctx.res_shape = residual.shape if residual is not None else None
+        ctx.save_for_backward(x, weight, wd, sigma, u_saved, v_saved, y if cfg.get("relu", False) else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, wd, sigma, u_saved, v_saved, y = ctx.saved_tensors
+        cfg = ctx.cfg
+        KH, KW, pad = cfg["KH"], cfg["KW"], cfg["pad"]
+        Cout, Cin, taps = ctx.dims
+        dz = _grad_bf16(dy)
+        if cfg.get("relu", False) and not cfg.get("premasked", False):
+            dz = K.axpby(dz, mask=y)
+        dx = dW = dbias = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = K.conv_fprop(dz, wd, K.pad8(Cin), KH, KW, KH - 1 - pad, KW - 1 - pad,
+                              mask=x if cfg.get("mask_input", False) else None)
+            if dx.shape[1] != x.shape[1]:
+                dx = dx[:, :x.shape[1]]
+        if ctx.needs_input_grad[1]:
+            G = K.conv_wgrad(x, dz, KH, KW, pad, pad)
+            dW = K.sn_backward(G, weight, u_saved, v_saved, sigma, Cout, Cin, taps, cfg.get("perm_S", 1))
+        if ctx.needs_input_grad[2]:
+            dbias = K.bn_stats(dz)[0][:Cout]
+        if ctx.has_res and ctx.needs_input_grad[3]:
+            dres = K.pool2_fwd(dz, 2) if cfg.get("res_up2", False) else dz
+            rc = ctx.res_shape[1]
+            if dres.shape[1] != rc:  # residual was read from the first Cout channels of a wider tensor
+                full = K.zeros_nhwc(dres.shape[0], rc, dres.shape[2], dres.shape[3], dres.device)
+                K.axpby(dres, out=full[:, :dres.shape[1]])
+                dres = full
+        return dx, dW, dbias, dres, None
+
+
+def _pad_bias(bias, Cout_p):
+    if bias is None:
+        return None
+    out = torch.zeros(Cout_p, device=bias.device, dtype=torch.float32)
+    out[:bias.numel()] = bias
+    return out
+
+
+class BNActFn(Function):
+    """y = [relu](batch_norm(x) * g + b) with g/b per image (cBN), per channel (affine) or absent; optional nearest x2
+    upsample of the result.  cfg keys: mode (0 cBN, 1 affine, 2 plain), relu, up2, use_batch_stats, track, momentum, eps, group.
+    """
+
+    @staticmethod
+    def forward(ctx, x, gain, bias, running_mean, running_var, cfg):
+        B, C, H, W, _ = K.geom(x)
+        mode = cfg["mode"]
+        stats = None
+        count = float(B * H * W)
+        group = cfg.get("group")
+        if cfg["use_batch_stats"]:
+            stats = K.bn_stats(x)
+            if group is not None:
+                dist.all_reduce(stats, group=group)
+                count *= dist.get_world_size(group)
+        nb = B if mode == 0 else 1
+        g = gain.reshape(nb, C) if gain is not None else None
+        b = bias.reshape(nb, C) if bias is not None else None
+        if g is not None and not g.is_contiguous():
+            g = g.contiguous()
+        if b is not None and not b.is_contiguous():
+            b = b.contiguous()
+        mean, rstd, scale, shift = K.bn_finalize(stats, count, running_mean, running_var, cfg["momentum"], cfg["eps"],
+                                                 cfg["use_batch_stats"], cfg["track"], mode, g, b, nb, C, x.device)
+        y = K.scale_shift_act(x, scale, shift, mode == 0, cfg["relu"], cfg["up2"])
+        ctx.cfg = cfg
+        ctx.count = count
+        ctx.gshape = gain.shape if gain is not None else None
+        ctx.bshape = bias.shape if bias is not None else None
+        ctx.save_for_backward(x, scale, shift, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, scale, shift, mean, rstd = ctx.saved_tensors
+        cfg = ctx.cfg
+        mode = cfg["mode"]
+        dy = K.as_nhwc(dy)
+        s12, S12 = K.bn_bwd_reduce(dy, x, scale, shift, mode == 0, mean, rstd, cfg["relu"], cfg["up2"])
+        group = cfg.get("group")
+        if cfg["use_batch_stats"] and group is not None:
+            dist.all_reduce(S12, group=group)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = K.bn_bwd_apply(dy, x, scale, shift, mode == 0, mean, rstd, S12, ctx.count, cfg["relu"], cfg["up2"],
+                                cfg["use_batch_stats"])
+        dgain = dbias = None
+        if mode == 0:
+            if ctx.needs_input_grad[1]:
+                dgain = s12[1].reshape(ctx.gshape)
+            if ctx.needs_input_grad[2]:
+                dbias = s12[0].reshape(ctx.bshape)
+        elif mode == 1:
+            if ctx.needs_input_grad[1]:
+                dgain = s12[1].sum(0).reshape(ctx.gshape)
+            if ctx.needs_input_grad[2]:
+                dbias = s12[0].sum(0).reshape(ctx.bshape)
+        return dx, dgain, dbias, None, None, None
+
+
+class SplitResidualFn(Function):
+    """x -> (x, x[:, :c]): main branch and channel-drop skip branch of a generator block
+    (src/models/big_resnet_deep_legacy.py:50-53).  Backward adds the narrower skip gradient into the first channels of
+    the main gradient in place."""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        return x.view_as(x), x[:, :c]
+
+    @staticmethod
+    def backward(ctx, d_main, d_res):
+        if d_res is None:
+            return d_main, None
+        if d_main is None:
+            raise RuntimeError("SplitResidualFn: skip gradient without a main-branch gradient")
+        d_main = K.as_nhwc(d_main)
+        d_res = K.as_nhwc(d_res)
+        c = d_res.shape[1]
+        tgt = d_main[:, :c]
+        K.axpby(tgt, d_res, out=tgt)
+        return d_main, None
+
+
+class DBlockEntryFn(Function):
+    """x -> (a0, skip_src) with a0 = relu(x) and skip_src = avgpool2(a0) | a0: the two consumers of a discriminator
+    block input (src/models/big_resnet_deep_legacy.py:211-224).  The reference's d_act_fn is nn.ReLU(inplace=True)
+    (src/config.py:486), which rectifies the aliased skip tensor ``x0`` as well, so the skip path carries relu(x).
+    Both incoming gradients refer to a0; the result is masked once by (a0 > 0)."""
+
+    @staticmethod
+    def forward(ctx, x, downsample):
+        a0 = K.axpby(x, relu=True)
+        px = K.pool2_fwd(a0, 0) if downsample else a0.view_as(a0)
+        ctx.downsample = downsample
+        ctx.save_for_backward(a0)
+        return a0, px
+
+    @staticmethod
+    def backward(ctx, da0, dpx):
+        (a0,) = ctx.saved_tensors
+        da0 = K.as_nhwc(da0) if da0 is not None else None
+        dpx = K.as_nhwc(dpx) if dpx is not None else None
+        if dpx is None:
+            return K.axpby(da0, mask=a0), None
+        if ctx.downsample:
+            return K.pool2_bwd(dpx, 0, add=da0, relu_src=a0), None
+        if da0 is None:
+            return K.axpby(dpx, mask=a0), None
+        return K.axpby(da0, dpx, mask=a0), None
+
+
+class AvgPoolFn(Function):
+    """2x2 average pooling; ``relu_src``: the input is a post-ReLU tensor and the gradient is returned premasked."""
+
+    @staticmethod
+    def forward(ctx, x, input_is_relu_out):
+        ctx.input_is_relu_out = input_is_relu_out
+        ctx.save_for_backward(x if input_is_relu_out else None)
+        return K.pool2_fwd(x, 0)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return K.pool2_bwd(K.as_nhwc(dy), 0, relu_src=x), None
+
+
+class ReluFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = K.axpby(x, relu=True)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return K.axpby(K.as_nhwc(dy), mask=y)
+
+
+class AddFn(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return K.axpby(a, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+class ConcatSkipFn(Function):
+    """skip = cat([px, conv1x1(px)], channel) written into one buffer (learnable shortcut of the BigGAN-Deep D block,
+    src/models/big_resnet_deep_legacy.py:225-226)."""
+
+    @staticmethod
+    def forward(ctx, px, weight, bias, cfg):
+        B, Cin, H, W, _ = K.geom(px)
+        Cextra = weight.shape[0]
+        sn = cfg.get("sn")
+        sigma = u_saved = v_saved = None
+        if sn is not None:
+            u, v, ws = sn.tensors()
+            sigma = torch.empty(1, device=weight.device, dtype=torch.float32)
+            K.sn_power_iter(weight, u, v, sigma, ws, sn.eps, cfg.get("do_power_iteration", True))
+        need_dx = ctx.needs_input_grad[0]
+        wf, wd = K.weight_pack(weight, sigma, Cextra, Cin, 1, True, need_dx)
+        skip = K.empty_nhwc(B, Cin + Cextra, H, W, px.device)
+        K.axpby(px, out=skip[:, :Cin])
+        K.conv_fprop(skip[:, :Cin], wf, Cextra, 1, 1, 0, 0, bias=bias, out=skip[:, Cin:])
+        if ctx.needs_input_grad[1] and sn is not None:
+            u_saved, v_saved = u.clone(), v.clone()
+        ctx.cfg = cfg
+        ctx.dims = (Cextra, Cin)
+        ctx.save_for_backward(px, weight, wd, sigma, u_saved, v_saved)
+        return skip
+
+    @staticmethod
+    def backward(ctx, dskip):
+        px, weight, wd, sigma, u_saved, v_saved = ctx.saved_tensors
+        Cextra, Cin = ctx.dims
+        dskip = K.as_nhwc(dskip)
+        d_lo, d_hi = dskip[:, :Cin], dskip[:, Cin:]
+        dpx = dW = dbias = None
+        if ctx.needs_input_grad[0]:
+            dpx = K.conv_fprop(d_hi, wd, Cin, 1, 1, 0, 0, residual=d_lo)
+        if ctx.needs_input_grad[1]:
+            G = K.conv_wgrad(px, d_hi, 1, 1, 0, 0)
+            dW = K.sn_backward(G, weight, u_saved, v_saved, sigma, Cextra, Cin, 1)
+        if ctx.needs_input_grad[2]:
+            dbias = K.bn_stats(d_hi)[0]
+        return dpx, dW, dbias, None
+
+
+class SumHWFn(Function):
+    """h[b, c] = sum_{h,w} relu(x) in fp32 (src/models/big_resnet_deep_legacy.py:344-345)."""
+
+    @staticmethod
+    def forward(ctx, x, relu):
+        ctx.relu = relu
+        ctx.save_for_backward(x)
+        return K.sum_hw(x, relu)
+
+    @staticmethod
+    def backward(ctx, dh):
+        (x,) = ctx.saved_tensors
+        return K.sum_hw_bwd(dh.contiguous(), x, ctx.relu), None
+
+
+class ToBF16Fn(Function):
+    """[B, K] fp32 -> [B, Kp, 1, 1] bf16 activation (input of the linear layers); K is zero-padded to a multiple of 8
+    (TMA stride granularity), e.g. the 10-way one-hot cBN input of ResNetGAN or BigGAN's 148-wide [embedding, z-chunk]."""
+
+    @staticmethod
+    def forward(ctx, x):
+        B, Kd = x.shape
+        Kp = K.pad8(Kd)
+        ctx.Kd = Kd
+        if Kp != Kd:
+            xp = torch.zeros((B, Kp), device=x.device, dtype=x.dtype)
+            xp[:, :Kd] = x
+            x = xp
+        out = torch.empty((B, Kp), device=x.device, dtype=bf16)
+        K.cast_f32_to_bf16(x.contiguous(), out=out)
+        return out.view(B, Kp, 1, 1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, Kp = dy.shape[0], dy.shape[1]
+        g = dy.reshape(B, Kp) if dy.dtype == torch.float32 else K.cast_bf16_to_f32(dy.reshape(B, Kp).contiguous())
+        return g[:, :ctx.Kd] if Kp != ctx.Kd else g
+
+
+class ImageInFn(Function):
+    """NCHW fp32 image in [-1, 1] -> NHWC bf16 activation with 8 (zero-padded) channels."""
+
+    @staticmethod
+    def forward(ctx, img):
+        ctx.C = img.shape[1]
+        return K.img_to_nhwc(img, 8)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.nhwc_to_img(K.as_nhwc(dy), ctx.C, tanh=False)
+
+
+class ImageOutFn(Function):
+    """NHWC activation (>= 3 channels) -> tanh -> NCHW fp32 image (nn.Tanh at big_resnet_deep_legacy.py:183)."""
+
+    @staticmethod
+    def forward(ctx, x, C):
+        img = K.nhwc_to_img(x, C, tanh=True)
+        ctx.Cp = x.shape[1]
+        ctx.save_for_backward(img)
+        return img
+
+    @staticmethod
+    def backward(ctx, dimg):
+        (img,) = ctx.saved_tensors
+        return K.img_grad_to_nhwc(dimg, img, ctx.Cp), None
+
+
+class SelfAttentionFn(Function):
+    """ops.SelfAttention.forward (src/utils/ops.py:83-103) with the attention map materialised in bf16:
+       theta = conv(x), phi = maxpool(conv(x)), g = maxpool(conv(x)); P = softmax(theta . phi^T); o = P . g;
+       out = x + sigma * conv(o).  All contractions run on the tcgen05 engine (batched modes 1/2)."""
+
+    @staticmethod
+    def forward(ctx, x, w_theta, w_phi, w_g, w_o, sigma, cfgs):
+        B, C, H, W, _ = K.geom(x)
+        c8, c2 = C // 8, C // 2
+        N, M = H * W, (H // 2) * (W // 2)
+        packs = []
+        sn_saved = []
+        for w, cfg, cin, cout in ((w_theta, cfgs[0], C, c8), (w_phi, cfgs[1], C, c8), (w_g, cfgs[2], C, c2), (w_o, cfgs[3], c2, C)):
+            sn = cfg.get("sn")
+            sg = None
+            us = vs = None
+            if sn is not None:
+                u, v, ws = sn.tensors()
+                sg = torch.empty(1, device=w.device, dtype=torch.float32)
+                K.sn_power_iter(w, u, v, sg, ws, sn.eps, cfg.get("do_power_iteration", True))
+                us, vs = u.clone(), v.clone()
+            wf, wd = K.weight_pack(w, sg, cout, cin, 1, True, True)
+            packs.append((wf, wd))
+            sn_saved.append((sg, us, vs))
+        theta = K.conv_fprop(x, packs[0][0], c8, 1, 1, 0, 0)                      # [B, c8, H, W]
+        phi_f = K.conv_fprop(x, packs[1][0], c8, 1, 1, 0, 0)
+        g_f = K.conv_fprop(x, packs[2][0], c2, 1, 1, 0, 0)
+        phi = K.pool2_fwd(phi_f, 1)                                               # [B, c8, H/2, W/2]  keys  [M][c8]
+        g = K.pool2_fwd(g_f, 1)                                                   # [B, c2, H/2, W/2]  values [M][c2]
+        S = K.conv_fprop(theta, phi, M, 1, 1, 0, 0, w_mode=1)                     # [B, M, H, W] == [B][N][M]
+        K.softmax_rows(S, M, out=S)                                               # P in place
+        o = K.conv_fprop(S, g, c2, 1, 1, 0, 0, w_mode=2)                          # [B, c2, H, W]
+        t = K.conv_fprop(o, packs[3][0], C, 1, 1, 0, 0)                           # conv1x1_attn
+        out = K.axpby(t, x, a=1.0, a_dev=sigma, b=1.0)
+        ctx.dims = (B, C, H, W, c8, c2, N, M)
+        ctx.sn_saved = sn_saved
+        ctx.packs = packs
+        ctx.save_for_backward(x, theta, phi_f, phi, g_f, g, S, o, t, sigma, w_theta, w_phi, w_g, w_o)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, theta, phi_f, phi, g_f, g, P, o, t, sigma, w_theta, w_phi, w_g, w_o = ctx.saved_tensors
+        B, C, H, W, c8, c2, N, M = ctx.dims
+        packs, sn_saved = ctx.packs, ctx.sn_saved
+        dout = K.as_nhwc(dout)
+        dsigma = K.dot(dout, t).reshape(sigma.shape)
+        dt = K.axpby(dout, a=1.0, a_dev=sigma)
+        # conv1x1_attn
+        do = K.conv_fprop(dt, packs[3][1], c2, 1, 1, 0, 0)
+        G_o = K.conv_wgrad(o, dt, 1, 1, 0, 0)
+        # o = P . g   ->  dP = do . g^T (keys as output channels), dg = P^T . do (per image)
+        dP = K.conv_fprop(do, g, M, 1, 1, 0, 0, w_mode=1)                         # g as [B][M][c2] K-major operand
+        dg_pool = K.conv_wgrad(do, P, 1, 1, 0, 0, per_image=True)                 # [B][M][1][c2] fp32
+        dS = K.softmax_bwd_rows(P, dP, M, out=dP)
+        # S = theta . phi^T -> dtheta = dS . phi (phi as [B][K=M][N=c8] MN-major), dphi = dS^T . theta (per image)
+        dtheta = K.conv_fprop(dS, phi, c8, 1, 1, 0, 0, w_mode=2)
+        dphi_pool = K.conv_wgrad(theta, dS, 1, 1, 0, 0, per_image=True)           # [B][M][1][c8] fp32
+        dphi_p = K.cast_f32_to_bf16(dphi_pool.view(B, H // 2, W // 2, c8)).permute(0, 3, 1, 2)
+        dg_p = K.cast_f32_to_bf16(dg_pool.view(B, H // 2, W // 2, c2)).permute(0, 3, 1, 2)
+        dphi_f = K.pool2_bwd(dphi_p, 1, x=phi_f)
+        dg_f = K.pool2_bwd(dg_p, 1, x=g_f)
+        # the three input 1x1 convs: dx = dout + dgrads (chained through the residual epilogue)
+        dx = K.conv_fprop(dtheta, packs[0][1], C, 1, 1, 0, 0, residual=dout)
+        dx = K.conv_fprop(dphi_f, packs[1][1], C, 1, 1, 0, 0, residual=dx)
+        dx = K.conv_fprop(dg_f, packs[2][1], C, 1, 1, 0, 0, residual=dx)
+        grads_w = []
+        for (w, xin, dyv, cout, cin, idx) in ((w_theta, x, dtheta, c8, C, 0), (w_phi, x, dphi_f, c8, C, 1), (w_g, x, dg_f, c2, C, 2),
+                                              (w_o, o, None, C, c2, 3)):
+            if not ctx.needs_input_grad[1 + idx]:
+                grads_w.append(None)
+                continue
+            G = G_o if idx == 3 else K.conv_wgrad(xin, dyv, 1, 1, 0, 0)
+            sg, us, vs = sn_saved[idx]
+            grads_w.append(K.sn_backward(G, w, us, vs, sg, cout, cin, 1))
+        return dx, grads_w[0], grads_w[1], grads_w[2], grads_w[3], dsigma, None

@@ -1,0 +1,293 @@
+"""Tensor-level wrappers over the C ABI (no autograd here; see autograd_ops.py).
+
+Activation convention: a torch tensor of logical shape [B, C, H, W], dtype bfloat16, whose memory is NHWC
+(stride(1) == 1).  Channel slices ``x[:, a:b]`` stay valid (channel stride > C).  Everything runs on the
+current CUDA stream of the tensor's device.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+bf16 = torch.bfloat16
+
+
+def empty_nhwc(B, C, H, W, device, dtype=bf16):
+    return torch.empty((B, H, W, C), device=device, dtype=dtype).permute(0, 3, 1, 2)
+
+
+def zeros_nhwc(B, C, H, W, device, dtype=bf16):
+    return torch.zeros((B, H, W, C), device=device, dtype=dtype).permute(0, 3, 1, 2)
+
+
+def geom(x):
+    """(B, C, H, W, channel_stride) of an NHWC-in-memory activation; raises on any other layout."""
+    B, C, H, W = x.shape
+    sb, sc, sh, sw = x.stride()
+    if C > 1 and sc != 1:
+        raise RuntimeError("sgb200: activation is not NHWC in memory (strides %s)" % (x.stride(),))
+    cs = sw if W > 1 else (sh if H > 1 else sb)
+    if W > 1 and H > 1 and sh != W * cs:
+        raise RuntimeError("sgb200: unexpected row stride %s" % (x.stride(),))
+    if B > 1 and sb != H * W * cs:
+        raise RuntimeError("sgb200: unexpected batch stride %s" % (x.stride(),))
+    return B, C, H, W, cs
+
+
+def as_nhwc(x):
+    """Return x if it already is NHWC-in-memory bf16, otherwise re-layout through the library (rare guard path)."""
+    try:
+        if x.dtype == bf16:
+            geom(x)
+            return x
+    except RuntimeError:
+        pass
+    B, C, H, W = x.shape
+    out = empty_nhwc(B, C, H, W, x.device)
+    out.copy_(x)  # layout guard only; never hit on the model paths (asserted in tests)
+    return out
+
+
+def _s():
+    return L.stream_ptr()
+
+
+# ---------------------------------------------------------------------------------------------- conv engine
+def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_up2=False, res_after_mask=False,
+               mask=None, relu=False, alpha=1.0, alpha_ptr=None, out=None, out_fp32=False, w_mode=0):
+    """y = epilogue(conv(x, w)); see sgb_conv_fprop. ``w`` is a packed bf16 weight (layout by w_mode)."""
+    B, Cin, H, W, xcs = geom(x)
+    if out is None:
+        out = empty_nhwc(B, Cout, H, W, x.device, torch.float32 if out_fp32 else bf16)
+    _, _, _, _, ycs = geom(out)
+    d = L.ConvDesc()
+    d.B, d.H, d.W, d.Cin, d.Cout = B, H, W, Cin, Cout
+    d.KH, d.KW, d.pad_h, d.pad_w = KH, KW, pad_h, pad_w
+    d.x, d.x_cstride = x.data_ptr(), xcs
+    d.w, d.w_mode = w.data_ptr(), w_mode
+    d.alpha = alpha
+    d.alpha_ptr = alpha_ptr.data_ptr() if alpha_ptr is not None else None
+    d.bias = bias.data_ptr() if bias is not None else None
+    if residual is not None:
+        d.residual, d.res_cstride = residual.data_ptr(), geom(residual)[4]
+    d.res_up2 = 1 if res_up2 else 0
+    d.res_after_mask = 1 if res_after_mask else 0
+    if mask is not None:
+        d.mask, d.mask_cstride = mask.data_ptr(), geom(mask)[4]
+    d.relu = 1 if relu else 0
+    d.y, d.y_cstride, d.y_fp32 = out.data_ptr(), ycs, 1 if out.dtype == torch.float32 else 0
+    L.call("sgb_conv_fprop", ctypes.byref(d), _s())
+    return out
+
+
+def conv_wgrad(x, dy, KH, KW, pad_h, pad_w, dw=None, accumulate=False, per_image=False):
+    """fp32 weight gradient in the fprop-pack layout [Cout][KH*KW][Cin] (or [B][...] when per_image)."""
+    B, Cin, H, W, xcs = geom(x)
+    _, Cout, _, _, dcs = geom(dy)
+    if dw is None:
+        shape = (B, Cout, KH * KW, Cin) if per_image else (Cout, KH * KW, Cin)
+        dw = torch.empty(shape, device=x.device, dtype=torch.float32)
+        accumulate = False
+    d = L.WgradDesc()
+    d.B, d.H, d.W, d.Cin, d.Cout = B, H, W, Cin, Cout
+    d.KH, d.KW, d.pad_h, d.pad_w = KH, KW, pad_h, pad_w
+    d.x, d.x_cstride = x.data_ptr(), xcs
+    d.dy, d.dy_cstride = dy.data_ptr(), dcs
+    d.dw, d.accumulate, d.per_image = dw.data_ptr(), 1 if accumulate else 0, 1 if per_image else 0
+    L.call("sgb_conv_wgrad", ctypes.byref(d), _s())
+    return dw
+
+
+# ---------------------------------------------------------------------------------------------- spectral norm
+def sn_workspace(R, K, device):
+    n = L.load().sgb_sn_workspace_floats(R, K)
+    return torch.zeros(n, device=device, dtype=torch.float32)
+
+
+def sn_power_iter(W, u, v, sigma, ws, eps, do_power_iteration):
+    R = W.shape[0]
+    K = W.numel() // R
+    L.call("sgb_sn_power_iter", L.ptr(W), L.ptr(u), L.ptr(v), L.ptr(sigma), L.ptr(ws), R, K, eps,
+           1 if do_power_iteration else 0, _s())
+
+
+def pad8(c):
+    return (c + 7) // 8 * 8
+
+
+def weight_pack(W, sigma, Cout, Cin, taps, want_fprop=True, want_dgrad=True, perm_S=1):
+    """bf16 packs of W/sigma; channel extents are zero-padded to multiples of 8 (TMA stride granularity)."""
+    Cout_p, Cin_p = pad8(Cout), pad8(Cin)
+    alloc = torch.zeros if (Cout_p != Cout or Cin_p != Cin) else torch.empty
+    wf = alloc((Cout_p, taps, Cin_p), device=W.device, dtype=bf16) if want_fprop else None
+    wd = alloc((Cin_p, taps, Cout_p), device=W.device, dtype=bf16) if want_dgrad else None
+    L.call("sgb_weight_pack", L.ptr(W), L.ptr(sigma), L.ptr(wf), L.ptr(wd), Cout, Cin, taps, perm_S, Cout_p, Cin_p, _s())
+    return wf, wd
+
+
+def sn_backward(G, W, u, v, sigma, Cout, Cin, taps, perm_S=1):
+    """G: fp32 [Cout_p][taps][Cin_p] from conv_wgrad -> dL/dW in the module's [Cout][Cin][taps] layout."""
+    dW = torch.empty_like(W)
+    scratch = torch.empty(1, device=W.device, dtype=torch.float32) if sigma is not None else None
+    L.call("sgb_sn_backward", L.ptr(G), L.ptr(W), L.ptr(u), L.ptr(v), L.ptr(sigma), L.ptr(scratch), L.ptr(dW), Cout, Cin, taps,
+           perm_S, pad8(Cin), 0, _s())
+    return dW
+
+
+# ---------------------------------------------------------------------------------------------- batch norm
+def bn_stats(x):
+    B, C, H, W, cs = geom(x)
+    s = torch.empty((2, C), device=x.device, dtype=torch.float32)
+    L.call("sgb_bn_stats", L.ptr(x), B * H * W, C, cs, L.ptr(s[0]), L.ptr(s[1]), _s())
+    return s
+
+
+def bn_finalize(stats, count, running_mean, running_var, momentum, eps, use_batch_stats, track, mode, gain, bias, nb, C,
+                device):
+    mean = torch.empty(C, device=device, dtype=torch.float32)
+    rstd = torch.empty(C, device=device, dtype=torch.float32)
+    scale = torch.empty((nb, C), device=device, dtype=torch.float32)
+    shift = torch.empty((nb, C), device=device, dtype=torch.float32)
+    L.call("sgb_bn_finalize", L.ptr(stats[0]) if stats is not None else None, L.ptr(stats[1]) if stats is not None else None,
+           float(count), L.ptr(running_mean), L.ptr(running_var), float(momentum), float(eps), 1 if use_batch_stats else 0,
+           1 if track else 0, mode, L.ptr(gain), L.ptr(bias), nb, C, L.ptr(mean), L.ptr(rstd), L.ptr(scale), L.ptr(shift), _s())
+    return mean, rstd, scale, shift
+
+
+def scale_shift_act(x, scale, shift, per_image, relu, up2):
+    B, C, H, W, cs = geom(x)
+    y = empty_nhwc(B, C, 2 * H if up2 else H, 2 * W if up2 else W, x.device)
+    L.call("sgb_scale_shift_act", L.ptr(x), B, H, W, C, cs, L.ptr(scale), L.ptr(shift), 1 if per_image else 0, 1 if relu else 0,
+           1 if up2 else 0, L.ptr(y), geom(y)[4], _s())
+    return y
+
+
+def bn_bwd_reduce(dy, x, scale, shift, per_image, mean, rstd, relu, up2):
+    B, C, H, W, cs = geom(x)
+    s12 = torch.empty((2, B, C), device=x.device, dtype=torch.float32)
+    S12 = torch.empty((2, C), device=x.device, dtype=torch.float32)
+    L.call("sgb_bn_bwd_reduce", L.ptr(dy), geom(dy)[4], L.ptr(x), cs, B, H, W, C, L.ptr(scale), L.ptr(shift),
+           1 if per_image else 0, L.ptr(mean), L.ptr(rstd), 1 if relu else 0, 1 if up2 else 0, L.ptr(s12[0]), L.ptr(s12[1]),
+           L.ptr(S12[0]), L.ptr(S12[1]), _s())
+    return s12, S12
+
+
+def bn_bwd_apply(dy, x, scale, shift, per_image, mean, rstd, S12, count, relu, up2, use_batch_stats):
+    B, C, H, W, cs = geom(x)
+    dx = empty_nhwc(B, C, H, W, x.device)
+    L.call("sgb_bn_bwd_apply", L.ptr(dy), geom(dy)[4], L.ptr(x), cs, B, H, W, C, L.ptr(scale), L.ptr(shift),
+           1 if per_image else 0, L.ptr(mean), L.ptr(rstd), L.ptr(S12[0]) if S12 is not None else None,
+           L.ptr(S12[1]) if S12 is not None else None, float(count), 1 if relu else 0, 1 if up2 else 0,
+           1 if use_batch_stats else 0, L.ptr(dx), geom(dx)[4], _s())
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------- element-wise
+def axpby(x, y=None, a=1.0, b=1.0, a_dev=None, mask=None, relu=False, out=None):
+    B, C, H, W, xs = geom(x)
+    if out is None:
+        out = empty_nhwc(B, C, H, W, x.device)
+    L.call("sgb_axpby", L.ptr(x), xs, L.ptr(y), geom(y)[4] if y is not None else 0, L.ptr(mask),
+           geom(mask)[4] if mask is not None else 0, L.ptr(out), geom(out)[4], B * H * W, C, float(a), L.ptr(a_dev), float(b),
+           1 if relu else 0, _s())
+    return out
+
+
+def pool2_fwd(x, mode, out=None):
+    """mode 0 average, 1 max (2x2, stride 2)."""
+    B, C, H, W, xs = geom(x)
+    if out is None:
+        out = empty_nhwc(B, C, H // 2, W // 2, x.device)
+    L.call("sgb_pool2_fwd", L.ptr(x), xs, L.ptr(out), geom(out)[4], B, H // 2, W // 2, C, mode, _s())
+    return out
+
+
+def pool2_bwd(dy, mode, x=None, add=None, relu_src=None):
+    B, C, Ho, Wo, dys = geom(dy)
+    dx = empty_nhwc(B, C, 2 * Ho, 2 * Wo, dy.device)
+    L.call("sgb_pool2_bwd", L.ptr(dy), dys, L.ptr(x), geom(x)[4] if x is not None else 0, L.ptr(add),
+           geom(add)[4] if add is not None else 0, L.ptr(relu_src), geom(relu_src)[4] if relu_src is not None else 0, L.ptr(dx),
+           geom(dx)[4], B, Ho, Wo, C, mode, _s())
+    return dx
+
+
+def softmax_rows(s, n, out=None):
+    if out is None:
+        out = torch.empty_like(s)
+    L.call("sgb_softmax_rows", L.ptr(s), L.ptr(out), s.numel() // n, n, _s())
+    return out
+
+
+def softmax_bwd_rows(p, dp, n, out=None):
+    if out is None:
+        out = torch.empty_like(p)
+    L.call("sgb_softmax_bwd_rows", L.ptr(p), L.ptr(dp), L.ptr(out), p.numel() // n, n, _s())
+    return out
+
+
+def dot(x, y):
+    out = torch.empty(1, device=x.device, dtype=torch.float32)
+    L.call("sgb_dot", L.ptr(x), L.ptr(y), x.numel(), L.ptr(out), _s())
+    return out
+
+
+def sum_hw(x, relu):
+    B, C, H, W, xs = geom(x)
+    h = torch.empty((B, C), device=x.device, dtype=torch.float32)
+    L.call("sgb_sum_hw", L.ptr(x), xs, B, H * W, C, 1 if relu else 0, L.ptr(h), _s())
+    return h
+
+
+def sum_hw_bwd(dh, x, relu):
+    B, C, H, W, xs = geom(x)
+    dx = empty_nhwc(B, C, H, W, x.device)
+    L.call("sgb_sum_hw_bwd", L.ptr(dh), L.ptr(x), xs, L.ptr(dx), geom(dx)[4], B, H * W, C, 1 if relu else 0, _s())
+    return dx
+
+
+def img_to_nhwc(img, Cp=8):
+    """NCHW fp32 image -> NHWC bf16 activation with channels zero-padded to Cp."""
+    B, C, H, W = img.shape
+    img = img.contiguous()
+    out = empty_nhwc(B, Cp, H, W, img.device)
+    L.call("sgb_img_to_nhwc", L.ptr(img), L.ptr(out), B, C, H * W, Cp, _s())
+    return out
+
+
+def nhwc_to_img(x, C, tanh=False):
+    """First C channels of an NHWC activation (bf16 or fp32) -> contiguous NCHW fp32 (optionally tanh)."""
+    B, Cx, H, W, cs = geom(x)
+    img = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32)
+    L.call("sgb_nhwc_to_img", L.ptr(x), 1 if x.dtype == torch.float32 else 0, cs, L.ptr(img), B, C, H * W, 1 if tanh else 0, _s())
+    return img
+
+
+def img_grad_to_nhwc(dimg, y=None, Cp=8):
+    B, C, H, W = dimg.shape
+    dimg = dimg.contiguous()
+    out = empty_nhwc(B, Cp, H, W, dimg.device)
+    L.call("sgb_img_grad_to_nhwc", L.ptr(dimg), L.ptr(y), L.ptr(out), B, C, H * W, Cp, _s())
+    return out
+
+
+def cast_f32_to_bf16(x, scale=1.0, out=None):
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=bf16)
+    L.call("sgb_cast_f32_to_bf16", L.ptr(x), L.ptr(out), x.numel(), float(scale), _s())
+    return out
+
+
+def cast_bf16_to_f32(x):
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    L.call("sgb_cast_bf16_to_f32", L.ptr(x), L.ptr(out), x.numel(), _s())
+    return out
+
+
+def adam_ema_step(p, g, m, v, lr, beta1, beta2, eps, step, ema=None, ema_decay=0.0, grad_scale=1.0):
+    L.call("sgb_adam_ema_step", L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), float(lr), float(beta1), float(beta2),
+           float(eps), int(step), L.ptr(ema), float(ema_decay), float(grad_scale), _s())
+
+
+def ema_lerp(ema, p, decay):
+    L.call("sgb_ema_lerp", L.ptr(ema), L.ptr(p), p.numel(), float(decay), _s())

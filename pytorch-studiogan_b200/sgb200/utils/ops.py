@@ -1,0 +1,307 @@
+"""Operator library behind ``cfgs.MODULES`` — same factory names, signatures and state_dict keys as the reference
+``src/utils/ops.py`` (conv2d / snconv2d / linear / snlinear / embedding / sn_embedding / batchnorm_2d /
+ConditionalBatchNorm2d / SelfAttention / init_weights), but every forward runs libsgb200 kernels on NHWC bf16
+activations.  Modules subclass nn.Conv2d / nn.Linear / nn.Embedding / nn.BatchNorm2d so that the reference's
+``isinstance`` based toggles (src/utils/misc.py:192-267,345-364) keep matching.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn import init
+
+from .. import autograd_ops as A
+from .. import kernels as K
+
+SN_EPS = 1e-6  # src/utils/ops.py:204,216,220,224
+
+
+def _apply_spectral_norm(module, eps=SN_EPS):
+    """Re-registers ``weight`` as ``weight_orig`` and draws u, v exactly like torch.nn.utils.spectral_norm
+    (torch/nn/utils/spectral_norm.py:128-160): u ~ normalize(N(0,1)^h), v ~ normalize(N(0,1)^w), dim = 0."""
+    weight = module._parameters.pop("weight")
+    h = weight.shape[0]
+    w = weight.numel() // h
+    with torch.no_grad():
+        u = F.normalize(weight.new_empty(h).normal_(0, 1), dim=0, eps=eps)
+        v = F.normalize(weight.new_empty(w).normal_(0, 1), dim=0, eps=eps)
+    module.register_parameter("weight_orig", weight)
+    module.register_buffer("weight_u", u)
+    module.register_buffer("weight_v", v)
+    module._sn = A.SpectralNormState(module, eps)
+
+
+def _w(module):
+    return module.weight_orig if hasattr(module, "weight_orig") else module.weight
+
+
+class _ConvBase(nn.Conv2d):
+    """Stride-1 convolution on the tcgen05 engine (3x3 / 1x1 as used by every BigGAN / ResNetGAN block)."""
+    spectral = False
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True):
+        super().__init__(in_channels, out_channels, kernel_size, stride=stride, padding=padding, dilation=dilation,
+                         groups=groups, bias=bias)
+        if self.stride != (1, 1) or self.dilation != (1, 1) or self.groups != 1 or self.padding[0] != self.padding[1]:
+            raise NotImplementedError("sgb200 conv engine: stride-1, dilation-1, groups-1 square-padded convolutions only")
+        if self.spectral:
+            _apply_spectral_norm(self)
+
+    def forward(self, x, residual=None, relu=False, premasked=False, mask_input=False, res_up2=False):
+        cfg = {"KH": self.kernel_size[0], "KW": self.kernel_size[1], "pad": self.padding[0], "relu": relu,
+               "premasked": premasked, "mask_input": mask_input, "res_up2": res_up2,
+               "sn": getattr(self, "_sn", None), "do_power_iteration": self.training}
+        return A.ConvFn.apply(x, _w(self), self.bias, residual, cfg)
+
+
+class Conv2d(_ConvBase):
+    spectral = False
+
+
+class SNConv2d(_ConvBase):
+    spectral = True
+
+
+class _LinearBase(nn.Linear):
+    """Linear layer as a 1x1 'convolution' over a [B, K, 1, 1] bf16 activation; returns [B, N, 1, 1].
+    perm_S > 1 emits the output features in NHWC order (see sgb_weight_pack)."""
+    spectral = False
+
+    def __init__(self, in_features, out_features, bias=True):
+        super().__init__(in_features, out_features, bias=bias)
+        if self.spectral:
+            _apply_spectral_norm(self)
+
+    def forward(self, x, out_fp32=False, perm_S=1):
+        if x.dim() == 2:
+            x = A.ToBF16Fn.apply(x) if x.dtype != torch.bfloat16 else x.view(x.shape[0], x.shape[1], 1, 1)
+        bias = self.bias
+        if bias is not None and perm_S > 1:
+            bias = bias.view(-1, perm_S).t().reshape(-1)
+        cfg = {"KH": 1, "KW": 1, "pad": 0, "relu": False, "out_fp32": out_fp32, "perm_S": perm_S,
+               "sn": getattr(self, "_sn", None), "do_power_iteration": self.training}
+        return A.ConvFn.apply(x, _w(self), bias, None, cfg)
+
+
+class Linear(_LinearBase):
+    spectral = False
+
+
+class SNLinear(_LinearBase):
+    spectral = True
+
+
+class Embedding(nn.Embedding):
+    pass
+
+
+class SNEmbedding(nn.Embedding):
+    """Spectrally-normalised embedding (projection discriminator, src/utils/ops.py:223-224).  The table is tiny
+    ([num_classes, C]); sigma comes from the library's power-iteration kernel, the lookup itself is indexing."""
+
+    def __init__(self, num_embeddings, embedding_dim):
+        super().__init__(num_embeddings, embedding_dim)
+        _apply_spectral_norm(self)
+
+    def forward(self, label):
+        W = self.weight_orig
+        u, v, ws = self._sn.tensors()
+        sigma = torch.empty(1, device=W.device, dtype=torch.float32)
+        K.sn_power_iter(W.detach(), u, v, sigma, ws, self._sn.eps, self.training)
+        if not torch.is_grad_enabled() or not W.requires_grad:
+            return F.embedding(label, W.detach()) / sigma
+        # sigma = u^T W v with u, v constant: keep the dependence of sigma on W for the gradient
+        sig = torch.dot(u.detach().clone(), torch.mv(W, v.detach().clone()))
+        return F.embedding(label, W) / sig
+
+
+def conv2d(in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True):
+    return Conv2d(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias)
+
+
+def snconv2d(in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True):
+    return SNConv2d(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias)
+
+
+def linear(in_features, out_features, bias=True):
+    return Linear(in_features, out_features, bias)
+
+
+def snlinear(in_features, out_features, bias=True):
+    return SNLinear(in_features, out_features, bias)
+
+
+def embedding(num_embeddings, embedding_dim):
+    return Embedding(num_embeddings, embedding_dim)
+
+
+def sn_embedding(num_embeddings, embedding_dim):
+    return SNEmbedding(num_embeddings, embedding_dim)
+
+
+def deconv2d(*args, **kwargs):
+    raise NotImplementedError("ConvTranspose2d (DCGAN generator, config 1) is the CPU-only oracle case; no sm_100a kernel")
+
+
+sndeconv2d = deconv2d
+
+
+class BatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d whose forward is the fused stats -> (NCCL all-reduce) -> scale/shift [+ReLU] [+nearest x2] path.
+    ``sync_group`` is set by models.model.prepare_parallel_training instead of converting to torch SyncBatchNorm."""
+    sync_group = None
+
+    def forward(self, x, relu=False, up2=False, gain=None, bias=None):
+        training = self.training or (self.running_mean is None)
+        track = self.training and self.track_running_stats and self.running_mean is not None
+        if track and self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
+        if gain is not None:
+            mode, g, b = 0, gain, bias
+        elif self.affine:
+            mode, g, b = 1, self.weight, self.bias
+        else:
+            mode, g, b = 2, None, None
+        cfg = {"mode": mode, "relu": relu, "up2": up2, "use_batch_stats": training, "track": track,
+               "momentum": self.momentum if self.momentum is not None else 0.1, "eps": self.eps,
+               "group": self.sync_group if training else None}
+        return A.BNActFn.apply(x, g, b, self.running_mean, self.running_var, cfg)
+
+
+def batchnorm_2d(in_features, eps=1e-4, momentum=0.1, affine=True):
+    return BatchNorm2d(in_features, eps=eps, momentum=momentum, affine=affine, track_running_stats=True)
+
+
+class ConditionalBatchNorm2d(nn.Module):
+    """out = bn(x) * (1 + gain(y)) + bias(y)  (src/utils/ops.py:14-28); ``y`` is the [B, K, 1, 1] bf16 conditioning
+    activation shared by all cBN layers of a generator pass.  ReLU and the nearest x2 upsample that follow in every
+    generator block are fused into the same pass."""
+
+    def __init__(self, in_features, out_features, MODULES):
+        super().__init__()
+        self.in_features = in_features
+        self.bn = batchnorm_2d(out_features, eps=1e-4, momentum=0.1, affine=False)
+        self.gain = MODULES.g_linear(in_features=in_features, out_features=out_features, bias=False)
+        self.bias = MODULES.g_linear(in_features=in_features, out_features=out_features, bias=False)
+
+    def forward(self, x, y, relu=False, up2=False):
+        gain = self.gain(y, out_fp32=True)
+        bias = self.bias(y, out_fp32=True)
+        return self.bn(x, relu=relu, up2=up2, gain=gain, bias=bias)
+
+
+class SelfAttention(nn.Module):
+    """Non-local block of SAGAN / BigGAN (src/utils/ops.py:31-103): same sub-module names and shapes."""
+
+    def __init__(self, in_channels, is_generator, MODULES):
+        super().__init__()
+        self.in_channels = in_channels
+        mk = MODULES.g_conv2d if is_generator else MODULES.d_conv2d
+        self.conv1x1_theta = mk(in_channels=in_channels, out_channels=in_channels // 8, kernel_size=1, stride=1, padding=0,
+                                bias=False)
+        self.conv1x1_phi = mk(in_channels=in_channels, out_channels=in_channels // 8, kernel_size=1, stride=1, padding=0,
+                              bias=False)
+        self.conv1x1_g = mk(in_channels=in_channels, out_channels=in_channels // 2, kernel_size=1, stride=1, padding=0,
+                            bias=False)
+        self.conv1x1_attn = mk(in_channels=in_channels // 2, out_channels=in_channels, kernel_size=1, stride=1, padding=0,
+                               bias=False)
+        self.maxpool = nn.MaxPool2d(2, stride=2, padding=0)
+        self.softmax = nn.Softmax(dim=-1)
+        self.sigma = nn.Parameter(torch.zeros(1), requires_grad=True)
+
+    def forward(self, x):
+        mods = (self.conv1x1_theta, self.conv1x1_phi, self.conv1x1_g, self.conv1x1_attn)
+        cfgs = tuple({"sn": getattr(m, "_sn", None), "do_power_iteration": m.training} for m in mods)
+        return A.SelfAttentionFn.apply(x, _w(mods[0]), _w(mods[1]), _w(mods[2]), _w(mods[3]), self.sigma, cfgs)
+
+
+def init_weights(modules, initialize):
+    """Same traversal and RNG consumption as src/utils/ops.py:135-162 (the reference initialises the spectral-norm
+    modules through the ``weight`` alias of ``weight_orig``; here the parameter is addressed directly)."""
+    for module in modules():
+        if isinstance(module, (nn.Conv2d, nn.ConvTranspose2d, nn.Linear)):
+            w = _w(module)
+            if initialize == "ortho":
+                init.orthogonal_(w)
+            elif initialize == "N02":
+                init.normal_(w, 0, 0.02)
+            elif initialize in ["glorot", "xavier"]:
+                init.xavier_uniform_(w)
+            else:
+                continue
+            if module.bias is not None:
+                module.bias.data.fill_(0.)
+        elif isinstance(module, nn.Embedding):
+            w = _w(module)
+            if initialize == "ortho":
+                init.orthogonal_(w)
+            elif initialize == "N02":
+                init.normal_(w, 0, 0.02)
+            elif initialize in ["glorot", "xavier"]:
+                init.xavier_uniform_(w)
+
+
+def quantize_images(x):
+    """src/utils/ops.py:251-255 (host path kept for API parity; the eval pipeline uses the fused device kernel)."""
+    x = (x + 1) / 2
+    x = (255.0 * x + 0.5).clamp(0.0, 255.0)
+    return x.detach().cpu().numpy().astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Discriminator head.  After the sum-pool the features are a [B, C] fp32 matrix; the remaining arithmetic (one GEMV,
+# one embedding row product per image) is a few kFLOP and is expressed directly on those tensors.  Spectral norm of the
+# head layers still goes through the library's power-iteration kernel so u / v evolve exactly like every other layer.
+# ----------------------------------------------------------------------------------------------------------------------
+def _head_weight(module):
+    W = _w(module)
+    sn = getattr(module, "_sn", None)
+    if sn is None:
+        return W
+    u, v, ws = sn.tensors()
+    sigma = torch.empty(1, device=W.device, dtype=torch.float32)
+    K.sn_power_iter(W.detach(), u, v, sigma, ws, sn.eps, module.training)
+    if torch.is_grad_enabled() and W.requires_grad:
+        sigma = torch.dot(u.detach().clone(), torch.mv(W.reshape(W.shape[0], -1), v.detach().clone()))
+    return W / sigma
+
+
+def head_linear(module, h):
+    return F.linear(h, _head_weight(module), module.bias)
+
+
+def discriminator_head(D, h, label, adc_fake=False):
+    """Everything after ``h = sum(relu(features), [2, 3])`` in the reference discriminators
+    (src/models/big_resnet_deep_legacy.py:347-413; identical in big_resnet.py / resnet.py): adversarial logit,
+    class conditioning (PD / AC / 2C / D2DCE / MD / MH), TAC / ADC extras, and the 12-key result dict."""
+    out = dict.fromkeys(["embed", "proxy", "cls_output", "mi_embed", "mi_proxy", "mi_cls_output",
+                         "info_discrete_c_logits", "info_conti_mu", "info_conti_var"])
+    adv = torch.squeeze(head_linear(D.linear1, h))
+    if D.aux_cls_type == "ADC":
+        label = label * 2 + 1 if adc_fake else label * 2
+    mtd = D.d_cond_mtd
+    if mtd == "PD":
+        adv = adv + torch.sum(D.embedding(label) * h, 1)
+    elif mtd == "AC":
+        if D.normalize_d_embed:
+            h = F.normalize(h, dim=1)
+        out["cls_output"] = head_linear(D.linear2, h)
+    elif mtd in ("2C", "D2DCE"):
+        embed, proxy = head_linear(D.linear2, h), D.embedding(label)
+        if D.normalize_d_embed:
+            embed, proxy = F.normalize(embed, dim=1), F.normalize(proxy, dim=1)
+        out["embed"], out["proxy"] = embed, proxy
+    elif mtd == "MD":
+        adv = adv[torch.arange(label.size(0), device=label.device), label]
+    elif mtd not in ("W/O", "MH"):
+        raise NotImplementedError(mtd)
+    if D.aux_cls_type == "TAC":
+        if mtd == "AC":
+            out["mi_cls_output"] = head_linear(D.linear_mi, h)
+        elif mtd in ("2C", "D2DCE"):
+            mi_embed, mi_proxy = head_linear(D.linear_mi, h), D.embedding_mi(label)
+            if D.normalize_d_embed:
+                mi_embed, mi_proxy = F.normalize(mi_embed, dim=1), F.normalize(mi_proxy, dim=1)
+            out["mi_embed"], out["mi_proxy"] = mi_embed, mi_proxy
+    out.update({"h": h, "adv_output": adv, "label": label})
+    return out

@@ -1,0 +1,178 @@
+"""Generates the golden vectors under tests/golden/ by running the UNMODIFIED reference (imported from
+/root/reference/src) on seeded CPU inputs.  Run in the build container only:
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+The reference tree is read-only and absent on the GPU box, so the resulting .npz files are committed next to this
+script.  Missing plotting / IO packages of the reference are stubbed (they are not on the hot path), see SURVEY.md A.1.
+"""
+import os
+import sys
+import types
+from unittest.mock import MagicMock
+
+import numpy as np
+
+os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
+sys.dont_write_bytecode = True
+for name in ["matplotlib", "matplotlib.pyplot", "seaborn", "h5py", "kornia", "kornia.filters", "kornia.geometry",
+             "kornia.geometry.transform", "timm", "timm.models", "timm.models.layers"]:
+    sys.modules[name] = MagicMock()
+REF = os.environ.get("SGB_REFERENCE", "/root/reference/src")
+sys.path.insert(0, REF)
+
+import torch  # noqa: E402
+import torch.nn as nn  # noqa: E402
+
+import utils.ops as rops  # noqa: E402  (reference)
+import utils.losses as rlosses  # noqa: E402
+import utils.ema as rema  # noqa: E402
+import models.big_resnet_deep_legacy as rdeep  # noqa: E402
+import scipy.linalg  # noqa: E402
+import metrics.fid as rfid  # noqa: E402
+import metrics.ins as rins  # noqa: E402
+import metrics.prdc as rprdc  # noqa: E402
+import utils.resize as rresize  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def modules(g_sn=True, d_sn=True, cbn=True):
+    m = types.SimpleNamespace()
+    m.g_conv2d = rops.snconv2d if g_sn else rops.conv2d
+    m.g_linear = rops.snlinear if g_sn else rops.linear
+    m.g_embedding = rops.sn_embedding if g_sn else rops.embedding
+    m.d_conv2d = rops.snconv2d if d_sn else rops.conv2d
+    m.d_linear = rops.snlinear if d_sn else rops.linear
+    m.d_embedding = rops.sn_embedding if d_sn else rops.embedding
+    m.g_bn = rops.ConditionalBatchNorm2d if cbn else rops.batchnorm_2d
+    if not d_sn:
+        m.d_bn = rops.batchnorm_2d
+    m.g_act_fn = nn.ReLU(inplace=True)
+    m.d_act_fn = nn.ReLU(inplace=True)
+    return m
+
+
+MODEL = types.SimpleNamespace(info_type="N/A", g_info_injection="N/A")
+
+
+def sd_np(module, prefix):
+    return {prefix + k: v.detach().cpu().numpy().copy() for k, v in module.state_dict().items()}
+
+
+def golden_deep(tag, img_size, conv_dim, depth, attn, z_dim=16, shared=16, classes=5, B=3):
+    torch.manual_seed(1234)
+    M = modules()
+    G = rdeep.Generator(z_dim=z_dim, g_shared_dim=shared, img_size=img_size, g_conv_dim=conv_dim, apply_attn=attn,
+                        attn_g_loc=[2], g_cond_mtd="cBN", num_classes=classes, g_init="ortho", g_depth=depth,
+                        mixed_precision=False, MODULES=M, MODEL=MODEL)
+    D = rdeep.Discriminator(img_size=img_size, d_conv_dim=conv_dim, apply_d_sn=True, apply_attn=attn, attn_d_loc=[1],
+                            d_cond_mtd="PD", aux_cls_type="W/O", d_embed_dim="N/A", normalize_d_embed=False,
+                            num_classes=classes, d_init="ortho", d_depth=depth, mixed_precision=False, MODULES=M, MODEL=MODEL)
+    G.train()
+    D.train()
+    # make the attention gate non-trivial (its init value 0 would hide the whole branch)
+    with torch.no_grad():
+        for mod in list(G.modules()) + list(D.modules()):
+            if isinstance(mod, rops.SelfAttention):
+                mod.sigma.fill_(0.37)
+    out = {}
+    out.update(sd_np(G, "G0/"))
+    out.update(sd_np(D, "D0/"))
+    z = torch.randn(B, z_dim)
+    y_fake = torch.randint(0, classes, (B,))
+    real = torch.rand(B, 3, img_size, img_size) * 2 - 1
+    y_real = torch.randint(0, classes, (B,))
+    out.update({"z": z.numpy(), "y_fake": y_fake.numpy(), "real": real.numpy(), "y_real": y_real.numpy()})
+
+    # ---- discriminator phase (src/worker.py:213-497): G forward without graph, D(real), D(fake), hinge, backward
+    for p in G.parameters():
+        p.requires_grad_(False)
+    fake = G(z, y_fake)
+    real_d = D(real, y_real)
+    fake_d = D(fake.detach(), y_fake)
+    d_loss = rlosses.d_hinge(real_d["adv_output"], fake_d["adv_output"], False)
+    d_loss.backward()
+    out.update({"fake": fake.detach().numpy(), "adv_real": real_d["adv_output"].detach().numpy(),
+                "adv_fake": fake_d["adv_output"].detach().numpy(), "h_real": real_d["h"].detach().numpy(),
+                "d_loss": d_loss.detach().numpy()})
+    for k, p in D.named_parameters():
+        out["Dgrad/" + k] = p.grad.detach().numpy().copy()
+    out.update(sd_np(G, "G1/"))   # buffers after one forward (u, v, running stats)
+    out.update(sd_np(D, "D1/"))   # buffers after two forwards
+
+    # ---- generator phase (src/worker.py:502-681): G forward with graph, D forward with frozen params, hinge, backward
+    D.zero_grad()
+    for p in G.parameters():
+        p.requires_grad_(True)
+    for p in D.parameters():
+        p.requires_grad_(False)
+    fake2 = G(z, y_fake)
+    g_loss = rlosses.g_hinge(D(fake2, y_fake)["adv_output"], False)
+    g_loss.backward()
+    out.update({"fake2": fake2.detach().numpy(), "g_loss": g_loss.detach().numpy()})
+    for k, p in G.named_parameters():
+        out["Ggrad/" + k] = p.grad.detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
+    print(tag, "keys", len(out), "d_loss", float(d_loss), "g_loss", float(g_loss))
+
+
+def golden_metrics():
+    rng = np.random.RandomState(0)
+    out = {}
+    # quantisation + legacy resize (src/utils/ops.py:251-263, src/utils/resize.py:50-94)
+    x = torch.from_numpy(rng.uniform(-1.1, 1.1, size=(2, 3, 8, 8)).astype(np.float32))
+    q = rops.quantize_images(x)
+    out["q_in"], out["q_out"] = x.numpy(), q
+    resizer = rresize.build_resizer("legacy", "InceptionV3_tf", 19)
+    rs = np.stack([resizer(img) for img in q.transpose(0, 2, 3, 1)], 0)
+    out["resize_legacy_19"] = rs
+    # FID / moments
+    real = rng.randn(300, 24).astype(np.float64)
+    fake = (rng.randn(280, 24) * 1.1 + 0.05).astype(np.float32)
+    rfid.linalg = types.SimpleNamespace(sqrtm=lambda m, disp=True: (scipy.linalg.sqrtm(m), None) if disp is False
+                                        else scipy.linalg.sqrtm(m))
+    mu1, s1 = np.mean(fake, axis=0), np.cov(fake, rowvar=False)
+    mu2, s2 = np.mean(real, axis=0), np.cov(real, rowvar=False)
+    out["feat_real"], out["feat_fake"] = real, fake
+    out["fid"] = np.array(rfid.frechet_inception_distance(mu1, s1, mu2, s2))
+    # IS
+    logits = rng.randn(200, 11).astype(np.float32)
+    probs = torch.softmax(torch.from_numpy(logits), 1)
+    m, s = rins.calculate_kl_div(probs, splits=1)
+    m4, s4 = rins.calculate_kl_div(probs, splits=4)
+    out["probs"] = probs.numpy()
+    out["is_1"] = np.array([float(m), float(s)])
+    out["is_4"] = np.array([float(m4), float(s4)])
+    # PRDC
+    pr = rprdc.compute_prdc(real_features=real[:200], fake_features=fake[:180].astype(np.float64), nearest_k=5)
+    out["prdc"] = np.array([pr["precision"], pr["recall"], pr["density"], pr["coverage"]])
+    # EMA (src/utils/ema.py:27-40)
+    torch.manual_seed(3)
+    src = nn.Sequential(nn.Conv2d(3, 4, 3), nn.BatchNorm2d(4))
+    tgt = nn.Sequential(nn.Conv2d(3, 4, 3), nn.BatchNorm2d(4))
+    out.update({"ema_src/" + k: v.numpy().copy() for k, v in src.state_dict().items()})
+    out.update({"ema_tgt0/" + k: v.numpy().copy() for k, v in tgt.state_dict().items()})
+    e = rema.Ema(src, tgt, decay=0.9, start_iter=2)
+    out.update({"ema_init/" + k: v.numpy().copy() for k, v in tgt.state_dict().items()})
+    with torch.no_grad():
+        for p in src.parameters():
+            p.add_(0.5)
+        src[1].running_mean.add_(0.25)
+    out.update({"ema_src2/" + k: v.numpy().copy() for k, v in src.state_dict().items()})
+    e.update(5)
+    out.update({"ema_after/" + k: v.numpy().copy() for k, v in tgt.state_dict().items()})
+    # losses
+    a, b = torch.from_numpy(rng.randn(16).astype(np.float32)), torch.from_numpy(rng.randn(16).astype(np.float32))
+    out["loss_in_real"], out["loss_in_fake"] = a.numpy(), b.numpy()
+    out["losses"] = np.array([float(rlosses.d_hinge(a, b, False)), float(rlosses.g_hinge(b, False)),
+                              float(rlosses.d_wasserstein(a, b, False)), float(rlosses.g_wasserstein(b, False)),
+                              float(rlosses.d_vanilla(a, b, False)), float(rlosses.g_vanilla(b, False))])
+    np.savez_compressed(os.path.join(HERE, "metrics.npz"), **out)
+    print("metrics", {k: out[k] for k in ["fid", "is_1", "prdc", "losses"]})
+
+
+if __name__ == "__main__":
+    golden_deep("deep32_c8", 32, 8, 1, attn=False)
+    golden_deep("deep32_c16_attn_d2", 32, 16, 2, attn=True, B=2)
+    golden_metrics()

@@ -1,0 +1,111 @@
+"""Pins oracle/studiogan_oracle.py to the reference: every value here was produced by the real StudioGAN code
+(tests/golden/make_golden.py, run in the build container) and must be reproduced by the oracle on CPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import studiogan_oracle as O
+
+CASES = [("deep32_c8", dict(img_size=32, conv_dim=8, depth=1, attn=False)),
+         ("deep32_c16_attn_d2", dict(img_size=32, conv_dim=16, depth=2, attn=True))]
+
+
+def load_sd(npz, prefix, grad=False):
+    sd = {}
+    for k in npz.files:
+        if k.startswith(prefix):
+            t = torch.from_numpy(npz[k].copy())
+            if grad and t.is_floating_point() and (k.endswith("weight_orig") or k.endswith("weight") or k.endswith("bias")
+                                                   or k.endswith("sigma")) and "running" not in k:
+                t.requires_grad_(True)
+            sd[k[len(prefix):]] = t
+    return sd
+
+
+@pytest.mark.parametrize("tag,cfg", CASES)
+def test_deep_d_phase_and_g_phase(golden_dir, tag, cfg):
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    z, yf = torch.from_numpy(g["z"]), torch.from_numpy(g["y_fake"])
+    real, yr = torch.from_numpy(g["real"]), torch.from_numpy(g["y_real"])
+    kw_g = dict(img_size=cfg["img_size"], g_conv_dim=cfg["conv_dim"], g_depth=cfg["depth"], attn_g_loc=(2,), apply_attn=cfg["attn"])
+    kw_d = dict(img_size=cfg["img_size"], d_conv_dim=cfg["conv_dim"], d_depth=cfg["depth"], attn_d_loc=(1,), apply_attn=cfg["attn"])
+
+    # discriminator phase
+    sdG = load_sd(g, "G0/")
+    sdD = load_sd(g, "D0/", grad=True)
+    with torch.no_grad():
+        fake = O.deep_generator(sdG, z, yf, **kw_g)
+    np.testing.assert_allclose(fake.numpy(), g["fake"], rtol=1e-4, atol=2e-5)
+    adv_r, h_r = O.deep_discriminator(sdD, real, yr, **kw_d)
+    adv_f, _ = O.deep_discriminator(sdD, fake, yf, **kw_d)
+    np.testing.assert_allclose(adv_r.detach().numpy(), g["adv_real"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(adv_f.detach().numpy(), g["adv_fake"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(h_r.detach().numpy(), g["h_real"], rtol=1e-4, atol=1e-4)
+    loss = O.d_hinge(adv_r, adv_f)
+    np.testing.assert_allclose(loss.item(), g["d_loss"], rtol=1e-5)
+    loss.backward()
+    for k in g.files:
+        if k.startswith("Dgrad/"):
+            name = k[len("Dgrad/"):]
+            ref = g[k]
+            got = sdD[name].grad.numpy()
+            assert np.abs(got - ref).max() <= 2e-3 * (1e-3 + np.abs(ref).max()), name  # ReLU-boundary flips dominate the fp32 noise
+    # buffers after the forwards (u, v, running statistics)
+    for k in g.files:
+        if k.startswith("G1/") and ("weight_u" in k or "running_" in k):
+            np.testing.assert_allclose(sdG[k[3:]].numpy(), g[k], rtol=1e-4, atol=1e-5, err_msg=k)
+        if k.startswith("D1/") and "weight_u" in k:
+            np.testing.assert_allclose(sdD[k[3:]].numpy(), g[k], rtol=1e-4, atol=1e-5, err_msg=k)
+
+    # generator phase (continues from the buffers left by the discriminator phase)
+    sdG2 = load_sd(g, "G1/", grad=True)
+    sdD2 = load_sd(g, "D1/")
+    fake2 = O.deep_generator(sdG2, z, yf, **kw_g)
+    np.testing.assert_allclose(fake2.detach().numpy(), g["fake2"], rtol=1e-4, atol=2e-5)
+    adv2, _ = O.deep_discriminator(sdD2, fake2, yf, **kw_d)
+    gl = O.g_hinge(adv2)
+    np.testing.assert_allclose(gl.item(), g["g_loss"], rtol=1e-5)
+    gl.backward()
+    for k in g.files:
+        if k.startswith("Ggrad/"):
+            name = k[len("Ggrad/"):]
+            ref = g[k]
+            got = sdG2[name].grad.numpy()
+            assert np.abs(got - ref).max() <= 2e-3 * (1e-3 + np.abs(ref).max()), name  # ReLU-boundary flips dominate the fp32 noise
+
+
+def test_metrics_and_losses(golden_dir):
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    assert np.array_equal(O.quantize_images(torch.from_numpy(g["q_in"])), g["q_out"])            # integer path: bit exact
+    rs = O.resize_legacy(g["q_out"], 19).numpy()
+    np.testing.assert_allclose(rs, g["resize_legacy_19"].transpose(0, 3, 1, 2), rtol=0, atol=1e-4)
+    mu1, s1 = O.moments(g["feat_fake"])
+    mu2, s2 = O.moments(g["feat_real"])
+    np.testing.assert_allclose(O.frechet_distance(mu1, s1, mu2, s2), g["fid"], rtol=1e-9)
+    m, s = O.calculate_kl_div(g["probs"], 1)
+    np.testing.assert_allclose(m, g["is_1"][0], rtol=1e-6)
+    assert np.isnan(g["is_1"][1])                                                               # reference quirk: splits=1 -> NaN std
+    m4, s4 = O.calculate_kl_div(g["probs"], 4)
+    np.testing.assert_allclose([m4, s4], g["is_4"], rtol=1e-5)
+    pr = O.prdc(g["feat_real"][:200], g["feat_fake"][:180].astype(np.float64), 5)
+    np.testing.assert_allclose([pr["precision"], pr["recall"], pr["density"], pr["coverage"]], g["prdc"], rtol=1e-12)
+    a, b = torch.from_numpy(g["loss_in_real"]), torch.from_numpy(g["loss_in_fake"])
+    got = [O.d_hinge(a, b), O.g_hinge(b), O.d_wasserstein(a, b), O.g_wasserstein(b), O.d_vanilla(a, b), O.g_vanilla(b)]
+    np.testing.assert_allclose([float(x) for x in got], g["losses"], rtol=1e-6)
+
+
+def test_ema(golden_dir):
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    keys = [k[len("ema_src/"):] for k in g.files if k.startswith("ema_src/")]
+    src0 = {k: torch.from_numpy(g["ema_src/" + k].copy()) for k in keys}
+    # Ema.__init__ copies source -> target (src/utils/ema.py:21-25)
+    for k in keys:
+        if "num_batches" not in k:
+            np.testing.assert_allclose(g["ema_init/" + k], src0[k].numpy())
+    src2 = {k: torch.from_numpy(g["ema_src2/" + k].copy()) for k in keys}
+    tgt = {k: torch.from_numpy(g["ema_init/" + k].copy()) for k in keys}
+    O.ema_update(src2, tgt, decay=0.9, step=5, start_iter=2)
+    for k in keys:
+        np.testing.assert_allclose(tgt[k].numpy(), g["ema_after/" + k], rtol=1e-6, atol=1e-7, err_msg=k)
