@@ -1,0 +1,353 @@
+"""bench.py — BigGAN-Deep 256x256 G+D step throughput (BASELINE.json config 4) on N B200s, one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--config yaml]
+
+step     = WORKER.train_discriminator (d_updates_per_step = 2 discriminator updates) + WORKER.train_generator
+           (one generator update + EMA), i.e. one iteration of the reference loop (src/loader.py:392-398).
+metric   = images/s = global batch x acml_steps / step time, whole job over all ranks (strong scaling: the global
+           batch is fixed at 256, each rank takes 256/N).
+value    = synthetic real images already resident in HBM.
+e2e      = the same step driven from pinned HOST buffers: the basket's H2D copy and a D2H read of both losses are inside
+           the timed region.
+--impl reference : the CPU path (oracle port of the reference step) on the host cores, bounded sample, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "pytorch-studiogan_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+# conv + linear + attention-bmm FLOPs per image (2 x MAC), BASELINE.md section 3 / SURVEY.md 8(d)
+STEP_GFLOP_PER_IMAGE = {"BigGAN-Deep-256res": 1141.0}
+G_FWD_GF, D_FWD_GF = 58.80, 60.50
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="override the global batch (diagnostics only)")
+    ap.add_argument("--config", default=os.path.join(PKG, "configs", "BigGAN-Deep-256res.yaml"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=2)
+    return ap.parse_args()
+
+
+class Logger:
+    def info(self, *a, **k):
+        pass
+
+
+class SyntheticBasketLoader:
+    """Infinite loader with the reference basket contract (src/loader.py:178-193): one item = batch x acml x d_updates
+    images in [-1, 1] fp32 NCHW + int64 labels.  ``device`` None -> pinned host memory (the e2e leg), else HBM-resident."""
+
+    def __init__(self, per_rank_batch, n_items, img_size, num_classes, seed, device=None, pool=2):
+        g = torch.Generator().manual_seed(seed)
+        self.items = []
+        for _ in range(pool):
+            img = torch.rand(per_rank_batch * n_items, 3, img_size, img_size, generator=g) * 2 - 1
+            lab = torch.randint(0, num_classes, (per_rank_batch * n_items,), generator=g)
+            if device is None:
+                img, lab = img.pin_memory(), lab.pin_memory()
+            else:
+                img, lab = img.to(device), lab.to(device)
+            self.items.append((img, lab))
+        self.i = 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        self.i += 1
+        return self.items[self.i % len(self.items)]
+
+
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) > 8:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_worker(args, rank, world, device):
+    from sgb200 import config as C
+    from sgb200.models import model as M
+    from sgb200.utils import misc
+    from sgb200.worker import WORKER
+    cfgs = C.Configurations(args.config)
+    if args.batch:
+        cfgs.OPTIMIZATION.batch_size = args.batch
+    global_batch = cfgs.OPTIMIZATION.batch_size
+    assert global_batch % world == 0
+    cfgs.OPTIMIZATION.batch_size = global_batch // world           # per-rank batch, as src/loader.py:162
+    cfgs.RUN.distributed_data_parallel = world > 1
+    cfgs.RUN.synchronized_bn = world > 1
+    misc.fix_seed(0 + rank)                                         # seed + rank (src/loader.py:99)
+    Gen, _, _, Dis, Gen_ema, _, _, ema = M.load_generator_discriminator(cfgs.DATA, cfgs.OPTIMIZATION, cfgs.MODEL, cfgs.STYLEGAN,
+                                                                        cfgs.MODULES, cfgs.RUN, device, Logger())
+    if world > 1:
+        Gen, _, _, Dis, Gen_ema, _, _ = M.prepare_parallel_training(Gen, None, None, Dis, Gen_ema, None, None, cfgs.MODEL, world,
+                                                                    True, True, cfgs.MODEL.apply_g_ema, device)
+    cfgs.define_optimizer(Gen, Dis)
+    worker = WORKER(cfgs=cfgs, run_name="bench", Gen=Gen, Gen_mapping=None, Gen_synthesis=None, Dis=Dis, Gen_ema=Gen_ema,
+                    Gen_ema_mapping=None, Gen_ema_synthesis=None, ema=ema, eval_model=None, train_dataloader=None,
+                    eval_dataloader=None, global_rank=rank, local_rank=device, mu=None, sigma=None, real_feats=None, logger=Logger())
+    return cfgs, worker, global_batch
+
+
+def run_steps(worker, n, read_losses):
+    out = None
+    for s in range(n):
+        _, d_loss = worker.train_discriminator(s)
+        g_loss = worker.train_generator(s)
+        if read_losses:
+            out = (float(d_loss), float(g_loss))      # D2H read of the step's results
+    return out
+
+
+def timed(worker, steps, world, read_losses):
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    losses = run_steps(worker, steps, read_losses)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms) / steps, losses
+
+
+def cpu_step_images_per_sec(config_path, batch, threads, n_steps=1):
+    """The reference step restated by the oracle (fp32 CPU torch): 2 discriminator updates + 1 generator update with Adam,
+    BigGAN-Deep 256x256, on ``threads`` host threads.  A bounded sample: ``batch`` images per step."""
+    import yaml
+    from oracle import studiogan_oracle as O
+    from sgb200 import config as C
+    from sgb200.models import model as M
+    torch.set_num_threads(threads)
+    cfgs = C.Configurations(config_path)
+    torch.manual_seed(0)
+    Gen, _, _, Dis, _, _, _, _ = M.load_generator_discriminator(cfgs.DATA, cfgs.OPTIMIZATION, _no_ema(cfgs.MODEL), cfgs.STYLEGAN,
+                                                                 cfgs.MODULES, cfgs.RUN, "cpu", Logger())
+    m = cfgs.MODEL
+    sdG = {k: v.detach().clone() for k, v in Gen.state_dict().items()}
+    sdD = {k: v.detach().clone() for k, v in Dis.state_dict().items()}
+    pG = [k for k, _ in Gen.named_parameters()]
+    pD = [k for k, _ in Dis.named_parameters()]
+    del Gen, Dis
+    kw_g = dict(img_size=cfgs.DATA.img_size, g_conv_dim=m.g_conv_dim, g_depth=m.g_depth, attn_g_loc=tuple(m.attn_g_loc), apply_attn=m.apply_attn)
+    kw_d = dict(img_size=cfgs.DATA.img_size, d_conv_dim=m.d_conv_dim, d_depth=m.d_depth, attn_d_loc=tuple(m.attn_d_loc), apply_attn=m.apply_attn)
+    optG = torch.optim.Adam([sdG[k].requires_grad_(True) for k in pG], lr=cfgs.OPTIMIZATION.g_lr, betas=(cfgs.OPTIMIZATION.beta1, cfgs.OPTIMIZATION.beta2), eps=1e-6)
+    optD = torch.optim.Adam([sdD[k].requires_grad_(True) for k in pD], lr=cfgs.OPTIMIZATION.d_lr, betas=(cfgs.OPTIMIZATION.beta1, cfgs.OPTIMIZATION.beta2), eps=1e-6)
+    S, nc = cfgs.DATA.img_size, cfgs.DATA.num_classes
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        for _ in range(cfgs.OPTIMIZATION.d_updates_per_step):
+            optD.zero_grad()
+            real, yr = torch.rand(batch, 3, S, S) * 2 - 1, torch.randint(0, nc, (batch,))
+            yf = torch.randint(0, nc, (batch,))
+            z = torch.randn(batch, m.z_dim)
+            with torch.no_grad():
+                fake = O.deep_generator(sdG, z, yf, track=False, **kw_g)
+            a, _ = O.deep_discriminator(sdD, real, yr, **kw_d)
+            b, _ = O.deep_discriminator(sdD, fake, yf, **kw_d)
+            O.d_hinge(a, b).backward()
+            optD.step()
+        optG.zero_grad()
+        yf = torch.randint(0, nc, (batch,))
+        z = torch.randn(batch, m.z_dim)
+        fake = O.deep_generator(sdG, z, yf, **kw_g)
+        a, _ = O.deep_discriminator({k: v.detach() for k, v in sdD.items()}, fake, yf, **kw_d)
+        O.g_hinge(a).backward()
+        optG.step()
+    dt = time.perf_counter() - t0
+    return batch * n_steps / dt, dt
+
+
+def _no_ema(MODEL):
+    import copy
+    m = copy.copy(MODEL)
+    m.apply_g_ema = False
+    return m
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = os.path.splitext(os.path.basename(args.config))[0]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        vals = []
+        for _ in range(max(1, min(args.steps, 2))):
+            v, dt = cpu_step_images_per_sec(args.config, args.cpu_batch, threads)
+            vals.append(v)
+        v = float(np.mean(vals))
+        line = {"impl": "reference", "metric": "BigGAN-Deep 256x256 G+D step images/sec", "value": v, "unit": "img/s",
+                "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": 1000.0 * args.cpu_batch / v,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "global_batch": args.cpu_batch, "img_size": 256, "d_updates_per_step": 2,
+                           "note": "CPU restatement (oracle port) of the reference step; /root/reference is not present on the GPU box"},
+                "cpu_baseline": {"value": v, "unit": "img/s", "cores": threads, "kind": "port",
+                                 "sample": "%d-image batch, one full step (2 D updates + 1 G update, fwd+bwd+Adam) per measurement" % args.cpu_batch},
+                "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from sgb200 import _lib
+    _lib.check(_lib.load().sgb_device_check(), "sgb_device_check")
+    cfgs, worker, global_batch = build_worker(args, rank, world, device)
+    opt = cfgs.OPTIMIZATION
+    per_rank = opt.batch_size
+    n_items = opt.acml_steps * opt.d_updates_per_step
+    S = cfgs.DATA.img_size
+
+    # ---- device-resident leg (value)
+    dev_loader = SyntheticBasketLoader(per_rank, n_items, S, cfgs.DATA.num_classes, 100 + rank, device=device)
+    worker.train_dataloader, worker.train_iter = dev_loader, iter(dev_loader)
+    run_steps(worker, args.warmup, False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.LAUNCHES[0]
+    ms_step, _ = timed(worker, args.steps, world, False)
+    launches = (_lib.LAUNCHES[0] - launches0)
+    sampler.stop_flag = True
+    value = global_batch * opt.acml_steps / (ms_step * 1e-3)
+
+    # ---- per-kernel accounting on one extra (untimed) step: CUDA events around every conv-engine launch
+    prof = None
+    try:
+        from sgb200 import kernels as K
+        K.PROFILE = {"enabled": True, "events": []}
+        run_steps(worker, 1, False)
+        torch.cuda.synchronize()
+        K.PROFILE["enabled"] = False
+        agg = {}
+        for name, flops, e0, e1 in K.PROFILE["events"]:
+            a = agg.setdefault(name, [0.0, 0.0, 0])
+            a[0] += e0.elapsed_time(e1)
+            a[1] += flops
+            a[2] += 1
+        K.PROFILE = None
+        prof = {k: {"ms": v[0], "tflops": (v[1] / (v[0] * 1e-3) * 1e-12) if v[0] > 0 else 0.0, "launches": v[2], "flop": v[1]}
+                for k, v in agg.items()}
+    except Exception as ex:  # accounting must never take the bench line down
+        prof = {"error": repr(ex)}
+
+    # ---- end-to-end leg: pinned host baskets, H2D inside the timed region, loss read back every step
+    e2e = None
+    if not args.no_e2e:
+        host_loader = SyntheticBasketLoader(per_rank, n_items, S, cfgs.DATA.num_classes, 200 + rank, device=None)
+        worker.train_dataloader, worker.train_iter = host_loader, iter(host_loader)
+        run_steps(worker, 1, True)
+        ms_e2e, _ = timed(worker, args.steps, world, True)
+        h2d = world * per_rank * n_items * (3 * S * S * 4 + 8)
+        e2e = {"value": global_batch * opt.acml_steps / (ms_e2e * 1e-3), "unit": "img/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained"
+    step_flop = STEP_GFLOP_PER_IMAGE.get(workload, 0.0) * 1e9 * global_batch
+    roof = {"bound": "tensor", "unit": "TFLOP/s", "peak": peak_tf, "peak_source": peak_src, "traffic": None,
+            "step_algorithmic_tflop": step_flop * 1e-12,
+            "step_achieved": step_flop / (ms_step * 1e-3) * 1e-12 / world,
+            "step_frac": step_flop / (ms_step * 1e-3) * 1e-12 / world / peak_tf}
+    if isinstance(prof, dict) and "conv_fprop" in prof:
+        k = prof["conv_fprop"]
+        roof.update({"kernel": "conv_fprop_kernel (fprop + dgrad, tcgen05)", "achieved": k["tflops"], "frac": k["tflops"] / peak_tf,
+                     "kernel_ms_per_step": k["ms"], "kernel_share_of_step": k["ms"] / ms_step, "kernels": prof})
+    else:
+        roof.update({"achieved": roof["step_achieved"], "frac": roof["step_frac"], "kernels": prof})
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        try:
+            v, dt = cpu_step_images_per_sec(args.config, args.cpu_batch, threads)
+            cpu = {"value": v, "unit": "img/s", "cores": threads, "kind": "port",
+                   "sample": "%d-image batch, one full step (2 D updates + 1 G update, fwd+bwd+Adam), %.1f s" % (args.cpu_batch, dt)}
+        except Exception as ex:
+            cpu = {"value": None, "unit": "img/s", "cores": threads, "kind": "port", "sample": "failed: %r" % (ex,)}
+
+    line = {"metric": "BigGAN-Deep 256x256 G+D step images/sec", "value": value, "unit": "img/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload, "global_batch": global_batch, "per_gpu_batch": per_rank, "img_size": S,
+                       "d_updates_per_step": opt.d_updates_per_step, "acml_steps": opt.acml_steps, "parallelism": "dp%d" % world,
+                       "l2": "per-step working set (tens of GB of activations) >> 126 MB L2; no explicit flush needed"},
+            "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary()}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

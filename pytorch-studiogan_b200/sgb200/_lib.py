@@ -122,7 +122,11 @@ def ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+LAUNCHES = [0]  # number of library entry-point calls (each launches >= 1 kernel); bench.py reports the delta per step
+
+
 def call(name, *args):
     lib = load()
     rc = getattr(lib, name)(*args)
+    LAUNCHES[0] += 1
     check(rc, name)

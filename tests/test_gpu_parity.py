@@ -1,0 +1,288 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every test drives the product path — Python modules ->
+autograd ops -> ctypes -> libsgb200 kernels — and compares with the CPU oracle (oracle/studiogan_oracle.py) or with the
+committed golden vectors produced by the real reference.
+
+Tolerances (stated per test): the kernels compute in bf16 with fp32 accumulation, the oracle in fp32; activations are
+compared at bf16 resolution (2^-8 relative per rounding, a few roundings per block), integer/label paths bit-exactly.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import studiogan_oracle as O  # noqa: E402
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def bfr(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def rel_err(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    return float((got - ref).abs().max() / (ref.abs().max() + 1e-12))
+
+
+def to_nhwc(x, dev):
+    """fp32 NCHW cpu -> product activation (NHWC-in-memory bf16 on device)."""
+    return x.to(dev).to(torch.bfloat16).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------------ conv engine
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", [(2, 16, 16, 64, 64, 3), (3, 8, 8, 32, 128, 1), (2, 32, 32, 128, 24, 3),
+                                              (4, 4, 4, 256, 64, 3), (2, 64, 64, 8, 16, 3), (5, 1, 1, 40, 72, 1)])
+def test_conv_fwd_bwd_vs_fp32_reference(B, H, W, Cin, Cout, k):
+    from sgb200 import autograd_ops as A
+    dev = _cuda()
+    g = torch.Generator().manual_seed(0)
+    x = bfr(torch.randn(B, Cin, H, W, generator=g))
+    w = torch.randn(Cout, Cin, k, k, generator=g) * 0.1
+    b = torch.randn(Cout, generator=g)
+    dy = bfr(torch.randn(B, Cout, H, W, generator=g))
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.conv2d(xr, bfr(wr) + (wr - wr.detach()), br, padding=k // 2)   # weights rounded to bf16, gradient to fp32 master
+    yr.backward(dy)
+    xd = to_nhwc(x, dev).requires_grad_(True)
+    wd, bd = w.to(dev).requires_grad_(True), b.to(dev).requires_grad_(True)
+    y = A.ConvFn.apply(xd, wd, bd, None, {"KH": k, "KW": k, "pad": k // 2})
+    y.backward(to_nhwc(dy, dev))
+    assert rel_err(y[:, :Cout], yr) < 8e-3            # output rounded once to bf16
+    assert rel_err(xd.grad[:, :Cin], xr.grad) < 8e-3
+    assert rel_err(wd.grad, wr.grad) < 2e-3           # fp32 accumulation of bf16 products
+    assert rel_err(bd.grad, br.grad) < 2e-3
+
+
+def test_spectral_norm_power_iteration_matches_oracle():
+    from sgb200 import kernels as K
+    dev = _cuda()
+    g = torch.Generator().manual_seed(1)
+    for (R, Kd) in [(64, 576), (2048, 512), (10, 128), (512, 4608)]:
+        W = torch.randn(R, Kd, generator=g)
+        u = F.normalize(torch.randn(R, generator=g), dim=0)
+        v = F.normalize(torch.randn(Kd, generator=g), dim=0)
+        sd = {"weight_orig": W.clone(), "weight_u": u.clone(), "weight_v": v.clone()}
+        Wsn = O.sn_weight(sd, "", training=True)
+        Wd, ud, vd = W.to(dev), u.to(dev), v.to(dev)
+        sigma = torch.empty(1, device=dev)
+        ws = K.sn_workspace(R, Kd, dev)
+        for it in range(2):     # second call re-uses the workspace (tickets / accumulators must have been reset)
+            if it == 1:
+                Wsn = O.sn_weight(sd, "", training=True)
+            K.sn_power_iter(Wd, ud, vd, sigma, ws, 1e-6, True)
+            np.testing.assert_allclose(ud.cpu().numpy(), sd["weight_u"].numpy(), rtol=2e-4, atol=2e-5)
+            np.testing.assert_allclose(vd.cpu().numpy(), sd["weight_v"].numpy(), rtol=2e-4, atol=2e-5)
+            ref_sigma = float((W / Wsn).flatten()[0])
+            assert abs(float(sigma) - ref_sigma) < 2e-4 * abs(ref_sigma)
+
+
+@pytest.mark.parametrize("mode,up2", [(0, False), (0, True), (1, False), (2, True)])
+def test_bn_act_fwd_bwd(mode, up2):
+    from sgb200 import autograd_ops as A
+    dev = _cuda()
+    g = torch.Generator().manual_seed(2)
+    B, C, H, W = 4, 48, 8, 8
+    x = bfr(torch.randn(B, C, H, W, generator=g) * 1.5 + 0.3)
+    gain = torch.randn(B, C, generator=g) * 0.3 if mode == 0 else (torch.rand(C, generator=g) + 0.5 if mode == 1 else None)
+    bias = torch.randn(B, C, generator=g) * 0.3 if mode == 0 else (torch.randn(C, generator=g) if mode == 1 else None)
+    dy = bfr(torch.randn(B, C, H * (2 if up2 else 1), W * (2 if up2 else 1), generator=g))
+    xr = x.clone().requires_grad_(True)
+    gr = gain.clone().requires_grad_(True) if gain is not None else None
+    br = bias.clone().requires_grad_(True) if bias is not None else None
+    rm, rv = torch.zeros(C), torch.ones(C)
+    yn = F.batch_norm(xr, rm, rv, None, None, True, 0.1, 1e-4)
+    if mode == 0:
+        yn = yn * (1 + gr)[:, :, None, None] + br[:, :, None, None]
+    elif mode == 1:
+        yn = yn * gr[None, :, None, None] + br[None, :, None, None]
+    yr = F.relu(yn)
+    if up2:
+        yr = F.interpolate(yr, scale_factor=2, mode="nearest")
+    yr.backward(dy)
+    xd = to_nhwc(x, dev).requires_grad_(True)
+    gd = gain.to(dev).requires_grad_(True) if gain is not None else None
+    bd = bias.to(dev).requires_grad_(True) if bias is not None else None
+    rmd, rvd = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    cfg = {"mode": mode, "relu": True, "up2": up2, "use_batch_stats": True, "track": True, "momentum": 0.1, "eps": 1e-4, "group": None}
+    y = A.BNActFn.apply(xd, gd, bd, rmd, rvd, cfg)
+    y.backward(to_nhwc(dy, dev))
+    assert rel_err(y, yr) < 8e-3
+    assert rel_err(xd.grad, xr.grad) < 1.5e-2
+    np.testing.assert_allclose(rmd.cpu().numpy(), rm.numpy(), rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(rvd.cpu().numpy(), rv.numpy(), rtol=1e-3, atol=1e-4)
+    if mode in (0, 1):
+        assert rel_err(gd.grad, gr.grad) < 1e-2
+        assert rel_err(bd.grad, br.grad) < 1e-2
+
+
+def test_self_attention_fwd_bwd_vs_oracle():
+    from sgb200 import config as C
+    from sgb200.utils import ops
+    dev = _cuda()
+    torch.manual_seed(3)
+    M = C.make_modules(True, True)
+    att = ops.SelfAttention(64, True, M)
+    with torch.no_grad():
+        att.sigma.fill_(0.5)
+    sd = {k: v.clone() for k, v in att.state_dict().items()}
+    for k in sd:
+        if k.endswith("weight_orig") or k == "sigma":
+            sd[k].requires_grad_(True)
+    x = bfr(torch.randn(2, 64, 16, 16) * 0.7)
+    dy = bfr(torch.randn(2, 64, 16, 16))
+    xr = x.clone().requires_grad_(True)
+    yr = O.self_attention(sd, "", xr, training=True)
+    yr.backward(dy)
+    att = att.to(dev)
+    xd = to_nhwc(x, dev).requires_grad_(True)
+    y = att(xd)
+    y.backward(to_nhwc(dy, dev))
+    assert rel_err(y, yr) < 1e-2
+    assert rel_err(xd.grad, xr.grad) < 2e-2
+    for name, p in att.named_parameters():
+        assert rel_err(p.grad, sd[name].grad) < 3e-2, name
+    np.testing.assert_allclose(att.conv1x1_theta.weight_u.cpu().numpy(), sd["conv1x1_theta.weight_u"].numpy(), rtol=1e-3, atol=1e-4)
+
+
+def test_pool_softmax_sumhw_kernels():
+    from sgb200 import kernels as K
+    dev = _cuda()
+    g = torch.Generator().manual_seed(4)
+    x = bfr(torch.randn(2, 16, 8, 8, generator=g))
+    xd = to_nhwc(x, dev)
+    assert rel_err(K.pool2_fwd(xd, 0), F.avg_pool2d(x, 2)) < 8e-3
+    assert rel_err(K.pool2_fwd(xd, 1), F.max_pool2d(x, 2)) == 0.0
+    s = bfr(torch.randn(6, 64, generator=g) * 3)
+    sd_ = s.to(dev).to(torch.bfloat16)
+    assert rel_err(K.softmax_rows(sd_, 64), torch.softmax(s, -1)) < 8e-3
+    assert rel_err(K.sum_hw(xd, True), F.relu(x).sum((2, 3))) < 1e-5
+    xr = x.clone().requires_grad_(True)
+    dy = bfr(torch.randn(2, 16, 4, 4, generator=g))
+    F.max_pool2d(xr, 2).backward(dy)
+    assert rel_err(K.pool2_bwd(to_nhwc(dy, dev), 1, x=xd), xr.grad) == 0.0
+
+
+def test_image_layout_kernels_bit_exact():
+    from sgb200 import kernels as K
+    dev = _cuda()
+    img = torch.rand(3, 3, 16, 16) * 2 - 1
+    a = K.img_to_nhwc(img.to(dev), 8)
+    assert torch.equal(a[:, :3].float().cpu(), bfr(img)) and float(a[:, 3:].abs().max()) == 0.0
+    back = K.nhwc_to_img(a, 3, tanh=False)
+    assert torch.equal(back.cpu(), bfr(img))
+
+
+def test_adam_ema_kernel_matches_torch_adam():
+    from sgb200 import kernels as K
+    dev = _cuda()
+    torch.manual_seed(5)
+    p0 = torch.randn(10000)
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=2e-4, betas=(0.0, 0.999), eps=1e-6)
+    p, m, v = p0.to(dev), torch.zeros(10000, device=dev), torch.zeros(10000, device=dev)
+    ema = p.clone()
+    ema_ref = p0.clone()
+    for step in range(1, 4):
+        gr = torch.randn(10000)
+        pr.grad = gr.clone()
+        opt.step()
+        K.adam_ema_step(p, gr.to(dev), m, v, 2e-4, 0.0, 0.999, 1e-6, step, ema=ema, ema_decay=0.9)
+        ema_ref = pr.detach().lerp(ema_ref, 0.9)
+    np.testing.assert_allclose(p.cpu().numpy(), pr.detach().numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(ema.cpu().numpy(), ema_ref.numpy(), rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ full models vs golden
+def _build_from_golden(g, conv_dim, depth, attn, dev):
+    from sgb200 import config as C
+    from sgb200.models import big_resnet_deep_legacy as deep
+    M = C.make_modules(True, True, "cBN", "big_resnet_deep_legacy")
+    MODEL = C._Section(info_type="N/A", g_info_injection="N/A")
+    G = deep.Generator(z_dim=16, g_shared_dim=16, img_size=32, g_conv_dim=conv_dim, apply_attn=attn, attn_g_loc=[2],
+                       g_cond_mtd="cBN", num_classes=5, g_init="ortho", g_depth=depth, mixed_precision=False, MODULES=M, MODEL=MODEL)
+    D = deep.Discriminator(img_size=32, d_conv_dim=conv_dim, apply_d_sn=True, apply_attn=attn, attn_d_loc=[1], d_cond_mtd="PD",
+                           aux_cls_type="W/O", d_embed_dim="N/A", normalize_d_embed=False, num_classes=5, d_init="ortho",
+                           d_depth=depth, mixed_precision=False, MODULES=M, MODEL=MODEL)
+    G.load_state_dict({k[3:]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith("G0/")}, strict=True)
+    D.load_state_dict({k[3:]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith("D0/")}, strict=True)
+    return G.to(dev).train(), D.to(dev).train()
+
+
+@pytest.mark.parametrize("tag,conv_dim,depth,attn", [("deep32_c8", 8, 1, False), ("deep32_c16_attn_d2", 16, 2, True)])
+def test_biggan_deep_d_and_g_phase_vs_reference_golden(golden_dir, tag, conv_dim, depth, attn):
+    """The reference's own D-phase / G-phase numbers (src/worker.py:213-681 order) reproduced by the CUDA path.
+    Tolerance: 3e-2 of the tensor's max magnitude for activations / logits / gradients (bf16 compute through ~40 layers;
+    the fp32 oracle itself moves by ~1e-3 under ReLU-boundary flips), u/v buffers 1e-2."""
+    from sgb200.utils import losses
+    dev = _cuda()
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    G, D = _build_from_golden(g, conv_dim, depth, attn, dev)
+    z, yf = torch.from_numpy(g["z"]).to(dev), torch.from_numpy(g["y_fake"]).to(dev)
+    real, yr = torch.from_numpy(g["real"]).to(dev), torch.from_numpy(g["y_real"]).to(dev)
+    for p in G.parameters():
+        p.requires_grad_(False)
+    fake = G(z, yf)
+    assert fake.shape == (z.shape[0], 3, 32, 32) and fake.dtype == torch.float32
+    assert rel_err(fake, torch.from_numpy(g["fake"])) < 3e-2
+    real_d = D(real, yr)
+    fake_d = D(fake.detach(), yf)
+    assert set(real_d.keys()) == {"h", "adv_output", "embed", "proxy", "cls_output", "label", "mi_embed", "mi_proxy",
+                                  "mi_cls_output", "info_discrete_c_logits", "info_conti_mu", "info_conti_var"}
+    assert torch.equal(real_d["label"].cpu(), torch.from_numpy(g["y_real"]))        # label path: bit exact
+    assert rel_err(real_d["h"], torch.from_numpy(g["h_real"])) < 3e-2
+    assert rel_err(real_d["adv_output"], torch.from_numpy(g["adv_real"])) < 3e-2
+    assert rel_err(fake_d["adv_output"], torch.from_numpy(g["adv_fake"])) < 3e-2
+    d_loss = losses.d_hinge(real_d["adv_output"], fake_d["adv_output"])
+    d_loss.backward()
+    assert abs(float(d_loss) - float(g["d_loss"])) < 3e-2 * abs(float(g["d_loss"]))
+    worst = max((rel_err(p.grad, torch.from_numpy(g["Dgrad/" + n])), n) for n, p in D.named_parameters())
+    assert worst[0] < 6e-2, worst
+    for n, b in list(G.named_buffers()) + list(D.named_buffers()):
+        key = ("G1/" if any(b is bb for bb in G.buffers()) else "D1/") + n
+        if "weight_u" in n or "running_" in n:
+            assert rel_err(b, torch.from_numpy(g[key])) < 1e-2, key
+        if "num_batches_tracked" in n:
+            assert int(b) == int(g[key]), key
+    # generator phase
+    D.zero_grad(set_to_none=True)
+    for p in G.parameters():
+        p.requires_grad_(True)
+    for p in D.parameters():
+        p.requires_grad_(False)
+    fake2 = G(z, yf)
+    assert rel_err(fake2, torch.from_numpy(g["fake2"])) < 3e-2
+    g_loss = losses.g_hinge(D(fake2, yf)["adv_output"])
+    g_loss.backward()
+    assert abs(float(g_loss) - float(g["g_loss"])) < 3e-2 * abs(float(g["g_loss"]))
+    worst = max((rel_err(p.grad, torch.from_numpy(g["Ggrad/" + n])), n) for n, p in G.named_parameters())
+    assert worst[0] < 8e-2, worst
+    assert all(p.grad is None for p in D.parameters())
+
+
+def test_property_conv_linearity_and_dgrad_adjoint_at_scale():
+    """Size-independent properties at a BASELINE-sized layer (3x3, 256 ch, 64x64, B=8): linearity in x, and
+    <conv(x), y> == <x, dgrad(y)> (the dgrad pack is the exact adjoint of the fprop pack)."""
+    from sgb200 import kernels as K
+    dev = _cuda()
+    torch.manual_seed(7)
+    B, C, H = 8, 256, 64
+    w = torch.randn(C, C, 3, 3, device=dev) * 0.02
+    wf, wd = K.weight_pack(w, None, C, C, 9)
+    x1 = K.empty_nhwc(B, C, H, H, dev).normal_()
+    x2 = K.empty_nhwc(B, C, H, H, dev).normal_()
+    y = K.empty_nhwc(B, C, H, H, dev).normal_()
+    f = lambda t: K.conv_fprop(t, wf, C, 3, 3, 1, 1, out_fp32=True)
+    s = K.axpby(x1, x2)
+    lin = (f(s) - f(x1) - f(x2)).abs().max() / f(s).abs().max()
+    assert float(lin) < 2e-2            # bf16 rounding of x1 + x2
+    lhs = (f(x1) * y.float()).sum()
+    rhs = (x1.float() * K.conv_fprop(y, wd, C, 3, 3, 1, 1, out_fp32=True)).sum()
+    assert abs(float(lhs - rhs)) < 2e-3 * abs(float(lhs)) + 1.0
