@@ -30,6 +30,9 @@ typedef void* sgb_stream_t; /* cudaStream_t */
 int sgb_abi_version(void);
 /* 0 if a sm_100 device is current and usable, else SGB_ERR_CUDA. */
 int sgb_device_check(void);
+/* Make ``device``'s primary context current on the calling host thread (call once per thread that uses the library,
+ * e.g. PyTorch autograd worker threads). */
+int sgb_bind_device(int32_t device);
 
 /* ------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores (TMA-staged NHWC tiles, TMEM accumulators).

@@ -15,3 +15,12 @@ extern "C" int sgb_device_check(void) {
   }
   return SGB_OK;
 }
+
+// Binds the calling host thread to ``device`` (primary context made current).  PyTorch's autograd engine runs backward
+// on its own threads, where no context is current until some runtime call binds one; driver-level helpers used here
+// (cuTensorMapEncodeTiled) need a current context, so the Python layer calls this once per thread.
+extern "C" int sgb_bind_device(int32_t device) {
+  SGB_CUDA(cudaSetDevice(device));
+  SGB_CUDA(cudaFree(0));
+  return SGB_OK;
+}

@@ -6,6 +6,7 @@ PyTorch is used only for device memory and streams; every pointer handed to the 
 """
 import ctypes
 import os
+import threading
 
 import torch
 
@@ -51,6 +52,7 @@ class WgradDesc(ctypes.Structure):
 SIGNATURES = {
     "sgb_abi_version": (c_int, []),
     "sgb_device_check": (c_int, []),
+    "sgb_bind_device": (c_int, [c_int]),
     "sgb_conv_fprop": (c_int, [ctypes.POINTER(ConvDesc), c_p]),
     "sgb_conv_wgrad": (c_int, [ctypes.POINTER(WgradDesc), c_p]),
     "sgb_sn_workspace_floats": (c_i64, [c_int, c_int]),
@@ -125,8 +127,16 @@ def ptr(t):
 LAUNCHES = [0]  # number of library entry-point calls (each launches >= 1 kernel); bench.py reports the delta per step
 
 
+_tls = threading.local()
+
+
 def call(name, *args):
     lib = load()
+    if getattr(_tls, "device", None) is None:
+        # first library call on this host thread (e.g. an autograd worker): bind the thread to torch's current device
+        dev = torch.cuda.current_device()
+        check(lib.sgb_bind_device(dev), "sgb_bind_device")
+        _tls.device = dev
     rc = getattr(lib, name)(*args)
     LAUNCHES[0] += 1
     check(rc, name)

@@ -175,4 +175,5 @@ def golden_metrics():
 if __name__ == "__main__":
     golden_deep("deep32_c8", 32, 8, 1, attn=False)
     golden_deep("deep32_c16_attn_d2", 32, 16, 2, attn=True, B=2)
+    golden_deep("deep32_c8_b16", 32, 8, 1, attn=False, B=16)      # well-conditioned BatchNorm statistics for gradient parity
     golden_metrics()

@@ -9,7 +9,8 @@ import torch
 from oracle import studiogan_oracle as O
 
 CASES = [("deep32_c8", dict(img_size=32, conv_dim=8, depth=1, attn=False)),
-         ("deep32_c16_attn_d2", dict(img_size=32, conv_dim=16, depth=2, attn=True))]
+         ("deep32_c16_attn_d2", dict(img_size=32, conv_dim=16, depth=2, attn=True)),
+         ("deep32_c8_b16", dict(img_size=32, conv_dim=8, depth=1, attn=False))]
 
 
 def load_sd(npz, prefix, grad=False):
