@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--config", default=os.path.join(PKG, "configs", "BigGAN-Deep-256res.yaml"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--cpu-batch", type=int, default=1)
+    ap.add_argument("--cpu-threads", type=int, default=0, help="0 = min(32, host cores): more threads only add contention for these layer sizes")
     return ap.parse_args()
 
 
@@ -145,7 +146,7 @@ def run_steps(worker, n, read_losses):
         _, d_loss = worker.train_discriminator(s)
         g_loss = worker.train_generator(s)
         if read_losses:
-            out = (float(d_loss), float(g_loss))      # D2H read of the step's results
+            out = (float(d_loss.detach()), float(g_loss.detach()))      # D2H read of the step's results
     return out
 
 
@@ -230,9 +231,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        threads = os.cpu_count() or 1
+        threads = args.cpu_threads or min(32, os.cpu_count() or 1)
         vals = []
-        for _ in range(max(1, min(args.steps, 2))):
+        for _ in range(1):
             v, dt = cpu_step_images_per_sec(args.config, args.cpu_batch, threads)
             vals.append(v)
         v = float(np.mean(vals))
@@ -328,8 +329,8 @@ def main():
         roof.update({"achieved": roof["step_achieved"], "frac": roof["step_frac"], "kernels": prof})
 
     cpu = None
-    if not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+    if not args.no_cpu_baseline and world == 1:
+        threads = args.cpu_threads or min(32, os.cpu_count() or 1)
         try:
             v, dt = cpu_step_images_per_sec(args.config, args.cpu_batch, threads)
             cpu = {"value": v, "unit": "img/s", "cores": threads, "kind": "port",

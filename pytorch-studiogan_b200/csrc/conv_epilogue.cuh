@@ -1,0 +1,134 @@
+// Fused conv epilogue shared by the tcgen05 conv kernels: TMEM accumulator row -> alpha, bias, residual (optionally read
+// from a half-resolution tensor = nearest x2 upsample), ReLU, ReLU-mask, post-mask residual -> bf16 / fp32 NHWC store.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sgb {
+
+struct EpiArgs {
+  int H, W, Cout;
+  float alpha;
+  const float* alpha_ptr;
+  const float* bias;
+  const bf16* residual; long long res_cstride; int res_up2; int res_after;
+  const bf16* mask; long long mask_cstride;
+  int relu;
+  void* y; long long y_cstride; int y_fp32;
+};
+
+__device__ __forceinline__ float bf16_bits_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_bits_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__device__ __forceinline__ bool epi_vec_ok(const EpiArgs& p) {
+  return (p.Cout % 8 == 0) && (p.y_cstride % 8 == 0) && (p.residual == nullptr || p.res_cstride % 8 == 0) &&
+         (p.mask == nullptr || p.mask_cstride % 8 == 0);
+}
+
+// One thread = one accumulator row (TMEM lane).  t_row: TMEM address of this warp's lane quadrant at the accumulator's
+// first column.  All 32 lanes of the warp must call this (tcgen05.ld is warp-collective); stores are predicated by valid.
+__device__ __forceinline__ void epilogue_row(const EpiArgs& p, uint32_t t_row, int BN, int n0, bool valid, long long pix,
+                                             long long rpix, float alpha, bool vec_ok) {
+  const bool res_pre = p.residual != nullptr && !p.res_after;
+  const bool res_post = p.residual != nullptr && p.res_after;
+  for (int c0 = 0; c0 < BN; c0 += 16) {
+    uint32_t v[16];
+    __syncwarp();
+    tmem_ld16(t_row + c0, v);
+    tmem_ld_wait();
+    const int n = n0 + c0;
+    if (!valid || n >= p.Cout) continue;
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * alpha;
+    if (vec_ok && n + 16 <= p.Cout) {
+      if (p.bias) {
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 bb = __ldg(bp + j);
+          f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+        }
+      }
+      if (res_pre) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.res_cstride + n);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint4 r = __ldg(rp + j);
+          f[8 * j + 0] += bf16_bits_lo(r.x); f[8 * j + 1] += bf16_bits_hi(r.x);
+          f[8 * j + 2] += bf16_bits_lo(r.y); f[8 * j + 3] += bf16_bits_hi(r.y);
+          f[8 * j + 4] += bf16_bits_lo(r.z); f[8 * j + 5] += bf16_bits_hi(r.z);
+          f[8 * j + 6] += bf16_bits_lo(r.w); f[8 * j + 7] += bf16_bits_hi(r.w);
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      if (p.mask) {
+        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_cstride + n);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint4 m = __ldg(mp + j);
+          f[8 * j + 0] = bf16_bits_lo(m.x) > 0.f ? f[8 * j + 0] : 0.f;
+          f[8 * j + 1] = bf16_bits_hi(m.x) > 0.f ? f[8 * j + 1] : 0.f;
+          f[8 * j + 2] = bf16_bits_lo(m.y) > 0.f ? f[8 * j + 2] : 0.f;
+          f[8 * j + 3] = bf16_bits_hi(m.y) > 0.f ? f[8 * j + 3] : 0.f;
+          f[8 * j + 4] = bf16_bits_lo(m.z) > 0.f ? f[8 * j + 4] : 0.f;
+          f[8 * j + 5] = bf16_bits_hi(m.z) > 0.f ? f[8 * j + 5] : 0.f;
+          f[8 * j + 6] = bf16_bits_lo(m.w) > 0.f ? f[8 * j + 6] : 0.f;
+          f[8 * j + 7] = bf16_bits_hi(m.w) > 0.f ? f[8 * j + 7] : 0.f;
+        }
+      }
+      if (res_post) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.res_cstride + n);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint4 r = __ldg(rp + j);
+          f[8 * j + 0] += bf16_bits_lo(r.x); f[8 * j + 1] += bf16_bits_hi(r.x);
+          f[8 * j + 2] += bf16_bits_lo(r.y); f[8 * j + 3] += bf16_bits_hi(r.y);
+          f[8 * j + 4] += bf16_bits_lo(r.z); f[8 * j + 5] += bf16_bits_hi(r.z);
+          f[8 * j + 6] += bf16_bits_lo(r.w); f[8 * j + 7] += bf16_bits_hi(r.w);
+        }
+      }
+      if (p.y_fp32) {
+        float4* yp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + pix * p.y_cstride + n);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) yp[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      } else {
+        uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.y) + pix * p.y_cstride + n);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint4 o;
+          o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+          o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+          o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+          o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+          yp[j] = o;
+        }
+      }
+    } else {
+      // ragged / unaligned channel tail (e.g. Cout = 3): scalar path
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int nn = n + j;
+        if (nn < p.Cout) {
+          float x = f[j];
+          if (p.bias) x += __ldg(p.bias + nn);
+          if (res_pre) x += __bfloat162float(p.residual[rpix * p.res_cstride + nn]);
+          if (p.relu) x = fmaxf(x, 0.f);
+          if (p.mask) x = __bfloat162float(p.mask[pix * p.mask_cstride + nn]) > 0.f ? x : 0.f;
+          if (res_post) x += __bfloat162float(p.residual[rpix * p.res_cstride + nn]);
+          if (p.y_fp32) reinterpret_cast<float*>(p.y)[pix * p.y_cstride + nn] = x;
+          else reinterpret_cast<bf16*>(p.y)[pix * p.y_cstride + nn] = __float2bfloat16_rn(x);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace sgb

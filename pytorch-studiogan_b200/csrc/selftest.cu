@@ -322,6 +322,12 @@ int main(int argc, char** argv) {
       {"1x7 c64->96 17x17 ragged",     2, 17, 17, 64,  96,  1, 7, 0, 3, 1, 1, 0, 0, 0, 0},
       {"3x3 c192->320 64x64",          1, 64, 64, 192, 320, 3, 3, 1, 1, 1, 0, 0, 0, 0, 0},
       {"3x3 c64->64 256x256 (tw=128)", 1, 256, 256, 64, 64, 3, 3, 1, 1, 0, 0, 0, 0, 0, 0},
+      {"rows c64->64 128x128 b/r/res",  2, 128, 128, 64, 64, 3, 3, 1, 1, 1, 1, 1, 0, 0, 0},
+      {"rows c128->128 128x128 mask",   1, 128, 128, 128, 128, 3, 3, 1, 1, 1, 0, 0, 0, 1, 0},
+      {"rows c64->128 128x128 up2res",  1, 128, 128, 64, 128, 3, 3, 1, 1, 1, 0, 1, 1, 0, 0},
+      {"rows c128->64 256x256 fp32",    1, 256, 256, 128, 64, 3, 3, 1, 1, 0, 0, 0, 0, 0, 1},
+      {"rows c64->192 128x128",         1, 128, 128, 64, 192, 3, 3, 1, 1, 1, 0, 0, 0, 0, 0},
+      {"rows c64->16 128x128",          3, 128, 128, 64, 16, 3, 3, 1, 1, 1, 0, 0, 0, 0, 0},
   };
   if (on("fprop"))
     for (const auto& c : cases) fails += run_fprop_case(c, true);

@@ -10,8 +10,11 @@
 // One persistent CTA per SM, 6 warps: warp 0 = TMA producer (one lane), warp 1 = tcgen05.mma issuer (one lane) and
 // TMEM owner, warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global).  Two TMEM accumulator stages so
 // the epilogue of tile i overlaps the main loop of tile i+1.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
+#include "conv_epilogue.cuh"
 
 namespace sgb {
 
@@ -29,21 +32,8 @@ struct FpropArgs {
   int w_mode;                     // 0: shared weights [Cout][taps][Cin]; 1: per-image [B][N][K]; 2: per-image MN-major [B][K][N]
   int stages;
   uint32_t tmem_cols;
-  float alpha;
-  const float* alpha_ptr;
-  const float* bias;
-  const bf16* residual; long long res_cstride; int res_up2; int res_after;
-  const bf16* mask; long long mask_cstride;
-  int relu;
-  void* y; long long y_cstride; int y_fp32;
+  EpiArgs e;
 };
-
-__device__ __forceinline__ float bf16_bits_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16_bits_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropArgs p) {
@@ -155,11 +145,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int wi = row % p.tw, hi = (row / p.tw) % p.th, bi = row / (p.tw * p.th);
-    const bool vec_ok = (p.Cout % 8 == 0) && (p.y_cstride % 8 == 0) &&
-                        (p.residual == nullptr || p.res_cstride % 8 == 0) && (p.mask == nullptr || p.mask_cstride % 8 == 0);
-    const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
-    const bool res_pre = p.residual != nullptr && !p.res_after;
-    const bool res_post = p.residual != nullptr && p.res_after;
+    const bool vec_ok = epi_vec_ok(p.e);
+    const float alpha = p.e.alpha_ptr ? p.e.alpha * __ldg(p.e.alpha_ptr) : p.e.alpha;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
       int t = tile;
@@ -171,107 +158,14 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int w = wt * p.tw + wi, h = ht * p.th + hi, b = bt * p.nb + bi;
       const bool valid = (w < p.W) && (h < p.H) && (b < p.B);
       const long long pix = ((long long)b * p.H + h) * p.W + w;
-      const long long rpix = p.res_up2 ? (((long long)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) : pix;
+      const long long rpix = p.e.res_up2 ? (((long long)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) : pix;
 
       const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + a * p.BN;
 
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t v[16];
-        __syncwarp();
-        tmem_ld16(t_row + c0, v);
-        tmem_ld_wait();
-        const int n = n0 + c0;
-        if (!valid || n >= p.Cout) continue;
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * alpha;
-        if (vec_ok && n + 16 <= p.Cout) {
-          if (p.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 bb = __ldg(bp + j);
-              f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
-            }
-          }
-          if (res_pre) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.res_cstride + n);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint4 r = __ldg(rp + j);
-              f[8 * j + 0] += bf16_bits_lo(r.x); f[8 * j + 1] += bf16_bits_hi(r.x);
-              f[8 * j + 2] += bf16_bits_lo(r.y); f[8 * j + 3] += bf16_bits_hi(r.y);
-              f[8 * j + 4] += bf16_bits_lo(r.z); f[8 * j + 5] += bf16_bits_hi(r.z);
-              f[8 * j + 6] += bf16_bits_lo(r.w); f[8 * j + 7] += bf16_bits_hi(r.w);
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (p.mask) {
-            const uint4* mp = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_cstride + n);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint4 m = __ldg(mp + j);
-              f[8 * j + 0] = bf16_bits_lo(m.x) > 0.f ? f[8 * j + 0] : 0.f;
-              f[8 * j + 1] = bf16_bits_hi(m.x) > 0.f ? f[8 * j + 1] : 0.f;
-              f[8 * j + 2] = bf16_bits_lo(m.y) > 0.f ? f[8 * j + 2] : 0.f;
-              f[8 * j + 3] = bf16_bits_hi(m.y) > 0.f ? f[8 * j + 3] : 0.f;
-              f[8 * j + 4] = bf16_bits_lo(m.z) > 0.f ? f[8 * j + 4] : 0.f;
-              f[8 * j + 5] = bf16_bits_hi(m.z) > 0.f ? f[8 * j + 5] : 0.f;
-              f[8 * j + 6] = bf16_bits_lo(m.w) > 0.f ? f[8 * j + 6] : 0.f;
-              f[8 * j + 7] = bf16_bits_hi(m.w) > 0.f ? f[8 * j + 7] : 0.f;
-            }
-          }
-          if (res_post) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.res_cstride + n);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint4 r = __ldg(rp + j);
-              f[8 * j + 0] += bf16_bits_lo(r.x); f[8 * j + 1] += bf16_bits_hi(r.x);
-              f[8 * j + 2] += bf16_bits_lo(r.y); f[8 * j + 3] += bf16_bits_hi(r.y);
-              f[8 * j + 4] += bf16_bits_lo(r.z); f[8 * j + 5] += bf16_bits_hi(r.z);
-              f[8 * j + 6] += bf16_bits_lo(r.w); f[8 * j + 7] += bf16_bits_hi(r.w);
-            }
-          }
-          if (p.y_fp32) {
-            float4* yp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + pix * p.y_cstride + n);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) yp[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-            uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.y) + pix * p.y_cstride + n);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-              o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-              o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-              o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              yp[j] = o;
-            }
-          }
-        } else {
-          // ragged / unaligned channel tail (e.g. Cout = 3): scalar path
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int nn = n + j;
-            if (nn < p.Cout) {
-              float x = f[j];
-              if (p.bias) x += __ldg(p.bias + nn);
-              if (res_pre) x += __bfloat162float(p.residual[rpix * p.res_cstride + nn]);
-              if (p.relu) x = fmaxf(x, 0.f);
-              if (p.mask) x = __bfloat162float(p.mask[pix * p.mask_cstride + nn]) > 0.f ? x : 0.f;
-              if (res_post) x += __bfloat162float(p.residual[rpix * p.res_cstride + nn]);
-              if (p.y_fp32) reinterpret_cast<float*>(p.y)[pix * p.y_cstride + nn] = x;
-              else reinterpret_cast<bf16*>(p.y)[pix * p.y_cstride + nn] = __float2bfloat16_rn(x);
-            }
-          }
-        }
-      }
+      epilogue_row(p.e, t_row, p.BN, n0, valid, pix, rpix, alpha, vec_ok);
       tc_fence_before();
       mbar_arrive(tempty_bar(a));
     }
@@ -467,6 +361,14 @@ static void pick_tile(int H, int W, int B, int& tw, int& th, int& nb) {
   (void)B;
 }
 
+void fill_epi(EpiArgs& e, const sgb_conv_desc* d) {
+  e.H = d->H; e.W = d->W; e.Cout = d->Cout;
+  e.alpha = d->alpha; e.alpha_ptr = d->alpha_ptr; e.bias = d->bias;
+  e.residual = (const bf16*)d->residual; e.res_cstride = d->res_cstride; e.res_up2 = d->res_up2; e.res_after = d->res_after_mask;
+  e.mask = (const bf16*)d->mask; e.mask_cstride = d->mask_cstride; e.relu = d->relu;
+  e.y = d->y; e.y_cstride = d->y_cstride; e.y_fp32 = d->y_fp32;
+}
+
 static int make_act_tmap(CUtensorMap* m, const void* base, int B, int H, int W, int C, long long cstride, int tw, int th,
                          int nb) {
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
@@ -479,6 +381,16 @@ static int make_act_tmap(CUtensorMap* m, const void* base, int B, int H, int W, 
 
 using namespace sgb;
 
+namespace sgb {
+bool conv3x3_rows_eligible(const sgb_conv_desc* d);
+int launch_conv3x3_rows(const sgb_conv_desc* d, cudaStream_t stream, int bo_mode);
+}  // namespace sgb
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SGB_REQUIRE(d && d->x && d->w && d->y);
@@ -489,6 +401,13 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   SGB_REQUIRE(d->w_mode >= 0 && d->w_mode <= 2);
   SGB_REQUIRE(d->w_mode == 0 || (d->KH == 1 && d->KW == 1 && d->H * d->W >= 128));
   SGB_REQUIRE(d->w_mode != 2 || d->Cout % 8 == 0);
+  SGB_REQUIRE(((uintptr_t)d->bias & 15) == 0 && ((uintptr_t)d->residual & 15) == 0 && ((uintptr_t)d->mask & 15) == 0);
+  {
+    // wide, few-channel 3x3 layers: halo-row kernel (umma_conv3x3.cu).  SGB_CONV3X3_ROWS=0 forces the generic kernel.
+    static const int use_rows = env_int("SGB_CONV3X3_ROWS", 1);
+    static const int bo_mode = env_int("SGB_ROWS_BASE_OFFSET", 0);
+    if (use_rows && conv3x3_rows_eligible(d)) return launch_conv3x3_rows(d, stream, bo_mode);
+  }
   SGB_REQUIRE(((uintptr_t)d->bias & 15) == 0 && ((uintptr_t)d->residual & 15) == 0 && ((uintptr_t)d->mask & 15) == 0);
 
   FpropArgs p;
@@ -521,14 +440,7 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   if (stages < 2) stages = 2;
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * BN);
-  p.alpha = d->alpha;
-  p.alpha_ptr = d->alpha_ptr;
-  p.bias = d->bias;
-  p.residual = (const bf16*)d->residual; p.res_cstride = d->res_cstride; p.res_up2 = d->res_up2;
-  p.res_after = d->res_after_mask;
-  p.mask = (const bf16*)d->mask; p.mask_cstride = d->mask_cstride;
-  p.relu = d->relu;
-  p.y = d->y; p.y_cstride = d->y_cstride; p.y_fp32 = d->y_fp32;
+  fill_epi(p.e, d);
 
   CUtensorMap tmA, tmB;
   int rc = make_act_tmap(&tmA, d->x, d->B, d->H, d->W, d->Cin, d->x_cstride, p.tw, p.th, p.nb);

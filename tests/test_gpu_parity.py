@@ -45,7 +45,8 @@ def to_nhwc(x, dev):
 
 # ------------------------------------------------------------------------------------------------ conv engine
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k", [(2, 16, 16, 64, 64, 3), (3, 8, 8, 32, 128, 1), (2, 32, 32, 128, 24, 3),
-                                              (4, 4, 4, 256, 64, 3), (2, 64, 64, 8, 16, 3), (5, 1, 1, 40, 72, 1)])
+                                              (4, 4, 4, 256, 64, 3), (2, 64, 64, 8, 16, 3), (5, 1, 1, 40, 72, 1),
+                                              (1, 128, 128, 64, 64, 3), (1, 128, 256, 128, 64, 3)])   # halo-row kernel
 def test_conv_fwd_bwd_vs_fp32_reference(B, H, W, Cin, Cout, k):
     from sgb200 import autograd_ops as A
     dev = _cuda()

@@ -1,0 +1,72 @@
+"""world_size-2 gloo tests (CPU) of the multi-rank host logic: replica broadcast, gradient averaging, the sync-BN
+statistics algebra (sum / sum-of-squares all-reduce == statistics of the concatenated batch) and batch sharding."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, os.path.join(ROOT, "pytorch-studiogan_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sgb200.models import model as M
+    torch.manual_seed(100 + rank)                      # different replicas before the broadcast
+    net = nn.Sequential(nn.Linear(4, 3), nn.BatchNorm1d(3))
+    M.prepare_parallel_training(net, None, None, net, None, None, None, None, world, True, False, False, "cpu")
+    w0 = [p.detach().clone() for p in net.parameters()]
+    # gradient averaging
+    torch.manual_seed(7 + rank)
+    for p in net.parameters():
+        p.grad = torch.randn_like(p)
+    local = [p.grad.clone() for p in net.parameters()]
+    M.allreduce_gradients(net)
+    avg = [p.grad.clone() for p in net.parameters()]
+    # sync-BN algebra: all-reduce of [sum, sumsq] and count gives the statistics of the global batch
+    torch.manual_seed(11 + rank)
+    x = torch.randn(5 + rank, 3) * (1 + rank) + rank
+    stats = torch.stack([x.sum(0), (x * x).sum(0)])
+    cnt = torch.tensor([float(x.shape[0])])
+    dist.all_reduce(stats)
+    dist.all_reduce(cnt)
+    mean = stats[0] / cnt
+    var = stats[1] / cnt - mean * mean
+    q.put((rank, [w.numpy() for w in w0], [g.numpy() for g in local], [g.numpy() for g in avg], x.numpy(), mean.numpy(), var.numpy()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_replicas_gradients_and_syncbn_stats():
+    import numpy as np
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, w_a, g_a, avg_a, x_a, mean_a, var_a), (_, w_b, g_b, avg_b, x_b, mean_b, var_b) = out
+    for a, b in zip(w_a, w_b):
+        assert np.array_equal(a, b)                                   # rank 0's replica everywhere
+    for ga, gb, aa, ab in zip(g_a, g_b, avg_a, avg_b):
+        np.testing.assert_allclose(aa, (ga + gb) / 2, rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(ab, aa, rtol=0, atol=0)
+    allx = np.concatenate([x_a, x_b], 0)
+    np.testing.assert_allclose(mean_a, allx.mean(0), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(var_a, allx.var(0), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(mean_b, mean_a)
+
+
+def test_strong_scaling_batch_sharding():
+    # bench.py / src/loader.py:162: per-rank batch = global // world, the whole-job value uses the global batch
+    for world in (1, 2, 4, 8):
+        assert 256 % world == 0 and (256 // world) * world == 256
