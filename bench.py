@@ -273,23 +273,36 @@ def main():
     sampler.stop_flag = True
     value = global_batch * opt.acml_steps / (ms_step * 1e-3)
 
-    # ---- per-kernel accounting on one extra (untimed) step: CUDA events around every conv-engine launch
-    prof = None
+    # ---- per-kernel accounting on one extra (untimed) step: CUDA events around every library call
+    prof, prof_top = None, None
     try:
-        from sgb200 import kernels as K
-        K.PROFILE = {"enabled": True, "events": []}
+        _lib.PROFILE["events"] = []
+        _lib.PROFILE["enabled"] = True
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
         run_steps(worker, 1, False)
         torch.cuda.synchronize()
-        K.PROFILE["enabled"] = False
-        agg = {}
-        for name, flops, e0, e1 in K.PROFILE["events"]:
-            a = agg.setdefault(name, [0.0, 0.0, 0])
-            a[0] += e0.elapsed_time(e1)
-            a[1] += flops
-            a[2] += 1
-        K.PROFILE = None
-        prof = {k: {"ms": v[0], "tflops": (v[1] / (v[0] * 1e-3) * 1e-12) if v[0] > 0 else 0.0, "launches": v[2], "flop": v[1]}
+        prof_wall_ms = (time.perf_counter() - w0) * 1e3
+        _lib.PROFILE["enabled"] = False
+        agg, by_tag = {}, {}
+        for tag, flops, e0, e1 in _lib.PROFILE["events"]:
+            ms = e0.elapsed_time(e1)
+            kind = tag.split(" ")[0]
+            a = agg.setdefault(kind, [0.0, 0.0, 0])
+            a[0] += ms; a[1] += flops; a[2] += 1
+            t = by_tag.setdefault(tag, [0.0, 0.0, 0])
+            t[0] += ms; t[1] += flops; t[2] += 1
+        _lib.PROFILE["events"] = []
+        prof = {k: {"ms": v[0], "tflops": (v[1] / (v[0] * 1e-3) * 1e-12) if v[0] > 0 and v[1] > 0 else None, "launches": v[2], "flop": v[1]}
                 for k, v in agg.items()}
+        prof_top = [{"tag": k, "ms": round(v[0], 3), "n": v[2], "tflops": round(v[1] / (v[0] * 1e-3) * 1e-12, 1) if v[1] > 0 else None}
+                    for k, v in sorted(by_tag.items(), key=lambda kv: -kv[1][0])[:40]]
+        if rank == 0:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "kernel_breakdown_n%d_b%d.json" % (world, global_batch)), "w") as fh:
+                json.dump({"wall_ms_of_profiled_step": prof_wall_ms, "sum_ms": sum(v[0] for v in agg.values()),
+                           "by_kind": prof, "by_tag": [{"tag": k, "ms": v[0], "n": v[2], "flop": v[1]} for k, v in
+                                                       sorted(by_tag.items(), key=lambda kv: -kv[1][0])]}, fh, indent=1)
     except Exception as ex:  # accounting must never take the bench line down
         prof = {"error": repr(ex)}
 
@@ -323,6 +336,7 @@ def main():
             "step_frac": step_flop / (ms_step * 1e-3) * 1e-12 / world / peak_tf}
     if isinstance(prof, dict) and "conv_fprop" in prof:
         k = prof["conv_fprop"]
+        prof = {kk: vv for kk, vv in prof.items() if kk in ("conv_fprop", "conv_wgrad")}
         roof.update({"kernel": "conv_fprop_kernel (fprop + dgrad, tcgen05)", "achieved": k["tflops"], "frac": k["tflops"] / peak_tf,
                      "kernel_ms_per_step": k["ms"], "kernel_share_of_step": k["ms"] / ms_step, "kernels": prof})
     else:

@@ -131,4 +131,108 @@ __device__ __forceinline__ void epilogue_row(const EpiArgs& p, uint32_t t_row, i
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------------------------
+// Epilogue v2 (bf16 NHWC output, channel tile a multiple of 64): two teams of four warps take alternate 64-channel
+// chunks; a team converts its 128 x 64 chunk into a SWIZZLE_128B staging tile in shared memory and one thread issues
+// a TMA tensor store (full 128-byte lines, asynchronous, out-of-range rows / channels clipped by the hardware).  This
+// replaces 16-byte-per-lane strided global stores, which bound every wide 1x1 layer (K = 64..128) at ~1/6 of HBM speed.
+// -------------------------------------------------------------------------------------------------------------------
+static constexpr int kEpiThreads = 256;           // 8 epilogue warps
+static constexpr int kEpiStageBytes = 128 * 128;  // one 128-row x 64-channel bf16 chunk
+
+__device__ __forceinline__ bool epi_use_tma(const EpiArgs& p, int BN) {
+  return !p.y_fp32 && (BN % 64 == 0) && epi_vec_ok(p);
+}
+
+// t_row : TMEM address (lane quadrant of this warp, first column of the accumulator).
+// c1..c3: box coordinates (w0, h0, b0) of the tile in the output tensor map; channel coordinate = n0 + chunk * 64.
+// stage : this team's staging buffer (1024-byte aligned).  team in {0,1}; row = accumulator row of this thread.
+__device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtensorMap* tmY, uint32_t t_row, int BN, int n0,
+                                                  int c1, int c2, int c3, bool valid, long long pix, long long rpix, float alpha,
+                                                  uint32_t stage, int team, int row, bool leader, int chunk_stride = 2) {
+  const bool res_pre = p.residual != nullptr && !p.res_after;
+  const bool res_post = p.residual != nullptr && p.res_after;
+  const uint32_t srow = stage + (uint32_t)row * 128u;
+  const uint32_t sw = (uint32_t)(row & 7);
+  for (int cc = (chunk_stride == 2 ? team : 0); cc * 64 < BN; cc += chunk_stride) {
+    const int nbase = n0 + cc * 64;
+    if (nbase >= p.Cout) break;
+    if (leader) bulk_wait_read0();               // the previous store of this team has finished reading the staging tile
+    named_bar_sync(1 + team, 128);
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+      uint32_t v[16];
+      __syncwarp();
+      tmem_ld16(t_row + cc * 64 + s * 16, v);
+      tmem_ld_wait();
+      const int n = nbase + s * 16;
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * alpha;
+      const bool in_c = (n + 16 <= p.Cout);
+      if (in_c && p.bias) {
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 bb = __ldg(bp + j);
+          f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+        }
+      }
+      if (in_c && valid && res_pre) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.res_cstride + n);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint4 r = __ldg(rp + j);
+          f[8 * j + 0] += bf16_bits_lo(r.x); f[8 * j + 1] += bf16_bits_hi(r.x);
+          f[8 * j + 2] += bf16_bits_lo(r.y); f[8 * j + 3] += bf16_bits_hi(r.y);
+          f[8 * j + 4] += bf16_bits_lo(r.z); f[8 * j + 5] += bf16_bits_hi(r.z);
+          f[8 * j + 6] += bf16_bits_lo(r.w); f[8 * j + 7] += bf16_bits_hi(r.w);
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      if (in_c && valid && p.mask) {
+        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_cstride + n);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint4 m = __ldg(mp + j);
+          f[8 * j + 0] = bf16_bits_lo(m.x) > 0.f ? f[8 * j + 0] : 0.f;
+          f[8 * j + 1] = bf16_bits_hi(m.x) > 0.f ? f[8 * j + 1] : 0.f;
+          f[8 * j + 2] = bf16_bits_lo(m.y) > 0.f ? f[8 * j + 2] : 0.f;
+          f[8 * j + 3] = bf16_bits_hi(m.y) > 0.f ? f[8 * j + 3] : 0.f;
+          f[8 * j + 4] = bf16_bits_lo(m.z) > 0.f ? f[8 * j + 4] : 0.f;
+          f[8 * j + 5] = bf16_bits_hi(m.z) > 0.f ? f[8 * j + 5] : 0.f;
+          f[8 * j + 6] = bf16_bits_lo(m.w) > 0.f ? f[8 * j + 6] : 0.f;
+          f[8 * j + 7] = bf16_bits_hi(m.w) > 0.f ? f[8 * j + 7] : 0.f;
+        }
+      }
+      if (in_c && valid && res_post) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.res_cstride + n);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint4 r = __ldg(rp + j);
+          f[8 * j + 0] += bf16_bits_lo(r.x); f[8 * j + 1] += bf16_bits_hi(r.x);
+          f[8 * j + 2] += bf16_bits_lo(r.y); f[8 * j + 3] += bf16_bits_hi(r.y);
+          f[8 * j + 4] += bf16_bits_lo(r.z); f[8 * j + 5] += bf16_bits_hi(r.z);
+          f[8 * j + 6] += bf16_bits_lo(r.w); f[8 * j + 7] += bf16_bits_hi(r.w);
+        }
+      }
+      // 16 channels = two 16-byte units (2s, 2s+1) of this row's 128-byte line; unit u lives at (u ^ (row & 7))
+      st_shared_v4(srow + (((uint32_t)(2 * s) ^ sw) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                   pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      st_shared_v4(srow + (((uint32_t)(2 * s + 1) ^ sw) << 4), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                   pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+    }
+    fence_proxy_async_smem();                    // generic-proxy smem writes -> visible to the TMA (async proxy)
+    named_bar_sync(1 + team, 128);
+    if (leader) {
+      tma_store_4d(tmY, stage, nbase, c1, c2, c3);
+      bulk_commit();
+    }
+  }
+}
+
 }  // namespace sgb

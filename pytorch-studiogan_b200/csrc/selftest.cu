@@ -356,6 +356,12 @@ int main(int argc, char** argv) {
     time_fprop("1x1 512->2048 8^2 B=256", 256, 8, 8, 512, 2048, 1);
     time_fprop("1x1 256->64 256^2 B=32", 32, 256, 256, 256, 64, 1);
     time_fprop("1x1 4096->4096 M=16384", 16384, 1, 1, 4096, 4096, 1);
+    time_fprop("1x1 64->256 128^2 B=64", 64, 128, 128, 64, 256, 1);
+    time_fprop("1x1 64->128 256^2 B=32", 32, 256, 256, 64, 128, 1);
+    time_fprop("1x1 128->512 64^2 B=64", 64, 64, 64, 128, 512, 1);
+    time_fprop("1x1 256->1024 32^2 B=64", 64, 32, 32, 256, 1024, 1);
+    time_fprop("1x1 256->512 64^2 B=64", 64, 64, 64, 256, 512, 1);
+    time_fprop("1x1 512->2048 16^2 B=64", 64, 16, 16, 512, 2048, 1);
     time_wgrad("3x3 64->64 256^2 B=32", 32, 256, 256, 64, 64, 3);
     time_wgrad("3x3 256->256 64^2 B=64", 64, 64, 64, 256, 256, 3);
     time_wgrad("3x3 512->512 32^2 B=64", 64, 32, 32, 512, 512, 3);

@@ -18,7 +18,8 @@
 
 namespace sgb {
 
-static constexpr int kThreads = 192;
+static constexpr int kWgradThreads = 192;                // wgrad: warps 0 producer, 1 MMA, 2..5 epilogue
+static constexpr int kThreads = 128 + kEpiThreads;  // warps 0..3: producer / MMA / (idle), warps 4..11: epilogue teams
 static constexpr int kTileM = 128;          // pixels (fprop) or output channels (wgrad) per tile = TMEM lanes
 static constexpr int kBlockK = 64;          // bf16 elements per 128-byte swizzle row
 static constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB
@@ -31,14 +32,17 @@ struct FpropArgs {
   int BN;                         // output-channel tile (multiple of 16, <= 256)
   int w_mode;                     // 0: shared weights [Cout][taps][Cin]; 1: per-image [B][N][K]; 2: per-image MN-major [B][K][N]
   int stages;
+  int use_tma;                    // epilogue through staging tiles + TMA tensor stores
   uint32_t tmem_cols;
   EpiArgs e;
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FpropArgs p) {
+conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmY, const FpropArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t epi_stage_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // two 16 KiB staging tiles when use_tma
+  const uint32_t smem_base = epi_stage_base + (p.use_tma ? 2u * kEpiStageBytes : 0u);
   const uint32_t b_bytes = (uint32_t)p.BN * kBlockK * 2;  // same size for K-major [BN][64] and MN-major (BN/64) x [64][64]
   const uint32_t stage_bytes = kABytes + b_bytes;  // multiple of 1024 because BN % 8 == 0 -> b_bytes % 1024 == 0
   const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
@@ -60,9 +64,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), kEpiThreads);
     }
     fence_barrier_init();
+    if (p.use_tma) tma_prefetch_desc(&tmY);
   }
   if (warp == 1) {
     tmem_alloc(holder, p.tmem_cols);
@@ -140,13 +145,16 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         umma_commit(tfull_bar(a));    // accumulator complete
       }
     }
-  } else {
-    // --------------------------------------------------------------- epilogue warps (TMEM lane quadrant = warp % 4)
+  } else if (warp >= 4) {
+    // --------------------------------------------------------------- epilogue: 8 warps, TMEM lane quadrant = warp % 4
     const int q = warp & 3;
+    const int team = (warp - 4) >> 2;
     const int row = q * 32 + lane;
+    const bool leader = (q == 0) && (lane == 0);
     const int wi = row % p.tw, hi = (row / p.tw) % p.th, bi = row / (p.tw * p.th);
     const bool vec_ok = epi_vec_ok(p.e);
     const float alpha = p.e.alpha_ptr ? p.e.alpha * __ldg(p.e.alpha_ptr) : p.e.alpha;
+    const uint32_t stage = epi_stage_base + team * kEpiStageBytes;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
       int t = tile;
@@ -164,11 +172,16 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + a * p.BN;
-
-      epilogue_row(p.e, t_row, p.BN, n0, valid, pix, rpix, alpha, vec_ok);
+      if (p.use_tma) {
+        epilogue_tile_tma(p.e, &tmY, t_row, p.BN, n0, wt * p.tw, ht * p.th, bt * p.nb, valid, pix, rpix, alpha, stage, team, row,
+                          leader);
+      } else if (team == 0) {
+        epilogue_row(p.e, t_row, p.BN, n0, valid, pix, rpix, alpha, vec_ok);
+      }
       tc_fence_before();
       mbar_arrive(tempty_bar(a));
     }
+    if (p.use_tma && leader) bulk_wait_all();   // staging tiles must outlive the last tensor store
   }
 
   tc_fence_before();
@@ -195,7 +208,7 @@ struct WgradArgs {
   long long dw_group_stride;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kWgradThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgradArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -383,7 +396,7 @@ using namespace sgb;
 
 namespace sgb {
 bool conv3x3_rows_eligible(const sgb_conv_desc* d);
-int launch_conv3x3_rows(const sgb_conv_desc* d, cudaStream_t stream, int bo_mode);
+int launch_conv3x3_rows(const sgb_conv_desc* d, cudaStream_t stream, int bo_mode, int use_tma_env);
 }  // namespace sgb
 
 static int env_int(const char* name, int dflt) {
@@ -406,7 +419,7 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
     // wide, few-channel 3x3 layers: halo-row kernel (umma_conv3x3.cu).  SGB_CONV3X3_ROWS=0 forces the generic kernel.
     static const int use_rows = env_int("SGB_CONV3X3_ROWS", 1);
     static const int bo_mode = env_int("SGB_ROWS_BASE_OFFSET", 0);
-    if (use_rows && conv3x3_rows_eligible(d)) return launch_conv3x3_rows(d, stream, bo_mode);
+    if (use_rows && conv3x3_rows_eligible(d)) return launch_conv3x3_rows(d, stream, bo_mode, env_int("SGB_EPI_TMA", 1));
   }
   SGB_REQUIRE(((uintptr_t)d->bias & 15) == 0 && ((uintptr_t)d->residual & 15) == 0 && ((uintptr_t)d->mask & 15) == 0);
 
@@ -434,8 +447,11 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   p.tiles_n = (d->Cout + BN - 1) / BN;
   p.num_tiles = p.tiles_n * p.tiles_w * p.tiles_h * p.tiles_b;
   p.kblocks = (d->Cin + kBlockK - 1) / kBlockK;
+  p.use_tma = (!d->y_fp32 && BN % 64 == 0 && d->Cout % 8 == 0 && d->y_cstride % 8 == 0 &&
+               (!d->residual || d->res_cstride % 8 == 0) && (!d->mask || d->mask_cstride % 8 == 0) &&
+               p.taps * d->Cin <= env_int("SGB_EPI_TMA_MAXK", 640) && env_int("SGB_EPI_TMA", 1)) ? 1 : 0;   // output-heavy layers only
   const uint32_t stage_bytes = kABytes + BN * kBlockK * 2;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  int stages = (int)(((200 - (p.use_tma ? 32 : 0)) * 1024) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
@@ -462,14 +478,19 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
     rc = make_tmap_bf16(&tmB, d->w, 3, dims, strides, box);
   }
   if (rc) return rc;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 4) + 16;
+  CUtensorMap tmY = tmA;
+  if (p.use_tma) {
+    rc = make_act_tmap(&tmY, d->y, d->B, d->H, d->W, d->Cout, d->y_cstride, p.tw, p.th, p.nb);
+    if (rc) return rc;
+  }
+  const size_t smem = (size_t)stages * stage_bytes + (p.use_tma ? 2 * kEpiStageBytes : 0) + 1024 + 8 * (2 * stages + 4) + 16;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     SGB_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     smem_set = 227 * 1024;
   }
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  conv_fprop_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  conv_fprop_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmY, p);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }
@@ -526,7 +547,7 @@ extern "C" int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream_) {
     attr_set = true;
   }
   int grid = p.num_items < sm_count() ? p.num_items : sm_count();
-  conv_wgrad_kernel<<<grid, kThreads, smem, stream>>>(tmDY, tmX, p);
+  conv_wgrad_kernel<<<grid, kWgradThreads, smem, stream>>>(tmDY, tmX, p);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }

@@ -19,12 +19,13 @@ namespace sgb {
 static constexpr int kRowPix = 130;
 static constexpr int kRowLoadBytes = kRowPix * 128;   // 16640
 static constexpr int kRowBufBytes = 17 * 1024;        // 17408, keeps every row buffer 1024-byte aligned
-static constexpr int kRowsThreads = 224;
+static constexpr int kRowsThreads = 128 + kEpiThreads;  // warps 0: A producer, 1: MMA, 2: B producer, 3: idle, 4..11: epilogue
 
 struct RowsArgs {
   int B, H, W, Cin, Cout;
   int kblocks, BN, tiles_n, segs, hpairs, num_tiles;
   int resident, a_stages, b_stages, bo_mode;
+  int use_tma, epi_bufs;   // TMA-store epilogue; 2 staging tiles: team t owns output row t, 1: team 0 handles both rows
   uint32_t tmem_cols;
   EpiArgs e;
 };
@@ -36,9 +37,11 @@ __device__ __forceinline__ uint64_t sdesc_rows(uint32_t addr, int bo_mode) {
 }
 
 __global__ void __launch_bounds__(kRowsThreads, 1)
-conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const RowsArgs p) {
+conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmY, const RowsArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t epi_stage_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_base = epi_stage_base + (p.use_tma ? (uint32_t)p.epi_bufs * kEpiStageBytes : 0u);
   const uint32_t a_stage_bytes = 4 * kRowBufBytes;
   const uint32_t b_tile_bytes = (uint32_t)p.BN * 128u;
   const uint32_t a_base = smem_base;
@@ -62,7 +65,7 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < nb; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), kEpiThreads); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -100,7 +103,7 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 2) {
     if (lane == 0) {
       // ------------------------------------------------------------- B producer: filter taps (resident or ring)
       if (p.resident) {
@@ -166,10 +169,12 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         umma_commit(tfull(as));
       }
     }
-  } else {
-    // --------------------------------------------------------------- epilogue warps 2..5
+  } else if (warp >= 4) {
+    // --------------------------------------------------------------- epilogue: 8 warps (two teams)
     const int q = warp & 3;
+    const int team = (warp - 4) >> 2;
     const int row = q * 32 + lane;
+    const bool leader = (q == 0) && (lane == 0);
     const bool vec_ok = epi_vec_ok(p.e);
     const float alpha = p.e.alpha_ptr ? p.e.alpha * __ldg(p.e.alpha_ptr) : p.e.alpha;
     uint32_t tcount = 0;
@@ -186,11 +191,22 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const long long pix = ((long long)b * p.H + h) * p.W + w;
         const long long rpix = p.e.res_up2 ? (((long long)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) : pix;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (as * 2 + j) * p.BN;
-        epilogue_row(p.e, t_row, p.BN, nt * p.BN, true, pix, rpix, alpha, vec_ok);
+        if (p.use_tma) {
+          // epi_bufs == 2: team t stores output row t with both of its 64-channel chunk parities; epi_bufs == 1: team 0 does all
+          const bool mine = (p.epi_bufs == 2) ? (team == j) : (team == 0);
+          if (mine) {
+            const uint32_t stage = epi_stage_base + ((p.epi_bufs == 2) ? team : 0) * kEpiStageBytes;
+            // one team covers every chunk of its row: run the chunk loop for both parities on the team's own barrier
+            epilogue_tile_tma(p.e, &tmY, t_row, p.BN, nt * p.BN, ws * 128, h, b, true, pix, rpix, alpha, stage, team, row, leader, 1);
+          }
+        } else if (team == 0) {
+          epilogue_row(p.e, t_row, p.BN, nt * p.BN, true, pix, rpix, alpha, vec_ok);
+        }
       }
       tc_fence_before();
       mbar_arrive(tempty(as));
     }
+    if (p.use_tma && leader) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -205,15 +221,15 @@ void fill_epi(EpiArgs& e, const sgb_conv_desc* d);
 
 bool conv3x3_rows_eligible(const sgb_conv_desc* d) {
   return d->KH == 3 && d->KW == 3 && d->pad_h == 1 && d->pad_w == 1 && d->w_mode == 0 && d->W % 128 == 0 && d->H % 2 == 0 &&
-         d->Cin % 64 == 0 && d->Cin <= 128 && d->Cout % 16 == 0 && d->Cout >= 16;
+         d->Cin % 64 == 0 && d->Cin <= 128 && d->Cout % 8 == 0;
 }
 
 // bo_mode: 0 = no matrix base offset in the row-shifted descriptors (default), 1 = (addr >> 7) & 7.
-int launch_conv3x3_rows(const sgb_conv_desc* d, cudaStream_t stream, int bo_mode) {
+int launch_conv3x3_rows(const sgb_conv_desc* d, cudaStream_t stream, int bo_mode, int use_tma_env) {
   RowsArgs p;
   p.B = d->B; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
   p.kblocks = d->Cin / 64;
-  p.BN = d->Cout <= 128 ? d->Cout : 128;
+  p.BN = d->Cout <= 128 ? (d->Cout + 15) / 16 * 16 : 128;   // Cout = 8 (padded image channels) runs as one N = 16 tile
   p.tiles_n = (d->Cout + p.BN - 1) / p.BN;
   p.segs = d->W / 128;
   p.hpairs = d->H / 2;
@@ -223,14 +239,20 @@ int launch_conv3x3_rows(const sgb_conv_desc* d, cudaStream_t stream, int bo_mode
   const uint32_t budget = 227u * 1024u - 2048u;
   const uint32_t a_stage = 4 * kRowBufBytes;
   const uint32_t resident_bytes = 9u * p.kblocks * b_tile;
-  p.resident = (p.tiles_n == 1 && resident_bytes + 2 * a_stage <= budget) ? 1 : 0;
+  p.use_tma = (!d->y_fp32 && p.BN % 64 == 0 && d->y_cstride % 8 == 0 && (!d->residual || d->res_cstride % 8 == 0) &&
+               (!d->mask || d->mask_cstride % 8 == 0) && use_tma_env) ? 1 : 0;
+  p.epi_bufs = 2;
+  p.resident = (p.tiles_n == 1 && resident_bytes + 2 * a_stage + (p.use_tma ? kEpiStageBytes : 0) <= budget) ? 1 : 0;
   if (p.resident) {
-    p.a_stages = (int)((budget - resident_bytes) / a_stage);
+    if (p.use_tma && resident_bytes + 2 * a_stage + 2 * kEpiStageBytes > budget) p.epi_bufs = 1;
+    const uint32_t epi_bytes = p.use_tma ? p.epi_bufs * kEpiStageBytes : 0;
+    p.a_stages = (int)((budget - resident_bytes - epi_bytes) / a_stage);
     if (p.a_stages > 3) p.a_stages = 3;
     p.b_stages = 1;
   } else {
     p.a_stages = 2;
-    p.b_stages = (int)((budget - 2 * a_stage) / b_tile);
+    const uint32_t epi_bytes = p.use_tma ? p.epi_bufs * kEpiStageBytes : 0;
+    p.b_stages = (int)((budget - 2 * a_stage - epi_bytes) / b_tile);
     if (p.b_stages > 6) p.b_stages = 6;
     if (p.b_stages < 2) return SGB_ERR_UNSUPPORTED;
   }
@@ -254,8 +276,17 @@ int launch_conv3x3_rows(const sgb_conv_desc* d, cudaStream_t stream, int bo_mode
     int rc = make_tmap_bf16(&tmB, d->w, 3, dims, strides, box);
     if (rc) return rc;
   }
+  CUtensorMap tmY = tmA;
+  if (p.use_tma) {
+    uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+    uint64_t strides[3] = {(uint64_t)d->y_cstride * 2, (uint64_t)d->y_cstride * 2 * d->W, (uint64_t)d->y_cstride * 2 * d->W * d->H};
+    uint32_t box[4] = {64, 128, 1, 1};
+    int rc = make_tmap_bf16(&tmY, d->y, 4, dims, strides, box);
+    if (rc) return rc;
+  }
   const int nb = p.resident ? 1 : p.b_stages;
-  const size_t smem = (size_t)p.a_stages * a_stage + (p.resident ? resident_bytes : p.b_stages * b_tile) + 1024 +
+  const size_t smem = (size_t)p.a_stages * a_stage + (p.resident ? resident_bytes : p.b_stages * b_tile) +
+                      (p.use_tma ? p.epi_bufs * kEpiStageBytes : 0) + 1024 +
                       8 * (2 * p.a_stages + 2 * nb + 4) + 16;
   static bool attr_set = false;
   if (!attr_set) {
@@ -263,7 +294,7 @@ int launch_conv3x3_rows(const sgb_conv_desc* d, cudaStream_t stream, int bo_mode
     attr_set = true;
   }
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  conv3x3_rows_kernel<<<grid, kRowsThreads, smem, stream>>>(tmA, tmB, p);
+  conv3x3_rows_kernel<<<grid, kRowsThreads, smem, stream>>>(tmA, tmB, tmY, p);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }

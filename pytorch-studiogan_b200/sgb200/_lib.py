@@ -130,13 +130,25 @@ LAUNCHES = [0]  # number of library entry-point calls (each launches >= 1 kernel
 _tls = threading.local()
 
 
-def call(name, *args):
+# Optional per-call accounting (bench.py's roofline block / profiles): when PROFILE["enabled"], every library call is
+# bracketed by CUDA events on the launching stream and logged as (tag, algorithmic FLOPs, start, stop).
+PROFILE = {"enabled": False, "events": []}
+
+
+def call(name, *args, tag=None, flops=0.0):
     lib = load()
     if getattr(_tls, "device", None) is None:
         # first library call on this host thread (e.g. an autograd worker): bind the thread to torch's current device
         dev = torch.cuda.current_device()
         check(lib.sgb_bind_device(dev), "sgb_bind_device")
         _tls.device = dev
-    rc = getattr(lib, name)(*args)
+    if PROFILE["enabled"]:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        PROFILE["events"].append((tag or name, flops, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     LAUNCHES[0] += 1
     check(rc, name)

@@ -53,28 +53,6 @@ def _s():
     return L.stream_ptr()
 
 
-# Optional per-launch accounting for bench.py's roofline block: when PROFILE["enabled"], conv-engine launches are
-# bracketed by CUDA events on the launching stream and logged as (kernel, algorithmic FLOPs, start, stop).
-PROFILE = None
-
-
-class _profiled:
-    def __init__(self, name, flops):
-        self.on = PROFILE is not None and PROFILE.get("enabled", False)
-        self.name, self.flops = name, flops
-
-    def __enter__(self):
-        if self.on:
-            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            self.e0.record()
-
-    def __exit__(self, *exc):
-        if self.on:
-            self.e1.record()
-            PROFILE["events"].append((self.name, self.flops, self.e0, self.e1))
-        return False
-
-
 # ---------------------------------------------------------------------------------------------- conv engine
 def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_up2=False, res_after_mask=False,
                mask=None, relu=False, alpha=1.0, alpha_ptr=None, out=None, out_fp32=False, w_mode=0):
@@ -99,8 +77,8 @@ def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_u
         d.mask, d.mask_cstride = mask.data_ptr(), geom(mask)[4]
     d.relu = 1 if relu else 0
     d.y, d.y_cstride, d.y_fp32 = out.data_ptr(), ycs, 1 if out.dtype == torch.float32 else 0
-    with _profiled("conv_fprop", 2.0 * B * H * W * Cout * Cin * KH * KW):
-        L.call("sgb_conv_fprop", ctypes.byref(d), _s())
+    L.call("sgb_conv_fprop", ctypes.byref(d), _s(), tag="conv_fprop %dx%d %d->%d @%dx%d m%d" % (KH, KW, Cin, Cout, H, W, w_mode),
+           flops=2.0 * B * H * W * Cout * Cin * KH * KW)
     return out
 
 
@@ -118,8 +96,8 @@ def conv_wgrad(x, dy, KH, KW, pad_h, pad_w, dw=None, accumulate=False, per_image
     d.x, d.x_cstride = x.data_ptr(), xcs
     d.dy, d.dy_cstride = dy.data_ptr(), dcs
     d.dw, d.accumulate, d.per_image = dw.data_ptr(), 1 if accumulate else 0, 1 if per_image else 0
-    with _profiled("conv_wgrad", 2.0 * B * H * W * Cout * Cin * KH * KW):
-        L.call("sgb_conv_wgrad", ctypes.byref(d), _s())
+    L.call("sgb_conv_wgrad", ctypes.byref(d), _s(), tag="conv_wgrad %dx%d %d->%d @%dx%d%s" % (KH, KW, Cin, Cout, H, W, " per-image" if per_image else ""),
+           flops=2.0 * B * H * W * Cout * Cin * KH * KW)
     return dw
 
 
