@@ -165,6 +165,10 @@ int sgb_nhwc_to_img(const void* in, int32_t in_fp32, int64_t cs, float* img, int
                     sgb_stream_t stream);
 int sgb_img_grad_to_nhwc(const float* dimg, const float* y, void* out, int32_t B, int32_t C, int32_t HW, int32_t Cp,
                          sgb_stream_t stream);
+/* 3x3 / pad-1 patch gather of a 3-channel image into [B,H,W,32] bf16 (k = tap*3 + c, 27..31 zero) and its adjoint:
+ * the 3 -> C input convolution (input_conv, src/models/big_resnet_deep_legacy.py:259) becomes a K = 32 GEMM. */
+int sgb_col27(const void* src, int32_t src_nchw_f32, int64_t cs, void* out, int32_t B, int32_t H, int32_t W, sgb_stream_t stream);
+int sgb_col27_bwd(const void* dcol, float* dimg, int32_t B, int32_t H, int32_t W, sgb_stream_t stream);
 int sgb_cast_f32_to_bf16(const float* in, void* out, int64_t n, float scale, sgb_stream_t stream);
 int sgb_cast_bf16_to_f32(const void* in, float* out, int64_t n, sgb_stream_t stream);
 

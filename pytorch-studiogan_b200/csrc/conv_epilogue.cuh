@@ -139,6 +139,25 @@ __device__ __forceinline__ void epilogue_row(const EpiArgs& p, uint32_t t_row, i
 // replaces 16-byte-per-lane strided global stores, which bound every wide 1x1 layer (K = 64..128) at ~1/6 of HBM speed.
 // -------------------------------------------------------------------------------------------------------------------
 static constexpr int kEpiThreads = 256;           // 8 epilogue warps
+
+// Optional auxiliary operand of the epilogue (the residual OR the ReLU-mask tensor) staged by TMA: one SWIZZLE_128B box of
+// the same pixels (or of the half-resolution source pixels for the nearest-x2 residual) per 64-channel chunk.
+struct EpiAux {
+  int kind;                 // 1 residual, 2 mask
+  const CUtensorMap* tm;
+  uint32_t stage;           // 1024-byte aligned staging tile of this team
+  uint32_t bar;             // mbarrier (count 1)
+  uint32_t* phase;          // per-thread phase bit, toggled per chunk
+  uint32_t bytes;           // bytes of one box
+  int c1, c2, c3;           // box coordinates (w, h, b) in the auxiliary tensor
+  int arow;                 // staging-tile row this thread reads
+};
+
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
 static constexpr int kEpiStageBytes = 128 * 128;  // one 128-row x 64-channel bf16 chunk
 
 __device__ __forceinline__ bool epi_use_tma(const EpiArgs& p, int BN) {
@@ -150,16 +169,28 @@ __device__ __forceinline__ bool epi_use_tma(const EpiArgs& p, int BN) {
 // stage : this team's staging buffer (1024-byte aligned).  team in {0,1}; row = accumulator row of this thread.
 __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtensorMap* tmY, uint32_t t_row, int BN, int n0,
                                                   int c1, int c2, int c3, bool valid, long long pix, long long rpix, float alpha,
-                                                  uint32_t stage, int team, int row, bool leader, int chunk_stride = 2) {
+                                                  uint32_t stage, int team, int row, bool leader, int chunk_stride = 2,
+                                                  const EpiAux* aux = nullptr) {
   const bool res_pre = p.residual != nullptr && !p.res_after;
   const bool res_post = p.residual != nullptr && p.res_after;
   const uint32_t srow = stage + (uint32_t)row * 128u;
   const uint32_t sw = (uint32_t)(row & 7);
+  const int aux_kind = aux ? aux->kind : 0;                       // 1: residual tile via TMA, 2: mask tile via TMA
+  const uint32_t arow_addr = aux ? aux->stage + (uint32_t)aux->arow * 128u : 0u;
+  const uint32_t asw = aux ? (uint32_t)(aux->arow & 7) : 0u;
   for (int cc = (chunk_stride == 2 ? team : 0); cc * 64 < BN; cc += chunk_stride) {
     const int nbase = n0 + cc * 64;
     if (nbase >= p.Cout) break;
     if (leader) bulk_wait_read0();               // the previous store of this team has finished reading the staging tile
     named_bar_sync(1 + team, 128);
+    if (aux_kind) {                              // residual / mask chunk for this tile: one TMA box instead of strided 16-byte loads
+      if (leader) {
+        mbar_arrive_expect_tx(aux->bar, aux->bytes);
+        tma_load_4d(aux->stage, aux->tm, aux->bar, nbase, aux->c1, aux->c2, aux->c3);
+      }
+      mbar_wait(aux->bar, *aux->phase);
+      *aux->phase ^= 1u;
+    }
 #pragma unroll 1
     for (int s = 0; s < 4; ++s) {
       uint32_t v[16];
@@ -170,20 +201,24 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
       float f[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * alpha;
-      const bool in_c = (n + 16 <= p.Cout);
+      const int nvalid = p.Cout - n;               // channels of this 16-wide piece inside the tensor: >= 16, 8 (Cout % 16 == 8) or <= 0
+      const bool in_c = nvalid > 0;
       if (in_c && p.bias) {
         const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 bb = __ldg(bp + j);
-          f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+          if (4 * j < nvalid) {
+            const float4 bb = __ldg(bp + j);
+            f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+          }
         }
       }
       if (in_c && valid && res_pre) {
         const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.res_cstride + n);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const uint4 r = __ldg(rp + j);
+          const uint4 r = (aux_kind == 1) ? ld_shared_v4(arow_addr + (((uint32_t)(2 * s + j) ^ asw) << 4))
+                                          : (8 * j < nvalid ? __ldg(rp + j) : make_uint4(0u, 0u, 0u, 0u));
           f[8 * j + 0] += bf16_bits_lo(r.x); f[8 * j + 1] += bf16_bits_hi(r.x);
           f[8 * j + 2] += bf16_bits_lo(r.y); f[8 * j + 3] += bf16_bits_hi(r.y);
           f[8 * j + 4] += bf16_bits_lo(r.z); f[8 * j + 5] += bf16_bits_hi(r.z);
@@ -198,7 +233,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
         const uint4* mp = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_cstride + n);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const uint4 m = __ldg(mp + j);
+          const uint4 m = (aux_kind == 2) ? ld_shared_v4(arow_addr + (((uint32_t)(2 * s + j) ^ asw) << 4))
+                                          : (8 * j < nvalid ? __ldg(mp + j) : make_uint4(0u, 0u, 0u, 0u));
           f[8 * j + 0] = bf16_bits_lo(m.x) > 0.f ? f[8 * j + 0] : 0.f;
           f[8 * j + 1] = bf16_bits_hi(m.x) > 0.f ? f[8 * j + 1] : 0.f;
           f[8 * j + 2] = bf16_bits_lo(m.y) > 0.f ? f[8 * j + 2] : 0.f;
@@ -213,7 +249,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
         const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.res_cstride + n);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const uint4 r = __ldg(rp + j);
+          const uint4 r = (aux_kind == 1) ? ld_shared_v4(arow_addr + (((uint32_t)(2 * s + j) ^ asw) << 4))
+                                          : (8 * j < nvalid ? __ldg(rp + j) : make_uint4(0u, 0u, 0u, 0u));
           f[8 * j + 0] += bf16_bits_lo(r.x); f[8 * j + 1] += bf16_bits_hi(r.x);
           f[8 * j + 2] += bf16_bits_lo(r.y); f[8 * j + 3] += bf16_bits_hi(r.y);
           f[8 * j + 4] += bf16_bits_lo(r.z); f[8 * j + 5] += bf16_bits_hi(r.z);

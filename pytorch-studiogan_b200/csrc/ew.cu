@@ -333,6 +333,64 @@ __global__ void __launch_bounds__(256) img_grad_to_nhwc_kernel(const float* __re
   }
 }
 
+// 3x3 / pad-1 patch gather for 3-channel images ("im2col27"): out[b,h,w, t*3+c] = src[b, c, h+th-1, w+tw-1] (zero outside),
+// t = th*3+tw, k = 27..31 zero.  Turns the 3 -> C input convolution of the discriminators (src/models/*: input_conv /
+// DiscOptBlock conv) and the dgrad of the generators' C -> 3 output convolution into a K = 32 1x1 GEMM for the tensor
+// core (a 3-channel NHWC tensor would waste 8x of every TMA box and MMA).
+// src: NCHW fp32 (src_nchw = 1) or NHWC bf16 with channel stride cs (first 3 channels used).
+__global__ void __launch_bounds__(256) col27_kernel(const void* __restrict__ src, int src_nchw, long long cs, bf16* __restrict__ out,
+                                                     int B, int H, int W) {
+  const long long total = (long long)B * H * W;
+  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < total; p += (long long)gridDim.x * 256) {
+    const int w = (int)(p % W), h = (int)((p / W) % H), b = (int)(p / ((long long)W * H));
+    float v[32];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
+      const bool in = (hh >= 0) && (hh < H) && (ww >= 0) && (ww < W);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float x = 0.f;
+        if (in) {
+          if (src_nchw) x = __ldg(reinterpret_cast<const float*>(src) + (((long long)b * 3 + c) * H + hh) * W + ww);
+          else x = __bfloat162float(reinterpret_cast<const bf16*>(src)[(((long long)b * H + hh) * W + ww) * cs + c]);
+        }
+        v[t * 3 + c] = x;
+      }
+    }
+#pragma unroll
+    for (int k = 27; k < 32; ++k) v[k] = 0.f;
+    uint4* op = reinterpret_cast<uint4*>(out + p * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 o;
+      o.x = pack2(v[8 * j + 0], v[8 * j + 1]); o.y = pack2(v[8 * j + 2], v[8 * j + 3]);
+      o.z = pack2(v[8 * j + 4], v[8 * j + 5]); o.w = pack2(v[8 * j + 6], v[8 * j + 7]);
+      op[j] = o;
+    }
+  }
+}
+
+// Adjoint of col27: dimg[b,c,h,w] = sum_t dcol[b, h-th+1, w-tw+1, t*3+c]  (NCHW fp32 result).
+__global__ void __launch_bounds__(256) col27_bwd_kernel(const bf16* __restrict__ dcol, float* __restrict__ dimg, int B, int H, int W) {
+  const long long total = (long long)B * H * W;
+  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < total; p += (long long)gridDim.x * 256) {
+    const int w = (int)(p % W), h = (int)((p / W) % H), b = (int)(p / ((long long)W * H));
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int hh = h - (t / 3) + 1, ww = w - (t % 3) + 1;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+        const bf16* q = dcol + (((long long)b * H + hh) * W + ww) * 32 + t * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] += __bfloat162float(q[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dimg[(((long long)b * 3 + c) * H + h) * W + w] = acc[c];
+  }
+}
+
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n,
                                                              float scale) {
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
@@ -488,6 +546,23 @@ extern "C" int sgb_img_grad_to_nhwc(const float* dimg, const float* y, void* out
   cudaStream_t stream = (cudaStream_t)stream_;
   SGB_REQUIRE(dimg && out && B > 0 && C > 0 && HW > 0 && Cp >= C && Cp % 8 == 0);
   img_grad_to_nhwc_kernel<<<ew_blocks((long long)B * HW), 256, 0, stream>>>(dimg, y, (bf16*)out, B, C, HW, Cp);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_col27(const void* src, int32_t src_nchw_f32, int64_t cs, void* out, int32_t B, int32_t H, int32_t W,
+                         sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(src && out && B > 0 && H > 0 && W > 0 && (src_nchw_f32 || cs >= 3));
+  col27_kernel<<<ew_blocks((long long)B * H * W), 256, 0, stream>>>(src, src_nchw_f32, cs, (bf16*)out, B, H, W);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_col27_bwd(const void* dcol, float* dimg, int32_t B, int32_t H, int32_t W, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(dcol && dimg && B > 0 && H > 0 && W > 0);
+  col27_bwd_kernel<<<ew_blocks((long long)B * H * W), 256, 0, stream>>>((const bf16*)dcol, dimg, B, H, W);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }

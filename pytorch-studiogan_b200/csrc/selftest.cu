@@ -328,6 +328,15 @@ int main(int argc, char** argv) {
       {"rows c128->64 256x256 fp32",    1, 256, 256, 128, 64, 3, 3, 1, 1, 0, 0, 0, 0, 0, 1},
       {"rows c64->192 128x128",         1, 128, 128, 64, 192, 3, 3, 1, 1, 1, 0, 0, 0, 0, 0},
       {"rows c64->16 128x128",          3, 128, 128, 64, 16, 3, 3, 1, 1, 1, 0, 0, 0, 0, 0},
+      {"rows c128->8 128x128",          2, 128, 128, 128, 8, 3, 3, 1, 1, 1, 0, 0, 0, 0, 0},
+      {"aux 1x1 c64->256 32x32 res",    2, 32, 32, 64, 256, 1, 1, 0, 0, 1, 0, 1, 0, 0, 0},
+      {"aux 1x1 c64->128 32x32 up2res", 2, 32, 32, 64, 128, 1, 1, 0, 0, 1, 0, 1, 1, 0, 0},
+      {"aux 1x1 c128->64 16x16 mask",   3, 16, 16, 128, 64, 1, 1, 0, 0, 0, 0, 0, 0, 1, 0},
+      {"aux 3x3 c64->64 16x16 res+relu", 2, 16, 16, 64, 64, 3, 3, 1, 1, 1, 1, 1, 0, 0, 0},
+      {"aux 1x1 c64->256 4x4 up2 B=12", 12, 4, 4, 64, 256, 1, 1, 0, 0, 1, 0, 1, 1, 0, 0},
+      {"aux 1x1 c64->192 8x8 res",      5, 8, 8, 64, 192, 1, 1, 0, 0, 1, 0, 1, 0, 0, 0},
+      {"aux 1x1 c64->128 256x128 up2",  1, 256, 128, 64, 128, 1, 1, 0, 0, 0, 0, 1, 1, 0, 0},
+      {"aux 1x1 c32->64 64x64 mask",    2, 64, 64, 32, 64, 1, 1, 0, 0, 1, 0, 0, 0, 1, 0},
   };
   if (on("fprop"))
     for (const auto& c : cases) fails += run_fprop_case(c, true);

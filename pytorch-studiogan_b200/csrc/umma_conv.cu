@@ -33,16 +33,18 @@ struct FpropArgs {
   int w_mode;                     // 0: shared weights [Cout][taps][Cin]; 1: per-image [B][N][K]; 2: per-image MN-major [B][K][N]
   int stages;
   int use_tma;                    // epilogue through staging tiles + TMA tensor stores
+  int aux_kind, aux_tw, aux_th;   // residual (1) / mask (2) tile staged by TMA; its box is aux_tw x aux_th x nb pixels
   uint32_t tmem_cols;
   EpiArgs e;
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmY, const FpropArgs p) {
+                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmAux, const FpropArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t epi_stage_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // two 16 KiB staging tiles when use_tma
-  const uint32_t smem_base = epi_stage_base + (p.use_tma ? 2u * kEpiStageBytes : 0u);
+  const uint32_t aux_stage_base = epi_stage_base + (p.use_tma ? 2u * kEpiStageBytes : 0u);   // + two aux tiles when aux_kind
+  const uint32_t smem_base = aux_stage_base + (p.aux_kind ? 2u * kEpiStageBytes : 0u);
   const uint32_t b_bytes = (uint32_t)p.BN * kBlockK * 2;  // same size for K-major [BN][64] and MN-major (BN/64) x [64][64]
   const uint32_t stage_bytes = kABytes + b_bytes;  // multiple of 1024 because BN % 8 == 0 -> b_bytes % 1024 == 0
   const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
@@ -51,6 +53,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
   const uint32_t holder = bar_base + 8u * (2 * p.stages + 4);
+  auto aux_bar = [&](int t) { return bar_base + 8u * (2 * p.stages + 6 + t); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -65,6 +68,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kEpiThreads);
+      mbar_init(aux_bar(a), 1);
     }
     fence_barrier_init();
     if (p.use_tma) tma_prefetch_desc(&tmY);
@@ -155,6 +159,12 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool vec_ok = epi_vec_ok(p.e);
     const float alpha = p.e.alpha_ptr ? p.e.alpha * __ldg(p.e.alpha_ptr) : p.e.alpha;
     const uint32_t stage = epi_stage_base + team * kEpiStageBytes;
+    uint32_t aux_phase = 0;
+    EpiAux aux;
+    aux.kind = p.aux_kind; aux.tm = &tmAux; aux.stage = aux_stage_base + team * kEpiStageBytes; aux.bar = aux_bar(team);
+    aux.phase = &aux_phase; aux.bytes = (uint32_t)(p.aux_tw * p.aux_th * p.nb) * 128u;
+    const bool aux_half = p.aux_kind == 1 && p.e.res_up2;
+    aux.arow = aux_half ? ((bi * p.aux_th + (p.aux_th == p.th ? hi : (hi >> 1))) * p.aux_tw + (wi >> 1)) : row;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
       int t = tile;
@@ -173,8 +183,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + a * p.BN;
       if (p.use_tma) {
+        aux.c1 = aux_half ? (wt * p.tw) >> 1 : wt * p.tw;
+        aux.c2 = aux_half ? (ht * p.th) >> 1 : ht * p.th;
+        aux.c3 = bt * p.nb;
         epilogue_tile_tma(p.e, &tmY, t_row, p.BN, n0, wt * p.tw, ht * p.th, bt * p.nb, valid, pix, rpix, alpha, stage, team, row,
-                          leader);
+                          leader, 2, p.aux_kind ? &aux : nullptr);
       } else if (team == 0) {
         epilogue_row(p.e, t_row, p.BN, n0, valid, pix, rpix, alpha, vec_ok);
       }
@@ -450,8 +463,15 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   p.use_tma = (!d->y_fp32 && BN % 64 == 0 && d->Cout % 8 == 0 && d->y_cstride % 8 == 0 &&
                (!d->residual || d->res_cstride % 8 == 0) && (!d->mask || d->mask_cstride % 8 == 0) &&
                p.taps * d->Cin <= env_int("SGB_EPI_TMA_MAXK", 640) && env_int("SGB_EPI_TMA", 1)) ? 1 : 0;   // output-heavy layers only
+  // auxiliary epilogue operand through TMA: exactly one of residual / mask, bf16 NHWC with 16-byte aligned channel stride
+  p.aux_kind = 0; p.aux_tw = p.tw; p.aux_th = p.th;
+  if (p.use_tma && env_int("SGB_EPI_AUX", 1) && ((d->residual != nullptr) != (d->mask != nullptr))) {
+    if (d->mask) p.aux_kind = 2;
+    else if (!d->res_up2) p.aux_kind = 1;
+    else if (p.tw >= 2) { p.aux_kind = 1; p.aux_tw = p.tw / 2; p.aux_th = p.th >= 2 ? p.th / 2 : 1; }
+  }
   const uint32_t stage_bytes = kABytes + BN * kBlockK * 2;
-  int stages = (int)(((200 - (p.use_tma ? 32 : 0)) * 1024) / stage_bytes);
+  int stages = (int)(((200 - (p.use_tma ? 32 : 0) - (p.aux_kind ? 32 : 0)) * 1024) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
@@ -483,14 +503,23 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
     rc = make_act_tmap(&tmY, d->y, d->B, d->H, d->W, d->Cout, d->y_cstride, p.tw, p.th, p.nb);
     if (rc) return rc;
   }
-  const size_t smem = (size_t)stages * stage_bytes + (p.use_tma ? 2 * kEpiStageBytes : 0) + 1024 + 8 * (2 * stages + 4) + 16;
+  CUtensorMap tmAux = tmA;
+  if (p.aux_kind) {
+    const bool half = (p.aux_kind == 1 && d->res_up2);
+    const void* ap = p.aux_kind == 1 ? d->residual : d->mask;
+    const long long acs = p.aux_kind == 1 ? d->res_cstride : d->mask_cstride;
+    rc = make_act_tmap(&tmAux, ap, d->B, half ? d->H / 2 : d->H, half ? d->W / 2 : d->W, d->Cout, acs, p.aux_tw, p.aux_th, p.nb);
+    if (rc) return rc;
+  }
+  const size_t smem = (size_t)stages * stage_bytes + (p.use_tma ? 2 * kEpiStageBytes : 0) + (p.aux_kind ? 2 * kEpiStageBytes : 0) +
+                      1024 + 8 * (2 * stages + 8) + 16;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     SGB_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     smem_set = 227 * 1024;
   }
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  conv_fprop_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmY, p);
+  conv_fprop_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmY, tmAux, p);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }

@@ -79,6 +79,8 @@ SIGNATURES = {
     "sgb_img_to_nhwc": (c_int, [c_p, c_p, c_int, c_int, c_int, c_int, c_p]),
     "sgb_nhwc_to_img": (c_int, [c_p, c_int, c_i64, c_p, c_int, c_int, c_int, c_int, c_p]),
     "sgb_img_grad_to_nhwc": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p]),
+    "sgb_col27": (c_int, [c_p, c_int, c_i64, c_p, c_int, c_int, c_int, c_p]),
+    "sgb_col27_bwd": (c_int, [c_p, c_p, c_int, c_int, c_int, c_p]),
     "sgb_cast_f32_to_bf16": (c_int, [c_p, c_p, c_i64, c_f, c_p]),
     "sgb_cast_bf16_to_f32": (c_int, [c_p, c_p, c_i64, c_p]),
     "sgb_adam_ema_step": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_f, c_f, c_f, c_f, c_int, c_p, c_f, c_f, c_p]),

@@ -93,8 +93,16 @@ class ConvFn(Function):
             dz = K.axpby(dz, mask=y)
         dx = dW = dbias = dres = None
         if ctx.needs_input_grad[0]:
-            dx = K.conv_fprop(dz, wd, K.pad8(Cin), KH, KW, KH - 1 - pad, KW - 1 - pad,
-                              mask=x if cfg.get("mask_input", False) else None)
+            mask = x if cfg.get("mask_input", False) else None
+            if Cout <= 3 and KH == 3 and KW == 3 and pad == 1 and cfg.get("perm_S", 1) == 1:
+                # C -> 3 image convolution (generator output layer): its input gradient is a 3 -> C convolution of the
+                # 3-channel dz; gather dz's 3x3 patches (K = 27 -> 32) and run it as a 1x1 GEMM instead of a K-padded 3x3.
+                wsn = weight if sigma is None else weight / sigma
+                wcol = wsn.flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, 27).contiguous()
+                wf2, _ = K.weight_pack(wcol, None, Cin, 27, 1, True, False)
+                dx = K.conv_fprop(K.col27(dz), wf2, K.pad8(Cin), 1, 1, 0, 0, mask=mask)
+            else:
+                dx = K.conv_fprop(dz, wd, K.pad8(Cin), KH, KW, KH - 1 - pad, KW - 1 - pad, mask=mask)
             if dx.shape[1] != x.shape[1]:
                 dx = dx[:, :x.shape[1]]
         if ctx.needs_input_grad[1]:
@@ -364,6 +372,19 @@ class ImageInFn(Function):
     @staticmethod
     def backward(ctx, dy):
         return K.nhwc_to_img(K.as_nhwc(dy), ctx.C, tanh=False)
+
+
+class ImageColFn(Function):
+    """NCHW fp32 image -> [B, 32, H, W] bf16 tensor of its 3x3 patches (k = tap*3 + c, zero padded): the operand of the
+    3 -> C input convolution run as a K = 32 GEMM (see ops._ConvBase.forward)."""
+
+    @staticmethod
+    def forward(ctx, img):
+        return K.col27(img)
+
+    @staticmethod
+    def backward(ctx, dcol):
+        return K.col27_bwd(K.as_nhwc(dcol))
 
 
 class ImageOutFn(Function):

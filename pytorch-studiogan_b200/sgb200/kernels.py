@@ -273,6 +273,28 @@ def img_grad_to_nhwc(dimg, y=None, Cp=8):
     return out
 
 
+def col27(src):
+    """3x3 patch gather of a 3-channel image: NCHW fp32 [B,3,H,W] or NHWC bf16 activation (first 3 channels) -> [B,32,H,W]."""
+    if src.dtype == torch.float32:
+        B, C, H, W = src.shape
+        src = src.contiguous()
+        nchw, cs = 1, 0
+    else:
+        B, C, H, W, cs = geom(src)
+        nchw = 0
+    out = empty_nhwc(B, 32, H, W, src.device)
+    L.call("sgb_col27", L.ptr(src), nchw, cs, L.ptr(out), B, H, W, _s())
+    return out
+
+
+def col27_bwd(dcol):
+    B, C, H, W, cs = geom(dcol)
+    assert C == 32 and cs == 32
+    dimg = torch.empty((B, 3, H, W), device=dcol.device, dtype=torch.float32)
+    L.call("sgb_col27_bwd", L.ptr(dcol), L.ptr(dimg), B, H, W, _s())
+    return dimg
+
+
 def cast_f32_to_bf16(x, scale=1.0, out=None):
     if out is None:
         out = torch.empty(x.shape, device=x.device, dtype=bf16)

@@ -225,8 +225,7 @@ class Discriminator(nn.Module):
             ops.init_weights(self.modules, d_init)
 
     def forward(self, x, label, eval=False, adc_fake=False):
-        h = A.ImageInFn.apply(x)
-        h = self.input_conv(h)
+        h = self.input_conv(A.ImageColFn.apply(x))                   # 3x3 patches of the image -> K = 32 GEMM
         for blocklist in self.blocks:
             for block in blocklist:
                 h = block(h)
