@@ -329,3 +329,136 @@ def prdc(real, fake, nearest_k=5):
     density = (1. / float(nearest_k)) * (rf < r_real[:, None]).sum(axis=0).mean()
     coverage = (rf.min(axis=1) < r_real).mean()
     return dict(precision=float(precision), recall=float(recall), density=float(density), coverage=float(coverage))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BigGAN (src/models/big_resnet.py) and ResNetGAN / SNGAN / WGAN-GP (src/models/resnet.py): shared block arithmetic
+# ---------------------------------------------------------------------------------------------------------------------
+R_G_IN = {"32": [4, 4, 4], "64": [16, 8, 4, 2], "128": [16, 16, 8, 4, 2], "256": [16, 16, 8, 8, 4, 2]}
+R_G_OUT = {"32": [4, 4, 4], "64": [8, 4, 2, 1], "128": [16, 8, 4, 2, 1], "256": [16, 8, 8, 4, 2, 1]}
+R_D_IN = {"32": [2, 2, 2], "64": [1, 2, 4, 8], "128": [1, 2, 4, 8, 16], "256": [1, 2, 4, 8, 8, 16]}
+R_D_OUT = {"32": [2, 2, 2, 2], "64": [1, 2, 4, 8, 16], "128": [1, 2, 4, 8, 16, 16], "256": [1, 2, 4, 8, 8, 16, 16]}
+
+
+def _gen_bn(sd, p, x, affine, training, track):
+    if (p + "gain.weight_orig") in sd or (p + "gain.weight") in sd:
+        return cbn(sd, p, x, affine, training, track)
+    return batch_norm(sd, p, x, training, track, affine=True)
+
+
+def res_gen_block(sd, p, x, affine, training=True, track=True):
+    """GenBlock.forward (src/models/big_resnet.py:28-42 == src/models/resnet.py:35-59)."""
+    x0 = x
+    h = F.relu(_gen_bn(sd, p + "bn1.", x, affine, training, track))
+    h = F.interpolate(h, scale_factor=2, mode="nearest")
+    h = conv(sd, p + "conv2d1.", h, 1, training)
+    h = F.relu(_gen_bn(sd, p + "bn2.", h, affine, training, track))
+    h = conv(sd, p + "conv2d2.", h, 1, training)
+    x0 = F.interpolate(x0, scale_factor=2, mode="nearest")
+    x0 = conv(sd, p + "conv2d0.", x0, 0, training)
+    return h + x0
+
+
+def biggan_generator(sd, z, label, img_size, g_conv_dim, attn_g_loc=(), apply_attn=False, training=True, track=True):
+    """Generator.forward of BigGAN (src/models/big_resnet.py:122-158): z chunks, cBN on [shared, chunk]."""
+    key = str(img_size)
+    in_dims = [g_conv_dim * m for m in R_G_IN[key]]
+    nb = len(in_dims)
+    chunk = z.shape[1] // (nb + 1)
+    zs = torch.split(z, chunk, 1)
+    shared = F.embedding(label, sd["shared.weight"])
+    affines = [torch.cat([shared, item], 1) for item in zs[1:]]
+    act = linear(sd, "linear0.", zs[0], training).view(-1, in_dims[0], 4, 4)
+    bi, counter = 0, 0
+    for index in range(nb):
+        act = res_gen_block(sd, "blocks.%d.0." % bi, act, affines[counter], training, track)
+        bi += 1
+        counter += 1
+        if (index + 1) in attn_g_loc and apply_attn:
+            act = self_attention(sd, "blocks.%d.0." % bi, act, training)
+            bi += 1
+    act = F.relu(batch_norm(sd, "bn4.", act, training, track, affine=True))
+    return torch.tanh(conv(sd, "conv2d5.", act, 1, training))
+
+
+def resnet_generator(sd, z, label, img_size, g_conv_dim, num_classes, conditional=True, attn_g_loc=(), apply_attn=False,
+                     training=True, track=True):
+    """Generator.forward of ResNetGAN (src/models/resnet.py:137-169): cBN conditioned on one-hot labels, or plain BN."""
+    key = str(img_size)
+    in_dims = [g_conv_dim * m for m in R_G_IN[key]]
+    affine = F.one_hot(label, num_classes=num_classes).to(torch.float32) if conditional else None
+    act = linear(sd, "linear0.", z, training).view(-1, in_dims[0], 4, 4)
+    bi = 0
+    for index in range(len(in_dims)):
+        act = res_gen_block(sd, "blocks.%d.0." % bi, act, affine, training, track)
+        bi += 1
+        if (index + 1) in attn_g_loc and apply_attn:
+            act = self_attention(sd, "blocks.%d.0." % bi, act, training)
+            bi += 1
+    act = F.relu(batch_norm(sd, "bn4.", act, training, track, affine=True))
+    return torch.tanh(conv(sd, "conv2d5.", act, 1, training))
+
+
+def _has(sd, key):
+    return (key + "weight_orig") in sd or (key + "weight") in sd
+
+
+def res_disc_opt_block(sd, p, x, training=True):
+    """DiscOptBlock.forward (src/models/big_resnet.py:177-192 == src/models/resnet.py:189-204)."""
+    sn = (p + "bn1.weight") not in sd
+    x0 = x
+    h = conv(sd, p + "conv2d1.", x, 1, training)
+    if not sn:
+        h = batch_norm(sd, p + "bn1.", h, training, True, affine=True)
+    h = conv(sd, p + "conv2d2.", F.relu(h), 1, training)
+    h = F.avg_pool2d(h, 2)
+    x0 = F.avg_pool2d(x0, 2)
+    if not sn:
+        x0 = batch_norm(sd, p + "bn0.", x0, training, True, affine=True)
+    return h + conv(sd, p + "conv2d0.", x0, 0, training)
+
+
+def res_disc_block(sd, p, x, downsample, training=True):
+    """DiscBlock.forward (src/models/big_resnet.py:223-242 == src/models/resnet.py:233-254).  With spectral norm the
+    in-place ReLU (src/config.py:486) also rectifies the aliased skip input; with BN in between it does not."""
+    sn = (p + "bn1.weight") not in sd
+    if sn:
+        x = F.relu(x)
+        x0 = x
+        h = x
+    else:
+        x0 = x
+        h = F.relu(batch_norm(sd, p + "bn1.", x, training, True, affine=True))
+    h = conv(sd, p + "conv2d1.", h, 1, training)
+    if not sn:
+        h = batch_norm(sd, p + "bn2.", h, training, True, affine=True)
+    h = conv(sd, p + "conv2d2.", F.relu(h), 1, training)
+    if downsample:
+        h = F.avg_pool2d(h, 2)
+    if _has(sd, p + "conv2d0."):
+        if not sn:
+            x0 = batch_norm(sd, p + "bn0.", x0, training, True, affine=True)
+        x0 = conv(sd, p + "conv2d0.", x0, 0, training)
+        if downsample:
+            x0 = F.avg_pool2d(x0, 2)
+    return h + x0
+
+
+def res_discriminator(sd, x, label, img_size, d_conv_dim, attn_d_loc=(), apply_attn=False, training=True, cond="PD"):
+    """Discriminator.forward of BigGAN / ResNetGAN (src/models/big_resnet.py:349-428, src/models/resnet.py:363-442)."""
+    key = str(img_size)
+    n = len(R_D_IN[key]) + 1
+    down = D_DOWN[key]
+    h = x
+    bi = 0
+    for index in range(n):
+        if index == 0:
+            h = res_disc_opt_block(sd, "blocks.%d.0." % bi, h, training)
+        else:
+            h = res_disc_block(sd, "blocks.%d.0." % bi, h, down[index], training)
+        bi += 1
+        if (index + 1) in attn_d_loc and apply_attn:
+            h = self_attention(sd, "blocks.%d.0." % bi, h, training)
+            bi += 1
+    h = torch.sum(F.relu(h), dim=[2, 3])
+    return disc_head_pd(sd, h, label, training, cond), h

@@ -479,3 +479,32 @@ class SelfAttentionFn(Function):
             sg, us, vs = sn_saved[idx]
             grads_w.append(K.sn_backward(G, w, us, vs, sg, cout, cin, 1))
         return dx, grads_w[0], grads_w[1], grads_w[2], grads_w[3], dsigma, None
+
+
+class ForkFn(Function):
+    """x -> (x, x) for a tensor with two consumers; the two gradients are summed by the library instead of by autograd's
+    implicit accumulation (keeps every full-size element-wise pass on the hot path inside libsgb200)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        if g1 is None:
+            return g2
+        if g2 is None:
+            return g1
+        return K.axpby(K.as_nhwc(g1), K.as_nhwc(g2))
+
+
+class PoolFn(Function):
+    """2x2 average pooling of a tensor that is not a ReLU output (no mask in the backward)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return K.pool2_fwd(x, 0)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.pool2_bwd(K.as_nhwc(dy), 0)

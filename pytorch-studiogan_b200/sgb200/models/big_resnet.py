@@ -1,0 +1,125 @@
+"""BigGAN generator / discriminator (reference ``src/models/big_resnet.py``): hierarchical latent (z split into
+num_blocks + 1 chunks, :77,132-141), cBN conditioned on [shared embedding, z chunk], projection discriminator.
+Same constructor / forward signatures, sub-module names and registration order as the reference."""
+import torch
+import torch.nn as nn
+
+from .. import autograd_ops as A
+from ..utils import ops
+from ._resblocks import DiscBlock, DiscOptBlock, GenBlock
+
+G_IN = {"32": [4, 4, 4], "64": [16, 8, 4, 2], "128": [16, 16, 8, 4, 2], "256": [16, 16, 8, 8, 4, 2], "512": [16, 16, 8, 8, 4, 2, 1]}
+G_OUT = {"32": [4, 4, 4], "64": [8, 4, 2, 1], "128": [16, 8, 4, 2, 1], "256": [16, 8, 8, 4, 2, 1], "512": [16, 8, 8, 4, 2, 1, 1]}
+D_IN = {"32": [2, 2, 2], "64": [1, 2, 4, 8], "128": [1, 2, 4, 8, 16], "256": [1, 2, 4, 8, 8, 16], "512": [1, 1, 2, 4, 8, 8, 16]}
+D_OUT = {"32": [2, 2, 2, 2], "64": [1, 2, 4, 8, 16], "128": [1, 2, 4, 8, 16, 16], "256": [1, 2, 4, 8, 8, 16, 16],
+         "512": [1, 1, 2, 4, 8, 8, 16, 16]}
+D_DOWN = {"32": [True, True, False, False], "64": [True, True, True, True, False], "128": [True, True, True, True, True, False],
+          "256": [True, True, True, True, True, True, False], "512": [True, True, True, True, True, True, True, False]}
+
+
+class Generator(nn.Module):
+    def __init__(self, z_dim, g_shared_dim, img_size, g_conv_dim, apply_attn, attn_g_loc, g_cond_mtd, num_classes, g_init,
+                 g_depth, mixed_precision, MODULES, MODEL):
+        super().__init__()
+        key = str(img_size)
+        self.z_dim = z_dim
+        self.g_shared_dim = g_shared_dim
+        self.g_cond_mtd = g_cond_mtd
+        self.num_classes = num_classes
+        self.mixed_precision = mixed_precision
+        self.MODEL = MODEL
+        self.in_dims = [g_conv_dim * m for m in G_IN[key]]
+        self.out_dims = [g_conv_dim * m for m in G_OUT[key]]
+        self.bottom = 4
+        self.num_blocks = len(self.in_dims)
+        self.chunk_size = z_dim // (self.num_blocks + 1)
+        self.affine_input_dim = self.chunk_size
+        assert self.z_dim % (self.num_blocks + 1) == 0, "z_dim should be divided by the number of blocks"
+        if getattr(MODEL, "info_type", "N/A") != "N/A":
+            raise NotImplementedError("InfoGAN heads are outside the sgb200 hot-path scope (SURVEY.md section 8)")
+
+        self.linear0 = MODULES.g_linear(in_features=self.chunk_size, out_features=self.in_dims[0] * self.bottom * self.bottom, bias=True)
+        if self.g_cond_mtd != "W/O":
+            self.affine_input_dim += self.g_shared_dim
+            self.shared = ops.embedding(num_embeddings=self.num_classes, embedding_dim=self.g_shared_dim)
+
+        blocks = []
+        for index in range(self.num_blocks):
+            blocks.append([GenBlock(in_channels=self.in_dims[index], out_channels=self.out_dims[index], g_cond_mtd=self.g_cond_mtd,
+                                    affine_input_dim=self.affine_input_dim, MODULES=MODULES)])
+            if index + 1 in attn_g_loc and apply_attn:
+                blocks.append([ops.SelfAttention(self.out_dims[index], is_generator=True, MODULES=MODULES)])
+        self.blocks = nn.ModuleList([nn.ModuleList(b) for b in blocks])
+
+        self.bn4 = ops.batchnorm_2d(in_features=self.out_dims[-1])
+        self.activation = MODULES.g_act_fn
+        self.conv2d5 = MODULES.g_conv2d(in_channels=self.out_dims[-1], out_channels=3, kernel_size=3, stride=1, padding=1)
+        self.tanh = nn.Tanh()
+        ops.init_weights(self.modules, g_init)
+
+    def forward(self, z, label, shared_label=None, eval=False):
+        zs = torch.split(z, self.chunk_size, 1)
+        z0 = zs[0]
+        if self.g_cond_mtd != "W/O":
+            if shared_label is None:
+                shared_label = self.shared(label)
+            affines = [A.ToBF16Fn.apply(torch.cat([shared_label, item], 1)) for item in zs[1:]]
+        else:
+            affines = [A.ToBF16Fn.apply(item) for item in zs[1:]]
+        S = self.bottom * self.bottom
+        act = self.linear0(z0, perm_S=S)
+        B = act.shape[0]
+        act = act.reshape(B, self.bottom, self.bottom, self.in_dims[0]).permute(0, 3, 1, 2)
+        counter = 0
+        for blocklist in self.blocks:
+            for block in blocklist:
+                if isinstance(block, ops.SelfAttention):
+                    act = block(act)
+                else:
+                    act = block(act, affines[counter])
+                    counter += 1
+        act = self.bn4(act, relu=True)
+        act = self.conv2d5(act)
+        return A.ImageOutFn.apply(act, 3)
+
+
+class Discriminator(nn.Module):
+    def __init__(self, img_size, d_conv_dim, apply_d_sn, apply_attn, attn_d_loc, d_cond_mtd, aux_cls_type, d_embed_dim,
+                 normalize_d_embed, num_classes, d_init, d_depth, mixed_precision, MODULES, MODEL):
+        super().__init__()
+        key = str(img_size)
+        self.d_cond_mtd = d_cond_mtd
+        self.aux_cls_type = aux_cls_type
+        self.normalize_d_embed = normalize_d_embed
+        self.num_classes = num_classes
+        self.mixed_precision = mixed_precision
+        self.in_dims = [3] + [d_conv_dim * m for m in D_IN[key]]
+        self.out_dims = [d_conv_dim * m for m in D_OUT[key]]
+        self.MODEL = MODEL
+        down = D_DOWN[key]
+        if getattr(MODEL, "info_type", "N/A") != "N/A":
+            raise NotImplementedError("InfoGAN heads are outside the sgb200 hot-path scope (SURVEY.md section 8)")
+
+        blocks = []
+        for index in range(len(self.in_dims)):
+            if index == 0:
+                blocks.append([DiscOptBlock(in_channels=self.in_dims[index], out_channels=self.out_dims[index],
+                                            apply_d_sn=apply_d_sn, MODULES=MODULES)])
+            else:
+                blocks.append([DiscBlock(in_channels=self.in_dims[index], out_channels=self.out_dims[index], apply_d_sn=apply_d_sn,
+                                         MODULES=MODULES, downsample=down[index])])
+            if index + 1 in attn_d_loc and apply_attn:
+                blocks.append([ops.SelfAttention(self.out_dims[index], is_generator=False, MODULES=MODULES)])
+        self.blocks = nn.ModuleList([nn.ModuleList(b) for b in blocks])
+        self.activation = MODULES.d_act_fn
+        ops.build_discriminator_head(self, MODULES, self.out_dims[-1], d_cond_mtd, aux_cls_type, d_embed_dim, num_classes)
+        if d_init:
+            ops.init_weights(self.modules, d_init)
+
+    def forward(self, x, label, eval=False, adc_fake=False):
+        h = x
+        for blocklist in self.blocks:
+            for block in blocklist:
+                h = block(h)
+        h = A.SumHWFn.apply(h, True)
+        return ops.discriminator_head(self, h, label, adc_fake)

@@ -325,3 +325,31 @@ def discriminator_head(D, h, label, adc_fake=False):
             out["mi_embed"], out["mi_proxy"] = mi_embed, mi_proxy
     out.update({"h": h, "adv_output": adv, "label": label})
     return out
+
+
+def build_discriminator_head(D, MODULES, feat, d_cond_mtd, aux_cls_type, d_embed_dim, num_classes):
+    """Registers the head layers in the reference's order (linear1, linear2 / embedding, linear_mi / embedding_mi;
+    src/models/big_resnet.py:303-336, identical in resnet.py and big_resnet_deep_*.py)."""
+    if d_cond_mtd == "MH":
+        D.linear1 = MODULES.d_linear(in_features=feat, out_features=1 + num_classes, bias=True)
+    elif d_cond_mtd == "MD":
+        D.linear1 = MODULES.d_linear(in_features=feat, out_features=num_classes, bias=True)
+    else:
+        D.linear1 = MODULES.d_linear(in_features=feat, out_features=1, bias=True)
+    if aux_cls_type == "ADC":
+        num_classes = num_classes * 2
+    if d_cond_mtd == "AC":
+        D.linear2 = MODULES.d_linear(in_features=feat, out_features=num_classes, bias=False)
+    elif d_cond_mtd == "PD":
+        D.embedding = MODULES.d_embedding(num_classes, feat)
+    elif d_cond_mtd in ["2C", "D2DCE"]:
+        D.linear2 = MODULES.d_linear(in_features=feat, out_features=d_embed_dim, bias=True)
+        D.embedding = MODULES.d_embedding(num_classes, d_embed_dim)
+    if aux_cls_type == "TAC":
+        if d_cond_mtd == "AC":
+            D.linear_mi = MODULES.d_linear(in_features=feat, out_features=num_classes, bias=False)
+        elif d_cond_mtd in ["2C", "D2DCE"]:
+            D.linear_mi = MODULES.d_linear(in_features=feat, out_features=d_embed_dim, bias=True)
+            D.embedding_mi = MODULES.d_embedding(num_classes, d_embed_dim)
+        else:
+            raise NotImplementedError

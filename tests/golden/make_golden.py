@@ -28,6 +28,8 @@ import utils.ops as rops  # noqa: E402  (reference)
 import utils.losses as rlosses  # noqa: E402
 import utils.ema as rema  # noqa: E402
 import models.big_resnet_deep_legacy as rdeep  # noqa: E402
+import models.big_resnet as rbig  # noqa: E402
+import models.resnet as rres  # noqa: E402
 import scipy.linalg  # noqa: E402
 import metrics.fid as rfid  # noqa: E402
 import metrics.ins as rins  # noqa: E402
@@ -117,6 +119,54 @@ def golden_deep(tag, img_size, conv_dim, depth, attn, z_dim=16, shared=16, class
     print(tag, "keys", len(out), "d_loss", float(d_loss), "g_loss", float(g_loss))
 
 
+def golden_resfamily(tag, family, conv_dim, attn, g_sn, d_sn, g_cond, d_cond, adv, z_dim=20, shared=16, classes=5, B=8, img_size=32):
+    """BigGAN (big_resnet) / ResNetGAN (resnet): D phase + G phase exactly as golden_deep."""
+    torch.manual_seed(4321)
+    M = modules(g_sn=g_sn, d_sn=d_sn, cbn=(g_cond == "cBN" or family == "big_resnet"))
+    mod = rbig if family == "big_resnet" else rres
+    G = mod.Generator(z_dim=z_dim, g_shared_dim=shared, img_size=img_size, g_conv_dim=conv_dim, apply_attn=attn, attn_g_loc=[2],
+                      g_cond_mtd=g_cond, num_classes=classes, g_init="ortho", g_depth="N/A", mixed_precision=False, MODULES=M, MODEL=MODEL)
+    D = mod.Discriminator(img_size=img_size, d_conv_dim=conv_dim, apply_d_sn=d_sn, apply_attn=attn, attn_d_loc=[1], d_cond_mtd=d_cond,
+                          aux_cls_type="W/O", d_embed_dim="N/A", normalize_d_embed=False, num_classes=classes, d_init="ortho",
+                          d_depth="N/A", mixed_precision=False, MODULES=M, MODEL=MODEL)
+    G.train(); D.train()
+    with torch.no_grad():
+        for m_ in list(G.modules()) + list(D.modules()):
+            if isinstance(m_, rops.SelfAttention):
+                m_.sigma.fill_(0.37)
+    d_loss_fn = {"hinge": rlosses.d_hinge, "wasserstein": rlosses.d_wasserstein}[adv]
+    g_loss_fn = {"hinge": rlosses.g_hinge, "wasserstein": rlosses.g_wasserstein}[adv]
+    out = {}
+    out.update(sd_np(G, "G0/")); out.update(sd_np(D, "D0/"))
+    z = torch.randn(B, z_dim); y_fake = torch.randint(0, classes, (B,))
+    real = torch.rand(B, 3, img_size, img_size) * 2 - 1; y_real = torch.randint(0, classes, (B,))
+    out.update({"z": z.numpy(), "y_fake": y_fake.numpy(), "real": real.numpy(), "y_real": y_real.numpy()})
+    for p in G.parameters():
+        p.requires_grad_(False)
+    fake = G(z, y_fake)
+    real_d = D(real, y_real); fake_d = D(fake.detach(), y_fake)
+    d_loss = d_loss_fn(real_d["adv_output"], fake_d["adv_output"], False)
+    d_loss.backward()
+    out.update({"fake": fake.detach().numpy(), "adv_real": real_d["adv_output"].detach().numpy(),
+                "adv_fake": fake_d["adv_output"].detach().numpy(), "h_real": real_d["h"].detach().numpy(), "d_loss": d_loss.detach().numpy()})
+    for k, p in D.named_parameters():
+        out["Dgrad/" + k] = p.grad.detach().numpy().copy()
+    out.update(sd_np(G, "G1/")); out.update(sd_np(D, "D1/"))
+    D.zero_grad()
+    for p in G.parameters():
+        p.requires_grad_(True)
+    for p in D.parameters():
+        p.requires_grad_(False)
+    fake2 = G(z, y_fake)
+    g_loss = g_loss_fn(D(fake2, y_fake)["adv_output"], False)
+    g_loss.backward()
+    out.update({"fake2": fake2.detach().numpy(), "g_loss": g_loss.detach().numpy()})
+    for k, p in G.named_parameters():
+        out["Ggrad/" + k] = p.grad.detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
+    print(tag, "keys", len(out), "d_loss", float(d_loss), "g_loss", float(g_loss))
+
+
 def golden_metrics():
     rng = np.random.RandomState(0)
     out = {}
@@ -176,4 +226,8 @@ if __name__ == "__main__":
     golden_deep("deep32_c8", 32, 8, 1, attn=False)
     golden_deep("deep32_c16_attn_d2", 32, 16, 2, attn=True, B=2)
     golden_deep("deep32_c8_b16", 32, 8, 1, attn=False, B=16)      # well-conditioned BatchNorm statistics for gradient parity
+    golden_resfamily("biggan32_c16_attn", "big_resnet", 16, True, True, True, "cBN", "PD", "hinge")
+    golden_resfamily("sngan32_c16", "resnet", 16, False, False, True, "W/O", "W/O", "hinge", z_dim=32)
+    golden_resfamily("resnet32_cbn_c16", "resnet", 16, False, False, True, "cBN", "PD", "hinge", z_dim=32)
+    golden_resfamily("wgan32_bn_c16", "resnet", 16, False, False, False, "W/O", "W/O", "wasserstein", z_dim=32)
     golden_metrics()

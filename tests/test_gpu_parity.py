@@ -323,3 +323,66 @@ def test_property_conv_linearity_and_dgrad_adjoint_at_scale():
     lhs = (f(x1) * y.float()).sum()
     rhs = (x1.float() * K.conv_fprop(y, wd, C, 3, 3, 1, 1, out_fp32=True)).sum()
     assert abs(float(lhs - rhs)) < 2e-3 * abs(float(lhs)) + 1.0
+
+
+# ------------------------------------------------------------------------------------------------ BigGAN / ResNetGAN families
+RES_CASES = {
+    "biggan32_c16_attn": dict(family="big_resnet", attn=True, g_sn=True, d_sn=True, g_cond="cBN", d_cond="PD", adv="hinge", z_dim=20),
+    "sngan32_c16": dict(family="resnet", attn=False, g_sn=False, d_sn=True, g_cond="W/O", d_cond="W/O", adv="hinge", z_dim=32),
+    "resnet32_cbn_c16": dict(family="resnet", attn=False, g_sn=False, d_sn=True, g_cond="cBN", d_cond="PD", adv="hinge", z_dim=32),
+    "wgan32_bn_c16": dict(family="resnet", attn=False, g_sn=False, d_sn=False, g_cond="W/O", d_cond="W/O", adv="wasserstein", z_dim=32),
+}
+
+
+@pytest.mark.parametrize("tag", list(RES_CASES))
+def test_biggan_and_resnetgan_d_and_g_phase_vs_reference_golden(golden_dir, tag):
+    """BigGAN (src/models/big_resnet.py) and ResNetGAN / SNGAN / BN-discriminator (src/models/resnet.py) through the CUDA
+    path against the reference's own numbers (B = 8).  Tolerances as for BigGAN-Deep: relative L2 <= 4e-2 on images / logits,
+    <= 1e-1 on D-phase gradients; G-phase gradients (bf16 through two networks and batch-norm backward at B = 8):
+    worst <= 0.5, cosine >= 0.9."""
+    import importlib
+    from sgb200 import config as C
+    from sgb200.utils import losses
+    dev = _cuda()
+    c = RES_CASES[tag]
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    mod = importlib.import_module("sgb200.models." + c["family"])
+    M = C.make_modules(c["g_sn"], c["d_sn"], c["g_cond"], c["family"])
+    MODEL = C._Section(info_type="N/A", g_info_injection="N/A")
+    G = mod.Generator(z_dim=c["z_dim"], g_shared_dim=16, img_size=32, g_conv_dim=16, apply_attn=c["attn"], attn_g_loc=[2],
+                      g_cond_mtd=c["g_cond"], num_classes=5, g_init="ortho", g_depth="N/A", mixed_precision=False, MODULES=M, MODEL=MODEL)
+    D = mod.Discriminator(img_size=32, d_conv_dim=16, apply_d_sn=c["d_sn"], apply_attn=c["attn"], attn_d_loc=[1], d_cond_mtd=c["d_cond"],
+                          aux_cls_type="W/O", d_embed_dim="N/A", normalize_d_embed=False, num_classes=5, d_init="ortho", d_depth="N/A",
+                          mixed_precision=False, MODULES=M, MODEL=MODEL)
+    G.load_state_dict({k[3:]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith("G0/")}, strict=True)
+    D.load_state_dict({k[3:]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith("D0/")}, strict=True)
+    G, D = G.to(dev).train(), D.to(dev).train()
+    dl = {"hinge": losses.d_hinge, "wasserstein": losses.d_wasserstein}[c["adv"]]
+    gl = {"hinge": losses.g_hinge, "wasserstein": losses.g_wasserstein}[c["adv"]]
+    z, yf = torch.from_numpy(g["z"]).to(dev), torch.from_numpy(g["y_fake"]).to(dev)
+    real, yr = torch.from_numpy(g["real"]).to(dev), torch.from_numpy(g["y_real"]).to(dev)
+    for p in G.parameters():
+        p.requires_grad_(False)
+    fake = G(z, yf)
+    assert l2_err(fake, torch.from_numpy(g["fake"])) < 4e-2
+    rd, fd = D(real, yr), D(fake.detach(), yf)
+    assert l2_err(rd["h"], torch.from_numpy(g["h_real"])) < 4e-2
+    assert l2_err(rd["adv_output"], torch.from_numpy(g["adv_real"])) < 4e-2
+    assert l2_err(fd["adv_output"], torch.from_numpy(g["adv_fake"])) < 4e-2
+    d_loss = dl(rd["adv_output"], fd["adv_output"])
+    d_loss.backward()
+    assert abs(float(d_loss.detach()) - float(g["d_loss"])) < 5e-2 * abs(float(g["d_loss"])) + 1e-2
+    worst = _worst_grad(D, g, "Dgrad/")
+    assert worst[0] < 1e-1, worst
+    D.zero_grad(set_to_none=True)
+    for p in G.parameters():
+        p.requires_grad_(True)
+    for p in D.parameters():
+        p.requires_grad_(False)
+    fake2 = G(z, yf)
+    assert l2_err(fake2, torch.from_numpy(g["fake2"])) < 4e-2
+    g_loss = gl(D(fake2, yf)["adv_output"])
+    g_loss.backward()
+    assert abs(float(g_loss.detach()) - float(g["g_loss"])) < 5e-2 * abs(float(g["g_loss"])) + 1e-2
+    worst, median, cos = _grad_errors(G, g, "Ggrad/")
+    assert worst[0] <= 0.5 and cos[0] >= 0.9, (worst, median, cos)
