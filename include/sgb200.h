@@ -105,6 +105,23 @@ int sgb_sn_power_iter(const float* W, float* u, float* v, float* sigma, float* w
 /* Cout_p / Cin_p >= Cout / Cin are the (zero-padded, caller-zeroed) pack extents, e.g. 3 -> 8 for image convs. */
 int sgb_weight_pack(const float* W, const float* sigma, void* w_fprop, void* w_dgrad, int32_t Cout, int32_t Cin,
                     int32_t taps, int32_t perm_S, int32_t Cout_p, int32_t Cin_p, sgb_stream_t stream);
+/* Batched form: all layers of a network in three launches.  ``table`` is a DEVICE array of sgb_sn_layer; per layer it
+ * runs the power iteration (has_sn) and writes sigma_all[layer] (1 for layers without spectral norm), then emits the packs
+ * at pack_f + off_f / pack_d + off_d (element offsets, bf16; caller zero-fills padded extents; pack_d may be NULL).
+ * max_blocks_*: grid.x of the three kernels (>= the largest per-layer need, see sgb200/snbatch.py). */
+typedef struct sgb_sn_layer {
+  const float* W;
+  float* u;
+  float* v;
+  float* ws;
+  int32_t R, K;
+  int32_t Cout, Cin, taps, perm_S, Cout_p, Cin_p;
+  int64_t off_f, off_d;
+  int32_t has_sn, reserved;
+} sgb_sn_layer;
+int sgb_sn_batch(const sgb_sn_layer* table, int32_t n_layers, float* sigma_all, void* pack_f, void* pack_d, float eps,
+                 int32_t do_power_iteration, int32_t max_blocks_wtu, int32_t max_blocks_wv, int32_t max_blocks_pack,
+                 sgb_stream_t stream);
 /* dW[Cout][Cin][taps] (=|+=) (G - <G, W/sigma> u v^T) / sigma with G in the fprop-pack layout (fp32, from
  * sgb_conv_wgrad).  sigma NULL: plain re-layout of G (layers without spectral norm). */
 int sgb_sn_backward(const float* G, const float* W, const float* u, const float* v, const float* sigma,

@@ -171,9 +171,140 @@ __global__ void __launch_bounds__(256) sn_bwd_apply_kernel(const float* __restri
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Batched variant: every spectrally-normalised layer of a network in three launches (blockIdx.y = layer).  The per-layer
+// launches above cost ~30 us each in dependent tiny kernels; a BigGAN-Deep generator has 150+ such layers per forward.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sn_wtu_batch_kernel(const sgb_sn_layer* __restrict__ table, float eps) {
+  __shared__ float sh[32];
+  __shared__ bool last;
+  const sgb_sn_layer L = table[blockIdx.y];
+  if (!L.has_sn) return;
+  const int R = L.R, K = L.K;
+  const int col_blocks = (K + 255) / 256, rows_per_block = 64;
+  const int row_blocks = (R + rows_per_block - 1) / rows_per_block;
+  const unsigned total = (unsigned)col_blocks * row_blocks;
+  if (blockIdx.x >= total) return;
+  const int bx = blockIdx.x % col_blocks, by = blockIdx.x / col_blocks;
+  const float* W = L.W;
+  float* ws = L.ws;
+  const int c = bx * 256 + threadIdx.x;
+  const int r0 = by * rows_per_block, r1 = min(r0 + rows_per_block, R);
+  if (c < K) {
+    float acc = 0.f;
+    const float* wp = W + (size_t)r0 * K + c;
+    for (int r = r0; r < r1; ++r, wp += K) acc = fmaf(__ldg(wp), __ldg(L.u + r), acc);
+    atomicAdd(ws + c, acc);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* ticket = reinterpret_cast<unsigned*>(ws + K + R);
+    last = (atomicAdd(ticket, 1u) == total - 1);
+    if (last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < K; i += 256) { const float t = __ldcg(ws + i); ss = fmaf(t, t, ss); }
+  ss = block_sum(ss, sh);
+  const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+  for (int i = threadIdx.x; i < K; i += 256) {
+    L.v[i] = __ldcg(ws + i) * inv;
+    ws[i] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) sn_wv_batch_kernel(const sgb_sn_layer* __restrict__ table, float* __restrict__ sigma_all,
+                                                           float eps, int update_u) {
+  __shared__ float sh[32];
+  __shared__ bool last;
+  const sgb_sn_layer L = table[blockIdx.y];
+  if (!L.has_sn) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) sigma_all[blockIdx.y] = 1.f;
+    return;
+  }
+  const int R = L.R, K = L.K;
+  const unsigned nblk = min((unsigned)gridDim.x, (unsigned)((R + 7) / 8));
+  if (blockIdx.x >= nblk) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s = L.ws + K;
+  for (int r = blockIdx.x * 8 + warp; r < R; r += nblk * 8) {
+    const float* wp = L.W + (size_t)r * K;
+    float acc = 0.f;
+    for (int i = lane; i < K; i += 32) acc = fmaf(__ldg(wp + i), __ldcg(L.v + i), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) s[r] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* ticket = reinterpret_cast<unsigned*>(L.ws + K + R + 1);
+    last = (atomicAdd(ticket, 1u) == nblk - 1);
+    if (last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float* sigma = sigma_all + blockIdx.y;
+  if (update_u) {
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < R; i += 256) { const float t = __ldcg(s + i); ss = fmaf(t, t, ss); }
+    ss = block_sum(ss, sh);
+    const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+    for (int i = threadIdx.x; i < R; i += 256) L.u[i] = __ldcg(s + i) * inv;
+    if (threadIdx.x == 0) *sigma = ss * inv;
+  } else {
+    float d = 0.f;
+    for (int i = threadIdx.x; i < R; i += 256) d = fmaf(__ldcg(s + i), L.u[i], d);
+    d = block_sum(d, sh);
+    if (threadIdx.x == 0) *sigma = d;
+  }
+}
+
+__global__ void __launch_bounds__(256) sn_pack_batch_kernel(const sgb_sn_layer* __restrict__ table, const float* __restrict__ sigma_all,
+                                                             bf16* __restrict__ pack_f, bf16* __restrict__ pack_d) {
+  const sgb_sn_layer L = table[blockIdx.y];
+  const int Cout = L.Cout, Cin = L.Cin, taps = L.taps, perm_S = L.perm_S;
+  const size_t total = (size_t)Cout * Cin * taps;
+  const float inv = 1.f / __ldcg(sigma_all + blockIdx.y);
+  bf16* wf = pack_f ? pack_f + L.off_f : nullptr;
+  bf16* wd = pack_d ? pack_d + L.off_d : nullptr;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int tap = (int)(i % taps);
+    const int ci = (int)((i / taps) % Cin);
+    int co = (int)(i / ((size_t)taps * Cin));
+    const float val = __ldg(L.W + i) * inv;
+    if (perm_S > 1) { const int C = Cout / perm_S; co = (co % perm_S) * C + co / perm_S; }
+    const bf16 b = __float2bfloat16_rn(val);
+    if (wf) wf[((size_t)co * taps + tap) * L.Cin_p + ci] = b;
+    if (wd) wd[((size_t)ci * taps + (taps - 1 - tap)) * L.Cout_p + co] = b;
+  }
+}
+
 }  // namespace sgb
 
 using namespace sgb;
+
+extern "C" int sgb_sn_batch(const sgb_sn_layer* table, int32_t n_layers, float* sigma_all, void* pack_f, void* pack_d, float eps,
+                            int32_t do_power_iteration, int32_t max_blocks_wtu, int32_t max_blocks_wv, int32_t max_blocks_pack,
+                            sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(table && n_layers > 0 && sigma_all && max_blocks_wtu > 0 && max_blocks_wv > 0 && max_blocks_pack > 0);
+  if (do_power_iteration) {
+    sn_wtu_batch_kernel<<<dim3(max_blocks_wtu, n_layers), 256, 0, stream>>>(table, eps);
+    SGB_LAUNCH_CHECK();
+  }
+  sn_wv_batch_kernel<<<dim3(max_blocks_wv, n_layers), 256, 0, stream>>>(table, sigma_all, eps, do_power_iteration);
+  SGB_LAUNCH_CHECK();
+  if (pack_f || pack_d) {
+    sn_pack_batch_kernel<<<dim3(max_blocks_pack, n_layers), 256, 0, stream>>>(table, sigma_all, (bf16*)pack_f, (bf16*)pack_d);
+    SGB_LAUNCH_CHECK();
+  }
+  return SGB_OK;
+}
 
 extern "C" int64_t sgb_sn_workspace_floats(int32_t R, int32_t K) { return (int64_t)R + K + 4; }
 

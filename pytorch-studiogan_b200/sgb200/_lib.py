@@ -58,6 +58,7 @@ SIGNATURES = {
     "sgb_sn_workspace_floats": (c_i64, [c_int, c_int]),
     "sgb_sn_power_iter": (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_f, c_int, c_p]),
     "sgb_weight_pack": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "sgb_sn_batch": (c_int, [c_p, c_int, c_p, c_p, c_p, c_f, c_int, c_int, c_int, c_int, c_p]),
     "sgb_sn_backward": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "sgb_bn_stats": (c_int, [c_p, c_i64, c_int, c_i64, c_p, c_p, c_p]),
     "sgb_bn_finalize": (c_int, [c_p, c_p, c_f, c_p, c_p, c_f, c_f, c_int, c_int, c_int, c_p, c_p, c_int, c_int,

@@ -61,19 +61,24 @@ class ConvFn(Function):
         taps = KH * KW
         sn = cfg.get("sn")
         sigma = u_saved = v_saved = None
-        if sn is not None:
-            u, v, ws = sn.tensors()
-            sigma = torch.empty(1, device=weight.device, dtype=torch.float32)
-            K.sn_power_iter(weight, u, v, sigma, ws, sn.eps, cfg.get("do_power_iteration", True))
         need_dx = ctx.needs_input_grad[0]
         need_dw = ctx.needs_input_grad[1]
-        wf, wd = K.weight_pack(weight, sigma, Cout, Cin, taps, True, need_dx, cfg.get("perm_S", 1))
+        cache = cfg.get("sn_cache")
+        if cache is not None:                       # power iteration + packs already done by the network's batched pass
+            wf, wd, sigma, u_saved, v_saved = cache
+            u = v = None
+        else:
+            if sn is not None:
+                u, v, ws = sn.tensors()
+                sigma = torch.empty(1, device=weight.device, dtype=torch.float32)
+                K.sn_power_iter(weight, u, v, sigma, ws, sn.eps, cfg.get("do_power_iteration", True))
+            wf, wd = K.weight_pack(weight, sigma, Cout, Cin, taps, True, need_dx, cfg.get("perm_S", 1))
         Cout_p = K.pad8(Cout)
         res = residual
         y = K.conv_fprop(x, wf, Cout_p, KH, KW, pad, pad, bias=bias if Cout_p == Cout else _pad_bias(bias, Cout_p),
                          residual=res, res_up2=cfg.get("res_up2", False), relu=cfg.get("relu", False),
                          out_fp32=cfg.get("out_fp32", False))
-        if need_dw and sn is not None:
+        if need_dw and sn is not None and cache is None:
             u_saved, v_saved = u.clone(), v.clone()
         ctx.cfg = cfg
         ctx.dims = (Cout, Cin, taps)
@@ -289,16 +294,20 @@ class ConcatSkipFn(Function):
         Cextra = weight.shape[0]
         sn = cfg.get("sn")
         sigma = u_saved = v_saved = None
-        if sn is not None:
-            u, v, ws = sn.tensors()
-            sigma = torch.empty(1, device=weight.device, dtype=torch.float32)
-            K.sn_power_iter(weight, u, v, sigma, ws, sn.eps, cfg.get("do_power_iteration", True))
         need_dx = ctx.needs_input_grad[0]
-        wf, wd = K.weight_pack(weight, sigma, Cextra, Cin, 1, True, need_dx)
+        cache = cfg.get("sn_cache")
+        if cache is not None:
+            wf, wd, sigma, u_saved, v_saved = cache
+        else:
+            if sn is not None:
+                u, v, ws = sn.tensors()
+                sigma = torch.empty(1, device=weight.device, dtype=torch.float32)
+                K.sn_power_iter(weight, u, v, sigma, ws, sn.eps, cfg.get("do_power_iteration", True))
+            wf, wd = K.weight_pack(weight, sigma, Cextra, Cin, 1, True, need_dx)
         skip = K.empty_nhwc(B, Cin + Cextra, H, W, px.device)
         K.axpby(px, out=skip[:, :Cin])
         K.conv_fprop(skip[:, :Cin], wf, Cextra, 1, 1, 0, 0, bias=bias, out=skip[:, Cin:])
-        if ctx.needs_input_grad[1] and sn is not None:
+        if ctx.needs_input_grad[1] and sn is not None and cache is None:
             u_saved, v_saved = u.clone(), v.clone()
         ctx.cfg = cfg
         ctx.dims = (Cextra, Cin)
@@ -419,12 +428,16 @@ class SelfAttentionFn(Function):
             sn = cfg.get("sn")
             sg = None
             us = vs = None
-            if sn is not None:
-                u, v, ws = sn.tensors()
-                sg = torch.empty(1, device=w.device, dtype=torch.float32)
-                K.sn_power_iter(w, u, v, sg, ws, sn.eps, cfg.get("do_power_iteration", True))
-                us, vs = u.clone(), v.clone()
-            wf, wd = K.weight_pack(w, sg, cout, cin, 1, True, True)
+            cache = cfg.get("sn_cache")
+            if cache is not None and cache[1] is not None:
+                wf, wd, sg, us, vs = cache
+            else:
+                if sn is not None:
+                    u, v, ws = sn.tensors()
+                    sg = torch.empty(1, device=w.device, dtype=torch.float32)
+                    K.sn_power_iter(w, u, v, sg, ws, sn.eps, cfg.get("do_power_iteration", True))
+                    us, vs = u.clone(), v.clone()
+                wf, wd = K.weight_pack(w, sg, cout, cin, 1, True, True)
             packs.append((wf, wd))
             sn_saved.append((sg, us, vs))
         theta = K.conv_fprop(x, packs[0][0], c8, 1, 1, 0, 0)                      # [B, c8, H, W]

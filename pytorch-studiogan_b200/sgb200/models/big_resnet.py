@@ -5,6 +5,7 @@ import torch
 import torch.nn as nn
 
 from .. import autograd_ops as A
+from ..snbatch import SNBatch
 from ..utils import ops
 from ._resblocks import DiscBlock, DiscOptBlock, GenBlock
 
@@ -56,8 +57,11 @@ class Generator(nn.Module):
         self.conv2d5 = MODULES.g_conv2d(in_channels=self.out_dims[-1], out_channels=3, kernel_size=3, stride=1, padding=1)
         self.tanh = nn.Tanh()
         ops.init_weights(self.modules, g_init)
+        self.linear0._perm_S = self.bottom * self.bottom
+        self._snb = SNBatch(self)
 
     def forward(self, z, label, shared_label=None, eval=False):
+        self._snb.run()
         zs = torch.split(z, self.chunk_size, 1)
         z0 = zs[0]
         if self.g_cond_mtd != "W/O":
@@ -80,6 +84,7 @@ class Generator(nn.Module):
                     counter += 1
         act = self.bn4(act, relu=True)
         act = self.conv2d5(act)
+        self._snb.clear()
         return A.ImageOutFn.apply(act, 3)
 
 
@@ -115,11 +120,14 @@ class Discriminator(nn.Module):
         ops.build_discriminator_head(self, MODULES, self.out_dims[-1], d_cond_mtd, aux_cls_type, d_embed_dim, num_classes)
         if d_init:
             ops.init_weights(self.modules, d_init)
+        self._snb = SNBatch(self)
 
     def forward(self, x, label, eval=False, adc_fake=False):
+        self._snb.run()
         h = x
         for blocklist in self.blocks:
             for block in blocklist:
                 h = block(h)
         h = A.SumHWFn.apply(h, True)
+        self._snb.clear()
         return ops.discriminator_head(self, h, label, adc_fake)

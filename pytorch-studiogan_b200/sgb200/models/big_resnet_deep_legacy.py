@@ -14,6 +14,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import autograd_ops as A
+from ..snbatch import SNBatch
 from ..utils import ops
 
 G_IN = {"32": [4, 4, 4], "64": [16, 8, 4, 2], "128": [16, 16, 8, 4, 2], "256": [16, 16, 8, 8, 4, 2],
@@ -105,8 +106,11 @@ class Generator(nn.Module):
         self.tanh = nn.Tanh()
 
         ops.init_weights(self.modules, g_init)
+        self.linear0._perm_S = self.bottom * self.bottom
+        self._snb = SNBatch(self)
 
     def forward(self, z, label, shared_label=None, eval=False):
+        self._snb.run()                                               # one power iteration + packs for every layer
         parts = []
         if self.g_cond_mtd != "W/O":
             if shared_label is None:
@@ -124,6 +128,7 @@ class Generator(nn.Module):
                 act = block(act) if isinstance(block, ops.SelfAttention) else block(act, affine)
         act = self.bn4(act, relu=True)
         act = self.conv2d5(act)
+        self._snb.clear()
         return A.ImageOutFn.apply(act, 3)
 
 
@@ -157,7 +162,8 @@ class DiscBlock(nn.Module):
         if self.learnable_sc:
             c0 = self.conv2d0
             skip = A.ConcatSkipFn.apply(px, ops._w(c0), c0.bias,
-                                        {"sn": getattr(c0, "_sn", None), "do_power_iteration": c0.training})
+                                        {"sn": getattr(c0, "_sn", None), "do_power_iteration": c0.training,
+                                         "sn_cache": getattr(c0, "_sn_cache", None)})
         return self.conv2d4(h, residual=skip, mask_input=not self.downsample)
 
 
@@ -223,11 +229,17 @@ class Discriminator(nn.Module):
 
         if d_init:
             ops.init_weights(self.modules, d_init)
+        for name in ("linear1", "linear2", "linear_mi"):
+            if hasattr(self, name):
+                getattr(self, name)._head_layer = True      # fp32 head path, outside the batched SN / pack pass
+        self._snb = SNBatch(self)
 
     def forward(self, x, label, eval=False, adc_fake=False):
+        self._snb.run()
         h = self.input_conv(A.ImageColFn.apply(x))                   # 3x3 patches of the image -> K = 32 GEMM
         for blocklist in self.blocks:
             for block in blocklist:
                 h = block(h)
         h = A.SumHWFn.apply(h, True)                                  # relu + sum over (H, W), fp32 [B, C]
+        self._snb.clear()
         return ops.discriminator_head(self, h, label, adc_fake)

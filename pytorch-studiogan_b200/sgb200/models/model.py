@@ -37,6 +37,8 @@ def load_generator_discriminator(DATA, OPTIMIZATION, MODEL, STYLEGAN, MODULES, R
             if hasattr(m, "_sn"):
                 m._sn.module = m
                 m._sn.ws = None
+        if hasattr(Gen_ema, "_snb"):
+            Gen_ema._snb.net, Gen_ema._snb.mods = Gen_ema, None
         ema = Ema(source=Gen, target=Gen_ema, decay=MODEL.g_ema_decay, start_iter=MODEL.g_ema_start)
     else:
         Gen_ema, ema = None, None

@@ -1,0 +1,124 @@
+"""Batched spectral normalisation for a whole network: one power iteration + sigma + weight packs for EVERY conv / linear
+layer in three kernel launches (``sgb_sn_batch``), run at the top of ``Generator.forward`` / ``Discriminator.forward``.
+
+Semantics are those of the per-layer forward-pre-hooks of the reference (torch/nn/utils/spectral_norm.py:62-114): each
+layer's iteration depends only on its own W, u, v, and every network forward performs exactly one iteration per layer,
+so running them all before the first layer is arithmetically the same as running each right before its layer.
+
+Implementation notes
+* u / v buffers of all layers become views of two flat arenas (their values and state_dict keys are unchanged), so the
+  copies the backward pass needs ("u, v at the time of this forward") are two clones instead of 2 x layers.
+* packs of one forward live in one flat bf16 buffer per direction; each layer receives views.
+* layers that are not spectrally normalised (e.g. SNGAN's generator) are packed by the same launch with sigma = 1.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import kernels as K
+from .utils import ops
+
+LAYER_DTYPE = np.dtype([("W", "<u8"), ("u", "<u8"), ("v", "<u8"), ("ws", "<u8"), ("R", "<i4"), ("K", "<i4"),
+                        ("Cout", "<i4"), ("Cin", "<i4"), ("taps", "<i4"), ("perm_S", "<i4"), ("Cout_p", "<i4"), ("Cin_p", "<i4"),
+                        ("off_f", "<i8"), ("off_d", "<i8"), ("has_sn", "<i4"), ("reserved", "<i4")])
+assert LAYER_DTYPE.itemsize == 88
+
+
+def _eligible(m):
+    if isinstance(m, ops._ConvBase):
+        return not (m.in_channels == 3 and m.kernel_size == (3, 3))      # image convs run the im2col path
+    return isinstance(m, ops._LinearBase) and not getattr(m, "_head_layer", False)
+
+
+class SNBatch:
+    def __init__(self, net):
+        self.net = net
+        self.mods = None
+        self.device = None
+
+    def _build(self, device):
+        mods = [m for m in self.net.modules() if _eligible(m)]
+        nu = sum(ops._w(m).shape[0] for m in mods if hasattr(m, "_sn"))
+        nv = sum(ops._w(m).numel() // ops._w(m).shape[0] for m in mods if hasattr(m, "_sn"))
+        self.u_flat = torch.empty(max(nu, 1), device=device, dtype=torch.float32)
+        self.v_flat = torch.empty(max(nv, 1), device=device, dtype=torch.float32)
+        nws = sum(ops._w(m).shape[0] + ops._w(m).numel() // ops._w(m).shape[0] + 4 for m in mods if hasattr(m, "_sn"))
+        self.ws_flat = torch.zeros(max(nws, 1), device=device, dtype=torch.float32)
+        table = np.zeros(len(mods), dtype=LAYER_DTYPE)
+        ou = ov = ows = 0
+        off_f = off_d = 0
+        self.slices = []
+        mb1 = mb2 = mb3 = 1
+        for i, m in enumerate(mods):
+            W = ops._w(m)
+            Cout = W.shape[0]
+            taps = W.shape[2] * W.shape[3] if W.dim() == 4 else 1
+            Cin = W.numel() // (Cout * taps)
+            R, Kd = Cout, Cin * taps
+            Cout_p, Cin_p = K.pad8(Cout), K.pad8(Cin)
+            e = table[i]
+            e["W"] = W.data_ptr()
+            e["R"], e["K"], e["Cout"], e["Cin"], e["taps"] = R, Kd, Cout, Cin, taps
+            e["perm_S"] = getattr(m, "_perm_S", 1)
+            e["Cout_p"], e["Cin_p"] = Cout_p, Cin_p
+            nf = Cout_p * taps * Cin_p
+            e["off_f"], e["off_d"] = off_f, off_d
+            su = sv = None
+            if hasattr(m, "_sn"):
+                e["has_sn"] = 1
+                with torch.no_grad():
+                    self.u_flat[ou:ou + R].copy_(m.weight_u)
+                    self.v_flat[ov:ov + Kd].copy_(m.weight_v)
+                m.weight_u.data = self.u_flat[ou:ou + R]
+                m.weight_v.data = self.v_flat[ov:ov + Kd]
+                e["u"], e["v"] = m.weight_u.data_ptr(), m.weight_v.data_ptr()
+                e["ws"] = self.ws_flat[ows:].data_ptr()
+                su, sv = (ou, ou + R), (ov, ov + Kd)
+                ou += R
+                ov += Kd
+                ows += R + Kd + 4
+                mb1 = max(mb1, ((Kd + 255) // 256) * ((R + 63) // 64))
+                mb2 = max(mb2, (R + 7) // 8)
+            mb3 = max(mb3, (Cout * Cin * taps + 255) // 256)
+            self.slices.append((off_f, off_d, nf, (Cout_p, taps, Cin_p), (Cin_p, taps, Cout_p), su, sv))
+            off_f += (nf + 63) // 64 * 64            # keep every pack 128-byte aligned (TMA base alignment)
+            off_d += (nf + 63) // 64 * 64
+        self.total_f, self.total_d = off_f, off_d
+        self.table = torch.from_numpy(table.view(np.uint8).copy()).to(device)
+        self.max_blocks = (min(mb1, 4096), min(mb2, 1024), min(mb3, 2048))
+        self.mods = mods
+        self.device = device
+        self.params = [ops._w(m) for m in mods]
+        self.ptrs = [w.data_ptr() for w in self.params]
+
+    def run(self):
+        """Power-iterate (layers in train mode, as the reference's hooks) and pack every layer; leaves per-layer views in
+        ``module._sn_cache`` for the ops of this forward pass."""
+        W0 = next(self.net.parameters())
+        if self.mods is None or self.device != W0.device or any(w.data_ptr() != p for w, p in zip(self.params, self.ptrs)):
+            self._build(W0.device)
+        dev = self.device
+        training = self.mods[0].training
+        need_grad = torch.is_grad_enabled()
+        sigma = torch.empty(len(self.mods), device=dev, dtype=torch.float32)
+        pf = torch.zeros(self.total_f, device=dev, dtype=torch.bfloat16)
+        pd = torch.zeros(self.total_d, device=dev, dtype=torch.bfloat16) if need_grad else None
+        mb = self.max_blocks
+        L.call("sgb_sn_batch", L.ptr(self.table), len(self.mods), L.ptr(sigma), L.ptr(pf), L.ptr(pd), ops.SN_EPS,
+               1 if training else 0, mb[0], mb[1], mb[2], L.stream_ptr())
+        us = self.u_flat.clone() if need_grad else None
+        vs = self.v_flat.clone() if need_grad else None
+        for i, (m, (of, od, nf, shf, shd, su, sv)) in enumerate(zip(self.mods, self.slices)):
+            wf = pf[of:of + nf].view(shf)
+            wd = pd[od:od + nf].view(shd) if pd is not None else None
+            has_sn = su is not None
+            m._sn_cache = (wf, wd, sigma[i:i + 1] if has_sn else None,
+                           us[su[0]:su[1]] if (has_sn and us is not None) else None,
+                           vs[sv[0]:sv[1]] if (has_sn and vs is not None) else None)
+
+    def clear(self):
+        if self.mods:
+            for m in self.mods:
+                m._sn_cache = None

@@ -52,7 +52,8 @@ class _ConvBase(nn.Conv2d):
             return self._forward_image(x, residual, relu, premasked)
         cfg = {"KH": self.kernel_size[0], "KW": self.kernel_size[1], "pad": self.padding[0], "relu": relu,
                "premasked": premasked, "mask_input": mask_input, "res_up2": res_up2,
-               "sn": getattr(self, "_sn", None), "do_power_iteration": self.training}
+               "sn": getattr(self, "_sn", None), "do_power_iteration": self.training,
+               "sn_cache": getattr(self, "_sn_cache", None)}
         return A.ConvFn.apply(x, _w(self), self.bias, residual, cfg)
 
     def _forward_image(self, x_col, residual, relu, premasked):
@@ -99,7 +100,8 @@ class _LinearBase(nn.Linear):
         if bias is not None and perm_S > 1:
             bias = bias.view(-1, perm_S).t().reshape(-1)
         cfg = {"KH": 1, "KW": 1, "pad": 0, "relu": False, "out_fp32": out_fp32, "perm_S": perm_S,
-               "sn": getattr(self, "_sn", None), "do_power_iteration": self.training}
+               "sn": getattr(self, "_sn", None), "do_power_iteration": self.training,
+               "sn_cache": getattr(self, "_sn_cache", None)}
         return A.ConvFn.apply(x, _w(self), bias, None, cfg)
 
 
@@ -231,7 +233,8 @@ class SelfAttention(nn.Module):
 
     def forward(self, x):
         mods = (self.conv1x1_theta, self.conv1x1_phi, self.conv1x1_g, self.conv1x1_attn)
-        cfgs = tuple({"sn": getattr(m, "_sn", None), "do_power_iteration": m.training} for m in mods)
+        cfgs = tuple({"sn": getattr(m, "_sn", None), "do_power_iteration": m.training, "sn_cache": getattr(m, "_sn_cache", None)}
+                     for m in mods)
         return A.SelfAttentionFn.apply(x, _w(mods[0]), _w(mods[1]), _w(mods[2]), _w(mods[3]), self.sigma, cfgs)
 
 
@@ -336,6 +339,7 @@ def build_discriminator_head(D, MODULES, feat, d_cond_mtd, aux_cls_type, d_embed
         D.linear1 = MODULES.d_linear(in_features=feat, out_features=num_classes, bias=True)
     else:
         D.linear1 = MODULES.d_linear(in_features=feat, out_features=1, bias=True)
+    D.linear1._head_layer = True                  # fp32 head path (ops.head_linear), not part of the batched SN / pack pass
     if aux_cls_type == "ADC":
         num_classes = num_classes * 2
     if d_cond_mtd == "AC":
@@ -353,3 +357,6 @@ def build_discriminator_head(D, MODULES, feat, d_cond_mtd, aux_cls_type, d_embed
             D.embedding_mi = MODULES.d_embedding(num_classes, d_embed_dim)
         else:
             raise NotImplementedError
+    for name in ("linear2", "linear_mi"):
+        if hasattr(D, name):
+            getattr(D, name)._head_layer = True
