@@ -58,8 +58,12 @@ def modules(g_sn=True, d_sn=True, cbn=True):
 MODEL = types.SimpleNamespace(info_type="N/A", g_info_injection="N/A")
 
 
-def sd_np(module, prefix):
-    return {prefix + k: v.detach().cpu().numpy().copy() for k, v in module.state_dict().items()}
+def sd_np(module, prefix, buffers_only=False):
+    """state_dict as numpy; ``buffers_only`` keeps u / v / running statistics only (parameters are unchanged between the
+    G0/D0 and G1/D1 snapshots, so storing them twice would only bloat the fixtures)."""
+    params = {k for k, _ in module.named_parameters()}
+    return {prefix + k: v.detach().cpu().numpy().copy() for k, v in module.state_dict().items()
+            if not (buffers_only and k in params)}
 
 
 def golden_deep(tag, img_size, conv_dim, depth, attn, z_dim=16, shared=16, classes=5, B=3):
@@ -100,8 +104,8 @@ def golden_deep(tag, img_size, conv_dim, depth, attn, z_dim=16, shared=16, class
                 "d_loss": d_loss.detach().numpy()})
     for k, p in D.named_parameters():
         out["Dgrad/" + k] = p.grad.detach().numpy().copy()
-    out.update(sd_np(G, "G1/"))   # buffers after one forward (u, v, running stats)
-    out.update(sd_np(D, "D1/"))   # buffers after two forwards
+    out.update(sd_np(G, "G1/", True))   # buffers after one forward (u, v, running stats)
+    out.update(sd_np(D, "D1/", True))   # buffers after two forwards
 
     # ---- generator phase (src/worker.py:502-681): G forward with graph, D forward with frozen params, hinge, backward
     D.zero_grad()
@@ -151,7 +155,7 @@ def golden_resfamily(tag, family, conv_dim, attn, g_sn, d_sn, g_cond, d_cond, ad
                 "adv_fake": fake_d["adv_output"].detach().numpy(), "h_real": real_d["h"].detach().numpy(), "d_loss": d_loss.detach().numpy()})
     for k, p in D.named_parameters():
         out["Dgrad/" + k] = p.grad.detach().numpy().copy()
-    out.update(sd_np(G, "G1/")); out.update(sd_np(D, "D1/"))
+    out.update(sd_np(G, "G1/", True)); out.update(sd_np(D, "D1/", True))
     D.zero_grad()
     for p in G.parameters():
         p.requires_grad_(True)
@@ -226,7 +230,7 @@ if __name__ == "__main__":
     golden_deep("deep32_c8", 32, 8, 1, attn=False)
     golden_deep("deep32_c16_attn_d2", 32, 16, 2, attn=True, B=2)
     golden_deep("deep32_c8_b16", 32, 8, 1, attn=False, B=16)      # well-conditioned BatchNorm statistics for gradient parity
-    golden_resfamily("biggan32_c16_attn", "big_resnet", 16, True, True, True, "cBN", "PD", "hinge")
+    golden_resfamily("biggan32_c32_attn", "big_resnet", 32, True, True, True, "cBN", "PD", "hinge", B=4)
     golden_resfamily("sngan32_c16", "resnet", 16, False, False, True, "W/O", "W/O", "hinge", z_dim=32)
     golden_resfamily("resnet32_cbn_c16", "resnet", 16, False, False, True, "cBN", "PD", "hinge", z_dim=32)
     golden_resfamily("wgan32_bn_c16", "resnet", 16, False, False, False, "W/O", "W/O", "wasserstein", z_dim=32)

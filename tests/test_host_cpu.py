@@ -94,7 +94,8 @@ def test_reference_checkpoint_loads_strictly(golden_dir):
     g = np.load(os.path.join(golden_dir, "deep32_c16_attn_d2.npz"))
     G, D = _build(dict(conv_dim=16, depth=2, attn=True))
     for net, prefix in ((G, "G1/"), (D, "D1/")):
-        sd = {k[len(prefix):]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith(prefix)}
+        sd = {k[3:]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith(prefix[0] + "0/")}
+        sd.update({k[len(prefix):]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith(prefix)})
         net.load_state_dict(sd, strict=True)
 
 

@@ -14,7 +14,10 @@ CASES = [("deep32_c8", dict(img_size=32, conv_dim=8, depth=1, attn=False)),
 
 
 def load_sd(npz, prefix, grad=False):
+    """State dict ``prefix``; the G1/ and D1/ snapshots hold buffers only and take their parameters from G0/ and D0/."""
     sd = {}
+    if prefix in ("G1/", "D1/"):
+        sd = load_sd(npz, prefix[0] + "0/", grad)
     for k in npz.files:
         if k.startswith(prefix):
             t = torch.from_numpy(npz[k].copy())

@@ -10,7 +10,7 @@ from oracle import studiogan_oracle as O
 from sgb200 import config as C
 
 CASES = {
-    "biggan32_c16_attn": dict(family="big_resnet", attn=True, g_sn=True, d_sn=True, g_cond="cBN", d_cond="PD", adv="hinge", z_dim=20),
+    "biggan32_c32_attn": dict(family="big_resnet", conv_dim=32, attn=True, g_sn=True, d_sn=True, g_cond="cBN", d_cond="PD", adv="hinge", z_dim=20),
     "sngan32_c16": dict(family="resnet", attn=False, g_sn=False, d_sn=True, g_cond="W/O", d_cond="W/O", adv="hinge", z_dim=32),
     "resnet32_cbn_c16": dict(family="resnet", attn=False, g_sn=False, d_sn=True, g_cond="cBN", d_cond="PD", adv="hinge", z_dim=32),
     "wgan32_bn_c16": dict(family="resnet", attn=False, g_sn=False, d_sn=False, g_cond="W/O", d_cond="W/O", adv="wasserstein", z_dim=32),
@@ -18,7 +18,10 @@ CASES = {
 
 
 def load_sd(npz, prefix, grad=False):
+    """State dict ``prefix``; the G1/ and D1/ snapshots hold buffers only and take their parameters from G0/ and D0/."""
     sd = {}
+    if prefix in ("G1/", "D1/"):
+        sd = load_sd(npz, prefix[0] + "0/", grad)
     for k in npz.files:
         if k.startswith(prefix):
             t = torch.from_numpy(npz[k].copy())
@@ -30,12 +33,12 @@ def load_sd(npz, prefix, grad=False):
 
 def oracle_G(c, sd, z, y):
     if c["family"] == "big_resnet":
-        return O.biggan_generator(sd, z, y, 32, 16, attn_g_loc=(2,), apply_attn=c["attn"])
+        return O.biggan_generator(sd, z, y, 32, c.get("conv_dim", 16), attn_g_loc=(2,), apply_attn=c["attn"])
     return O.resnet_generator(sd, z, y, 32, 16, num_classes=5, conditional=c["g_cond"] == "cBN")
 
 
 def oracle_D(c, sd, x, y):
-    return O.res_discriminator(sd, x, y, 32, 16, attn_d_loc=(1,), apply_attn=c["attn"], cond=c["d_cond"])
+    return O.res_discriminator(sd, x, y, 32, c.get("conv_dim", 16), attn_d_loc=(1,), apply_attn=c["attn"], cond=c["d_cond"])
 
 
 @pytest.mark.parametrize("tag", list(CASES))
@@ -85,9 +88,9 @@ def build(c):
     M = C.make_modules(c["g_sn"], c["d_sn"], c["g_cond"], c["family"])
     MODEL = C._Section(info_type="N/A", g_info_injection="N/A")
     torch.manual_seed(4321)
-    G = mod.Generator(z_dim=c["z_dim"], g_shared_dim=16, img_size=32, g_conv_dim=16, apply_attn=c["attn"], attn_g_loc=[2],
+    G = mod.Generator(z_dim=c["z_dim"], g_shared_dim=16, img_size=32, g_conv_dim=c.get("conv_dim", 16), apply_attn=c["attn"], attn_g_loc=[2],
                       g_cond_mtd=c["g_cond"], num_classes=5, g_init="ortho", g_depth="N/A", mixed_precision=False, MODULES=M, MODEL=MODEL)
-    D = mod.Discriminator(img_size=32, d_conv_dim=16, apply_d_sn=c["d_sn"], apply_attn=c["attn"], attn_d_loc=[1], d_cond_mtd=c["d_cond"],
+    D = mod.Discriminator(img_size=32, d_conv_dim=c.get("conv_dim", 16), apply_d_sn=c["d_sn"], apply_attn=c["attn"], attn_d_loc=[1], d_cond_mtd=c["d_cond"],
                           aux_cls_type="W/O", d_embed_dim="N/A", normalize_d_embed=False, num_classes=5, d_init="ortho", d_depth="N/A",
                           mixed_precision=False, MODULES=M, MODEL=MODEL)
     return G, D
