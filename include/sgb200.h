@@ -65,6 +65,12 @@ typedef struct sgb_conv_desc {
   void* y;             /* output, bf16 (or fp32 if y_fp32) */
   int64_t y_cstride;
   int32_t y_fp32;
+  /* Generalisations used by the InceptionV3 feature extractor (src/metrics/inception_net.py); 0 = plain same-size conv.
+   * Hin/Win: input spatial size when it differs from the output grid H x W ("valid" convolutions: H = Hin - KH + 1 + 2 pad).
+   * out_sub = 2: only the even (h, w) positions of the H x W grid are stored, at (h/2, w/2) of a ceil(H/2) x ceil(W/2)
+   * tensor, i.e. a stride-2 convolution computed on the stride-1 grid (four layers of the network). */
+  int32_t Hin, Win;
+  int32_t out_sub;
 } sgb_conv_desc;
 
 int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream);
@@ -186,6 +192,17 @@ int sgb_img_grad_to_nhwc(const float* dimg, const float* y, void* out, int32_t B
  * the 3 -> C input convolution (input_conv, src/models/big_resnet_deep_legacy.py:259) becomes a K = 32 GEMM. */
 int sgb_col27(const void* src, int32_t src_nchw_f32, int64_t cs, void* out, int32_t B, int32_t H, int32_t W, sgb_stream_t stream);
 int sgb_col27_bwd(const void* dcol, float* dimg, int32_t B, int32_t H, int32_t W, sgb_stream_t stream);
+/* Inception pooling: 3x3, stride 1|2, pad 0|1; mode 0 = average with count_include_pad=False, 1 = max
+ * (src/metrics/inception_net.py:86,91,153,178,208,241). */
+int sgb_pool3x3(const void* x, int64_t xs, void* y, int64_t ys, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride,
+                int32_t pad, int32_t mode, sgb_stream_t stream);
+/* uint8 quantisation of generated images, bit-exact with ops.quantize_images (src/utils/ops.py:251-255). */
+int sgb_quantize_u8(const float* img, uint8_t* out, int64_t n, sgb_stream_t stream);
+/* Fused evaluation pre-processing on the device (quantise -> "legacy" bilinear resize to SxS -> /255 -> (x-0.5)/0.5;
+ * src/utils/ops.py:251-263, src/utils/resize.py:83-91, src/metrics/preparation.py:103-122).  img: NCHW fp32 [B,3,H,W].
+ * out_img (optional): NCHW fp32 [B,3,S,S]; out_col (optional): [B,So,So,32] bf16 stride-2 valid 3x3 patches, So=(S-3)/2+1. */
+int sgb_quantize_resize_normalize(const float* img, int32_t quantize, int32_t B, int32_t H, int32_t W, int32_t S, float* out_img,
+                                  void* out_col, sgb_stream_t stream);
 int sgb_cast_f32_to_bf16(const float* in, void* out, int64_t n, float scale, sgb_stream_t stream);
 int sgb_cast_bf16_to_f32(const void* in, float* out, int64_t n, sgb_stream_t stream);
 

@@ -391,6 +391,111 @@ __global__ void __launch_bounds__(256) col27_bwd_kernel(const bf16* __restrict__
   }
 }
 
+// 3x3 pooling of the Inception feature extractor (src/metrics/inception_net.py:81-107,135-249): max (stride 2, no padding:
+// nn.MaxPool2d(3, 2); stride 1, padding 1 in FIDInceptionE_2) or average with count_include_pad=False (stride 1, padding 1).
+__global__ void __launch_bounds__(256) pool3x3_kernel(const bf16* __restrict__ x, long long xs, bf16* __restrict__ y, long long ys,
+                                                       int B, int H, int W, int Ho, int Wo, int C, int stride, int pad, int mode) {
+  const int VG = C >> 3;
+  const long long total = (long long)B * Ho * Wo * VG;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int g = (int)(i % VG);
+    const long long p = i / VG;
+    const int wo = (int)(p % Wo), ho = (int)((p / Wo) % Ho), b = (int)(p / ((long long)Wo * Ho));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = mode == 1 ? -INFINITY : 0.f;
+    int cnt = 0;
+    for (int kh = 0; kh < 3; ++kh) {
+      const int h = ho * stride + kh - pad;
+      if (h < 0 || h >= H) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int w = wo * stride + kw - pad;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((long long)b * H + h) * W + w) * xs) + g), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = mode == 1 ? fmaxf(acc[j], f[j]) : acc[j] + f[j];
+        ++cnt;
+      }
+    }
+    if (mode == 0) {
+      const float inv = 1.f / (float)cnt;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    }
+    reinterpret_cast<uint4*>(y + p * ys)[g] = pack8(acc);
+  }
+}
+
+// Fused evaluation pre-processing (src/utils/ops.py:251-263 + src/utils/resize.py:83-91 "legacy" + InceptionV3_tf mean/std):
+// float image in [-1,1] -> uint8 quantisation ((255*(x+1)/2 + 0.5) clamped, truncated) -> bilinear resize to S x S
+// (align_corners = False, on the uint8 values, clipped to [0,255]) -> x/255 -> (x - 0.5)/0.5, all on the device; the
+// reference does this on the host with a Python loop per image and two PCIe crossings.
+// Output: the 3x3 / stride-2 / valid patches of the resized image, [B, So, So, 32] bf16 (So = (S-3)/2+1), i.e. the operand
+// of Inception's first convolution as a K = 32 GEMM; also (optionally) the quantised uint8 image for bit-exact checks.
+__device__ __forceinline__ float quant_u8(float x) {
+  float q = 255.0f * ((x + 1.0f) / 2.0f) + 0.5f;
+  q = fminf(fmaxf(q, 0.0f), 255.0f);
+  return floorf(q);     // astype(np.uint8) truncates; q >= 0
+}
+__global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__ img, uint8_t* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+    out[i] = (uint8_t)quant_u8(__ldg(img + i));
+}
+__device__ __forceinline__ float resized_pixel(const float* __restrict__ img, int quantize, int H, int W, int S, int oh, int ow,
+                                               float scale_h, float scale_w) {
+  // torch upsample_bilinear2d, align_corners=False: src = max(scale*(dst+0.5)-0.5, 0)
+  const float sh = fmaxf(scale_h * (oh + 0.5f) - 0.5f, 0.f), sw = fmaxf(scale_w * (ow + 0.5f) - 0.5f, 0.f);
+  const int h0 = (int)sh, w0 = (int)sw;
+  const int h1 = h0 + (h0 < H - 1 ? 1 : 0), w1 = w0 + (w0 < W - 1 ? 1 : 0);
+  const float lh = sh - h0, lw = sw - w0;
+  float v00 = __ldg(img + (long long)h0 * W + w0), v01 = __ldg(img + (long long)h0 * W + w1);
+  float v10 = __ldg(img + (long long)h1 * W + w0), v11 = __ldg(img + (long long)h1 * W + w1);
+  if (quantize) { v00 = quant_u8(v00); v01 = quant_u8(v01); v10 = quant_u8(v10); v11 = quant_u8(v11); }
+  const float r = (1.f - lh) * ((1.f - lw) * v00 + lw * v01) + lh * ((1.f - lw) * v10 + lw * v11);
+  return fminf(fmaxf(r, 0.f), 255.f);
+}
+// mode 0: write the normalised resized image as NCHW fp32 [B,3,S,S] (API parity / tests);
+// mode 1: write the stride-2 valid 3x3 patch tensor [B,So,So,32] bf16 of the normalised resized image.
+__global__ void __launch_bounds__(256) resize_norm_kernel(const float* __restrict__ img, int quantize, int B, int H, int W, int S,
+                                                           float* __restrict__ out_img, bf16* __restrict__ out_col, int So) {
+  const float scale_h = (float)H / (float)S, scale_w = (float)W / (float)S;
+  if (out_img) {
+    const long long total = (long long)B * 3 * S * S;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+      const int ow = (int)(i % S), oh = (int)((i / S) % S);
+      const long long bc = i / ((long long)S * S);
+      const float r = resized_pixel(img + bc * H * W, quantize, H, W, S, oh, ow, scale_h, scale_w);
+      out_img[i] = (r / 255.0f - 0.5f) / 0.5f;
+    }
+  }
+  if (out_col) {
+    const long long total = (long long)B * So * So;
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < total; p += (long long)gridDim.x * 256) {
+      const int wo = (int)(p % So), ho = (int)((p / So) % So), b = (int)(p / ((long long)So * So));
+      float v[32];
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float r = resized_pixel(img + ((long long)b * 3 + c) * H * W, quantize, H, W, S, 2 * ho + t / 3, 2 * wo + t % 3,
+                                        scale_h, scale_w);
+          v[t * 3 + c] = (r / 255.0f - 0.5f) / 0.5f;
+        }
+#pragma unroll
+      for (int k = 27; k < 32; ++k) v[k] = 0.f;
+      uint4* op = reinterpret_cast<uint4*>(out_col + p * 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack2(v[8 * j + 0], v[8 * j + 1]); o.y = pack2(v[8 * j + 2], v[8 * j + 3]);
+        o.z = pack2(v[8 * j + 4], v[8 * j + 5]); o.w = pack2(v[8 * j + 6], v[8 * j + 7]);
+        op[j] = o;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n,
                                                              float scale) {
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
@@ -563,6 +668,37 @@ extern "C" int sgb_col27_bwd(const void* dcol, float* dimg, int32_t B, int32_t H
   cudaStream_t stream = (cudaStream_t)stream_;
   SGB_REQUIRE(dcol && dimg && B > 0 && H > 0 && W > 0);
   col27_bwd_kernel<<<ew_blocks((long long)B * H * W), 256, 0, stream>>>((const bf16*)dcol, dimg, B, H, W);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_pool3x3(const void* x, int64_t xs, void* y, int64_t ys, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride,
+                           int32_t pad, int32_t mode, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(x && y && B > 0 && H >= 3 && W >= 3 && C > 0 && C % 8 == 0 && xs % 8 == 0 && ys % 8 == 0);
+  SGB_REQUIRE((stride == 1 || stride == 2) && (pad == 0 || pad == 1) && (mode == 0 || mode == 1));
+  const int Ho = (H + 2 * pad - 3) / stride + 1, Wo = (W + 2 * pad - 3) / stride + 1;
+  pool3x3_kernel<<<ew_blocks((long long)B * Ho * Wo * (C / 8)), 256, 0, stream>>>((const bf16*)x, xs, (bf16*)y, ys, B, H, W, Ho, Wo, C,
+                                                                                 stride, pad, mode);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_quantize_u8(const float* img, uint8_t* out, int64_t n, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(img && out && n > 0);
+  quantize_kernel<<<ew_blocks(n), 256, 0, stream>>>(img, out, n);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_quantize_resize_normalize(const float* img, int32_t quantize, int32_t B, int32_t H, int32_t W, int32_t S,
+                                             float* out_img, void* out_col, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(img && (out_img || out_col) && B > 0 && H > 0 && W > 0 && S >= 3);
+  const int So = (S - 3) / 2 + 1;
+  const long long work = out_img ? (long long)B * 3 * S * S : (long long)B * So * So;
+  resize_norm_kernel<<<ew_blocks(work), 256, 0, stream>>>(img, quantize, B, H, W, S, out_img, (bf16*)out_col, So);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }

@@ -34,6 +34,7 @@ struct FpropArgs {
   int stages;
   int use_tma;                    // epilogue through staging tiles + TMA tensor stores
   int aux_kind, aux_tw, aux_th;   // residual (1) / mask (2) tile staged by TMA; its box is aux_tw x aux_th x nb pixels
+  int out_sub;                    // 2: store only even (h, w) outputs at (h/2, w/2) -> stride-2 convolution (Inception reduction blocks)
   uint32_t tmem_cols;
   EpiArgs e;
 };
@@ -174,8 +175,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int bt = t;
       const int n0 = nt * p.BN;
       const int w = wt * p.tw + wi, h = ht * p.th + hi, b = bt * p.nb + bi;
-      const bool valid = (w < p.W) && (h < p.H) && (b < p.B);
-      const long long pix = ((long long)b * p.H + h) * p.W + w;
+      const bool valid = (w < p.W) && (h < p.H) && (b < p.B) && (p.out_sub == 1 || (((w | h) & 1) == 0));
+      const long long pix = p.out_sub == 1 ? ((long long)b * p.H + h) * p.W + w
+                                           : ((long long)b * ((p.H + 1) >> 1) + (h >> 1)) * ((p.W + 1) >> 1) + (w >> 1);
       const long long rpix = p.e.res_up2 ? (((long long)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) : pix;
 
       const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
@@ -432,7 +434,7 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
     // wide, few-channel 3x3 layers: halo-row kernel (umma_conv3x3.cu).  SGB_CONV3X3_ROWS=0 forces the generic kernel.
     static const int use_rows = env_int("SGB_CONV3X3_ROWS", 1);
     static const int bo_mode = env_int("SGB_ROWS_BASE_OFFSET", 0);
-    if (use_rows && conv3x3_rows_eligible(d)) return launch_conv3x3_rows(d, stream, bo_mode, env_int("SGB_EPI_TMA", 1));
+    if (use_rows && d->Hin <= 0 && d->Win <= 0 && d->out_sub != 2 && conv3x3_rows_eligible(d)) return launch_conv3x3_rows(d, stream, bo_mode, env_int("SGB_EPI_TMA", 1));
   }
   SGB_REQUIRE(((uintptr_t)d->bias & 15) == 0 && ((uintptr_t)d->residual & 15) == 0 && ((uintptr_t)d->mask & 15) == 0);
 
@@ -460,7 +462,10 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   p.tiles_n = (d->Cout + BN - 1) / BN;
   p.num_tiles = p.tiles_n * p.tiles_w * p.tiles_h * p.tiles_b;
   p.kblocks = (d->Cin + kBlockK - 1) / kBlockK;
-  p.use_tma = (!d->y_fp32 && BN % 64 == 0 && d->Cout % 8 == 0 && d->y_cstride % 8 == 0 &&
+  const int Hin = d->Hin > 0 ? d->Hin : d->H, Win = d->Win > 0 ? d->Win : d->W;
+  p.out_sub = d->out_sub == 2 ? 2 : 1;
+  SGB_REQUIRE(p.out_sub == 1 || (!d->residual && !d->mask));
+  p.use_tma = (p.out_sub == 1 && !d->y_fp32 && BN % 64 == 0 && d->Cout % 8 == 0 && d->y_cstride % 8 == 0 &&
                (!d->residual || d->res_cstride % 8 == 0) && (!d->mask || d->mask_cstride % 8 == 0) &&
                p.taps * d->Cin <= env_int("SGB_EPI_TMA_MAXK", 640) && env_int("SGB_EPI_TMA", 1)) ? 1 : 0;   // output-heavy layers only
   // auxiliary epilogue operand through TMA: exactly one of residual / mask, bf16 NHWC with 16-byte aligned channel stride
@@ -479,7 +484,7 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   fill_epi(p.e, d);
 
   CUtensorMap tmA, tmB;
-  int rc = make_act_tmap(&tmA, d->x, d->B, d->H, d->W, d->Cin, d->x_cstride, p.tw, p.th, p.nb);
+  int rc = make_act_tmap(&tmA, d->x, d->B, Hin, Win, d->Cin, d->x_cstride, p.tw, p.th, p.nb);
   if (rc) return rc;
   if (d->w_mode == 0) {
     uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)p.taps, (uint64_t)d->Cout};

@@ -33,6 +33,7 @@ class ConvDesc(ctypes.Structure):
         ("mask", c_p), ("mask_cstride", c_i64),
         ("relu", c_int),
         ("y", c_p), ("y_cstride", c_i64), ("y_fp32", c_int),
+        ("Hin", c_int), ("Win", c_int), ("out_sub", c_int),
     ]
 
 
@@ -82,6 +83,9 @@ SIGNATURES = {
     "sgb_img_grad_to_nhwc": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p]),
     "sgb_col27": (c_int, [c_p, c_int, c_i64, c_p, c_int, c_int, c_int, c_p]),
     "sgb_col27_bwd": (c_int, [c_p, c_p, c_int, c_int, c_int, c_p]),
+    "sgb_pool3x3": (c_int, [c_p, c_i64, c_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "sgb_quantize_u8": (c_int, [c_p, c_p, c_i64, c_p]),
+    "sgb_quantize_resize_normalize": (c_int, [c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p]),
     "sgb_cast_f32_to_bf16": (c_int, [c_p, c_p, c_i64, c_f, c_p]),
     "sgb_cast_bf16_to_f32": (c_int, [c_p, c_p, c_i64, c_p]),
     "sgb_adam_ema_step": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_f, c_f, c_f, c_f, c_int, c_p, c_f, c_f, c_p]),
