@@ -462,3 +462,70 @@ def res_discriminator(sd, x, label, img_size, d_conv_dim, attn_d_loc=(), apply_a
             bi += 1
     h = torch.sum(F.relu(h), dim=[2, 3])
     return disc_head_pd(sd, h, label, training, cond), h
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# FID InceptionV3  (src/metrics/inception_net.py:16-249) on top of torchvision's module definitions (the reference builds
+# on torchvision.models.inception_v3 too, :117) with the TF-compatible pooling of FIDInceptionA/C/E_1/E_2 restated here.
+# ---------------------------------------------------------------------------------------------------------------------
+def _fid_a(m, x):
+    b1 = m.branch1x1(x)
+    b5 = m.branch5x5_2(m.branch5x5_1(x))
+    d = m.branch3x3dbl_3(m.branch3x3dbl_2(m.branch3x3dbl_1(x)))
+    bp = m.branch_pool(F.avg_pool2d(x, kernel_size=3, stride=1, padding=1, count_include_pad=False))
+    return torch.cat([b1, b5, d, bp], 1)
+
+
+def _fid_c(m, x):
+    b1 = m.branch1x1(x)
+    s = m.branch7x7_3(m.branch7x7_2(m.branch7x7_1(x)))
+    d = m.branch7x7dbl_5(m.branch7x7dbl_4(m.branch7x7dbl_3(m.branch7x7dbl_2(m.branch7x7dbl_1(x)))))
+    bp = m.branch_pool(F.avg_pool2d(x, kernel_size=3, stride=1, padding=1, count_include_pad=False))
+    return torch.cat([b1, s, d, bp], 1)
+
+
+def _fid_e(m, x, use_max):
+    b1 = m.branch1x1(x)
+    t = m.branch3x3_1(x)
+    b3 = torch.cat([m.branch3x3_2a(t), m.branch3x3_2b(t)], 1)
+    t = m.branch3x3dbl_2(m.branch3x3dbl_1(x))
+    d = torch.cat([m.branch3x3dbl_3a(t), m.branch3x3dbl_3b(t)], 1)
+    pooled = F.max_pool2d(x, kernel_size=3, stride=1, padding=1) if use_max else \
+        F.avg_pool2d(x, kernel_size=3, stride=1, padding=1, count_include_pad=False)
+    return torch.cat([b1, b3, d, m.branch_pool(pooled)], 1)
+
+
+def fid_inception(state_dict):
+    """torchvision Inception3(1008 classes, no aux) in eval mode carrying ``state_dict`` (torchvision key layout)."""
+    import torchvision
+    net = torchvision.models.inception_v3(num_classes=1008, aux_logits=False, weights=None, init_weights=False)
+    net.load_state_dict(state_dict)
+    return net.eval()
+
+
+@torch.no_grad()
+def fid_inception_forward(net, x):
+    """InceptionV3.forward (src/metrics/inception_net.py:81-107) with resize_input=False, normalize_input=False:
+    x is the normalised 299x299 batch; returns (pool [B,2048], logits [B,1008])."""
+    x = net.Conv2d_2b_3x3(net.Conv2d_2a_3x3(net.Conv2d_1a_3x3(x)))
+    x = F.max_pool2d(x, kernel_size=3, stride=2)
+    x = net.Conv2d_4a_3x3(net.Conv2d_3b_1x1(x))
+    x = F.max_pool2d(x, kernel_size=3, stride=2)
+    x = _fid_a(net.Mixed_5b, x)
+    x = _fid_a(net.Mixed_5c, x)
+    x = _fid_a(net.Mixed_5d, x)
+    x = net.Mixed_6a(x)
+    for name in ("Mixed_6b", "Mixed_6c", "Mixed_6d", "Mixed_6e"):
+        x = _fid_c(getattr(net, name), x)
+    x = net.Mixed_7a(x)
+    x = _fid_e(net.Mixed_7b, x, False)
+    x = _fid_e(net.Mixed_7c, x, True)
+    x = torch.flatten(F.adaptive_avg_pool2d(x, (1, 1)), 1)
+    return x, net.fc(x)
+
+
+def eval_preprocess(images, size=299, quantize=True):
+    """LoadEvalModel.get_outputs pre-processing for InceptionV3_tf with the default 'legacy' resizer
+    (src/metrics/preparation.py:103-108, src/utils/ops.py:251-263): returns the normalised [B,3,size,size] batch."""
+    q = quantize_images(images) if quantize else images.detach().cpu().numpy().astype(np.uint8)
+    return normalize_for_inception(resize_legacy(q, size))

@@ -55,14 +55,20 @@ def _s():
 
 # ---------------------------------------------------------------------------------------------- conv engine
 def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_up2=False, res_after_mask=False,
-               mask=None, relu=False, alpha=1.0, alpha_ptr=None, out=None, out_fp32=False, w_mode=0):
-    """y = epilogue(conv(x, w)); see sgb_conv_fprop. ``w`` is a packed bf16 weight (layout by w_mode)."""
-    B, Cin, H, W, xcs = geom(x)
+               mask=None, relu=False, alpha=1.0, alpha_ptr=None, out=None, out_fp32=False, w_mode=0, same_size=True, stride=1):
+    """y = epilogue(conv(x, w)); see sgb_conv_fprop. ``w`` is a packed bf16 weight (layout by w_mode).
+    same_size=False: output grid = Hin + 2*pad - K + 1 ("valid"-style); stride=2 stores its even positions only."""
+    B, Cin, Hin, Win, xcs = geom(x)
+    H, W = (Hin, Win) if same_size else (Hin + 2 * pad_h - KH + 1, Win + 2 * pad_w - KW + 1)
+    Ho, Wo = ((H + 1) // 2, (W + 1) // 2) if stride == 2 else (H, W)
     if out is None:
-        out = empty_nhwc(B, Cout, H, W, x.device, torch.float32 if out_fp32 else bf16)
+        out = empty_nhwc(B, Cout, Ho, Wo, x.device, torch.float32 if out_fp32 else bf16)
     _, _, _, _, ycs = geom(out)
     d = L.ConvDesc()
     d.B, d.H, d.W, d.Cin, d.Cout = B, H, W, Cin, Cout
+    if not same_size:
+        d.Hin, d.Win = Hin, Win
+    d.out_sub = 2 if stride == 2 else 0
     d.KH, d.KW, d.pad_h, d.pad_w = KH, KW, pad_h, pad_w
     d.x, d.x_cstride = x.data_ptr(), xcs
     d.w, d.w_mode = w.data_ptr(), w_mode
@@ -293,6 +299,35 @@ def col27_bwd(dcol):
     dimg = torch.empty((B, 3, H, W), device=dcol.device, dtype=torch.float32)
     L.call("sgb_col27_bwd", L.ptr(dcol), L.ptr(dimg), B, H, W, _s())
     return dimg
+
+
+def pool3x3(x, stride, pad, mode, out=None):
+    """Inception 3x3 pooling; mode 0 = average (count_include_pad=False), 1 = max."""
+    B, C, H, W, xs = geom(x)
+    Ho, Wo = (H + 2 * pad - 3) // stride + 1, (W + 2 * pad - 3) // stride + 1
+    if out is None:
+        out = empty_nhwc(B, C, Ho, Wo, x.device)
+    L.call("sgb_pool3x3", L.ptr(x), xs, L.ptr(out), geom(out)[4], B, H, W, C, stride, pad, mode, _s())
+    return out
+
+
+def quantize_u8(img):
+    img = img.contiguous()
+    out = torch.empty(img.shape, device=img.device, dtype=torch.uint8)
+    L.call("sgb_quantize_u8", L.ptr(img), L.ptr(out), img.numel(), _s())
+    return out
+
+
+def quantize_resize_normalize(img, S=299, quantize=True, want_image=False, want_col=True):
+    """Fused eval pre-processing; returns (normalised resized image NCHW fp32 | None, stride-2 3x3 patch tensor | None)."""
+    B, C, H, W = img.shape
+    assert C == 3
+    img = img.contiguous()
+    So = (S - 3) // 2 + 1
+    out_img = torch.empty((B, 3, S, S), device=img.device, dtype=torch.float32) if want_image else None
+    out_col = empty_nhwc(B, 32, So, So, img.device) if want_col else None
+    L.call("sgb_quantize_resize_normalize", L.ptr(img), 1 if quantize else 0, B, H, W, S, L.ptr(out_img), L.ptr(out_col), _s())
+    return out_img, out_col
 
 
 def cast_f32_to_bf16(x, scale=1.0, out=None):

@@ -26,6 +26,8 @@ class WORKER(object):
         self.mu, self.sigma, self.real_feats = mu, sigma, real_feats
         self.logger = logger
         self.best_step, self.best_fid, self.best_ckpt_path = best_step, best_fid, best_ckpt_path
+        self.num_eval = num_eval
+        self.last_metrics = None
         self.DATA, self.MODEL, self.LOSS, self.OPTIMIZATION, self.RUN = cfgs.DATA, cfgs.MODEL, cfgs.LOSS, cfgs.OPTIMIZATION, cfgs.RUN
         self.DDP = self.RUN.distributed_data_parallel
         self.train_iter = iter(train_dataloader) if train_dataloader is not None else None
@@ -105,3 +107,47 @@ class WORKER(object):
             if self.MODEL.apply_g_ema:
                 self.ema.update(current_step)
         return gen_acml_loss
+
+
+# ------------------------------------------------------------------------------------------------------ evaluation
+def _evaluate(self, step, metrics, writing=True, training=False):
+    """WORKER.evaluate (reference src/worker.py:805-935): generated images -> device pre-processing -> Inception
+    features -> IS / FID / PRDC, with the reference's mode choreography (make_GAN_untrainable keeps the spectral-norm
+    power iteration running, BN uses running statistics) and best-FID bookkeeping.  Results are also kept in
+    ``self.last_metrics``.  wandb / npy dumps are outside the hot-path scope."""
+    from .metrics import features, fid, ins, prdc
+    is_best, num_splits, nearest_k = False, 1, 5
+    is_acc = "ImageNet" in self.DATA.name and "Tiny" not in self.DATA.name
+    num_eval = self.num_eval if isinstance(self.num_eval, int) else self.num_eval[getattr(self.RUN, "ref_dataset", "train")]
+    metric_dict = {}
+    with torch.no_grad():
+        misc.make_GAN_untrainable(self.Gen, self.Gen_ema, self.Dis)
+        generator = self.Gen_ema if (self.MODEL.apply_g_ema and self.Gen_ema is not None) else self.Gen
+        fake_feats, fake_probs, fake_labels = features.generate_images_and_stack_features(
+            generator=generator, discriminator=self.Dis, eval_model=self.eval_model, num_generate=num_eval,
+            y_sampler="totally_random", batch_size=self.OPTIMIZATION.batch_size, z_prior=self.MODEL.z_prior,
+            truncation_factor=self.RUN.truncation_factor, z_dim=self.MODEL.z_dim, num_classes=self.DATA.num_classes, LOSS=self.LOSS,
+            RUN=self.RUN, MODEL=self.MODEL, quantize=True, world_size=getattr(self.OPTIMIZATION, "world_size", 1), DDP=self.DDP,
+            device=self.local_rank, logger=self.logger)
+        if "is" in metrics:
+            kl_score, kl_std, top1, top5 = ins.eval_features(probs=fake_probs, labels=fake_labels, data_loader=self.eval_dataloader,
+                                                             num_features=num_eval, split=num_splits, is_acc=is_acc)
+            metric_dict.update({"IS": float(kl_score), "Top1_acc": top1, "Top5_acc": top5})
+        if "fid" in metrics:
+            fid_score, m1, c1 = fid.calculate_fid(fake_feats, self.mu, self.sigma, num_eval)
+            if self.best_fid is None or fid_score <= self.best_fid:
+                self.best_fid, self.best_step, is_best = fid_score, step, True
+            metric_dict.update({"FID": fid_score})
+        if "prdc" in metrics:
+            pr = prdc.compute_prdc(real_features=torch.as_tensor(self.real_feats, dtype=torch.float64, device=fake_feats.device),
+                                   fake_features=fake_feats[:num_eval].to(torch.float64), nearest_k=nearest_k)
+            metric_dict.update({"Improved_Precision": pr["precision"], "Improved_Recall": pr["recall"], "Density": pr["density"],
+                                "Coverage": pr["coverage"]})
+    self.last_metrics = metric_dict
+    if self.global_rank == 0 and self.logger is not None:
+        self.logger.info("evaluation (step {}): {}".format(step, metric_dict))
+    misc.make_GAN_trainable(self.Gen, self.Gen_ema, self.Dis)
+    return is_best
+
+
+WORKER.evaluate = _evaluate

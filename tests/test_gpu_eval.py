@@ -1,0 +1,150 @@
+"""GPU tests of the evaluation path: device pre-processing, Inception conv pipeline on the
+tcgen05 engine, and IS / FID / PRDC computed from its features, against the oracle and the reference goldens."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import studiogan_oracle as O  # noqa: E402
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def l2_err(got, ref):
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    return float((got - ref).norm() / (ref.norm() + 1e-30))
+
+
+def test_quantize_is_bit_exact_and_resize_matches_legacy(golden_dir):
+    from sgb200 import kernels as K
+    dev = _cuda()
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    x = torch.from_numpy(g["q_in"]).to(dev)
+    assert np.array_equal(K.quantize_u8(x).cpu().numpy(), g["q_out"])                     # integer path: bit exact
+    torch.manual_seed(0)
+    img = torch.rand(3, 3, 40, 56) * 2.4 - 1.2
+    ref = O.eval_preprocess(img, 299, True)
+    got, col = K.quantize_resize_normalize(img.to(dev), 299, quantize=True, want_image=True, want_col=True)
+    assert float((got.cpu() - ref).abs().max()) < 5e-5                                    # fp32 bilinear weights
+    # the patch tensor is the stride-2 valid 3x3 unfold of the same image (bf16)
+    unf = F.unfold(ref, kernel_size=3, stride=2).view(3, 3, 9, 149, 149).permute(0, 3, 4, 2, 1).reshape(3, 149, 149, 27)
+    colc = col.permute(0, 2, 3, 1).float().cpu()
+    assert float((colc[..., :27] - unf.bfloat16().float()).abs().max()) < 1e-2 and float(colc[..., 27:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("stride,pad,mode", [(2, 0, 1), (1, 1, 0), (1, 1, 1)])
+def test_pool3x3_modes(stride, pad, mode):
+    from sgb200 import kernels as K
+    dev = _cuda()
+    x = torch.randn(2, 16, 17, 17).bfloat16().float()
+    xd = x.to(dev).bfloat16().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    ref = F.max_pool2d(x, 3, stride, pad) if mode == 1 else F.avg_pool2d(x, 3, stride, pad, count_include_pad=False)
+    got = K.pool3x3(xd, stride, pad, mode)
+    assert got.shape == ref.shape and float((got.float().cpu() - ref).abs().max()) < 2e-2
+
+
+@pytest.mark.parametrize("Cin,Cout,KH,KW,ph,pw,stride,same,H", [(32, 32, 3, 3, 0, 0, 1, False, 21), (64, 96, 3, 3, 0, 0, 2, False, 35),
+                                                                 (128, 128, 1, 7, 0, 3, 1, True, 17), (48, 64, 5, 5, 2, 2, 1, True, 35),
+                                                                 (80, 192, 3, 3, 0, 0, 1, False, 73)])
+def test_inception_conv_shapes(Cin, Cout, KH, KW, ph, pw, stride, same, H):
+    from sgb200 import kernels as K
+    dev = _cuda()
+    g = torch.Generator().manual_seed(1)
+    x = (torch.randn(2, Cin, H, H, generator=g)).bfloat16().float()
+    w = (torch.randn(Cout, Cin, KH, KW, generator=g) * (2.0 / (Cin * KH * KW)) ** 0.5).bfloat16().float()
+    b = torch.randn(Cout, generator=g)
+    ref = F.relu(F.conv2d(x, w, b, stride=stride, padding=(ph, pw)))
+    xd = x.to(dev).bfloat16().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    wf, _ = K.weight_pack(w.to(dev), None, Cout, Cin, KH * KW, True, False)
+    got = K.conv_fprop(xd, wf, Cout, KH, KW, ph, pw, bias=b.to(dev), relu=True, same_size=same, stride=stride)
+    assert got.shape == ref.shape
+    assert float((got.float().cpu() - ref).abs().max()) < 1e-2 * (1 + float(ref.abs().max()))
+
+
+def test_inception_features_vs_reference_golden(golden_dir):
+    """Product InceptionV3 (bf16 conv pipeline, folded BN) vs the reference's LoadEvalModel.get_outputs on the same seeded
+    weights and inputs.  Tolerance: relative L2 <= 3e-2 on the 2048-d pool features and on the 1008 logits."""
+    from sgb200.metrics.preparation import LoadEvalModel
+    dev = _cuda()
+    g = np.load(os.path.join(golden_dir, "inception_seed0.npz"))
+    ev = LoadEvalModel("InceptionV3_tf", "legacy", 1, False, dev)
+    pool, logits = ev.get_outputs(torch.from_numpy(g["x"]).to(dev), quantize=True)
+    assert pool.shape == (2, 2048) and logits.shape == (2, 1008)
+    assert l2_err(pool, torch.from_numpy(g["pool"])) < 3e-2
+    assert l2_err(logits, torch.from_numpy(g["logits"])) < 3e-2
+
+
+def test_fid_is_prdc_from_cuda_features_vs_oracle_features():
+    """FID / IS / PRDC of 192 structured images: CUDA Inception features vs the fp32 oracle features (same seeded weights).
+    Stated tolerance (north_star): FID and IS within +-0.5 %; PRDC counts within 0.03 absolute at this tiny N."""
+    from sgb200.metrics import fid, ins, prdc
+    from sgb200.metrics.inception_net import InceptionV3, seeded_state_dict
+    dev = _cuda()
+    sd = seeded_state_dict(0)
+    net = InceptionV3(sd, dev)
+    onet = O.fid_inception(sd)
+    g = torch.Generator().manual_seed(5)
+
+    def images(n, shift):
+        base = F.interpolate(torch.randn(n, 3, 8, 8, generator=g), size=(48, 48), mode="bilinear", align_corners=False)
+        return torch.tanh(base * 1.5 + shift)
+    real, fake = images(192, 0.0), images(192, 0.25)
+    feats, probs = {}, {}
+    for name, imgs in (("real", real), ("fake", fake)):
+        p, l = net.forward(imgs.to(dev), quantize=True)
+        po, lo = O.fid_inception_forward(onet, O.eval_preprocess(imgs, 299, True))
+        feats[name] = (p.cpu().double(), po.double())
+        probs[name] = (torch.softmax(l, 1).cpu(), torch.softmax(lo, 1))
+    out = []
+    for k in (0, 1):
+        m1, s1 = fid.calculate_moments(feats["fake"][k])
+        m2, s2 = fid.calculate_moments(feats["real"][k])
+        out.append((fid.frechet_distance_device(m1, s1, m2, s2), float(ins.calculate_kl_div(probs["fake"][k], 1)[0]),
+                    prdc.compute_prdc(feats["real"][k], feats["fake"][k], 5)))
+    (fid_c, is_c, pr_c), (fid_o, is_o, pr_o) = out
+    print("FID cuda/oracle", fid_c, fid_o, "IS", is_c, is_o, "PRDC", pr_c, pr_o)
+    assert abs(fid_c - fid_o) <= 5e-3 * abs(fid_o)
+    assert abs(is_c - is_o) <= 5e-3 * abs(is_o)
+    for key in pr_o:
+        assert abs(pr_c[key] - pr_o[key]) <= 0.03, key
+
+
+def test_worker_evaluate_runs_end_to_end():
+    """WORKER.evaluate on a small BigGAN-Deep: generator (EMA off) -> device pre-processing -> Inception -> IS/FID/PRDC."""
+    from sgb200 import config as C
+    from sgb200.metrics import fid
+    from sgb200.metrics.preparation import LoadEvalModel
+    from sgb200.models import model as M
+    from sgb200.worker import WORKER
+    dev = _cuda()
+    cfgs = C.Configurations(None)
+    cfgs.DATA.img_size, cfgs.DATA.num_classes = 32, 10
+    m = cfgs.MODEL
+    m.backbone, m.g_cond_mtd, m.d_cond_mtd, m.apply_g_sn, m.apply_d_sn = "big_resnet_deep_legacy", "cBN", "PD", True, True
+    m.z_dim, m.g_shared_dim, m.g_conv_dim, m.d_conv_dim, m.g_depth, m.d_depth = 32, 32, 16, 16, 1, 1
+    cfgs.LOSS.adv_loss = "hinge"
+    cfgs.OPTIMIZATION.batch_size = 32
+    cfgs.define_modules()
+    cfgs.define_losses()
+    torch.manual_seed(0)
+    Gen, _, _, Dis, _, _, _, _ = M.load_generator_discriminator(cfgs.DATA, cfgs.OPTIMIZATION, cfgs.MODEL, cfgs.STYLEGAN, cfgs.MODULES,
+                                                                 cfgs.RUN, dev, None)
+    ev = LoadEvalModel("InceptionV3_tf", "legacy", 1, False, dev)
+    real = torch.rand(96, 3, 32, 32) * 2 - 1
+    rf, _ = ev.get_outputs(real.to(dev), quantize=True)
+    mu, sigma = fid.calculate_moments(rf)
+    w = WORKER(cfgs=cfgs, run_name="t", Gen=Gen, Gen_mapping=None, Gen_synthesis=None, Dis=Dis, Gen_ema=None, Gen_ema_mapping=None,
+               Gen_ema_synthesis=None, ema=None, eval_model=ev, train_dataloader=None, eval_dataloader=None, global_rank=0,
+               local_rank=dev, mu=mu, sigma=sigma, real_feats=rf, logger=None, num_eval=96)
+    best = w.evaluate(step=0, metrics=["is", "fid", "prdc"], writing=False, training=True)
+    r = w.last_metrics
+    assert best is True and np.isfinite(r["FID"]) and r["FID"] > 0 and np.isfinite(r["IS"]) and 0.0 <= r["Coverage"] <= 1.0
+    assert Gen.training and Dis.training                       # make_GAN_trainable restored the modes
