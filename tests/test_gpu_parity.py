@@ -389,3 +389,27 @@ def test_biggan_and_resnetgan_d_and_g_phase_vs_reference_golden(golden_dir, tag)
     assert abs(float(g_loss.detach()) - float(g["g_loss"])) < 5e-2 * abs(float(g["g_loss"])) + 1e-2
     worst, median, cos = _grad_errors(G, g, "Ggrad/")
     assert worst[0] <= (0.5 if c["d_sn"] else 0.8) and cos[0] >= (0.9 if c["d_sn"] else 0.75), (worst, median, cos)
+
+
+def test_ema_flat_arena_matches_reference_semantics(golden_dir):
+    """Ema.update through the flat-arena lerp kernel == reference Ema (src/utils/ema.py:27-40) on the golden modules:
+    decay 0 before start_iter, lerp afterwards, integer buffers copied; parameters keep their names / shapes."""
+    import torch.nn as nn
+    from sgb200.utils.ema import Ema
+    dev = _cuda()
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    src = nn.Sequential(nn.Conv2d(3, 4, 3), nn.BatchNorm2d(4))
+    tgt = nn.Sequential(nn.Conv2d(3, 4, 3), nn.BatchNorm2d(4))
+    src.load_state_dict({k[len("ema_src/"):]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith("ema_src/")})
+    tgt.load_state_dict({k[len("ema_tgt0/"):]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith("ema_tgt0/")})
+    src, tgt = src.to(dev), tgt.to(dev)
+    e = Ema(src, tgt, decay=0.9, start_iter=2)
+    for k, v in tgt.state_dict().items():
+        np.testing.assert_allclose(v.cpu().numpy(), g["ema_init/" + k])
+    src.load_state_dict({k[len("ema_src2/"):]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith("ema_src2/")})
+    e.update(5)
+    for k, v in tgt.state_dict().items():
+        np.testing.assert_allclose(v.cpu().numpy(), g["ema_after/" + k], rtol=1e-6, atol=1e-7, err_msg=k)
+    e.update(1)                                                   # before start_iter: decay 0 -> plain copy
+    for (k, v), (_, s) in zip(tgt.state_dict().items(), src.state_dict().items()):
+        np.testing.assert_allclose(v.cpu().numpy(), s.cpu().numpy(), err_msg=k)
