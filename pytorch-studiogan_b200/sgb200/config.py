@@ -90,11 +90,17 @@ class Configurations(object):
                             self.MODEL.g_act_fn, self.MODEL.d_act_fn, self.MODEL.g_info_injection, out=self.MODULES)
 
     def define_optimizer(self, Gen, Dis):
-        """torch.optim.Adam with eps=1e-6 (src/config.py:541-563) — or the fused arena optimiser when asked for."""
+        """Adam with eps=1e-6 (src/config.py:541-563): on the device the one-launch arena optimiser (same arithmetic and
+        state_dict format as torch.optim.Adam), on the CPU (host-logic tests) torch.optim.Adam itself."""
         opt = self.OPTIMIZATION
         if opt.type_ != "Adam":
             raise NotImplementedError("only Adam is on the BASELINE configs' hot path")
         betas_g = [opt.beta1, opt.beta2]
+        if next(Gen.parameters()).is_cuda and opt.g_weight_decay == 0.0 and opt.d_weight_decay == 0.0:
+            from .utils.optim import ArenaAdam
+            self.OPTIMIZATION.g_optimizer = ArenaAdam(Gen, lr=opt.g_lr, betas=betas_g, eps=1e-6)
+            self.OPTIMIZATION.d_optimizer = ArenaAdam(Dis, lr=opt.d_lr, betas=betas_g, eps=1e-6)
+            return
         self.OPTIMIZATION.g_optimizer = torch.optim.Adam(params=[p for p in Gen.parameters()], lr=opt.g_lr, betas=betas_g,
                                                          weight_decay=opt.g_weight_decay, eps=1e-6)
         self.OPTIMIZATION.d_optimizer = torch.optim.Adam(params=[p for p in Dis.parameters()], lr=opt.d_lr, betas=betas_g,

@@ -65,16 +65,15 @@ def prepare_parallel_training(Gen, Gen_mapping, Gen_synthesis, Dis, Gen_ema, Gen
     return Gen, Gen_mapping, Gen_synthesis, Dis, Gen_ema, Gen_ema_mapping, Gen_ema_synthesis
 
 
-def allreduce_gradients(net):
-    """Average gradients across ranks: one NCCL all-reduce when the parameters live in a flat arena, else per tensor."""
+def allreduce_gradients(net, optimizer=None):
+    """Average gradients across ranks: ONE all-reduce over the flat gradient arena when the optimiser keeps one (the
+    1/world scale is folded into the fused Adam launch), else flatten / reduce / scatter back."""
     group = getattr(net, "sgb_group", None)
     if group is None:
         return
     world = net.sgb_world_size
-    arena = getattr(net, "sgb_arena", None)
-    if arena is not None:
-        dist.all_reduce(arena.grad, group=group)
-        arena.grad_scale = 1.0 / world
+    if optimizer is not None and hasattr(optimizer, "all_reduce"):
+        optimizer.all_reduce(group, world)
         return
     grads = [p.grad for p in net.parameters() if p.grad is not None]
     if not grads:

@@ -25,3 +25,35 @@ class ParamArena:
 
     def intact(self):
         return all(p.data_ptr() == q for p, q in zip(self.params, self.ptrs))
+
+
+def param_arena(module):
+    """The (cached) arena of ``module``; rebuilt if some parameter storage was replaced since (e.g. ``module.to``)."""
+    a = getattr(module, "_sgb_param_arena", None)
+    if a is None or not a.intact():
+        a = ParamArena(module)
+        module._sgb_param_arena = a
+    return a
+
+
+class GradArena:
+    """Gradients of every arena parameter as views of one flat buffer laid out like the parameter arena: zero_grad is
+    one memset, the data-parallel gradient exchange one all-reduce, the optimiser one launch."""
+
+    def __init__(self, arena):
+        self.arena = arena
+        self.flat = torch.zeros_like(arena.flat)
+        self.views = []
+        o = 0
+        for p in arena.params:
+            self.views.append(self.flat[o:o + p.numel()].view(p.shape))
+            o += (p.numel() + 63) // 64 * 64
+
+    def attach(self):
+        for p, g in zip(self.arena.params, self.views):
+            if p.grad is None or p.grad.data_ptr() != g.data_ptr():
+                p.grad = g
+
+    def zero(self):
+        self.flat.zero_()
+        self.attach()

@@ -8,7 +8,7 @@ spectral-norm u / v buffers are lerped through the two flat arenas of the batche
 import torch
 
 from .. import kernels as K
-from .arena import ParamArena
+from .arena import param_arena
 
 
 class Ema(object):
@@ -28,8 +28,7 @@ class Ema(object):
         p0 = next(self.source.parameters())
         if not p0.is_cuda:
             return False
-        if self.src_arena is None or not (self.src_arena.intact() and self.tgt_arena.intact()):
-            self.src_arena, self.tgt_arena = ParamArena(self.source), ParamArena(self.target)
+        self.src_arena, self.tgt_arena = param_arena(self.source), param_arena(self.target)
         return True
 
     def update(self, iter=None):

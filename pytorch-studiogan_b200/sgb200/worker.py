@@ -83,7 +83,7 @@ class WORKER(object):
                 dis_acml_loss = dis_acml_loss / self.OPTIMIZATION.acml_steps
                 dis_acml_loss.backward()
                 batch_counter += 1
-            model_lib.allreduce_gradients(self.Dis)
+            model_lib.allreduce_gradients(self.Dis, self.OPTIMIZATION.d_optimizer)
             self.OPTIMIZATION.d_optimizer.step()
         return "N/A", dis_acml_loss
 
@@ -102,7 +102,7 @@ class WORKER(object):
                 gen_acml_loss = self.LOSS.g_loss(fake_dict["adv_output"], DDP=self.DDP)
                 gen_acml_loss = gen_acml_loss / self.OPTIMIZATION.acml_steps
                 gen_acml_loss.backward()
-            model_lib.allreduce_gradients(self.Gen)
+            model_lib.allreduce_gradients(self.Gen, self.OPTIMIZATION.g_optimizer)
             self.OPTIMIZATION.g_optimizer.step()
             if self.MODEL.apply_g_ema:
                 self.ema.update(current_step)

@@ -413,3 +413,46 @@ def test_ema_flat_arena_matches_reference_semantics(golden_dir):
     e.update(1)                                                   # before start_iter: decay 0 -> plain copy
     for (k, v), (_, s) in zip(tgt.state_dict().items(), src.state_dict().items()):
         np.testing.assert_allclose(v.cpu().numpy(), s.cpu().numpy(), err_msg=k)
+
+
+def test_arena_adam_matches_torch_adam_and_state_dict_format(golden_dir):
+    """The one-launch arena optimiser == torch.optim.Adam (reference src/config.py:541-563, eps 1e-6) over three steps on
+    a golden-sized discriminator, gradients accumulated by autograd into the flat arena; state_dict round-trips through
+    torch.optim.Adam's own format."""
+    import copy
+    from sgb200.utils.optim import ArenaAdam
+    dev = _cuda()
+    g = np.load(os.path.join(golden_dir, "deep32_c8.npz"))
+    _, D = _build_from_golden(g, 8, 1, False, dev)
+    Dref = copy.deepcopy(D)
+    opt = ArenaAdam(D, lr=2e-4, betas=(0.0, 0.999), eps=1e-6)
+    ref = torch.optim.Adam(Dref.parameters(), lr=2e-4, betas=(0.0, 0.999), eps=1e-6)
+    gen = torch.Generator().manual_seed(3)
+    for step in range(3):
+        opt.zero_grad()
+        ref.zero_grad()
+        for _ in range(2):                                         # two accumulation rounds (acml_steps)
+            for p, q in zip(D.parameters(), Dref.parameters()):
+                gr = torch.randn(p.shape, generator=gen).to(dev)
+                (p * gr).sum().backward()
+                (q * gr).sum().backward()
+        opt.step()
+        ref.step()
+        for (n, p), q in zip(D.named_parameters(), Dref.parameters()):
+            np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().cpu().numpy(), rtol=1e-5, atol=1e-7, err_msg=n)
+    sd = opt.state_dict()
+    rsd = ref.state_dict()
+    assert set(sd["state"].keys()) == set(rsd["state"].keys())
+    for i in sd["state"]:
+        np.testing.assert_allclose(sd["state"][i]["exp_avg_sq"].cpu().numpy(), rsd["state"][i]["exp_avg_sq"].cpu().numpy(),
+                                   rtol=1e-5, atol=1e-12)
+        assert int(sd["state"][i]["step"]) == int(rsd["state"][i]["step"]) == 3
+    ref2 = torch.optim.Adam(Dref.parameters(), lr=2e-4, betas=(0.0, 0.999), eps=1e-6)
+    ref2.load_state_dict(sd)                                       # our state loads into torch's optimiser ...
+    opt2 = ArenaAdam(D, lr=1.0, betas=(0.5, 0.5), eps=1e-6)
+    opt2.load_state_dict(rsd)                                      # ... and torch's into ours
+    assert opt2.step_count == 3 and opt2.param_groups[0]["lr"] == 2e-4
+    sd2 = opt2.state_dict()
+    for i in sd["state"]:
+        np.testing.assert_allclose(sd2["state"][i]["exp_avg"].cpu().numpy(), rsd["state"][i]["exp_avg"].cpu().numpy(), rtol=1e-5,
+                                   atol=1e-12)
