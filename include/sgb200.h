@@ -214,6 +214,26 @@ int sgb_adam_ema_step(float* p, const float* g, float* m, float* v, int64_t n, f
                       int32_t step, float* ema, float ema_decay, float grad_scale, sgb_stream_t stream);
 int sgb_ema_lerp(float* ema, const float* p, int64_t n, float decay, sgb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Gradient penalty (replaces utils/losses.py:268-275 cal_deriv + :301-316 cal_grad_penalty).
+ * The second-order term is evaluated as "reverse over forward": P = mean_b (||g_b|| - 1)^2 with g = d(sum adv)/dx_hat;
+ * dP/dtheta = d/dtheta <v, g(theta)> for the constant seed v = dP/dg, and <v, g> is the directional derivative of the
+ * discriminator along v, i.e. the output of a tangent (JVP) pass.  Kernels: interpolation, per-sample norms, the seed,
+ * and the (x, tangent, gamma) derivatives of a training-mode batch norm's tangent map (torch's
+ * batchnorm_double_backward).  All other layers' tangent maps are the forward kernels above (convolutions are linear).
+ *   sums layout: [5][C] = sum a, sum c, sum xhat*a, sum xhat*c, sum a*c   (a = tangent, c = incoming cotangent)
+ * ------------------------------------------------------------------------------------------ */
+int sgb_gp_interpolate(const float* real, const float* fake, const float* alpha, float* out, int32_t B, int64_t n_per,
+                       sgb_stream_t stream);
+int sgb_gp_sumsq(const float* g, float* sumsq, int32_t B, int64_t n_per, sgb_stream_t stream);
+int sgb_gp_seed(const float* g, const float* sumsq, float* v, int32_t B, int64_t n_per, sgb_stream_t stream);
+int sgb_bn_tangent_bwd_reduce(const void* x, int64_t x_cstride, const void* a, int64_t a_cstride, const void* c, int64_t c_cstride,
+                              int64_t npix, int32_t C, const float* mean, const float* rstd, float* sums, sgb_stream_t stream);
+int sgb_bn_tangent_bwd_apply(const void* x, int64_t x_cstride, const void* a, int64_t a_cstride, const void* c, int64_t c_cstride,
+                             int64_t npix, int32_t C, const float* gamma, const float* mean, const float* rstd,
+                             const float* sums, float count, int32_t use_batch_stats, void* dx, int64_t dx_cstride, void* da,
+                             int64_t da_cstride, sgb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -232,6 +232,37 @@ def grad_penalty(disc_fn, real, fake, alpha):
     return ((grads.norm(2, dim=1) - 1) ** 2).mean() + interp[:, 0, 0, 0].mean() * 0
 
 
+def bn_tangent(x, a, gamma, eps):
+    """Tangent (JVP) of training-mode batch norm y = gamma * xhat + beta along a: gamma * r * (a - mean a - xhat * mean(xhat a)).
+    (Jacobian of torch's native_batch_norm; identical to its backward map since the Jacobian is symmetric.)"""
+    dims = (0, 2, 3)
+    mu = x.mean(dims, keepdim=True)
+    r = torch.rsqrt(x.var(dims, unbiased=False, keepdim=True) + eps)
+    xh = (x - mu) * r
+    g = gamma.view(1, -1, 1, 1) if gamma is not None else 1.0
+    return g * r * (a - a.mean(dims, keepdim=True) - xh * (xh * a).mean(dims, keepdim=True))
+
+
+def bn_tangent_backward(x, a, c, gamma, eps):
+    """Derivatives of <c, bn_tangent(x, a, gamma)> w.r.t. (x, a, gamma): torch's batchnorm_double_backward
+    (tools/autograd/templates/Functions.cpp) with gO := a, ggI := c, written with per-channel sums
+    Sa, Sc, Sxa = sum xhat a, Sxc = sum xhat c, Sac = sum a c over M = B*H*W elements."""
+    dims = (0, 2, 3)
+    M = x.numel() // x.shape[1]
+    mu = x.mean(dims, keepdim=True)
+    r = torch.rsqrt(x.var(dims, unbiased=False, keepdim=True) + eps)
+    xh = (x - mu) * r
+    g = gamma.view(1, -1, 1, 1) if gamma is not None else torch.ones_like(r)
+    Sa, Sc = a.sum(dims, keepdim=True), c.sum(dims, keepdim=True)
+    Sxa, Sxc = (xh * a).sum(dims, keepdim=True), (xh * c).sum(dims, keepdim=True)
+    Sac = (a * c).sum(dims, keepdim=True)
+    T = Sa * Sc / M - Sac + 3.0 * Sxa * Sxc / M
+    dx = g * r * r / M * (xh * T + Sxc * (Sa / M - a) + Sxa * (Sc / M - c))
+    da = g * r * (c - Sc / M - xh * Sxc / M)
+    dgamma = (r * (Sac - (Sa * Sc + Sxa * Sxc) / M)).reshape(-1)
+    return dx, da, dgamma
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # EMA / Adam  (src/utils/ema.py:27-40; src/config.py:541-563 -> torch.optim.Adam, eps 1e-6)
 # ---------------------------------------------------------------------------------------------------------------------

@@ -260,6 +260,106 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- tangent (JVP) backward
+// The gradient-penalty pass (sgb200/utils/gp.py) pushes a tangent a = dx/d(eps) through the discriminator.  For a
+// training-mode batch norm the tangent map is  t = gamma * r * (a - mean(a) - xhat * mean(xhat * a))  (the same linear
+// map as its backward, run by the bwd kernels above).  Differentiating t w.r.t. (x, a, gamma) for an incoming cotangent c
+// (torch: batchnorm_double_backward, tools/autograd/templates/Functions.cpp) needs five per-channel sums
+//   Sa = sum a, Sc = sum c, Sxa = sum xhat*a, Sxc = sum xhat*c, Sac = sum a*c            (M = pixels per channel)
+//   dx = gamma r^2 / M * [ xhat * T + Sxc * (Sa/M - a) + Sxa * (Sc/M - c) ],  T = Sa*Sc/M - Sac + 3*Sxa*Sxc/M
+//   da = gamma r * (c - Sc/M - xhat * Sxc/M)
+//   dgamma = r * (Sac - Sa*Sc/M - Sxa*Sxc/M)                                              (host side, [C] vectors)
+__global__ void __launch_bounds__(256) bn_tan_bwd_reduce_kernel(const bf16* __restrict__ x, long long xs,
+                                                                 const bf16* __restrict__ a, long long as_,
+                                                                 const bf16* __restrict__ c, long long cs, long long npix, int C,
+                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                 float* __restrict__ sums, long long pix_per_block) {
+  __shared__ float acc[5][256];
+  const int VG = C >> 3;
+  const int VGb = VG < 32 ? VG : 32;          // channel groups handled per block (blockIdx.y strides the rest)
+  const int nrows = 256 / VGb;
+  const int gl = threadIdx.x % VGb, prow = threadIdx.x / VGb;
+  const int g = blockIdx.y * VGb + gl;
+  for (int i = threadIdx.x; i < 5 * 256; i += 256) acc[i / 256][i % 256] = 0.f;
+  __syncthreads();
+  if (prow < nrows && g < VG) {
+    float t[5][8], mu[8], rs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mu[j] = mean[g * 8 + j]; rs[j] = rstd[g * 8 + j];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) t[k][j] = 0.f;
+    }
+    const long long p0 = (long long)blockIdx.x * pix_per_block;
+    const long long p1 = p0 + pix_per_block < npix ? p0 + pix_per_block : npix;
+    for (long long p = p0 + prow; p < p1; p += nrows) {
+      float xv[8], av[8], cv[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * xs) + g), xv);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(a + p * as_) + g), av);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(c + p * cs) + g), cv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xv[j] - mu[j]) * rs[j];
+        t[0][j] += av[j];
+        t[1][j] += cv[j];
+        t[2][j] = fmaf(xh, av[j], t[2][j]);
+        t[3][j] = fmaf(xh, cv[j], t[3][j]);
+        t[4][j] = fmaf(av[j], cv[j], t[4][j]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&acc[k][gl * 8 + j], t[k][j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 5 * VGb * 8; i += 256) {
+    const int k = i / (VGb * 8), cl = i % (VGb * 8);
+    const int ch = blockIdx.y * VGb * 8 + cl;
+    if (ch < C) atomicAdd(sums + (size_t)k * C + ch, acc[k][cl]);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_tan_bwd_apply_kernel(const bf16* __restrict__ x, long long xs,
+                                                                const bf16* __restrict__ a, long long as_,
+                                                                const bf16* __restrict__ c, long long cs, long long npix, int C,
+                                                                const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd, const float* __restrict__ sums,
+                                                                float inv_count, int use_batch_stats, bf16* __restrict__ dx,
+                                                                long long dxs, bf16* __restrict__ da, long long das) {
+  const int VG = C >> 3;
+  const long long total = npix * VG;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int g = (int)(i % VG);
+    const long long p = i / VG;
+    float xv[8], av[8], cv[8], ox[8], oa[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * xs) + g), xv);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(a + p * as_) + g), av);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(c + p * cs) + g), cv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = g * 8 + j;
+      const float gm = gamma ? __ldg(gamma + ch) : 1.f;
+      const float rs = __ldg(rstd + ch);
+      if (use_batch_stats) {
+        const float xh = (xv[j] - __ldg(mean + ch)) * rs;
+        const float Sa = __ldg(sums + ch) * inv_count, Sc = __ldg(sums + C + ch) * inv_count;
+        const float Sxa = __ldg(sums + 2 * C + ch) * inv_count, Sxc = __ldg(sums + 3 * C + ch) * inv_count;
+        const float Sac = __ldg(sums + 4 * C + ch) * inv_count;
+        const float T = Sa * Sc - Sac + 3.f * Sxa * Sxc;                      // all already divided by M once
+        ox[j] = gm * rs * rs * (xh * T + Sxc * (Sa - av[j]) + Sxa * (Sc - cv[j]));
+        oa[j] = gm * rs * (cv[j] - Sc - xh * Sxc);
+      } else {
+        ox[j] = 0.f;
+        oa[j] = gm * rs * cv[j];
+      }
+    }
+    if (dx) reinterpret_cast<uint4*>(dx + p * dxs)[g] = pack8(ox);
+    if (da) reinterpret_cast<uint4*>(da + p * das)[g] = pack8(oa);
+  }
+}
+
 }  // namespace sgb
 
 using namespace sgb;
@@ -356,6 +456,42 @@ extern "C" int sgb_bn_bwd_apply(const void* dy, int64_t dy_cstride, const void* 
                                                            shift, per_image ? C : 0, mean, rstd, S1, S2,
                                                            use_batch_stats ? 1.f / count : 0.f, relu, up2, use_batch_stats, (bf16*)dx,
                                                            dx_cstride);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_bn_tangent_bwd_reduce(const void* x, int64_t xs, const void* a, int64_t as_, const void* c, int64_t cs,
+                                         int64_t npix, int32_t C, const float* mean, const float* rstd, float* sums,
+                                         sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(x && a && c && mean && rstd && sums && npix > 0 && C > 0 && C % 8 == 0);
+  SGB_REQUIRE(xs % 8 == 0 && as_ % 8 == 0 && cs % 8 == 0);
+  SGB_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 5 * (size_t)C, stream));
+  const int VG = C / 8, VGb = VG < 32 ? VG : 32;
+  const int gy = (VG + VGb - 1) / VGb;
+  long long target = 8LL * sm_count() / gy;
+  if (target < 1) target = 1;
+  long long ppb = (npix + target - 1) / target;
+  if (ppb < 64) ppb = 64;
+  dim3 grid((unsigned)((npix + ppb - 1) / ppb), gy);
+  bn_tan_bwd_reduce_kernel<<<grid, 256, 0, stream>>>((const bf16*)x, xs, (const bf16*)a, as_, (const bf16*)c, cs, npix, C, mean, rstd,
+                                                    sums, ppb);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_bn_tangent_bwd_apply(const void* x, int64_t xs, const void* a, int64_t as_, const void* c, int64_t cs,
+                                        int64_t npix, int32_t C, const float* gamma, const float* mean, const float* rstd,
+                                        const float* sums, float count, int32_t use_batch_stats, void* dx, int64_t dxs, void* da,
+                                        int64_t das, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(x && a && c && mean && rstd && (dx || da) && npix > 0 && C > 0 && C % 8 == 0);
+  SGB_REQUIRE(!use_batch_stats || (sums && count > 0.f));
+  SGB_REQUIRE(xs % 8 == 0 && as_ % 8 == 0 && cs % 8 == 0 && (!dx || dxs % 8 == 0) && (!da || das % 8 == 0));
+  bn_tan_bwd_apply_kernel<<<ew_blocks(npix * (C / 8)), 256, 0, stream>>>((const bf16*)x, xs, (const bf16*)a, as_, (const bf16*)c, cs,
+                                                                        npix, C, gamma, mean, rstd, sums,
+                                                                        use_batch_stats ? 1.f / count : 0.f, use_batch_stats,
+                                                                        (bf16*)dx, dxs, (bf16*)da, das);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }

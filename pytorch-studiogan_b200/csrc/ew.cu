@@ -532,6 +532,44 @@ __global__ void __launch_bounds__(256) lerp_kernel(float* __restrict__ ema, cons
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- gradient penalty
+// losses.cal_grad_penalty (src/utils/losses.py:301-316): x_hat = alpha*real + (1-alpha)*fake (per-sample alpha, torch's
+// operation order: two products, one sum, each rounded), per-sample ||grad||_2, and the seed of the second pass
+// v_b = dP/dgrad_b = 2 (||g_b|| - 1) / (B ||g_b||) * g_b   for P = mean_b (||g_b|| - 1)^2.
+__global__ void __launch_bounds__(256) gp_interpolate_kernel(const float* __restrict__ real, const float* __restrict__ fake,
+                                                              const float* __restrict__ alpha, float* __restrict__ out,
+                                                              long long n_per, long long total) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const float a = __ldg(alpha + i / n_per);
+    out[i] = __fadd_rn(__fmul_rn(a, real[i]), __fmul_rn(__fsub_rn(1.f, a), fake[i]));
+  }
+}
+__global__ void __launch_bounds__(256) gp_sumsq_kernel(const float* __restrict__ g, float* __restrict__ sumsq, long long n_per,
+                                                        int blocks_per_sample) {
+  const int b = blockIdx.x / blocks_per_sample, k = blockIdx.x % blocks_per_sample;
+  const float* gb = g + (long long)b * n_per;
+  float acc = 0.f;
+  for (long long i = (long long)k * 256 + threadIdx.x; i < n_per; i += (long long)blocks_per_sample * 256) acc = fmaf(gb[i], gb[i], acc);
+  __shared__ float red[8];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(sumsq + b, t);
+  }
+}
+__global__ void __launch_bounds__(256) gp_seed_kernel(const float* __restrict__ g, const float* __restrict__ sumsq,
+                                                       float* __restrict__ v, long long n_per, long long total, float inv_B) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const float n = sqrtf(__ldg(sumsq + i / n_per));
+    const float coef = n > 0.f ? 2.f * (n - 1.f) * inv_B / n : 0.f;
+    v[i] = coef * g[i];
+  }
+}
+
 }  // namespace sgb
 
 using namespace sgb;
@@ -735,6 +773,38 @@ extern "C" int sgb_ema_lerp(float* ema, const float* p, int64_t n, float decay, 
   cudaStream_t stream = (cudaStream_t)stream_;
   SGB_REQUIRE(ema && p && n > 0);
   lerp_kernel<<<ew_blocks(n), 256, 0, stream>>>(ema, p, n, decay);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_gp_interpolate(const float* real, const float* fake, const float* alpha, float* out, int32_t B, int64_t n_per,
+                                  sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(real && fake && alpha && out && B > 0 && n_per > 0);
+  const long long total = (long long)B * n_per;
+  gp_interpolate_kernel<<<ew_blocks(total), 256, 0, stream>>>(real, fake, alpha, out, n_per, total);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_gp_sumsq(const float* g, float* sumsq, int32_t B, int64_t n_per, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(g && sumsq && B > 0 && n_per > 0);
+  SGB_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * (size_t)B, stream));
+  long long bps = (n_per + 256 * 16 - 1) / (256 * 16);
+  const long long cap = (8LL * sm_count() + B - 1) / B;
+  if (bps > cap) bps = cap;
+  if (bps < 1) bps = 1;
+  gp_sumsq_kernel<<<(unsigned)(B * bps), 256, 0, stream>>>(g, sumsq, n_per, (int)bps);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_gp_seed(const float* g, const float* sumsq, float* v, int32_t B, int64_t n_per, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(g && sumsq && v && B > 0 && n_per > 0);
+  const long long total = (long long)B * n_per;
+  gp_seed_kernel<<<ew_blocks(total), 256, 0, stream>>>(g, sumsq, v, n_per, total, 1.f / (float)B);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }

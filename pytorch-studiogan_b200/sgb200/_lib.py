@@ -90,6 +90,12 @@ SIGNATURES = {
     "sgb_cast_bf16_to_f32": (c_int, [c_p, c_p, c_i64, c_p]),
     "sgb_adam_ema_step": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_f, c_f, c_f, c_f, c_int, c_p, c_f, c_f, c_p]),
     "sgb_ema_lerp": (c_int, [c_p, c_p, c_i64, c_f, c_p]),
+    "sgb_gp_interpolate": (c_int, [c_p, c_p, c_p, c_p, c_int, c_i64, c_p]),
+    "sgb_gp_sumsq": (c_int, [c_p, c_p, c_int, c_i64, c_p]),
+    "sgb_gp_seed": (c_int, [c_p, c_p, c_p, c_int, c_i64, c_p]),
+    "sgb_bn_tangent_bwd_reduce": (c_int, [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i64, c_int, c_p, c_p, c_p, c_p]),
+    "sgb_bn_tangent_bwd_apply": (c_int, [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i64, c_int, c_p, c_p, c_p, c_p, c_f, c_int,
+                                         c_p, c_i64, c_p, c_i64, c_p]),
 }
 
 _ERR = {1: "SGB_ERR_ARG (invalid argument)", 2: "SGB_ERR_CUDA (CUDA failure)", 3: "SGB_ERR_UNSUPPORTED"}

@@ -15,6 +15,43 @@ from . import kernels as K
 
 bf16 = torch.bfloat16
 
+# ---- tangent tape (gradient penalty, utils/gp.py) ---------------------------------------------------------------------
+# While TAPE is a list, every op applied through ``<Fn>.call(...)`` is appended as (rule, args, outputs); replaying the
+# tape with ``rule.tangent(args, outputs, tan)`` pushes a tangent (directional derivative) through the same network.
+# ``tan(t)`` returns the tangent of primal tensor t or None (zero).  SKIP_PARAM_GRADS suppresses weight gradients in a
+# backward pass that only needs the input gradient (first pass of the penalty).
+TAPE = None
+SKIP_PARAM_GRADS = False
+
+
+def tape_record(rule, args, out):
+    if TAPE is not None:
+        TAPE.append((rule, args, out))
+
+
+class TFunction(Function):
+    """autograd.Function + ``call`` (apply and record on the tangent tape) + ``tangent`` (its JVP rule, itself built
+    from differentiable Functions so that the tangent pass can be back-propagated)."""
+
+    @classmethod
+    def call(cls, *args):
+        out = cls.apply(*args)
+        if TAPE is not None:
+            TAPE.append((cls, args, out))
+        return out
+
+    @staticmethod
+    def tangent(args, out, tan):
+        raise NotImplementedError("no tangent rule for this op (gradient penalty through it is unsupported)")
+
+
+def _tadd(a, b):
+    if a is None:
+        return b
+    if b is None:
+        return a
+    return AddFn.apply(a, b)
+
 
 class SpectralNormState:
     """u / v buffers + workspace of one spectrally-normalised weight (torch/nn/utils/spectral_norm.py semantics)."""
@@ -46,7 +83,7 @@ def _grad_bf16(dy):
     return K.as_nhwc(dy)
 
 
-class ConvFn(Function):
+class ConvFn(TFunction):
     """y = [relu](conv(x, W / sigma) + bias [+ residual])  — conv2d (stride 1) or linear (H = W = 1).
 
     cfg keys: KH, KW, pad, relu, premasked, mask_input, res_up2, res_channels, out_fp32, perm_S, sn (SpectralNormState|None),
@@ -110,10 +147,10 @@ class ConvFn(Function):
                 dx = K.conv_fprop(dz, wd, K.pad8(Cin), KH, KW, KH - 1 - pad, KW - 1 - pad, mask=mask)
             if dx.shape[1] != x.shape[1]:
                 dx = dx[:, :x.shape[1]]
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and not SKIP_PARAM_GRADS:
             G = K.conv_wgrad(x, dz, KH, KW, pad, pad)
             dW = K.sn_backward(G, weight, u_saved, v_saved, sigma, Cout, Cin, taps, cfg.get("perm_S", 1))
-        if ctx.needs_input_grad[2]:
+        if ctx.needs_input_grad[2] and not SKIP_PARAM_GRADS:
             dbias = K.bn_stats(dz)[0][:Cout]
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = K.pool2_fwd(dz, 2) if cfg.get("res_up2", False) else dz
@@ -124,6 +161,41 @@ class ConvFn(Function):
                 dres = full
         return dx, dW, dbias, dres, None
 
+    @staticmethod
+    def tangent(args, out, tan):
+        """d/d(eps) [relu](conv(x) + b + res) = [y > 0] * (conv(tx) + t_res): same weights, no bias, no new power
+        iteration (the primal call's sigma / packs are reused through cfg['sn_cache'])."""
+        x, weight, bias, residual, cfg = args
+        tx, tres = tan(x), tan(residual)
+        if cfg.get("out_fp32", False) or cfg.get("perm_S", 1) != 1:
+            raise NotImplementedError("tangent of fp32-output / permuted linear layers")
+        if tx is None:
+            t = tres
+            if t is not None and cfg.get("res_up2", False):
+                raise NotImplementedError("tangent through an up-sampled residual without a main-branch tangent")
+        else:
+            tcfg = {"KH": cfg["KH"], "KW": cfg["KW"], "pad": cfg["pad"], "relu": False, "res_up2": cfg.get("res_up2", False),
+                    "sn": cfg.get("sn"), "sn_cache": cfg.get("sn_cache"), "do_power_iteration": False}
+            t = ConvFn.apply(tx, weight, None, tres, tcfg)
+        if t is not None and cfg.get("relu", False):
+            t = MaskFn.apply(t, out)
+        return t
+
+
+class MaskFn(TFunction):
+    """t * [src > 0]: tangent of a ReLU whose (post- or pre-activation) primal is ``src``; linear in t, no gradient to
+    src (the mask is piecewise constant)."""
+
+    @staticmethod
+    def forward(ctx, t, src):
+        ctx.save_for_backward(src)
+        return K.axpby(K.as_nhwc(t), mask=src)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (src,) = ctx.saved_tensors
+        return K.axpby(K.as_nhwc(dy), mask=src), None
+
 
 def _pad_bias(bias, Cout_p):
     if bias is None:
@@ -133,7 +205,7 @@ def _pad_bias(bias, Cout_p):
     return out
 
 
-class BNActFn(Function):
+class BNActFn(TFunction):
     """y = [relu](batch_norm(x) * g + b) with g/b per image (cBN), per channel (affine) or absent; optional nearest x2
     upsample of the result.  cfg keys: mode (0 cBN, 1 affine, 2 plain), relu, up2, use_batch_stats, track, momentum, eps, group.
     """
@@ -165,7 +237,22 @@ class BNActFn(Function):
         ctx.gshape = gain.shape if gain is not None else None
         ctx.bshape = bias.shape if bias is not None else None
         ctx.save_for_backward(x, scale, shift, mean, rstd)
+        if TAPE is not None:
+            cfg["_tangent_stats"] = (mean, rstd, count)
         return y
+
+    @staticmethod
+    def tangent(args, out, tan):
+        x, gain, bias, running_mean, running_var, cfg = args
+        tx = tan(x)
+        if tx is None:
+            return None
+        if cfg["mode"] == 0 or cfg["up2"]:
+            raise NotImplementedError("tangent of conditional / up-sampling batch norm (generator-side op)")
+        mean, rstd, count = cfg["_tangent_stats"]
+        t = BNTangentFn.apply(x, tx, gain, mean, rstd, {"count": count, "use_batch_stats": cfg["use_batch_stats"],
+                                                         "group": cfg.get("group")})
+        return MaskFn.apply(t, out) if cfg["relu"] else t
 
     @staticmethod
     def backward(ctx, dy):
@@ -195,7 +282,49 @@ class BNActFn(Function):
         return dx, dgain, dbias, None, None, None
 
 
-class SplitResidualFn(Function):
+class BNTangentFn(TFunction):
+    """t = gamma * r * (a - mean(a) - xhat * mean(xhat * a)): the tangent map of y = gamma * xhat + beta with batch
+    statistics (r = rstd; running statistics: t = gamma * r * a).  Its own backward returns the derivatives w.r.t. the
+    primal input x, the incoming tangent a and gamma (torch: batchnorm_double_backward); mean / rstd are treated as the
+    functions of x they are."""
+
+    @staticmethod
+    def forward(ctx, x, a, gamma, mean, rstd, cfg):
+        B, C, H, W, _ = K.geom(x)
+        a = K.as_nhwc(a)
+        g = gamma if gamma is not None else torch.ones(C, device=x.device, dtype=torch.float32)
+        scale = (g * rstd).reshape(1, C).contiguous()
+        shift = torch.zeros_like(scale)
+        S12 = None
+        if cfg["use_batch_stats"]:
+            _, S12 = K.bn_bwd_reduce(a, x, scale, shift, False, mean, rstd, False, False)
+            if cfg.get("group") is not None:
+                dist.all_reduce(S12, group=cfg["group"])
+        t = K.bn_bwd_apply(a, x, scale, shift, False, mean, rstd, S12, cfg["count"], False, False, cfg["use_batch_stats"])
+        ctx.cfg = cfg
+        ctx.has_gamma = gamma is not None
+        ctx.save_for_backward(x, a, gamma, mean, rstd)
+        return t
+
+    @staticmethod
+    def backward(ctx, c):
+        x, a, gamma, mean, rstd = ctx.saved_tensors
+        cfg = ctx.cfg
+        c = K.as_nhwc(c)
+        M = cfg["count"]
+        sums = K.bn_tangent_bwd_reduce(x, a, c, mean, rstd)
+        if cfg["use_batch_stats"] and cfg.get("group") is not None:
+            dist.all_reduce(sums, group=cfg["group"])
+        dx, da = K.bn_tangent_bwd_apply(x, a, c, gamma, mean, rstd, sums, M, cfg["use_batch_stats"],
+                                        want_dx=ctx.needs_input_grad[0] and cfg["use_batch_stats"], want_da=ctx.needs_input_grad[1])
+        dgamma = None
+        if ctx.has_gamma and ctx.needs_input_grad[2]:
+            Sa, Sc, Sxa, Sxc, Sac = sums.unbind(0)
+            dgamma = rstd * (Sac - (Sa * Sc + Sxa * Sxc) / M) if cfg["use_batch_stats"] else rstd * Sac
+        return dx, da, dgamma, None, None, None
+
+
+class SplitResidualFn(TFunction):
     """x -> (x, x[:, :c]): main branch and channel-drop skip branch of a generator block
     (src/models/big_resnet_deep_legacy.py:50-53).  Backward adds the narrower skip gradient into the first channels of
     the main gradient in place."""
@@ -218,7 +347,7 @@ class SplitResidualFn(Function):
         return d_main, None
 
 
-class DBlockEntryFn(Function):
+class DBlockEntryFn(TFunction):
     """x -> (a0, skip_src) with a0 = relu(x) and skip_src = avgpool2(a0) | a0: the two consumers of a discriminator
     block input (src/models/big_resnet_deep_legacy.py:211-224).  The reference's d_act_fn is nn.ReLU(inplace=True)
     (src/config.py:486), which rectifies the aliased skip tensor ``x0`` as well, so the skip path carries relu(x).
@@ -245,8 +374,17 @@ class DBlockEntryFn(Function):
             return K.axpby(dpx, mask=a0), None
         return K.axpby(da0, dpx, mask=a0), None
 
+    @staticmethod
+    def tangent(args, out, tan):
+        x, downsample = args
+        tx = tan(x)
+        if tx is None:
+            return None, None
+        ta0 = MaskFn.apply(tx, out[0])
+        return ta0, (PoolFn.apply(ta0) if downsample else ta0)
 
-class AvgPoolFn(Function):
+
+class AvgPoolFn(TFunction):
     """2x2 average pooling; ``relu_src``: the input is a post-ReLU tensor and the gradient is returned premasked."""
 
     @staticmethod
@@ -260,8 +398,13 @@ class AvgPoolFn(Function):
         (x,) = ctx.saved_tensors
         return K.pool2_bwd(K.as_nhwc(dy), 0, relu_src=x), None
 
+    @staticmethod
+    def tangent(args, out, tan):
+        tx = tan(args[0])
+        return PoolFn.apply(tx) if tx is not None else None
 
-class ReluFn(Function):
+
+class ReluFn(TFunction):
     @staticmethod
     def forward(ctx, x):
         y = K.axpby(x, relu=True)
@@ -273,8 +416,13 @@ class ReluFn(Function):
         (y,) = ctx.saved_tensors
         return K.axpby(K.as_nhwc(dy), mask=y)
 
+    @staticmethod
+    def tangent(args, out, tan):
+        tx = tan(args[0])
+        return MaskFn.apply(tx, out) if tx is not None else None
 
-class AddFn(Function):
+
+class AddFn(TFunction):
     @staticmethod
     def forward(ctx, a, b):
         return K.axpby(a, b)
@@ -283,8 +431,12 @@ class AddFn(Function):
     def backward(ctx, dy):
         return dy, dy
 
+    @staticmethod
+    def tangent(args, out, tan):
+        return _tadd(tan(args[0]), tan(args[1]))
 
-class ConcatSkipFn(Function):
+
+class ConcatSkipFn(TFunction):
     """skip = cat([px, conv1x1(px)], channel) written into one buffer (learnable shortcut of the BigGAN-Deep D block,
     src/models/big_resnet_deep_legacy.py:225-226)."""
 
@@ -323,15 +475,24 @@ class ConcatSkipFn(Function):
         dpx = dW = dbias = None
         if ctx.needs_input_grad[0]:
             dpx = K.conv_fprop(d_hi, wd, Cin, 1, 1, 0, 0, residual=d_lo)
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and not SKIP_PARAM_GRADS:
             G = K.conv_wgrad(px, d_hi, 1, 1, 0, 0)
             dW = K.sn_backward(G, weight, u_saved, v_saved, sigma, Cextra, Cin, 1)
         if ctx.needs_input_grad[2]:
             dbias = K.bn_stats(d_hi)[0]
         return dpx, dW, dbias, None
 
+    @staticmethod
+    def tangent(args, out, tan):
+        px, weight, bias, cfg = args
+        tpx = tan(px)
+        if tpx is None:
+            return None
+        return ConcatSkipFn.apply(tpx, weight, None, {"sn": cfg.get("sn"), "sn_cache": cfg.get("sn_cache"),
+                                                       "do_power_iteration": False})
 
-class SumHWFn(Function):
+
+class SumHWFn(TFunction):
     """h[b, c] = sum_{h,w} relu(x) in fp32 (src/models/big_resnet_deep_legacy.py:344-345)."""
 
     @staticmethod
@@ -345,8 +506,16 @@ class SumHWFn(Function):
         (x,) = ctx.saved_tensors
         return K.sum_hw_bwd(dh.contiguous(), x, ctx.relu), None
 
+    @staticmethod
+    def tangent(args, out, tan):
+        x, relu = args
+        tx = tan(x)
+        if tx is None:
+            return None
+        return SumHWFn.apply(MaskFn.apply(tx, x) if relu else tx, False)
 
-class ToBF16Fn(Function):
+
+class ToBF16Fn(TFunction):
     """[B, K] fp32 -> [B, Kp, 1, 1] bf16 activation (input of the linear layers); K is zero-padded to a multiple of 8
     (TMA stride granularity), e.g. the 10-way one-hot cBN input of ResNetGAN or BigGAN's 148-wide [embedding, z-chunk]."""
 
@@ -370,7 +539,7 @@ class ToBF16Fn(Function):
         return g[:, :ctx.Kd] if Kp != ctx.Kd else g
 
 
-class ImageInFn(Function):
+class ImageInFn(TFunction):
     """NCHW fp32 image in [-1, 1] -> NHWC bf16 activation with 8 (zero-padded) channels."""
 
     @staticmethod
@@ -382,8 +551,13 @@ class ImageInFn(Function):
     def backward(ctx, dy):
         return K.nhwc_to_img(K.as_nhwc(dy), ctx.C, tanh=False)
 
+    @staticmethod
+    def tangent(args, out, tan):
+        t = tan(args[0])
+        return ImageInFn.apply(t) if t is not None else None
 
-class ImageColFn(Function):
+
+class ImageColFn(TFunction):
     """NCHW fp32 image -> [B, 32, H, W] bf16 tensor of its 3x3 patches (k = tap*3 + c, zero padded): the operand of the
     3 -> C input convolution run as a K = 32 GEMM (see ops._ConvBase.forward)."""
 
@@ -395,8 +569,13 @@ class ImageColFn(Function):
     def backward(ctx, dcol):
         return K.col27_bwd(K.as_nhwc(dcol))
 
+    @staticmethod
+    def tangent(args, out, tan):
+        t = tan(args[0])
+        return ImageColFn.apply(t) if t is not None else None
 
-class ImageOutFn(Function):
+
+class ImageOutFn(TFunction):
     """NHWC activation (>= 3 channels) -> tanh -> NCHW fp32 image (nn.Tanh at big_resnet_deep_legacy.py:183)."""
 
     @staticmethod
@@ -412,7 +591,7 @@ class ImageOutFn(Function):
         return K.img_grad_to_nhwc(dimg, img, ctx.Cp), None
 
 
-class SelfAttentionFn(Function):
+class SelfAttentionFn(TFunction):
     """ops.SelfAttention.forward (src/utils/ops.py:83-103) with the attention map materialised in bf16:
        theta = conv(x), phi = maxpool(conv(x)), g = maxpool(conv(x)); P = softmax(theta . phi^T); o = P . g;
        out = x + sigma * conv(o).  All contractions run on the tcgen05 engine (batched modes 1/2)."""
@@ -494,7 +673,7 @@ class SelfAttentionFn(Function):
         return dx, grads_w[0], grads_w[1], grads_w[2], grads_w[3], dsigma, None
 
 
-class ForkFn(Function):
+class ForkFn(TFunction):
     """x -> (x, x) for a tensor with two consumers; the two gradients are summed by the library instead of by autograd's
     implicit accumulation (keeps every full-size element-wise pass on the hot path inside libsgb200)."""
 
@@ -510,8 +689,13 @@ class ForkFn(Function):
             return g1
         return K.axpby(K.as_nhwc(g1), K.as_nhwc(g2))
 
+    @staticmethod
+    def tangent(args, out, tan):
+        t = tan(args[0])
+        return t, t
 
-class PoolFn(Function):
+
+class PoolFn(TFunction):
     """2x2 average pooling of a tensor that is not a ReLU output (no mask in the backward)."""
 
     @staticmethod
@@ -521,3 +705,8 @@ class PoolFn(Function):
     @staticmethod
     def backward(ctx, dy):
         return K.pool2_bwd(K.as_nhwc(dy), 0)
+
+    @staticmethod
+    def tangent(args, out, tan):
+        t = tan(args[0])
+        return PoolFn.apply(t) if t is not None else None

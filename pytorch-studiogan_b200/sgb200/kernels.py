@@ -350,3 +350,48 @@ def adam_ema_step(p, g, m, v, lr, beta1, beta2, eps, step, ema=None, ema_decay=0
 
 def ema_lerp(ema, p, decay):
     L.call("sgb_ema_lerp", L.ptr(ema), L.ptr(p), p.numel(), float(decay), _s())
+
+
+# ---------------------------------------------------------------------------------------------- gradient penalty
+def gp_interpolate(real, fake, alpha):
+    """alpha[b] * real + (1 - alpha[b]) * fake on contiguous fp32 [B, ...] tensors (torch's operation order)."""
+    real, fake = real.contiguous(), fake.contiguous()
+    out = torch.empty_like(real)
+    B = real.shape[0]
+    L.call("sgb_gp_interpolate", L.ptr(real), L.ptr(fake), L.ptr(alpha), L.ptr(out), B, real.numel() // B, _s())
+    return out
+
+
+def gp_sumsq(g):
+    g = g.contiguous()
+    B = g.shape[0]
+    out = torch.empty(B, device=g.device, dtype=torch.float32)
+    L.call("sgb_gp_sumsq", L.ptr(g), L.ptr(out), B, g.numel() // B, _s())
+    return out
+
+
+def gp_seed(g, sumsq):
+    g = g.contiguous()
+    B = g.shape[0]
+    v = torch.empty_like(g)
+    L.call("sgb_gp_seed", L.ptr(g), L.ptr(sumsq), L.ptr(v), B, g.numel() // B, _s())
+    return v
+
+
+def bn_tangent_bwd_reduce(x, a, c, mean, rstd):
+    B, C, H, W, xs = geom(x)
+    sums = torch.empty((5, C), device=x.device, dtype=torch.float32)
+    L.call("sgb_bn_tangent_bwd_reduce", L.ptr(x), xs, L.ptr(a), geom(a)[4], L.ptr(c), geom(c)[4], B * H * W, C, L.ptr(mean),
+           L.ptr(rstd), L.ptr(sums), _s())
+    return sums
+
+
+def bn_tangent_bwd_apply(x, a, c, gamma, mean, rstd, sums, count, use_batch_stats, want_dx=True, want_da=True):
+    B, C, H, W, xs = geom(x)
+    dx = empty_nhwc(B, C, H, W, x.device) if want_dx else None
+    da = empty_nhwc(B, C, H, W, x.device) if want_da else None
+    L.call("sgb_bn_tangent_bwd_apply", L.ptr(x), xs, L.ptr(a), geom(a)[4], L.ptr(c), geom(c)[4], B * H * W, C,
+           L.ptr(gamma) if gamma is not None else None, L.ptr(mean), L.ptr(rstd), L.ptr(sums) if sums is not None else None,
+           float(count), 1 if use_batch_stats else 0, L.ptr(dx) if dx is not None else None, geom(dx)[4] if dx is not None else 0,
+           L.ptr(da) if da is not None else None, geom(da)[4] if da is not None else 0, _s())
+    return dx, da

@@ -35,7 +35,7 @@ class GenBlock(nn.Module):
         self.conv2d2 = MODULES.g_conv2d(in_channels=out_channels, out_channels=out_channels, kernel_size=3, stride=1, padding=1)
 
     def forward(self, x, affine):
-        main, side = A.ForkFn.apply(x)
+        main, side = A.ForkFn.call(x)
         if self.conditional:
             h = self.bn1(main, affine, relu=True, up2=True)
         else:
@@ -44,6 +44,29 @@ class GenBlock(nn.Module):
         h = self.bn2(h, affine, relu=True) if self.conditional else self.bn2(h, relu=True)
         skip = self.conv2d0(side)                               # low resolution; up-sampled inside conv2d2's epilogue
         return self.conv2d2(h, residual=skip, res_up2=True)
+
+
+class _ImageSkipTangent:
+    """Tangent of x0 = [bn0](avg_pool2d(img)) on the 3-channel image, written with tensor ops (a [B,3,H/2,W/2] array):
+    pooling is linear; training-mode BN maps a tangent t to w * r * (t - mean(t) - xhat * mean(xhat * t))."""
+
+    @staticmethod
+    def tangent(args, out, tan):
+        img, bn = args
+        t = tan(img)
+        if t is None:
+            return None
+        t0 = F.avg_pool2d(t, 2)
+        if bn is None:
+            return t0
+        w = bn.weight.view(1, -1, 1, 1) if bn.weight is not None else 1.0
+        if not bn.training:
+            return w * torch.rsqrt(bn.running_var.view(1, -1, 1, 1) + bn.eps) * t0
+        x0 = F.avg_pool2d(img, 2)
+        mu = x0.mean((0, 2, 3), keepdim=True)
+        r = torch.rsqrt(x0.var((0, 2, 3), unbiased=False, keepdim=True) + bn.eps)
+        xh = (x0 - mu) * r
+        return w * r * (t0 - t0.mean((0, 2, 3), keepdim=True) - xh * (xh * t0).mean((0, 2, 3), keepdim=True))
 
 
 class DiscOptBlock(nn.Module):
@@ -63,20 +86,21 @@ class DiscOptBlock(nn.Module):
 
     def forward(self, img):
         """``img``: NCHW fp32 image."""
-        h = self.conv2d1(A.ImageColFn.apply(img), relu=self.apply_d_sn, premasked=self.apply_d_sn)
+        h = self.conv2d1(A.ImageColFn.call(img), relu=self.apply_d_sn, premasked=self.apply_d_sn)
         if not self.apply_d_sn:
             h = self.bn1(h, relu=True)
             h = self.conv2d2(h)
         else:
             h = self.conv2d2(h, mask_input=True)
-        h = A.PoolFn.apply(h)
+        h = A.PoolFn.call(h)
         x0 = F.avg_pool2d(img, 2)                               # 3-channel image: a [B,3,H/2,W/2] tensor op
         if not self.apply_d_sn:
             x0 = self.bn0(x0) if not isinstance(self.bn0, ops.BatchNorm2d) else F.batch_norm(
                 x0, self.bn0.running_mean, self.bn0.running_var, self.bn0.weight, self.bn0.bias,
                 self.bn0.training, self.bn0.momentum, self.bn0.eps)
-        s = self.conv2d0(A.ImageInFn.apply(x0))
-        return A.AddFn.apply(h, s)
+        A.tape_record(_ImageSkipTangent, (img, None if self.apply_d_sn else self.bn0), x0)
+        s = self.conv2d0(A.ImageInFn.call(x0))
+        return A.AddFn.call(h, s)
 
 
 class DiscBlock(nn.Module):
@@ -104,15 +128,15 @@ class DiscBlock(nn.Module):
     def forward(self, x):
         has_sc = self.downsample or self.ch_mismatch
         if self.apply_d_sn:
-            a = A.ReluFn.apply(x)                               # in-place ReLU of the reference: both branches see relu(x)
-            main, side = A.ForkFn.apply(a)
+            a = A.ReluFn.call(x)                               # in-place ReLU of the reference: both branches see relu(x)
+            main, side = A.ForkFn.call(a)
             h = self.conv2d1(main, relu=True, premasked=True)
             skip = self.conv2d0(side) if has_sc else side
             h = self.conv2d2(h, residual=skip, mask_input=True)
         else:
-            main, side = A.ForkFn.apply(x)
+            main, side = A.ForkFn.call(x)
             h = self.conv2d1(self.bn1(main, relu=True))
             h = self.bn2(h, relu=True)
             skip = self.conv2d0(self.bn0(side)) if has_sc else side
             h = self.conv2d2(h, residual=skip)
-        return A.PoolFn.apply(h) if self.downsample else h
+        return A.PoolFn.call(h) if self.downsample else h

@@ -67,9 +67,9 @@ class Generator(nn.Module):
         if self.g_cond_mtd != "W/O":
             if shared_label is None:
                 shared_label = self.shared(label)
-            affines = [A.ToBF16Fn.apply(torch.cat([shared_label, item], 1)) for item in zs[1:]]
+            affines = [A.ToBF16Fn.call(torch.cat([shared_label, item], 1)) for item in zs[1:]]
         else:
-            affines = [A.ToBF16Fn.apply(item) for item in zs[1:]]
+            affines = [A.ToBF16Fn.call(item) for item in zs[1:]]
         S = self.bottom * self.bottom
         act = self.linear0(z0, perm_S=S)
         B = act.shape[0]
@@ -85,7 +85,7 @@ class Generator(nn.Module):
         act = self.bn4(act, relu=True)
         act = self.conv2d5(act)
         self._snb.clear()
-        return A.ImageOutFn.apply(act, 3)
+        return A.ImageOutFn.call(act, 3)
 
 
 class Discriminator(nn.Module):
@@ -128,6 +128,6 @@ class Discriminator(nn.Module):
         for blocklist in self.blocks:
             for block in blocklist:
                 h = block(h)
-        h = A.SumHWFn.apply(h, True)
+        h = A.SumHWFn.call(h, True)
         self._snb.clear()
         return ops.discriminator_head(self, h, label, adc_fake)

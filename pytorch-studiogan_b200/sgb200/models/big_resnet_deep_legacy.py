@@ -54,7 +54,7 @@ class GenBlock(nn.Module):
         self.conv2d4 = MODULES.g_conv2d(in_channels=hid, out_channels=out_channels, kernel_size=1, stride=1, padding=0)
 
     def forward(self, x, affine):
-        main, skip = A.SplitResidualFn.apply(x, self.out_channels)
+        main, skip = A.SplitResidualFn.call(x, self.out_channels)
         h = self.conv2d1(self.bn1(main, affine, relu=True))
         h = self.conv2d2(self.bn2(h, affine, relu=True, up2=self.upsample))
         h = self.conv2d3(self.bn3(h, affine, relu=True))
@@ -118,7 +118,7 @@ class Generator(nn.Module):
             parts.append(shared_label)
         if parts:
             z = torch.cat(parts + [z], 1)
-        affine = A.ToBF16Fn.apply(z)                                  # [B, K, 1, 1] bf16, shared by every cBN
+        affine = A.ToBF16Fn.call(z)                                  # [B, K, 1, 1] bf16, shared by every cBN
         S = self.bottom * self.bottom
         act = self.linear0(affine, perm_S=S)                          # [B, S*C0, 1, 1], features already in (s, c) order
         B = act.shape[0]
@@ -129,7 +129,7 @@ class Generator(nn.Module):
         act = self.bn4(act, relu=True)
         act = self.conv2d5(act)
         self._snb.clear()
-        return A.ImageOutFn.apply(act, 3)
+        return A.ImageOutFn.call(act, 3)
 
 
 class DiscBlock(nn.Module):
@@ -152,16 +152,16 @@ class DiscBlock(nn.Module):
             self.average_pooling = nn.AvgPool2d(2)
 
     def forward(self, x):
-        a0, px = A.DBlockEntryFn.apply(x, self.downsample)
+        a0, px = A.DBlockEntryFn.call(x, self.downsample)
         h = self.conv2d1(a0, relu=True, premasked=True, mask_input=True)
         h = self.conv2d2(h, relu=True, premasked=True, mask_input=True)
         h = self.conv2d3(h, relu=True, premasked=True, mask_input=True)
         if self.downsample:
-            h = A.AvgPoolFn.apply(h, True)
+            h = A.AvgPoolFn.call(h, True)
         skip = px
         if self.learnable_sc:
             c0 = self.conv2d0
-            skip = A.ConcatSkipFn.apply(px, ops._w(c0), c0.bias,
+            skip = A.ConcatSkipFn.call(px, ops._w(c0), c0.bias,
                                         {"sn": getattr(c0, "_sn", None), "do_power_iteration": c0.training,
                                          "sn_cache": getattr(c0, "_sn_cache", None)})
         return self.conv2d4(h, residual=skip, mask_input=not self.downsample)
@@ -236,10 +236,10 @@ class Discriminator(nn.Module):
 
     def forward(self, x, label, eval=False, adc_fake=False):
         self._snb.run()
-        h = self.input_conv(A.ImageColFn.apply(x))                   # 3x3 patches of the image -> K = 32 GEMM
+        h = self.input_conv(A.ImageColFn.call(x))                   # 3x3 patches of the image -> K = 32 GEMM
         for blocklist in self.blocks:
             for block in blocklist:
                 h = block(h)
-        h = A.SumHWFn.apply(h, True)                                  # relu + sum over (H, W), fp32 [B, C]
+        h = A.SumHWFn.call(h, True)                                  # relu + sum over (H, W), fp32 [B, C]
         self._snb.clear()
         return ops.discriminator_head(self, h, label, adc_fake)

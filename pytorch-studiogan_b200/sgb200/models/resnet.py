@@ -56,7 +56,7 @@ class Generator(nn.Module):
         affines = None
         if self.g_cond_mtd != "W/O":
             onehot = F.one_hot(label, num_classes=self.num_classes).to(torch.float32)
-            affines = A.ToBF16Fn.apply(onehot)
+            affines = A.ToBF16Fn.call(onehot)
         S = self.bottom * self.bottom
         act = self.linear0(z, perm_S=S)
         B = act.shape[0]
@@ -67,7 +67,7 @@ class Generator(nn.Module):
         act = self.bn4(act, relu=True)
         act = self.conv2d5(act)
         self._snb.clear()
-        return A.ImageOutFn.apply(act, 3)
+        return A.ImageOutFn.call(act, 3)
 
 
 class Discriminator(nn.Module):
@@ -110,6 +110,6 @@ class Discriminator(nn.Module):
         for blocklist in self.blocks:
             for block in blocklist:
                 h = block(h)
-        h = A.SumHWFn.apply(h, True)
+        h = A.SumHWFn.call(h, True)
         self._snb.clear()
         return ops.discriminator_head(self, h, label, adc_fake)

@@ -61,3 +61,14 @@ def d_wasserstein(d_logit_real, d_logit_fake, DDP=False):
 
 def g_wasserstein(d_logit_fake, DDP=False):
     return -torch.mean(d_logit_fake)
+
+
+def cal_deriv(inputs, outputs, device=None):
+    from . import gp
+    return gp.cal_deriv(inputs, outputs, device)
+
+
+def cal_grad_penalty(real_images, real_labels, fake_images, discriminator, device=None, alpha=None):
+    """src/utils/losses.py:301-316; see utils/gp.py for how the second-order term is evaluated."""
+    from . import gp
+    return gp.cal_grad_penalty(real_images, real_labels, fake_images, discriminator, device, alpha)

@@ -54,7 +54,7 @@ class _ConvBase(nn.Conv2d):
                "premasked": premasked, "mask_input": mask_input, "res_up2": res_up2,
                "sn": getattr(self, "_sn", None), "do_power_iteration": self.training,
                "sn_cache": getattr(self, "_sn_cache", None)}
-        return A.ConvFn.apply(x, _w(self), self.bias, residual, cfg)
+        return A.ConvFn.call(x, _w(self), self.bias, residual, cfg)
 
     def _forward_image(self, x_col, residual, relu, premasked):
         """3 -> C convolution on an image: ``x_col`` is the [B, 32, H, W] patch tensor from ImageColFn and the layer runs
@@ -72,7 +72,7 @@ class _ConvBase(nn.Conv2d):
             W = W / sigma
         Wp = W.permute(0, 2, 3, 1).reshape(W.shape[0], 27)
         cfg = {"KH": 1, "KW": 1, "pad": 0, "relu": relu, "premasked": premasked, "sn": None}
-        return A.ConvFn.apply(x_col, Wp, self.bias, residual, cfg)
+        return A.ConvFn.call(x_col, Wp, self.bias, residual, cfg)
 
 
 class Conv2d(_ConvBase):
@@ -95,14 +95,14 @@ class _LinearBase(nn.Linear):
 
     def forward(self, x, out_fp32=False, perm_S=1):
         if x.dim() == 2:
-            x = A.ToBF16Fn.apply(x) if x.dtype != torch.bfloat16 else x.view(x.shape[0], x.shape[1], 1, 1)
+            x = A.ToBF16Fn.call(x) if x.dtype != torch.bfloat16 else x.view(x.shape[0], x.shape[1], 1, 1)
         bias = self.bias
         if bias is not None and perm_S > 1:
             bias = bias.view(-1, perm_S).t().reshape(-1)
         cfg = {"KH": 1, "KW": 1, "pad": 0, "relu": False, "out_fp32": out_fp32, "perm_S": perm_S,
                "sn": getattr(self, "_sn", None), "do_power_iteration": self.training,
                "sn_cache": getattr(self, "_sn_cache", None)}
-        return A.ConvFn.apply(x, _w(self), bias, None, cfg)
+        return A.ConvFn.call(x, _w(self), bias, None, cfg)
 
 
 class Linear(_LinearBase):
@@ -187,7 +187,7 @@ class BatchNorm2d(nn.BatchNorm2d):
         cfg = {"mode": mode, "relu": relu, "up2": up2, "use_batch_stats": training, "track": track,
                "momentum": self.momentum if self.momentum is not None else 0.1, "eps": self.eps,
                "group": self.sync_group if training else None}
-        return A.BNActFn.apply(x, g, b, self.running_mean, self.running_var, cfg)
+        return A.BNActFn.call(x, g, b, self.running_mean, self.running_var, cfg)
 
 
 def batchnorm_2d(in_features, eps=1e-4, momentum=0.1, affine=True):
@@ -235,7 +235,7 @@ class SelfAttention(nn.Module):
         mods = (self.conv1x1_theta, self.conv1x1_phi, self.conv1x1_g, self.conv1x1_attn)
         cfgs = tuple({"sn": getattr(m, "_sn", None), "do_power_iteration": m.training, "sn_cache": getattr(m, "_sn_cache", None)}
                      for m in mods)
-        return A.SelfAttentionFn.apply(x, _w(mods[0]), _w(mods[1]), _w(mods[2]), _w(mods[3]), self.sigma, cfgs)
+        return A.SelfAttentionFn.call(x, _w(mods[0]), _w(mods[1]), _w(mods[2]), _w(mods[3]), self.sigma, cfgs)
 
 
 def init_weights(modules, initialize):
@@ -289,6 +289,24 @@ def _head_weight(module):
     return W / sigma
 
 
+class _HeadTangent:
+    """Tangent of the adversarial logit w.r.t. the pooled features (the head is linear in h): same effective weights,
+    same embedding rows, no bias, no new power iteration."""
+
+    @staticmethod
+    def tangent(args, out, tan):
+        h, w_eff, emb, mtd = args
+        th = tan(h)
+        if th is None:
+            return None
+        if mtd not in ("W/O", "PD"):
+            raise NotImplementedError("gradient penalty with d_cond_mtd=%s" % mtd)
+        t = torch.squeeze(F.linear(th, w_eff))
+        if emb is not None:
+            t = t + torch.sum(emb * th, 1)
+        return t
+
+
 def head_linear(module, h):
     return F.linear(h, _head_weight(module), module.bias)
 
@@ -299,12 +317,15 @@ def discriminator_head(D, h, label, adc_fake=False):
     class conditioning (PD / AC / 2C / D2DCE / MD / MH), TAC / ADC extras, and the 12-key result dict."""
     out = dict.fromkeys(["embed", "proxy", "cls_output", "mi_embed", "mi_proxy", "mi_cls_output",
                          "info_discrete_c_logits", "info_conti_mu", "info_conti_var"])
-    adv = torch.squeeze(head_linear(D.linear1, h))
+    w_eff = _head_weight(D.linear1)
+    adv = torch.squeeze(F.linear(h, w_eff, D.linear1.bias))
     if D.aux_cls_type == "ADC":
         label = label * 2 + 1 if adc_fake else label * 2
     mtd = D.d_cond_mtd
+    emb = None
     if mtd == "PD":
-        adv = adv + torch.sum(D.embedding(label) * h, 1)
+        emb = D.embedding(label)
+        adv = adv + torch.sum(emb * h, 1)
     elif mtd == "AC":
         if D.normalize_d_embed:
             h = F.normalize(h, dim=1)
@@ -326,6 +347,7 @@ def discriminator_head(D, h, label, adc_fake=False):
             if D.normalize_d_embed:
                 mi_embed, mi_proxy = F.normalize(mi_embed, dim=1), F.normalize(mi_proxy, dim=1)
             out["mi_embed"], out["mi_proxy"] = mi_embed, mi_proxy
+    A.tape_record(_HeadTangent, (h, w_eff, emb, mtd), adv)
     out.update({"h": h, "adv_output": adv, "label": label})
     return out
 

@@ -171,6 +171,43 @@ def golden_resfamily(tag, family, conv_dim, attn, g_sn, d_sn, g_cond, d_cond, ad
     print(tag, "keys", len(out), "d_loss", float(d_loss), "g_loss", float(g_loss))
 
 
+def golden_gp(tag, family, conv_dim, d_sn, d_cond, classes=5, B=8, img_size=32, depth=1):
+    """losses.cal_grad_penalty (src/utils/losses.py:301-316) of the reference discriminators: penalty value, the first
+    gradient g = d(sum adv)/d(x_hat), and dP/dtheta from the reference's double backward.  alpha is captured by re-seeding
+    torch's host RNG right before the call."""
+    import copy
+    torch.manual_seed(777)
+    M = modules(g_sn=True, d_sn=d_sn, cbn=True)
+    mod = {"big_resnet": rbig, "resnet": rres, "deep": rdeep}[family]
+    D = mod.Discriminator(img_size=img_size, d_conv_dim=conv_dim, apply_d_sn=d_sn, apply_attn=False, attn_d_loc=[1], d_cond_mtd=d_cond,
+                          aux_cls_type="W/O", d_embed_dim="N/A", normalize_d_embed=False, num_classes=classes, d_init="ortho",
+                          d_depth=depth if family == "deep" else "N/A", mixed_precision=False, MODULES=M, MODEL=MODEL)
+    D.train()
+    out = {}
+    out.update(sd_np(D, "D0/"))
+    real = torch.rand(B, 3, img_size, img_size) * 2 - 1
+    fake = torch.tanh(torch.randn(B, 3, img_size, img_size))
+    y_real = torch.randint(0, classes, (B,))
+    torch.manual_seed(99)
+    alpha = torch.rand(B, 1)
+    # first gradient on a copy (every forward moves u / running statistics)
+    D2 = copy.deepcopy(D)
+    a4 = alpha.view(B, 1, 1, 1)
+    x_hat = (a4 * real + (1 - a4) * fake).requires_grad_(True)
+    adv2 = D2(x_hat, y_real, eval=False)["adv_output"]
+    g = rlosses.cal_deriv(inputs=x_hat, outputs=adv2, device="cpu")
+    out.update({"x_hat": x_hat.detach().numpy(), "adv_hat": adv2.detach().numpy(), "g": g.detach().numpy()})
+    torch.manual_seed(99)
+    gp = rlosses.cal_grad_penalty(real_images=real, real_labels=y_real, fake_images=fake, discriminator=D, device="cpu")
+    gp.backward()
+    out.update({"real": real.numpy(), "fake": fake.numpy(), "y_real": y_real.numpy(), "alpha": alpha.numpy(), "gp": gp.detach().numpy()})
+    for k, p in D.named_parameters():
+        out["Dgrad/" + k] = (p.grad.detach().numpy().copy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32))
+    out.update(sd_np(D, "D1/", True))
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
+    print(tag, "keys", len(out), "gp", float(gp), "|g| per sample", g.flatten(1).norm(dim=1)[:4].tolist())
+
+
 def golden_metrics():
     rng = np.random.RandomState(0)
     out = {}
@@ -235,3 +272,6 @@ if __name__ == "__main__":
     golden_resfamily("resnet32_cbn_c16", "resnet", 16, False, False, True, "cBN", "PD", "hinge", z_dim=32)
     golden_resfamily("wgan32_bn_c16", "resnet", 16, False, False, False, "W/O", "W/O", "wasserstein", z_dim=32)
     golden_metrics()
+    golden_gp("gp_resnet32_bn_c16", "resnet", 16, False, "W/O")           # the WGAN-GP config's discriminator (BatchNorm, no SN)
+    golden_gp("gp_resnet32_sn_c16_pd", "resnet", 16, True, "PD")
+    golden_gp("gp_deep32_sn_c8_pd", "deep", 8, True, "PD")

@@ -445,7 +445,7 @@ def test_arena_adam_matches_torch_adam_and_state_dict_format(golden_dir):
     assert set(sd["state"].keys()) == set(rsd["state"].keys())
     for i in sd["state"]:
         np.testing.assert_allclose(sd["state"][i]["exp_avg_sq"].cpu().numpy(), rsd["state"][i]["exp_avg_sq"].cpu().numpy(),
-                                   rtol=1e-5, atol=1e-12)
+                                   rtol=1e-4, atol=1e-12)
         assert int(sd["state"][i]["step"]) == int(rsd["state"][i]["step"]) == 3
     ref2 = torch.optim.Adam(Dref.parameters(), lr=2e-4, betas=(0.0, 0.999), eps=1e-6)
     ref2.load_state_dict(sd)                                       # our state loads into torch's optimiser ...
@@ -454,5 +454,96 @@ def test_arena_adam_matches_torch_adam_and_state_dict_format(golden_dir):
     assert opt2.step_count == 3 and opt2.param_groups[0]["lr"] == 2e-4
     sd2 = opt2.state_dict()
     for i in sd["state"]:
-        np.testing.assert_allclose(sd2["state"][i]["exp_avg"].cpu().numpy(), rsd["state"][i]["exp_avg"].cpu().numpy(), rtol=1e-5,
+        np.testing.assert_allclose(sd2["state"][i]["exp_avg"].cpu().numpy(), rsd["state"][i]["exp_avg"].cpu().numpy(), rtol=1e-4,
                                    atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------ gradient penalty
+def test_gp_kernels_interpolate_bit_exact_norm_seed_and_bn_tangent_vs_oracle(golden_dir):
+    from oracle import studiogan_oracle as O
+    from sgb200 import kernels as K
+    dev = _cuda()
+    g = np.load(os.path.join(golden_dir, "gp_resnet32_bn_c16.npz"))
+    real, fake, alpha = (torch.from_numpy(g[k]).to(dev) for k in ("real", "fake", "alpha"))
+    x_hat = K.gp_interpolate(real, fake, alpha.reshape(-1))
+    assert np.array_equal(x_hat.cpu().numpy(), g["x_hat"])                       # same operation order as torch: bit exact
+    gr = torch.from_numpy(g["g"]).to(dev)
+    ss = K.gp_sumsq(gr)
+    n_ref = torch.from_numpy(g["g"]).flatten(1).norm(dim=1)
+    np.testing.assert_allclose(ss.sqrt().cpu().numpy(), n_ref.numpy(), rtol=1e-5)
+    v = K.gp_seed(gr, ss)
+    v_ref = (2 * (n_ref - 1) / (len(n_ref) * n_ref)).view(-1, 1, 1, 1) * torch.from_numpy(g["g"])
+    np.testing.assert_allclose(v.cpu().numpy(), v_ref.numpy(), rtol=1e-4, atol=1e-9)
+    # batch-norm tangent map and its (x, a, gamma) derivatives vs the oracle's closed forms (bf16 inputs, fp32 sums)
+    torch.manual_seed(3)
+    B, C, H, W = 4, 24, 12, 12
+    x, a, c = (torch.randn(B, C, H, W).bfloat16().float() for _ in range(3))
+    gamma = torch.rand(C) + 0.5
+    eps = 1e-4
+    nh = lambda t: t.to(dev).bfloat16().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)   # noqa: E731
+    xd, ad, cd = nh(x), nh(a), nh(c)
+    from sgb200 import autograd_ops as A
+    mean = x.mean((0, 2, 3)).to(dev)
+    rstd = torch.rsqrt(x.var((0, 2, 3), unbiased=False) + eps).to(dev)
+    cfg = {"count": float(B * H * W), "use_batch_stats": True, "group": None}
+    xd.requires_grad_(True); ad.requires_grad_(True)
+    gd = gamma.to(dev).requires_grad_(True)
+    t = A.BNTangentFn.apply(xd, ad, gd, mean, rstd, cfg)
+    assert l2_err(t, O.bn_tangent(x, a, gamma, eps)) < 1e-2
+    t.backward(cd)
+    dx, da, dgamma = O.bn_tangent_backward(x, a, c, gamma, eps)
+    assert l2_err(xd.grad, dx) < 2e-2 and l2_err(ad.grad, da) < 1e-2 and l2_err(gd.grad, dgamma) < 1e-2
+
+
+GP_CASES = {
+    "gp_resnet32_bn_c16": dict(family="resnet", conv_dim=16, d_sn=False, d_cond="W/O"),
+    "gp_resnet32_sn_c16_pd": dict(family="resnet", conv_dim=16, d_sn=True, d_cond="PD"),
+    "gp_deep32_sn_c8_pd": dict(family="big_resnet_deep_legacy", conv_dim=8, d_sn=True, d_cond="PD"),
+}
+
+
+@pytest.mark.parametrize("tag", list(GP_CASES))
+def test_grad_penalty_vs_reference_golden(golden_dir, tag):
+    """losses.cal_grad_penalty through the CUDA path (primal pass, input-gradient pass, tangent pass; utils/gp.py) against
+    the reference's double-backward numbers (src/utils/losses.py:301-316) with the same alpha.
+    Stated tolerance: first gradient g relative L2 <= 4e-2; penalty value 5e-2 relative (it is a function of ||g_b||);
+    dP/dtheta (second-order, bf16 storage): worst parameter relative L2 <= 0.35, median <= 0.1, cosine >= 0.93 --
+    u / running statistics after the pass 1e-2."""
+    import importlib
+    from sgb200 import config as C
+    from sgb200.utils import losses
+    dev = _cuda()
+    c = GP_CASES[tag]
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    mod = importlib.import_module("sgb200.models." + c["family"])
+    M = C.make_modules(True, c["d_sn"], "cBN", c["family"])
+    MODEL = C._Section(info_type="N/A", g_info_injection="N/A")
+    D = mod.Discriminator(img_size=32, d_conv_dim=c["conv_dim"], apply_d_sn=c["d_sn"], apply_attn=False, attn_d_loc=[1],
+                          d_cond_mtd=c["d_cond"], aux_cls_type="W/O", d_embed_dim="N/A", normalize_d_embed=False, num_classes=5,
+                          d_init="ortho", d_depth=1 if "deep" in c["family"] else "N/A", mixed_precision=False, MODULES=M, MODEL=MODEL)
+    D.load_state_dict({k[3:]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith("D0/")}, strict=True)
+    D = D.to(dev).train()
+    real, fake, yr = (torch.from_numpy(g[k]).to(dev) for k in ("real", "fake", "y_real"))
+    alpha = torch.from_numpy(g["alpha"])
+    # first gradient alone (a copy of D: every forward moves u / running statistics)
+    import copy
+    from sgb200.utils import gp as gp_mod
+    D2 = copy.deepcopy(D)
+    x_hat = torch.from_numpy(g["x_hat"]).to(dev).requires_grad_(True)
+    adv = D2(x_hat, yr)["adv_output"]
+    assert l2_err(adv, torch.from_numpy(g["adv_hat"])) < 4e-2
+    g1 = gp_mod.cal_deriv(x_hat, adv)
+    assert l2_err(g1, torch.from_numpy(g["g"])) < 4e-2
+    assert all(p.grad is None for p in D2.parameters())
+    pen = losses.cal_grad_penalty(real_images=real, real_labels=yr, fake_images=fake, discriminator=D, device=dev, alpha=alpha)
+    assert abs(float(pen.detach()) - float(g["gp"])) <= 5e-2 * abs(float(g["gp"])), (float(pen.detach()), float(g["gp"]))
+    pen.backward()
+    for p in D.parameters():
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    worst, median, cos = _grad_errors(D, g, "Dgrad/")
+    print(tag, "gp", float(pen.detach()), float(g["gp"]), "worst", worst, "median", median, "cos", cos)
+    assert worst[0] <= 0.35 and median <= 0.1 and cos[0] >= 0.93, (worst, median, cos)
+    for n, b in D.named_buffers():
+        if "weight_u" in n or "running_" in n:
+            assert rel_err(b, torch.from_numpy(g["D1/" + n])) < 1e-2, n

@@ -114,3 +114,61 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU / PyTorch fallback"):
         L.load()
+
+
+def test_bn_tangent_formulas_and_reverse_over_forward_identity():
+    """(1) The oracle's closed forms for the tangent of a training-mode batch norm and its (x, a, gamma) derivatives (what the
+    sgb_bn_tangent_* kernels compute) equal torch autograd's JVP / double backward in fp64.
+    (2) dP/dtheta of the gradient penalty obtained by reverse-over-forward (utils/gp.py) equals the reference's
+    double-backward formulation (src/utils/losses.py:268-316) on a conv -> BN -> ReLU -> conv -> sum -> linear discriminator."""
+    import torch.nn.functional as F
+    from oracle import studiogan_oracle as O
+    torch.manual_seed(0)
+    dd = torch.float64
+    x = torch.randn(4, 3, 5, 5, dtype=dd, requires_grad=True)
+    a = torch.randn(4, 3, 5, 5, dtype=dd, requires_grad=True)
+    c = torch.randn(4, 3, 5, 5, dtype=dd)
+    gamma = (torch.rand(3, dtype=dd) + 0.5).requires_grad_(True)
+    beta = torch.zeros(3, dtype=dd)
+    eps = 1e-4
+    bn = lambda t: F.batch_norm(t, None, None, gamma, beta, True, 0.1, eps)                      # noqa: E731
+    _, jvp = torch.autograd.functional.jvp(bn, x, a)
+    t = O.bn_tangent(x, a, gamma, eps)
+    assert float((t - jvp).abs().max()) < 1e-10                                                 # closed form == torch's JVP
+    gx, ga, gg = torch.autograd.grad((t * c).sum(), (x, a, gamma))                              # autograd through the closed form
+    dx, da, dgamma = O.bn_tangent_backward(x.detach(), a.detach(), c, gamma.detach(), eps)
+    assert float((dx - gx).abs().max()) < 1e-9 and float((da - ga).abs().max()) < 1e-9 and float((dgamma - gg).abs().max()) < 1e-9
+
+    w1 = (torch.randn(6, 3, 3, 3, dtype=dd) * 0.3).requires_grad_(True)
+    w2 = (torch.randn(4, 6, 3, 3, dtype=dd) * 0.3).requires_grad_(True)
+    g1 = (torch.rand(6, dtype=dd) + 0.5).requires_grad_(True)
+    b1 = torch.zeros(6, dtype=dd, requires_grad=True)
+    wl = torch.randn(1, 4, dtype=dd, requires_grad=True)
+    params = (w1, w2, g1, wl)
+
+    def disc(img):
+        h = F.conv2d(img, w1, padding=1)
+        h = F.relu(F.batch_norm(h, None, None, g1, b1, True, 0.1, eps))
+        h = F.conv2d(h, w2, padding=1)
+        return F.linear(F.relu(h).sum((2, 3)), wl).squeeze(1)
+
+    real, fake = torch.randn(4, 3, 6, 6, dtype=dd), torch.randn(4, 3, 6, 6, dtype=dd)
+    alpha = torch.rand(4, 1, dtype=dd)
+    gp = O.grad_penalty(disc, real, fake, alpha)
+    ref = torch.autograd.grad(gp, params)
+    # reverse over forward, exactly as utils/gp.py: g (no graph) -> seed v -> tangent pass -> backward
+    a4 = alpha.view(4, 1, 1, 1)
+    x_hat = (a4 * real + (1 - a4) * fake).requires_grad_(True)
+    (g,) = torch.autograd.grad(disc(x_hat).sum(), x_hat)
+    n = g.flatten(1).norm(dim=1)
+    assert abs(float(((n - 1) ** 2).mean()) - float(gp)) < 1e-10
+    v = (2 * (n - 1) / (4 * n)).view(4, 1, 1, 1) * g
+    h = F.conv2d(x_hat, w1, padding=1)
+    th = F.conv2d(v, w1, padding=1)
+    y = F.relu(F.batch_norm(h, None, None, g1, b1, True, 0.1, eps))
+    ty = O.bn_tangent(h, th, g1, eps) * (y > 0)
+    h2, th2 = F.conv2d(y, w2, padding=1), F.conv2d(ty, w2, padding=1)
+    t_adv = F.linear((th2 * (h2 > 0)).sum((2, 3)), wl).squeeze(1)
+    got = torch.autograd.grad(t_adv.sum(), params)
+    for r_, g_ in zip(ref, got):
+        assert float((r_ - g_).abs().max()) < 1e-8 * (1 + float(r_.abs().max()))

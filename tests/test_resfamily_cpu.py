@@ -108,3 +108,40 @@ def test_module_keys_and_seeded_init_match_reference(golden_dir, tag):
             if k.endswith("sigma"):
                 continue
             np.testing.assert_array_equal(sd[k].numpy(), g[prefix + k], err_msg=k)
+
+
+GP_CASES = {
+    "gp_resnet32_bn_c16": dict(family="resnet", conv_dim=16, d_sn=False, d_cond="W/O"),
+    "gp_resnet32_sn_c16_pd": dict(family="resnet", conv_dim=16, d_sn=True, d_cond="PD"),
+    "gp_deep32_sn_c8_pd": dict(family="deep", conv_dim=8, d_sn=True, d_cond="PD"),
+}
+
+
+@pytest.mark.parametrize("tag", list(GP_CASES))
+def test_oracle_grad_penalty_matches_reference(golden_dir, tag):
+    """O.grad_penalty over the oracle discriminators == the reference's cal_grad_penalty (src/utils/losses.py:301-316):
+    interpolates (bit exact), penalty value, and dP/dtheta from the double backward."""
+    c = GP_CASES[tag]
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    sdD = load_sd(g, "D0/", grad=True)
+    real, fake, yr = torch.from_numpy(g["real"]), torch.from_numpy(g["fake"]), torch.from_numpy(g["y_real"])
+    alpha = torch.from_numpy(g["alpha"])
+    a4 = alpha.view(-1, 1, 1, 1)
+    assert np.array_equal((a4 * real + (1 - a4) * fake).numpy(), g["x_hat"])
+
+    def disc(x):
+        if c["family"] == "deep":
+            return O.deep_discriminator(sdD, x, yr, img_size=32, d_conv_dim=c["conv_dim"], d_depth=1)[0]
+        return O.res_discriminator(sdD, x, yr, 32, c["conv_dim"], cond=c["d_cond"])[0]
+    gp = O.grad_penalty(disc, real, fake, alpha)
+    np.testing.assert_allclose(gp.item(), g["gp"], rtol=2e-4)
+    gp.backward()
+    gmax = max(np.abs(g[k]).max() for k in g.files if k.startswith("Dgrad/"))
+    for k in g.files:
+        if k.startswith("Dgrad/"):
+            got = sdD[k[6:]].grad
+            got = got.numpy() if got is not None else np.zeros_like(g[k])
+            assert np.abs(got - g[k]).max() <= 1e-2 * (1e-3 * gmax + np.abs(g[k]).max()), k
+    for k in g.files:
+        if k.startswith("D1/") and ("weight_u" in k or "running_" in k):
+            np.testing.assert_allclose(sdD[k[3:]].detach().numpy(), g[k], rtol=2e-4, atol=1e-5, err_msg=k)
