@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--config", default=os.path.join(PKG, "configs", "BigGAN-Deep-256res.yaml"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fid", action="store_true", help="skip the FID-50k evaluation timing (N = 1 only)")
+    ap.add_argument("--fid-num", type=int, default=50000)
     ap.add_argument("--cpu-batch", type=int, default=1)
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = min(32, host cores): more threads only add contention for these layer sizes")
     return ap.parse_args()
@@ -167,6 +169,42 @@ def timed(worker, steps, world, read_losses):
     return float(ms) / steps, losses
 
 
+def fid_eval_seconds(worker, cfgs, device, num_eval, batch):
+    """BASELINE metric, second half: wall seconds of one FID-N evaluation (WORKER.evaluate: N generated images through
+    G_ema -> quantise/resize/normalise -> InceptionV3 -> IS + FID), preceded by the reference-statistics pass over N
+    synthetic uint8-valued reference images.  Inception weights are seeded (the pretrained file cannot be downloaded
+    here), which changes no shape or FLOP."""
+    from sgb200.metrics import features, fid
+    from sgb200.metrics.preparation import LoadEvalModel
+    ev = LoadEvalModel("InceptionV3_tf", "legacy", 1, False, device)
+    gen = torch.Generator(device=device).manual_seed(1234)
+    S = cfgs.DATA.img_size
+
+    def ref_batches():
+        for i in range(0, num_eval, batch):
+            n = min(batch, num_eval - i)
+            yield torch.randint(0, 256, (n, 3, S, S), generator=gen, device=device).float()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rf, _ = features.stack_real_features(ref_batches(), ev, False, device)
+    mu, sigma = fid.calculate_moments(rf)
+    torch.cuda.synchronize()
+    t_ref = time.perf_counter() - t0
+    worker.eval_model, worker.mu, worker.sigma, worker.num_eval = ev, mu, sigma, num_eval
+    bs = cfgs.OPTIMIZATION.batch_size
+    cfgs.OPTIMIZATION.batch_size = batch
+    try:
+        t0 = time.perf_counter()
+        worker.evaluate(step=0, metrics=["is", "fid"], writing=False, training=True)
+        torch.cuda.synchronize()
+        t_eval = time.perf_counter() - t0
+    finally:
+        cfgs.OPTIMIZATION.batch_size = bs
+    m = worker.last_metrics or {}
+    return {"seconds": t_eval, "ref_stats_seconds": t_ref, "num_eval": num_eval, "batch": batch, "img_per_s": num_eval / t_eval,
+            "FID": m.get("FID"), "IS": m.get("IS"), "inception_weights": "seeded (pretrained FID weights unavailable offline)"}
+
+
 def cpu_step_images_per_sec(config_path, batch, threads, n_steps=1):
     """The reference step restated by the oracle (fp32 CPU torch): 2 discriminator updates + 1 generator update with Adam,
     BigGAN-Deep 256x256, on ``threads`` host threads.  A bounded sample: ``batch`` images per step."""
@@ -285,15 +323,16 @@ def main():
         prof_wall_ms = (time.perf_counter() - w0) * 1e3
         _lib.PROFILE["enabled"] = False
         agg, by_tag = {}, {}
-        for tag, flops, e0, e1 in _lib.PROFILE["events"]:
+        for tag, flops, e0, e1, nbytes in _lib.PROFILE["events"]:
             ms = e0.elapsed_time(e1)
             kind = tag.split(" ")[0]
-            a = agg.setdefault(kind, [0.0, 0.0, 0])
-            a[0] += ms; a[1] += flops; a[2] += 1
-            t = by_tag.setdefault(tag, [0.0, 0.0, 0])
-            t[0] += ms; t[1] += flops; t[2] += 1
+            a = agg.setdefault(kind, [0.0, 0.0, 0, 0.0])
+            a[0] += ms; a[1] += flops; a[2] += 1; a[3] += nbytes
+            t = by_tag.setdefault(tag, [0.0, 0.0, 0, 0.0])
+            t[0] += ms; t[1] += flops; t[2] += 1; t[3] += nbytes
         _lib.PROFILE["events"] = []
-        prof = {k: {"ms": v[0], "tflops": (v[1] / (v[0] * 1e-3) * 1e-12) if v[0] > 0 and v[1] > 0 else None, "launches": v[2], "flop": v[1]}
+        prof = {k: {"ms": v[0], "tflops": (v[1] / (v[0] * 1e-3) * 1e-12) if v[0] > 0 and v[1] > 0 else None, "launches": v[2], "flop": v[1],
+                    "gbytes": v[3] * 1e-9, "gb_per_s": (v[3] / (v[0] * 1e-3) * 1e-9) if v[0] > 0 and v[3] > 0 else None}
                 for k, v in agg.items()}
         prof_top = [{"tag": k, "ms": round(v[0], 3), "n": v[2], "tflops": round(v[1] / (v[0] * 1e-3) * 1e-12, 1) if v[1] > 0 else None}
                     for k, v in sorted(by_tag.items(), key=lambda kv: -kv[1][0])[:40]]
@@ -301,7 +340,7 @@ def main():
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             with open(os.path.join(ROOT, "gpurun_out", "kernel_breakdown_n%d_b%d.json" % (world, global_batch)), "w") as fh:
                 json.dump({"wall_ms_of_profiled_step": prof_wall_ms, "sum_ms": sum(v[0] for v in agg.values()),
-                           "by_kind": prof, "by_tag": [{"tag": k, "ms": v[0], "n": v[2], "flop": v[1]} for k, v in
+                           "by_kind": prof, "by_tag": [{"tag": k, "ms": v[0], "n": v[2], "flop": v[1], "bytes": v[3]} for k, v in
                                                        sorted(by_tag.items(), key=lambda kv: -kv[1][0])]}, fh, indent=1)
     except Exception as ex:  # accounting must never take the bench line down
         prof = {"error": repr(ex)}
@@ -316,6 +355,13 @@ def main():
         h2d = world * per_rank * n_items * (3 * S * S * 4 + 8)
         e2e = {"value": global_batch * opt.acml_steps / (ms_e2e * 1e-3), "unit": "img/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e2e}
+
+    fid50k = None
+    if not args.no_fid and world == 1:
+        try:
+            fid50k = fid_eval_seconds(worker, cfgs, device, args.fid_num, min(256, per_rank))
+        except Exception as ex:  # the evaluation timing must never take the bench line down
+            fid50k = {"error": repr(ex)}
 
     if rank != 0:
         if world > 1:
@@ -358,7 +404,8 @@ def main():
             "config": {"workload": workload, "global_batch": global_batch, "per_gpu_batch": per_rank, "img_size": S,
                        "d_updates_per_step": opt.d_updates_per_step, "acml_steps": opt.acml_steps, "parallelism": "dp%d" % world,
                        "l2": "per-step working set (tens of GB of activations) >> 126 MB L2; no explicit flush needed"},
-            "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary()}
+            "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "fid50k": fid50k,
+            "clocks": sampler.summary()}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -81,7 +81,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
   if (use_batch_stats) {
     mean = sum[c] / count;
     var = fmaxf(sumsq[c] / count - mean * mean, 0.f);
-    if (track && running_mean) {
+    if (track && running_mean && blockIdx.y == 0) {
       const float unbiased = count > 1.f ? var * (count / (count - 1.f)) : var;
       running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
@@ -91,9 +91,11 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
     var = running_var[c];
   }
   const float rstd = rsqrtf(var + eps);
-  mean_out[c] = mean;
-  rstd_out[c] = rstd;
-  for (int b = 0; b < nb; ++b) {
+  if (blockIdx.y == 0) {
+    mean_out[c] = mean;
+    rstd_out[c] = rstd;
+  }
+  for (int b = blockIdx.y; b < nb; b += gridDim.y) {   // images spread over blockIdx.y: no 256-deep serial loop for cBN
     float g = 1.f, be = 0.f;
     if (mode == 0) { g = 1.f + gain[(size_t)b * C + c]; be = bias[(size_t)b * C + c]; }
     else if (mode == 1) { g = gain[c]; be = bias[c]; }
@@ -397,7 +399,7 @@ extern "C" int sgb_bn_finalize(const float* sum, const float* sumsq, float count
   SGB_REQUIRE(C > 0 && nb > 0 && mean && rstd && scale && shift);
   SGB_REQUIRE(use_batch_stats ? (sum && sumsq && count > 0.f) : (running_mean && running_var));
   SGB_REQUIRE(mode == 2 || (gain && bias));
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sum, sumsq, count, running_mean, running_var, momentum, eps,
+  bn_finalize_kernel<<<dim3((C + 127) / 128, nb < 128 ? nb : 128), 128, 0, stream>>>(sum, sumsq, count, running_mean, running_var, momentum, eps,
                                                           use_batch_stats, track, mode, gain, bias, nb, C, mean, rstd, scale,
                                                           shift);
   SGB_LAUNCH_CHECK();

@@ -148,7 +148,7 @@ _tls = threading.local()
 PROFILE = {"enabled": False, "events": []}
 
 
-def call(name, *args, tag=None, flops=0.0):
+def call(name, *args, tag=None, flops=0.0, nbytes=0.0):
     lib = load()
     if getattr(_tls, "device", None) is None:
         # first library call on this host thread (e.g. an autograd worker): bind the thread to torch's current device
@@ -160,7 +160,7 @@ def call(name, *args, tag=None, flops=0.0):
         e0.record()
         rc = getattr(lib, name)(*args)
         e1.record()
-        PROFILE["events"].append((tag or name, flops, e0, e1))
+        PROFILE["events"].append((tag or name, flops, e0, e1, nbytes))
     else:
         rc = getattr(lib, name)(*args)
     LAUNCHES[0] += 1

@@ -120,6 +120,11 @@ def sn_power_iter(W, u, v, sigma, ws, eps, do_power_iteration):
            1 if do_power_iteration else 0, _s())
 
 
+def _nb(*ts):
+    """Algorithmic bytes of an element-wise launch: every operand read or written once (profile accounting only)."""
+    return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
+
+
 def pad8(c):
     return (c + 7) // 8 * 8
 
@@ -147,7 +152,7 @@ def sn_backward(G, W, u, v, sigma, Cout, Cin, taps, perm_S=1):
 def bn_stats(x):
     B, C, H, W, cs = geom(x)
     s = torch.empty((2, C), device=x.device, dtype=torch.float32)
-    L.call("sgb_bn_stats", L.ptr(x), B * H * W, C, cs, L.ptr(s[0]), L.ptr(s[1]), _s())
+    L.call("sgb_bn_stats", L.ptr(x), B * H * W, C, cs, L.ptr(s[0]), L.ptr(s[1]), _s(), nbytes=_nb(x))
     return s
 
 
@@ -167,7 +172,7 @@ def scale_shift_act(x, scale, shift, per_image, relu, up2):
     B, C, H, W, cs = geom(x)
     y = empty_nhwc(B, C, 2 * H if up2 else H, 2 * W if up2 else W, x.device)
     L.call("sgb_scale_shift_act", L.ptr(x), B, H, W, C, cs, L.ptr(scale), L.ptr(shift), 1 if per_image else 0, 1 if relu else 0,
-           1 if up2 else 0, L.ptr(y), geom(y)[4], _s())
+           1 if up2 else 0, L.ptr(y), geom(y)[4], _s(), nbytes=_nb(x, y))
     return y
 
 
@@ -177,7 +182,7 @@ def bn_bwd_reduce(dy, x, scale, shift, per_image, mean, rstd, relu, up2):
     S12 = torch.empty((2, C), device=x.device, dtype=torch.float32)
     L.call("sgb_bn_bwd_reduce", L.ptr(dy), geom(dy)[4], L.ptr(x), cs, B, H, W, C, L.ptr(scale), L.ptr(shift),
            1 if per_image else 0, L.ptr(mean), L.ptr(rstd), 1 if relu else 0, 1 if up2 else 0, L.ptr(s12[0]), L.ptr(s12[1]),
-           L.ptr(S12[0]), L.ptr(S12[1]), _s())
+           L.ptr(S12[0]), L.ptr(S12[1]), _s(), nbytes=_nb(dy, x))
     return s12, S12
 
 
@@ -187,7 +192,7 @@ def bn_bwd_apply(dy, x, scale, shift, per_image, mean, rstd, S12, count, relu, u
     L.call("sgb_bn_bwd_apply", L.ptr(dy), geom(dy)[4], L.ptr(x), cs, B, H, W, C, L.ptr(scale), L.ptr(shift),
            1 if per_image else 0, L.ptr(mean), L.ptr(rstd), L.ptr(S12[0]) if S12 is not None else None,
            L.ptr(S12[1]) if S12 is not None else None, float(count), 1 if relu else 0, 1 if up2 else 0,
-           1 if use_batch_stats else 0, L.ptr(dx), geom(dx)[4], _s())
+           1 if use_batch_stats else 0, L.ptr(dx), geom(dx)[4], _s(), nbytes=_nb(dy, x, dx))
     return dx
 
 
@@ -198,7 +203,7 @@ def axpby(x, y=None, a=1.0, b=1.0, a_dev=None, mask=None, relu=False, out=None):
         out = empty_nhwc(B, C, H, W, x.device)
     L.call("sgb_axpby", L.ptr(x), xs, L.ptr(y), geom(y)[4] if y is not None else 0, L.ptr(mask),
            geom(mask)[4] if mask is not None else 0, L.ptr(out), geom(out)[4], B * H * W, C, float(a), L.ptr(a_dev), float(b),
-           1 if relu else 0, _s())
+           1 if relu else 0, _s(), nbytes=_nb(x, y, mask, out))
     return out
 
 
@@ -207,7 +212,7 @@ def pool2_fwd(x, mode, out=None):
     B, C, H, W, xs = geom(x)
     if out is None:
         out = empty_nhwc(B, C, H // 2, W // 2, x.device)
-    L.call("sgb_pool2_fwd", L.ptr(x), xs, L.ptr(out), geom(out)[4], B, H // 2, W // 2, C, mode, _s())
+    L.call("sgb_pool2_fwd", L.ptr(x), xs, L.ptr(out), geom(out)[4], B, H // 2, W // 2, C, mode, _s(), nbytes=_nb(x, out))
     return out
 
 
@@ -216,21 +221,21 @@ def pool2_bwd(dy, mode, x=None, add=None, relu_src=None):
     dx = empty_nhwc(B, C, 2 * Ho, 2 * Wo, dy.device)
     L.call("sgb_pool2_bwd", L.ptr(dy), dys, L.ptr(x), geom(x)[4] if x is not None else 0, L.ptr(add),
            geom(add)[4] if add is not None else 0, L.ptr(relu_src), geom(relu_src)[4] if relu_src is not None else 0, L.ptr(dx),
-           geom(dx)[4], B, Ho, Wo, C, mode, _s())
+           geom(dx)[4], B, Ho, Wo, C, mode, _s(), nbytes=_nb(dy, x, add, relu_src, dx))
     return dx
 
 
 def softmax_rows(s, n, out=None):
     if out is None:
         out = torch.empty_like(s)
-    L.call("sgb_softmax_rows", L.ptr(s), L.ptr(out), s.numel() // n, n, _s())
+    L.call("sgb_softmax_rows", L.ptr(s), L.ptr(out), s.numel() // n, n, _s(), nbytes=_nb(s, out))
     return out
 
 
 def softmax_bwd_rows(p, dp, n, out=None):
     if out is None:
         out = torch.empty_like(p)
-    L.call("sgb_softmax_bwd_rows", L.ptr(p), L.ptr(dp), L.ptr(out), p.numel() // n, n, _s())
+    L.call("sgb_softmax_bwd_rows", L.ptr(p), L.ptr(dp), L.ptr(out), p.numel() // n, n, _s(), nbytes=_nb(p, dp, out))
     return out
 
 
