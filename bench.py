@@ -376,7 +376,11 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained"
     step_flop = STEP_GFLOP_PER_IMAGE.get(workload, 0.0) * 1e9 * global_batch
-    roof = {"bound": "tensor", "unit": "TFLOP/s", "peak": peak_tf, "peak_source": peak_src, "traffic": None,
+    # dram__bytes_read.sum + dram__bytes_write.sum of one captured launch (ncu --set full, profiles/r01_ncu_full_summary.txt):
+    # conv3x3_rows_kernel, 3x3 64->64 @256x256, B=32 -- 268.7 MB read + 221.4 MB written for 536.9 MB of algorithmic bytes
+    # (the tail of the output was still in L2 when the kernel ended): no re-reads.
+    roof = {"bound": "tensor", "unit": "TFLOP/s", "peak": peak_tf, "peak_source": peak_src, "traffic": 490.1e6,
+            "traffic_note": "bytes per launch of the captured conv3x3_rows_kernel launch (B=32 3x3 64->64 256^2; algorithmic 536.9e6)",
             "step_algorithmic_tflop": step_flop * 1e-12,
             "step_achieved": step_flop / (ms_step * 1e-3) * 1e-12 / world,
             "step_frac": step_flop / (ms_step * 1e-3) * 1e-12 / world / peak_tf}
