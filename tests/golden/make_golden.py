@@ -208,6 +208,26 @@ def golden_gp(tag, family, conv_dim, d_sn, d_cond, classes=5, B=8, img_size=32, 
     print(tag, "keys", len(out), "gp", float(gp), "|g| per sample", g.flatten(1).norm(dim=1)[:4].tolist())
 
 
+def golden_inception():
+    """The reference's LoadEvalModel("InceptionV3_tf", "legacy").get_outputs (src/metrics/preparation.py:103-122 ->
+    src/metrics/inception_net.py:81-107, FID blocks :135-249) on the seeded weights of
+    sgb200.metrics.inception_net.seeded_state_dict(0): the pretrained file cannot be downloaded here, so the weight
+    download inside fid_inception_v3 (:130) is replaced by that state dict -- topology and arithmetic are the reference's."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "pytorch-studiogan_b200"))
+    from sgb200.metrics.inception_net import seeded_state_dict
+    import metrics.inception_net as rinc
+    import metrics.preparation as rprep
+    rinc.load_state_dict_from_url = lambda *a, **k: seeded_state_dict(0)
+    ev = rprep.LoadEvalModel("InceptionV3_tf", "legacy", 1, False, "cpu")
+    ev.eval()
+    torch.manual_seed(11)
+    x = torch.tanh(torch.randn(2, 3, 32, 32) * 1.2)
+    with torch.no_grad():
+        pool, logits = ev.get_outputs(x, quantize=True)
+    np.savez_compressed(os.path.join(HERE, "inception_seed0.npz"), x=x.numpy(), pool=pool.numpy(), logits=logits.numpy())
+    print("inception_seed0 pool", tuple(pool.shape), float(pool.abs().mean()), "logits", tuple(logits.shape))
+
+
 def golden_metrics():
     rng = np.random.RandomState(0)
     out = {}
@@ -272,6 +292,7 @@ if __name__ == "__main__":
     golden_resfamily("resnet32_cbn_c16", "resnet", 16, False, False, True, "cBN", "PD", "hinge", z_dim=32)
     golden_resfamily("wgan32_bn_c16", "resnet", 16, False, False, False, "W/O", "W/O", "wasserstein", z_dim=32)
     golden_metrics()
+    golden_inception()
     golden_gp("gp_resnet32_bn_c16", "resnet", 16, False, "W/O")           # the WGAN-GP config's discriminator (BatchNorm, no SN)
     golden_gp("gp_resnet32_sn_c16_pd", "resnet", 16, True, "PD")
     golden_gp("gp_deep32_sn_c8_pd", "deep", 8, True, "PD")
