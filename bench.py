@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--config", default=os.path.join(PKG, "configs", "BigGAN-Deep-256res.yaml"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--graphs", default="auto", choices=["auto", "on", "off"],
+                    help="capture each training phase in a CUDA graph; auto = on when the per-GPU batch is <= 64 (launch-bound regime)")
     ap.add_argument("--no-fid", action="store_true", help="skip the FID-50k evaluation timing (N = 1 only)")
     ap.add_argument("--fid-num", type=int, default=50000)
     ap.add_argument("--cpu-batch", type=int, default=1)
@@ -127,6 +129,7 @@ def build_worker(args, rank, world, device):
     global_batch = cfgs.OPTIMIZATION.batch_size
     assert global_batch % world == 0
     cfgs.OPTIMIZATION.batch_size = global_batch // world           # per-rank batch, as src/loader.py:162
+    cfgs.RUN.cuda_graphs = args.graphs == "on" or (args.graphs == "auto" and cfgs.OPTIMIZATION.batch_size <= 64)
     cfgs.RUN.distributed_data_parallel = world > 1
     cfgs.RUN.synchronized_bn = world > 1
     misc.fix_seed(0 + rank)                                         # seed + rank (src/loader.py:99)
@@ -316,12 +319,14 @@ def main():
     try:
         _lib.PROFILE["events"] = []
         _lib.PROFILE["enabled"] = True
+        graphs_on, cfgs.RUN.cuda_graphs = cfgs.RUN.cuda_graphs, False      # the accounting step runs eagerly (events per call)
         torch.cuda.synchronize()
         w0 = time.perf_counter()
         run_steps(worker, 1, False)
         torch.cuda.synchronize()
         prof_wall_ms = (time.perf_counter() - w0) * 1e3
         _lib.PROFILE["enabled"] = False
+        cfgs.RUN.cuda_graphs = graphs_on
         agg, by_tag = {}, {}
         for tag, flops, e0, e1, nbytes in _lib.PROFILE["events"]:
             ms = e0.elapsed_time(e1)
@@ -406,7 +411,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "global_batch": global_batch, "per_gpu_batch": per_rank, "img_size": S,
-                       "d_updates_per_step": opt.d_updates_per_step, "acml_steps": opt.acml_steps, "parallelism": "dp%d" % world,
+                       "d_updates_per_step": opt.d_updates_per_step, "acml_steps": opt.acml_steps, "parallelism": "dp%d" % world, "cuda_graphs": bool(cfgs.RUN.cuda_graphs),
                        "l2": "per-step working set (tens of GB of activations) >> 126 MB L2; no explicit flush needed"},
             "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "fid50k": fid50k,
             "clocks": sampler.summary()}

@@ -211,7 +211,9 @@ int sgb_cast_bf16_to_f32(const void* in, float* out, int64_t n, sgb_stream_t str
  * (src/utils/ema.py:27-40) over a flat fp32 parameter arena.  ema may be NULL.
  * ------------------------------------------------------------------------------------------ */
 int sgb_adam_ema_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                      int32_t step, float* ema, float ema_decay, float grad_scale, sgb_stream_t stream);
+                      int32_t step, const int32_t* step_dev, float* ema, float ema_decay, float grad_scale, sgb_stream_t stream);
+/* step_dev (optional): int32 step counter in device memory used for the bias corrections instead of `step`, so that a
+ * captured CUDA graph of the update stays correct when replayed. */
 int sgb_ema_lerp(float* ema, const float* p, int64_t n, float decay, sgb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -196,17 +196,30 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
     const int HW = H * W;
     const int p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, HW);
     const int gg = (c_base >> 3) + g;
-    for (int hw = p0 + prow; hw < p1; hw += nrows) {
-      const long long p = (long long)b * HW + hw;
-      float xv[8], dz[8];
+    for (int hw = p0 + prow; hw < p1; hw += 2 * nrows) {
+      const int hw2 = hw + nrows;
+      const bool two = hw2 < p1;
+      const long long p = (long long)b * HW + hw, q = (long long)b * HW + hw2;
+      float xv[8], dz[8], xw[8], dw[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * x_cstride) + gg), xv);
-      load_dz(dy, dy_cstride, b, hw / W, hw % W, H, W, gg, up2, p, dz);
+      if (two) unpack8(__ldg(reinterpret_cast<const uint4*>(x + q * x_cstride) + gg), xw);
+      load_dz(dy, dy_cstride, b, up2 ? hw / W : 0, up2 ? hw % W : 0, H, W, gg, up2, p, dz);
+      if (two) load_dz(dy, dy_cstride, b, up2 ? hw2 / W : 0, up2 ? hw2 % W : 0, H, W, gg, up2, q, dw);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float z = fmaf(xv[j], sc[j], sh[j]);
         const float d = (relu && !(z > 0.f)) ? 0.f : dz[j];
         t1[j] += d;
         t2[j] = fmaf(d, (xv[j] - mu[j]) * rs[j], t2[j]);
+      }
+      if (two) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(xw[j], sc[j], sh[j]);
+          const float d = (relu && !(z > 0.f)) ? 0.f : dw[j];
+          t1[j] += d;
+          t2[j] = fmaf(d, (xw[j] - mu[j]) * rs[j], t2[j]);
+        }
       }
     }
 #pragma unroll
@@ -226,42 +239,68 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
 }
 
 // dx = scale[b,c]*dz - rstd*(S1/N) - rstd*(S2/N)*xhat   (train) ;   dx = scale[b,c]*dz   (eval: use_batch_stats = 0)
+// grid = (pixel chunks, B, channel chunks) like the reduce kernel: a thread owns one 8-channel group of one image, so
+// every per-(image, channel) constant lives in registers and the loop body is two 16-byte loads, 8 FMAs and one store.
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_cstride,
-                                                            const bf16* __restrict__ x, long long x_cstride, int B, int H, int W,
+                                                            const bf16* __restrict__ x, long long x_cstride, int H, int W,
                                                             int C, const float* __restrict__ scale, const float* __restrict__ shift,
                                                             int bstride, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const float* __restrict__ S1,
                                                             const float* __restrict__ S2, float inv_count, int relu, int up2,
-                                                            int use_batch_stats, bf16* __restrict__ dx, long long dx_cstride) {
-  const int VG = C >> 3;
-  const long long total = (long long)B * H * W * VG;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int g = (int)(i % VG);
-    const long long p = i / VG;
-    const int HW = H * W;
-    const int b = (int)(p / HW);
-    const int hw = (int)(p % HW);
-    float xv[8], dz[8], o[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * x_cstride) + g), xv);
-    load_dz(dy, dy_cstride, b, hw / W, hw % W, H, W, g, up2, p, dz);
+                                                            int use_batch_stats, bf16* __restrict__ dx, long long dx_cstride,
+                                                            int pix_per_block) {
+  const int b = blockIdx.y;
+  const int c_base = blockIdx.z * kChunkC;
+  const int cc = min(C - c_base, kChunkC);
+  const int VG = cc >> 3;
+  const int VGb = VG < 256 ? VG : 256;
+  const int nrows = 256 / VGb;
+  const int g = threadIdx.x % VGb, prow = threadIdx.x / VGb;
+  if (prow >= nrows) return;
+  const int gg = (c_base >> 3) + g;
+  float sc[8], sh[8], mu[8], ka[8], kb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c_base + g * 8 + j;
+    sc[j] = scale[(size_t)b * bstride + c]; sh[j] = shift[(size_t)b * bstride + c];
+    mu[j] = mean[c];
+    if (use_batch_stats) {
+      const float rs = rstd[c];
+      ka[j] = rs * inv_count * S1[c];
+      kb[j] = rs * rs * inv_count * S2[c];
+    } else {
+      ka[j] = 0.f; kb[j] = 0.f;
+    }
+  }
+  const int HW = H * W;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, HW);
+  for (int hw = p0 + prow; hw < p1; hw += 2 * nrows) {
+    const int hw2 = hw + nrows;
+    const bool two = hw2 < p1;
+    const long long pa = (long long)b * HW + hw, pb = (long long)b * HW + hw2;
+    float xa[8], xb[8], da[8], db[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + pa * x_cstride) + gg), xa);
+    if (two) unpack8(__ldg(reinterpret_cast<const uint4*>(x + pb * x_cstride) + gg), xb);
+    load_dz(dy, dy_cstride, b, up2 ? hw / W : 0, up2 ? hw % W : 0, H, W, gg, up2, pa, da);
+    if (two) load_dz(dy, dy_cstride, b, up2 ? hw2 / W : 0, up2 ? hw2 % W : 0, H, W, gg, up2, pb, db);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
-      const float sc = __ldg(scale + (size_t)b * bstride + c), sh = __ldg(shift + (size_t)b * bstride + c);
-      const float z = fmaf(xv[j], sc, sh);
-      const float d = (relu && !(z > 0.f)) ? 0.f : dz[j];
-      float r = sc * d;
-      if (use_batch_stats) {
-        const float rs = __ldg(rstd + c);
-        const float xh = (xv[j] - __ldg(mean + c)) * rs;
-        r -= rs * inv_count * (__ldg(S1 + c) + xh * __ldg(S2 + c));
-      }
-      o[j] = r;
+      const float z = fmaf(xa[j], sc[j], sh[j]);
+      const float d = (relu && !(z > 0.f)) ? 0.f : da[j];
+      o[j] = sc[j] * d - ka[j] - kb[j] * (xa[j] - mu[j]);
     }
-    reinterpret_cast<uint4*>(dx + p * dx_cstride)[g] = pack8(o);
+    reinterpret_cast<uint4*>(dx + pa * dx_cstride)[gg] = pack8(o);
+    if (two) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(xb[j], sc[j], sh[j]);
+        const float d = (relu && !(z > 0.f)) ? 0.f : db[j];
+        o[j] = sc[j] * d - ka[j] - kb[j] * (xb[j] - mu[j]);
+      }
+      reinterpret_cast<uint4*>(dx + pb * dx_cstride)[gg] = pack8(o);
+    }
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------- tangent (JVP) backward
 // The gradient-penalty pass (sgb200/utils/gp.py) pushes a tangent a = dx/d(eps) through the discriminator.  For a
@@ -453,11 +492,16 @@ extern "C" int sgb_bn_bwd_apply(const void* dy, int64_t dy_cstride, const void* 
   SGB_REQUIRE(dy && x && dx && scale && shift && mean && rstd);
   SGB_REQUIRE(!use_batch_stats || (S1 && S2 && count > 0.f));
   SGB_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && dy_cstride % 8 == 0 && x_cstride % 8 == 0 && dx_cstride % 8 == 0);
-  const long long total = (long long)B * H * W * (C / 8);
-  bn_bwd_apply_kernel<<<ew_blocks(total), 256, 0, stream>>>((const bf16*)dy, dy_cstride, (const bf16*)x, x_cstride, B, H, W, C, scale,
-                                                           shift, per_image ? C : 0, mean, rstd, S1, S2,
-                                                           use_batch_stats ? 1.f / count : 0.f, relu, up2, use_batch_stats, (bf16*)dx,
-                                                           dx_cstride);
+  const int chunks = (C + kChunkC - 1) / kChunkC;
+  const int HW = H * W;
+  long long target = 16LL * sm_count() / ((long long)B * chunks);
+  if (target < 1) target = 1;
+  int ppb = (int)((HW + target - 1) / target);
+  if (ppb < 64) ppb = 64;
+  dim3 grid((HW + ppb - 1) / ppb, B, chunks);
+  bn_bwd_apply_kernel<<<grid, 256, 0, stream>>>((const bf16*)dy, dy_cstride, (const bf16*)x, x_cstride, H, W, C, scale, shift,
+                                               per_image ? C : 0, mean, rstd, S1, S2, use_batch_stats ? 1.f / count : 0.f, relu,
+                                               up2, use_batch_stats, (bf16*)dx, dx_cstride, ppb);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }

@@ -512,7 +512,12 @@ __global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const bf16* __restri
 __global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, long long n, float lr, float b1, float b2,
                                                         float eps, float bc1, float bc2_sqrt, float* __restrict__ ema,
-                                                        float decay, float grad_scale) {
+                                                        float decay, float grad_scale, const int* __restrict__ step_dev) {
+  if (step_dev) {                                   // step counter kept on the device (CUDA-graph replays advance it)
+    const float t = (float)__ldg(step_dev);
+    bc1 = 1.f - powf(b1, t);
+    bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  }
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
     const float gi = g[i] * grad_scale;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -758,13 +763,14 @@ extern "C" int sgb_cast_bf16_to_f32(const void* in, float* out, int64_t n, sgb_s
 }
 
 extern "C" int sgb_adam_ema_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                                 float eps, int32_t step, float* ema, float ema_decay, float grad_scale, sgb_stream_t stream_) {
+                                 float eps, int32_t step, const int32_t* step_dev, float* ema, float ema_decay, float grad_scale,
+                                 sgb_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  SGB_REQUIRE(p && g && m && v && n > 0 && step >= 1);
+  SGB_REQUIRE(p && g && m && v && n > 0 && (step >= 1 || step_dev));
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
   adam_ema_kernel<<<ew_blocks(n), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), ema, ema_decay,
-                                                   grad_scale);
+                                                   grad_scale, step_dev);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }

@@ -43,7 +43,7 @@ def _defaults():
     c["AUG"] = _Section(apply_diffaug=False, apply_ada=False, apply_apa=False)
     c["STYLEGAN"] = _Section()
     c["RUN"] = _Section(mixed_precision=False, distributed_data_parallel=False, synchronized_bn=False, batch_statistics=False,
-                        standing_statistics=False, standing_step=-1, standing_max_batch=-1, freezeD=-1, langevin_sampling=False,
+                        standing_statistics=False, standing_step=-1, standing_max_batch=-1, freezeD=-1, cuda_graphs=False, langevin_sampling=False,
                         truncation_factor=-1.0, eval_backbone="InceptionV3_tf", post_resizer="legacy", seed=-1)
     c["MISC"] = _Section(no_proc_data=["CIFAR10", "CIFAR100", "Tiny_ImageNet"])
     c["MODULES"] = _Section()

@@ -348,9 +348,10 @@ def cast_bf16_to_f32(x):
     return out
 
 
-def adam_ema_step(p, g, m, v, lr, beta1, beta2, eps, step, ema=None, ema_decay=0.0, grad_scale=1.0):
+def adam_ema_step(p, g, m, v, lr, beta1, beta2, eps, step, ema=None, ema_decay=0.0, grad_scale=1.0, step_dev=None):
+    """``step_dev``: optional int32 device scalar holding the step count (used instead of ``step``; CUDA-graph safe)."""
     L.call("sgb_adam_ema_step", L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), float(lr), float(beta1), float(beta2),
-           float(eps), int(step), L.ptr(ema), float(ema_decay), float(grad_scale), _s())
+           float(eps), int(step), L.ptr(step_dev), L.ptr(ema), float(ema_decay), float(grad_scale), _s())
 
 
 def ema_lerp(ema, p, decay):

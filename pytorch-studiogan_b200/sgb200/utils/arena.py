@@ -57,3 +57,24 @@ class GradArena:
     def zero(self):
         self.flat.zero_()
         self.attach()
+
+
+class BufferArena:
+    """Float buffers (BatchNorm running statistics) and integer buffers (num_batches_tracked) of a module, minus those that
+    already live in another flat arena (spectral-norm u / v), flattened per dtype so that the EMA buffer update is one
+    lerp + one copy."""
+
+    def __init__(self, module, skip=lambda b: False):
+        bufs = [b for b in module.buffers() if not skip(b)]
+        self.floats = [b for b in bufs if b.dtype == torch.float32]
+        self.ints = [b for b in bufs if not b.is_floating_point()]
+        self.other = [b for b in bufs if b.is_floating_point() and b.dtype != torch.float32]
+        self.fflat = _flatten(self.floats, align=4) if self.floats else None
+        self.iflat = None
+        if self.ints and all(b.dtype == self.ints[0].dtype for b in self.ints):
+            self.ints = [b if b.dim() > 0 else b for b in self.ints]
+            self.iflat = _flatten(self.ints, align=1)
+        self.ptrs = [b.data_ptr() for b in self.floats + self.ints]
+
+    def intact(self):
+        return all(b.data_ptr() == q for b, q in zip(self.floats + self.ints, self.ptrs))

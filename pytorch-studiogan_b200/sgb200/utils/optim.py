@@ -20,10 +20,21 @@ class ArenaAdam(object):
         self.module = module
         self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, amsgrad=False)
         self.param_groups = [dict(self.defaults, params=[p for p in module.parameters()])]
-        self.step_count = 0
+        self._step_host = 0
+        self.step_t = None                       # int32 device scalar: the step count lives on the device (graph replays)
         self.arena = self.grads = self.exp_avg = self.exp_avg_sq = None
         self.grad_scale = 1.0
         self._pending = None
+
+    @property
+    def step_count(self):
+        return int(self.step_t) if self.step_t is not None else self._step_host
+
+    @step_count.setter
+    def step_count(self, v):
+        self._step_host = int(v)
+        if self.step_t is not None:
+            self.step_t.fill_(int(v))
 
     def _ensure(self):
         arena = param_arena(self.module)
@@ -32,6 +43,8 @@ class ArenaAdam(object):
                 raise RuntimeError("parameter set changed under the optimiser")
             self.arena = arena
             self.grads = GradArena(arena)
+            if self.step_t is None or self.step_t.device != arena.flat.device:
+                self.step_t = torch.full((1,), self._step_host, device=arena.flat.device, dtype=torch.int32)
             if self.exp_avg is None or self.exp_avg.device != arena.flat.device:
                 old = (self.exp_avg, self.exp_avg_sq)
                 self.exp_avg = torch.zeros_like(arena.flat)
@@ -59,10 +72,10 @@ class ArenaAdam(object):
     def step(self):
         self._ensure()
         self.grads.attach()
-        self.step_count += 1
+        self.step_t.add_(1)
         g = self.param_groups[0]
         K.adam_ema_step(self.arena.flat, self.grads.flat, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1],
-                        g["eps"], self.step_count, grad_scale=self.grad_scale)
+                        g["eps"], 0, grad_scale=self.grad_scale, step_dev=self.step_t)
         self.grad_scale = 1.0
 
     # ---------------------------------------------------------------------------------------- torch.optim.Adam format

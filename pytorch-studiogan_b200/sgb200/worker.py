@@ -7,8 +7,51 @@ fp32 accumulation and fp32 master weights, which needs no loss scaling.
 """
 import torch
 
+from . import _lib
 from .models import model as model_lib
 from .utils import losses, misc, sample
+
+
+class _GraphedPhase:
+    """One training phase (all of train_discriminator's or train_generator's device work) captured into a CUDA graph
+    after ``warmup`` eager calls and replayed afterwards: at small per-GPU batches (8-GPU strong scaling: 32 images per
+    rank) the phase is ~1.8k library launches and the host cannot issue them as fast as the GPU retires them.  Inputs
+    live in static device buffers filled before each replay; z / labels come from the device RNG inside the graph; the
+    Adam step counters live on the device (ArenaAdam.step_t).  Any capture failure falls back to eager execution."""
+
+    def __init__(self, fn, warmup=2):
+        self.fn, self.warmup = fn, warmup
+        self.calls = 0
+        self.graph = self.out = None
+        self.failed = False
+        self.launches = 0                         # library launches recorded in the graph (re-issued by every replay)
+
+    def __call__(self):
+        if self.graph is not None:
+            self.graph.replay()
+            _lib.LAUNCHES[0] += self.launches
+            return self.out
+        self.calls += 1
+        if self.failed or self.calls <= self.warmup:
+            return self.fn()
+        try:
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.LAUNCHES[0]
+            with torch.cuda.graph(g):
+                out = self.fn()
+            self.launches = _lib.LAUNCHES[0] - n0
+            self.graph, self.out = g, out
+            g.replay()
+            return out
+        except Exception as ex:  # noqa: BLE001 - keep training alive, eagerly
+            self.failed = True
+            self.graph = None
+            import warnings
+            warnings.warn("sgb200: CUDA-graph capture failed (%r); continuing without graphs" % (ex,))
+            torch.cuda.synchronize()
+            return self.fn()
 
 
 class WORKER(object):
@@ -40,6 +83,13 @@ class WORKER(object):
                 raise NotImplementedError("LOSS.%s is outside the sgb200 hot-path scope" % flag)
 
     # ------------------------------------------------------------------------------------------------ data
+    def sample_data_basket_raw(self):
+        try:
+            return next(self.train_iter)
+        except StopIteration:
+            self.train_iter = iter(self.train_dataloader)
+            return next(self.train_iter)
+
     def sample_data_basket(self):
         """One loader item carries batch_size * acml_steps * d_updates_per_step samples (src/worker.py:194-208)."""
         try:
@@ -57,13 +107,33 @@ class WORKER(object):
                                       RUN=self.RUN, MODEL=self.MODEL, device=self.local_rank)
 
     # ------------------------------------------------------------------------------------------------ D phase
+    def _graphs_enabled(self):
+        return bool(getattr(self.RUN, "cuda_graphs", False)) and not self.LOSS.apply_gp
+
     def train_discriminator(self, current_step):
+        real_image_basket, real_label_basket = self.sample_data_basket_raw()
+        if self._graphs_enabled():
+            # static input buffers: the graph reads the same addresses every replay
+            if getattr(self, "_static_imgs", None) is None or self._static_imgs.shape != real_image_basket.shape:
+                self._static_imgs = torch.empty(real_image_basket.shape, device=self.local_rank, dtype=real_image_basket.dtype)
+                self._static_labels = torch.empty(real_label_basket.shape, device=self.local_rank, dtype=real_label_basket.dtype)
+                self._d_graph = _GraphedPhase(self._d_phase_static)
+            self._static_imgs.copy_(real_image_basket, non_blocking=True)
+            self._static_labels.copy_(real_label_basket, non_blocking=True)
+            return "N/A", self._d_graph()
+        return "N/A", self._d_phase(real_image_basket, real_label_basket)
+
+    def _d_phase_static(self):
+        return self._d_phase(self._static_imgs, self._static_labels)
+
+    def _d_phase(self, real_images_all, real_labels_all):
+        bs = self.OPTIMIZATION.batch_size
+        real_image_basket, real_label_basket = torch.split(real_images_all, bs), torch.split(real_labels_all, bs)
         misc.make_GAN_trainable(self.Gen, self.Gen_ema, self.Dis)
         misc.toggle_grad(self.Gen, False)
         misc.toggle_grad(self.Dis, True, self.RUN.freezeD)
         # the generator uses batch statistics here but must not move its running statistics (src/worker.py:225)
         self.Gen.apply(misc.untrack_bn_statistics)
-        real_image_basket, real_label_basket = self.sample_data_basket()
         batch_counter = 0
         dis_acml_loss = None
         for _ in range(self.OPTIMIZATION.d_updates_per_step):
@@ -85,10 +155,23 @@ class WORKER(object):
                 batch_counter += 1
             model_lib.allreduce_gradients(self.Dis, self.OPTIMIZATION.d_optimizer)
             self.OPTIMIZATION.d_optimizer.step()
-        return "N/A", dis_acml_loss
+        return dis_acml_loss.detach()
 
     # ------------------------------------------------------------------------------------------------ G phase
     def train_generator(self, current_step):
+        if self._graphs_enabled():
+            if getattr(self, "_g_graph", None) is None:
+                self._g_graph = _GraphedPhase(self._g_phase)
+            gen_acml_loss = self._g_graph()
+            if self.MODEL.apply_g_ema:           # decay depends on the step number: stays outside the graph (5 launches)
+                self.ema.update(current_step)
+            return gen_acml_loss
+        return self._g_phase(current_step)
+
+    def _g_phase(self, ema_step=None):
+        """``ema_step`` None: graph capture / replay (the EMA update follows outside, needs g_updates_per_step == 1)."""
+        if ema_step is None and self.OPTIMIZATION.g_updates_per_step != 1 and self.MODEL.apply_g_ema:
+            raise NotImplementedError("CUDA graphs with g_updates_per_step > 1 and EMA")
         misc.make_GAN_trainable(self.Gen, self.Gen_ema, self.Dis)
         misc.toggle_grad(self.Dis, False)
         misc.toggle_grad(self.Gen, True)
@@ -104,9 +187,9 @@ class WORKER(object):
                 gen_acml_loss.backward()
             model_lib.allreduce_gradients(self.Gen, self.OPTIMIZATION.g_optimizer)
             self.OPTIMIZATION.g_optimizer.step()
-            if self.MODEL.apply_g_ema:
-                self.ema.update(current_step)
-        return gen_acml_loss
+            if ema_step is not None and self.MODEL.apply_g_ema:
+                self.ema.update(ema_step)
+        return gen_acml_loss.detach()
 
 
 # ------------------------------------------------------------------------------------------------------ evaluation

@@ -596,3 +596,62 @@ def test_worker_wgan_gp_step_runs_and_matches_two_phase_reference_order():
     assert all(torch.isfinite(p).all() for p in list(Dis.parameters()) + list(Gen.parameters()))
     assert any(float((p.detach() - q).abs().max()) > 0 for p, q in zip(Dis.parameters(), d0))
     assert any(float((p.detach() - q).abs().max()) > 0 for p, q in zip(Gen.parameters(), g0))
+
+
+def test_worker_cuda_graph_phases_capture_and_advance_state():
+    """RUN.cuda_graphs: after two eager calls each phase is captured and replayed.  Checks that the graphs exist, that
+    replays keep training (parameters move every step, Adam's device step counters advance by d_updates / 1 per step,
+    BatchNorm's num_batches_tracked advances), that losses stay finite, and that the EMA (outside the graph) follows."""
+    from sgb200 import config as C
+    from sgb200.models import model as M
+    from sgb200.worker import WORKER
+    dev = _cuda()
+    cfgs = C.Configurations(None)
+    cfgs.DATA.img_size, cfgs.DATA.num_classes = 32, 10
+    m = cfgs.MODEL
+    m.backbone, m.g_cond_mtd, m.d_cond_mtd, m.apply_g_sn, m.apply_d_sn = "big_resnet_deep_legacy", "cBN", "PD", True, True
+    m.z_dim, m.g_shared_dim, m.g_conv_dim, m.d_conv_dim, m.g_depth, m.d_depth = 32, 32, 16, 16, 1, 1
+    m.apply_g_ema, m.g_ema_decay, m.g_ema_start = True, 0.9, 0
+    cfgs.LOSS.adv_loss = "hinge"
+    o = cfgs.OPTIMIZATION
+    o.batch_size, o.d_updates_per_step, o.g_updates_per_step, o.acml_steps = 16, 2, 1, 1
+    cfgs.RUN.cuda_graphs = True
+    cfgs.define_modules()
+    cfgs.define_losses()
+    torch.manual_seed(0)
+    Gen, _, _, Dis, Gen_ema, _, _, ema = M.load_generator_discriminator(cfgs.DATA, o, cfgs.MODEL, cfgs.STYLEGAN, cfgs.MODULES,
+                                                                        cfgs.RUN, dev, None)
+    cfgs.define_optimizer(Gen, Dis)
+
+    class Loader:
+        def __init__(self):
+            self.i = 0
+
+        def __iter__(self):
+            return self
+
+        def __next__(self):
+            self.i += 1
+            g = torch.Generator().manual_seed(self.i)
+            return (torch.rand(32, 3, 32, 32, generator=g) * 2 - 1).pin_memory(), torch.randint(0, 10, (32,), generator=g).pin_memory()
+    w = WORKER(cfgs=cfgs, run_name="t", Gen=Gen, Gen_mapping=None, Gen_synthesis=None, Dis=Dis, Gen_ema=Gen_ema, Gen_ema_mapping=None,
+               Gen_ema_synthesis=None, ema=ema, eval_model=None, train_dataloader=Loader(), eval_dataloader=None, global_rank=0,
+               local_rank=dev, mu=None, sigma=None, real_feats=None, logger=None)
+    prev_d = prev_g = prev_e = None
+    for step in range(6):
+        _, d_loss = w.train_discriminator(step)
+        g_loss = w.train_generator(step)
+        torch.cuda.synchronize()
+        assert torch.isfinite(d_loss).all() and torch.isfinite(g_loss).all()
+        d_now = torch.cat([p.detach().flatten() for p in Dis.parameters()]).clone()
+        g_now = torch.cat([p.detach().flatten() for p in Gen.parameters()]).clone()
+        e_now = torch.cat([p.detach().flatten() for p in Gen_ema.parameters()]).clone()
+        if prev_d is not None:
+            assert float((d_now - prev_d).abs().max()) > 0 and float((g_now - prev_g).abs().max()) > 0
+            assert float((e_now - prev_e).abs().max()) > 0
+        prev_d, prev_g, prev_e = d_now, g_now, e_now
+    assert w._d_graph.graph is not None and w._g_graph.graph is not None and not w._d_graph.failed
+    assert o.d_optimizer.step_count == 12 and o.g_optimizer.step_count == 6
+    nbt = [b for n, b in Gen.named_buffers() if n.endswith("num_batches_tracked")]
+    assert all(int(b) == 6 for b in nbt)          # the D phase does not track (src/worker.py:225), the G phase does
+    assert w._d_graph.launches > 100 and w._g_graph.launches > 100
