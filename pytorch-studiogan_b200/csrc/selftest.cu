@@ -352,6 +352,11 @@ int main(int argc, char** argv) {
       {"3x3 4x4 nb=8 ragged B=12",     12, 4, 4,  64,  128, 3, 3, 1, 1},
       {"1x7 c64->96 17x17 ragged",     2, 17, 17, 64,  96,  1, 7, 0, 3},
       {"3x3 c192->320 64x64",          1, 64, 64, 192, 320, 3, 3, 1, 1},
+      {"w3 c64->64 128x128 B=2",       2, 128, 128, 64, 64, 3, 3, 1, 1},
+      {"w3 c64->64 256x8 B=3",         3, 8, 256, 64, 64, 3, 3, 1, 1},
+      {"w3 c64->32 128x128 B=1",       1, 128, 128, 64, 32, 3, 3, 1, 1},
+      {"w3 c32->64 128x128 B=1",       1, 128, 128, 32, 64, 3, 3, 1, 1},
+      {"w3 c64->64 128x128 B=5",       5, 128, 128, 64, 64, 3, 3, 1, 1},
   };
   if (on("wgrad"))
     for (const auto& c : wcases) fails += run_wgrad_case(c, true);
@@ -372,6 +377,7 @@ int main(int argc, char** argv) {
     time_fprop("1x1 256->512 64^2 B=64", 64, 64, 64, 256, 512, 1);
     time_fprop("1x1 512->2048 16^2 B=64", 64, 16, 16, 512, 2048, 1);
     time_wgrad("3x3 64->64 256^2 B=32", 32, 256, 256, 64, 64, 3);
+    time_wgrad("3x3 64->64 128^2 B=32", 32, 128, 128, 64, 64, 3);
     time_wgrad("3x3 256->256 64^2 B=64", 64, 64, 64, 256, 256, 3);
     time_wgrad("3x3 512->512 32^2 B=64", 64, 32, 32, 512, 512, 3);
     time_wgrad("1x1 2048->512 8^2 B=256", 256, 8, 8, 2048, 512, 1);

@@ -410,6 +410,8 @@ static int make_act_tmap(CUtensorMap* m, const void* base, int B, int H, int W, 
 using namespace sgb;
 
 namespace sgb {
+bool wgrad3x3_c64_eligible(const sgb_wgrad_desc* d);
+int launch_wgrad3x3_c64(const sgb_wgrad_desc* d, cudaStream_t stream);
 bool conv3x3_rows_eligible(const sgb_conv_desc* d);
 int launch_conv3x3_rows(const sgb_conv_desc* d, cudaStream_t stream, int bo_mode, int use_tma_env);
 }  // namespace sgb
@@ -535,6 +537,7 @@ extern "C" int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream_) {
   SGB_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0 && d->KH > 0 && d->KW > 0);
   SGB_REQUIRE(d->Cin % 8 == 0 && d->x_cstride % 8 == 0 && d->Cout % 8 == 0 && d->dy_cstride % 8 == 0);
   SGB_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->dy & 15) == 0);
+  if (env_int("SGB_WGRAD3X3", 1) && wgrad3x3_c64_eligible(d)) return launch_wgrad3x3_c64(d, stream);
 
   WgradArgs p;
   p.B = d->B; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
