@@ -192,12 +192,17 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const long long rpix = p.e.res_up2 ? (((long long)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) : pix;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (as * 2 + j) * p.BN;
         if (p.use_tma) {
-          // epi_bufs == 2: team t stores output row t with both of its 64-channel chunk parities; epi_bufs == 1: team 0 does all
-          const bool mine = (p.epi_bufs == 2) ? (team == j) : (team == 0);
-          if (mine) {
-            const uint32_t stage = epi_stage_base + ((p.epi_bufs == 2) ? team : 0) * kEpiStageBytes;
-            // one team covers every chunk of its row: run the chunk loop for both parities on the team's own barrier
-            epilogue_tile_tma(p.e, &tmY, t_row, p.BN, nt * p.BN, ws * 128, h, b, true, pix, rpix, alpha, stage, team, row, leader, 1);
+          // team t owns output row t.  epi_bufs == 2: both teams stage + TMA-store; epi_bufs == 1 (no room for a second
+          // staging tile, C = 64): team 0 stages + TMA-stores row 0 while team 1 writes row 1 with direct 16-byte stores
+          // (one full 128-byte line per thread at C = 64) -- two rows drain concurrently instead of back to back.
+          if (team == j) {
+            if (p.epi_bufs == 2 || team == 0) {
+              const uint32_t stage = epi_stage_base + ((p.epi_bufs == 2) ? team : 0) * kEpiStageBytes;
+              // one team covers every chunk of its row: run the chunk loop for both parities on the team's own barrier
+              epilogue_tile_tma(p.e, &tmY, t_row, p.BN, nt * p.BN, ws * 128, h, b, true, pix, rpix, alpha, stage, team, row, leader, 1);
+            } else {
+              epilogue_row(p.e, t_row, p.BN, nt * p.BN, true, pix, rpix, alpha, vec_ok);
+            }
           }
         } else if (team == 0) {
           epilogue_row(p.e, t_row, p.BN, nt * p.BN, true, pix, rpix, alpha, vec_ok);
