@@ -89,9 +89,14 @@ typedef struct sgb_wgrad_desc {
   float* dw;          /* fp32 [Cout][KH*KW][Cin]  (per_image: [B][Cout][KH*KW][Cin]) */
   int32_t accumulate; /* 0: dw is zeroed first */
   int32_t per_image;  /* 1: one gradient per image (attention dK/dV); needs H*W >= 128 */
+  float* dbias;       /* optional fp32 [Cout]: bias gradient sum_{b,h,w} dy, produced by the same launch (zeroed first unless
+                         accumulate) -- only when sgb_conv_wgrad_fuses_dbias(d) returns 1, otherwise it must be NULL */
 } sgb_wgrad_desc;
 
 int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream);
+/* 1 if sgb_conv_wgrad(d) can also deliver d->dbias (the 3x3 / 64-channel kernel feeds a constant-one operand atom to the
+ * otherwise idle half of its last MMA group, so the bias gradient costs no extra pass over dy); 0 otherwise. */
+int sgb_conv_wgrad_fuses_dbias(const sgb_wgrad_desc* d);
 
 /* ------------------------------------------------------------------------------------------
  * Spectral normalisation (power iteration + sigma) and tensor-core weight packs.

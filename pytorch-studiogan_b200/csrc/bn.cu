@@ -417,8 +417,12 @@ extern "C" int sgb_bn_stats(const void* x, int64_t npix, int32_t C, int64_t x_cs
                             sgb_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SGB_REQUIRE(x && sum && sumsq && npix > 0 && C > 0 && C % 8 == 0 && x_cstride % 8 == 0);
-  SGB_CUDA(cudaMemsetAsync(sum, 0, sizeof(float) * C, stream));
-  SGB_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * C, stream));
+  if (sumsq == sum + C) {                              // the usual case: one [2][C] buffer -> one memset node
+    SGB_CUDA(cudaMemsetAsync(sum, 0, sizeof(float) * 2 * (size_t)C, stream));
+  } else {
+    SGB_CUDA(cudaMemsetAsync(sum, 0, sizeof(float) * C, stream));
+    SGB_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * C, stream));
+  }
   const int chunks = (C + kChunkC - 1) / kChunkC;
   long long target_blocks = 8LL * sm_count() / chunks;
   if (target_blocks < 1) target_blocks = 1;
@@ -466,10 +470,18 @@ extern "C" int sgb_bn_bwd_reduce(const void* dy, int64_t dy_cstride, const void*
   cudaStream_t stream = (cudaStream_t)stream_;
   SGB_REQUIRE(dy && x && scale && shift && mean && rstd && s1 && s2 && S1 && S2);
   SGB_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && dy_cstride % 8 == 0 && x_cstride % 8 == 0);
-  SGB_CUDA(cudaMemsetAsync(s1, 0, sizeof(float) * (size_t)B * C, stream));
-  SGB_CUDA(cudaMemsetAsync(s2, 0, sizeof(float) * (size_t)B * C, stream));
-  SGB_CUDA(cudaMemsetAsync(S1, 0, sizeof(float) * C, stream));
-  SGB_CUDA(cudaMemsetAsync(S2, 0, sizeof(float) * C, stream));
+  if (s2 == s1 + (size_t)B * C) {
+    SGB_CUDA(cudaMemsetAsync(s1, 0, sizeof(float) * 2 * (size_t)B * C, stream));
+  } else {
+    SGB_CUDA(cudaMemsetAsync(s1, 0, sizeof(float) * (size_t)B * C, stream));
+    SGB_CUDA(cudaMemsetAsync(s2, 0, sizeof(float) * (size_t)B * C, stream));
+  }
+  if (S2 == S1 + C) {
+    SGB_CUDA(cudaMemsetAsync(S1, 0, sizeof(float) * 2 * (size_t)C, stream));
+  } else {
+    SGB_CUDA(cudaMemsetAsync(S1, 0, sizeof(float) * C, stream));
+    SGB_CUDA(cudaMemsetAsync(S2, 0, sizeof(float) * C, stream));
+  }
   const int chunks = (C + kChunkC - 1) / kChunkC;
   const int HW = H * W;
   long long target = 8LL * sm_count() / ((long long)B * chunks);

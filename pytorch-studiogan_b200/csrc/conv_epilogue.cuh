@@ -151,6 +151,11 @@ struct EpiAux {
   uint32_t bytes;           // bytes of one box
   int c1, c2, c3;           // box coordinates (w, h, b) in the auxiliary tensor
   int arow;                 // staging-tile row this thread reads
+  // Prefetch: the box of the NEXT chunk (same tile, or this team's first chunk of the CTA's next tile) is requested as soon
+  // as the current chunk's staging tile has been consumed, so its ~1 us latency hides behind the store / the next MMAs.
+  uint32_t* primed;         // leader-only flag: the load for the upcoming chunk is already in flight
+  int has_next;             // next tile exists and has a chunk for this team
+  int n_nbase, n_c1, n_c2, n_c3;
 };
 
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
@@ -185,8 +190,11 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
     named_bar_sync(1 + team, 128);
     if (aux_kind) {                              // residual / mask chunk for this tile: one TMA box instead of strided 16-byte loads
       if (leader) {
-        mbar_arrive_expect_tx(aux->bar, aux->bytes);
-        tma_load_4d(aux->stage, aux->tm, aux->bar, nbase, aux->c1, aux->c2, aux->c3);
+        if (!*aux->primed) {
+          mbar_arrive_expect_tx(aux->bar, aux->bytes);
+          tma_load_4d(aux->stage, aux->tm, aux->bar, nbase, aux->c1, aux->c2, aux->c3);
+        }
+        *aux->primed = 0u;
       }
       mbar_wait(aux->bar, *aux->phase);
       *aux->phase ^= 1u;
@@ -268,6 +276,18 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
     if (leader) {
       tma_store_4d(tmY, stage, nbase, c1, c2, c3);
       bulk_commit();
+      if (aux_kind) {                            // every thread of the team is past its last read of the aux tile (barrier above)
+        const int cc2 = cc + chunk_stride;
+        if (cc2 * 64 < BN && n0 + cc2 * 64 < p.Cout) {
+          mbar_arrive_expect_tx(aux->bar, aux->bytes);
+          tma_load_4d(aux->stage, aux->tm, aux->bar, n0 + cc2 * 64, aux->c1, aux->c2, aux->c3);
+          *aux->primed = 1u;
+        } else if (aux->has_next) {
+          mbar_arrive_expect_tx(aux->bar, aux->bytes);
+          tma_load_4d(aux->stage, aux->tm, aux->bar, aux->n_nbase, aux->n_c1, aux->n_c2, aux->n_c3);
+          *aux->primed = 1u;
+        }
+      }
     }
   }
 }

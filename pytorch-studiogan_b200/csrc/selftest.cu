@@ -165,11 +165,28 @@ static int run_wgrad_case(const Case& c, bool verbose) {
   memset(&d, 0, sizeof(d));
   d.B = c.B; d.H = c.H; d.W = c.W; d.Cin = c.Cin; d.Cout = c.Cout; d.KH = c.KH; d.KW = c.KW; d.pad_h = c.ph; d.pad_w = c.pw;
   d.x = dx; d.x_cstride = c.Cin; d.dy = ddy; d.dy_cstride = c.Cout; d.dw = ddw; d.accumulate = 0;
+  float* ddb = nullptr;
+  if (sgb_conv_wgrad_fuses_dbias(&d)) {
+    CK(cudaMalloc(&ddb, c.Cout * 4));
+    d.dbias = ddb;
+  }
   int rc = sgb_conv_wgrad(&d, 0);
   cudaError_t se = cudaDeviceSynchronize();
   if (rc || se != cudaSuccess) {
     printf("[wgrad %-28s] LAUNCH FAIL rc=%d cuda=%s\n", c.name, rc, cudaGetErrorString(se));
     return 1;
+  }
+  size_t bad_b = 0;
+  if (ddb) {                                     // fused bias gradient: sum of dy over all pixels
+    std::vector<float> gb(c.Cout);
+    CK(cudaMemcpy(gb.data(), ddb, c.Cout * 4, cudaMemcpyDeviceToHost));
+    for (int co = 0; co < c.Cout; ++co) {
+      double r = 0;
+      for (size_t px = 0; px < (size_t)c.B * c.H * c.W; ++px) r += dy[px * c.Cout + co];
+      if (!(fabs(gb[co] - r) <= 2e-3 * (1.0 + fabs(r)))) { if (!bad_b) printf("    dbias[%d] got=%g ref=%g\n", co, gb[co], r); ++bad_b; }
+    }
+    printf("[wgrad %-28s] fused dbias %s\n", c.name, bad_b ? "FAIL" : "PASS");
+    cudaFree(ddb);
   }
   std::vector<float> got(nw);
   CK(cudaMemcpy(got.data(), ddw, nw * 4, cudaMemcpyDeviceToHost));
@@ -193,7 +210,7 @@ static int run_wgrad_case(const Case& c, bool verbose) {
     }
   }
   cudaFree(dx); cudaFree(ddy); cudaFree(ddw);
-  return bad ? 1 : 0;
+  return (bad || bad_b) ? 1 : 0;
 }
 
 // Layout probes: delta inputs, identity weights; prints where the energy lands.

@@ -160,8 +160,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool vec_ok = epi_vec_ok(p.e);
     const float alpha = p.e.alpha_ptr ? p.e.alpha * __ldg(p.e.alpha_ptr) : p.e.alpha;
     const uint32_t stage = epi_stage_base + team * kEpiStageBytes;
-    uint32_t aux_phase = 0;
+    uint32_t aux_phase = 0, aux_primed = 0;
     EpiAux aux;
+    aux.primed = &aux_primed; aux.has_next = 0; aux.n_nbase = aux.n_c1 = aux.n_c2 = aux.n_c3 = 0;
     aux.kind = p.aux_kind; aux.tm = &tmAux; aux.stage = aux_stage_base + team * kEpiStageBytes; aux.bar = aux_bar(team);
     aux.phase = &aux_phase; aux.bytes = (uint32_t)(p.aux_tw * p.aux_th * p.nb) * 128u;
     const bool aux_half = p.aux_kind == 1 && p.e.res_up2;
@@ -188,6 +189,19 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         aux.c1 = aux_half ? (wt * p.tw) >> 1 : wt * p.tw;
         aux.c2 = aux_half ? (ht * p.th) >> 1 : ht * p.th;
         aux.c3 = bt * p.nb;
+        const int ntile = tile + (int)gridDim.x;       // this CTA's next tile: its first chunk of this team is prefetched
+        aux.has_next = 0;
+        if (p.aux_kind && ntile < p.num_tiles) {
+          int u = ntile;
+          const int nt2 = u % p.tiles_n; u /= p.tiles_n;
+          const int wt2 = u % p.tiles_w; u /= p.tiles_w;
+          const int ht2 = u % p.tiles_h; u /= p.tiles_h;
+          aux.n_nbase = nt2 * p.BN + team * 64;
+          aux.has_next = (team * 64 < p.BN && aux.n_nbase < p.e.Cout) ? 1 : 0;
+          aux.n_c1 = aux_half ? (wt2 * p.tw) >> 1 : wt2 * p.tw;
+          aux.n_c2 = aux_half ? (ht2 * p.th) >> 1 : ht2 * p.th;
+          aux.n_c3 = u * p.nb;
+        }
         epilogue_tile_tma(p.e, &tmY, t_row, p.BN, n0, wt * p.tw, ht * p.th, bt * p.nb, valid, pix, rpix, alpha, stage, team, row,
                           leader, 2, p.aux_kind ? &aux : nullptr);
       } else if (team == 0) {
@@ -531,6 +545,10 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   return SGB_OK;
 }
 
+extern "C" int sgb_conv_wgrad_fuses_dbias(const sgb_wgrad_desc* d) {
+  return (d && env_int("SGB_WGRAD3X3", 1) && wgrad3x3_c64_eligible(d)) ? 1 : 0;
+}
+
 extern "C" int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SGB_REQUIRE(d && d->x && d->dy && d->dw);
@@ -538,6 +556,7 @@ extern "C" int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream_) {
   SGB_REQUIRE(d->Cin % 8 == 0 && d->x_cstride % 8 == 0 && d->Cout % 8 == 0 && d->dy_cstride % 8 == 0);
   SGB_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->dy & 15) == 0);
   if (env_int("SGB_WGRAD3X3", 1) && wgrad3x3_c64_eligible(d)) return launch_wgrad3x3_c64(d, stream);
+  SGB_REQUIRE(d->dbias == nullptr);   // only the fused 3x3 kernel produces the bias gradient (sgb_conv_wgrad_fuses_dbias)
 
   WgradArgs p;
   p.B = d->B; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;

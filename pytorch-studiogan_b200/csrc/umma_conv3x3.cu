@@ -108,9 +108,10 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // ------------------------------------------------------------- B producer: filter taps (resident or ring)
       if (p.resident) {
         mbar_arrive_expect_tx(b_full(0), 9u * p.kblocks * b_tile_bytes);
+        // resident order [kb][kw][kh]: the taps (kh, kw) and (kh + 1, kw) are adjacent, so one N = 2 BN operand covers both
         for (int tap = 0; tap < 9; ++tap)
           for (int kb = 0; kb < p.kblocks; ++kb)
-            tma_load_3d(b_base + (tap * p.kblocks + kb) * b_tile_bytes, &tmB, b_full(0), kb * 64, tap, 0);
+            tma_load_3d(b_base + ((kb * 3 + tap % 3) * 3 + tap / 3) * b_tile_bytes, &tmB, b_full(0), kb * 64, tap, 0);
       } else {
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -141,6 +142,31 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(a_full(sa_i), (ita / p.a_stages) & 1);
           tc_fence_after();
           const uint32_t sa = a_base + sa_i * a_stage_bytes;
+          if (p.resident) {
+            // Halo row r feeds output row 1 through tap row r - 1 and output row 0 through tap row r.  For r = 1, 2 both exist:
+            // ONE MMA with B = [W(r-1, kw); W(r, kw)] (N = 2 BN) writes the [row 1 | row 0] accumulator pair, so the A
+            // operand (the dominant shared-memory read at N = 64) is fetched once instead of twice.
+            const uint32_t d_pair = tmem_base + as * 2 * p.BN;
+            const uint32_t idesc2 = make_idesc_bf16(128, 2 * p.BN, 0, 0);
+            for (int r = 1; r <= 2; ++r)
+              for (int kw = 0; kw < 3; ++kw) {
+                const uint64_t bdesc = make_sdesc_sw128(b_base + ((kb * 3 + kw) * 3 + (r - 1)) * b_tile_bytes, 16, 1024);
+                const uint64_t adesc = sdesc_rows(sa + r * kRowBufBytes + kw * 128, p.bo_mode);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_f16_ss(d_pair, adesc + 2 * kk, bdesc + 2 * kk, idesc2, (kb > 0 || r > 1 || kw > 0 || kk > 0) ? 1u : 0u);
+              }
+            for (int e = 0; e < 2; ++e)          // r = 0: tap row 0 -> output row 0;  r = 3: tap row 2 -> output row 1
+              for (int kw = 0; kw < 3; ++kw) {
+                const uint64_t bdesc = make_sdesc_sw128(b_base + ((kb * 3 + kw) * 3 + (e ? 2 : 0)) * b_tile_bytes, 16, 1024);
+                const uint64_t adesc = sdesc_rows(sa + (e ? 3 : 0) * kRowBufBytes + kw * 128, p.bo_mode);
+                const uint32_t d_one = d_pair + (e ? 0 : p.BN);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) umma_f16_ss(d_one, adesc + 2 * kk, bdesc + 2 * kk, idesc, 1u);
+              }
+            umma_commit(a_empty(sa_i));
+            continue;
+          }
           for (int tap = 0; tap < 9; ++tap) {
             const int kh = tap / 3, kw = tap % 3;
             uint32_t bb;
@@ -190,7 +216,7 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int h = hp * 2 + j;
         const long long pix = ((long long)b * p.H + h) * p.W + w;
         const long long rpix = p.e.res_up2 ? (((long long)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) : pix;
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (as * 2 + j) * p.BN;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (as * 2 + (p.resident ? 1 - j : j)) * p.BN;
         if (p.use_tma) {
           // team t owns output row t.  epi_bufs == 2: both teams stage + TMA-store; epi_bufs == 1 (no room for a second
           // staging tile, C = 64): team 0 stages + TMA-stores row 0 while team 1 writes row 1 with direct 16-byte stores

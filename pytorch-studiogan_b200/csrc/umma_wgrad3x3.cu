@@ -32,6 +32,7 @@ struct W3Args {
   int tiles_w, tiles_h;          // tiles per row, row pairs per image
   long long tiles;               // B * tiles_h * tiles_w
   float* dw;
+  float* dbias;                  // optional: sum of dY over all pixels (idle atom of the unpaired tap reads constant ones)
 };
 
 __global__ void __launch_bounds__(kW3Threads, 1)
@@ -43,6 +44,7 @@ wgrad3x3_c64_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
   auto empty_bar = [&](int s) { return bar_base + 8u * (kW3Stages + s); };
   const uint32_t done_bar = bar_base + 8u * (2 * kW3Stages);
   const uint32_t holder = bar_base + 8u * (2 * kW3Stages + 1);
+  const uint32_t ones_base = (bar_base + 8u * (2 * kW3Stages + 2) + 1023u) & ~1023u;   // 2 KB of bf16 1.0 (16 K rows x 128 B)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -60,6 +62,11 @@ wgrad3x3_c64_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
   if (warp == 1) {
     tmem_alloc(holder, 512);
     tmem_relinquish();
+  }
+  if (p.dbias) {
+    for (int i = threadIdx.x; i < 2048 / 4; i += kW3Threads)
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(ones_base + 4u * i), "r"(0x3F803F80u) : "memory");
+    fence_proxy_async_smem();                     // the MMA reads this region through the async proxy
   }
   tc_fence_before();
   __syncthreads();
@@ -108,13 +115,18 @@ wgrad3x3_c64_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
             // second atom = next tap: +1 pixel, or (row + 1, dw = -1) for the pair (tap 2, tap 3): 130 - 2 pixels;
             // the unpaired tap 8 drags an idle atom one pixel further (rows ignored by the drain, reads stay in the slack)
             const uint32_t lbo = (tap == 2 ? (uint32_t)(kW3Halo - 2) : 1u) * 128u;
-            const uint64_t adesc = make_sdesc_sw128(xs + (uint32_t)off * 128u, lbo, 1024);
+            const uint32_t a0 = xs + (uint32_t)off * 128u;
+            const uint64_t adesc = make_sdesc_sw128(a0, lbo, 1024);
             const uint64_t bdesc = make_sdesc_sw128(ys + (uint32_t)(j * kW3Px) * 128u, 128 * kW3Px, 1024);
             const uint32_t d_tmem = tmem_base + (uint32_t)g * 64u;
 #pragma unroll
             for (int kk = 0; kk < kW3Px / 16; ++kk) {
               // 16 pixels (K) = two 8-row groups = 2048 bytes -> +128 in the (addr >> 4) field
-              umma_f16_ss(d_tmem, adesc + 128 * kk, bdesc + 128 * kk, idesc, (it > 0 || j > 0 || kk > 0) ? 1u : 0u);
+              uint64_t ad = adesc + 128 * kk;
+              // bias gradient for free: the idle second atom of the unpaired tap 8 is pointed (through the LBO) at a
+              // constant-one K slab, so rows 64..127 of its accumulator block receive sum_k dY[k][co]
+              if (g == 4 && p.dbias) ad = make_sdesc_sw128(a0 + 2048u * kk, ones_base - (a0 + 2048u * kk), 1024);
+              umma_f16_ss(d_tmem, ad, bdesc + 128 * kk, idesc, (it > 0 || j > 0 || kk > 0) ? 1u : 0u);
             }
           }
         }
@@ -138,6 +150,11 @@ wgrad3x3_c64_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
         __syncwarp();
         tmem_ld16(t_row + c0, v);
         tmem_ld_wait();
+        if (tap == 9 && m == 64 && p.dbias) {          // row (tap 9, ci 0): the bias gradient
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < p.Cout) atomicAdd(p.dbias + c0 + i, __uint_as_float(v[i]));
+        }
         if (tap >= 9 || ci >= p.Cin) continue;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -170,7 +187,11 @@ int launch_wgrad3x3_c64(const sgb_wgrad_desc* d, cudaStream_t stream) {
   p.tiles_h = d->H / 2;
   p.tiles = (long long)d->B * p.tiles_h * p.tiles_w;
   p.dw = d->dw;
-  if (!d->accumulate) SGB_CUDA(cudaMemsetAsync(d->dw, 0, sizeof(float) * (size_t)d->Cout * 9 * d->Cin, stream));
+  p.dbias = d->dbias;
+  if (!d->accumulate) {
+    SGB_CUDA(cudaMemsetAsync(d->dw, 0, sizeof(float) * (size_t)d->Cout * 9 * d->Cin, stream));
+    if (d->dbias) SGB_CUDA(cudaMemsetAsync(d->dbias, 0, sizeof(float) * (size_t)d->Cout, stream));
+  }
 
   CUtensorMap tmDY, tmX;
   {
@@ -187,7 +208,7 @@ int launch_wgrad3x3_c64(const sgb_wgrad_desc* d, cudaStream_t stream) {
     int rc = make_tmap_bf16(&tmX, d->x, 4, dims, strides, box);
     if (rc) return rc;
   }
-  const size_t smem = (size_t)kW3Stages * kW3Stage + 1024 + 8 * (2 * kW3Stages + 2) + 16;
+  const size_t smem = (size_t)kW3Stages * kW3Stage + 1024 + 8 * (2 * kW3Stages + 2) + 1024 + 2048 + 16;
   static bool attr_set = false;
   if (!attr_set) {
     SGB_CUDA(cudaFuncSetAttribute(wgrad3x3_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

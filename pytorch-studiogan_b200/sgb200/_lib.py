@@ -46,6 +46,7 @@ class WgradDesc(ctypes.Structure):
         ("x", c_p), ("x_cstride", c_i64),
         ("dy", c_p), ("dy_cstride", c_i64),
         ("dw", c_p), ("accumulate", c_int), ("per_image", c_int),
+        ("dbias", c_p),
     ]
 
 
@@ -55,6 +56,7 @@ SIGNATURES = {
     "sgb_device_check": (c_int, []),
     "sgb_bind_device": (c_int, [c_int]),
     "sgb_conv_fprop": (c_int, [ctypes.POINTER(ConvDesc), c_p]),
+    "sgb_conv_wgrad_fuses_dbias": (c_int, [ctypes.POINTER(WgradDesc)]),
     "sgb_conv_wgrad": (c_int, [ctypes.POINTER(WgradDesc), c_p]),
     "sgb_sn_workspace_floats": (c_i64, [c_int, c_int]),
     "sgb_sn_power_iter": (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_f, c_int, c_p]),

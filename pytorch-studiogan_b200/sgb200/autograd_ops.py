@@ -148,9 +148,14 @@ class ConvFn(TFunction):
             if dx.shape[1] != x.shape[1]:
                 dx = dx[:, :x.shape[1]]
         if ctx.needs_input_grad[1] and not SKIP_PARAM_GRADS:
-            G = K.conv_wgrad(x, dz, KH, KW, pad, pad)
+            if ctx.needs_input_grad[2]:
+                G, dbias = K.conv_wgrad(x, dz, KH, KW, pad, pad, want_dbias=True)
+                if dbias is not None:
+                    dbias = dbias[:Cout]
+            else:
+                G = K.conv_wgrad(x, dz, KH, KW, pad, pad)
             dW = K.sn_backward(G, weight, u_saved, v_saved, sigma, Cout, Cin, taps, cfg.get("perm_S", 1))
-        if ctx.needs_input_grad[2] and not SKIP_PARAM_GRADS:
+        if ctx.needs_input_grad[2] and not SKIP_PARAM_GRADS and dbias is None:
             dbias = K.bn_stats(dz)[0][:Cout]
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = K.pool2_fwd(dz, 2) if cfg.get("res_up2", False) else dz

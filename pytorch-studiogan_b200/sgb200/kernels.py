@@ -88,8 +88,10 @@ def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_u
     return out
 
 
-def conv_wgrad(x, dy, KH, KW, pad_h, pad_w, dw=None, accumulate=False, per_image=False):
-    """fp32 weight gradient in the fprop-pack layout [Cout][KH*KW][Cin] (or [B][...] when per_image)."""
+def conv_wgrad(x, dy, KH, KW, pad_h, pad_w, dw=None, accumulate=False, per_image=False, want_dbias=False):
+    """fp32 weight gradient in the fprop-pack layout [Cout][KH*KW][Cin] (or [B][...] when per_image).
+    want_dbias: returns (dw, dbias) where dbias is the fp32 [Cout] bias gradient if this launch can produce it for free,
+    else None (the caller then reduces dy itself)."""
     B, Cin, H, W, xcs = geom(x)
     _, Cout, _, _, dcs = geom(dy)
     if dw is None:
@@ -102,9 +104,13 @@ def conv_wgrad(x, dy, KH, KW, pad_h, pad_w, dw=None, accumulate=False, per_image
     d.x, d.x_cstride = x.data_ptr(), xcs
     d.dy, d.dy_cstride = dy.data_ptr(), dcs
     d.dw, d.accumulate, d.per_image = dw.data_ptr(), 1 if accumulate else 0, 1 if per_image else 0
+    dbias = None
+    if want_dbias and not accumulate and L.load().sgb_conv_wgrad_fuses_dbias(ctypes.byref(d)):
+        dbias = torch.empty(Cout, device=x.device, dtype=torch.float32)
+        d.dbias = dbias.data_ptr()
     L.call("sgb_conv_wgrad", ctypes.byref(d), _s(), tag="conv_wgrad %dx%d %d->%d @%dx%d%s" % (KH, KW, Cin, Cout, H, W, " per-image" if per_image else ""),
            flops=2.0 * B * H * W * Cout * Cin * KH * KW)
-    return dw
+    return (dw, dbias) if want_dbias else dw
 
 
 # ---------------------------------------------------------------------------------------------- spectral norm
