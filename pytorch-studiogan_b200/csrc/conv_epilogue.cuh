@@ -175,10 +175,11 @@ __device__ __forceinline__ bool epi_use_tma(const EpiArgs& p, int BN) {
 __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtensorMap* tmY, uint32_t t_row, int BN, int n0,
                                                   int c1, int c2, int c3, bool valid, long long pix, long long rpix, float alpha,
                                                   uint32_t stage, int team, int row, bool leader, int chunk_stride = 2,
-                                                  const EpiAux* aux = nullptr) {
+                                                  const EpiAux* aux = nullptr, uint32_t* sbuf = nullptr) {
   const bool res_pre = p.residual != nullptr && !p.res_after;
   const bool res_post = p.residual != nullptr && p.res_after;
-  const uint32_t srow = stage + (uint32_t)row * 128u;
+  // sbuf != nullptr: the team owns TWO staging tiles (stage, stage + 16 KiB) used alternately, so a chunk only waits for the
+  // store issued two chunks ago -- the latency of the previous tensor store is off the critical path.
   const uint32_t sw = (uint32_t)(row & 7);
   const int aux_kind = aux ? aux->kind : 0;                       // 1: residual tile via TMA, 2: mask tile via TMA
   const uint32_t arow_addr = aux ? aux->stage + (uint32_t)aux->arow * 128u : 0u;
@@ -186,7 +187,12 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
   for (int cc = (chunk_stride == 2 ? team : 0); cc * 64 < BN; cc += chunk_stride) {
     const int nbase = n0 + cc * 64;
     if (nbase >= p.Cout) break;
-    if (leader) bulk_wait_read0();               // the previous store of this team has finished reading the staging tile
+    const uint32_t stage_cur = stage + (sbuf ? (*sbuf & 1u) * kEpiStageBytes : 0u);
+    const uint32_t srow = stage_cur + (uint32_t)row * 128u;
+    if (leader) {                                // the store that last used this staging tile has finished reading it
+      if (sbuf) bulk_wait_read1(); else bulk_wait_read0();
+    }
+    if (sbuf) *sbuf ^= 1u;
     named_bar_sync(1 + team, 128);
     if (aux_kind) {                              // residual / mask chunk for this tile: one TMA box instead of strided 16-byte loads
       if (leader) {
@@ -274,7 +280,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
     fence_proxy_async_smem();                    // generic-proxy smem writes -> visible to the TMA (async proxy)
     named_bar_sync(1 + team, 128);
     if (leader) {
-      tma_store_4d(tmY, stage, nbase, c1, c2, c3);
+      tma_store_4d(tmY, stage_cur, nbase, c1, c2, c3);
       bulk_commit();
       if (aux_kind) {                            // every thread of the team is past its last read of the aux tile (barrier above)
         const int cc2 = cc + chunk_stride;

@@ -378,6 +378,10 @@ int main(int argc, char** argv) {
   if (on("wgrad"))
     for (const auto& c : wcases) fails += run_wgrad_case(c, true);
   printf("selftest[%s]: %d failing case(s)\n", mode, fails);
+  if (strcmp(mode, "one") == 0 && argc >= 8) {     // ./sgb_selftest one B H W Cin Cout K : time a single fprop shape (ncu target)
+    time_fprop("one", atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]));
+    return 0;
+  }
   if (strcmp(mode, "time") == 0) {
     time_fprop("3x3 64->64 256^2 B=32", 32, 256, 256, 64, 64, 3);
     time_fprop("3x3 128->128 128^2 B=32", 32, 128, 128, 128, 128, 3);

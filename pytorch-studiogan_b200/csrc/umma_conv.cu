@@ -33,6 +33,7 @@ struct FpropArgs {
   int w_mode;                     // 0: shared weights [Cout][taps][Cin]; 1: per-image [B][N][K]; 2: per-image MN-major [B][K][N]
   int stages;
   int use_tma;                    // epilogue through staging tiles + TMA tensor stores
+  int epi_nbuf;                   // staging tiles per epilogue team (2: stores overlap the next chunk's conversion)
   int aux_kind, aux_tw, aux_th;   // residual (1) / mask (2) tile staged by TMA; its box is aux_tw x aux_th x nb pixels
   int out_sub;                    // 2: store only even (h, w) outputs at (h/2, w/2) -> stride-2 convolution (Inception reduction blocks)
   uint32_t tmem_cols;
@@ -44,7 +45,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmAux, const FpropArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t epi_stage_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // two 16 KiB staging tiles when use_tma
-  const uint32_t aux_stage_base = epi_stage_base + (p.use_tma ? 2u * kEpiStageBytes : 0u);   // + two aux tiles when aux_kind
+  const uint32_t aux_stage_base = epi_stage_base + (p.use_tma ? 2u * p.epi_nbuf * kEpiStageBytes : 0u);   // + two aux tiles when aux_kind
   const uint32_t smem_base = aux_stage_base + (p.aux_kind ? 2u * kEpiStageBytes : 0u);
   const uint32_t b_bytes = (uint32_t)p.BN * kBlockK * 2;  // same size for K-major [BN][64] and MN-major (BN/64) x [64][64]
   const uint32_t stage_bytes = kABytes + b_bytes;  // multiple of 1024 because BN % 8 == 0 -> b_bytes % 1024 == 0
@@ -159,8 +160,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int wi = row % p.tw, hi = (row / p.tw) % p.th, bi = row / (p.tw * p.th);
     const bool vec_ok = epi_vec_ok(p.e);
     const float alpha = p.e.alpha_ptr ? p.e.alpha * __ldg(p.e.alpha_ptr) : p.e.alpha;
-    const uint32_t stage = epi_stage_base + team * kEpiStageBytes;
-    uint32_t aux_phase = 0, aux_primed = 0;
+    const uint32_t stage = epi_stage_base + team * p.epi_nbuf * kEpiStageBytes;
+    uint32_t aux_phase = 0, aux_primed = 0, sbuf = 0;
     EpiAux aux;
     aux.primed = &aux_primed; aux.has_next = 0; aux.n_nbase = aux.n_c1 = aux.n_c2 = aux.n_c3 = 0;
     aux.kind = p.aux_kind; aux.tm = &tmAux; aux.stage = aux_stage_base + team * kEpiStageBytes; aux.bar = aux_bar(team);
@@ -203,7 +204,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           aux.n_c3 = u * p.nb;
         }
         epilogue_tile_tma(p.e, &tmY, t_row, p.BN, n0, wt * p.tw, ht * p.th, bt * p.nb, valid, pix, rpix, alpha, stage, team, row,
-                          leader, 2, p.aux_kind ? &aux : nullptr);
+                          leader, 2, p.aux_kind ? &aux : nullptr, p.epi_nbuf == 2 ? &sbuf : nullptr);
       } else if (team == 0) {
         epilogue_row(p.e, t_row, p.BN, n0, valid, pix, rpix, alpha, vec_ok);
       }
@@ -492,8 +493,11 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
     else if (p.tw >= 2) { p.aux_kind = 1; p.aux_tw = p.tw / 2; p.aux_th = p.th >= 2 ? p.th / 2 : 1; }
   }
   const uint32_t stage_bytes = kABytes + BN * kBlockK * 2;
-  int stages = (int)(((200 - (p.use_tma ? 32 : 0) - (p.aux_kind ? 32 : 0)) * 1024) / stage_bytes);
+  // short-K layers (one or two K blocks per tile) are epilogue / store bound: give each team a second staging tile
+  p.epi_nbuf = (p.use_tma && p.taps * p.kblocks <= 2 && env_int("SGB_EPI_NBUF", 2) == 2) ? 2 : 1;
+  int stages = (int)(((200 - (p.use_tma ? 32 * p.epi_nbuf : 0) - (p.aux_kind ? 32 : 0)) * 1024) / stage_bytes);
   if (stages > 8) stages = 8;
+  if (stages < 2) { p.epi_nbuf = 1; stages = (int)(((200 - (p.use_tma ? 32 : 0) - (p.aux_kind ? 32 : 0)) * 1024) / stage_bytes); }
   if (stages < 2) stages = 2;
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * BN);
@@ -532,7 +536,7 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
     rc = make_act_tmap(&tmAux, ap, d->B, half ? d->H / 2 : d->H, half ? d->W / 2 : d->W, d->Cout, acs, p.aux_tw, p.aux_th, p.nb);
     if (rc) return rc;
   }
-  const size_t smem = (size_t)stages * stage_bytes + (p.use_tma ? 2 * kEpiStageBytes : 0) + (p.aux_kind ? 2 * kEpiStageBytes : 0) +
+  const size_t smem = (size_t)stages * stage_bytes + (p.use_tma ? 2 * p.epi_nbuf * kEpiStageBytes : 0) + (p.aux_kind ? 2 * kEpiStageBytes : 0) +
                       1024 + 8 * (2 * stages + 8) + 16;
   static size_t smem_set = 0;
   if (smem > smem_set) {
