@@ -108,8 +108,10 @@ D_DOWN = {"32": [True, True, False, False], "64": [True, True, True, True, False
 
 
 def deep_gen_block(sd, p, x, affine, out_channels, upsample, training=True, track=True):
-    """GenBlock.forward (src/models/big_resnet_deep_legacy.py:49-73)."""
-    x0 = x[:, :out_channels] if x.shape[1] != out_channels else x
+    """GenBlock.forward (src/models/big_resnet_deep_legacy.py:49-73); with a ``conv2d0`` in the state dict it is the
+    StudioGAN flavour (src/models/big_resnet_deep_studiogan.py:57-78): learnable 1x1 skip applied after the up-sampling."""
+    studiogan = _has(sd, p + "conv2d0.")
+    x0 = x if studiogan else (x[:, :out_channels] if x.shape[1] != out_channels else x)
     h = conv(sd, p + "conv2d1.", F.relu(cbn(sd, p + "bn1.", x, affine, training, track)), 0, training)
     h = F.relu(cbn(sd, p + "bn2.", h, affine, training, track))
     if upsample:
@@ -119,6 +121,8 @@ def deep_gen_block(sd, p, x, affine, out_channels, upsample, training=True, trac
     h = conv(sd, p + "conv2d4.", F.relu(cbn(sd, p + "bn4.", h, affine, training, track)), 0, training)
     if upsample:
         x0 = F.interpolate(x0, scale_factor=2, mode="nearest")
+    if studiogan:
+        x0 = conv(sd, p + "conv2d0.", x0, 0, training)
     return h + x0
 
 
@@ -166,6 +170,27 @@ def deep_disc_block(sd, p, x, downsample, training=True):
     return h + x0
 
 
+def deep_disc_block_studiogan(sd, p, x, downsample, optblock, training=True):
+    """DiscBlock.forward of the StudioGAN flavour (src/models/big_resnet_deep_studiogan.py:233-253): pooling before the
+    last activation, skip = conv2d0 (pool first in the opt block, conv first otherwise); the in-place activation
+    rectifies the aliased skip tensor exactly as in the legacy variant."""
+    x = F.relu(x)
+    x0 = x
+    h = conv(sd, p + "conv2d1.", x, 0, training)
+    h = conv(sd, p + "conv2d2.", F.relu(h), 1, training)
+    h = conv(sd, p + "conv2d3.", F.relu(h), 1, training)
+    if downsample:
+        h = F.avg_pool2d(h, 2)
+    h = conv(sd, p + "conv2d4.", F.relu(h), 0, training)
+    if optblock:
+        x0 = conv(sd, p + "conv2d0.", F.avg_pool2d(x0, 2), 0, training)
+    elif _has(sd, p + "conv2d0."):
+        x0 = conv(sd, p + "conv2d0.", x0, 0, training)
+        if downsample:
+            x0 = F.avg_pool2d(x0, 2)
+    return h + x0
+
+
 def disc_head_pd(sd, h, label, training=True, cond="PD"):
     """Sum-pooled features -> adversarial logit (+ projection) (src/models/big_resnet_deep_legacy.py:344-372)."""
     adv = torch.squeeze(linear(sd, "linear1.", h, training))
@@ -175,8 +200,9 @@ def disc_head_pd(sd, h, label, training=True, cond="PD"):
 
 
 def deep_discriminator(sd, x, label, img_size, d_conv_dim, d_depth, attn_d_loc=(), apply_attn=False, training=True,
-                       cond="PD"):
-    """Discriminator.forward (src/models/big_resnet_deep_legacy.py:334-413); returns (adv_output, h)."""
+                       cond="PD", studiogan=False):
+    """Discriminator.forward (src/models/big_resnet_deep_legacy.py:334-413; studiogan=True: the same loop of
+    src/models/big_resnet_deep_studiogan.py:345-424 with its block); returns (adv_output, h)."""
     key = str(img_size)
     in_dims = [d_conv_dim * m for m in D_IN[key]]
     down = D_DOWN[key]
@@ -184,7 +210,11 @@ def deep_discriminator(sd, x, label, img_size, d_conv_dim, d_depth, attn_d_loc=(
     bi = 0
     for index in range(len(in_dims)):
         for d_index in range(d_depth):
-            h = deep_disc_block(sd, "blocks.%d.0." % bi, h, bool(down[index] and d_index == 0), training)
+            if studiogan:
+                h = deep_disc_block_studiogan(sd, "blocks.%d.0." % bi, h, bool(down[index] and d_index == 0),
+                                              index == 0 and d_index == 0, training)
+            else:
+                h = deep_disc_block(sd, "blocks.%d.0." % bi, h, bool(down[index] and d_index == 0), training)
             bi += 1
         if (index + 1) in attn_d_loc and apply_attn:
             h = self_attention(sd, "blocks.%d.0." % bi, h, training)

@@ -28,6 +28,7 @@ import utils.ops as rops  # noqa: E402  (reference)
 import utils.losses as rlosses  # noqa: E402
 import utils.ema as rema  # noqa: E402
 import models.big_resnet_deep_legacy as rdeep  # noqa: E402
+import models.big_resnet_deep_studiogan as rdeep_sg  # noqa: E402
 import models.big_resnet as rbig  # noqa: E402
 import models.resnet as rres  # noqa: E402
 import scipy.linalg  # noqa: E402
@@ -66,7 +67,7 @@ def sd_np(module, prefix, buffers_only=False):
             if not (buffers_only and k in params)}
 
 
-def golden_deep(tag, img_size, conv_dim, depth, attn, z_dim=16, shared=16, classes=5, B=3):
+def golden_deep(tag, img_size, conv_dim, depth, attn, z_dim=16, shared=16, classes=5, B=3, rdeep=rdeep):
     torch.manual_seed(1234)
     M = modules()
     G = rdeep.Generator(z_dim=z_dim, g_shared_dim=shared, img_size=img_size, g_conv_dim=conv_dim, apply_attn=attn,
@@ -286,6 +287,7 @@ def golden_metrics():
 if __name__ == "__main__":
     golden_deep("deep32_c8", 32, 8, 1, attn=False)
     golden_deep("deep32_c16_attn_d2", 32, 16, 2, attn=True, B=2)
+    golden_deep("deepsg32_c8", 32, 8, 1, attn=False, B=8, rdeep=rdeep_sg)  # StudioGAN flavour of BigGAN-Deep
     golden_deep("deep32_c8_b16", 32, 8, 1, attn=False, B=16)      # well-conditioned BatchNorm statistics for gradient parity
     golden_resfamily("biggan32_c32_attn", "big_resnet", 32, True, True, True, "cBN", "PD", "hinge", B=4)
     golden_resfamily("sngan32_c16", "resnet", 16, False, False, True, "W/O", "W/O", "hinge", z_dim=32)

@@ -209,10 +209,11 @@ def test_adam_ema_kernel_matches_torch_adam():
 
 
 # ------------------------------------------------------------------------------------------------ full models vs golden
-def _build_from_golden(g, conv_dim, depth, attn, dev):
+def _build_from_golden(g, conv_dim, depth, attn, dev, backbone="big_resnet_deep_legacy"):
+    import importlib
     from sgb200 import config as C
-    from sgb200.models import big_resnet_deep_legacy as deep
-    M = C.make_modules(True, True, "cBN", "big_resnet_deep_legacy")
+    deep = importlib.import_module("sgb200.models." + backbone)
+    M = C.make_modules(True, True, "cBN", backbone)
     MODEL = C._Section(info_type="N/A", g_info_injection="N/A")
     G = deep.Generator(z_dim=16, g_shared_dim=16, img_size=32, g_conv_dim=conv_dim, apply_attn=attn, attn_g_loc=[2],
                        g_cond_mtd="cBN", num_classes=5, g_init="ortho", g_depth=depth, mixed_precision=False, MODULES=M, MODEL=MODEL)
@@ -244,7 +245,7 @@ def _worst_grad(net, g, prefix):
 
 
 @pytest.mark.parametrize("tag,conv_dim,depth,attn", [("deep32_c8", 8, 1, False), ("deep32_c16_attn_d2", 16, 2, True),
-                                                     ("deep32_c8_b16", 8, 1, False)])
+                                                     ("deep32_c8_b16", 8, 1, False), ("deepsg32_c8", 8, 1, False)])
 def test_biggan_deep_d_and_g_phase_vs_reference_golden(golden_dir, tag, conv_dim, depth, attn):
     """The reference's own D-phase / G-phase numbers (src/worker.py:213-681 order) reproduced by the CUDA path.
     Tolerance (stated): relative L2 error <= 4e-2 for images / features / logits and <= 1e-1 for parameter gradients
@@ -258,7 +259,8 @@ def test_biggan_deep_d_and_g_phase_vs_reference_golden(golden_dir, tag, conv_dim
     from sgb200.utils import losses
     dev = _cuda()
     g = np.load(os.path.join(golden_dir, tag + ".npz"))
-    G, D = _build_from_golden(g, conv_dim, depth, attn, dev)
+    G, D = _build_from_golden(g, conv_dim, depth, attn, dev,
+                              "big_resnet_deep_studiogan" if tag.startswith("deepsg") else "big_resnet_deep_legacy")
     z, yf = torch.from_numpy(g["z"]).to(dev), torch.from_numpy(g["y_fake"]).to(dev)
     real, yr = torch.from_numpy(g["real"]).to(dev), torch.from_numpy(g["y_real"]).to(dev)
     for p in G.parameters():

@@ -60,8 +60,9 @@ def test_struct_layout_matches_header():
 
 
 def _build(tag_cfg):
-    from sgb200.models import big_resnet_deep_legacy as deep
-    M = C.make_modules(True, True, "cBN", "big_resnet_deep_legacy")
+    import importlib
+    deep = importlib.import_module("sgb200.models." + tag_cfg.get("backbone", "big_resnet_deep_legacy"))
+    M = C.make_modules(True, True, "cBN", tag_cfg.get("backbone", "big_resnet_deep_legacy"))
     MODEL = C._Section(info_type="N/A", g_info_injection="N/A")
     torch.manual_seed(1234)
     G = deep.Generator(z_dim=16, g_shared_dim=16, img_size=32, g_conv_dim=tag_cfg["conv_dim"], apply_attn=tag_cfg["attn"],
@@ -74,7 +75,8 @@ def _build(tag_cfg):
 
 
 @pytest.mark.parametrize("tag,cfg", [("deep32_c8", dict(conv_dim=8, depth=1, attn=False)),
-                                     ("deep32_c16_attn_d2", dict(conv_dim=16, depth=2, attn=True))])
+                                     ("deep32_c16_attn_d2", dict(conv_dim=16, depth=2, attn=True)),
+                                     ("deepsg32_c8", dict(conv_dim=8, depth=1, attn=False, backbone="big_resnet_deep_studiogan"))])
 def test_state_dict_keys_and_seeded_init_match_reference(golden_dir, tag, cfg):
     g = np.load(os.path.join(golden_dir, tag + ".npz"))
     G, D = _build(cfg)

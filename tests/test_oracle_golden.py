@@ -10,7 +10,8 @@ from oracle import studiogan_oracle as O
 
 CASES = [("deep32_c8", dict(img_size=32, conv_dim=8, depth=1, attn=False)),
          ("deep32_c16_attn_d2", dict(img_size=32, conv_dim=16, depth=2, attn=True)),
-         ("deep32_c8_b16", dict(img_size=32, conv_dim=8, depth=1, attn=False))]
+         ("deep32_c8_b16", dict(img_size=32, conv_dim=8, depth=1, attn=False)),
+         ("deepsg32_c8", dict(img_size=32, conv_dim=8, depth=1, attn=False, studiogan=True))]
 
 
 def load_sd(npz, prefix, grad=False):
@@ -34,7 +35,8 @@ def test_deep_d_phase_and_g_phase(golden_dir, tag, cfg):
     z, yf = torch.from_numpy(g["z"]), torch.from_numpy(g["y_fake"])
     real, yr = torch.from_numpy(g["real"]), torch.from_numpy(g["y_real"])
     kw_g = dict(img_size=cfg["img_size"], g_conv_dim=cfg["conv_dim"], g_depth=cfg["depth"], attn_g_loc=(2,), apply_attn=cfg["attn"])
-    kw_d = dict(img_size=cfg["img_size"], d_conv_dim=cfg["conv_dim"], d_depth=cfg["depth"], attn_d_loc=(1,), apply_attn=cfg["attn"])
+    kw_d = dict(img_size=cfg["img_size"], d_conv_dim=cfg["conv_dim"], d_depth=cfg["depth"], attn_d_loc=(1,), apply_attn=cfg["attn"],
+                studiogan=cfg.get("studiogan", False))
 
     # discriminator phase
     sdG = load_sd(g, "G0/")
