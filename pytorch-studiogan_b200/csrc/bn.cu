@@ -231,11 +231,25 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
     const float v1 = a1[i], v2 = a2[i];
     atomicAdd(s1 + (size_t)b * C + c, v1);
     atomicAdd(s2 + (size_t)b * C + c, v2);
-    // d(xhat) = dz * g1 with g1 = scale / rstd (cBN: 1+gain, affine: weight, plain: 1)
-    const float g1 = scale[(size_t)b * bstride + c] / rstd[c];
-    atomicAdd(S1 + c, g1 * v1);
-    atomicAdd(S2 + c, g1 * v2);
   }
+}
+
+// S1[c] = sum_b g1[b,c] * s1[b,c], S2 likewise, with g1 = scale / rstd (cBN: 1 + gain, affine: weight, plain: 1): d(xhat) = dz * g1.
+// A separate C-thread pass over the [B][C] partials instead of B * blocks atomics per channel on two hot addresses.
+__global__ void bn_bwd_total_kernel(const float* __restrict__ s1, const float* __restrict__ s2, const float* __restrict__ scale,
+                                    int bstride, const float* __restrict__ rstd, int B, int C, float* __restrict__ S1,
+                                    float* __restrict__ S2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float ir = 1.f / rstd[c];
+  float a1 = 0.f, a2 = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float g1 = scale[(size_t)b * bstride + c] * ir;
+    a1 = fmaf(g1, s1[(size_t)b * C + c], a1);
+    a2 = fmaf(g1, s2[(size_t)b * C + c], a2);
+  }
+  S1[c] = a1;
+  S2[c] = a2;
 }
 
 // dx = scale[b,c]*dz - rstd*(S1/N) - rstd*(S2/N)*xhat   (train) ;   dx = scale[b,c]*dz   (eval: use_batch_stats = 0)
@@ -476,12 +490,7 @@ extern "C" int sgb_bn_bwd_reduce(const void* dy, int64_t dy_cstride, const void*
     SGB_CUDA(cudaMemsetAsync(s1, 0, sizeof(float) * (size_t)B * C, stream));
     SGB_CUDA(cudaMemsetAsync(s2, 0, sizeof(float) * (size_t)B * C, stream));
   }
-  if (S2 == S1 + C) {
-    SGB_CUDA(cudaMemsetAsync(S1, 0, sizeof(float) * 2 * (size_t)C, stream));
-  } else {
-    SGB_CUDA(cudaMemsetAsync(S1, 0, sizeof(float) * C, stream));
-    SGB_CUDA(cudaMemsetAsync(S2, 0, sizeof(float) * C, stream));
-  }
+
   const int chunks = (C + kChunkC - 1) / kChunkC;
   const int HW = H * W;
   long long target = 8LL * sm_count() / ((long long)B * chunks);
@@ -491,6 +500,8 @@ extern "C" int sgb_bn_bwd_reduce(const void* dy, int64_t dy_cstride, const void*
   dim3 grid((HW + ppb - 1) / ppb, B, chunks);
   bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>((const bf16*)dy, dy_cstride, (const bf16*)x, x_cstride, H, W, C, scale, shift,
                                                 per_image ? C : 0, mean, rstd, relu, up2, s1, s2, S1, S2, ppb);
+  SGB_LAUNCH_CHECK();
+  bn_bwd_total_kernel<<<(C + 127) / 128, 128, 0, stream>>>(s1, s2, scale, per_image ? C : 0, rstd, B, C, S1, S2);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }
