@@ -262,6 +262,31 @@ def _no_ema(MODEL):
     return m
 
 
+def shutdown(worker, world):
+    """Leave without hanging: captured CUDA graphs that contain NCCL kernels must die before the process group does, and a
+    watchdog hard-exits if the teardown still blocks (the JSON line is already flushed by then)."""
+    sys.stdout.flush()
+    if world <= 1:
+        return
+
+    def _hard_exit():
+        time.sleep(20.0)
+        os._exit(0)
+    threading.Thread(target=_hard_exit, daemon=True).start()
+    for name in ("_d_graph", "_g_graph"):
+        if getattr(worker, name, None) is not None:
+            setattr(worker, name, None)
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        pass
+    os._exit(0)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -374,8 +399,7 @@ def main():
             fid50k = {"error": repr(ex)}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown(worker, world)
         return
 
     peaks = {}
@@ -421,8 +445,7 @@ def main():
             "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "fid50k": fid50k,
             "clocks": sampler.summary()}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown(worker, world)
 
 
 if __name__ == "__main__":
