@@ -91,6 +91,34 @@ __global__ void __launch_bounds__(256) pool2_fwd_kernel(const bf16* __restrict__
   }
 }
 
+// a0 = relu(x) at full resolution AND y = avgpool2(a0) in one pass (entry of a down-sampling discriminator block: the skip
+// path pools the rectified input, big_resnet_deep_legacy.py:211-224); saves re-reading a0 for the pooling.
+__global__ void __launch_bounds__(256) relu_pool2_kernel(const bf16* __restrict__ x, long long xs, bf16* __restrict__ a0,
+                                                          long long as_, bf16* __restrict__ y, long long ys, int B, int Ho, int Wo,
+                                                          int C) {
+  const int VG = C >> 3;
+  const long long total = (long long)B * Ho * Wo * VG;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int g = (int)(i % VG);
+    const long long p = i / VG;
+    const int wo = (int)(p % Wo), ho = (int)((p / Wo) % Ho), b = (int)(p / ((long long)Wo * Ho));
+    const long long q = ((long long)b * (2 * Ho) + 2 * ho) * (2 * Wo) + 2 * wo;
+    const long long qs[4] = {q, q + 1, q + 2 * Wo, q + 2 * Wo + 1};
+    float f[4][8], o[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) unpack8(__ldg(reinterpret_cast<const uint4*>(x + qs[k] * xs) + g), f[k]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) f[k][j] = fmaxf(f[k][j], 0.f);
+      o[j] = 0.25f * (f[0][j] + f[1][j] + f[2][j] + f[3][j]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) reinterpret_cast<uint4*>(a0 + qs[k] * as_)[g] = pack8(f[k]);
+    reinterpret_cast<uint4*>(y + p * ys)[g] = pack8(o);
+  }
+}
+
 // Backward of 2x2 pooling, one thread = 8 channels of one OUTPUT-resolution pixel, writes the 4 input-resolution pixels.
 // mode 0 (avg): dx = 0.25*dy; mode 1 (max): dy routed to the first maximum in (h,w) scan order (torch MaxPool2d).
 // Optional: add (same layout as dx) is summed in, relu_src masks the result where relu_src <= 0.
@@ -605,6 +633,16 @@ extern "C" int sgb_pool2_fwd(const void* x, int64_t xs, void* y, int64_t ys, int
   SGB_REQUIRE(x && y && B > 0 && Ho > 0 && Wo > 0 && C > 0 && C % 8 == 0 && xs % 8 == 0 && ys % 8 == 0);
   pool2_fwd_kernel<<<ew_blocks((long long)B * Ho * Wo * (C / 8)), 256, 0, stream>>>((const bf16*)x, xs, (bf16*)y, ys, B, Ho, Wo, C,
                                                                                   mode);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_relu_pool2(const void* x, int64_t xs, void* a0, int64_t as_, void* y, int64_t ys, int32_t B, int32_t Ho,
+                              int32_t Wo, int32_t C, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(x && a0 && y && B > 0 && Ho > 0 && Wo > 0 && C > 0 && C % 8 == 0 && xs % 8 == 0 && as_ % 8 == 0 && ys % 8 == 0);
+  relu_pool2_kernel<<<ew_blocks((long long)B * Ho * Wo * (C / 8)), 256, 0, stream>>>((const bf16*)x, xs, (bf16*)a0, as_, (bf16*)y, ys, B,
+                                                                                    Ho, Wo, C);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }

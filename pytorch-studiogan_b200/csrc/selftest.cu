@@ -374,6 +374,7 @@ int main(int argc, char** argv) {
       {"w3 c64->32 128x128 B=1",       1, 128, 128, 64, 32, 3, 3, 1, 1},
       {"w3 c32->64 128x128 B=1",       1, 128, 128, 32, 64, 3, 3, 1, 1},
       {"w3 c64->64 128x128 B=5",       5, 128, 128, 64, 64, 3, 3, 1, 1},
+      {"w3 c128->8 128x128 B=2",       2, 128, 128, 128, 8, 3, 3, 1, 1},
   };
   if (on("wgrad"))
     for (const auto& c : wcases) fails += run_wgrad_case(c, true);

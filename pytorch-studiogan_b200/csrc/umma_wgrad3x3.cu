@@ -28,7 +28,8 @@ static constexpr uint32_t kW3Stage = kW3DyBytes + kW3XAlloc;
 static constexpr int kW3Stages = 2;
 
 struct W3Args {
-  int H, W, Cin, Cout;
+  int H, W, Cin, Cout;           // Cin: channels of THIS launch's 64-wide input-channel block
+  int dw_cin;                    // row pitch of dw (= the layer's full Cin)
   int tiles_w, tiles_h;          // tiles per row, row pairs per image
   long long tiles;               // B * tiles_h * tiles_w
   float* dw;
@@ -159,7 +160,7 @@ wgrad3x3_c64_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int co = c0 + i;
-          if (co < p.Cout) atomicAdd(p.dw + ((long long)co * 9 + tap) * p.Cin + ci, __uint_as_float(v[i]));
+          if (co < p.Cout) atomicAdd(p.dw + ((long long)co * 9 + tap) * p.dw_cin + ci, __uint_as_float(v[i]));
         }
       }
     }
@@ -175,37 +176,24 @@ wgrad3x3_c64_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_const
 }
 
 bool wgrad3x3_c64_eligible(const sgb_wgrad_desc* d) {
-  return d->KH == 3 && d->KW == 3 && d->pad_h == 1 && d->pad_w == 1 && !d->per_image && d->Cin <= 64 && d->Cin % 8 == 0 &&
+  // Cin > 64 (the generator's 128 -> 3 output convolution) runs as one launch per 64-channel block of the input
+  return d->KH == 3 && d->KW == 3 && d->pad_h == 1 && d->pad_w == 1 && !d->per_image &&
+         ((d->Cin <= 64 && d->Cin % 8 == 0) || (d->Cin % 64 == 0 && d->Cin <= 256 && d->Cout <= 16)) &&
          d->Cout <= 64 && d->Cout % 8 == 0 && d->W % kW3Px == 0 && d->H % 2 == 0 &&
          (long long)d->B * (d->H / 2) * (d->W / kW3Px) >= 64;
 }
 
 int launch_wgrad3x3_c64(const sgb_wgrad_desc* d, cudaStream_t stream) {
-  W3Args p;
-  p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
-  p.tiles_w = d->W / kW3Px;
-  p.tiles_h = d->H / 2;
-  p.tiles = (long long)d->B * p.tiles_h * p.tiles_w;
-  p.dw = d->dw;
-  p.dbias = d->dbias;
   if (!d->accumulate) {
     SGB_CUDA(cudaMemsetAsync(d->dw, 0, sizeof(float) * (size_t)d->Cout * 9 * d->Cin, stream));
     if (d->dbias) SGB_CUDA(cudaMemsetAsync(d->dbias, 0, sizeof(float) * (size_t)d->Cout, stream));
   }
-
-  CUtensorMap tmDY, tmX;
+  CUtensorMap tmDY;
   {
     uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
     uint64_t strides[3] = {(uint64_t)d->dy_cstride * 2, (uint64_t)d->dy_cstride * 2 * d->W, (uint64_t)d->dy_cstride * 2 * d->W * d->H};
     uint32_t box[4] = {64, (uint32_t)kW3Px, 2, 1};
     int rc = make_tmap_bf16(&tmDY, d->dy, 4, dims, strides, box);
-    if (rc) return rc;
-  }
-  {
-    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
-    uint64_t strides[3] = {(uint64_t)d->x_cstride * 2, (uint64_t)d->x_cstride * 2 * d->W, (uint64_t)d->x_cstride * 2 * d->W * d->H};
-    uint32_t box[4] = {64, (uint32_t)kW3Halo, 4, 1};
-    int rc = make_tmap_bf16(&tmX, d->x, 4, dims, strides, box);
     if (rc) return rc;
   }
   const size_t smem = (size_t)kW3Stages * kW3Stage + 1024 + 8 * (2 * kW3Stages + 2) + 1024 + 2048 + 16;
@@ -214,9 +202,26 @@ int launch_wgrad3x3_c64(const sgb_wgrad_desc* d, cudaStream_t stream) {
     SGB_CUDA(cudaFuncSetAttribute(wgrad3x3_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int grid = p.tiles < sm_count() ? (int)p.tiles : sm_count();
-  wgrad3x3_c64_kernel<<<grid, kW3Threads, smem, stream>>>(tmDY, tmX, p);
-  SGB_LAUNCH_CHECK();
+  for (int ci0 = 0; ci0 < d->Cin; ci0 += 64) {
+    W3Args p;
+    p.H = d->H; p.W = d->W; p.Cout = d->Cout;
+    p.Cin = d->Cin - ci0 < 64 ? d->Cin - ci0 : 64;
+    p.dw_cin = d->Cin;
+    p.tiles_w = d->W / kW3Px;
+    p.tiles_h = d->H / 2;
+    p.tiles = (long long)d->B * p.tiles_h * p.tiles_w;
+    p.dw = d->dw + ci0;
+    p.dbias = ci0 == 0 ? d->dbias : nullptr;
+    CUtensorMap tmX;
+    uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+    uint64_t strides[3] = {(uint64_t)d->x_cstride * 2, (uint64_t)d->x_cstride * 2 * d->W, (uint64_t)d->x_cstride * 2 * d->W * d->H};
+    uint32_t box[4] = {64, (uint32_t)kW3Halo, 4, 1};
+    int rc = make_tmap_bf16(&tmX, (const bf16*)d->x + ci0, 4, dims, strides, box);
+    if (rc) return rc;
+    const int grid = p.tiles < sm_count() ? (int)p.tiles : sm_count();
+    wgrad3x3_c64_kernel<<<grid, kW3Threads, smem, stream>>>(tmDY, tmX, p);
+    SGB_LAUNCH_CHECK();
+  }
   return SGB_OK;
 }
 

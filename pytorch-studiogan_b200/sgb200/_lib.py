@@ -73,6 +73,7 @@ SIGNATURES = {
                                  c_f, c_int, c_int, c_int, c_p, c_i64, c_p]),
     "sgb_axpby": (c_int, [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i64, c_int, c_f, c_p, c_f, c_int, c_p]),
     "sgb_pool2_fwd": (c_int, [c_p, c_i64, c_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "sgb_relu_pool2": (c_int, [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_int, c_int, c_int, c_int, c_p]),
     "sgb_pool2_bwd": (c_int, [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_int, c_int, c_int, c_int,
                               c_int, c_p]),
     "sgb_softmax_rows": (c_int, [c_p, c_p, c_i64, c_int, c_p]),

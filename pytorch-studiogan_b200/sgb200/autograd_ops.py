@@ -360,8 +360,11 @@ class DBlockEntryFn(TFunction):
 
     @staticmethod
     def forward(ctx, x, downsample):
-        a0 = K.axpby(x, relu=True)
-        px = K.pool2_fwd(a0, 0) if downsample else a0.view_as(a0)
+        if downsample and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
+            a0, px = K.relu_pool2(x)
+        else:
+            a0 = K.axpby(x, relu=True)
+            px = K.pool2_fwd(a0, 0) if downsample else a0.view_as(a0)
         ctx.downsample = downsample
         ctx.save_for_backward(a0)
         return a0, px

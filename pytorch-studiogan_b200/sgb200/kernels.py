@@ -222,6 +222,16 @@ def pool2_fwd(x, mode, out=None):
     return out
 
 
+def relu_pool2(x):
+    """(relu(x), avgpool2(relu(x))) in one pass."""
+    B, C, H, W, xs = geom(x)
+    a0 = empty_nhwc(B, C, H, W, x.device)
+    y = empty_nhwc(B, C, H // 2, W // 2, x.device)
+    L.call("sgb_relu_pool2", L.ptr(x), xs, L.ptr(a0), geom(a0)[4], L.ptr(y), geom(y)[4], B, H // 2, W // 2, C, _s(),
+           nbytes=_nb(x, a0, y))
+    return a0, y
+
+
 def pool2_bwd(dy, mode, x=None, add=None, relu_src=None):
     B, C, Ho, Wo, dys = geom(dy)
     dx = empty_nhwc(B, C, 2 * Ho, 2 * Wo, dy.device)
