@@ -236,20 +236,29 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
 
 // S1[c] = sum_b g1[b,c] * s1[b,c], S2 likewise, with g1 = scale / rstd (cBN: 1 + gain, affine: weight, plain: 1): d(xhat) = dz * g1.
 // A separate C-thread pass over the [B][C] partials instead of B * blocks atomics per channel on two hot addresses.
-__global__ void bn_bwd_total_kernel(const float* __restrict__ s1, const float* __restrict__ s2, const float* __restrict__ scale,
-                                    int bstride, const float* __restrict__ rstd, int B, int C, float* __restrict__ S1,
-                                    float* __restrict__ S2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) bn_bwd_total_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
+                                                            const float* __restrict__ scale, int bstride,
+                                                            const float* __restrict__ rstd, int B, int C, float* __restrict__ S1,
+                                                            float* __restrict__ S2) {
+  // one warp per channel, lanes stride over the images
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   const float ir = 1.f / rstd[c];
   float a1 = 0.f, a2 = 0.f;
-  for (int b = 0; b < B; ++b) {
+  for (int b = lane; b < B; b += 32) {
     const float g1 = scale[(size_t)b * bstride + c] * ir;
     a1 = fmaf(g1, s1[(size_t)b * C + c], a1);
     a2 = fmaf(g1, s2[(size_t)b * C + c], a2);
   }
-  S1[c] = a1;
-  S2[c] = a2;
+  for (int o = 16; o > 0; o >>= 1) {
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if (lane == 0) {
+    S1[c] = a1;
+    S2[c] = a2;
+  }
 }
 
 // dx = scale[b,c]*dz - rstd*(S1/N) - rstd*(S2/N)*xhat   (train) ;   dx = scale[b,c]*dz   (eval: use_batch_stats = 0)
@@ -501,7 +510,7 @@ extern "C" int sgb_bn_bwd_reduce(const void* dy, int64_t dy_cstride, const void*
   bn_bwd_reduce_kernel<<<grid, 256, 0, stream>>>((const bf16*)dy, dy_cstride, (const bf16*)x, x_cstride, H, W, C, scale, shift,
                                                 per_image ? C : 0, mean, rstd, relu, up2, s1, s2, S1, S2, ppb);
   SGB_LAUNCH_CHECK();
-  bn_bwd_total_kernel<<<(C + 127) / 128, 128, 0, stream>>>(s1, s2, scale, per_image ? C : 0, rstd, B, C, S1, S2);
+  bn_bwd_total_kernel<<<(C + 7) / 8, 256, 0, stream>>>(s1, s2, scale, per_image ? C : 0, rstd, B, C, S1, S2);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }
