@@ -45,6 +45,18 @@ class TFunction(Function):
         raise NotImplementedError("no tangent rule for this op (gradient penalty through it is unsupported)")
 
 
+def _direct_grad(p):
+    """The arena-backed ``.grad`` of a leaf parameter that opted in (utils/arena.GradArena.attach), else None.  ConvFn then
+    adds its weight gradient there itself and reports no gradient to autograd, which would otherwise launch one tiny add
+    per parameter and backward pass (~1.6 k per step for BigGAN-Deep)."""
+    if not getattr(p, "_sgb_direct_grad", False) or not p.is_leaf or torch.is_grad_enabled():
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape:
+        return None
+    return g
+
+
 def _tadd(a, b):
     if a is None:
         return b
@@ -154,7 +166,11 @@ class ConvFn(TFunction):
                     dbias = dbias[:Cout]
             else:
                 G = K.conv_wgrad(x, dz, KH, KW, pad, pad)
-            dW = K.sn_backward(G, weight, u_saved, v_saved, sigma, Cout, Cin, taps, cfg.get("perm_S", 1))
+            tgt = _direct_grad(weight)
+            if tgt is not None:       # accumulate straight into the flat gradient arena: no per-parameter add kernel
+                K.sn_backward(G, weight, u_saved, v_saved, sigma, Cout, Cin, taps, cfg.get("perm_S", 1), out=tgt)
+            else:
+                dW = K.sn_backward(G, weight, u_saved, v_saved, sigma, Cout, Cin, taps, cfg.get("perm_S", 1))
         if ctx.needs_input_grad[2] and not SKIP_PARAM_GRADS and dbias is None:
             dbias = K.bn_stats(dz)[0][:Cout]
         if ctx.has_res and ctx.needs_input_grad[3]:

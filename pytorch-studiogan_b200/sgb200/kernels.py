@@ -145,12 +145,13 @@ def weight_pack(W, sigma, Cout, Cin, taps, want_fprop=True, want_dgrad=True, per
     return wf, wd
 
 
-def sn_backward(G, W, u, v, sigma, Cout, Cin, taps, perm_S=1):
-    """G: fp32 [Cout_p][taps][Cin_p] from conv_wgrad -> dL/dW in the module's [Cout][Cin][taps] layout."""
-    dW = torch.empty_like(W)
+def sn_backward(G, W, u, v, sigma, Cout, Cin, taps, perm_S=1, out=None):
+    """G: fp32 [Cout_p][taps][Cin_p] from conv_wgrad -> dL/dW in the module's [Cout][Cin][taps] layout.
+    out: accumulate into this tensor (a view of the flat gradient arena) instead of returning a new one."""
+    dW = torch.empty_like(W) if out is None else out
     scratch = torch.empty(1, device=W.device, dtype=torch.float32) if sigma is not None else None
     L.call("sgb_sn_backward", L.ptr(G), L.ptr(W), L.ptr(u), L.ptr(v), L.ptr(sigma), L.ptr(scratch), L.ptr(dW), Cout, Cin, taps,
-           perm_S, pad8(Cin), 0, _s())
+           perm_S, pad8(Cin), 0 if out is None else 1, _s())
     return dW
 
 

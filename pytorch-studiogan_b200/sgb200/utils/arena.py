@@ -53,6 +53,7 @@ class GradArena:
         for p, g in zip(self.arena.params, self.views):
             if p.grad is None or p.grad.data_ptr() != g.data_ptr():
                 p.grad = g
+            p._sgb_direct_grad = True      # autograd_ops.ConvFn may accumulate into p.grad itself
 
     def zero(self):
         self.flat.zero_()

@@ -657,3 +657,27 @@ def test_worker_cuda_graph_phases_capture_and_advance_state():
     nbt = [b for n, b in Gen.named_buffers() if n.endswith("num_batches_tracked")]
     assert all(int(b) == 6 for b in nbt)          # the D phase does not track (src/worker.py:225), the G phase does
     assert w._d_graph.launches > 100 and w._g_graph.launches > 100
+
+
+def test_direct_arena_gradient_accumulation_equals_autograd(golden_dir):
+    """With the flat gradient arena attached, ConvFn adds its weight gradients into p.grad itself (no autograd add per
+    parameter).  Two accumulated discriminator passes must give the same gradients as plain autograd accumulation."""
+    import copy
+    from sgb200.utils import losses
+    from sgb200.utils.optim import ArenaAdam
+    dev = _cuda()
+    g = np.load(os.path.join(golden_dir, "deep32_c8_b16.npz"))
+    _, D = _build_from_golden(g, 8, 1, False, dev)
+    Dref = copy.deepcopy(D)
+    real, yr = torch.from_numpy(g["real"]).to(dev), torch.from_numpy(g["y_real"]).to(dev)
+    fake, yf = torch.from_numpy(g["fake"]).to(dev), torch.from_numpy(g["y_fake"]).to(dev)
+    opt = ArenaAdam(D, lr=2e-4, betas=(0.0, 0.999), eps=1e-6)
+    opt.zero_grad()
+    assert all(getattr(p, "_sgb_direct_grad", False) for p in D.parameters())
+    for net in (D, Dref):
+        for _ in range(2):                                       # two accumulation rounds
+            losses.d_hinge(net(real, yr)["adv_output"], net(fake, yf)["adv_output"]).backward()
+    for (n, p), q in zip(D.named_parameters(), Dref.parameters()):
+        assert p.grad.data_ptr() == opt.grads.views[[id(x) for x in opt.arena.params].index(id(p))].data_ptr(), n
+        np.testing.assert_allclose(p.grad.cpu().numpy(), q.grad.cpu().numpy(), rtol=2e-4, atol=2e-5 * float(q.grad.abs().max()) + 1e-9,
+                                   err_msg=n)
