@@ -30,7 +30,11 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 # conv + linear + attention-bmm FLOPs per image (2 x MAC), BASELINE.md section 3 / SURVEY.md 8(d)
-STEP_GFLOP_PER_IMAGE = {"BigGAN-Deep-256res": 1141.0}
+# WGAN-GP-128res (G 18.2 / D 9.4 GF per image forward): 5 D updates x (G fwd + 2 D fwd + 2 D bwd + penalty ~ 7 D fwd)
+# + 1 G update (G fwd + D fwd + D dgrad + G bwd) ~ 775 GF per batch image per step
+STEP_GFLOP_PER_IMAGE = {"BigGAN-Deep-256res": 1141.0, "WGAN-GP-128res": 775.0}
+METRIC_NAME = {"BigGAN-Deep-256res": "BigGAN-Deep 256x256 G+D step images/sec",
+               "WGAN-GP-128res": "WGAN-GP ResNetGAN 128x128 G+D step images/sec (5 D updates with gradient penalty + 1 G update)"}
 G_FWD_GF, D_FWD_GF = 58.80, 60.50
 
 
@@ -436,7 +440,7 @@ def main():
         except Exception as ex:
             cpu = {"value": None, "unit": "img/s", "cores": threads, "kind": "port", "sample": "failed: %r" % (ex,)}
 
-    line = {"metric": "BigGAN-Deep 256x256 G+D step images/sec", "value": value, "unit": "img/s", "n_gpus": world,
+    line = {"metric": METRIC_NAME.get(workload, workload + " G+D step images/sec"), "value": value, "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "global_batch": global_batch, "per_gpu_batch": per_rank, "img_size": S,
