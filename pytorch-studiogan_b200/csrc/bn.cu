@@ -185,45 +185,82 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
   const int nrows = 256 / VGb;
   const int g = threadIdx.x % VGb, prow = threadIdx.x / VGb;
   if (prow < nrows) {
-    float t1[8], t2[8], sc[8], sh[8], mu[8], rs[8];
+    // t2 accumulates sum(d * x) with the RAW input; sum(d * xhat) = rstd * (t2 - mean * t1) is formed once at the end, so the
+    // loop carries no per-channel mean / rstd.  Loads are issued packed (4 registers per 16 bytes) for several pixels before
+    // any arithmetic: the kernel is a pure stream and its speed is the number of bytes each SM keeps in flight.
+    float t1[8], t2[8], sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       t1[j] = 0.f; t2[j] = 0.f;
       const int c = c_base + g * 8 + j;
       sc[j] = scale[(size_t)b * bstride + c]; sh[j] = shift[(size_t)b * bstride + c];
-      mu[j] = mean[c]; rs[j] = rstd[c];
     }
     const int HW = H * W;
     const int p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, HW);
     const int gg = (c_base >> 3) + g;
-    for (int hw = p0 + prow; hw < p1; hw += 2 * nrows) {
-      const int hw2 = hw + nrows;
-      const bool two = hw2 < p1;
-      const long long p = (long long)b * HW + hw, q = (long long)b * HW + hw2;
-      float xv[8], dz[8], xw[8], dw[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * x_cstride) + gg), xv);
-      if (two) unpack8(__ldg(reinterpret_cast<const uint4*>(x + q * x_cstride) + gg), xw);
-      load_dz(dy, dy_cstride, b, up2 ? hw / W : 0, up2 ? hw % W : 0, H, W, gg, up2, p, dz);
-      if (two) load_dz(dy, dy_cstride, b, up2 ? hw2 / W : 0, up2 ? hw2 % W : 0, H, W, gg, up2, q, dw);
+    if (!up2) {
+      constexpr int U = 4;
+      for (int hw = p0 + prow; hw < p1; hw += U * nrows) {
+        uint4 rx[U], rd[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(xv[j], sc[j], sh[j]);
-        const float d = (relu && !(z > 0.f)) ? 0.f : dz[j];
-        t1[j] += d;
-        t2[j] = fmaf(d, (xv[j] - mu[j]) * rs[j], t2[j]);
+        for (int u = 0; u < U; ++u) {
+          const int h2 = hw + u * nrows;
+          if (h2 < p1) {
+            const long long p = (long long)b * HW + h2;
+            rx[u] = __ldg(reinterpret_cast<const uint4*>(x + p * x_cstride) + gg);
+            rd[u] = __ldg(reinterpret_cast<const uint4*>(dy + p * dy_cstride) + gg);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (hw + u * nrows < p1) {
+            float xv[8], dz[8];
+            unpack8(rx[u], xv);
+            unpack8(rd[u], dz);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float z = fmaf(xv[j], sc[j], sh[j]);
+              const float d = (relu && !(z > 0.f)) ? 0.f : dz[j];
+              t1[j] += d;
+              t2[j] = fmaf(d, xv[j], t2[j]);
+            }
+          }
+        }
       }
-      if (two) {
+    } else {
+      for (int hw = p0 + prow; hw < p1; hw += 2 * nrows) {
+        const int hw2 = hw + nrows;
+        const bool two = hw2 < p1;
+        const long long p = (long long)b * HW + hw, q = (long long)b * HW + hw2;
+        float xv[8], dz[8], xw[8], dw[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * x_cstride) + gg), xv);
+        if (two) unpack8(__ldg(reinterpret_cast<const uint4*>(x + q * x_cstride) + gg), xw);
+        load_dz(dy, dy_cstride, b, hw / W, hw % W, H, W, gg, 1, p, dz);
+        if (two) load_dz(dy, dy_cstride, b, hw2 / W, hw2 % W, H, W, gg, 1, q, dw);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float z = fmaf(xw[j], sc[j], sh[j]);
-          const float d = (relu && !(z > 0.f)) ? 0.f : dw[j];
+          const float z = fmaf(xv[j], sc[j], sh[j]);
+          const float d = (relu && !(z > 0.f)) ? 0.f : dz[j];
           t1[j] += d;
-          t2[j] = fmaf(d, (xw[j] - mu[j]) * rs[j], t2[j]);
+          t2[j] = fmaf(d, xv[j], t2[j]);
+        }
+        if (two) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float z = fmaf(xw[j], sc[j], sh[j]);
+            const float d = (relu && !(z > 0.f)) ? 0.f : dw[j];
+            t1[j] += d;
+            t2[j] = fmaf(d, xw[j], t2[j]);
+          }
         }
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { atomicAdd(&a1[g * 8 + j], t1[j]); atomicAdd(&a2[g * 8 + j], t2[j]); }
+    for (int j = 0; j < 8; ++j) {
+      const int c = c_base + g * 8 + j;
+      atomicAdd(&a1[g * 8 + j], t1[j]);
+      atomicAdd(&a2[g * 8 + j], rstd[c] * (t2[j] - mean[c] * t1[j]));
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < cc; i += 256) {
@@ -281,46 +318,79 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
   const int g = threadIdx.x % VGb, prow = threadIdx.x / VGb;
   if (prow >= nrows) return;
   const int gg = (c_base >> 3) + g;
-  float sc[8], sh[8], mu[8], ka[8], kb[8];
+  // dx = sc*d - ka - kb*(x - mu) = sc*d - k0 - kb*x with k0 = ka - kb*mu: four constants per channel, loads packed and issued
+  // for several pixels before any arithmetic (see the reduce kernel).
+  float sc[8], sh[8], k0[8], kb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = c_base + g * 8 + j;
     sc[j] = scale[(size_t)b * bstride + c]; sh[j] = shift[(size_t)b * bstride + c];
-    mu[j] = mean[c];
     if (use_batch_stats) {
       const float rs = rstd[c];
-      ka[j] = rs * inv_count * S1[c];
       kb[j] = rs * rs * inv_count * S2[c];
+      k0[j] = rs * inv_count * S1[c] - kb[j] * mean[c];
     } else {
-      ka[j] = 0.f; kb[j] = 0.f;
+      k0[j] = 0.f; kb[j] = 0.f;
     }
   }
   const int HW = H * W;
   const int p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, HW);
-  for (int hw = p0 + prow; hw < p1; hw += 2 * nrows) {
-    const int hw2 = hw + nrows;
-    const bool two = hw2 < p1;
-    const long long pa = (long long)b * HW + hw, pb = (long long)b * HW + hw2;
-    float xa[8], xb[8], da[8], db[8], o[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + pa * x_cstride) + gg), xa);
-    if (two) unpack8(__ldg(reinterpret_cast<const uint4*>(x + pb * x_cstride) + gg), xb);
-    load_dz(dy, dy_cstride, b, up2 ? hw / W : 0, up2 ? hw % W : 0, H, W, gg, up2, pa, da);
-    if (two) load_dz(dy, dy_cstride, b, up2 ? hw2 / W : 0, up2 ? hw2 % W : 0, H, W, gg, up2, pb, db);
+  if (!up2) {
+    constexpr int U = 4;
+    for (int hw = p0 + prow; hw < p1; hw += U * nrows) {
+      uint4 rx[U], rd[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(xa[j], sc[j], sh[j]);
-      const float d = (relu && !(z > 0.f)) ? 0.f : da[j];
-      o[j] = sc[j] * d - ka[j] - kb[j] * (xa[j] - mu[j]);
+      for (int u = 0; u < U; ++u) {
+        const int h2 = hw + u * nrows;
+        if (h2 < p1) {
+          const long long p = (long long)b * HW + h2;
+          rx[u] = __ldg(reinterpret_cast<const uint4*>(x + p * x_cstride) + gg);
+          rd[u] = __ldg(reinterpret_cast<const uint4*>(dy + p * dy_cstride) + gg);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int h2 = hw + u * nrows;
+        if (h2 < p1) {
+          float xv[8], dz[8], o[8];
+          unpack8(rx[u], xv);
+          unpack8(rd[u], dz);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float z = fmaf(xv[j], sc[j], sh[j]);
+            const float d = (relu && !(z > 0.f)) ? 0.f : dz[j];
+            o[j] = sc[j] * d - k0[j] - kb[j] * xv[j];
+          }
+          reinterpret_cast<uint4*>(dx + ((long long)b * HW + h2) * dx_cstride)[gg] = pack8(o);
+        }
+      }
     }
-    reinterpret_cast<uint4*>(dx + pa * dx_cstride)[gg] = pack8(o);
-    if (two) {
+  } else {
+    for (int hw = p0 + prow; hw < p1; hw += 2 * nrows) {
+      const int hw2 = hw + nrows;
+      const bool two = hw2 < p1;
+      const long long pa = (long long)b * HW + hw, pb = (long long)b * HW + hw2;
+      float xa[8], xb[8], da[8], db[8], o[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + pa * x_cstride) + gg), xa);
+      if (two) unpack8(__ldg(reinterpret_cast<const uint4*>(x + pb * x_cstride) + gg), xb);
+      load_dz(dy, dy_cstride, b, hw / W, hw % W, H, W, gg, 1, pa, da);
+      if (two) load_dz(dy, dy_cstride, b, hw2 / W, hw2 % W, H, W, gg, 1, pb, db);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(xb[j], sc[j], sh[j]);
-        const float d = (relu && !(z > 0.f)) ? 0.f : db[j];
-        o[j] = sc[j] * d - ka[j] - kb[j] * (xb[j] - mu[j]);
+        const float z = fmaf(xa[j], sc[j], sh[j]);
+        const float d = (relu && !(z > 0.f)) ? 0.f : da[j];
+        o[j] = sc[j] * d - k0[j] - kb[j] * xa[j];
       }
-      reinterpret_cast<uint4*>(dx + pb * dx_cstride)[gg] = pack8(o);
+      reinterpret_cast<uint4*>(dx + pa * dx_cstride)[gg] = pack8(o);
+      if (two) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(xb[j], sc[j], sh[j]);
+          const float d = (relu && !(z > 0.f)) ? 0.f : db[j];
+          o[j] = sc[j] * d - k0[j] - kb[j] * xb[j];
+        }
+        reinterpret_cast<uint4*>(dx + pb * dx_cstride)[gg] = pack8(o);
+      }
     }
   }
 }
