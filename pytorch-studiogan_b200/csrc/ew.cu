@@ -157,17 +157,27 @@ __global__ void __launch_bounds__(256) pool2_bwd_kernel(const bf16* __restrict__
         for (int k = 0; k < 4; ++k) o[k][j] = (k == arg) ? d[j] : 0.f;
       }
     }
+    // issue every operand load (packed) before the arithmetic: up to eight 16-byte loads in flight per thread
+    uint4 ra[4], rr[4];
+    if (add) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ra[k] = __ldg(reinterpret_cast<const uint4*>(add + qs[k] * adds) + g);
+    }
+    if (relu_src) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rr[k] = __ldg(reinterpret_cast<const uint4*>(relu_src + qs[k] * rs) + g);
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (add) {
         float t[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(add + qs[k] * adds) + g), t);
+        unpack8(ra[k], t);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[k][j] += t[j];
       }
       if (relu_src) {
         float t[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(relu_src + qs[k] * rs) + g), t);
+        unpack8(rr[k], t);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[k][j] = t[j] > 0.f ? o[k][j] : 0.f;
       }
