@@ -52,7 +52,7 @@ def parse():
                     help="capture each training phase in a CUDA graph; auto = on when the per-GPU batch is <= 64 (launch-bound regime)")
     ap.add_argument("--no-fid", action="store_true", help="skip the FID-50k evaluation timing (N = 1 only)")
     ap.add_argument("--fid-num", type=int, default=50000)
-    ap.add_argument("--cpu-batch", type=int, default=1)
+    ap.add_argument("--cpu-batch", type=int, default=4, help="images per CPU-baseline step (4 -> ~15 s of CPU work on 32 threads)")
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = min(32, host cores): more threads only add contention for these layer sizes")
     return ap.parse_args()
 
