@@ -48,12 +48,21 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ 
     for (int j = 0; j < 8; ++j) { a[j] = 0.f; q[j] = 0.f; }
     const long long p0 = (long long)blockIdx.x * pix_per_block;
     const long long p1 = min(p0 + pix_per_block, npix);
-    for (long long p = p0 + prow; p < p1; p += nrows) {
-      const uint4 r = __ldg(reinterpret_cast<const uint4*>(x + p * cstride + c_base) + g);
-      float f[8];
-      unpack8(r, f);
+    constexpr int U = 4;                         // four packed loads in flight per thread (latency-bound otherwise at small H*W)
+    for (long long p = p0 + prow; p < p1; p += (long long)U * nrows) {
+      uint4 r[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { a[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+      for (int u = 0; u < U; ++u)
+        if (p + (long long)u * nrows < p1) r[u] = __ldg(reinterpret_cast<const uint4*>(x + (p + (long long)u * nrows) * cstride + c_base) + g);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (p + (long long)u * nrows < p1) {
+          float f[8];
+          unpack8(r[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { a[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+        }
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { atomicAdd(&s_sum[g * 8 + j], a[j]); atomicAdd(&s_sq[g * 8 + j], q[j]); }
@@ -520,7 +529,10 @@ extern "C" int sgb_bn_stats(const void* x, int64_t npix, int32_t C, int64_t x_cs
   long long target_blocks = 8LL * sm_count() / chunks;
   if (target_blocks < 1) target_blocks = 1;
   long long ppb = (npix + target_blocks - 1) / target_blocks;
-  if (ppb < 64) ppb = 64;
+  const int vgb = (C < kChunkC ? C : kChunkC) / 8 < 256 ? (C < kChunkC ? C : kChunkC) / 8 : 256;
+  const long long ppb_min = 4LL * (256 / vgb);         // at least four pixels per thread row
+  if (ppb < ppb_min) ppb = ppb_min;
+  if (ppb < 16) ppb = 16;
   dim3 grid((unsigned)((npix + ppb - 1) / ppb), chunks);
   bn_stats_kernel<<<grid, 256, 0, stream>>>((const bf16*)x, npix, C, x_cstride, sum, sumsq, ppb);
   SGB_LAUNCH_CHECK();

@@ -167,19 +167,12 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             umma_commit(a_empty(sa_i));
             continue;
           }
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < 9; ++tap) {          // filter ring (the resident case was handled above)
             const int kh = tap / 3, kw = tap % 3;
-            uint32_t bb;
-            int sb = 0;
-            if (p.resident) {
-              bb = b_base + (tap * p.kblocks + kb) * b_tile_bytes;
-            } else {
-              sb = itb % p.b_stages;
-              mbar_wait(b_full(sb), (itb / p.b_stages) & 1);
-              tc_fence_after();
-              bb = b_base + sb * b_tile_bytes;
-            }
-            const uint64_t bdesc = make_sdesc_sw128(bb, 16, 1024);
+            const int sb = itb % p.b_stages;
+            mbar_wait(b_full(sb), (itb / p.b_stages) & 1);
+            tc_fence_after();
+            const uint64_t bdesc = make_sdesc_sw128(b_base + sb * b_tile_bytes, 16, 1024);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const uint64_t adesc = sdesc_rows(sa + (kh + j) * kRowBufBytes + kw * 128, p.bo_mode);
@@ -188,7 +181,8 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int kk = 0; kk < 4; ++kk)
                 umma_f16_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb > 0 || tap > 0 || kk > 0) ? 1u : 0u);
             }
-            if (!p.resident) { umma_commit(b_empty(sb)); ++itb; }
+            umma_commit(b_empty(sb));
+            ++itb;
           }
           umma_commit(a_empty(sa_i));
         }
