@@ -266,21 +266,64 @@ __global__ void __launch_bounds__(256) sn_wv_batch_kernel(const sgb_sn_layer* __
 
 __global__ void __launch_bounds__(256) sn_pack_batch_kernel(const sgb_sn_layer* __restrict__ table, const float* __restrict__ sigma_all,
                                                              bf16* __restrict__ pack_f, bf16* __restrict__ pack_d) {
+  // Tile = 32 output channels x 32 input channels x all taps, staged in shared memory so that the fp32 reads (one run of
+  // 32*taps floats per output channel) AND both bf16 writes are contiguous: the fprop pack [co][tap][ci] in runs of 32 ci,
+  // the dgrad pack [ci][taps-1-tap][co] in runs of 32 co.  (The element-wise version scattered 2-byte stores: 0.5 ms/call.)
+  constexpr int kT = 32, kMaxTaps = 9;
+  __shared__ bf16 tile[kT][kT * kMaxTaps + 2];
   const sgb_sn_layer L = table[blockIdx.y];
   const int Cout = L.Cout, Cin = L.Cin, taps = L.taps, perm_S = L.perm_S;
-  const size_t total = (size_t)Cout * Cin * taps;
   const float inv = 1.f / __ldcg(sigma_all + blockIdx.y);
   bf16* wf = pack_f ? pack_f + L.off_f : nullptr;
   bf16* wd = pack_d ? pack_d + L.off_d : nullptr;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-    const int tap = (int)(i % taps);
-    const int ci = (int)((i / taps) % Cin);
-    int co = (int)(i / ((size_t)taps * Cin));
-    const float val = __ldg(L.W + i) * inv;
-    if (perm_S > 1) { const int C = Cout / perm_S; co = (co % perm_S) * C + co / perm_S; }
-    const bf16 b = __float2bfloat16_rn(val);
-    if (wf) wf[((size_t)co * taps + tap) * L.Cin_p + ci] = b;
-    if (wd) wd[((size_t)ci * taps + (taps - 1 - tap)) * L.Cout_p + co] = b;
+  if (taps > kMaxTaps) {                          // generic fallback (no such layer on the hot path)
+    const size_t total = (size_t)Cout * Cin * taps;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+      const int tap = (int)(i % taps);
+      const int ci = (int)((i / taps) % Cin);
+      int co = (int)(i / ((size_t)taps * Cin));
+      const bf16 v = __float2bfloat16_rn(__ldg(L.W + i) * inv);
+      if (perm_S > 1) { const int C = Cout / perm_S; co = (co % perm_S) * C + co / perm_S; }
+      if (wf) wf[((size_t)co * taps + tap) * L.Cin_p + ci] = v;
+      if (wd) wd[((size_t)ci * taps + (taps - 1 - tap)) * L.Cout_p + co] = v;
+    }
+    return;
+  }
+  const int tiles_ci = (Cin + kT - 1) / kT, tiles_co = (Cout + kT - 1) / kT;
+  const int run = kT * taps;                      // source elements per output channel inside one tile
+  for (int t = blockIdx.x; t < tiles_ci * tiles_co; t += gridDim.x) {
+    const int co0 = (t / tiles_ci) * kT, ci0 = (t % tiles_ci) * kT;
+    const int nci = min(kT, Cin - ci0), nco = min(kT, Cout - co0);
+    __syncthreads();
+    // read: row r of the tile = source channel co0 + r, elements (ci0*taps .. (ci0+nci)*taps) contiguous in memory
+    for (int e = threadIdx.x; e < kT * run; e += 256) {
+      const int r = e / run, k = e % run;
+      if (r < nco && k < nci * taps)
+        tile[r][k] = __float2bfloat16_rn(__ldg(L.W + ((size_t)(co0 + r) * Cin + ci0) * taps + k) * inv);
+    }
+    __syncthreads();
+    if (wf) {   // [co][tap][ci]: runs of nci consecutive ci
+      for (int e = threadIdx.x; e < kT * run; e += 256) {
+        const int r = e / run, rem = e % run;
+        const int tap = rem / kT, c = rem % kT;
+        if (r < nco && c < nci) {
+          int co = co0 + r;
+          if (perm_S > 1) { const int C = Cout / perm_S; co = (co % perm_S) * C + co / perm_S; }
+          wf[((size_t)co * taps + tap) * L.Cin_p + ci0 + c] = tile[r][c * taps + tap];
+        }
+      }
+    }
+    if (wd) {   // [ci][taps-1-tap][co]: runs of nco consecutive co (perm_S > 1 only permutes the rows of linear0: scattered there)
+      for (int e = threadIdx.x; e < kT * run; e += 256) {
+        const int k = e / kT, r = e % kT;          // k = c * taps + tap
+        const int c = k / taps, tap = k % taps;
+        if (r < nco && c < nci) {
+          int co = co0 + r;
+          if (perm_S > 1) { const int C = Cout / perm_S; co = (co % perm_S) * C + co / perm_S; }
+          wd[((size_t)(ci0 + c) * taps + (taps - 1 - tap)) * L.Cout_p + co] = tile[r][k];
+        }
+      }
+    }
   }
 }
 
