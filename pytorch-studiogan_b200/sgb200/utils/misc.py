@@ -91,3 +91,32 @@ def peel_model(model):
 
 def peel_models(Gen, Gen_ema, Dis):
     return peel_model(Gen), (peel_model(Gen_ema) if Gen_ema is not None else None), peel_model(Dis)
+
+
+def reset_bn_statistics(m):
+    if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+        m.reset_running_stats()
+
+
+def apply_standing_statistics(generator, standing_max_batch, standing_step, DATA, MODEL, LOSS, OPTIMIZATION, RUN, STYLEGAN=None,
+                              device="cuda", global_rank=0, logger=None):
+    """``-std_stat`` evaluation mode (src/utils/misc.py:301-333): reset the generator's BatchNorm running statistics and
+    re-accumulate them over ``standing_step`` forward passes of random batch sizes (train mode, no gradient), then
+    switch to eval.  Host logic only; the forward passes run on the sgb200 kernels like any other."""
+    from . import sample
+    generator.train()
+    generator.apply(reset_bn_statistics)
+    if global_rank == 0 and logger is not None:
+        logger.info("Accumulate statistics of batchnorm layers to improve generation performance.")
+    world = getattr(OPTIMIZATION, "world_size", 1)
+    with torch.no_grad():
+        for _ in range(standing_step):
+            per_gpu = max(1, standing_max_batch // world)
+            if RUN.distributed_data_parallel:
+                rand_batch_size = random.randint(1, per_gpu)
+            else:
+                rand_batch_size = random.randint(1, per_gpu) * world
+            sample.generate_images(z_prior=MODEL.z_prior, truncation_factor=-1, batch_size=rand_batch_size, z_dim=MODEL.z_dim,
+                                   num_classes=DATA.num_classes, y_sampler="totally_random", radius="N/A", generator=generator,
+                                   discriminator=None, is_train=True, LOSS=LOSS, RUN=RUN, MODEL=MODEL, device=device)
+    generator.eval()

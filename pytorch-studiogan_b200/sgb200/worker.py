@@ -206,6 +206,15 @@ def _evaluate(self, step, metrics, writing=True, training=False):
     with torch.no_grad():
         misc.make_GAN_untrainable(self.Gen, self.Gen_ema, self.Dis)
         generator = self.Gen_ema if (self.MODEL.apply_g_ema and self.Gen_ema is not None) else self.Gen
+        if getattr(self.RUN, "standing_statistics", False):
+            # GeneratorController.prepare_generator (src/utils/misc.py:63-106): a copy of the generator whose BatchNorm
+            # statistics are re-accumulated over `standing_step` random-size batches
+            import copy
+            generator = copy.deepcopy(generator)
+            misc.apply_standing_statistics(generator=generator, standing_max_batch=self.RUN.standing_max_batch,
+                                           standing_step=self.RUN.standing_step, DATA=self.DATA, MODEL=self.MODEL, LOSS=self.LOSS,
+                                           OPTIMIZATION=self.OPTIMIZATION, RUN=self.RUN, device=self.local_rank,
+                                           global_rank=self.global_rank, logger=self.logger)
         fake_feats, fake_probs, fake_labels = features.generate_images_and_stack_features(
             generator=generator, discriminator=self.Dis, eval_model=self.eval_model, num_generate=num_eval,
             y_sampler="totally_random", batch_size=self.OPTIMIZATION.batch_size, z_prior=self.MODEL.z_prior,

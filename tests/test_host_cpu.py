@@ -174,3 +174,30 @@ def test_bn_tangent_formulas_and_reverse_over_forward_identity():
     got = torch.autograd.grad(t_adv.sum(), params)
     for r_, g_ in zip(ref, got):
         assert float((r_ - g_).abs().max()) < 1e-8 * (1 + float(r_.abs().max()))
+
+
+def test_standing_statistics_choreography():
+    """apply_standing_statistics (src/utils/misc.py:301-333): statistics reset, `standing_step` train-mode passes with
+    batch sizes in [1, standing_max_batch], generator left in eval mode."""
+    import torch.nn as nn
+    from sgb200.utils import misc
+
+    class G(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.bn = nn.BatchNorm2d(4)
+            self.sizes = []
+
+        def forward(self, z, label, eval=False):
+            assert self.training and not eval and not torch.is_grad_enabled()
+            self.sizes.append(z.shape[0])
+            return self.bn(torch.randn(z.shape[0], 4, 2, 2) + 3.0)
+    g = G()
+    g.bn.running_mean.fill_(7.0)
+    cfgs = C.Configurations(None)
+    cfgs.RUN.distributed_data_parallel = False
+    misc.apply_standing_statistics(g, standing_max_batch=6, standing_step=5, DATA=cfgs.DATA, MODEL=cfgs.MODEL, LOSS=cfgs.LOSS,
+                                   OPTIMIZATION=cfgs.OPTIMIZATION, RUN=cfgs.RUN, device="cpu")
+    assert len(g.sizes) == 5 and all(1 <= s <= 6 for s in g.sizes)
+    assert not g.training and int(g.bn.num_batches_tracked) == 5
+    assert 0.5 < float(g.bn.running_mean.mean()) < 3.5            # reset to 0, then moved towards the batch mean 3
