@@ -75,8 +75,18 @@ class WORKER(object):
         self.DDP = self.RUN.distributed_data_parallel
         self.train_iter = iter(train_dataloader) if train_dataloader is not None else None
         self.is_stylegan = False
-        if self.LOSS.adv_loss == "MH" or self.MODEL.aux_cls_type != "W/O" or self.MODEL.d_cond_mtd in ("AC", "2C", "D2DCE"):
-            raise NotImplementedError("conditioning losses other than PD / W/O are queued behind the hot path (SURVEY 8f-3)")
+        if self.LOSS.adv_loss == "MH":
+            raise NotImplementedError("the multi-hinge loss is queued behind the hot path (SURVEY 8f-3)")
+        # class-conditioning loss of the classifier-based GANs (src/worker.py:136-157)
+        self.adc_fake = self.MODEL.aux_cls_type == "ADC"
+        n_cls = self.DATA.num_classes * (2 if self.adc_fake else 1)
+        self.cond_loss = losses.make_cond_loss(self.MODEL.d_cond_mtd, n_cls, self.LOSS, self.DDP)
+        self.cond_loss_mi = None
+        if self.MODEL.aux_cls_type == "TAC":
+            import copy
+            self.cond_loss_mi = copy.deepcopy(self.cond_loss)
+        if self.MODEL.aux_cls_type not in ("W/O", "N/A", "TAC", "ADC"):
+            raise NotImplementedError("aux_cls_type %s" % self.MODEL.aux_cls_type)
         for flag in ("apply_cr", "apply_bcr", "apply_zcr", "apply_lo", "apply_topk", "apply_lecam", "apply_r1_reg",
                      "apply_dra", "apply_maxgp", "apply_fm", "apply_wc"):
             if getattr(self.LOSS, flag, False):
@@ -108,7 +118,7 @@ class WORKER(object):
 
     # ------------------------------------------------------------------------------------------------ D phase
     def _graphs_enabled(self):
-        return bool(getattr(self.RUN, "cuda_graphs", False)) and not self.LOSS.apply_gp
+        return bool(getattr(self.RUN, "cuda_graphs", False)) and not self.LOSS.apply_gp and self.cond_loss is None
 
     def train_discriminator(self, current_step):
         real_image_basket, real_label_basket = self.sample_data_basket_raw()
@@ -121,7 +131,8 @@ class WORKER(object):
             self._static_imgs.copy_(real_image_basket, non_blocking=True)
             self._static_labels.copy_(real_label_basket, non_blocking=True)
             return "N/A", self._d_graph()
-        return "N/A", self._d_phase(real_image_basket, real_label_basket)
+        dis_acml_loss = self._d_phase(real_image_basket, real_label_basket)
+        return self._real_cond_loss, dis_acml_loss
 
     def _d_phase_static(self):
         return self._d_phase(self._static_imgs, self._static_labels)
@@ -136,6 +147,7 @@ class WORKER(object):
         self.Gen.apply(misc.untrack_bn_statistics)
         batch_counter = 0
         dis_acml_loss = None
+        self._real_cond_loss = "N/A"
         for _ in range(self.OPTIMIZATION.d_updates_per_step):
             self.OPTIMIZATION.d_optimizer.zero_grad()
             for _ in range(self.OPTIMIZATION.acml_steps):
@@ -143,8 +155,16 @@ class WORKER(object):
                 real_labels = real_label_basket[batch_counter].to(self.local_rank, non_blocking=True)
                 fake_images, fake_labels, _, _, _, _, _ = self._generate(True)
                 real_dict = self.Dis(real_images, real_labels)
-                fake_dict = self.Dis(fake_images, fake_labels, adc_fake=False)
+                fake_dict = self.Dis(fake_images, fake_labels, adc_fake=self.adc_fake)
                 dis_acml_loss = self.LOSS.d_loss(real_dict["adv_output"], fake_dict["adv_output"], DDP=self.DDP)
+                if self.cond_loss is not None:          # src/worker.py:306-319
+                    real_cond_loss = self.cond_loss(**real_dict)
+                    dis_acml_loss = dis_acml_loss + self.LOSS.cond_lambda * real_cond_loss
+                    if self.cond_loss_mi is not None:
+                        dis_acml_loss = dis_acml_loss + self.LOSS.tac_dis_lambda * self.cond_loss_mi(**fake_dict)
+                    elif self.adc_fake:
+                        dis_acml_loss = dis_acml_loss + self.LOSS.cond_lambda * self.cond_loss(**fake_dict)
+                    self._real_cond_loss = real_cond_loss.detach()
                 if self.LOSS.apply_gp:
                     from .utils import gp
                     dis_acml_loss = dis_acml_loss + self.LOSS.gp_lambda * gp.cal_grad_penalty(
@@ -183,6 +203,13 @@ class WORKER(object):
                 fake_images, fake_labels, _, _, _, _, _ = self._generate(True)
                 fake_dict = self.Dis(fake_images, fake_labels)
                 gen_acml_loss = self.LOSS.g_loss(fake_dict["adv_output"], DDP=self.DDP)
+                if self.cond_loss is not None:          # src/worker.py:574-585
+                    gen_acml_loss = gen_acml_loss + self.LOSS.cond_lambda * self.cond_loss(**fake_dict)
+                    if self.cond_loss_mi is not None:
+                        gen_acml_loss = gen_acml_loss - self.LOSS.tac_gen_lambda * self.cond_loss_mi(**fake_dict)
+                    elif self.adc_fake:
+                        adc_fake_dict = self.Dis(fake_images, fake_labels, adc_fake=True)
+                        gen_acml_loss = gen_acml_loss - self.LOSS.cond_lambda * self.cond_loss(**adc_fake_dict)
                 gen_acml_loss = gen_acml_loss / self.OPTIMIZATION.acml_steps
                 gen_acml_loss.backward()
             model_lib.allreduce_gradients(self.Gen, self.OPTIMIZATION.g_optimizer)

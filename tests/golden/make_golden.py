@@ -229,6 +229,28 @@ def golden_inception():
     print("inception_seed0 pool", tuple(pool.shape), float(pool.abs().mean()), "logits", tuple(logits.shape))
 
 
+def golden_cond_losses():
+    """Reference conditioning losses (src/utils/losses.py:38-165) on seeded embeddings: values and input gradients."""
+    torch.manual_seed(2024)
+    B, d, classes = 12, 16, 4
+    out = {}
+    label = torch.randint(0, classes, (B,))
+    logits = torch.randn(B, classes, requires_grad=True)
+    ce = rlosses.CrossEntropyLoss()(cls_output=logits, label=label)
+    ce.backward()
+    out.update({"label": label.numpy(), "logits": logits.detach().numpy(), "ce": ce.detach().numpy(), "ce_dlogits": logits.grad.numpy()})
+    for name, cls, kw in (("c2", rlosses.ConditionalContrastiveLoss, dict(temperature=0.5)),
+                          ("d2dce", rlosses.Data2DataCrossEntropyLoss, dict(temperature=0.5, m_p=0.98))):
+        embed = torch.randn(B, d, requires_grad=True)
+        proxy = torch.randn(B, d, requires_grad=True)
+        loss = cls(num_classes=classes, master_rank="cpu", DDP=False, **kw)(embed=embed, proxy=proxy, label=label)
+        loss.backward()
+        out.update({name + "_embed": embed.detach().numpy(), name + "_proxy": proxy.detach().numpy(), name: loss.detach().numpy(),
+                    name + "_dembed": embed.grad.numpy(), name + "_dproxy": proxy.grad.numpy()})
+    np.savez_compressed(os.path.join(HERE, "cond_losses.npz"), **out)
+    print("cond_losses", {k: float(out[k]) for k in ("ce", "c2", "d2dce")})
+
+
 def golden_metrics():
     rng = np.random.RandomState(0)
     out = {}
@@ -294,6 +316,7 @@ if __name__ == "__main__":
     golden_resfamily("resnet32_cbn_c16", "resnet", 16, False, False, True, "cBN", "PD", "hinge", z_dim=32)
     golden_resfamily("wgan32_bn_c16", "resnet", 16, False, False, False, "W/O", "W/O", "wasserstein", z_dim=32)
     golden_metrics()
+    golden_cond_losses()
     golden_inception()
     golden_gp("gp_resnet32_bn_c16", "resnet", 16, False, "W/O")           # the WGAN-GP config's discriminator (BatchNorm, no SN)
     golden_gp("gp_resnet32_sn_c16_pd", "resnet", 16, True, "PD")

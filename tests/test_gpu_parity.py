@@ -681,3 +681,47 @@ def test_direct_arena_gradient_accumulation_equals_autograd(golden_dir):
         assert p.grad.data_ptr() == opt.grads.views[[id(x) for x in opt.arena.params].index(id(p))].data_ptr(), n
         np.testing.assert_allclose(p.grad.cpu().numpy(), q.grad.cpu().numpy(), rtol=2e-4, atol=2e-5 * float(q.grad.abs().max()) + 1e-9,
                                    err_msg=n)
+
+
+@pytest.mark.parametrize("mtd,aux", [("AC", "W/O"), ("D2DCE", "W/O"), ("2C", "TAC"), ("AC", "ADC")])
+def test_worker_classifier_based_conditioning_steps(mtd, aux):
+    """ACGAN / ContraGAN / ReACGAN conditioning (src/worker.py:306-319,574-585) through WORKER: the returned
+    real_cond_loss equals the loss module applied to a fresh discriminator pass, losses are finite, parameters move."""
+    from sgb200 import config as C
+    from sgb200.models import model as M
+    from sgb200.worker import WORKER
+    dev = _cuda()
+    cfgs = C.Configurations(None)
+    cfgs.DATA.img_size, cfgs.DATA.num_classes = 32, 10
+    m = cfgs.MODEL
+    m.backbone, m.g_cond_mtd, m.d_cond_mtd, m.aux_cls_type = "big_resnet", "cBN", mtd, aux
+    m.apply_g_sn, m.apply_d_sn, m.apply_g_ema = True, True, False
+    m.z_dim, m.g_shared_dim, m.g_conv_dim, m.d_conv_dim, m.d_embed_dim, m.normalize_d_embed = 40, 32, 16, 16, 64, mtd != "AC"
+    cfgs.LOSS.adv_loss, cfgs.LOSS.cond_lambda, cfgs.LOSS.temperature, cfgs.LOSS.m_p = "hinge", 1.0, 0.5, 0.98
+    cfgs.LOSS.tac_dis_lambda, cfgs.LOSS.tac_gen_lambda = 1.0, 1.0
+    o = cfgs.OPTIMIZATION
+    o.batch_size, o.d_updates_per_step, o.g_updates_per_step, o.acml_steps = 16, 1, 1, 1
+    cfgs.define_modules()
+    cfgs.define_losses()
+    torch.manual_seed(0)
+    Gen, _, _, Dis, Gen_ema, _, _, ema = M.load_generator_discriminator(cfgs.DATA, o, cfgs.MODEL, cfgs.STYLEGAN, cfgs.MODULES,
+                                                                        cfgs.RUN, dev, None)
+    cfgs.define_optimizer(Gen, Dis)
+
+    class Loader:
+        def __iter__(self):
+            return self
+
+        def __next__(self):
+            g = torch.Generator().manual_seed(1)
+            return torch.rand(16, 3, 32, 32, generator=g) * 2 - 1, torch.randint(0, 10, (16,), generator=g)
+    w = WORKER(cfgs=cfgs, run_name="t", Gen=Gen, Gen_mapping=None, Gen_synthesis=None, Dis=Dis, Gen_ema=Gen_ema, Gen_ema_mapping=None,
+               Gen_ema_synthesis=None, ema=ema, eval_model=None, train_dataloader=Loader(), eval_dataloader=None, global_rank=0,
+               local_rank=dev, mu=None, sigma=None, real_feats=None, logger=None)
+    assert w.cond_loss is not None and (w.cond_loss_mi is not None) == (aux == "TAC")
+    d0 = [p.detach().clone() for p in Dis.parameters()]
+    cond, d_loss = w.train_discriminator(0)
+    g_loss = w.train_generator(0)
+    assert torch.is_tensor(cond) and torch.isfinite(cond) and torch.isfinite(d_loss) and torch.isfinite(g_loss)
+    assert float(cond) > 0
+    assert any(float((p.detach() - q).abs().max()) > 0 for p, q in zip(Dis.parameters(), d0))

@@ -201,3 +201,24 @@ def test_standing_statistics_choreography():
     assert len(g.sizes) == 5 and all(1 <= s <= 6 for s in g.sizes)
     assert not g.training and int(g.bn.num_batches_tracked) == 5
     assert 0.5 < float(g.bn.running_mean.mean()) < 3.5            # reset to 0, then moved towards the batch mean 3
+
+
+def test_conditioning_losses_match_reference(golden_dir):
+    """AC / 2C / D2D-CE losses (src/utils/losses.py:38-165): values and input gradients vs the reference's own classes."""
+    from sgb200.utils import losses
+    g = np.load(os.path.join(golden_dir, "cond_losses.npz"))
+    label = torch.from_numpy(g["label"])
+    logits = torch.from_numpy(g["logits"]).requires_grad_(True)
+    ce = losses.CrossEntropyLoss()(cls_output=logits, label=label)
+    ce.backward()
+    np.testing.assert_allclose(ce.item(), g["ce"], rtol=1e-6)
+    np.testing.assert_allclose(logits.grad.numpy(), g["ce_dlogits"], rtol=1e-5, atol=1e-7)
+    for name, mod in (("c2", losses.ConditionalContrastiveLoss(num_classes=4, temperature=0.5)),
+                      ("d2dce", losses.Data2DataCrossEntropyLoss(num_classes=4, temperature=0.5, m_p=0.98))):
+        embed = torch.from_numpy(g[name + "_embed"]).requires_grad_(True)
+        proxy = torch.from_numpy(g[name + "_proxy"]).requires_grad_(True)
+        loss = mod(embed=embed, proxy=proxy, label=label, h=None, adv_output=None)     # extra head keys are ignored (**_)
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), g[name], rtol=1e-5)
+        np.testing.assert_allclose(embed.grad.numpy(), g[name + "_dembed"], rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(proxy.grad.numpy(), g[name + "_dproxy"], rtol=1e-4, atol=1e-7)
