@@ -222,3 +222,43 @@ def test_conditioning_losses_match_reference(golden_dir):
         np.testing.assert_allclose(loss.item(), g[name], rtol=1e-5)
         np.testing.assert_allclose(embed.grad.numpy(), g[name + "_dembed"], rtol=1e-4, atol=1e-7)
         np.testing.assert_allclose(proxy.grad.numpy(), g[name + "_dproxy"], rtol=1e-4, atol=1e-7)
+
+
+def test_checkpoint_round_trip_in_reference_format(tmp_path, golden_dir):
+    """utils/ckpt.py writes the reference's file names / dict keys (src/worker.py:940-985, src/utils/ckpt.py:28-141) and
+    reads them back strictly; the previous file of the same (model, when) is replaced."""
+    import types
+    from sgb200.utils import ckpt
+    G, D = _build(dict(conv_dim=8, depth=1, attn=False))
+    G2, D2 = _build(dict(conv_dim=8, depth=1, attn=False))
+    with torch.no_grad():
+        for p in list(G2.parameters()) + list(D2.parameters()):
+            p.add_(1.0)
+    g_opt = torch.optim.Adam(G.parameters(), lr=2e-4, betas=(0.0, 0.999), eps=1e-6)
+    d_opt = torch.optim.Adam(D.parameters(), lr=2e-4, betas=(0.0, 0.999), eps=1e-6)
+    for p in D.parameters():
+        p.grad = torch.ones_like(p)
+    d_opt.step()
+    w = types.SimpleNamespace(Gen=G, Dis=D, Gen_ema=G2, run_name="unit", best_step=3, best_fid=12.5,
+                              OPTIMIZATION=types.SimpleNamespace(g_optimizer=g_opt, d_optimizer=d_opt),
+                              RUN=types.SimpleNamespace(seed=7, ckpt_dir=str(tmp_path)))
+    ckpt.save(w, step=10, is_best=False)
+    paths = ckpt.save(w, step=20, is_best=False)
+    names = sorted(os.listdir(tmp_path))
+    assert names == ["model=D-current-weights-step=20.pth", "model=G-current-weights-step=20.pth",
+                     "model=G_ema-current-weights-step=20.pth"] and len(paths) == 3
+    d_file = torch.load(os.path.join(tmp_path, names[0]), weights_only=False)
+    assert set(d_file) == {"state_dict", "optimizer", "seed", "run_name", "step", "epoch", "topk", "aa_p", "best_step", "best_fid",
+                           "best_fid_ckpt", "lecam_emas"}
+    G3, D3 = _build(dict(conv_dim=8, depth=1, attn=False))
+    G4, _ = _build(dict(conv_dim=8, depth=1, attn=False))
+    d_opt3 = torch.optim.Adam(D3.parameters(), lr=1.0)
+    g_opt3 = torch.optim.Adam(G3.parameters(), lr=1.0)
+    ema = types.SimpleNamespace(source=None, target=None)
+    misc_ = ckpt.load_StudioGAN_ckpts(str(tmp_path), False, G3, D3, g_opt3, d_opt3, True, G4, ema)
+    assert misc_[:3] == (7, "unit", 20) and misc_[6:8] == (3, 12.5) and ema.source is G3 and ema.target is G4
+    for a, b in zip(D.state_dict().values(), D3.state_dict().values()):
+        assert torch.equal(a, b)
+    for a, b in zip(G2.state_dict().values(), G4.state_dict().values()):
+        assert torch.equal(a, b)
+    assert d_opt3.state_dict()["param_groups"][0]["lr"] == 2e-4 and len(d_opt3.state_dict()["state"]) == len(list(D3.parameters()))
