@@ -70,3 +70,61 @@ def test_strong_scaling_batch_sharding():
     # bench.py / src/loader.py:162: per-rank batch = global // world, the whole-job value uses the global batch
     for world in (1, 2, 4, 8):
         assert 256 % world == 0 and (256 // world) * world == 256
+
+
+def _d2dce_worker(rank, world, port, q):
+    sys.path.insert(0, os.path.join(ROOT, "pytorch-studiogan_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sgb200.utils import losses
+    g = torch.Generator().manual_seed(5)
+    embed_all, proxy_all = torch.randn(8, 6, generator=g), torch.randn(8, 6, generator=g)
+    label_all = torch.randint(0, 3, (8,), generator=g)
+    sl = slice(4 * rank, 4 * rank + 4)
+    embed = embed_all[sl].clone().requires_grad_(True)
+    proxy = proxy_all[sl].clone().requires_grad_(True)
+    out = {}
+    for name, mod in (("d2dce", losses.Data2DataCrossEntropyLoss(3, 0.5, 0.98, DDP=True)),
+                      ("c2", losses.ConditionalContrastiveLoss(3, 0.5, DDP=True))):
+        embed.grad = proxy.grad = None
+        loss = mod(embed=embed, proxy=proxy, label=label_all[sl])
+        loss.backward()
+        out[name] = (loss.item(), embed.grad.numpy().copy(), proxy.grad.numpy().copy())
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_conditioning_losses_gather_with_gradient():
+    """DDP path of the contrastive conditioning losses (src/utils/losses.py:84-88,140-144): every rank all-gathers embed /
+    proxy / label through GatherLayer, so each rank's loss equals the single-process loss on the concatenated batch and
+    receives the gradient of its own shard."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "pytorch-studiogan_b200"))
+    from sgb200.utils import losses
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_d2dce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(5)
+    embed_all = torch.randn(8, 6, generator=g).requires_grad_(True)
+    proxy_all = torch.randn(8, 6, generator=g).requires_grad_(True)
+    label_all = torch.randint(0, 3, (8,), generator=g)
+    for name, mod in (("d2dce", losses.Data2DataCrossEntropyLoss(3, 0.5, 0.98, DDP=False)),
+                      ("c2", losses.ConditionalContrastiveLoss(3, 0.5, DDP=False))):
+        embed_all.grad = proxy_all.grad = None
+        ref = mod(embed=embed_all, proxy=proxy_all, label=label_all)
+        ref.backward()
+        for rank in (0, 1):
+            val, de, dp = res[rank][name]
+            np.testing.assert_allclose(val, ref.item(), rtol=1e-6)
+            sl = slice(4 * rank, 4 * rank + 4)
+            # GatherLayer hands each rank the gradient of ITS OWN copy of the gathered loss (src/utils/losses.py:19-37)
+            np.testing.assert_allclose(de, embed_all.grad[sl].numpy(), rtol=1e-5, atol=1e-7)
+            np.testing.assert_allclose(dp, proxy_all.grad[sl].numpy(), rtol=1e-5, atol=1e-7)
