@@ -177,7 +177,9 @@ int sgb_axpby(const void* x, int64_t xs, const void* y, int64_t ys, const void* 
 int sgb_pool2_fwd(const void* x, int64_t xs, void* y, int64_t ys, int32_t B, int32_t Ho, int32_t Wo, int32_t C, int32_t mode,
                   sgb_stream_t stream);
 /* dx = pool2 backward of dy (+ add) (masked by relu_src > 0); x needed for max (first max in scan order wins). */
-/* a0 = relu(x) (full resolution) and y = 2x2 average of a0, one pass (entry of a down-sampling discriminator block). */
+/* a0 = relu(x) (full resolution) and y = 2x2 average of a0, one pass: entry of a down-sampling discriminator block
+ * (self.activation + self.average_pooling on the skip, src/models/big_resnet_deep_legacy.py:211-224,
+ * src/models/big_resnet_deep_studiogan.py:233-249). */
 int sgb_relu_pool2(const void* x, int64_t x_cstride, void* a0, int64_t a0_cstride, void* y, int64_t y_cstride, int32_t B,
                    int32_t Ho, int32_t Wo, int32_t C, sgb_stream_t stream);
 int sgb_pool2_bwd(const void* dy, int64_t dys, const void* x, int64_t xs, const void* add, int64_t adds, const void* relu_src,
