@@ -590,3 +590,59 @@ def eval_preprocess(images, size=299, quantize=True):
     (src/metrics/preparation.py:103-108, src/utils/ops.py:251-263): returns the normalised [B,3,size,size] batch."""
     q = quantize_images(images) if quantize else images.detach().cpu().numpy().astype(np.uint8)
     return normalize_for_inception(resize_legacy(q, size))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# DCGAN (src/models/deep_conv.py) -- BASELINE config 1, the reference's CPU-only case.  Oracle level only: the product
+# has no sm_100a kernel for the 4x4 / stride-2 (transposed) convolutions (DESIGN.md, out of scope).
+# ---------------------------------------------------------------------------------------------------------------------
+def dcgan_generator(sd, z, label=None, training=True, track=True):
+    """Generator.forward (src/models/deep_conv.py:96-126), unconditional (g_cond_mtd W/O, info N/A):
+    linear0 -> [B,512,4,4] -> 3 x (ConvTranspose 4x4 s2 p1 -> BN -> ReLU) -> conv3x3 -> tanh."""
+    act = linear(sd, "linear0.", z, training).view(-1, 512, 4, 4)
+    for i in range(3):
+        p = "blocks.%d.0." % i
+        w = sd[p + "deconv0.weight"]                                   # [Cin, Cout, 4, 4]
+        act = F.conv_transpose2d(act, w, sd.get(p + "deconv0.bias"), stride=2, padding=1)
+        act = F.relu(batch_norm(sd, p + "bn0.", act, training, track, affine=True))
+    return torch.tanh(conv(sd, "conv4.", act, 1, training))
+
+
+def dcgan_discriminator(sd, x, label=None, training=True):
+    """Discriminator.forward (src/models/deep_conv.py:233-...): 3 x (conv3x3 -> BN -> ReLU -> conv4x4 s2 p1 -> BN -> ReLU),
+    conv3x3 256->512 -> BN -> ReLU -> sum over (H, W) -> linear1.  Returns (adv_output, h)."""
+    h = x
+    for i in range(3):
+        p = "blocks.%d.0." % i
+        h = F.relu(batch_norm(sd, p + "bn0.", conv(sd, p + "conv0.", h, 1, training), training, True, affine=True))
+        h = F.conv2d(h, weight(sd, p + "conv1.", training), sd.get(p + "conv1.bias"), stride=2, padding=1)
+        h = F.relu(batch_norm(sd, p + "bn1.", h, training, True, affine=True))
+    h = F.relu(batch_norm(sd, "bn1.", conv(sd, "conv1.", h, 1, training), training, True, affine=True))
+    h = torch.sum(h, dim=[2, 3])
+    return torch.squeeze(linear(sd, "linear1.", h, training)), h
+
+
+def seeded_state(keys_shapes, seed):
+    """Deterministic weights for a (key, shape) list: used for the DCGAN fixture, whose 6.4 M parameters are regenerated
+    from the seed on both sides instead of being stored (conv / linear weights ~ N(0, 0.05^2), BN weight 1 + 0.1 N,
+    biases 0.1 N, running_mean 0.1 N, running_var 1 + 0.2 U, counters 0)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shape in keys_shapes:
+        shape = tuple(int(v) for v in shape)
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros(shape, dtype=torch.long)
+        elif k.endswith("running_var"):
+            sd[k] = 1.0 + 0.2 * torch.rand(shape, generator=g)
+        elif k.endswith("running_mean") or k.endswith("bias"):
+            sd[k] = 0.1 * torch.randn(shape, generator=g)
+        elif ".bn" in k or k.startswith("bn"):
+            sd[k] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif k.startswith("linear1."):
+            # small output head: keeps the logits O(1).  With saturated logits every sample gets the same loss gradient and
+            # the BatchNorm backward (dy - mean(dy) - ...) cancels catastrophically -- the reference's own fp32 gradients
+            # are then only good to ~1e-2, which would make the fixture a noise comparison.
+            sd[k] = 0.001 * torch.randn(shape, generator=g)
+        else:
+            sd[k] = 0.05 * torch.randn(shape, generator=g)
+    return sd

@@ -31,6 +31,7 @@ import models.big_resnet_deep_legacy as rdeep  # noqa: E402
 import models.big_resnet_deep_studiogan as rdeep_sg  # noqa: E402
 import models.big_resnet as rbig  # noqa: E402
 import models.resnet as rres  # noqa: E402
+import models.deep_conv as rdc  # noqa: E402
 import scipy.linalg  # noqa: E402
 import metrics.fid as rfid  # noqa: E402
 import metrics.ins as rins  # noqa: E402
@@ -43,6 +44,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def modules(g_sn=True, d_sn=True, cbn=True):
     m = types.SimpleNamespace()
     m.g_conv2d = rops.snconv2d if g_sn else rops.conv2d
+    m.g_deconv2d = rops.sndeconv2d if g_sn else rops.deconv2d
     m.g_linear = rops.snlinear if g_sn else rops.linear
     m.g_embedding = rops.sn_embedding if g_sn else rops.embedding
     m.d_conv2d = rops.snconv2d if d_sn else rops.conv2d
@@ -251,6 +253,64 @@ def golden_cond_losses():
     print("cond_losses", {k: float(out[k]) for k in ("ce", "c2", "d2dce")})
 
 
+def golden_dcgan(tag="dcgan32", B=8, z_dim=16):
+    """BASELINE config 1 (src/configs/CIFAR10/DCGAN.yaml): DCGAN, unconditional, vanilla loss, BatchNorm in G and D --
+    one D phase + one G phase exactly as golden_resfamily.  The 6.4 M weights are NOT stored: both sides regenerate them
+    from a seed (oracle.seeded_state); the fixture holds inputs, outputs, losses, per-parameter gradient norms and the full
+    gradients / updated statistics of the 1-D parameters."""
+    import json
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import studiogan_oracle as O
+    M = modules(g_sn=False, d_sn=False, cbn=False)
+    G = rdc.Generator(z_dim=z_dim, g_shared_dim="N/A", img_size=32, g_conv_dim="N/A", apply_attn=False, attn_g_loc=[], g_cond_mtd="W/O",
+                      num_classes=10, g_init="ortho", g_depth="N/A", mixed_precision=False, MODULES=M, MODEL=MODEL)
+    D = rdc.Discriminator(img_size=32, d_conv_dim="N/A", apply_d_sn=False, apply_attn=False, attn_d_loc=[], d_cond_mtd="W/O",
+                          aux_cls_type="W/O", d_embed_dim="N/A", normalize_d_embed=False, num_classes=10, d_init="ortho",
+                          d_depth="N/A", mixed_precision=False, MODULES=M, MODEL=MODEL)
+    ks_g = [(k, list(v.shape)) for k, v in G.state_dict().items()]
+    ks_d = [(k, list(v.shape)) for k, v in D.state_dict().items()]
+    G.load_state_dict(O.seeded_state(ks_g, 101), strict=True)
+    D.load_state_dict(O.seeded_state(ks_d, 202), strict=True)
+    G.train(); D.train()
+    torch.manual_seed(31)
+    out = {"keys_g": np.array(json.dumps(ks_g)), "keys_d": np.array(json.dumps(ks_d))}
+    z = torch.randn(B, z_dim); y = torch.randint(0, 10, (B,))
+    real = torch.rand(B, 3, 32, 32) * 2 - 1
+    out.update({"z": z.numpy(), "y": y.numpy(), "real": real.numpy()})
+    for p in G.parameters():
+        p.requires_grad_(False)
+    fake = G(z, y)
+    rd, fd = D(real, y), D(fake.detach(), y)
+    d_loss = rlosses.d_vanilla(rd["adv_output"], fd["adv_output"], False)
+    d_loss.backward()
+    out.update({"fake": fake.detach().numpy(), "adv_real": rd["adv_output"].detach().numpy(), "adv_fake": fd["adv_output"].detach().numpy(),
+                "d_loss": d_loss.detach().numpy()})
+    for k, p in D.named_parameters():
+        out["Dgnorm/" + k] = p.grad.norm().numpy()
+        if p.dim() == 1:
+            out["Dgrad/" + k] = p.grad.detach().numpy().copy()
+    for k, v in list(G.state_dict().items()) + list(D.state_dict().items()):
+        pass
+    out.update({"G1/" + k: v.numpy().copy() for k, v in G.state_dict().items() if "running_" in k})
+    out.update({"D1/" + k: v.numpy().copy() for k, v in D.state_dict().items() if "running_" in k})
+    D.zero_grad()
+    for p in G.parameters():
+        p.requires_grad_(True)
+    for p in D.parameters():
+        p.requires_grad_(False)
+    fake2 = G(z, y)
+    fake2.retain_grad()
+    g_loss = rlosses.g_vanilla(D(fake2, y)["adv_output"], False)
+    g_loss.backward()
+    out.update({"fake2": fake2.detach().numpy(), "g_loss": g_loss.detach().numpy(), "dfake2": fake2.grad.numpy().copy()})
+    for k, p in G.named_parameters():
+        out["Ggnorm/" + k] = p.grad.norm().numpy()
+        if p.dim() == 1:
+            out["Ggrad/" + k] = p.grad.detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
+    print(tag, "keys", len(out), "d_loss", float(d_loss), "g_loss", float(g_loss))
+
+
 def golden_metrics():
     rng = np.random.RandomState(0)
     out = {}
@@ -316,6 +376,7 @@ if __name__ == "__main__":
     golden_resfamily("resnet32_cbn_c16", "resnet", 16, False, False, True, "cBN", "PD", "hinge", z_dim=32)
     golden_resfamily("wgan32_bn_c16", "resnet", 16, False, False, False, "W/O", "W/O", "wasserstein", z_dim=32)
     golden_metrics()
+    golden_dcgan()
     golden_cond_losses()
     golden_inception()
     golden_gp("gp_resnet32_bn_c16", "resnet", 16, False, "W/O")           # the WGAN-GP config's discriminator (BatchNorm, no SN)
