@@ -11,7 +11,6 @@ a chain of fused kernels:
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .. import autograd_ops as A
 from ..snbatch import SNBatch

@@ -11,7 +11,6 @@ seeded initialisation)."""
 import torch.nn as nn
 
 from .. import autograd_ops as A
-from ..utils import ops
 from . import big_resnet_deep_legacy as legacy
 
 D_IN = dict(legacy.D_IN)

@@ -11,8 +11,6 @@ Implementation notes
 * packs of one forward live in one flat bf16 buffer per direction; each layer receives views.
 * layers that are not spectrally normalised (e.g. SNGAN's generator) are packed by the same launch with sigma = 1.
 """
-import ctypes
-
 import numpy as np
 import torch
 
