@@ -71,6 +71,14 @@ typedef struct sgb_conv_desc {
    * tensor, i.e. a stride-2 convolution computed on the stride-1 grid (four layers of the network). */
   int32_t Hin, Win;
   int32_t out_sub;
+  /* Optional per-channel column statistics of the STORED (bf16-rounded) output, accumulated by the epilogue
+   * (CTA-resident partial sums, one atomic flush per CTA) into caller-zeroed fp32 [Cout] vectors:
+   *   colsum[c] += sum_{b,h,w} y[b,h,w,c],  colsumsq[c] += sum y^2   (colsumsq may be NULL).
+   * They are BatchNorm's [sum x, sum x^2] of the next layer (src/utils/ops.py:24-28; the sync-BN exchange vector of
+   * torch/nn/modules/_functions.py:36-60) or, on a dgrad launch, the bias gradient of the producing layer -- without a
+   * separate pass over the tensor.  bf16 outputs only. */
+  float* colsum;
+  float* colsumsq;
 } sgb_conv_desc;
 
 int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream);

@@ -57,6 +57,14 @@ def _direct_grad(p):
     return g
 
 
+def _keep_colstats(src, view):
+    """A same-shape alias of ``src`` keeps the column statistics its producer's epilogue attached (kernels.colstats)."""
+    cs = getattr(src, "_sgb_colstats", None)
+    if cs is not None:
+        view._sgb_colstats = cs
+    return view
+
+
 def _tadd(a, b):
     if a is None:
         return b
@@ -126,7 +134,7 @@ class ConvFn(TFunction):
         res = residual
         y = K.conv_fprop(x, wf, Cout_p, KH, KW, pad, pad, bias=bias if Cout_p == Cout else _pad_bias(bias, Cout_p),
                          residual=res, res_up2=cfg.get("res_up2", False), relu=cfg.get("relu", False),
-                         out_fp32=cfg.get("out_fp32", False))
+                         out_fp32=cfg.get("out_fp32", False), stats=cfg.get("stats", 0))
         if need_dw and sn is not None and cache is None:
             u_saved, v_saved = u.clone(), v.clone()
         ctx.cfg = cfg
@@ -156,7 +164,10 @@ class ConvFn(TFunction):
                 wf2, _ = K.weight_pack(wcol, None, Cin, 27, 1, True, False)
                 dx = K.conv_fprop(K.col27(dz), wf2, K.pad8(Cin), 1, 1, 0, 0, mask=mask)
             else:
-                dx = K.conv_fprop(dz, wd, K.pad8(Cin), KH, KW, KH - 1 - pad, KW - 1 - pad, mask=mask)
+                # a premasked input gradient is the producing relu-conv's pre-activation gradient: its column sums are that
+                # layer's bias gradient (no separate reduction pass)
+                dx = K.conv_fprop(dz, wd, K.pad8(Cin), KH, KW, KH - 1 - pad, KW - 1 - pad, mask=mask,
+                                  stats=1 if (mask is not None and not SKIP_PARAM_GRADS) else 0)
             if dx.shape[1] != x.shape[1]:
                 dx = dx[:, :x.shape[1]]
         if ctx.needs_input_grad[1] and not SKIP_PARAM_GRADS:
@@ -172,7 +183,8 @@ class ConvFn(TFunction):
             else:
                 dW = K.sn_backward(G, weight, u_saved, v_saved, sigma, Cout, Cin, taps, cfg.get("perm_S", 1))
         if ctx.needs_input_grad[2] and not SKIP_PARAM_GRADS and dbias is None:
-            dbias = K.bn_stats(dz)[0][:Cout]
+            cs = K.colstats(dz, 1)
+            dbias = (cs[0] if cs is not None else K.bn_stats(dz)[0])[:Cout]
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = K.pool2_fwd(dz, 2) if cfg.get("res_up2", False) else dz
             rc = ctx.res_shape[1]
@@ -239,7 +251,11 @@ class BNActFn(TFunction):
         count = float(B * H * W)
         group = cfg.get("group")
         if cfg["use_batch_stats"]:
-            stats = K.bn_stats(x)
+            stats = K.colstats(x, 2)                 # [sum, sum of squares] left by the producing conv's epilogue
+            if stats is None:
+                stats = K.bn_stats(x)
+            elif group is not None:
+                stats = stats.clone()                # the all-reduce below must not alter what rides on x
             if group is not None:
                 dist.all_reduce(stats, group=group)
                 count *= dist.get_world_size(group)
@@ -352,7 +368,7 @@ class SplitResidualFn(TFunction):
 
     @staticmethod
     def forward(ctx, x, c):
-        return x.view_as(x), x[:, :c]
+        return _keep_colstats(x, x.view_as(x)), x[:, :c]
 
     @staticmethod
     def backward(ctx, d_main, d_res):
@@ -703,7 +719,7 @@ class ForkFn(TFunction):
 
     @staticmethod
     def forward(ctx, x):
-        return x.view_as(x), x.view_as(x)
+        return _keep_colstats(x, x.view_as(x)), _keep_colstats(x, x.view_as(x))
 
     @staticmethod
     def backward(ctx, g1, g2):

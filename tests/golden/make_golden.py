@@ -126,6 +126,74 @@ def golden_deep(tag, img_size, conv_dim, depth, attn, z_dim=16, shared=16, class
     print(tag, "keys", len(out), "d_loss", float(d_loss), "g_loss", float(g_loss))
 
 
+def grad_digest(out, prefix, named_params, full_below=16384, nproj=8):
+    """Gradient record that stays small for MB-sized models: every tensor's norm and ``nproj`` seeded +-1 projections
+    (an error e moves a projection by ~||e||), the full gradient for tensors below ``full_below`` elements."""
+    for i, (k, p) in enumerate(named_params):
+        g = p.grad.detach().double().flatten()
+        out[prefix + "norm/" + k] = np.array(float(g.norm()))
+        r = torch.randint(0, 2, (nproj, g.numel()), generator=torch.Generator().manual_seed(1000 + i)).double() * 2 - 1
+        out[prefix + "proj/" + k] = (r @ g).numpy()
+        if g.numel() <= full_below:
+            out[prefix + "full/" + k] = p.grad.detach().numpy().copy()
+
+
+def golden_deep_bench_shape(tag="deep256_c16_attn_d2", img_size=256, conv_dim=16, depth=2, B=4, z_dim=16, shared=16, classes=5):
+    """BigGAN-Deep at BASELINE config 4's resolution and topology (256x256, g_depth = d_depth = 2, attention at 64x64 ->
+    N = 4096 queries x M = 1024 keys, attn_g_loc [4] / attn_d_loc [2]) with conv_dim 16 so that the CPU reference runs in
+    seconds.  No weights are stored: the reference modules are built under torch.manual_seed(1234) and the product modules
+    reproduce that initialisation bit for bit (tests/test_host_cpu.py checks this); inputs are regenerated from seeds too.
+    Stored: labels / z, sub-sampled images, logits, losses, buffer states and gradient digests (grad_digest)."""
+    torch.manual_seed(1234)
+    M = modules()
+    G = rdeep.Generator(z_dim=z_dim, g_shared_dim=shared, img_size=img_size, g_conv_dim=conv_dim, apply_attn=True,
+                        attn_g_loc=[4], g_cond_mtd="cBN", num_classes=classes, g_init="ortho", g_depth=depth,
+                        mixed_precision=False, MODULES=M, MODEL=MODEL)
+    D = rdeep.Discriminator(img_size=img_size, d_conv_dim=conv_dim, apply_d_sn=True, apply_attn=True, attn_d_loc=[2],
+                            d_cond_mtd="PD", aux_cls_type="W/O", d_embed_dim="N/A", normalize_d_embed=False,
+                            num_classes=classes, d_init="ortho", d_depth=depth, mixed_precision=False, MODULES=M, MODEL=MODEL)
+    G.train(); D.train()
+    with torch.no_grad():
+        for mod in list(G.modules()) + list(D.modules()):
+            if isinstance(mod, rops.SelfAttention):
+                mod.sigma.fill_(0.37)
+    out = {"param_l1_G": np.array(sum(float(p.detach().double().abs().sum()) for p in G.parameters())),
+           "param_l1_D": np.array(sum(float(p.detach().double().abs().sum()) for p in D.parameters()))}
+    gi = torch.Generator().manual_seed(77)
+    z = torch.randn(B, z_dim, generator=gi)
+    y_fake = torch.randint(0, classes, (B,), generator=gi)
+    real = torch.rand(B, 3, img_size, img_size, generator=gi) * 2 - 1
+    y_real = torch.randint(0, classes, (B,), generator=gi)
+    out.update({"z": z.numpy(), "y_fake": y_fake.numpy(), "y_real": y_real.numpy(), "real_sum": np.array(float(real.double().sum()))})
+    for p in G.parameters():
+        p.requires_grad_(False)
+    fake = G(z, y_fake)
+    real_d = D(real, y_real)
+    fake_d = D(fake.detach(), y_fake)
+    # Wasserstein losses: every sample of both branches carries gradient (the seeded-init logits sit outside the hinge margins)
+    d_loss = rlosses.d_wasserstein(real_d["adv_output"], fake_d["adv_output"], False)
+    d_loss.backward()
+    out.update({"fake_sub8": fake.detach()[:, :, ::8, ::8].numpy().copy(), "fake_mean_abs": np.array(float(fake.detach().abs().mean())),
+                "adv_real": real_d["adv_output"].detach().numpy(), "adv_fake": fake_d["adv_output"].detach().numpy(),
+                "h_real": real_d["h"].detach().numpy(), "d_loss": d_loss.detach().numpy()})
+    grad_digest(out, "Dgrad/", list(D.named_parameters()))
+    out.update(sd_np(G, "G1/", True))
+    out.update(sd_np(D, "D1/", True))
+    D.zero_grad()
+    for p in G.parameters():
+        p.requires_grad_(True)
+    for p in D.parameters():
+        p.requires_grad_(False)
+    fake2 = G(z, y_fake)
+    g_loss = rlosses.g_wasserstein(D(fake2, y_fake)["adv_output"], False)
+    g_loss.backward()
+    out.update({"fake2_sub8": fake2.detach()[:, :, ::8, ::8].numpy().copy(), "g_loss": g_loss.detach().numpy()})
+    grad_digest(out, "Ggrad/", list(G.named_parameters()))
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
+    print(tag, "keys", len(out), "d_loss", float(d_loss), "g_loss", float(g_loss), "params",
+          sum(p.numel() for p in G.parameters()), sum(p.numel() for p in D.parameters()))
+
+
 def golden_resfamily(tag, family, conv_dim, attn, g_sn, d_sn, g_cond, d_cond, adv, z_dim=20, shared=16, classes=5, B=8, img_size=32):
     """BigGAN (big_resnet) / ResNetGAN (resnet): D phase + G phase exactly as golden_deep."""
     torch.manual_seed(4321)
@@ -382,3 +450,4 @@ if __name__ == "__main__":
     golden_gp("gp_resnet32_bn_c16", "resnet", 16, False, "W/O")           # the WGAN-GP config's discriminator (BatchNorm, no SN)
     golden_gp("gp_resnet32_sn_c16_pd", "resnet", 16, True, "PD")
     golden_gp("gp_deep32_sn_c8_pd", "deep", 8, True, "PD")
+    golden_deep_bench_shape()

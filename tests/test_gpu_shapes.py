@@ -1,0 +1,197 @@
+"""GPU parity at the layer shapes BASELINE configs 4 / 5 actually run: every code path of the
+conv engine that the 256x256 BigGAN-Deep step selects -- multi-K-block generic tiles, the halo-row kernel's resident and
+ring filter paths, the 64-channel weight-gradient kernel, split-K / per-image weight gradients, small-map 1x1 layers
+with many channel tiles -- against plain fp32 torch on the CPU, plus the epilogue column statistics against the
+stand-alone reduction kernel.  Tolerances as in test_gpu_parity.py: one bf16 rounding of the output (8e-3 max-norm),
+fp32 accumulation of bf16 products for weight gradients (2e-3).
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from test_gpu_parity import _cuda, bfr, rel_err, to_nhwc  # noqa: E402
+
+
+# (B, H, W, Cin, Cout, k): which kernel / path it selects at these sizes
+BENCH_SHAPES = [
+    (32, 4, 4, 2048, 512, 1),     # 1x1 2048->512 @4x4, B=32: 32 K blocks, 4 pixel tiles x 4 channel tiles (8-GPU operating point)
+    (4, 4, 4, 512, 2048, 1),      # 1x1 512->2048 @4x4: 8 channel tiles of 256
+    (2, 16, 16, 512, 512, 3),     # 3x3 512->512 @16x16: generic per-tap kernel, 72 K iterations, direct-store epilogue
+    (1, 128, 128, 128, 128, 3),   # 3x3 128->128 @128x128: halo-row kernel, filter ring (2 K blocks)
+    (1, 256, 256, 64, 64, 3),     # 3x3 64->64 @256x256: halo-row kernel, resident taps + wgrad3x3_c64
+    (2, 64, 64, 256, 256, 3),     # 3x3 256->256 @64x64: generic kernel at the roofline shape
+    (2, 128, 128, 64, 256, 1),    # write-dominated 1x1 (TMA-store epilogue, two staging tiles per team)
+    (1, 256, 256, 128, 64, 1),    # read-dominated 1x1 at 256x256
+    (2, 64, 64, 512, 64, 1),      # attention-adjacent 1x1 (theta / phi)
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", BENCH_SHAPES)
+def test_conv_fwd_bwd_at_bench_shapes(B, H, W, Cin, Cout, k):
+    from sgb200 import autograd_ops as A
+    dev = _cuda()
+    g = torch.Generator().manual_seed(B * 1000 + Cin + Cout + k)
+    x = bfr(torch.randn(B, Cin, H, W, generator=g))
+    w = torch.randn(Cout, Cin, k, k, generator=g) * (1.0 / np.sqrt(Cin * k * k))
+    b = torch.randn(Cout, generator=g)
+    dy = bfr(torch.randn(B, Cout, H, W, generator=g))
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.conv2d(xr, bfr(wr.detach()) + (wr - wr.detach()), br, padding=k // 2)
+    yr.backward(dy)
+    xd = to_nhwc(x, dev).requires_grad_(True)
+    wd, bd = w.to(dev).requires_grad_(True), b.to(dev).requires_grad_(True)
+    y = A.ConvFn.apply(xd, wd, bd, None, {"KH": k, "KW": k, "pad": k // 2})
+    y.backward(to_nhwc(dy, dev))
+    assert rel_err(y, yr) < 8e-3
+    assert rel_err(xd.grad, xr.grad) < 8e-3
+    assert rel_err(wd.grad, wr.grad) < 2e-3
+    assert rel_err(bd.grad, br.grad) < 2e-3
+
+
+def test_per_image_wgrad_at_attention_size():
+    """Per-image weight gradient at N = 4096 pixels (attention dK / dV of BASELINE config 4): dphi[b] = dS[b]^T theta[b]
+    with theta [B, 64, 64x64], dS [B, M = 1024, 64x64]."""
+    from sgb200 import kernels as K
+    dev = _cuda()
+    g = torch.Generator().manual_seed(5)
+    B, c8, M, S = 2, 64, 1024, 64
+    theta = bfr(torch.randn(B, c8, S, S, generator=g))
+    dS = bfr(torch.randn(B, M, S, S, generator=g) * 0.1)
+    got = K.conv_wgrad(to_nhwc(theta, dev), to_nhwc(dS, dev), 1, 1, 0, 0, per_image=True)     # [B][M][1][c8]
+    ref = torch.einsum("bmn,bcn->bmc", dS.flatten(2).double(), theta.flatten(2).double())
+    assert rel_err(got.view(B, M, c8), ref) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,extra", [
+    (4, 16, 16, 64, 256, 1, "res"),        # generic kernel, TMA-store epilogue, 2 channel chunks per team, residual via TMA
+    (4, 16, 16, 64, 192, 1, "mask"),       # Cout % 128 != 0: ragged last channel tile
+    (2, 8, 8, 512, 2048, 1, ""),           # 8 channel tiles: grid trimmed to a multiple of tiles_n
+    (2, 32, 32, 256, 256, 3, "relu"),      # K > TMA-epilogue limit: direct-store epilogue (epilogue_row)
+    (1, 128, 128, 64, 64, 3, ""),          # halo-row kernel, resident taps: team 0 TMA store + team 1 direct store
+    (1, 128, 128, 128, 128, 3, "relu"),    # halo-row kernel, filter ring, two staging tiles
+    (3, 8, 8, 32, 24, 1, ""),              # Cout = 24: BN = 32, not a TMA-store shape
+])
+def test_conv_epilogue_column_statistics(B, H, W, Cin, Cout, k, extra):
+    """sum / sum of squares of the stored output, accumulated by the conv epilogue, against the stand-alone bn_stats pass
+    over the same bf16 tensor (identical inputs to the reduction; only the fp32 summation order differs: 2e-5 relative to
+    the column's L1 mass)."""
+    from sgb200 import kernels as K
+    dev = _cuda()
+    torch.manual_seed(11)
+    x = K.empty_nhwc(B, Cin, H, W, dev).normal_()
+    w = torch.randn(Cout, Cin, k, k, device=dev) / np.sqrt(Cin * k * k)
+    wf, _ = K.weight_pack(w, None, Cout, Cin, k * k, True, False)
+    bias = torch.randn(Cout, device=dev)
+    res = K.empty_nhwc(B, Cout, H, W, dev).normal_() if extra == "res" else None
+    mask = K.empty_nhwc(B, Cout, H, W, dev).normal_() if extra == "mask" else None
+    y = K.conv_fprop(x, wf, Cout, k, k, k // 2, k // 2, bias=bias, residual=res, mask=mask, relu=(extra == "relu"), stats=2)
+    cs = K.colstats(y, 2)
+    assert cs is not None and cs.shape == (2, Cout)
+    ref = K.bn_stats(y)
+    l1 = y.float().abs().sum((0, 2, 3)) + 1e-3
+    l2 = (y.float() ** 2).sum((0, 2, 3)) + 1e-3
+    assert float(((cs[0] - ref[0]).abs() / l1).max()) < 2e-5
+    assert float(((cs[1] - ref[1]).abs() / l2).max()) < 2e-5
+    y2 = K.conv_fprop(x, wf, Cout, k, k, k // 2, k // 2, bias=bias, residual=res, mask=mask, relu=(extra == "relu"))
+    assert torch.equal(y, y2)             # the statistics path stores exactly what the plain epilogue stores
+
+
+# ------------------------------------------------------------------------------------------------ full model at 256x256
+def _digest_errors(net, g, prefix):
+    """Checks a gradient against tests/golden/make_golden.py::grad_digest: full tensors where stored, else norm + seeded
+    +-1 projections.  Returns (worst relative error over full tensors, worst norm ratio error, worst projection error in
+    units of the reference norm)."""
+    gmax = max(float(g[prefix + "norm/" + n]) for n, _ in net.named_parameters())
+    worst_full, worst_norm, worst_proj = (0.0, ""), (0.0, ""), (0.0, "")
+    for i, (n, p) in enumerate(net.named_parameters()):
+        got = p.grad.detach().double().cpu().flatten()
+        rn = float(g[prefix + "norm/" + n])
+        floor = rn + 1e-3 * gmax
+        r = torch.randint(0, 2, (8, got.numel()), generator=torch.Generator().manual_seed(1000 + i)).double() * 2 - 1
+        pe = float(((r @ got) - torch.from_numpy(g[prefix + "proj/" + n])).abs().max()) / floor
+        worst_proj = max(worst_proj, (pe, n))
+        worst_norm = max(worst_norm, (abs(float(got.norm()) - rn) / floor, n))
+        if prefix + "full/" + n in g.files:
+            ref = torch.from_numpy(g[prefix + "full/" + n]).double().flatten()
+            worst_full = max(worst_full, (float((got - ref).norm()) / floor, n))
+    return worst_full, worst_norm, worst_proj
+
+
+def test_biggan_deep_256_d_and_g_phase_vs_reference_golden(golden_dir):
+    """BASELINE config 4's topology at its resolution -- 256x256, g_depth = d_depth = 2, attention at 64x64 (N = 4096,
+    M = 1024), six up / down-sampling stages -- with conv_dim 16, against the reference's own CPU numbers
+    (tests/golden/deep256_c16_attn_d2.npz).  Weights and inputs are regenerated from the seeds the generator script used
+    (the parameter L1 checksums prove both sides hold the same values).  Same tolerances as the 32x32 goldens: relative L2
+    4e-2 on images / features / logits, 1e-1 on discriminator-phase gradients; generator-phase gradients (B = 4,
+    through D and G's batch-norm chain in bf16): worst tensor <= 0.3."""
+    import importlib
+    import os
+    from sgb200 import config as C
+    from sgb200 import kernels as K
+    from sgb200.utils import losses
+    from test_gpu_parity import l2_err
+    dev = _cuda()
+    g = np.load(os.path.join(golden_dir, "deep256_c16_attn_d2.npz"))
+    deep = importlib.import_module("sgb200.models.big_resnet_deep_legacy")
+    torch.manual_seed(1234)
+    M = C.make_modules(True, True, "cBN", "big_resnet_deep_legacy")
+    MODEL = C._Section(info_type="N/A", g_info_injection="N/A")
+    G = deep.Generator(z_dim=16, g_shared_dim=16, img_size=256, g_conv_dim=16, apply_attn=True, attn_g_loc=[4], g_cond_mtd="cBN",
+                       num_classes=5, g_init="ortho", g_depth=2, mixed_precision=False, MODULES=M, MODEL=MODEL)
+    D = deep.Discriminator(img_size=256, d_conv_dim=16, apply_d_sn=True, apply_attn=True, attn_d_loc=[2], d_cond_mtd="PD",
+                           aux_cls_type="W/O", d_embed_dim="N/A", normalize_d_embed=False, num_classes=5, d_init="ortho",
+                           d_depth=2, mixed_precision=False, MODULES=M, MODEL=MODEL)
+    from sgb200.utils import ops
+    with torch.no_grad():
+        for mod in list(G.modules()) + list(D.modules()):
+            if isinstance(mod, ops.SelfAttention):
+                mod.sigma.fill_(0.37)
+    l1g = sum(float(p.detach().double().abs().sum()) for p in G.parameters())
+    l1d = sum(float(p.detach().double().abs().sum()) for p in D.parameters())
+    assert abs(l1g - float(g["param_l1_G"])) < 1e-6 * l1g and abs(l1d - float(g["param_l1_D"])) < 1e-6 * l1d
+    gi = torch.Generator().manual_seed(77)
+    z = torch.randn(4, 16, generator=gi)
+    yf = torch.randint(0, 5, (4,), generator=gi)
+    real = torch.rand(4, 3, 256, 256, generator=gi) * 2 - 1
+    yr = torch.randint(0, 5, (4,), generator=gi)
+    assert torch.equal(yf, torch.from_numpy(g["y_fake"])) and torch.equal(yr, torch.from_numpy(g["y_real"]))   # index path: bit exact
+    assert abs(float(real.double().sum()) - float(g["real_sum"])) < 1e-6
+    G, D = G.to(dev).train(), D.to(dev).train()
+    z, yf, real, yr = z.to(dev), yf.to(dev), real.to(dev), yr.to(dev)
+    for p in G.parameters():
+        p.requires_grad_(False)
+    K.COLSTATS_HITS[0] = K.COLSTATS_HITS[1] = 0
+    fake = G(z, yf)
+    assert K.COLSTATS_HITS[0] >= 40, K.COLSTATS_HITS     # the generator's batch norms take their statistics from conv epilogues
+    assert fake.shape == (4, 3, 256, 256)
+    assert l2_err(fake[:, :, ::8, ::8], torch.from_numpy(g["fake_sub8"])) < 4e-2
+    real_d, fake_d = D(real, yr), D(fake.detach(), yf)
+    assert l2_err(real_d["h"], torch.from_numpy(g["h_real"])) < 4e-2
+    assert l2_err(real_d["adv_output"], torch.from_numpy(g["adv_real"])) < 4e-2
+    assert l2_err(fake_d["adv_output"], torch.from_numpy(g["adv_fake"])) < 4e-2
+    d_loss = losses.d_wasserstein(real_d["adv_output"], fake_d["adv_output"])
+    d_loss.backward()
+    assert abs(float(d_loss) - float(g["d_loss"])) < 5e-2 * max(1.0, abs(float(g["d_loss"])))
+    wf, wn, wp = _digest_errors(D, g, "Dgrad/")
+    assert wf[0] < 1e-1 and wn[0] < 1e-1 and wp[0] < 3e-1, (wf, wn, wp)
+    for n, b in D.named_buffers():
+        if "weight_u" in n:
+            assert rel_err(b, torch.from_numpy(g["D1/" + n])) < 1e-2, n
+    for n, b in G.named_buffers():
+        if "weight_u" in n or "running_" in n:
+            assert rel_err(b, torch.from_numpy(g["G1/" + n])) < 1e-2, n
+    D.zero_grad(set_to_none=True)
+    for p in G.parameters():
+        p.requires_grad_(True)
+    for p in D.parameters():
+        p.requires_grad_(False)
+    fake2 = G(z, yf)
+    assert l2_err(fake2[:, :, ::8, ::8], torch.from_numpy(g["fake2_sub8"])) < 4e-2
+    g_loss = losses.g_wasserstein(D(fake2, yf)["adv_output"])
+    g_loss.backward()
+    assert abs(float(g_loss) - float(g["g_loss"])) < 5e-2 * abs(float(g["g_loss"]))
+    wf, wn, wp = _digest_errors(G, g, "Ggrad/")
+    assert wf[0] < 0.3 and wn[0] < 0.3 and wp[0] < 0.9, (wf, wn, wp)

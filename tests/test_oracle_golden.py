@@ -178,3 +178,56 @@ def test_dcgan_config1_oracle_matches_reference(golden_dir):
         if k.startswith("Ggrad/"):
             ref = g[k]
             assert np.abs(sdG[k[6:]].grad.numpy() - ref).max() <= 2e-3 * (1e-4 + np.abs(ref).max()) + floor_g, k
+
+
+def test_deep_256_bench_topology(golden_dir):
+    """The oracle at BASELINE config 4's topology (256x256, depth 2, attention at 64x64: N = 4096, M = 1024) against the
+    reference golden deep256_c16_attn_d2 (weights regenerated from the generator script's seed through the product
+    modules, whose seeded initialisation equals the reference's bit for bit)."""
+    import importlib
+    from sgb200 import config as C
+    from sgb200.utils import ops
+    g = np.load(os.path.join(golden_dir, "deep256_c16_attn_d2.npz"))
+    deep = importlib.import_module("sgb200.models.big_resnet_deep_legacy")
+    torch.manual_seed(1234)
+    M = C.make_modules(True, True, "cBN", "big_resnet_deep_legacy")
+    MODEL = C._Section(info_type="N/A", g_info_injection="N/A")
+    G = deep.Generator(z_dim=16, g_shared_dim=16, img_size=256, g_conv_dim=16, apply_attn=True, attn_g_loc=[4], g_cond_mtd="cBN",
+                       num_classes=5, g_init="ortho", g_depth=2, mixed_precision=False, MODULES=M, MODEL=MODEL)
+    D = deep.Discriminator(img_size=256, d_conv_dim=16, apply_d_sn=True, apply_attn=True, attn_d_loc=[2], d_cond_mtd="PD",
+                           aux_cls_type="W/O", d_embed_dim="N/A", normalize_d_embed=False, num_classes=5, d_init="ortho",
+                           d_depth=2, mixed_precision=False, MODULES=M, MODEL=MODEL)
+    with torch.no_grad():
+        for mod in list(G.modules()) + list(D.modules()):
+            if isinstance(mod, ops.SelfAttention):
+                mod.sigma.fill_(0.37)
+    sdG = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    sdD = {k: v.detach().clone() for k, v in D.state_dict().items()}
+    l1 = sum(float(p.detach().double().abs().sum()) for p in G.parameters())
+    assert abs(l1 - float(g["param_l1_G"])) < 1e-6 * l1
+    pD = [k for k, _ in D.named_parameters()]
+    for k in pD:
+        sdD[k].requires_grad_(True)
+    gi = torch.Generator().manual_seed(77)
+    z = torch.randn(4, 16, generator=gi)
+    yf = torch.randint(0, 5, (4,), generator=gi)
+    real = torch.rand(4, 3, 256, 256, generator=gi) * 2 - 1
+    yr = torch.randint(0, 5, (4,), generator=gi)
+    kw_g = dict(img_size=256, g_conv_dim=16, g_depth=2, attn_g_loc=(4,), apply_attn=True)
+    kw_d = dict(img_size=256, d_conv_dim=16, d_depth=2, attn_d_loc=(2,), apply_attn=True)
+    with torch.no_grad():
+        fake = O.deep_generator(sdG, z, yf, **kw_g)
+    np.testing.assert_allclose(fake[:, :, ::8, ::8].numpy(), g["fake_sub8"], rtol=1e-3, atol=2e-4)
+    adv_r, h_r = O.deep_discriminator(sdD, real, yr, **kw_d)
+    adv_f, _ = O.deep_discriminator(sdD, fake, yf, **kw_d)
+    np.testing.assert_allclose(adv_r.detach().numpy(), g["adv_real"], rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(adv_f.detach().numpy(), g["adv_fake"], rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(h_r.detach().numpy(), g["h_real"], rtol=1e-3, atol=1e-3)
+    (-adv_r.mean() + adv_f.mean()).backward()                 # losses.d_wasserstein (src/utils/losses.py:214-215)
+    gmax = max(float(g["Dgrad/norm/" + k]) for k in pD)
+    for k in pD:
+        ref_n = float(g["Dgrad/norm/" + k])
+        assert abs(float(sdD[k].grad.norm()) - ref_n) <= 5e-3 * (ref_n + 1e-3 * gmax), k
+        if "Dgrad/full/" + k in g.files:
+            ref = g["Dgrad/full/" + k]
+            assert np.abs(sdD[k].grad.numpy() - ref).max() <= 5e-3 * (1e-3 * gmax + np.abs(ref).max()), k
