@@ -79,6 +79,8 @@ typedef struct sgb_conv_desc {
    * separate pass over the tensor.  bf16 outputs only. */
   float* colsum;
   float* colsumsq;
+  float res_scale;     /* residual multiplier (0 is read as 1): 0.25 with res_up2 = the backward of a 2x2 average pooling
+                          added in the epilogue (src/models/big_resnet_deep_legacy.py:220-224, the pooled skip branch) */
 } sgb_conv_desc;
 
 int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream);
@@ -98,12 +100,14 @@ typedef struct sgb_wgrad_desc {
   int32_t accumulate; /* 0: dw is zeroed first */
   int32_t per_image;  /* 1: one gradient per image (attention dK/dV); needs H*W >= 128 */
   float* dbias;       /* optional fp32 [Cout]: bias gradient sum_{b,h,w} dy, produced by the same launch (zeroed first unless
-                         accumulate) -- only when sgb_conv_wgrad_fuses_dbias(d) returns 1, otherwise it must be NULL */
+                         accumulate): a constant-ones operand rides along the dy tiles on the tensor pipe, so no separate
+                         reduction pass reads dy -- only when sgb_conv_wgrad_fuses_dbias(d) returns 1 (not per_image) */
 } sgb_wgrad_desc;
 
 int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream);
-/* 1 if sgb_conv_wgrad(d) can also deliver d->dbias (the 3x3 / 64-channel kernel feeds a constant-one operand atom to the
- * otherwise idle half of its last MMA group, so the bias gradient costs no extra pass over dy); 0 otherwise. */
+/* 1 if sgb_conv_wgrad(d) can also deliver d->dbias (3x3 / 64-channel kernel: constant-one operand atom in the otherwise
+ * idle half of its last MMA group; generic kernel: an N = 16 ones-product on its first-tap / first-channel-tile work
+ * items); 0 for per-image gradients. */
 int sgb_conv_wgrad_fuses_dbias(const sgb_wgrad_desc* d);
 
 /* ------------------------------------------------------------------------------------------

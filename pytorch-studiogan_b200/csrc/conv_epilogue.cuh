@@ -11,7 +11,7 @@ struct EpiArgs {
   float alpha;
   const float* alpha_ptr;
   const float* bias;
-  const bf16* residual; long long res_cstride; int res_up2; int res_after;
+  const bf16* residual; long long res_cstride; int res_up2; int res_after; float res_scale;
   const bf16* mask; long long mask_cstride;
   int relu;
   void* y; long long y_cstride; int y_fp32;
@@ -93,6 +93,7 @@ __device__ __forceinline__ void epilogue_row(const EpiArgs& p, uint32_t t_row, i
                                              long long rpix, float alpha, bool vec_ok, float* stat_acc = nullptr) {
   const bool res_pre = p.residual != nullptr && !p.res_after;
   const bool res_post = p.residual != nullptr && p.res_after;
+  const float rs = p.res_scale;
   for (int c0 = 0; c0 < BN; c0 += 16) {
     uint32_t v[16];
     __syncwarp();
@@ -111,10 +112,10 @@ __device__ __forceinline__ void epilogue_row(const EpiArgs& p, uint32_t t_row, i
         float x = f[j];
         const bool ok = valid && nn < p.Cout;
         if (p.bias && ok) x += __ldg(p.bias + nn);
-        if (res_pre && ok) x += __bfloat162float(p.residual[rpix * p.res_cstride + nn]);
+        if (res_pre && ok) x = fmaf(__bfloat162float(p.residual[rpix * p.res_cstride + nn]), rs, x);
         if (p.relu) x = fmaxf(x, 0.f);
         if (p.mask && ok) x = __bfloat162float(p.mask[pix * p.mask_cstride + nn]) > 0.f ? x : 0.f;
-        if (res_post && ok) x += __bfloat162float(p.residual[rpix * p.res_cstride + nn]);
+        if (res_post && ok) x = fmaf(__bfloat162float(p.residual[rpix * p.res_cstride + nn]), rs, x);
         f[j] = ok ? __bfloat162float(__float2bfloat16_rn(x)) : 0.f;
       }
       if (valid) {
@@ -156,10 +157,10 @@ __device__ __forceinline__ void epilogue_row(const EpiArgs& p, uint32_t t_row, i
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const uint4 r = __ldg(rp + j);
-          f[8 * j + 0] += bf16_bits_lo(r.x); f[8 * j + 1] += bf16_bits_hi(r.x);
-          f[8 * j + 2] += bf16_bits_lo(r.y); f[8 * j + 3] += bf16_bits_hi(r.y);
-          f[8 * j + 4] += bf16_bits_lo(r.z); f[8 * j + 5] += bf16_bits_hi(r.z);
-          f[8 * j + 6] += bf16_bits_lo(r.w); f[8 * j + 7] += bf16_bits_hi(r.w);
+          f[8 * j + 0] = fmaf(bf16_bits_lo(r.x), rs, f[8 * j + 0]); f[8 * j + 1] = fmaf(bf16_bits_hi(r.x), rs, f[8 * j + 1]);
+          f[8 * j + 2] = fmaf(bf16_bits_lo(r.y), rs, f[8 * j + 2]); f[8 * j + 3] = fmaf(bf16_bits_hi(r.y), rs, f[8 * j + 3]);
+          f[8 * j + 4] = fmaf(bf16_bits_lo(r.z), rs, f[8 * j + 4]); f[8 * j + 5] = fmaf(bf16_bits_hi(r.z), rs, f[8 * j + 5]);
+          f[8 * j + 6] = fmaf(bf16_bits_lo(r.w), rs, f[8 * j + 6]); f[8 * j + 7] = fmaf(bf16_bits_hi(r.w), rs, f[8 * j + 7]);
         }
       }
       if (p.relu) {
@@ -186,10 +187,10 @@ __device__ __forceinline__ void epilogue_row(const EpiArgs& p, uint32_t t_row, i
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const uint4 r = __ldg(rp + j);
-          f[8 * j + 0] += bf16_bits_lo(r.x); f[8 * j + 1] += bf16_bits_hi(r.x);
-          f[8 * j + 2] += bf16_bits_lo(r.y); f[8 * j + 3] += bf16_bits_hi(r.y);
-          f[8 * j + 4] += bf16_bits_lo(r.z); f[8 * j + 5] += bf16_bits_hi(r.z);
-          f[8 * j + 6] += bf16_bits_lo(r.w); f[8 * j + 7] += bf16_bits_hi(r.w);
+          f[8 * j + 0] = fmaf(bf16_bits_lo(r.x), rs, f[8 * j + 0]); f[8 * j + 1] = fmaf(bf16_bits_hi(r.x), rs, f[8 * j + 1]);
+          f[8 * j + 2] = fmaf(bf16_bits_lo(r.y), rs, f[8 * j + 2]); f[8 * j + 3] = fmaf(bf16_bits_hi(r.y), rs, f[8 * j + 3]);
+          f[8 * j + 4] = fmaf(bf16_bits_lo(r.z), rs, f[8 * j + 4]); f[8 * j + 5] = fmaf(bf16_bits_hi(r.z), rs, f[8 * j + 5]);
+          f[8 * j + 6] = fmaf(bf16_bits_lo(r.w), rs, f[8 * j + 6]); f[8 * j + 7] = fmaf(bf16_bits_hi(r.w), rs, f[8 * j + 7]);
         }
       }
       if (p.y_fp32) {
@@ -216,10 +217,10 @@ __device__ __forceinline__ void epilogue_row(const EpiArgs& p, uint32_t t_row, i
         if (nn < p.Cout) {
           float x = f[j];
           if (p.bias) x += __ldg(p.bias + nn);
-          if (res_pre) x += __bfloat162float(p.residual[rpix * p.res_cstride + nn]);
+          if (res_pre) x = fmaf(__bfloat162float(p.residual[rpix * p.res_cstride + nn]), rs, x);
           if (p.relu) x = fmaxf(x, 0.f);
           if (p.mask) x = __bfloat162float(p.mask[pix * p.mask_cstride + nn]) > 0.f ? x : 0.f;
-          if (res_post) x += __bfloat162float(p.residual[rpix * p.res_cstride + nn]);
+          if (res_post) x = fmaf(__bfloat162float(p.residual[rpix * p.res_cstride + nn]), rs, x);
           if (p.y_fp32) reinterpret_cast<float*>(p.y)[pix * p.y_cstride + nn] = x;
           else reinterpret_cast<bf16*>(p.y)[pix * p.y_cstride + nn] = __float2bfloat16_rn(x);
         }
@@ -276,6 +277,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
                                                   float* stat_acc = nullptr) {
   const bool res_pre = p.residual != nullptr && !p.res_after;
   const bool res_post = p.residual != nullptr && p.res_after;
+  const float rs = p.res_scale;
   // sbuf != nullptr: the team owns TWO staging tiles (stage, stage + 16 KiB) used alternately, so a chunk only waits for the
   // store issued two chunks ago -- the latency of the previous tensor store is off the critical path.
   const uint32_t sw = (uint32_t)(row & 7);
@@ -331,10 +333,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
         for (int j = 0; j < 2; ++j) {
           const uint4 r = (aux_kind == 1) ? ld_shared_v4(arow_addr + (((uint32_t)(2 * s + j) ^ asw) << 4))
                                           : (8 * j < nvalid ? __ldg(rp + j) : make_uint4(0u, 0u, 0u, 0u));
-          f[8 * j + 0] += bf16_bits_lo(r.x); f[8 * j + 1] += bf16_bits_hi(r.x);
-          f[8 * j + 2] += bf16_bits_lo(r.y); f[8 * j + 3] += bf16_bits_hi(r.y);
-          f[8 * j + 4] += bf16_bits_lo(r.z); f[8 * j + 5] += bf16_bits_hi(r.z);
-          f[8 * j + 6] += bf16_bits_lo(r.w); f[8 * j + 7] += bf16_bits_hi(r.w);
+          f[8 * j + 0] = fmaf(bf16_bits_lo(r.x), rs, f[8 * j + 0]); f[8 * j + 1] = fmaf(bf16_bits_hi(r.x), rs, f[8 * j + 1]);
+          f[8 * j + 2] = fmaf(bf16_bits_lo(r.y), rs, f[8 * j + 2]); f[8 * j + 3] = fmaf(bf16_bits_hi(r.y), rs, f[8 * j + 3]);
+          f[8 * j + 4] = fmaf(bf16_bits_lo(r.z), rs, f[8 * j + 4]); f[8 * j + 5] = fmaf(bf16_bits_hi(r.z), rs, f[8 * j + 5]);
+          f[8 * j + 6] = fmaf(bf16_bits_lo(r.w), rs, f[8 * j + 6]); f[8 * j + 7] = fmaf(bf16_bits_hi(r.w), rs, f[8 * j + 7]);
         }
       }
       if (p.relu) {
@@ -363,10 +365,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
         for (int j = 0; j < 2; ++j) {
           const uint4 r = (aux_kind == 1) ? ld_shared_v4(arow_addr + (((uint32_t)(2 * s + j) ^ asw) << 4))
                                           : (8 * j < nvalid ? __ldg(rp + j) : make_uint4(0u, 0u, 0u, 0u));
-          f[8 * j + 0] += bf16_bits_lo(r.x); f[8 * j + 1] += bf16_bits_hi(r.x);
-          f[8 * j + 2] += bf16_bits_lo(r.y); f[8 * j + 3] += bf16_bits_hi(r.y);
-          f[8 * j + 4] += bf16_bits_lo(r.z); f[8 * j + 5] += bf16_bits_hi(r.z);
-          f[8 * j + 6] += bf16_bits_lo(r.w); f[8 * j + 7] += bf16_bits_hi(r.w);
+          f[8 * j + 0] = fmaf(bf16_bits_lo(r.x), rs, f[8 * j + 0]); f[8 * j + 1] = fmaf(bf16_bits_hi(r.x), rs, f[8 * j + 1]);
+          f[8 * j + 2] = fmaf(bf16_bits_lo(r.y), rs, f[8 * j + 2]); f[8 * j + 3] = fmaf(bf16_bits_hi(r.y), rs, f[8 * j + 3]);
+          f[8 * j + 4] = fmaf(bf16_bits_lo(r.z), rs, f[8 * j + 4]); f[8 * j + 5] = fmaf(bf16_bits_hi(r.z), rs, f[8 * j + 5]);
+          f[8 * j + 6] = fmaf(bf16_bits_lo(r.w), rs, f[8 * j + 6]); f[8 * j + 7] = fmaf(bf16_bits_hi(r.w), rs, f[8 * j + 7]);
         }
       }
       // 16 channels = two 16-byte units (2s, 2s+1) of this row's 128-byte line; unit u lives at (u ^ (row & 7))

@@ -252,12 +252,14 @@ struct WgradArgs {
   uint32_t tmem_cols;
   float* dw;
   long long dw_group_stride;
+  float* dbias;                              // optional: sum over pixels of dy (bias gradient), from a constant-ones B operand
 };
 
 __global__ void __launch_bounds__(kWgradThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgradArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ones_base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // 16 KiB of bf16 1.0 when dbias (any swizzle of ones is ones)
+  const uint32_t smem_base = ones_base + (p.dbias ? (uint32_t)kABytes : 0u);
   const uint32_t a_bytes = 2 * kABytes;                       // two 64-channel boxes -> M = 128
   const uint32_t b_bytes = (uint32_t)(p.BN / 64) * kABytes;   // BN/64 boxes
   const uint32_t stage_bytes = a_bytes + b_bytes;
@@ -271,6 +273,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  if (p.dbias) {
+    for (uint32_t i = threadIdx.x; i < (uint32_t)kABytes / 16u; i += kWgradThreads)
+      st_shared_v4(ones_base + i * 16u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();                 // generic-proxy writes -> visible to the tensor core's operand reads
+  }
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmDY);
     tma_prefetch_desc(&tmX);
@@ -335,6 +342,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(kTileM, p.BN, 1, 1);  // both operands MN-major
+      const uint32_t idesc_ones = make_idesc_bf16(kTileM, 16, 1, 1);
+      const uint64_t ones_desc = make_sdesc_sw128(ones_base, kABytes, 1024);
       uint32_t it = 0, tcount = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++tcount) {
         int mt, nt, tap, grp, pb, pe;
@@ -343,6 +352,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         mbar_wait(tempty_bar(a), aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * p.BN;
+        // bias gradient: the (first input-channel tile, first tap) items also multiply dY^T by a block of ones
+        const bool with_bias = p.dbias != nullptr && nt == 0 && tap == 0;
+        const uint32_t d_bias = tmem_base + 2 * p.BN + a * 16;
         for (int pt = pb; pt < pe; ++pt, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
@@ -356,6 +368,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           for (int kk = 0; kk < kTileM / 16; ++kk) {
             // 16 pixels (K) = two 8-row groups = 2048 bytes -> +128 in the (addr >> 4) field
             umma_f16_ss(d_tmem, adesc + 128 * kk, bdesc + 128 * kk, idesc, (pt > pb || kk > 0) ? 1u : 0u);
+          }
+          if (with_bias) {
+#pragma unroll
+            for (int kk = 0; kk < kTileM / 16; ++kk)
+              umma_f16_ss(d_bias, adesc + 128 * kk, ones_desc + 128 * kk, idesc_ones, (pt > pb || kk > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(s));
         }
@@ -375,6 +392,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + a * p.BN;
       float* dst = p.dw + grp * p.dw_group_stride + ((long long)co * p.taps + tap) * p.Cin;
+      if (p.dbias != nullptr && nt == 0 && tap == 0) {      // warp-uniform: column 0 of the ones-product = sum over this item's pixels
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + 2 * p.BN + a * 16, v);
+        tmem_ld_wait();
+        if (pe > pb && co < p.Cout) atomicAdd(p.dbias + co, __uint_as_float(v[0]));
+      }
       for (int c0 = 0; c0 < p.BN; c0 += 16) {
         uint32_t v[16];
         __syncwarp();
@@ -424,6 +448,7 @@ void fill_epi(EpiArgs& e, const sgb_conv_desc* d) {
   e.H = d->H; e.W = d->W; e.Cout = d->Cout;
   e.alpha = d->alpha; e.alpha_ptr = d->alpha_ptr; e.bias = d->bias;
   e.residual = (const bf16*)d->residual; e.res_cstride = d->res_cstride; e.res_up2 = d->res_up2; e.res_after = d->res_after_mask;
+  e.res_scale = d->res_scale != 0.f ? d->res_scale : 1.f;
   e.mask = (const bf16*)d->mask; e.mask_cstride = d->mask_cstride; e.relu = d->relu;
   e.y = d->y; e.y_cstride = d->y_cstride; e.y_fp32 = d->y_fp32;
   e.colsum = d->colsum; e.colsumsq = d->colsumsq;
@@ -571,7 +596,9 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
 }
 
 extern "C" int sgb_conv_wgrad_fuses_dbias(const sgb_wgrad_desc* d) {
-  return (d && env_int("SGB_WGRAD3X3", 1) && wgrad3x3_c64_eligible(d)) ? 1 : 0;
+  if (!d) return 0;
+  if (env_int("SGB_WGRAD3X3", 1) && wgrad3x3_c64_eligible(d)) return 1;
+  return d->per_image ? 0 : 1;          // generic kernel: constant-ones B operand on its (first channel tile, first tap) items
 }
 
 extern "C" int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream_) {
@@ -581,7 +608,7 @@ extern "C" int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream_) {
   SGB_REQUIRE(d->Cin % 8 == 0 && d->x_cstride % 8 == 0 && d->Cout % 8 == 0 && d->dy_cstride % 8 == 0);
   SGB_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->dy & 15) == 0);
   if (env_int("SGB_WGRAD3X3", 1) && wgrad3x3_c64_eligible(d)) return launch_wgrad3x3_c64(d, stream);
-  SGB_REQUIRE(d->dbias == nullptr);   // only the fused 3x3 kernel produces the bias gradient (sgb_conv_wgrad_fuses_dbias)
+  SGB_REQUIRE(d->dbias == nullptr || !d->per_image);
 
   WgradArgs p;
   p.B = d->B; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
@@ -606,11 +633,13 @@ extern "C" int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream_) {
   p.splits = (p.tiles_per_group + p.tiles_per_split - 1) / p.tiles_per_split;
   p.num_items = base_items * p.splits;
   const uint32_t stage_bytes = 2 * kABytes + (p.BN / 64) * kABytes;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  int stages = (int)(((200 - (d->dbias ? 16 : 0)) * 1024) / stage_bytes);
   if (stages > 6) stages = 6;
   p.stages = stages;
-  p.tmem_cols = pow2_cols(2 * p.BN);
+  p.tmem_cols = pow2_cols(2 * p.BN + (d->dbias ? 32 : 0));
   p.dw = d->dw;
+  p.dbias = d->dbias;
+  if (d->dbias && !d->accumulate) SGB_CUDA(cudaMemsetAsync(d->dbias, 0, sizeof(float) * (size_t)d->Cout, stream));
 
   if (!d->accumulate)
     SGB_CUDA(cudaMemsetAsync(d->dw, 0, sizeof(float) * (size_t)d->Cout * p.taps * d->Cin * (d->per_image ? d->B : 1), stream));
@@ -621,7 +650,7 @@ extern "C" int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream_) {
   rc = make_act_tmap(&tmX, d->x, d->B, d->H, d->W, d->Cin, d->x_cstride, p.tw, p.th, p.nb);
   if (rc) return rc;
 
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 8 * (2 * stages + 4) + 16;
+  const size_t smem = (size_t)stages * stage_bytes + (d->dbias ? kABytes : 0) + 1024 + 8 * (2 * stages + 4) + 16;
   static bool attr_set = false;
   if (!attr_set) {
     SGB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -103,6 +103,34 @@ def _grad_bf16(dy):
     return K.as_nhwc(dy)
 
 
+def conv_param_grads(x, dz, weight, need_w, need_b, KH, KW, pad, dims, sigma, u_saved, v_saved, perm_S=1):
+    """Weight and bias gradient of y = conv(x, W / sigma) + b given dz = dL/dy (NHWC bf16): tcgen05 weight-gradient kernel,
+    then the spectral-norm chain rule (sgb_sn_backward).  The weight gradient is added straight into the flat gradient
+    arena when the parameter opted in (returns None for it then).  The bias gradient is taken, in this order, from the
+    column sums a dgrad epilogue left on dz, from the 3x3 weight-gradient kernel's idle MMA atom, or from a reduction."""
+    Cout, Cin, taps = dims
+    dW = dbias = None
+    if need_b:
+        cs = K.colstats(dz, 1)
+        if cs is not None:
+            dbias = cs[0][:Cout]
+    if need_w:
+        if need_b and dbias is None:
+            G, dbias = K.conv_wgrad(x, dz, KH, KW, pad, pad, want_dbias=True)
+            if dbias is not None:
+                dbias = dbias[:Cout]
+        else:
+            G = K.conv_wgrad(x, dz, KH, KW, pad, pad)
+        tgt = _direct_grad(weight)
+        if tgt is not None:       # accumulate straight into the flat gradient arena: no per-parameter add kernel
+            K.sn_backward(G, weight, u_saved, v_saved, sigma, Cout, Cin, taps, perm_S, out=tgt)
+        else:
+            dW = K.sn_backward(G, weight, u_saved, v_saved, sigma, Cout, Cin, taps, perm_S)
+    if need_b and dbias is None:
+        dbias = K.bn_stats(dz)[0][:Cout]
+    return dW, dbias
+
+
 class ConvFn(TFunction):
     """y = [relu](conv(x, W / sigma) + bias [+ residual])  — conv2d (stride 1) or linear (H = W = 1).
 
@@ -170,21 +198,9 @@ class ConvFn(TFunction):
                                   stats=1 if (mask is not None and not SKIP_PARAM_GRADS) else 0)
             if dx.shape[1] != x.shape[1]:
                 dx = dx[:, :x.shape[1]]
-        if ctx.needs_input_grad[1] and not SKIP_PARAM_GRADS:
-            if ctx.needs_input_grad[2]:
-                G, dbias = K.conv_wgrad(x, dz, KH, KW, pad, pad, want_dbias=True)
-                if dbias is not None:
-                    dbias = dbias[:Cout]
-            else:
-                G = K.conv_wgrad(x, dz, KH, KW, pad, pad)
-            tgt = _direct_grad(weight)
-            if tgt is not None:       # accumulate straight into the flat gradient arena: no per-parameter add kernel
-                K.sn_backward(G, weight, u_saved, v_saved, sigma, Cout, Cin, taps, cfg.get("perm_S", 1), out=tgt)
-            else:
-                dW = K.sn_backward(G, weight, u_saved, v_saved, sigma, Cout, Cin, taps, cfg.get("perm_S", 1))
-        if ctx.needs_input_grad[2] and not SKIP_PARAM_GRADS and dbias is None:
-            cs = K.colstats(dz, 1)
-            dbias = (cs[0] if cs is not None else K.bn_stats(dz)[0])[:Cout]
+        if not SKIP_PARAM_GRADS:
+            dW, dbias = conv_param_grads(x, dz, weight, ctx.needs_input_grad[1], ctx.needs_input_grad[2], KH, KW, pad, ctx.dims,
+                                         sigma, u_saved, v_saved, cfg.get("perm_S", 1))
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = K.pool2_fwd(dz, 2) if cfg.get("res_up2", False) else dz
             rc = ctx.res_shape[1]
@@ -476,6 +492,84 @@ class AddFn(TFunction):
         return _tadd(tan(args[0]), tan(args[1]))
 
 
+class ReluPassFn(TFunction):
+    """a0 = relu(x) for a consumer that returns its gradient already masked by (a0 > 0) (DEntryConvFn): the backward is the
+    identity.  Used where the producer could not apply the ReLU in its own epilogue (after a self-attention block)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return K.axpby(x, relu=True)
+
+    @staticmethod
+    def backward(ctx, da0):
+        return da0
+
+
+def _sn_packs(weight, cfg, Cout, Cin, taps, need_dx):
+    """(fprop pack, dgrad pack, sigma, u, v) of a conv weight: the network's batched spectral-norm pass left them in
+    cfg['sn_cache']; stand-alone use runs the per-layer kernels."""
+    cache = cfg.get("sn_cache")
+    if cache is not None:
+        return cache
+    sn = cfg.get("sn")
+    sigma = us = vs = None
+    if sn is not None:
+        u, v, ws = sn.tensors()
+        sigma = torch.empty(1, device=weight.device, dtype=torch.float32)
+        K.sn_power_iter(weight, u, v, sigma, ws, sn.eps, cfg.get("do_power_iteration", True))
+        us, vs = u.clone(), v.clone()
+    wf, wd = K.weight_pack(weight, sigma, Cout, Cin, taps, True, need_dx)
+    return wf, wd, sigma, us, vs
+
+
+class DEntryConvFn(TFunction):
+    """Entry of a BigGAN-Deep discriminator block (src/models/big_resnet_deep_legacy.py:211-224) as one op:
+         a0 (= relu(block input); the producer's epilogue applied the in-place ReLU) ->
+         h1 = relu(conv1x1(a0) + b1)  and  px = avgpool2(a0) | a0   (the skip source)
+       px is written into the first channels of the concat-skip buffer (cfg['skip_channels'] wide) when the block has a
+       learnable shortcut, so the concatenation of :225-226 needs no copy.
+       backward: ONE dgrad launch forms  dx = [a0 > 0] * (dgrad1(dh1) + 0.25 * up2(dpx))  (or ... + dpx without pooling):
+       the average-pool backward and both ReLU masks live in the conv epilogue (residual, res_up2, res_scale, mask), and
+       its column sums are the bias gradient of the layer that produced a0."""
+
+    @staticmethod
+    def forward(ctx, a0, weight, bias, cfg):
+        B, Cin, H, W, _ = K.geom(a0)
+        hid = weight.shape[0]
+        wf, wd, sigma, us, vs = _sn_packs(weight, cfg, hid, Cin, 1, True)
+        h1 = K.conv_fprop(a0, wf, hid, 1, 1, 0, 0, bias=bias, relu=True)
+        down = cfg["downsample"]
+        if down:
+            sc = cfg.get("skip_channels", 0) or Cin
+            buf = K.empty_nhwc(B, sc, H // 2, W // 2, a0.device)
+            px = buf[:, :Cin] if sc != Cin else buf
+            K.pool2_fwd(a0, 0, out=px)
+            if sc != Cin:
+                px._sgb_concat_buf = buf
+        else:
+            px = a0.view_as(a0)
+        ctx.cfg = cfg
+        ctx.dims = (hid, Cin, 1)
+        ctx.save_for_backward(a0, weight, wd, sigma, us, vs)
+        return h1, px
+
+    @staticmethod
+    def backward(ctx, dh1, dpx):
+        a0, weight, wd, sigma, us, vs = ctx.saved_tensors
+        cfg = ctx.cfg
+        hid, Cin, _ = ctx.dims
+        dz = K.as_nhwc(dh1)                       # premasked by conv2d2's dgrad epilogue
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            down = cfg["downsample"]
+            dx = K.conv_fprop(dz, wd, Cin, 1, 1, 0, 0, mask=a0, residual=K.as_nhwc(dpx) if dpx is not None else None,
+                              res_up2=down, res_scale=0.25 if down else 1.0, stats=0 if SKIP_PARAM_GRADS else 1)
+        if not SKIP_PARAM_GRADS:
+            dW, db = conv_param_grads(a0, dz, weight, ctx.needs_input_grad[1], ctx.needs_input_grad[2], 1, 1, 0, ctx.dims,
+                                      sigma, us, vs)
+        return dx, dW, db, None
+
+
 class ConcatSkipFn(TFunction):
     """skip = cat([px, conv1x1(px)], channel) written into one buffer (learnable shortcut of the BigGAN-Deep D block,
     src/models/big_resnet_deep_legacy.py:225-226)."""
@@ -496,8 +590,10 @@ class ConcatSkipFn(TFunction):
                 sigma = torch.empty(1, device=weight.device, dtype=torch.float32)
                 K.sn_power_iter(weight, u, v, sigma, ws, sn.eps, cfg.get("do_power_iteration", True))
             wf, wd = K.weight_pack(weight, sigma, Cextra, Cin, 1, True, need_dx)
-        skip = K.empty_nhwc(B, Cin + Cextra, H, W, px.device)
-        K.axpby(px, out=skip[:, :Cin])
+        skip = getattr(px, "_sgb_concat_buf", None)       # DEntryConvFn pooled straight into the concat buffer
+        if skip is None or skip.shape[1] != Cin + Cextra:
+            skip = K.empty_nhwc(B, Cin + Cextra, H, W, px.device)
+            K.axpby(px, out=skip[:, :Cin])
         K.conv_fprop(skip[:, :Cin], wf, Cextra, 1, 1, 0, 0, bias=bias, out=skip[:, Cin:])
         if ctx.needs_input_grad[1] and sn is not None and cache is None:
             u_saved, v_saved = u.clone(), v.clone()
@@ -515,11 +611,9 @@ class ConcatSkipFn(TFunction):
         dpx = dW = dbias = None
         if ctx.needs_input_grad[0]:
             dpx = K.conv_fprop(d_hi, wd, Cin, 1, 1, 0, 0, residual=d_lo)
-        if ctx.needs_input_grad[1] and not SKIP_PARAM_GRADS:
-            G = K.conv_wgrad(px, d_hi, 1, 1, 0, 0)
-            dW = K.sn_backward(G, weight, u_saved, v_saved, sigma, Cextra, Cin, 1)
-        if ctx.needs_input_grad[2]:
-            dbias = K.bn_stats(d_hi)[0]
+        if not SKIP_PARAM_GRADS:
+            dW, dbias = conv_param_grads(px, d_hi, weight, ctx.needs_input_grad[1], ctx.needs_input_grad[2], 1, 1, 0,
+                                         (Cextra, Cin, 1), sigma, u_saved, v_saved)
         return dpx, dW, dbias, None
 
     @staticmethod

@@ -56,7 +56,7 @@ def _s():
 # ---------------------------------------------------------------------------------------------- conv engine
 def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_up2=False, res_after_mask=False,
                mask=None, relu=False, alpha=1.0, alpha_ptr=None, out=None, out_fp32=False, w_mode=0, same_size=True, stride=1,
-               stats=0):
+               stats=0, res_scale=1.0):
     """y = epilogue(conv(x, w)); see sgb_conv_fprop. ``w`` is a packed bf16 weight (layout by w_mode).
     same_size=False: output grid = Hin + 2*pad - K + 1 ("valid"-style); stride=2 stores its even positions only.
     stats: 1 = the epilogue also accumulates the per-channel sum of the stored output, 2 = sum and sum of squares; the
@@ -82,6 +82,7 @@ def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_u
     if residual is not None:
         d.residual, d.res_cstride = residual.data_ptr(), geom(residual)[4]
     d.res_up2 = 1 if res_up2 else 0
+    d.res_scale = float(res_scale)
     d.res_after_mask = 1 if res_after_mask else 0
     if mask is not None:
         d.mask, d.mask_cstride = mask.data_ptr(), geom(mask)[4]
@@ -101,7 +102,12 @@ def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_u
 
 
 COLSTATS_HITS = [0, 0]   # [found, fell back to a reduction pass] (diagnostics)
-COLSTATS = True      # epilogue column statistics (tests switch this off to compare against the stand-alone reductions)
+# Epilogue column statistics are OFF by default: measured on B200 (profiles/r02_colstats_cuda_core_epilogue.md) the
+# CUDA-core butterfly reduction roughly doubles the epilogue's instruction count, and the epilogue is the critical path of
+# every memory-bound layer: bn_stats fell 35 -> 15 ms per step but conv_fprop rose 363 -> 663 ms.  The path stays
+# available (and tested) for layers that are tensor-bound with a short epilogue; bias gradients come from the
+# weight-gradient kernels instead (constant-ones operand atom).
+COLSTATS = False
 
 
 def colstats(x, rows):

@@ -151,7 +151,34 @@ class DiscBlock(nn.Module):
         if self.downsample:
             self.average_pooling = nn.AvgPool2d(2)
 
-    def forward(self, x):
+    def forward(self, x, in_relu=False, out_relu=False):
+        """in_relu: ``x`` already is relu(block input) -- the producing layer applied the reference's in-place ReLU
+        (src/config.py:486) in its epilogue; out_relu: do the same for the next block / the head.  The gradient contract of
+        such a tensor is "premasked": whoever consumes it returns a gradient that is already zero where it is zero."""
+        if A.TAPE is not None:
+            return self._forward_taped(x, in_relu, out_relu)
+        a0 = x if in_relu else A.ReluPassFn.call(x)
+        c1 = self.conv2d1
+        h, px = A.DEntryConvFn.call(a0, ops._w(c1), c1.bias,
+                                    {"downsample": self.downsample, "sn": getattr(c1, "_sn", None), "do_power_iteration": c1.training,
+                                     "sn_cache": getattr(c1, "_sn_cache", None),
+                                     "skip_channels": self.conv2d4.out_channels if self.learnable_sc else 0})
+        h = self.conv2d2(h, relu=True, premasked=True, mask_input=True)
+        h = self.conv2d3(h, relu=True, premasked=True, mask_input=True)
+        if self.downsample:
+            h = A.AvgPoolFn.call(h, True)
+        skip = px
+        if self.learnable_sc:
+            c0 = self.conv2d0
+            skip = A.ConcatSkipFn.call(px, ops._w(c0), c0.bias,
+                                        {"sn": getattr(c0, "_sn", None), "do_power_iteration": c0.training,
+                                         "sn_cache": getattr(c0, "_sn_cache", None)})
+        return self.conv2d4(h, residual=skip, mask_input=not self.downsample, relu=out_relu, premasked=out_relu)
+
+    def _forward_taped(self, x, in_relu, out_relu):
+        """Op-by-op form recorded on the tangent tape (gradient penalty, utils/gp.py)."""
+        if in_relu or out_relu:
+            raise NotImplementedError("fused ReLU hand-over between blocks under the tangent tape")
         a0, px = A.DBlockEntryFn.call(x, self.downsample)
         h = self.conv2d1(a0, relu=True, premasked=True, mask_input=True)
         h = self.conv2d2(h, relu=True, premasked=True, mask_input=True)
@@ -236,10 +263,20 @@ class Discriminator(nn.Module):
 
     def forward(self, x, label, eval=False, adc_fake=False):
         self._snb.run()
-        h = self.input_conv(A.ImageColFn.call(x))                   # 3x3 patches of the image -> K = 32 GEMM
-        for blocklist in self.blocks:
-            for block in blocklist:
+        seq = [b for bl in self.blocks for b in bl]
+        fuse = A.TAPE is None              # ReLU hand-over between consecutive blocks through the conv epilogues
+        first_relu = fuse and isinstance(seq[0], DiscBlock)
+        h = self.input_conv(A.ImageColFn.call(x), relu=first_relu, premasked=first_relu)   # 3x3 patches of the image -> K = 32 GEMM
+        relu_in = first_relu
+        for i, block in enumerate(seq):
+            if isinstance(block, DiscBlock):
+                nxt = seq[i + 1] if i + 1 < len(seq) else None
+                relu_out = fuse and (nxt is None or isinstance(nxt, DiscBlock))   # the head starts with the same ReLU (:344)
+                h = block(h, in_relu=relu_in, out_relu=relu_out)
+                relu_in = relu_out
+            else:
                 h = block(h)
+                relu_in = False
         h = A.SumHWFn.call(h, True)                                  # relu + sum over (H, W), fp32 [B, C]
         self._snb.clear()
         return ops.discriminator_head(self, h, label, adc_fake)

@@ -114,6 +114,13 @@ def apply_standing_statistics(generator, standing_max_batch, standing_step, DATA
             per_gpu = max(1, standing_max_batch // world)
             if RUN.distributed_data_parallel:
                 rand_batch_size = random.randint(1, per_gpu)
+                # sync-BN divides the all-reduced sums by (local count x world size): every rank must draw the SAME size.
+                # (torch's SyncBatchNorm exchanges per-rank counts; here rank 0's draw is broadcast instead.)
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                    t = torch.tensor([rand_batch_size], device=device if dist.get_backend() == "nccl" else "cpu")
+                    dist.broadcast(t, src=0)
+                    rand_batch_size = int(t.item())
             else:
                 rand_batch_size = random.randint(1, per_gpu) * world
             sample.generate_images(z_prior=MODEL.z_prior, truncation_factor=-1, batch_size=rand_batch_size, z_dim=MODEL.z_dim,

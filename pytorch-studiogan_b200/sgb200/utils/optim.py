@@ -2,8 +2,9 @@
 
 Arithmetic is torch.optim.Adam's (the reference's optimiser, src/config.py:541-563: eps 1e-6, no amsgrad, weight decay
 0 on every BASELINE config): m <- b1 m + (1-b1) g, v <- b2 v + (1-b2) g^2, p <- p - lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t)
-+ eps).  A parameter that received no gradient in a step keeps a zero gradient here (torch skips it); with zero moments
-that is the same no-op (frozen discriminator blocks), and on the hot path every parameter receives a gradient each step.
++ eps).  torch skips a parameter whose ``.grad`` is None: here the parameters that are frozen at step time
+(``requires_grad`` False -- ``misc.toggle_grad(..., freezeD)``, src/utils/misc.py:192-216) are left out of the update,
+moments included, by launching over the contiguous arena ranges of the trainable ones (one range on the hot path).
 
 ``state_dict`` / ``load_state_dict`` speak torch.optim.Adam's format, so reference checkpoints of the optimiser state
 load and save unchanged."""
@@ -74,9 +75,27 @@ class ArenaAdam(object):
         self.grads.attach()
         self.step_t.add_(1)
         g = self.param_groups[0]
-        K.adam_ema_step(self.arena.flat, self.grads.flat, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1],
-                        g["eps"], 0, grad_scale=self.grad_scale, step_dev=self.step_t)
+        for lo, hi in self._trainable_ranges():
+            K.adam_ema_step(self.arena.flat[lo:hi], self.grads.flat[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], g["lr"],
+                            g["betas"][0], g["betas"][1], g["eps"], 0, grad_scale=self.grad_scale, step_dev=self.step_t)
         self.grad_scale = 1.0
+
+    def _trainable_ranges(self):
+        """Contiguous [lo, hi) element ranges of the arena that hold parameters with requires_grad set."""
+        key = tuple(p.requires_grad for p in self.arena.params)
+        if getattr(self, "_ranges_key", None) != key:
+            ranges, cur = [], None
+            for o, p in self._offsets():
+                end = o + (p.numel() + 63) // 64 * 64
+                if p.requires_grad:
+                    cur = [o, end] if cur is None else [cur[0], end]
+                elif cur is not None:
+                    ranges.append(tuple(cur))
+                    cur = None
+            if cur is not None:
+                ranges.append(tuple(cur))
+            self._ranges_key, self._ranges = key, ranges
+        return self._ranges
 
     # ---------------------------------------------------------------------------------------- torch.optim.Adam format
     def _offsets(self):

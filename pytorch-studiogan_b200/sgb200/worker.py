@@ -88,9 +88,14 @@ class WORKER(object):
         if self.MODEL.aux_cls_type not in ("W/O", "N/A", "TAC", "ADC"):
             raise NotImplementedError("aux_cls_type %s" % self.MODEL.aux_cls_type)
         for flag in ("apply_cr", "apply_bcr", "apply_zcr", "apply_lo", "apply_topk", "apply_lecam", "apply_r1_reg",
-                     "apply_dra", "apply_maxgp", "apply_fm", "apply_wc"):
+                     "apply_dra", "apply_maxgp", "apply_fm", "apply_wc", "apply_inv_reg"):
             if getattr(self.LOSS, flag, False):
                 raise NotImplementedError("LOSS.%s is outside the sgb200 hot-path scope" % flag)
+        # a YAML that asks for an augmentation this path does not implement must not silently train a different recipe
+        AUG = getattr(cfgs, "AUG", None)
+        for flag in ("apply_diffaug", "apply_ada", "apply_apa"):
+            if AUG is not None and getattr(AUG, flag, False):
+                raise NotImplementedError("AUG.%s is outside the sgb200 hot-path scope" % flag)
 
     # ------------------------------------------------------------------------------------------------ data
     def sample_data_basket_raw(self):
@@ -233,15 +238,21 @@ def _evaluate(self, step, metrics, writing=True, training=False):
     with torch.no_grad():
         misc.make_GAN_untrainable(self.Gen, self.Gen_ema, self.Dis)
         generator = self.Gen_ema if (self.MODEL.apply_g_ema and self.Gen_ema is not None) else self.Gen
+        # GeneratorController.prepare_generator (src/utils/misc.py:77-106), in place like the reference: the standing
+        # statistics are accumulated ONCE per run (std_stat_counter, src/worker.py:809-810), the generator is then put in
+        # eval mode with conv / linear / embedding back in train mode (the spectral-norm iteration keeps running).
         if getattr(self.RUN, "standing_statistics", False):
-            # GeneratorController.prepare_generator (src/utils/misc.py:63-106): a copy of the generator whose BatchNorm
-            # statistics are re-accumulated over `standing_step` random-size batches
-            import copy
-            generator = copy.deepcopy(generator)
-            misc.apply_standing_statistics(generator=generator, standing_max_batch=self.RUN.standing_max_batch,
-                                           standing_step=self.RUN.standing_step, DATA=self.DATA, MODEL=self.MODEL, LOSS=self.LOSS,
-                                           OPTIMIZATION=self.OPTIMIZATION, RUN=self.RUN, device=self.local_rank,
-                                           global_rank=self.global_rank, logger=self.logger)
+            self.std_stat_counter = getattr(self, "std_stat_counter", 0) + 1
+            if self.std_stat_counter <= 1:
+                misc.apply_standing_statistics(generator=generator, standing_max_batch=self.RUN.standing_max_batch,
+                                               standing_step=self.RUN.standing_step, DATA=self.DATA, MODEL=self.MODEL, LOSS=self.LOSS,
+                                               OPTIMIZATION=self.OPTIMIZATION, RUN=self.RUN, device=self.local_rank,
+                                               global_rank=self.global_rank, logger=self.logger)
+            generator.eval()
+            generator.apply(misc.set_deterministic_op_trainable)
+        elif getattr(self.RUN, "batch_statistics", False):
+            generator.apply(misc.set_bn_trainable)
+            generator.apply(misc.untrack_bn_statistics)
         fake_feats, fake_probs, fake_labels = features.generate_images_and_stack_features(
             generator=generator, discriminator=self.Dis, eval_model=self.eval_model, num_generate=num_eval,
             y_sampler="totally_random", batch_size=self.OPTIMIZATION.batch_size, z_prior=self.MODEL.z_prior,

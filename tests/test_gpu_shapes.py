@@ -81,6 +81,7 @@ def test_conv_epilogue_column_statistics(B, H, W, Cin, Cout, k, extra):
     from sgb200 import kernels as K
     dev = _cuda()
     torch.manual_seed(11)
+    K.COLSTATS = True                     # opt-in path (off by default, see kernels.COLSTATS)
     x = K.empty_nhwc(B, Cin, H, W, dev).normal_()
     w = torch.randn(Cout, Cin, k, k, device=dev) / np.sqrt(Cin * k * k)
     wf, _ = K.weight_pack(w, None, Cout, Cin, k * k, True, False)
@@ -95,7 +96,9 @@ def test_conv_epilogue_column_statistics(B, H, W, Cin, Cout, k, extra):
     l2 = (y.float() ** 2).sum((0, 2, 3)) + 1e-3
     assert float(((cs[0] - ref[0]).abs() / l1).max()) < 2e-5
     assert float(((cs[1] - ref[1]).abs() / l2).max()) < 2e-5
-    y2 = K.conv_fprop(x, wf, Cout, k, k, k // 2, k // 2, bias=bias, residual=res, mask=mask, relu=(extra == "relu"))
+    K.COLSTATS = False
+    y2 = K.conv_fprop(x, wf, Cout, k, k, k // 2, k // 2, bias=bias, residual=res, mask=mask, relu=(extra == "relu"), stats=2)
+    assert K.colstats(y2, 2) is None
     assert torch.equal(y, y2)             # the statistics path stores exactly what the plain epilogue stores
 
 
@@ -163,9 +166,7 @@ def test_biggan_deep_256_d_and_g_phase_vs_reference_golden(golden_dir):
     z, yf, real, yr = z.to(dev), yf.to(dev), real.to(dev), yr.to(dev)
     for p in G.parameters():
         p.requires_grad_(False)
-    K.COLSTATS_HITS[0] = K.COLSTATS_HITS[1] = 0
     fake = G(z, yf)
-    assert K.COLSTATS_HITS[0] >= 40, K.COLSTATS_HITS     # the generator's batch norms take their statistics from conv epilogues
     assert fake.shape == (4, 3, 256, 256)
     assert l2_err(fake[:, :, ::8, ::8], torch.from_numpy(g["fake_sub8"])) < 4e-2
     real_d, fake_d = D(real, yr), D(fake.detach(), yf)
