@@ -32,9 +32,15 @@ import torch.distributed as dist  # noqa: E402
 # conv + linear + attention-bmm FLOPs per image (2 x MAC), BASELINE.md section 3 / SURVEY.md 8(d)
 # WGAN-GP-128res (G 18.2 / D 9.4 GF per image forward): 5 D updates x (G fwd + 2 D fwd + 2 D bwd + penalty ~ 7 D fwd)
 # + 1 G update (G fwd + D fwd + D dgrad + G bwd) ~ 775 GF per batch image per step
-STEP_GFLOP_PER_IMAGE = {"BigGAN-Deep-256res": 1141.0, "WGAN-GP-128res": 775.0}
+# SNGAN / BigGAN CIFAR10: 44.3 / 101.1 GF per batch image per step (5 D updates + 1 G update)
+STEP_GFLOP_PER_IMAGE = {"BigGAN-Deep-256res": 1141.0, "WGAN-GP-128res": 775.0, "SNGAN-CIFAR10-b256": 44.3, "BigGAN-CIFAR10-b512": 101.1}
 METRIC_NAME = {"BigGAN-Deep-256res": "BigGAN-Deep 256x256 G+D step images/sec",
-               "WGAN-GP-128res": "WGAN-GP ResNetGAN 128x128 G+D step images/sec (5 D updates with gradient penalty + 1 G update)"}
+               "WGAN-GP-128res": "WGAN-GP ResNetGAN 128x128 G+D step images/sec (5 D updates with gradient penalty + 1 G update)",
+               "SNGAN-CIFAR10-b256": "SNGAN CIFAR10 32x32 G+D step images/sec (5 D updates + 1 G update)",
+               "BigGAN-CIFAR10-b512": "BigGAN CIFAR10 32x32 G+D step images/sec (5 D updates + 1 G update + EMA, sync-BN when N > 1)"}
+# BASELINE.json configs 2 / 3 / 5, measured after the headline config and reported under config.also_measured:
+# (yaml, the world sizes it is run at)
+ALSO = [("SNGAN-CIFAR10-b256", (1,)), ("BigGAN-CIFAR10-b512", (1, 2, 4)), ("WGAN-GP-128res", (1, 2))]
 G_FWD_GF, D_FWD_GF = 58.80, 60.50
 
 
@@ -50,7 +56,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--graphs", default="auto", choices=["auto", "on", "off"],
                     help="capture each training phase in a CUDA graph; auto = on when the per-GPU batch is <= 64 (launch-bound regime)")
-    ap.add_argument("--no-fid", action="store_true", help="skip the FID-50k evaluation timing (N = 1 only)")
+    ap.add_argument("--no-fid", action="store_true", help="skip the FID-50k evaluation timing")
+    ap.add_argument("--no-also", action="store_true", help="skip BASELINE configs 2 / 3 / 5 (config.also_measured)")
     ap.add_argument("--fid-num", type=int, default=50000)
     ap.add_argument("--cpu-batch", type=int, default=4, help="images per CPU-baseline step (4 -> ~15 s of CPU work on 32 threads)")
     ap.add_argument("--cpu-threads", type=int, default=0, help="0 = min(32, host cores): more threads only add contention for these layer sizes")
@@ -122,18 +129,19 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_worker(args, rank, world, device):
+def build_worker(args, rank, world, device, config_path=None):
     from sgb200 import config as C
     from sgb200.models import model as M
     from sgb200.utils import misc
     from sgb200.worker import WORKER
-    cfgs = C.Configurations(args.config)
-    if args.batch:
+    cfgs = C.Configurations(config_path or args.config)
+    if args.batch and config_path is None:
         cfgs.OPTIMIZATION.batch_size = args.batch
     global_batch = cfgs.OPTIMIZATION.batch_size
     assert global_batch % world == 0
     cfgs.OPTIMIZATION.batch_size = global_batch // world           # per-rank batch, as src/loader.py:162
     cfgs.RUN.cuda_graphs = args.graphs == "on" or (args.graphs == "auto" and cfgs.OPTIMIZATION.batch_size <= 64)
+    cfgs.OPTIMIZATION.world_size = world
     cfgs.RUN.distributed_data_parallel = world > 1
     cfgs.RUN.synchronized_bn = world > 1
     misc.fix_seed(0 + rank)                                         # seed + rank (src/loader.py:99)
@@ -176,7 +184,7 @@ def timed(worker, steps, world, read_losses):
     return float(ms) / steps, losses
 
 
-def fid_eval_seconds(worker, cfgs, device, num_eval, batch):
+def fid_eval_seconds(worker, cfgs, device, num_eval, batch, world=1):
     """BASELINE metric, second half: wall seconds of one FID-N evaluation (WORKER.evaluate: N generated images through
     G_ema -> quantise/resize/normalise -> InceptionV3 -> IS + FID), preceded by the reference-statistics pass over N
     synthetic uint8-valued reference images.  Inception weights are seeded (the pretrained file cannot be downloaded
@@ -188,12 +196,24 @@ def fid_eval_seconds(worker, cfgs, device, num_eval, batch):
     S = cfgs.DATA.img_size
 
     def ref_batches():
-        for i in range(0, num_eval, batch):
-            n = min(batch, num_eval - i)
-            yield torch.randint(0, 256, (n, 3, S, S), generator=gen, device=device).float()
+        for i in range(0, num_eval, batch * world):          # N > 1: each rank extracts its share, features are all-gathered
+            n = min(batch, max(0, num_eval - i - batch * (dist.get_rank() if world > 1 else 0)))
+            if n > 0:
+                yield torch.randint(0, 256, (n, 3, S, S), generator=gen, device=device).float()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     rf, _ = features.stack_real_features(ref_batches(), ev, False, device)
+    if world > 1:
+        sizes = [torch.zeros(1, dtype=torch.long, device=device) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([rf.shape[0]], device=device))
+        mx = int(max(int(s) for s in sizes))
+        pad = torch.zeros((mx, rf.shape[1]), device=device, dtype=rf.dtype)
+        pad[:rf.shape[0]] = rf
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        rf = torch.cat([p[:int(n)] for p, n in zip(parts, sizes)], 0)
     mu, sigma = fid.calculate_moments(rf)
     torch.cuda.synchronize()
     t_ref = time.perf_counter() - t0
@@ -201,15 +221,19 @@ def fid_eval_seconds(worker, cfgs, device, num_eval, batch):
     bs = cfgs.OPTIMIZATION.batch_size
     cfgs.OPTIMIZATION.batch_size = batch
     try:
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         worker.evaluate(step=0, metrics=["is", "fid"], writing=False, training=True)
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t_eval = time.perf_counter() - t0
     finally:
         cfgs.OPTIMIZATION.batch_size = bs
     m = worker.last_metrics or {}
     return {"seconds": t_eval, "ref_stats_seconds": t_ref, "num_eval": num_eval, "batch": batch, "img_per_s": num_eval / t_eval,
-            "FID": m.get("FID"), "IS": m.get("IS"), "inception_weights": "seeded (pretrained FID weights unavailable offline)"}
+            "FID": m.get("FID"), "IS": m.get("IS"), "n_gpus": world, "inception_weights": "seeded (pretrained FID weights unavailable offline)"}
 
 
 def cpu_step_images_per_sec(config_path, batch, threads, n_steps=1):
@@ -235,8 +259,9 @@ def cpu_step_images_per_sec(config_path, batch, threads, n_steps=1):
     optG = torch.optim.Adam([sdG[k].requires_grad_(True) for k in pG], lr=cfgs.OPTIMIZATION.g_lr, betas=(cfgs.OPTIMIZATION.beta1, cfgs.OPTIMIZATION.beta2), eps=1e-6)
     optD = torch.optim.Adam([sdD[k].requires_grad_(True) for k in pD], lr=cfgs.OPTIMIZATION.d_lr, betas=(cfgs.OPTIMIZATION.beta1, cfgs.OPTIMIZATION.beta2), eps=1e-6)
     S, nc = cfgs.DATA.img_size, cfgs.DATA.num_classes
-    t0 = time.perf_counter()
-    for _ in range(n_steps):
+    samples = []
+    for it in range(n_steps + 1):           # iteration 0 warms the allocator / thread pool / oneDNN primitive caches, untimed
+        t0 = time.perf_counter()
         for _ in range(cfgs.OPTIMIZATION.d_updates_per_step):
             optD.zero_grad()
             real, yr = torch.rand(batch, 3, S, S) * 2 - 1, torch.randint(0, nc, (batch,))
@@ -255,8 +280,10 @@ def cpu_step_images_per_sec(config_path, batch, threads, n_steps=1):
         a, _ = O.deep_discriminator({k: v.detach() for k, v in sdD.items()}, fake, yf, **kw_d)
         O.g_hinge(a).backward()
         optG.step()
-    dt = time.perf_counter() - t0
-    return batch * n_steps / dt, dt
+        if it > 0:
+            samples.append(time.perf_counter() - t0)
+    dt = float(np.sum(samples))
+    return batch * len(samples) / dt, dt, [batch / t for t in samples]
 
 
 def _no_ema(MODEL):
@@ -277,9 +304,10 @@ def shutdown(worker, world):
         time.sleep(20.0)
         os._exit(0)
     threading.Thread(target=_hard_exit, daemon=True).start()
-    for name in ("_d_graph", "_g_graph"):
-        if getattr(worker, name, None) is not None:
-            setattr(worker, name, None)
+    if worker is not None:
+        for name in ("_d_graph", "_g_graph"):
+            if getattr(worker, name, None) is not None:
+                setattr(worker, name, None)
     import gc
     gc.collect()
     torch.cuda.synchronize()
@@ -289,6 +317,125 @@ def shutdown(worker, world):
     except Exception:
         pass
     os._exit(0)
+
+
+def config_dict(workload, cfgs_or_none, global_batch, world, graphs, S, d_updates, acml):
+    per_rank = global_batch // world
+    return {"workload": workload, "global_batch": global_batch, "per_gpu_batch": per_rank, "img_size": S,
+            "d_updates_per_step": d_updates, "acml_steps": acml, "parallelism": "dp%d" % world, "cuda_graphs": bool(graphs),
+            "l2": "per-step working set (tens of GB of activations) >> 126 MB L2; no explicit flush needed"}
+
+
+def graphs_wanted(args, per_rank):
+    return args.graphs == "on" or (args.graphs == "auto" and per_rank <= 64)
+
+
+def reference_arm(args, workload):
+    """The reference step on the host cores (oracle port: /root/reference does not travel to the GPU box), on OUR arm's
+    config / metric / unit: each step is a bounded sample of the workload -- ``cpu_batch`` images of the 256-image batch
+    through the full step (2 D updates + 1 G update, forward + backward + Adam) -- W warm-up steps, K timed steps."""
+    import yaml
+    from sgb200 import config as C
+    cfgs = C.Configurations(args.config)
+    threads = args.cpu_threads or min(32, os.cpu_count() or 1)
+    global_batch = args.batch or cfgs.OPTIMIZATION.batch_size
+    K, W = max(1, args.steps), max(1, args.warmup)
+    # size the per-step sample so that W + K steps end within ~4 minutes: one probe step at the requested sample size
+    batch = args.cpu_batch
+    _, t_probe, _ = cpu_step_images_per_sec(args.config, batch, threads, n_steps=1)
+    while batch > 1 and t_probe * (batch / args.cpu_batch) * (K + W) > 240.0:
+        batch //= 2
+    v, dt, per = cpu_step_images_per_sec(args.config, batch, threads, n_steps=K + W - 1)   # its iteration 0 is warm-up 1 of W
+    per = per[W - 1:]
+    v = float(len(per) / sum(1.0 / x for x in per))            # images / total seconds of the K timed steps
+    cfg = config_dict(workload, cfgs, global_batch, args.gpus, graphs_wanted(args, global_batch // args.gpus), cfgs.DATA.img_size,
+                      cfgs.OPTIMIZATION.d_updates_per_step, cfgs.OPTIMIZATION.acml_steps)
+    sample = ("%d of the %d images of each step (full step: 2 D updates + 1 G update, fwd + bwd + Adam) on %d host threads; %d warm-up + "
+              "%d timed steps; per-step img/s min %.3f max %.3f" % (batch, global_batch, threads, W, len(per), min(per), max(per)))
+    return {"impl": "reference", "metric": METRIC_NAME.get(workload, workload), "value": v, "unit": "img/s", "n_gpus": args.gpus,
+            "steps": len(per), "warmup": W, "ms_per_step": 1000.0 * batch / v, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": v, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+
+def measure(args, rank, world, device, config_path, steps, warmup, want_e2e, want_profile):
+    """Warm-up + timed steps of one workload (device-resident baskets), optional per-kernel accounting step and e2e leg."""
+    from sgb200 import _lib
+    cfgs, worker, global_batch = build_worker(args, rank, world, device, config_path)
+    opt = cfgs.OPTIMIZATION
+    per_rank = opt.batch_size
+    n_items = opt.acml_steps * opt.d_updates_per_step
+    S = cfgs.DATA.img_size
+    dev_loader = SyntheticBasketLoader(per_rank, n_items, S, cfgs.DATA.num_classes, 100 + rank, device=device)
+    worker.train_dataloader, worker.train_iter = dev_loader, iter(dev_loader)
+    run_steps(worker, warmup, False)
+    sampler = ClockSampler(device.index)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.LAUNCHES[0]
+    ms_step, _ = timed(worker, steps, world, False)
+    launches = (_lib.LAUNCHES[0] - launches0)
+    sampler.stop_flag = True
+    res = {"cfgs": cfgs, "worker": worker, "global_batch": global_batch, "per_rank": per_rank, "S": S, "ms_step": ms_step,
+           "value": global_batch * opt.acml_steps / (ms_step * 1e-3), "launches": launches, "clocks": sampler.summary() if rank == 0 else None,
+           "graphs_captured": {n: bool(getattr(getattr(worker, n, None), "graph", None) is not None) for n in ("_d_graph", "_g_graph")},
+           "prof": None, "prof_by_tag": None, "e2e": None}
+    if want_profile:
+        try:
+            _lib.PROFILE["events"] = []
+            _lib.PROFILE["enabled"] = True
+            graphs_on, cfgs.RUN.cuda_graphs = cfgs.RUN.cuda_graphs, False      # the accounting step runs eagerly (events per call)
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            run_steps(worker, 1, False)
+            torch.cuda.synchronize()
+            prof_wall_ms = (time.perf_counter() - w0) * 1e3
+            _lib.PROFILE["enabled"] = False
+            cfgs.RUN.cuda_graphs = graphs_on
+            agg, by_tag = {}, {}
+            for tag, flops, e0, e1, nbytes in _lib.PROFILE["events"]:
+                ms = e0.elapsed_time(e1)
+                for key, store in ((tag.split(" ")[0], agg), (tag, by_tag)):
+                    a = store.setdefault(key, [0.0, 0.0, 0, 0.0])
+                    a[0] += ms; a[1] += flops; a[2] += 1; a[3] += nbytes
+            _lib.PROFILE["events"] = []
+            res["prof"] = {k: {"ms": v[0], "tflops": (v[1] / (v[0] * 1e-3) * 1e-12) if v[0] > 0 and v[1] > 0 else None, "launches": v[2],
+                               "flop": v[1], "gbytes": v[3] * 1e-9, "gb_per_s": (v[3] / (v[0] * 1e-3) * 1e-9) if v[0] > 0 and v[3] > 0 else None}
+                           for k, v in agg.items()}
+            res["prof_by_tag"] = by_tag
+            if rank == 0:
+                os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+                with open(os.path.join(ROOT, "gpurun_out", "kernel_breakdown_n%d_b%d.json" % (world, global_batch)), "w") as fh:
+                    json.dump({"wall_ms_of_profiled_step": prof_wall_ms, "sum_ms": sum(v[0] for v in agg.values()), "by_kind": res["prof"],
+                               "by_tag": [{"tag": k, "ms": v[0], "n": v[2], "flop": v[1], "bytes": v[3]} for k, v in
+                                          sorted(by_tag.items(), key=lambda kv: -kv[1][0])]}, fh, indent=1)
+        except Exception as ex:  # accounting must never take the bench line down
+            _lib.PROFILE["enabled"] = False
+            res["prof"] = {"error": repr(ex)}
+    if want_e2e:
+        host_loader = SyntheticBasketLoader(per_rank, n_items, S, cfgs.DATA.num_classes, 200 + rank, device=None)
+        worker.train_dataloader, worker.train_iter = host_loader, iter(host_loader)
+        run_steps(worker, 1, True)
+        ms_e2e, _ = timed(worker, steps, world, True)
+        res["e2e"] = {"value": global_batch * opt.acml_steps / (ms_e2e * 1e-3), "unit": "img/s",
+                      "h2d_bytes_per_step": world * per_rank * n_items * (3 * S * S * 4 + 8), "d2h_bytes_per_step": 8 * world,
+                      "ms_per_step": ms_e2e}
+    return res
+
+
+def release(res):
+    """Drop a measured workload (graphs first: they pin their memory pools) so the next one starts from an empty allocator."""
+    w = res.pop("worker", None)
+    if w is not None:
+        for name in ("_d_graph", "_g_graph"):
+            if getattr(w, name, None) is not None:
+                setattr(w, name, None)
+    res.pop("cfgs", None)
+    del w
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
 
 
 def main():
@@ -301,26 +448,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        threads = args.cpu_threads or min(32, os.cpu_count() or 1)
-        # up to K timed measurements of one full CPU step each (the model is rebuilt per measurement, only the step itself
-        # is inside the timed region); the loop stops early so that the whole run stays within ~4 minutes.
-        vals, t_used = [], 0.0
-        for i in range(max(1, args.steps)):
-            v, dt = cpu_step_images_per_sec(args.config, args.cpu_batch, threads)
-            vals.append(v)
-            t_used += dt
-            if t_used + dt > 240.0:
-                break
-        v = float(np.mean(vals))
-        line = {"impl": "reference", "metric": "BigGAN-Deep 256x256 G+D step images/sec", "value": v, "unit": "img/s",
-                "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": 1000.0 * args.cpu_batch / v,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "global_batch": args.cpu_batch, "img_size": 256, "d_updates_per_step": 2,
-                           "note": "CPU restatement (oracle port) of the reference step; /root/reference is not present on the GPU box"},
-                "cpu_baseline": {"value": v, "unit": "img/s", "cores": threads, "kind": "port",
-                                 "sample": "%d-image batch, one full step (2 D updates + 1 G update, fwd+bwd+Adam) per measurement" % args.cpu_batch},
-                "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(reference_arm(args, workload)))
         return
 
     torch.cuda.set_device(local_rank)
@@ -329,81 +457,49 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     from sgb200 import _lib
     _lib.check(_lib.load().sgb_device_check(), "sgb_device_check")
-    cfgs, worker, global_batch = build_worker(args, rank, world, device)
+    # N > 1: numeric check of the data-parallel path before anything is timed (N ranks x 4 images == 1 rank x 4N images:
+    # sync-BN forward / backward exchanges, arena gradient all-reduce, running statistics); reported in the JSON line
+    mr_check = None
+    if world > 1:
+        try:
+            from sgb200.utils.ddp_check import multirank_parity_check
+            mr_check = multirank_parity_check(device)
+        except Exception as ex:  # noqa: BLE001
+            mr_check = {"ok": False, "error": repr(ex)}
+
+    res = measure(args, rank, world, device, None, args.steps, args.warmup, not args.no_e2e, True)
+    cfgs, worker, global_batch, per_rank, S = res["cfgs"], res["worker"], res["global_batch"], res["per_rank"], res["S"]
     opt = cfgs.OPTIMIZATION
-    per_rank = opt.batch_size
-    n_items = opt.acml_steps * opt.d_updates_per_step
-    S = cfgs.DATA.img_size
-
-    # ---- device-resident leg (value)
-    dev_loader = SyntheticBasketLoader(per_rank, n_items, S, cfgs.DATA.num_classes, 100 + rank, device=device)
-    worker.train_dataloader, worker.train_iter = dev_loader, iter(dev_loader)
-    run_steps(worker, args.warmup, False)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = _lib.LAUNCHES[0]
-    ms_step, _ = timed(worker, args.steps, world, False)
-    launches = (_lib.LAUNCHES[0] - launches0)
-    sampler.stop_flag = True
-    value = global_batch * opt.acml_steps / (ms_step * 1e-3)
-
-    # ---- per-kernel accounting on one extra (untimed) step: CUDA events around every library call
-    prof, prof_top = None, None
-    try:
-        _lib.PROFILE["events"] = []
-        _lib.PROFILE["enabled"] = True
-        graphs_on, cfgs.RUN.cuda_graphs = cfgs.RUN.cuda_graphs, False      # the accounting step runs eagerly (events per call)
-        torch.cuda.synchronize()
-        w0 = time.perf_counter()
-        run_steps(worker, 1, False)
-        torch.cuda.synchronize()
-        prof_wall_ms = (time.perf_counter() - w0) * 1e3
-        _lib.PROFILE["enabled"] = False
-        cfgs.RUN.cuda_graphs = graphs_on
-        agg, by_tag = {}, {}
-        for tag, flops, e0, e1, nbytes in _lib.PROFILE["events"]:
-            ms = e0.elapsed_time(e1)
-            kind = tag.split(" ")[0]
-            a = agg.setdefault(kind, [0.0, 0.0, 0, 0.0])
-            a[0] += ms; a[1] += flops; a[2] += 1; a[3] += nbytes
-            t = by_tag.setdefault(tag, [0.0, 0.0, 0, 0.0])
-            t[0] += ms; t[1] += flops; t[2] += 1; t[3] += nbytes
-        _lib.PROFILE["events"] = []
-        prof = {k: {"ms": v[0], "tflops": (v[1] / (v[0] * 1e-3) * 1e-12) if v[0] > 0 and v[1] > 0 else None, "launches": v[2], "flop": v[1],
-                    "gbytes": v[3] * 1e-9, "gb_per_s": (v[3] / (v[0] * 1e-3) * 1e-9) if v[0] > 0 and v[3] > 0 else None}
-                for k, v in agg.items()}
-        prof_top = [{"tag": k, "ms": round(v[0], 3), "n": v[2], "tflops": round(v[1] / (v[0] * 1e-3) * 1e-12, 1) if v[1] > 0 else None}
-                    for k, v in sorted(by_tag.items(), key=lambda kv: -kv[1][0])[:40]]
-        if rank == 0:
-            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-            with open(os.path.join(ROOT, "gpurun_out", "kernel_breakdown_n%d_b%d.json" % (world, global_batch)), "w") as fh:
-                json.dump({"wall_ms_of_profiled_step": prof_wall_ms, "sum_ms": sum(v[0] for v in agg.values()),
-                           "by_kind": prof, "by_tag": [{"tag": k, "ms": v[0], "n": v[2], "flop": v[1], "bytes": v[3]} for k, v in
-                                                       sorted(by_tag.items(), key=lambda kv: -kv[1][0])]}, fh, indent=1)
-    except Exception as ex:  # accounting must never take the bench line down
-        prof = {"error": repr(ex)}
-
-    # ---- end-to-end leg: pinned host baskets, H2D inside the timed region, loss read back every step
-    e2e = None
-    if not args.no_e2e:
-        host_loader = SyntheticBasketLoader(per_rank, n_items, S, cfgs.DATA.num_classes, 200 + rank, device=None)
-        worker.train_dataloader, worker.train_iter = host_loader, iter(host_loader)
-        run_steps(worker, 1, True)
-        ms_e2e, _ = timed(worker, args.steps, world, True)
-        h2d = world * per_rank * n_items * (3 * S * S * 4 + 8)
-        e2e = {"value": global_batch * opt.acml_steps / (ms_e2e * 1e-3), "unit": "img/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e2e}
+    ms_step, value, prof = res["ms_step"], res["value"], res["prof"]
 
     fid50k = None
-    if not args.no_fid and world == 1:
+    if not args.no_fid:                       # every rank takes part (features are all-gathered when N > 1)
         try:
-            fid50k = fid_eval_seconds(worker, cfgs, device, args.fid_num, min(256, per_rank))
+            fid50k = fid_eval_seconds(worker, cfgs, device, args.fid_num, min(256, per_rank), world)
         except Exception as ex:  # the evaluation timing must never take the bench line down
             fid50k = {"error": repr(ex)}
+    release(res)
+
+    # ---- BASELINE configs 2 / 3 / 5 at the world sizes they are defined for (same timing rules, no accounting step)
+    also = {}
+    if not args.no_also and not args.batch:
+        for name, worlds in ALSO:
+            if world not in worlds or name == workload:
+                continue
+            try:
+                r = measure(args, rank, world, device, os.path.join(PKG, "configs", name + ".yaml"), max(3, min(args.steps, 10)), 3,
+                            True, False)
+                gf = STEP_GFLOP_PER_IMAGE.get(name, 0.0) * 1e9 * r["global_batch"]
+                also[name] = {"metric": METRIC_NAME[name], "value": r["value"], "unit": "img/s", "ms_per_step": r["ms_step"],
+                              "global_batch": r["global_batch"], "img_size": r["S"], "d_updates_per_step": r["cfgs"].OPTIMIZATION.d_updates_per_step,
+                              "e2e": r["e2e"], "gpu_launches": r["launches"], "cuda_graphs_captured": r["graphs_captured"],
+                              "step_tflops_per_gpu": gf / (r["ms_step"] * 1e-3) * 1e-12 / world}
+                release(r)
+            except Exception as ex:  # noqa: BLE001
+                also[name] = {"error": repr(ex)}
 
     if rank != 0:
-        shutdown(worker, world)
+        shutdown(None, world)
         return
 
     peaks = {}
@@ -414,19 +510,31 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained"
     step_flop = STEP_GFLOP_PER_IMAGE.get(workload, 0.0) * 1e9 * global_batch
-    # dram__bytes_read.sum + dram__bytes_write.sum of one captured launch (ncu --set full, profiles/r01_ncu_full_summary.txt):
-    # conv3x3_rows_kernel, 3x3 64->64 @256x256, B=32 -- 268.7 MB read + 221.4 MB written for 536.9 MB of algorithmic bytes
-    # (the tail of the output was still in L2 when the kernel ended): no re-reads.
-    roof = {"bound": "tensor", "unit": "TFLOP/s", "peak": peak_tf, "peak_source": peak_src, "traffic": 490.1e6,
-            "traffic_note": "bytes per launch of the captured conv3x3_rows_kernel launch (B=32 3x3 64->64 256^2; algorithmic 536.9e6)",
+    # roofline.traffic: DRAM bytes per launch of the dominant kernel from this round's committed `ncu --set full` capture
+    # (profiles/r02_ncu_traffic.json, written by profiles/summarize_ncu.py); null when no capture of the current kernel exists
+    traffic, traffic_note = None, "no ncu capture of the current kernel committed"
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+        traffic, traffic_note = t["dram_bytes_per_launch"], t["note"]
+    except Exception:
+        pass
+    roof = {"bound": "tensor", "unit": "TFLOP/s", "peak": peak_tf, "peak_source": peak_src, "traffic": traffic, "traffic_note": traffic_note,
             "step_algorithmic_tflop": step_flop * 1e-12,
             "step_achieved": step_flop / (ms_step * 1e-3) * 1e-12 / world,
             "step_frac": step_flop / (ms_step * 1e-3) * 1e-12 / world / peak_tf}
     if isinstance(prof, dict) and "conv_fprop" in prof:
         k = prof["conv_fprop"]
-        prof = {kk: vv for kk, vv in prof.items() if kk in ("conv_fprop", "conv_wgrad")}
-        roof.update({"kernel": "conv_fprop_kernel (fprop + dgrad, tcgen05)", "achieved": k["tflops"], "frac": k["tflops"] / peak_tf,
-                     "kernel_ms_per_step": k["ms"], "kernel_share_of_step": k["ms"] / ms_step, "kernels": prof})
+        hbm = peaks.get("hbm_gbs", 6500.0)
+        ew = {kk: vv for kk, vv in prof.items() if kk not in ("conv_fprop", "conv_wgrad") and vv.get("gbytes")}
+        ew_ms = sum(v["ms"] for v in ew.values())
+        ew_gb = sum(v["gbytes"] for v in ew.values())
+        roof.update({"kernel": "conv_fprop_kernel + conv3x3_rows_kernel (fprop + dgrad, tcgen05)", "achieved": k["tflops"], "frac": k["tflops"] / peak_tf,
+                     "kernel_ms_per_step": k["ms"], "kernel_share_of_step": k["ms"] / ms_step,
+                     "kernel_algorithmic_gbytes_per_step": k["gbytes"], "kernel_gb_per_s": k["gb_per_s"],
+                     "kernels": {kk: vv for kk, vv in prof.items() if kk in ("conv_fprop", "conv_wgrad")},
+                     "streaming_kernels": {"ms_per_step": ew_ms, "algorithmic_gbytes_per_step": ew_gb,
+                                           "gb_per_s": ew_gb / (ew_ms * 1e-3) if ew_ms > 0 else None, "hbm_peak_gb_per_s": hbm,
+                                           "frac_of_hbm_copy_peak": (ew_gb / (ew_ms * 1e-3) / hbm) if ew_ms > 0 else None}})
     else:
         roof.update({"achieved": roof["step_achieved"], "frac": roof["step_frac"], "kernels": prof})
 
@@ -434,22 +542,27 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         threads = args.cpu_threads or min(32, os.cpu_count() or 1)
         try:
-            v, dt = cpu_step_images_per_sec(args.config, args.cpu_batch, threads)
+            v, dt, per = cpu_step_images_per_sec(args.config, args.cpu_batch, threads, n_steps=3)
             cpu = {"value": v, "unit": "img/s", "cores": threads, "kind": "port",
-                   "sample": "%d-image batch, one full step (2 D updates + 1 G update, fwd+bwd+Adam), %.1f s" % (args.cpu_batch, dt)}
+                   "sample": "%d of the %d images of each step (2 D updates + 1 G update, fwd+bwd+Adam); 1 warm-up + 3 timed steps, %.1f s; "
+                             "per-step img/s min %.3f max %.3f" % (args.cpu_batch, global_batch, dt, min(per), max(per))}
         except Exception as ex:
             cpu = {"value": None, "unit": "img/s", "cores": threads, "kind": "port", "sample": "failed: %r" % (ex,)}
 
+    cfg = config_dict(workload, cfgs, global_batch, world, graphs_wanted(args, per_rank), S, opt.d_updates_per_step, opt.acml_steps)
+    cfg["cuda_graphs_captured"] = res["graphs_captured"]
+    cfg["also_measured"] = also
+    e2e = res["e2e"]
+    if e2e is not None and isinstance(fid50k, dict) and "seconds" in fid50k:
+        e2e["fid50k_eval_seconds"] = fid50k["seconds"]                 # second half of BASELINE's metric
+        e2e["fid50k_ref_stats_seconds"] = fid50k["ref_stats_seconds"]
     line = {"metric": METRIC_NAME.get(workload, workload + " G+D step images/sec"), "value": value, "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload, "global_batch": global_batch, "per_gpu_batch": per_rank, "img_size": S,
-                       "d_updates_per_step": opt.d_updates_per_step, "acml_steps": opt.acml_steps, "parallelism": "dp%d" % world, "cuda_graphs": bool(cfgs.RUN.cuda_graphs),
-                       "l2": "per-step working set (tens of GB of activations) >> 126 MB L2; no explicit flush needed"},
-            "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "fid50k": fid50k,
-            "clocks": sampler.summary()}
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
+            "e2e": e2e, "gpu_launches": res["launches"], "roofline": roof, "cpu_baseline": cpu, "fid50k": fid50k, "multirank_check": mr_check,
+            "clocks": res["clocks"]}
     print(json.dumps(line))
-    shutdown(worker, world)
+    shutdown(None, world)
 
 
 if __name__ == "__main__":

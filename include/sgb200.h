@@ -71,14 +71,6 @@ typedef struct sgb_conv_desc {
    * tensor, i.e. a stride-2 convolution computed on the stride-1 grid (four layers of the network). */
   int32_t Hin, Win;
   int32_t out_sub;
-  /* Optional per-channel column statistics of the STORED (bf16-rounded) output, accumulated by the epilogue
-   * (CTA-resident partial sums, one atomic flush per CTA) into caller-zeroed fp32 [Cout] vectors:
-   *   colsum[c] += sum_{b,h,w} y[b,h,w,c],  colsumsq[c] += sum y^2   (colsumsq may be NULL).
-   * They are BatchNorm's [sum x, sum x^2] of the next layer (src/utils/ops.py:24-28; the sync-BN exchange vector of
-   * torch/nn/modules/_functions.py:36-60) or, on a dgrad launch, the bias gradient of the producing layer -- without a
-   * separate pass over the tensor.  bf16 outputs only. */
-  float* colsum;
-  float* colsumsq;
   float res_scale;     /* residual multiplier (0 is read as 1): 0.25 with res_up2 = the backward of a 2x2 average pooling
                           added in the epilogue (src/models/big_resnet_deep_legacy.py:220-224, the pooled skip branch) */
 } sgb_conv_desc;

@@ -15,7 +15,6 @@ struct EpiArgs {
   const bf16* mask; long long mask_cstride;
   int relu;
   void* y; long long y_cstride; int y_fp32;
-  float* colsum; float* colsumsq;   // optional column statistics of the stored output (see sgb_conv_desc)
 };
 
 __device__ __forceinline__ float bf16_bits_lo(uint32_t u) { return __uint_as_float(u << 16); }
@@ -23,63 +22,6 @@ __device__ __forceinline__ float bf16_bits_hi(uint32_t u) { return __uint_as_flo
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Column statistics in the epilogue.  Each lane of a warp holds one output row (pixel) of a 16-channel piece; a butterfly
-// transpose-reduce (8 + 4 + 2 + 1 + 1 shuffles) leaves the 32-row sum of column (lane >> 1) & 15 in every lane pair.
-// Even lanes add it to the CTA-resident accumulator acc[piece base + column] (shared-memory atomics: four warps of a team
-// meet on an address); the CTA flushes acc to global memory once, after its last tile.
-// ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float colreduce16(const float (&v)[16]) {
-  const uint32_t lane = lane_id();
-  float a[8], b[4], c[2];
-  {
-    const bool hi = (lane & 16u) != 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float send = hi ? v[j] : v[j + 8];
-      const float keep = hi ? v[j + 8] : v[j];
-      a[j] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 16);
-    }
-  }
-  {
-    const bool hi = (lane & 8u) != 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float send = hi ? a[j] : a[j + 4];
-      const float keep = hi ? a[j + 4] : a[j];
-      b[j] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 8);
-    }
-  }
-  {
-    const bool hi = (lane & 4u) != 0;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const float send = hi ? b[j] : b[j + 2];
-      const float keep = hi ? b[j + 2] : b[j];
-      c[j] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 4);
-    }
-  }
-  const bool hi = (lane & 2u) != 0;
-  float d = (hi ? c[1] : c[0]) + __shfl_xor_sync(0xFFFFFFFFu, hi ? c[0] : c[1], 2);
-  d += __shfl_xor_sync(0xFFFFFFFFu, d, 1);
-  return d;
-}
-
-// f: the 16 values this row stores (already rounded to the output precision; zero for rows / channels outside the tensor).
-// acc: CTA accumulators [2][acc_n] (sum, then sum of squares); col0: column of f[0] inside the CTA's channel tile.
-__device__ __forceinline__ void epi_colstats(const float (&f)[16], float* acc, int acc_n, int col0, bool want_sq) {
-  const uint32_t lane = lane_id();
-  const float s = colreduce16(f);
-  if ((lane & 1u) == 0) atomicAdd(acc + col0 + ((lane >> 1) & 15u), s);
-  if (want_sq) {
-    float g[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) g[j] = f[j] * f[j];
-    const float q = colreduce16(g);
-    if ((lane & 1u) == 0) atomicAdd(acc + acc_n + col0 + ((lane >> 1) & 15u), q);
-  }
 }
 
 __device__ __forceinline__ bool epi_vec_ok(const EpiArgs& p) {
@@ -90,7 +32,7 @@ __device__ __forceinline__ bool epi_vec_ok(const EpiArgs& p) {
 // One thread = one accumulator row (TMEM lane).  t_row: TMEM address of this warp's lane quadrant at the accumulator's
 // first column.  All 32 lanes of the warp must call this (tcgen05.ld is warp-collective); stores are predicated by valid.
 __device__ __forceinline__ void epilogue_row(const EpiArgs& p, uint32_t t_row, int BN, int n0, bool valid, long long pix,
-                                             long long rpix, float alpha, bool vec_ok, float* stat_acc = nullptr) {
+                                             long long rpix, float alpha, bool vec_ok) {
   const bool res_pre = p.residual != nullptr && !p.res_after;
   const bool res_post = p.residual != nullptr && p.res_after;
   const float rs = p.res_scale;
@@ -100,45 +42,6 @@ __device__ __forceinline__ void epilogue_row(const EpiArgs& p, uint32_t t_row, i
     tmem_ld16(t_row + c0, v);
     tmem_ld_wait();
     const int n = n0 + c0;
-    if (stat_acc) {
-      // statistics path (bf16 output, aligned channels): every lane takes part in the warp reduction
-      if (n >= p.Cout) continue;                       // warp-uniform
-      float f[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * alpha;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int nn = n + j;
-        float x = f[j];
-        const bool ok = valid && nn < p.Cout;
-        if (p.bias && ok) x += __ldg(p.bias + nn);
-        if (res_pre && ok) x = fmaf(__bfloat162float(p.residual[rpix * p.res_cstride + nn]), rs, x);
-        if (p.relu) x = fmaxf(x, 0.f);
-        if (p.mask && ok) x = __bfloat162float(p.mask[pix * p.mask_cstride + nn]) > 0.f ? x : 0.f;
-        if (res_post && ok) x = fmaf(__bfloat162float(p.residual[rpix * p.res_cstride + nn]), rs, x);
-        f[j] = ok ? __bfloat162float(__float2bfloat16_rn(x)) : 0.f;
-      }
-      if (valid) {
-        if (vec_ok && n + 16 <= p.Cout) {
-          uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.y) + pix * p.y_cstride + n);
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            uint4 o;
-            o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-            o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-            o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-            o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-            yp[j] = o;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n + j < p.Cout) reinterpret_cast<bf16*>(p.y)[pix * p.y_cstride + n + j] = __float2bfloat16_rn(f[j]);
-        }
-      }
-      epi_colstats(f, stat_acc, BN, c0, p.colsumsq != nullptr);
-      continue;
-    }
     if (!valid || n >= p.Cout) continue;
     float f[16];
 #pragma unroll
@@ -273,8 +176,7 @@ __device__ __forceinline__ bool epi_use_tma(const EpiArgs& p, int BN) {
 __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtensorMap* tmY, uint32_t t_row, int BN, int n0,
                                                   int c1, int c2, int c3, bool valid, long long pix, long long rpix, float alpha,
                                                   uint32_t stage, int team, int row, bool leader, int chunk_stride = 2,
-                                                  const EpiAux* aux = nullptr, uint32_t* sbuf = nullptr,
-                                                  float* stat_acc = nullptr) {
+                                                  const EpiAux* aux = nullptr, uint32_t* sbuf = nullptr) {
   const bool res_pre = p.residual != nullptr && !p.res_after;
   const bool res_post = p.residual != nullptr && p.res_after;
   const float rs = p.res_scale;
@@ -372,19 +274,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
         }
       }
       // 16 channels = two 16-byte units (2s, 2s+1) of this row's 128-byte line; unit u lives at (u ^ (row & 7))
-      uint32_t pk[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-      st_shared_v4(srow + (((uint32_t)(2 * s) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
-      st_shared_v4(srow + (((uint32_t)(2 * s + 1) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
-      if (stat_acc && in_c) {                      // in_c is warp-uniform: all 32 lanes reduce together
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          f[2 * j] = (valid && 2 * j < nvalid) ? bf16_bits_lo(pk[j]) : 0.f;
-          f[2 * j + 1] = (valid && 2 * j + 1 < nvalid) ? bf16_bits_hi(pk[j]) : 0.f;
-        }
-        epi_colstats(f, stat_acc, BN, cc * 64 + s * 16, p.colsumsq != nullptr);
-      }
+      st_shared_v4(srow + (((uint32_t)(2 * s) ^ sw) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                   pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      st_shared_v4(srow + (((uint32_t)(2 * s + 1) ^ sw) << 4), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                   pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
     }
     fence_proxy_async_smem();                    // generic-proxy smem writes -> visible to the TMA (async proxy)
     named_bar_sync(1 + team, 128);

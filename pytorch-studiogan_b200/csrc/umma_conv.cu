@@ -36,7 +36,6 @@ struct FpropArgs {
   int epi_nbuf;                   // staging tiles per epilogue team (2: stores overlap the next chunk's conversion)
   int aux_kind, aux_tw, aux_th;   // residual (1) / mask (2) tile staged by TMA; its box is aux_tw x aux_th x nb pixels
   int out_sub;                    // 2: store only even (h, w) outputs at (h/2, w/2) -> stride-2 convolution (Inception reduction blocks)
-  int stats;                      // epilogue column statistics (EpiArgs::colsum / colsumsq); grid is a multiple of tiles_n
   uint32_t tmem_cols;
   EpiArgs e;
 };
@@ -57,14 +56,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
   const uint32_t holder = bar_base + 8u * (2 * p.stages + 4);
   auto aux_bar = [&](int t) { return bar_base + 8u * (2 * p.stages + 6 + t); };
-  // CTA-resident column statistics [2][BN] (this CTA only ever sees the channel tile blockIdx.x % tiles_n)
-  float* stat_acc = reinterpret_cast<float*>(smem_raw + (((bar_base + 8u * (2 * p.stages + 8) + 15u) & ~15u) - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (p.stats)
-    for (int i = threadIdx.x; i < 2 * p.BN; i += kThreads) stat_acc[i] = 0.f;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -209,25 +204,14 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           aux.n_c3 = u * p.nb;
         }
         epilogue_tile_tma(p.e, &tmY, t_row, p.BN, n0, wt * p.tw, ht * p.th, bt * p.nb, valid, pix, rpix, alpha, stage, team, row,
-                          leader, 2, p.aux_kind ? &aux : nullptr, p.epi_nbuf == 2 ? &sbuf : nullptr, p.stats ? stat_acc : nullptr);
+                          leader, 2, p.aux_kind ? &aux : nullptr, p.epi_nbuf == 2 ? &sbuf : nullptr);
       } else if (team == 0) {
-        epilogue_row(p.e, t_row, p.BN, n0, valid, pix, rpix, alpha, vec_ok, p.stats ? stat_acc : nullptr);
+        epilogue_row(p.e, t_row, p.BN, n0, valid, pix, rpix, alpha, vec_ok);
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(a));
     }
     if (p.use_tma && leader) bulk_wait_all();   // staging tiles must outlive the last tensor store
-    if (p.stats) {                               // one flush of this CTA's partial sums
-      named_bar_sync(3, kEpiThreads);
-      const int nbase = (int)(blockIdx.x % (unsigned)p.tiles_n) * p.BN;
-      for (int i = threadIdx.x - 128; i < p.BN; i += kEpiThreads) {
-        const int c = nbase + i;
-        if (c < p.e.Cout) {
-          atomicAdd(p.e.colsum + c, stat_acc[i]);
-          if (p.e.colsumsq) atomicAdd(p.e.colsumsq + c, stat_acc[p.BN + i]);
-        }
-      }
-    }
   }
 
   tc_fence_before();
@@ -451,7 +435,6 @@ void fill_epi(EpiArgs& e, const sgb_conv_desc* d) {
   e.res_scale = d->res_scale != 0.f ? d->res_scale : 1.f;
   e.mask = (const bf16*)d->mask; e.mask_cstride = d->mask_cstride; e.relu = d->relu;
   e.y = d->y; e.y_cstride = d->y_cstride; e.y_fp32 = d->y_fp32;
-  e.colsum = d->colsum; e.colsumsq = d->colsumsq;
 }
 
 static int make_act_tmap(CUtensorMap* m, const void* base, int B, int H, int W, int C, long long cstride, int tw, int th,
@@ -489,8 +472,6 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   SGB_REQUIRE(d->w_mode == 0 || (d->KH == 1 && d->KW == 1 && d->H * d->W >= 128));
   SGB_REQUIRE(d->w_mode != 2 || d->Cout % 8 == 0);
   SGB_REQUIRE(((uintptr_t)d->bias & 15) == 0 && ((uintptr_t)d->residual & 15) == 0 && ((uintptr_t)d->mask & 15) == 0);
-  SGB_REQUIRE(!d->colsumsq || d->colsum);
-  SGB_REQUIRE(!d->colsum || (!d->y_fp32 && d->out_sub != 2));
   {
     // wide, few-channel 3x3 layers: halo-row kernel (umma_conv3x3.cu).  SGB_CONV3X3_ROWS=0 forces the generic kernel.
     static const int use_rows = env_int("SGB_CONV3X3_ROWS", 1);
@@ -531,7 +512,9 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
                p.taps * d->Cin <= env_int("SGB_EPI_TMA_MAXK", 640) && env_int("SGB_EPI_TMA", 1)) ? 1 : 0;   // output-heavy layers only
   // auxiliary epilogue operand through TMA: exactly one of residual / mask, bf16 NHWC with 16-byte aligned channel stride
   p.aux_kind = 0; p.aux_tw = p.tw; p.aux_th = p.th;
-  if (p.use_tma && env_int("SGB_EPI_AUX", 1) && ((d->residual != nullptr) != (d->mask != nullptr))) {
+  if (p.use_tma && env_int("SGB_EPI_AUX", 1) && (d->residual != nullptr || d->mask != nullptr)) {
+    // one operand rides TMA: the mask when both are present (full-resolution tile; the residual of such launches is the
+    // quarter-size pooled-skip gradient, whose direct 16-byte loads are shared by 2x2 pixel neighbours through L1)
     if (d->mask) p.aux_kind = 2;
     else if (!d->res_up2) p.aux_kind = 1;
     else if (p.tw >= 2) { p.aux_kind = 1; p.aux_tw = p.tw / 2; p.aux_th = p.th >= 2 ? p.th / 2 : 1; }
@@ -545,7 +528,6 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   if (stages < 2) stages = 2;
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * BN);
-  p.stats = d->colsum ? 1 : 0;
   fill_epi(p.e, d);
 
   CUtensorMap tmA, tmB;
@@ -582,14 +564,13 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
     if (rc) return rc;
   }
   const size_t smem = (size_t)stages * stage_bytes + (p.use_tma ? 2 * p.epi_nbuf * kEpiStageBytes : 0) + (p.aux_kind ? 2 * kEpiStageBytes : 0) +
-                      1024 + 8 * (2 * stages + 8) + 16 + (p.stats ? 2 * BN * 4 + 16 : 0);
+                      1024 + 8 * (2 * stages + 8) + 16;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     SGB_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     smem_set = 227 * 1024;
   }
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  if (p.stats) grid -= grid % p.tiles_n;   // every CTA stays on one channel tile (tile index = nt + tiles_n * ...), so its sums are flushed once
   conv_fprop_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmY, tmAux, p);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
@@ -633,7 +614,7 @@ extern "C" int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream_) {
   p.splits = (p.tiles_per_group + p.tiles_per_split - 1) / p.tiles_per_split;
   p.num_items = base_items * p.splits;
   const uint32_t stage_bytes = 2 * kABytes + (p.BN / 64) * kABytes;
-  int stages = (int)(((200 - (d->dbias ? 16 : 0)) * 1024) / stage_bytes);
+  int stages = (int)(((d->dbias ? 224 - 16 : 200) * 1024) / stage_bytes);   // the ones slab must not cost a pipeline stage
   if (stages > 6) stages = 6;
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * p.BN + (d->dbias ? 32 : 0));

@@ -26,7 +26,6 @@ struct RowsArgs {
   int kblocks, BN, tiles_n, segs, hpairs, num_tiles;
   int resident, a_stages, b_stages, bo_mode;
   int use_tma, epi_bufs;   // TMA-store epilogue; 2 staging tiles: team t owns output row t, 1: team 0 handles both rows
-  int stats;               // epilogue column statistics; grid is a multiple of tiles_n
   uint32_t tmem_cols;
   EpiArgs e;
 };
@@ -57,13 +56,10 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto tfull = [&](int a) { return bar_base + 8u * (2 * p.a_stages + 2 * nb + a); };
   auto tempty = [&](int a) { return bar_base + 8u * (2 * p.a_stages + 2 * nb + 2 + a); };
   const uint32_t holder = bar_base + 8u * (2 * p.a_stages + 2 * nb + 4);
-  float* stat_acc = reinterpret_cast<float*>(smem_raw + (((holder + 8u + 15u) & ~15u) - smem_u32(smem_raw)));   // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (p.stats)
-    for (int i = threadIdx.x; i < 2 * p.BN; i += kRowsThreads) stat_acc[i] = 0.f;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -223,31 +219,19 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (p.epi_bufs == 2 || team == 0) {
               const uint32_t stage = epi_stage_base + ((p.epi_bufs == 2) ? team : 0) * kEpiStageBytes;
               // one team covers every chunk of its row: run the chunk loop for both parities on the team's own barrier
-              epilogue_tile_tma(p.e, &tmY, t_row, p.BN, nt * p.BN, ws * 128, h, b, true, pix, rpix, alpha, stage, team, row, leader, 1,
-                                nullptr, nullptr, p.stats ? stat_acc : nullptr);
+              epilogue_tile_tma(p.e, &tmY, t_row, p.BN, nt * p.BN, ws * 128, h, b, true, pix, rpix, alpha, stage, team, row, leader, 1);
             } else {
-              epilogue_row(p.e, t_row, p.BN, nt * p.BN, true, pix, rpix, alpha, vec_ok, p.stats ? stat_acc : nullptr);
+              epilogue_row(p.e, t_row, p.BN, nt * p.BN, true, pix, rpix, alpha, vec_ok);
             }
           }
         } else if (team == 0) {
-          epilogue_row(p.e, t_row, p.BN, nt * p.BN, true, pix, rpix, alpha, vec_ok, p.stats ? stat_acc : nullptr);
+          epilogue_row(p.e, t_row, p.BN, nt * p.BN, true, pix, rpix, alpha, vec_ok);
         }
       }
       tc_fence_before();
       mbar_arrive(tempty(as));
     }
     if (p.use_tma && leader) bulk_wait_all();
-    if (p.stats) {
-      named_bar_sync(3, kEpiThreads);
-      const int nbase = (int)(blockIdx.x % (unsigned)p.tiles_n) * p.BN;
-      for (int i = threadIdx.x - 128; i < p.BN; i += kEpiThreads) {
-        const int c = nbase + i;
-        if (c < p.e.Cout) {
-          atomicAdd(p.e.colsum + c, stat_acc[i]);
-          if (p.e.colsumsq) atomicAdd(p.e.colsumsq + c, stat_acc[p.BN + i]);
-        }
-      }
-    }
   }
 
   tc_fence_before();
@@ -277,7 +261,7 @@ int launch_conv3x3_rows(const sgb_conv_desc* d, cudaStream_t stream, int bo_mode
   p.num_tiles = p.tiles_n * p.segs * p.hpairs * d->B;
   p.bo_mode = bo_mode;
   const uint32_t b_tile = p.BN * 128u;
-  const uint32_t budget = 227u * 1024u - 3072u;   // alignment slack + barriers + column-statistics accumulators
+  const uint32_t budget = 227u * 1024u - 2048u;
   const uint32_t a_stage = 4 * kRowBufBytes;
   const uint32_t resident_bytes = 9u * p.kblocks * b_tile;
   p.use_tma = (!d->y_fp32 && p.BN % 64 == 0 && d->y_cstride % 8 == 0 && (!d->residual || d->res_cstride % 8 == 0) &&
@@ -300,7 +284,6 @@ int launch_conv3x3_rows(const sgb_conv_desc* d, cudaStream_t stream, int bo_mode
   uint32_t cols = 32;
   while ((int)cols < 4 * p.BN) cols <<= 1;
   p.tmem_cols = cols;
-  p.stats = d->colsum ? 1 : 0;
   fill_epi(p.e, d);
 
   CUtensorMap tmA, tmB;
@@ -329,14 +312,13 @@ int launch_conv3x3_rows(const sgb_conv_desc* d, cudaStream_t stream, int bo_mode
   const int nb = p.resident ? 1 : p.b_stages;
   const size_t smem = (size_t)p.a_stages * a_stage + (p.resident ? resident_bytes : p.b_stages * b_tile) +
                       (p.use_tma ? p.epi_bufs * kEpiStageBytes : 0) + 1024 +
-                      8 * (2 * p.a_stages + 2 * nb + 4) + 16 + (p.stats ? 2 * p.BN * 4 + 32 : 0);
+                      8 * (2 * p.a_stages + 2 * nb + 4) + 16;
   static bool attr_set = false;
   if (!attr_set) {
     SGB_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  if (p.stats) grid -= grid % p.tiles_n;
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   conv3x3_rows_kernel<<<grid, kRowsThreads, smem, stream>>>(tmA, tmB, tmY, p);
   SGB_LAUNCH_CHECK();
   return SGB_OK;

@@ -34,7 +34,7 @@ class ConvDesc(ctypes.Structure):
         ("relu", c_int),
         ("y", c_p), ("y_cstride", c_i64), ("y_fp32", c_int),
         ("Hin", c_int), ("Win", c_int), ("out_sub", c_int),
-        ("colsum", c_p), ("colsumsq", c_p), ("res_scale", c_f),
+        ("res_scale", c_f),
     ]
 
 

@@ -57,14 +57,6 @@ def _direct_grad(p):
     return g
 
 
-def _keep_colstats(src, view):
-    """A same-shape alias of ``src`` keeps the column statistics its producer's epilogue attached (kernels.colstats)."""
-    cs = getattr(src, "_sgb_colstats", None)
-    if cs is not None:
-        view._sgb_colstats = cs
-    return view
-
-
 def _tadd(a, b):
     if a is None:
         return b
@@ -106,16 +98,13 @@ def _grad_bf16(dy):
 def conv_param_grads(x, dz, weight, need_w, need_b, KH, KW, pad, dims, sigma, u_saved, v_saved, perm_S=1):
     """Weight and bias gradient of y = conv(x, W / sigma) + b given dz = dL/dy (NHWC bf16): tcgen05 weight-gradient kernel,
     then the spectral-norm chain rule (sgb_sn_backward).  The weight gradient is added straight into the flat gradient
-    arena when the parameter opted in (returns None for it then).  The bias gradient is taken, in this order, from the
-    column sums a dgrad epilogue left on dz, from the 3x3 weight-gradient kernel's idle MMA atom, or from a reduction."""
+    arena when the parameter opted in (returns None for it then).  The bias gradient rides on the weight-gradient launch
+    (a constant-ones operand on the tensor pipe, sgb_conv_wgrad_fuses_dbias); only a frozen weight with a live bias falls
+    back to a reduction pass."""
     Cout, Cin, taps = dims
     dW = dbias = None
-    if need_b:
-        cs = K.colstats(dz, 1)
-        if cs is not None:
-            dbias = cs[0][:Cout]
     if need_w:
-        if need_b and dbias is None:
+        if need_b:
             G, dbias = K.conv_wgrad(x, dz, KH, KW, pad, pad, want_dbias=True)
             if dbias is not None:
                 dbias = dbias[:Cout]
@@ -162,7 +151,7 @@ class ConvFn(TFunction):
         res = residual
         y = K.conv_fprop(x, wf, Cout_p, KH, KW, pad, pad, bias=bias if Cout_p == Cout else _pad_bias(bias, Cout_p),
                          residual=res, res_up2=cfg.get("res_up2", False), relu=cfg.get("relu", False),
-                         out_fp32=cfg.get("out_fp32", False), stats=cfg.get("stats", 0))
+                         out_fp32=cfg.get("out_fp32", False))
         if need_dw and sn is not None and cache is None:
             u_saved, v_saved = u.clone(), v.clone()
         ctx.cfg = cfg
@@ -192,10 +181,7 @@ class ConvFn(TFunction):
                 wf2, _ = K.weight_pack(wcol, None, Cin, 27, 1, True, False)
                 dx = K.conv_fprop(K.col27(dz), wf2, K.pad8(Cin), 1, 1, 0, 0, mask=mask)
             else:
-                # a premasked input gradient is the producing relu-conv's pre-activation gradient: its column sums are that
-                # layer's bias gradient (no separate reduction pass)
-                dx = K.conv_fprop(dz, wd, K.pad8(Cin), KH, KW, KH - 1 - pad, KW - 1 - pad, mask=mask,
-                                  stats=1 if (mask is not None and not SKIP_PARAM_GRADS) else 0)
+                dx = K.conv_fprop(dz, wd, K.pad8(Cin), KH, KW, KH - 1 - pad, KW - 1 - pad, mask=mask)
             if dx.shape[1] != x.shape[1]:
                 dx = dx[:, :x.shape[1]]
         if not SKIP_PARAM_GRADS:
@@ -267,11 +253,7 @@ class BNActFn(TFunction):
         count = float(B * H * W)
         group = cfg.get("group")
         if cfg["use_batch_stats"]:
-            stats = K.colstats(x, 2)                 # [sum, sum of squares] left by the producing conv's epilogue
-            if stats is None:
-                stats = K.bn_stats(x)
-            elif group is not None:
-                stats = stats.clone()                # the all-reduce below must not alter what rides on x
+            stats = K.bn_stats(x)
             if group is not None:
                 dist.all_reduce(stats, group=group)
                 count *= dist.get_world_size(group)
@@ -384,7 +366,7 @@ class SplitResidualFn(TFunction):
 
     @staticmethod
     def forward(ctx, x, c):
-        return _keep_colstats(x, x.view_as(x)), x[:, :c]
+        return x.view_as(x), x[:, :c]
 
     @staticmethod
     def backward(ctx, d_main, d_res):
@@ -529,8 +511,7 @@ class DEntryConvFn(TFunction):
        px is written into the first channels of the concat-skip buffer (cfg['skip_channels'] wide) when the block has a
        learnable shortcut, so the concatenation of :225-226 needs no copy.
        backward: ONE dgrad launch forms  dx = [a0 > 0] * (dgrad1(dh1) + 0.25 * up2(dpx))  (or ... + dpx without pooling):
-       the average-pool backward and both ReLU masks live in the conv epilogue (residual, res_up2, res_scale, mask), and
-       its column sums are the bias gradient of the layer that produced a0."""
+       the average-pool backward and both ReLU masks live in the conv epilogue (residual, res_up2, res_scale, mask)."""
 
     @staticmethod
     def forward(ctx, a0, weight, bias, cfg):
@@ -563,7 +544,7 @@ class DEntryConvFn(TFunction):
         if ctx.needs_input_grad[0]:
             down = cfg["downsample"]
             dx = K.conv_fprop(dz, wd, Cin, 1, 1, 0, 0, mask=a0, residual=K.as_nhwc(dpx) if dpx is not None else None,
-                              res_up2=down, res_scale=0.25 if down else 1.0, stats=0 if SKIP_PARAM_GRADS else 1)
+                              res_up2=down, res_scale=0.25 if down else 1.0)
         if not SKIP_PARAM_GRADS:
             dW, db = conv_param_grads(a0, dz, weight, ctx.needs_input_grad[1], ctx.needs_input_grad[2], 1, 1, 0, ctx.dims,
                                       sigma, us, vs)
@@ -813,7 +794,7 @@ class ForkFn(TFunction):
 
     @staticmethod
     def forward(ctx, x):
-        return _keep_colstats(x, x.view_as(x)), _keep_colstats(x, x.view_as(x))
+        return x.view_as(x), x.view_as(x)
 
     @staticmethod
     def backward(ctx, g1, g2):

@@ -56,12 +56,10 @@ def _s():
 # ---------------------------------------------------------------------------------------------- conv engine
 def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_up2=False, res_after_mask=False,
                mask=None, relu=False, alpha=1.0, alpha_ptr=None, out=None, out_fp32=False, w_mode=0, same_size=True, stride=1,
-               stats=0, res_scale=1.0):
+               res_scale=1.0):
     """y = epilogue(conv(x, w)); see sgb_conv_fprop. ``w`` is a packed bf16 weight (layout by w_mode).
     same_size=False: output grid = Hin + 2*pad - K + 1 ("valid"-style); stride=2 stores its even positions only.
-    stats: 1 = the epilogue also accumulates the per-channel sum of the stored output, 2 = sum and sum of squares; the
-    fp32 [stats, Cout] result rides on the returned tensor (``colstats(y, ...)``): the next BatchNorm's statistics or, on a
-    dgrad launch, the producing layer's bias gradient, without another pass over y."""
+    res_scale: multiplier of the residual (0.25 with res_up2 = average-pool backward added in the epilogue)."""
     B, Cin, Hin, Win, xcs = geom(x)
     H, W = (Hin, Win) if same_size else (Hin + 2 * pad_h - KH + 1, Win + 2 * pad_w - KW + 1)
     Ho, Wo = ((H + 1) // 2, (W + 1) // 2) if stride == 2 else (H, W)
@@ -88,38 +86,15 @@ def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_u
         d.mask, d.mask_cstride = mask.data_ptr(), geom(mask)[4]
     d.relu = 1 if relu else 0
     d.y, d.y_cstride, d.y_fp32 = out.data_ptr(), ycs, 1 if out.dtype == torch.float32 else 0
-    cs = None
-    if stats and COLSTATS and out.dtype == bf16 and stride == 1:
-        cs = torch.zeros((stats, Cout), device=x.device, dtype=torch.float32)
-        d.colsum = cs.data_ptr()
-        if stats == 2:
-            d.colsumsq = cs[1].data_ptr()
+    # algorithmic bytes: every operand tensor once (the residual at its own resolution), weights once
+    nb = 2.0 * B * Hin * Win * Cin + out.element_size() * float(B * Ho * Wo * Cout) + 2.0 * Cout * Cin * KH * KW * (B if w_mode else 1)
+    if residual is not None:
+        nb += 2.0 * B * H * W * Cout / (4 if res_up2 else 1)
+    if mask is not None:
+        nb += 2.0 * B * H * W * Cout
     L.call("sgb_conv_fprop", ctypes.byref(d), _s(), tag="conv_fprop %dx%d %d->%d @%dx%d m%d" % (KH, KW, Cin, Cout, H, W, w_mode),
-           flops=2.0 * B * H * W * Cout * Cin * KH * KW)
-    if cs is not None:
-        out._sgb_colstats = cs
+           flops=2.0 * B * H * W * Cout * Cin * KH * KW, nbytes=nb)
     return out
-
-
-COLSTATS_HITS = [0, 0]   # [found, fell back to a reduction pass] (diagnostics)
-# Epilogue column statistics are OFF by default: measured on B200 (profiles/r02_colstats_cuda_core_epilogue.md) the
-# CUDA-core butterfly reduction roughly doubles the epilogue's instruction count, and the epilogue is the critical path of
-# every memory-bound layer: bn_stats fell 35 -> 15 ms per step but conv_fprop rose 363 -> 663 ms.  The path stays
-# available (and tested) for layers that are tensor-bound with a short epilogue; bias gradients come from the
-# weight-gradient kernels instead (constant-ones operand atom).
-COLSTATS = False
-
-
-def colstats(x, rows):
-    """The [rows, C] column statistics a conv epilogue attached to ``x`` (rows 1: sum; 2: sum, sum of squares), or None.
-    The attribute lives on the Python tensor object, so any re-layout / slice / accumulation in between drops it and the
-    caller falls back to the stand-alone reduction."""
-    cs = getattr(x, "_sgb_colstats", None)
-    if cs is None or cs.shape[0] < rows or cs.shape[1] != x.shape[1]:
-        COLSTATS_HITS[1] += 1
-        return None
-    COLSTATS_HITS[0] += 1
-    return cs
 
 
 def conv_wgrad(x, dy, KH, KW, pad_h, pad_w, dw=None, accumulate=False, per_image=False, want_dbias=False):
@@ -143,7 +118,7 @@ def conv_wgrad(x, dy, KH, KW, pad_h, pad_w, dw=None, accumulate=False, per_image
         dbias = torch.empty(Cout, device=x.device, dtype=torch.float32)
         d.dbias = dbias.data_ptr()
     L.call("sgb_conv_wgrad", ctypes.byref(d), _s(), tag="conv_wgrad %dx%d %d->%d @%dx%d%s" % (KH, KW, Cin, Cout, H, W, " per-image" if per_image else ""),
-           flops=2.0 * B * H * W * Cout * Cin * KH * KW)
+           flops=2.0 * B * H * W * Cout * Cin * KH * KW, nbytes=2.0 * B * H * W * (Cin + Cout) + 4.0 * dw.numel())
     return (dw, dbias) if want_dbias else dw
 
 

@@ -40,10 +40,10 @@ class GenBlock(nn.Module):
             h = self.bn1(main, affine, relu=True, up2=True)
         else:
             h = self.bn1(main, relu=True, up2=True)
-        h = self.conv2d1(h, stats=2)                            # epilogue leaves bn2's batch statistics
+        h = self.conv2d1(h)
         h = self.bn2(h, affine, relu=True) if self.conditional else self.bn2(h, relu=True)
         skip = self.conv2d0(side)                               # low resolution; up-sampled inside conv2d2's epilogue
-        return self.conv2d2(h, residual=skip, res_up2=True, stats=2)   # ... and the next block's bn1 / the output BN
+        return self.conv2d2(h, residual=skip, res_up2=True)
 
 
 class _ImageSkipTangent:
@@ -86,8 +86,7 @@ class DiscOptBlock(nn.Module):
 
     def forward(self, img):
         """``img``: NCHW fp32 image."""
-        h = self.conv2d1(A.ImageColFn.call(img), relu=self.apply_d_sn, premasked=self.apply_d_sn,
-                         stats=0 if self.apply_d_sn else 2)
+        h = self.conv2d1(A.ImageColFn.call(img), relu=self.apply_d_sn, premasked=self.apply_d_sn)
         if not self.apply_d_sn:
             h = self.bn1(h, relu=True)
             h = self.conv2d2(h)
@@ -136,8 +135,8 @@ class DiscBlock(nn.Module):
             h = self.conv2d2(h, residual=skip, mask_input=True)
         else:
             main, side = A.ForkFn.call(x)
-            h = self.conv2d1(self.bn1(main, relu=True), stats=2)
+            h = self.conv2d1(self.bn1(main, relu=True))
             h = self.bn2(h, relu=True)
             skip = self.conv2d0(self.bn0(side)) if has_sc else side
-            h = self.conv2d2(h, residual=skip, stats=0 if self.downsample else 2)
+            h = self.conv2d2(h, residual=skip)
         return A.PoolFn.call(h) if self.downsample else h

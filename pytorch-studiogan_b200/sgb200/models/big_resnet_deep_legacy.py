@@ -54,11 +54,10 @@ class GenBlock(nn.Module):
 
     def forward(self, x, affine):
         main, skip = A.SplitResidualFn.call(x, self.out_channels)
-        # stats=2: each conv epilogue leaves the batch statistics [sum, sum of squares] the following (c)BN needs
-        h = self.conv2d1(self.bn1(main, affine, relu=True), stats=2)
-        h = self.conv2d2(self.bn2(h, affine, relu=True, up2=self.upsample), stats=2)
-        h = self.conv2d3(self.bn3(h, affine, relu=True), stats=2)
-        return self.conv2d4(self.bn4(h, affine, relu=True), residual=skip, res_up2=self.upsample, stats=2)
+        h = self.conv2d1(self.bn1(main, affine, relu=True))
+        h = self.conv2d2(self.bn2(h, affine, relu=True, up2=self.upsample))
+        h = self.conv2d3(self.bn3(h, affine, relu=True))
+        return self.conv2d4(self.bn4(h, affine, relu=True), residual=skip, res_up2=self.upsample)
 
 
 class Generator(nn.Module):

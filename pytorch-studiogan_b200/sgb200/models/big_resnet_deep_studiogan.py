@@ -40,11 +40,11 @@ class GenBlock(nn.Module):
 
     def forward(self, x, affine):
         main, side = A.ForkFn.call(x)
-        h = self.conv2d1(self.bn1(main, affine, relu=True), stats=2)   # stats=2: epilogue leaves the next (c)BN's statistics
-        h = self.conv2d2(self.bn2(h, affine, relu=True, up2=self.upsample), stats=2)
-        h = self.conv2d3(self.bn3(h, affine, relu=True), stats=2)
+        h = self.conv2d1(self.bn1(main, affine, relu=True))
+        h = self.conv2d2(self.bn2(h, affine, relu=True, up2=self.upsample))
+        h = self.conv2d3(self.bn3(h, affine, relu=True))
         skip = self.conv2d0(side)                               # low resolution; up-sampled inside conv2d4's epilogue
-        return self.conv2d4(self.bn4(h, affine, relu=True), residual=skip, res_up2=self.upsample, stats=2)
+        return self.conv2d4(self.bn4(h, affine, relu=True), residual=skip, res_up2=self.upsample)
 
 
 class Generator(legacy.Generator):

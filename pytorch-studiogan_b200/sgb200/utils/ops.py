@@ -47,18 +47,16 @@ class _ConvBase(nn.Conv2d):
         if self.spectral:
             _apply_spectral_norm(self)
 
-    def forward(self, x, residual=None, relu=False, premasked=False, mask_input=False, res_up2=False, stats=0):
-        """stats=2: the epilogue also leaves [sum, sum of squares] per channel on the result for the BatchNorm that
-        follows (kernels.colstats)."""
+    def forward(self, x, residual=None, relu=False, premasked=False, mask_input=False, res_up2=False):
         if self.in_channels == 3 and self.kernel_size == (3, 3) and self.padding == (1, 1):
-            return self._forward_image(x, residual, relu, premasked, stats)
+            return self._forward_image(x, residual, relu, premasked)
         cfg = {"KH": self.kernel_size[0], "KW": self.kernel_size[1], "pad": self.padding[0], "relu": relu,
-               "premasked": premasked, "mask_input": mask_input, "res_up2": res_up2, "stats": stats,
+               "premasked": premasked, "mask_input": mask_input, "res_up2": res_up2,
                "sn": getattr(self, "_sn", None), "do_power_iteration": self.training,
                "sn_cache": getattr(self, "_sn_cache", None)}
         return A.ConvFn.call(x, _w(self), self.bias, residual, cfg)
 
-    def _forward_image(self, x_col, residual, relu, premasked, stats=0):
+    def _forward_image(self, x_col, residual, relu, premasked):
         """3 -> C convolution on an image: ``x_col`` is the [B, 32, H, W] patch tensor from ImageColFn and the layer runs
         as a K = 32 GEMM.  The [Cout, 3, 3, 3] weight (864..3456 numbers) is re-ordered to [Cout, (tap, c)] with tensor
         ops; its spectral norm uses the library's power iteration and the reference's sigma = u . (W v) with u, v held
@@ -73,7 +71,7 @@ class _ConvBase(nn.Conv2d):
                 sigma = torch.dot(u.detach().clone(), torch.mv(W.reshape(W.shape[0], -1), v.detach().clone()))
             W = W / sigma
         Wp = W.permute(0, 2, 3, 1).reshape(W.shape[0], 27)
-        cfg = {"KH": 1, "KW": 1, "pad": 0, "relu": relu, "premasked": premasked, "sn": None, "stats": stats}
+        cfg = {"KH": 1, "KW": 1, "pad": 0, "relu": relu, "premasked": premasked, "sn": None}
         return A.ConvFn.call(x_col, Wp, self.bias, residual, cfg)
 
 

@@ -138,7 +138,7 @@ def grad_digest(out, prefix, named_params, full_below=16384, nproj=8):
             out[prefix + "full/" + k] = p.grad.detach().numpy().copy()
 
 
-def golden_deep_bench_shape(tag="deep256_c16_attn_d2", img_size=256, conv_dim=16, depth=2, B=4, z_dim=16, shared=16, classes=5):
+def golden_deep_bench_shape(tag="deep256_c16_attn_d2", img_size=256, conv_dim=16, depth=2, B=16, z_dim=16, shared=16, classes=5):
     """BigGAN-Deep at BASELINE config 4's resolution and topology (256x256, g_depth = d_depth = 2, attention at 64x64 ->
     N = 4096 queries x M = 1024 keys, attn_g_loc [4] / attn_d_loc [2]) with conv_dim 16 so that the CPU reference runs in
     seconds.  No weights are stored: the reference modules are built under torch.manual_seed(1234) and the product modules

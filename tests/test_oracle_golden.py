@@ -209,10 +209,10 @@ def test_deep_256_bench_topology(golden_dir):
     for k in pD:
         sdD[k].requires_grad_(True)
     gi = torch.Generator().manual_seed(77)
-    z = torch.randn(4, 16, generator=gi)
-    yf = torch.randint(0, 5, (4,), generator=gi)
-    real = torch.rand(4, 3, 256, 256, generator=gi) * 2 - 1
-    yr = torch.randint(0, 5, (4,), generator=gi)
+    z = torch.randn(16, 16, generator=gi)
+    yf = torch.randint(0, 5, (16,), generator=gi)
+    real = torch.rand(16, 3, 256, 256, generator=gi) * 2 - 1
+    yr = torch.randint(0, 5, (16,), generator=gi)
     kw_g = dict(img_size=256, g_conv_dim=16, g_depth=2, attn_g_loc=(4,), apply_attn=True)
     kw_d = dict(img_size=256, d_conv_dim=16, d_depth=2, attn_d_loc=(2,), apply_attn=True)
     with torch.no_grad():
