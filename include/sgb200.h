@@ -143,6 +143,19 @@ int sgb_sn_backward(const float* G, const float* W, const float* u, const float*
                     float* scratch_dot, float* dW, int32_t Cout, int32_t Cin, int32_t taps, int32_t perm_S,
                     int32_t Cin_p, int32_t accumulate, sgb_stream_t stream);
 
+/* Batched form of sgb_sn_backward: every layer of one network pass in two launches.  ``table`` is a DEVICE array;
+ * layer l reads its weight gradient at g_flat + off_g (fprop-pack layout, fp32), the u / v / sigma copies of that forward
+ * pass at u_flat + off_u, v_flat + off_v, sigma_all[l], and ADDS to dW (NULL: layer skipped).  dots: fp32 [n_layers]
+ * scratch (zeroed here). */
+typedef struct sgb_snbwd_layer {
+  const float* W;
+  float* dW;
+  int64_t off_g, off_u, off_v;
+  int32_t Cout, Cin, taps, perm_S, Cin_p, has_sn;
+} sgb_snbwd_layer;
+int sgb_sn_backward_batch(const sgb_snbwd_layer* table, int32_t n_layers, const float* g_flat, const float* sigma_all,
+                          const float* u_flat, const float* v_flat, float* dots, int32_t max_blocks, sgb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Batch-norm family (NHWC bf16 activations, fp32 statistics).
  * Replaces: ops.ConditionalBatchNorm2d.forward (src/utils/ops.py:24-28), ops.batchnorm_2d (:227-228),
@@ -212,11 +225,13 @@ int sgb_pool3x3(const void* x, int64_t xs, void* y, int64_t ys, int32_t B, int32
                 int32_t pad, int32_t mode, sgb_stream_t stream);
 /* uint8 quantisation of generated images, bit-exact with ops.quantize_images (src/utils/ops.py:251-255). */
 int sgb_quantize_u8(const float* img, uint8_t* out, int64_t n, sgb_stream_t stream);
-/* Fused evaluation pre-processing on the device (quantise -> "legacy" bilinear resize to SxS -> /255 -> (x-0.5)/0.5;
- * src/utils/ops.py:251-263, src/utils/resize.py:83-91, src/metrics/preparation.py:103-122).  img: NCHW fp32 [B,3,H,W].
+/* Fused evaluation pre-processing on the device (quantise -> bilinear resize to SxS -> /255 -> (x-0.5)/0.5;
+ * src/utils/ops.py:251-263, src/utils/resize.py:50-94, src/metrics/preparation.py:103-122).  img: NCHW fp32 [B,3,H,W].
+ * resizer 0 = "legacy" (torch F.interpolate bilinear, align_corners=False, clipped to [0,255]; resize.py:83-91),
+ *         1 = "friendly" (PIL bilinear on float32 'F'-mode channels, anti-aliased when shrinking; resize.py:50-53,72-82).
  * out_img (optional): NCHW fp32 [B,3,S,S]; out_col (optional): [B,So,So,32] bf16 stride-2 valid 3x3 patches, So=(S-3)/2+1. */
 int sgb_quantize_resize_normalize(const float* img, int32_t quantize, int32_t B, int32_t H, int32_t W, int32_t S, float* out_img,
-                                  void* out_col, sgb_stream_t stream);
+                                  void* out_col, int32_t resizer, sgb_stream_t stream);
 int sgb_cast_f32_to_bf16(const float* in, void* out, int64_t n, float scale, sgb_stream_t stream);
 int sgb_cast_bf16_to_f32(const void* in, float* out, int64_t n, sgb_stream_t stream);
 

@@ -330,6 +330,41 @@ def resize_legacy(x_uint8_nchw, size=299):
     return x.clamp(0, 255)
 
 
+def _pil_taps(in_size, out_size):
+    """Pillow Resample.c::precompute_coeffs for the triangle ("bilinear", support 1) filter: per output coordinate the first
+    source index and the normalised float64 weights."""
+    scale = in_size / out_size
+    fs = max(scale, 1.0)
+    support = 1.0 * fs
+    taps = []
+    for o in range(out_size):
+        center = (o + 0.5) * scale
+        lo = max(int(center - support + 0.5), 0)
+        hi = min(int(center + support + 0.5), in_size)
+        w = np.array([max(0.0, 1.0 - abs((x + lo - center + 0.5) / fs)) for x in range(hi - lo)], dtype=np.float64)
+        if w.sum() != 0.0:
+            w = w / w.sum()
+        taps.append((lo, w))
+    return taps
+
+
+def resize_friendly(x_uint8_nchw, size=299):
+    """'friendly' resizer for InceptionV3_tf (src/utils/resize.py:50-53,72-82): PIL bilinear on every channel as a float32
+    'F'-mode image.  Pillow's algorithm restated (ImagingResampleHorizontal_32bpc then ...Vertical_32bpc): separable,
+    horizontal pass first, float64 accumulation of float32 pixels with float64 weights, float32 storage after each pass;
+    the filter support grows with the down-scaling factor (anti-aliasing)."""
+    x = np.asarray(x_uint8_nchw).astype(np.float32)
+    B, C, H, W = x.shape
+    tx, ty = _pil_taps(W, size), _pil_taps(H, size)
+    hor = np.empty((B, C, H, size), dtype=np.float32)
+    for o, (lo, w) in enumerate(tx):
+        hor[..., o] = (x[..., lo:lo + len(w)].astype(np.float64) * w).sum(-1).astype(np.float32)
+    out = np.empty((B, C, size, size), dtype=np.float32)
+    for o, (lo, w) in enumerate(ty):
+        out[:, :, o, :] = (hor[:, :, lo:lo + len(w), :].astype(np.float64) * w[None, None, :, None]).sum(2).astype(np.float32)
+    return torch.from_numpy(out)
+
+
 def normalize_for_inception(x255):
     """resize_images tail (src/utils/ops.py:262): x/255, (x-0.5)/0.5 for InceptionV3_tf."""
     return (x255 / 255.0 - 0.5) / 0.5

@@ -78,7 +78,9 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ 
 // mode 0: cBN     scale[b,c] = rstd*(1+gain[b,c]),  shift[b,c] = bias[b,c] - mean*scale[b,c]   (nb = B rows)
 // mode 1: affine  scale[c]   = rstd*weight[c],      shift[c]   = bias[c]   - mean*scale[c]     (nb = 1 row)
 // mode 2: plain   scale[c]   = rstd,                shift[c]   = -mean*rstd                    (nb = 1 row)
-// use_batch_stats: 1 -> mean/var from sum/sumsq/count (and running stats updated if track), 0 -> running stats.
+// use_batch_stats: 1 -> mean/var from sum/sumsq/count (and running stats updated if track), 0 -> running stats;
+//                  2 -> as 1 with the DataParallel-mode SynchronizedBatchNorm's inverse std, bias_var.clamp(eps)^-0.5
+//                       (src/sync_batchnorm/batchnorm.py:158-175) instead of torch's (var + eps)^-0.5.
 __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, float count,
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, int use_batch_stats, int track, int mode, const float* __restrict__ gain,
@@ -99,7 +101,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
     mean = running_mean[c];
     var = running_var[c];
   }
-  const float rstd = rsqrtf(var + eps);
+  const float rstd = use_batch_stats == 2 ? rsqrtf(fmaxf(var, eps)) : rsqrtf(var + eps);
   if (blockIdx.y == 0) {
     mean_out[c] = mean;
     rstd_out[c] = rstd;

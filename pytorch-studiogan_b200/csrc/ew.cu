@@ -493,17 +493,58 @@ __device__ __forceinline__ float resized_pixel(const float* __restrict__ img, in
   const float r = (1.f - lh) * ((1.f - lw) * v00 + lw * v01) + lh * ((1.f - lw) * v10 + lw * v11);
   return fminf(fmaxf(r, 0.f), 255.f);
 }
+// "friendly" post-resizer = PIL bilinear on float32 ('F'-mode) channels (src/utils/resize.py:50-53,72-82).  Pillow's
+// ImagingResample (Resample.c: precompute_coeffs + ImagingResampleHorizontal/Vertical_32bpc), restated: two separable
+// passes, horizontal first; per output coordinate o: centre = (o + 0.5) * in/out, filterscale = max(in/out, 1),
+// support = filterscale (triangle filter), taps [int(centre - support + 0.5), int(centre + support + 0.5)) clipped to the
+// image, weight tri((x - centre + 0.5) / filterscale) normalised by the tap sum; coefficients and accumulation in double,
+// the intermediate (after the horizontal pass) and the result rounded to float32.  Anti-aliased when down-scaling.
+struct PilTaps { int lo, n; double w[8]; };
+__device__ __forceinline__ PilTaps pil_taps(int o, int in_size, int out_size) {
+  PilTaps t;
+  const double scale = (double)in_size / (double)out_size;
+  const double fs = scale < 1.0 ? 1.0 : scale;
+  const double support = fs, center = (o + 0.5) * scale, ss = 1.0 / fs;
+  int lo = (int)(center - support + 0.5); if (lo < 0) lo = 0;
+  int hi = (int)(center + support + 0.5); if (hi > in_size) hi = in_size;
+  t.lo = lo; t.n = hi - lo; if (t.n > 8) t.n = 8;          // 8 taps cover down-scaling by up to 3.5x
+  double ww = 0.0;
+  for (int x = 0; x < t.n; ++x) {
+    double a = (x + lo - center + 0.5) * ss; if (a < 0.0) a = -a;
+    const double w = a < 1.0 ? 1.0 - a : 0.0;
+    t.w[x] = w; ww += w;
+  }
+  if (ww != 0.0) for (int x = 0; x < t.n; ++x) t.w[x] /= ww;
+  return t;
+}
+__device__ __forceinline__ float resized_pixel_pil(const float* __restrict__ img, int quantize, int H, int W, int S, int oh, int ow) {
+  const PilTaps tx = pil_taps(ow, W, S), ty = pil_taps(oh, H, S);
+  double acc = 0.0;
+  for (int y = 0; y < ty.n; ++y) {
+    const float* row = img + (long long)(ty.lo + y) * W + tx.lo;
+    double h = 0.0;
+    for (int x = 0; x < tx.n; ++x) {
+      float v = __ldg(row + x);
+      if (quantize) v = quant_u8(v);
+      h += (double)v * tx.w[x];
+    }
+    acc += (double)(float)h * ty.w[y];                       // the horizontal pass stores float32
+  }
+  return (float)acc;
+}
 // mode 0: write the normalised resized image as NCHW fp32 [B,3,S,S] (API parity / tests);
 // mode 1: write the stride-2 valid 3x3 patch tensor [B,So,So,32] bf16 of the normalised resized image.
 __global__ void __launch_bounds__(256) resize_norm_kernel(const float* __restrict__ img, int quantize, int B, int H, int W, int S,
-                                                           float* __restrict__ out_img, bf16* __restrict__ out_col, int So) {
+                                                           float* __restrict__ out_img, bf16* __restrict__ out_col, int So,
+                                                           int friendly) {
   const float scale_h = (float)H / (float)S, scale_w = (float)W / (float)S;
   if (out_img) {
     const long long total = (long long)B * 3 * S * S;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
       const int ow = (int)(i % S), oh = (int)((i / S) % S);
       const long long bc = i / ((long long)S * S);
-      const float r = resized_pixel(img + bc * H * W, quantize, H, W, S, oh, ow, scale_h, scale_w);
+      const float r = friendly ? resized_pixel_pil(img + bc * H * W, quantize, H, W, S, oh, ow)
+                               : resized_pixel(img + bc * H * W, quantize, H, W, S, oh, ow, scale_h, scale_w);
       out_img[i] = (r / 255.0f - 0.5f) / 0.5f;
     }
   }
@@ -516,8 +557,9 @@ __global__ void __launch_bounds__(256) resize_norm_kernel(const float* __restric
       for (int t = 0; t < 9; ++t)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float r = resized_pixel(img + ((long long)b * 3 + c) * H * W, quantize, H, W, S, 2 * ho + t / 3, 2 * wo + t % 3,
-                                        scale_h, scale_w);
+          const float* src = img + ((long long)b * 3 + c) * H * W;
+          const float r = friendly ? resized_pixel_pil(src, quantize, H, W, S, 2 * ho + t / 3, 2 * wo + t % 3)
+                                   : resized_pixel(src, quantize, H, W, S, 2 * ho + t / 3, 2 * wo + t % 3, scale_h, scale_w);
           v[t * 3 + c] = (r / 255.0f - 0.5f) / 0.5f;
         }
 #pragma unroll
@@ -784,12 +826,14 @@ extern "C" int sgb_quantize_u8(const float* img, uint8_t* out, int64_t n, sgb_st
 }
 
 extern "C" int sgb_quantize_resize_normalize(const float* img, int32_t quantize, int32_t B, int32_t H, int32_t W, int32_t S,
-                                             float* out_img, void* out_col, sgb_stream_t stream_) {
+                                             float* out_img, void* out_col, int32_t resizer, sgb_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SGB_REQUIRE(img && (out_img || out_col) && B > 0 && H > 0 && W > 0 && S >= 3);
+  SGB_REQUIRE(resizer == 0 || resizer == 1);
+  SGB_REQUIRE(resizer == 0 || (2 * H <= 7 * S && 2 * W <= 7 * S));   // PIL path: at most 8 taps per axis
   const int So = (S - 3) / 2 + 1;
   const long long work = out_img ? (long long)B * 3 * S * S : (long long)B * So * So;
-  resize_norm_kernel<<<ew_blocks(work), 256, 0, stream>>>(img, quantize, B, H, W, S, out_img, (bf16*)out_col, So);
+  resize_norm_kernel<<<ew_blocks(work), 256, 0, stream>>>(img, quantize, B, H, W, S, out_img, (bf16*)out_col, So, resizer);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }

@@ -327,9 +327,76 @@ __global__ void __launch_bounds__(256) sn_pack_batch_kernel(const sgb_sn_layer* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Batched spectral-norm backward: dW += (G - <G, W/sigma> u v^T) / sigma for EVERY layer of a network pass in two launches
+// (blockIdx.y = layer).  G lives in one flat fp32 buffer laid out like the fprop packs (layer l at g_flat + off_f[l]); u / v /
+// sigma are the copies taken at that forward pass (flat arenas, per-layer offsets in the table).  Layers that produced no
+// weight gradient in this pass hold zeros in g_flat and add zero.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sn_bwd_dot_batch_kernel(const sgb_snbwd_layer* __restrict__ table,
+                                                                const float* __restrict__ g_flat, float* __restrict__ dots) {
+  __shared__ float sh[32];
+  const sgb_snbwd_layer L = table[blockIdx.y];
+  if (!L.has_sn || !L.dW) return;
+  const float* G = g_flat + L.off_g;
+  const size_t total = (size_t)L.Cout * L.Cin * L.taps;
+  float acc = 0.f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int tap = (int)(i % L.taps);
+    const int ci = (int)((i / L.taps) % L.Cin);
+    int co = (int)(i / ((size_t)L.taps * L.Cin));
+    if (L.perm_S > 1) { const int C = L.Cout / L.perm_S; co = (co % L.perm_S) * C + co / L.perm_S; }
+    acc = fmaf(__ldg(G + ((size_t)co * L.taps + tap) * L.Cin_p + ci), __ldg(L.W + i), acc);
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0 && acc != 0.f) atomicAdd(dots + blockIdx.y, acc);
+}
+
+__global__ void __launch_bounds__(256) sn_bwd_apply_batch_kernel(const sgb_snbwd_layer* __restrict__ table,
+                                                                  const float* __restrict__ g_flat, const float* __restrict__ dots,
+                                                                  const float* __restrict__ sigma_all, const float* __restrict__ u_flat,
+                                                                  const float* __restrict__ v_flat) {
+  const sgb_snbwd_layer L = table[blockIdx.y];
+  if (!L.dW) return;
+  const float* G = g_flat + L.off_g;
+  const size_t total = (size_t)L.Cout * L.Cin * L.taps;
+  float inv = 1.f, coef = 0.f;
+  const float* u = nullptr;
+  const float* v = nullptr;
+  if (L.has_sn) {
+    inv = 1.f / __ldg(sigma_all + blockIdx.y);
+    coef = __ldg(dots + blockIdx.y) * inv;
+    u = u_flat + L.off_u;
+    v = v_flat + L.off_v;
+  }
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int tap = (int)(i % L.taps);
+    const int ci = (int)((i / L.taps) % L.Cin);
+    const int co_orig = (int)(i / ((size_t)L.taps * L.Cin));
+    int co = co_orig;
+    if (L.perm_S > 1) { const int C = L.Cout / L.perm_S; co = (co % L.perm_S) * C + co / L.perm_S; }
+    float g = __ldg(G + ((size_t)co * L.taps + tap) * L.Cin_p + ci);
+    if (L.has_sn) g = (g - coef * __ldg(u + co_orig) * __ldg(v + (size_t)ci * L.taps + tap)) * inv;
+    L.dW[i] += g;
+  }
+}
+
 }  // namespace sgb
 
 using namespace sgb;
+
+extern "C" int sgb_sn_backward_batch(const sgb_snbwd_layer* table, int32_t n_layers, const float* g_flat, const float* sigma_all,
+                                     const float* u_flat, const float* v_flat, float* dots, int32_t max_blocks,
+                                     sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(table && n_layers > 0 && g_flat && dots && max_blocks > 0);
+  SGB_CUDA(cudaMemsetAsync(dots, 0, sizeof(float) * (size_t)n_layers, stream));
+  sn_bwd_dot_batch_kernel<<<dim3(max_blocks, n_layers), 256, 0, stream>>>(table, g_flat, dots);
+  SGB_LAUNCH_CHECK();
+  sn_bwd_apply_batch_kernel<<<dim3(max_blocks, n_layers), 256, 0, stream>>>(table, g_flat, dots, sigma_all, u_flat, v_flat);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
 
 extern "C" int sgb_sn_batch(const sgb_sn_layer* table, int32_t n_layers, float* sigma_all, void* pack_f, void* pack_d, float eps,
                             int32_t do_power_iteration, int32_t max_blocks_wtu, int32_t max_blocks_wv, int32_t max_blocks_pack,

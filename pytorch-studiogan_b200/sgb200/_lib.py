@@ -64,6 +64,7 @@ SIGNATURES = {
     "sgb_weight_pack": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "sgb_sn_batch": (c_int, [c_p, c_int, c_p, c_p, c_p, c_f, c_int, c_int, c_int, c_int, c_p]),
     "sgb_sn_backward": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "sgb_sn_backward_batch": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_int, c_p]),
     "sgb_bn_stats": (c_int, [c_p, c_i64, c_int, c_i64, c_p, c_p, c_p]),
     "sgb_bn_finalize": (c_int, [c_p, c_p, c_f, c_p, c_p, c_f, c_f, c_int, c_int, c_int, c_p, c_p, c_int, c_int,
                                 c_p, c_p, c_p, c_p, c_p]),
@@ -89,7 +90,7 @@ SIGNATURES = {
     "sgb_col27_bwd": (c_int, [c_p, c_p, c_int, c_int, c_int, c_p]),
     "sgb_pool3x3": (c_int, [c_p, c_i64, c_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
     "sgb_quantize_u8": (c_int, [c_p, c_p, c_i64, c_p]),
-    "sgb_quantize_resize_normalize": (c_int, [c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p]),
+    "sgb_quantize_resize_normalize": (c_int, [c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_int, c_p]),
     "sgb_cast_f32_to_bf16": (c_int, [c_p, c_p, c_i64, c_f, c_p]),
     "sgb_cast_bf16_to_f32": (c_int, [c_p, c_p, c_i64, c_p]),
     "sgb_adam_ema_step": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_f, c_f, c_f, c_f, c_int, c_p, c_p, c_f, c_f, c_p]),

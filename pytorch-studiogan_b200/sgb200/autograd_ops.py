@@ -95,7 +95,18 @@ def _grad_bf16(dy):
     return K.as_nhwc(dy)
 
 
-def conv_param_grads(x, dz, weight, need_w, need_b, KH, KW, pad, dims, sigma, u_saved, v_saved, perm_S=1):
+def _direct_grad_ptr(p):
+    """Device address of the arena-backed ``.grad`` of a parameter (see _direct_grad), else None.  Frozen parameters keep
+    their arena slot, so the batched spectral-norm backward may address it (their pass buffer holds zeros)."""
+    if not getattr(p, "_sgb_direct_grad", False) or not p.is_leaf:
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape:
+        return None
+    return g.data_ptr()
+
+
+def conv_param_grads(x, dz, weight, need_w, need_b, KH, KW, pad, dims, sigma, u_saved, v_saved, perm_S=1, sn_pass=None):
     """Weight and bias gradient of y = conv(x, W / sigma) + b given dz = dL/dy (NHWC bf16): tcgen05 weight-gradient kernel,
     then the spectral-norm chain rule (sgb_sn_backward).  The weight gradient is added straight into the flat gradient
     arena when the parameter opted in (returns None for it then).  The bias gradient rides on the weight-gradient launch
@@ -103,7 +114,17 @@ def conv_param_grads(x, dz, weight, need_w, need_b, KH, KW, pad, dims, sigma, u_
     back to a reduction pass."""
     Cout, Cin, taps = dims
     dW = dbias = None
-    if need_w:
+    if need_w and sn_pass is not None and sn_pass[0] is not None and _direct_grad(weight) is not None and sn_pass[0].usable():
+        # batched path: accumulate the raw weight gradient into this forward pass's flat buffer; the spectral-norm chain
+        # rule of ALL layers runs as one launch pair when the backward pass ends (snbatch._Pass.flush)
+        G = sn_pass[0].g_slice(sn_pass[1])
+        if need_b:
+            _, dbias = K.conv_wgrad(x, dz, KH, KW, pad, pad, dw=G, accumulate=True, want_dbias=True)
+            if dbias is not None:
+                dbias = dbias[:Cout]
+        else:
+            K.conv_wgrad(x, dz, KH, KW, pad, pad, dw=G, accumulate=True)
+    elif need_w:
         if need_b:
             G, dbias = K.conv_wgrad(x, dz, KH, KW, pad, pad, want_dbias=True)
             if dbias is not None:
@@ -186,7 +207,7 @@ class ConvFn(TFunction):
                 dx = dx[:, :x.shape[1]]
         if not SKIP_PARAM_GRADS:
             dW, dbias = conv_param_grads(x, dz, weight, ctx.needs_input_grad[1], ctx.needs_input_grad[2], KH, KW, pad, ctx.dims,
-                                         sigma, u_saved, v_saved, cfg.get("perm_S", 1))
+                                         sigma, u_saved, v_saved, cfg.get("perm_S", 1), cfg.get("sn_pass"))
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = K.pool2_fwd(dz, 2) if cfg.get("res_up2", False) else dz
             rc = ctx.res_shape[1]
@@ -210,7 +231,7 @@ class ConvFn(TFunction):
                 raise NotImplementedError("tangent through an up-sampled residual without a main-branch tangent")
         else:
             tcfg = {"KH": cfg["KH"], "KW": cfg["KW"], "pad": cfg["pad"], "relu": False, "res_up2": cfg.get("res_up2", False),
-                    "sn": cfg.get("sn"), "sn_cache": cfg.get("sn_cache"), "do_power_iteration": False}
+                    "sn": cfg.get("sn"), "sn_cache": cfg.get("sn_cache"), "sn_pass": cfg.get("sn_pass"), "do_power_iteration": False}
             t = ConvFn.apply(tx, weight, None, tres, tcfg)
         if t is not None and cfg.get("relu", False):
             t = MaskFn.apply(t, out)
@@ -265,7 +286,8 @@ class BNActFn(TFunction):
         if b is not None and not b.is_contiguous():
             b = b.contiguous()
         mean, rstd, scale, shift = K.bn_finalize(stats, count, running_mean, running_var, cfg["momentum"], cfg["eps"],
-                                                 cfg["use_batch_stats"], cfg["track"], mode, g, b, nb, C, x.device)
+                                                 (2 if cfg.get("clamp_eps") else 1) if cfg["use_batch_stats"] else 0,
+                                                 cfg["track"], mode, g, b, nb, C, x.device)
         y = K.scale_shift_act(x, scale, shift, mode == 0, cfg["relu"], cfg["up2"])
         ctx.cfg = cfg
         ctx.count = count
@@ -299,6 +321,10 @@ class BNActFn(TFunction):
         group = cfg.get("group")
         if cfg["use_batch_stats"] and group is not None:
             dist.all_reduce(S12, group=group)
+        if cfg.get("clamp_eps") and cfg["use_batch_stats"]:
+            # DataParallel-mode variant: where the variance was clamped, inv_std is a constant and the variance term of the
+            # gradient vanishes (rare mode; a [C]-sized tensor op)
+            S12[1].mul_((rstd < (cfg["eps"] ** -0.5) * (1.0 - 1e-6)).to(S12.dtype))
         dx = None
         if ctx.needs_input_grad[0]:
             dx = K.bn_bwd_apply(dy, x, scale, shift, mode == 0, mean, rstd, S12, ctx.count, cfg["relu"], cfg["up2"],
@@ -547,7 +573,7 @@ class DEntryConvFn(TFunction):
                               res_up2=down, res_scale=0.25 if down else 1.0)
         if not SKIP_PARAM_GRADS:
             dW, db = conv_param_grads(a0, dz, weight, ctx.needs_input_grad[1], ctx.needs_input_grad[2], 1, 1, 0, ctx.dims,
-                                      sigma, us, vs)
+                                      sigma, us, vs, 1, cfg.get("sn_pass"))
         return dx, dW, db, None
 
 
@@ -594,7 +620,7 @@ class ConcatSkipFn(TFunction):
             dpx = K.conv_fprop(d_hi, wd, Cin, 1, 1, 0, 0, residual=d_lo)
         if not SKIP_PARAM_GRADS:
             dW, dbias = conv_param_grads(px, d_hi, weight, ctx.needs_input_grad[1], ctx.needs_input_grad[2], 1, 1, 0,
-                                         (Cextra, Cin, 1), sigma, u_saved, v_saved)
+                                         (Cextra, Cin, 1), sigma, u_saved, v_saved, 1, ctx.cfg.get("sn_pass"))
         return dpx, dW, dbias, None
 
     @staticmethod
@@ -603,7 +629,7 @@ class ConcatSkipFn(TFunction):
         tpx = tan(px)
         if tpx is None:
             return None
-        return ConcatSkipFn.apply(tpx, weight, None, {"sn": cfg.get("sn"), "sn_cache": cfg.get("sn_cache"),
+        return ConcatSkipFn.apply(tpx, weight, None, {"sn": cfg.get("sn"), "sn_cache": cfg.get("sn_cache"), "sn_pass": cfg.get("sn_pass"),
                                                        "do_power_iteration": False})
 
 

@@ -114,8 +114,9 @@ def conv_wgrad(x, dy, KH, KW, pad_h, pad_w, dw=None, accumulate=False, per_image
     d.dy, d.dy_cstride = dy.data_ptr(), dcs
     d.dw, d.accumulate, d.per_image = dw.data_ptr(), 1 if accumulate else 0, 1 if per_image else 0
     dbias = None
-    if want_dbias and not accumulate and L.load().sgb_conv_wgrad_fuses_dbias(ctypes.byref(d)):
-        dbias = torch.empty(Cout, device=x.device, dtype=torch.float32)
+    if want_dbias and L.load().sgb_conv_wgrad_fuses_dbias(ctypes.byref(d)):
+        # accumulate: the launch zeroes neither dw nor dbias, so dbias starts from zeros here
+        dbias = (torch.zeros if accumulate else torch.empty)(Cout, device=x.device, dtype=torch.float32)
         d.dbias = dbias.data_ptr()
     L.call("sgb_conv_wgrad", ctypes.byref(d), _s(), tag="conv_wgrad %dx%d %d->%d @%dx%d%s" % (KH, KW, Cin, Cout, H, W, " per-image" if per_image else ""),
            flops=2.0 * B * H * W * Cout * Cin * KH * KW, nbytes=2.0 * B * H * W * (Cin + Cout) + 4.0 * dw.numel())
@@ -179,7 +180,7 @@ def bn_finalize(stats, count, running_mean, running_var, momentum, eps, use_batc
     scale = torch.empty((nb, C), device=device, dtype=torch.float32)
     shift = torch.empty((nb, C), device=device, dtype=torch.float32)
     L.call("sgb_bn_finalize", L.ptr(stats[0]) if stats is not None else None, L.ptr(stats[1]) if stats is not None else None,
-           float(count), L.ptr(running_mean), L.ptr(running_var), float(momentum), float(eps), 1 if use_batch_stats else 0,
+           float(count), L.ptr(running_mean), L.ptr(running_var), float(momentum), float(eps), int(use_batch_stats),
            1 if track else 0, mode, L.ptr(gain), L.ptr(bias), nb, C, L.ptr(mean), L.ptr(rstd), L.ptr(scale), L.ptr(shift), _s())
     return mean, rstd, scale, shift
 
@@ -349,15 +350,17 @@ def quantize_u8(img):
     return out
 
 
-def quantize_resize_normalize(img, S=299, quantize=True, want_image=False, want_col=True):
-    """Fused eval pre-processing; returns (normalised resized image NCHW fp32 | None, stride-2 3x3 patch tensor | None)."""
+def quantize_resize_normalize(img, S=299, quantize=True, want_image=False, want_col=True, resizer="legacy"):
+    """Fused eval pre-processing; returns (normalised resized image NCHW fp32 | None, stride-2 3x3 patch tensor | None).
+    resizer: "legacy" (torch bilinear) or "friendly" (PIL 'F'-mode bilinear), src/utils/resize.py:50-94."""
     B, C, H, W = img.shape
     assert C == 3
     img = img.contiguous()
     So = (S - 3) // 2 + 1
     out_img = torch.empty((B, 3, S, S), device=img.device, dtype=torch.float32) if want_image else None
     out_col = empty_nhwc(B, 32, So, So, img.device) if want_col else None
-    L.call("sgb_quantize_resize_normalize", L.ptr(img), 1 if quantize else 0, B, H, W, S, L.ptr(out_img), L.ptr(out_col), _s())
+    L.call("sgb_quantize_resize_normalize", L.ptr(img), 1 if quantize else 0, B, H, W, S, L.ptr(out_img), L.ptr(out_col),
+           {"legacy": 0, "friendly": 1}[resizer], _s())
     return out_img, out_col
 
 

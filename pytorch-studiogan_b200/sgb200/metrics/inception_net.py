@@ -162,9 +162,9 @@ class InceptionV3(object):
         return pool, logits.reshape(B, -1)[:, :self.fc_out].contiguous()
 
     @torch.no_grad()
-    def forward(self, images, quantize=True):
+    def forward(self, images, quantize=True, resizer="legacy"):
         """``images``: NCHW fp32 in [-1, 1] (quantize=True, the generated-image path) or already 0..255 valued."""
-        _, col = K.quantize_resize_normalize(images, 299, quantize=quantize, want_image=False, want_col=True)
+        _, col = K.quantize_resize_normalize(images, 299, quantize=quantize, want_image=False, want_col=True, resizer=resizer)
         return self.forward_col(col)
 
     __call__ = forward

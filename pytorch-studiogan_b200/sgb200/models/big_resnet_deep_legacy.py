@@ -160,7 +160,7 @@ class DiscBlock(nn.Module):
         c1 = self.conv2d1
         h, px = A.DEntryConvFn.call(a0, ops._w(c1), c1.bias,
                                     {"downsample": self.downsample, "sn": getattr(c1, "_sn", None), "do_power_iteration": c1.training,
-                                     "sn_cache": getattr(c1, "_sn_cache", None),
+                                     "sn_cache": getattr(c1, "_sn_cache", None), "sn_pass": getattr(c1, "_sn_pass", None),
                                      "skip_channels": self.conv2d4.out_channels if self.learnable_sc else 0})
         h = self.conv2d2(h, relu=True, premasked=True, mask_input=True)
         h = self.conv2d3(h, relu=True, premasked=True, mask_input=True)
@@ -171,7 +171,7 @@ class DiscBlock(nn.Module):
             c0 = self.conv2d0
             skip = A.ConcatSkipFn.call(px, ops._w(c0), c0.bias,
                                         {"sn": getattr(c0, "_sn", None), "do_power_iteration": c0.training,
-                                         "sn_cache": getattr(c0, "_sn_cache", None)})
+                                         "sn_cache": getattr(c0, "_sn_cache", None), "sn_pass": getattr(c0, "_sn_pass", None)})
         return self.conv2d4(h, residual=skip, mask_input=not self.downsample, relu=out_relu, premasked=out_relu)
 
     def _forward_taped(self, x, in_relu, out_relu):
@@ -189,7 +189,7 @@ class DiscBlock(nn.Module):
             c0 = self.conv2d0
             skip = A.ConcatSkipFn.call(px, ops._w(c0), c0.bias,
                                         {"sn": getattr(c0, "_sn", None), "do_power_iteration": c0.training,
-                                         "sn_cache": getattr(c0, "_sn_cache", None)})
+                                         "sn_cache": getattr(c0, "_sn_cache", None), "sn_pass": getattr(c0, "_sn_pass", None)})
         return self.conv2d4(h, residual=skip, mask_input=not self.downsample)
 
 

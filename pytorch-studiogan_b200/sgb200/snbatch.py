@@ -22,6 +22,46 @@ LAYER_DTYPE = np.dtype([("W", "<u8"), ("u", "<u8"), ("v", "<u8"), ("ws", "<u8"),
                         ("Cout", "<i4"), ("Cin", "<i4"), ("taps", "<i4"), ("perm_S", "<i4"), ("Cout_p", "<i4"), ("Cin_p", "<i4"),
                         ("off_f", "<i8"), ("off_d", "<i8"), ("has_sn", "<i4"), ("reserved", "<i4")])
 assert LAYER_DTYPE.itemsize == 88
+BWD_DTYPE = np.dtype([("W", "<u8"), ("dW", "<u8"), ("off_g", "<i8"), ("off_u", "<i8"), ("off_v", "<i8"), ("Cout", "<i4"),
+                      ("Cin", "<i4"), ("taps", "<i4"), ("perm_S", "<i4"), ("Cin_p", "<i4"), ("has_sn", "<i4")])
+assert BWD_DTYPE.itemsize == 64
+
+
+class _Pass:
+    """One network forward's spectral-norm state for the backward pass: sigma / u / v as they were at that forward, and a
+    flat fp32 buffer into which every layer's weight-gradient launch accumulates (fprop-pack layout).  When the backward
+    pass of the graph finishes, ONE batched launch pair applies the spectral-norm chain rule of all layers and adds the
+    result to the flat gradient arena (instead of ~2 launches + a memset per layer)."""
+
+    def __init__(self, owner, sigma, us, vs):
+        self.owner, self.sigma, self.us, self.vs = owner, sigma, us, vs
+        self.g_flat = None
+        self.queued = False
+
+    def usable(self):
+        return self.us is not None and self.owner.bwd_table() is not None
+
+    def g_slice(self, i):
+        """fp32 [Cout_p][taps][Cin_p] accumulator of layer i (zero-initialised with the whole buffer on first use)."""
+        o = self.owner
+        if self.g_flat is None:
+            self.g_flat = torch.zeros(o.total_f, device=o.device, dtype=torch.float32)
+        of, _, nf, shf = o.slices[i][0], None, o.slices[i][2], o.slices[i][3]
+        if not self.queued:
+            self.queued = True
+            torch.autograd.Variable._execution_engine.queue_callback(self.flush)
+        return self.g_flat[of:of + nf].view(shf)
+
+    def flush(self):
+        o = self.owner
+        self.queued = False
+        if self.g_flat is None:
+            return
+        table = o.bwd_table()
+        dots = torch.empty(len(o.mods), device=o.device, dtype=torch.float32)
+        L.call("sgb_sn_backward_batch", L.ptr(table), len(o.mods), L.ptr(self.g_flat), L.ptr(self.sigma), L.ptr(self.us),
+               L.ptr(self.vs), L.ptr(dots), 96, L.stream_ptr())
+        self.g_flat = None
 
 
 def _eligible(m):
@@ -90,6 +130,30 @@ class SNBatch:
         self.device = device
         self.params = [ops._w(m) for m in mods]
         self.ptrs = [w.data_ptr() for w in self.params]
+        self._bwd_table = self._bwd_key = None
+        bt = np.zeros(len(mods), dtype=BWD_DTYPE)
+        for i, (m, (of, od, nf, shf, shd, su, sv)) in enumerate(zip(mods, self.slices)):
+            e = bt[i]
+            e["W"], e["off_g"] = self.params[i].data_ptr(), of
+            e["Cout"], e["Cin"], e["taps"], e["perm_S"], e["Cin_p"] = table[i]["Cout"], table[i]["Cin"], table[i]["taps"], table[i]["perm_S"], table[i]["Cin_p"]
+            if su is not None:
+                e["has_sn"], e["off_u"], e["off_v"] = 1, su[0], sv[0]
+        self._bwd_host = bt
+
+    def bwd_table(self):
+        """Device table for sgb_sn_backward_batch, valid while every layer's ``.grad`` is its view of the flat gradient arena
+        (utils/arena.GradArena.attach); None otherwise (the per-layer path is used then)."""
+        from .autograd_ops import _direct_grad_ptr
+        key = tuple(_direct_grad_ptr(w) for w in self.params)
+        if any(k is None for k in key):
+            return None
+        if key != self._bwd_key:
+            bt = self._bwd_host.copy()
+            for i, k in enumerate(key):
+                bt[i]["dW"] = k
+            self._bwd_table = torch.from_numpy(bt.view(np.uint8).copy()).to(self.device)
+            self._bwd_key = key
+        return self._bwd_table
 
     def run(self):
         """Power-iterate (layers in train mode, as the reference's hooks) and pack every layer; leaves per-layer views in
@@ -108,7 +172,9 @@ class SNBatch:
                1 if training else 0, mb[0], mb[1], mb[2], L.stream_ptr())
         us = self.u_flat.clone() if need_grad else None
         vs = self.v_flat.clone() if need_grad else None
+        cur = _Pass(self, sigma, us, vs) if need_grad else None
         for i, (m, (of, od, nf, shf, shd, su, sv)) in enumerate(zip(self.mods, self.slices)):
+            m._sn_pass = (cur, i) if cur is not None else None
             wf = pf[of:of + nf].view(shf)
             wd = pd[od:od + nf].view(shd) if pd is not None else None
             has_sn = su is not None
@@ -120,3 +186,4 @@ class SNBatch:
         if self.mods:
             for m in self.mods:
                 m._sn_cache = None
+                m._sn_pass = None

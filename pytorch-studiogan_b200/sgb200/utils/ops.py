@@ -53,7 +53,7 @@ class _ConvBase(nn.Conv2d):
         cfg = {"KH": self.kernel_size[0], "KW": self.kernel_size[1], "pad": self.padding[0], "relu": relu,
                "premasked": premasked, "mask_input": mask_input, "res_up2": res_up2,
                "sn": getattr(self, "_sn", None), "do_power_iteration": self.training,
-               "sn_cache": getattr(self, "_sn_cache", None)}
+               "sn_cache": getattr(self, "_sn_cache", None), "sn_pass": getattr(self, "_sn_pass", None)}
         return A.ConvFn.call(x, _w(self), self.bias, residual, cfg)
 
     def _forward_image(self, x_col, residual, relu, premasked):
@@ -101,7 +101,7 @@ class _LinearBase(nn.Linear):
             bias = bias.view(-1, perm_S).t().reshape(-1)
         cfg = {"KH": 1, "KW": 1, "pad": 0, "relu": False, "out_fp32": out_fp32, "perm_S": perm_S,
                "sn": getattr(self, "_sn", None), "do_power_iteration": self.training,
-               "sn_cache": getattr(self, "_sn_cache", None)}
+               "sn_cache": getattr(self, "_sn_cache", None), "sn_pass": getattr(self, "_sn_pass", None)}
         return A.ConvFn.call(x, _w(self), bias, None, cfg)
 
 
@@ -172,6 +172,10 @@ class BatchNorm2d(nn.BatchNorm2d):
     """nn.BatchNorm2d whose forward is the fused stats -> (NCCL all-reduce) -> scale/shift [+ReLU] [+nearest x2] path.
     ``sync_group`` is set by models.model.prepare_parallel_training instead of converting to torch SyncBatchNorm."""
     sync_group = None
+    # True: the inverse std of the reference's DataParallel-mode SynchronizedBatchNorm, bias_var.clamp(eps) ** -0.5
+    # (src/sync_batchnorm/batchnorm.py:158-175), instead of torch's (var + eps) ** -0.5.  DataParallel replicas themselves
+    # are not supported (DDP only); the switch exists so that statistics trained under that mode can be reproduced.
+    dp_sync_semantics = False
 
     def forward(self, x, relu=False, up2=False, gain=None, bias=None):
         training = self.training or (self.running_mean is None)
@@ -186,7 +190,7 @@ class BatchNorm2d(nn.BatchNorm2d):
             mode, g, b = 2, None, None
         cfg = {"mode": mode, "relu": relu, "up2": up2, "use_batch_stats": training, "track": track,
                "momentum": self.momentum if self.momentum is not None else 0.1, "eps": self.eps,
-               "group": self.sync_group if training else None}
+               "group": self.sync_group if training else None, "clamp_eps": self.dp_sync_semantics}
         return A.BNActFn.call(x, g, b, self.running_mean, self.running_var, cfg)
 
 
@@ -233,7 +237,7 @@ class SelfAttention(nn.Module):
 
     def forward(self, x):
         mods = (self.conv1x1_theta, self.conv1x1_phi, self.conv1x1_g, self.conv1x1_attn)
-        cfgs = tuple({"sn": getattr(m, "_sn", None), "do_power_iteration": m.training, "sn_cache": getattr(m, "_sn_cache", None)}
+        cfgs = tuple({"sn": getattr(m, "_sn", None), "do_power_iteration": m.training, "sn_cache": getattr(m, "_sn_cache", None), "sn_pass": getattr(m, "_sn_pass", None)}
                      for m in mods)
         return A.SelfAttentionFn.call(x, _w(mods[0]), _w(mods[1]), _w(mods[2]), _w(mods[3]), self.sigma, cfgs)
 

@@ -15,8 +15,18 @@ def sample_normal(batch_size, z_dim, truncation_factor, device):
 
 
 def sample_y(y_sampler, batch_size, num_classes, device):
+    """src/utils/sample.py:41-66.  "acending_some" / "acending_all" are the visualisation samplers (8 images per class:
+    a numpy permutation of the classes, or every class)."""
     if y_sampler == "totally_random":
         return torch.randint(low=0, high=num_classes, size=(batch_size,), dtype=torch.long, device=device)
+    if y_sampler in ("acending_some", "acending_all"):
+        if y_sampler == "acending_some":
+            assert batch_size % 8 == 0, "The size of batches should be a multiple of 8."
+            import numpy as np
+            classes = np.random.permutation(num_classes)[:batch_size // 8]
+        else:
+            classes = range(num_classes)
+        return torch.tensor([int(c) for c in classes for _ in range(8)], dtype=torch.long).to(device)
     if isinstance(y_sampler, int):
         return torch.tensor([y_sampler] * batch_size, dtype=torch.long).to(device)
     return None

@@ -379,6 +379,29 @@ def golden_dcgan(tag="dcgan32", B=8, z_dim=16):
     print(tag, "keys", len(out), "d_loss", float(d_loss), "g_loss", float(g_loss))
 
 
+def golden_sampler():
+    """utils.sample.sample_zy of the reference (src/utils/sample.py:69-90) on the CPU generator: labels are drawn BEFORE
+    the latents; gaussian / uniform priors, the eps-ball branch, truncation (scipy truncnorm on numpy's global RNG) and the
+    visualisation label samplers."""
+    import utils.sample as rsample
+    out = {}
+    for name, kw in (("gauss", dict(z_prior="gaussian", truncation_factor=-1.0, y_sampler="totally_random", radius="N/A")),
+                     ("uniform", dict(z_prior="uniform", truncation_factor=-1.0, y_sampler="totally_random", radius="N/A")),
+                     ("eps", dict(z_prior="gaussian", truncation_factor=-1.0, y_sampler="totally_random", radius=0.5)),
+                     ("trunc", dict(z_prior="gaussian", truncation_factor=0.7, y_sampler="totally_random", radius="N/A")),
+                     ("some", dict(z_prior="gaussian", truncation_factor=-1.0, y_sampler="acending_some", radius="N/A")),
+                     ("all", dict(z_prior="gaussian", truncation_factor=-1.0, y_sampler="acending_all", radius="N/A")),
+                     ("fixed", dict(z_prior="gaussian", truncation_factor=-1.0, y_sampler=3, radius="N/A"))):
+        torch.manual_seed(2718)
+        np.random.seed(31)
+        zs, y, zs_eps = rsample.sample_zy(batch_size=16, z_dim=12, num_classes=7, device="cpu", **kw)
+        out[name + "_z"], out[name + "_y"] = zs.numpy(), y.numpy()
+        if zs_eps is not None:
+            out[name + "_zeps"] = zs_eps.numpy()
+    np.savez_compressed(os.path.join(HERE, "sampler.npz"), **out)
+    print("sampler", {k: v.shape for k, v in out.items()})
+
+
 def golden_metrics():
     rng = np.random.RandomState(0)
     out = {}
@@ -389,6 +412,14 @@ def golden_metrics():
     resizer = rresize.build_resizer("legacy", "InceptionV3_tf", 19)
     rs = np.stack([resizer(img) for img in q.transpose(0, 2, 3, 1)], 0)
     out["resize_legacy_19"] = rs
+    # "friendly" = PIL bilinear on float32 channels: up-scaling (8 -> 19) and anti-aliased down-scaling (20 -> 13)
+    fr = rresize.build_resizer("friendly", "InceptionV3_tf", 19)
+    out["resize_friendly_19"] = np.stack([fr(img) for img in q.transpose(0, 2, 3, 1)], 0)
+    x20 = torch.from_numpy(np.random.RandomState(5).uniform(-1.1, 1.1, size=(2, 3, 20, 20)).astype(np.float32))   # own stream: the draws below keep their values
+    q20 = rops.quantize_images(x20)
+    out["q20_in"] = x20.numpy()
+    fr13 = rresize.build_resizer("friendly", "InceptionV3_tf", 13)
+    out["resize_friendly_20to13"] = np.stack([fr13(img) for img in q20.transpose(0, 2, 3, 1)], 0)
     # FID / moments
     real = rng.randn(300, 24).astype(np.float64)
     fake = (rng.randn(280, 24) * 1.1 + 0.05).astype(np.float32)
@@ -451,3 +482,4 @@ if __name__ == "__main__":
     golden_gp("gp_resnet32_sn_c16_pd", "resnet", 16, True, "PD")
     golden_gp("gp_deep32_sn_c8_pd", "deep", 8, True, "PD")
     golden_deep_bench_shape()
+    golden_sampler()

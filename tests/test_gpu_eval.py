@@ -40,6 +40,32 @@ def test_quantize_is_bit_exact_and_resize_matches_legacy(golden_dir):
     assert float((colc[..., :27] - unf.bfloat16().float()).abs().max()) < 1e-2 and float(colc[..., 27:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("S_in", [32, 128, 256, 512])
+def test_friendly_resizer_matches_pil_f_mode_bilinear(golden_dir, S_in):
+    """post_resizer "friendly" (src/utils/resize.py:50-53,72-82): the device kernel against Pillow itself at the
+    evaluation size 299 (up-scaling from 32 / 128 / 256, anti-aliased down-scaling from 512) and against the reference's
+    golden at small sizes.  Same arithmetic (float64 taps and sums, float32 after each pass): agreement to float32
+    round-off of the 0..255 values (2e-5 absolute on the 255-scale, i.e. 1.6e-7 after normalisation x 2/255)."""
+    from PIL import Image
+    from sgb200 import kernels as K
+    dev = _cuda()
+    rs = np.random.RandomState(S_in)
+    u8 = rs.randint(0, 256, size=(2, 3, S_in, S_in)).astype(np.float32)
+    got, _ = K.quantize_resize_normalize(torch.from_numpy(u8).to(dev), 299, quantize=False, want_image=True, want_col=False,
+                                         resizer="friendly")
+    ref = np.stack([[np.asarray(Image.fromarray(u8[b, c], mode="F").resize((299, 299), resample=Image.BILINEAR)) for c in range(3)]
+                    for b in range(2)])
+    ref = (torch.from_numpy(ref) / 255.0 - 0.5) / 0.5
+    assert float((got.cpu() - ref).abs().max()) < 4e-7
+    if S_in == 32:
+        g = np.load(os.path.join(golden_dir, "metrics.npz"))
+        for key_in, key_out, S in (("q_in", "resize_friendly_19", 19), ("q20_in", "resize_friendly_20to13", 13)):
+            x = torch.from_numpy(g[key_in]).to(dev)
+            got, _ = K.quantize_resize_normalize(x, S, quantize=True, want_image=True, want_col=False, resizer="friendly")
+            ref = (torch.from_numpy(g[key_out].transpose(0, 3, 1, 2)) / 255.0 - 0.5) / 0.5
+            assert float((got.cpu() - ref).abs().max()) < 4e-7
+
+
 @pytest.mark.parametrize("stride,pad,mode", [(2, 0, 1), (1, 1, 0), (1, 1, 1)])
 def test_pool3x3_modes(stride, pad, mode):
     from sgb200 import kernels as K

@@ -130,6 +130,40 @@ def test_bn_act_fwd_bwd(mode, up2):
         assert rel_err(bd.grad, br.grad) < 1e-2
 
 
+def test_bn_dataparallel_mode_clamp_variant():
+    """The reference's DataParallel-mode SynchronizedBatchNorm (src/sync_batchnorm/batchnorm.py:158-175) normalises with
+    bias_var.clamp(eps) ** -0.5, not (var + eps) ** -0.5: with eps = 0.5 and channel variances on both sides of it the two
+    differ visibly; ops.BatchNorm2d(dp_sync_semantics=True) must give the former (output, input gradient, running stats)."""
+    from sgb200.utils import ops
+    dev = _cuda()
+    g = torch.Generator().manual_seed(8)
+    B, C, H, W = 4, 16, 8, 8
+    sd = torch.linspace(0.2, 2.0, C)
+    x = bfr(torch.randn(B, C, H, W, generator=g) * sd[None, :, None, None] + 0.1)
+    dy = bfr(torch.randn(B, C, H, W, generator=g))
+    eps = 0.5
+    xr = x.clone().double().requires_grad_(True)
+    n = B * H * W
+    s1, s2 = xr.sum((0, 2, 3)), (xr * xr).sum((0, 2, 3))
+    mean = s1 / n
+    sumvar = s2 - s1 * mean
+    inv = (sumvar / n).clamp(eps) ** -0.5
+    yr = (xr - mean[None, :, None, None]) * inv[None, :, None, None]
+    yr.backward(dy.double())
+    bn = ops.BatchNorm2d(C, eps=eps, momentum=0.1, affine=False).to(dev).train()
+    bn.dp_sync_semantics = True
+    xd = to_nhwc(x, dev).requires_grad_(True)
+    y = bn(xd)
+    y.backward(to_nhwc(dy, dev))
+    assert rel_err(y, yr) < 8e-3
+    assert float((sumvar / n).min()) < eps < float((sumvar / n).max())      # both regimes present
+    assert rel_err(xd.grad, xr.grad) < 2e-2          # incl. the clamped channels, whose variance term vanishes
+    np.testing.assert_allclose(bn.running_var.cpu().numpy(), (0.9 + 0.1 * sumvar.detach() / (n - 1)).numpy(), rtol=2e-3)
+    bn2 = ops.BatchNorm2d(C, eps=eps, momentum=0.1, affine=False).to(dev).train()
+    y2 = bn2(to_nhwc(x, dev))
+    assert rel_err(y2, yr) > 5e-2                                            # torch's (var + eps) is a different function here
+
+
 def test_self_attention_fwd_bwd_vs_oracle():
     from sgb200 import config as C
     from sgb200.utils import ops

@@ -262,3 +262,25 @@ def test_checkpoint_round_trip_in_reference_format(tmp_path, golden_dir):
     for a, b in zip(G2.state_dict().values(), G4.state_dict().values()):
         assert torch.equal(a, b)
     assert d_opt3.state_dict()["param_groups"][0]["lr"] == 2e-4 and len(d_opt3.state_dict()["state"]) == len(list(D3.parameters()))
+
+
+def test_sampler_rng_order_matches_reference_bit_for_bit(golden_dir):
+    """sample_zy (src/utils/sample.py:69-90): labels first, then z, on the same generator -- every branch reproduces the
+    reference's draws exactly (tests/golden/sampler.npz, from the unmodified reference)."""
+    import numpy as np
+    from sgb200.utils import sample
+    g = np.load(os.path.join(golden_dir, "sampler.npz"))
+    for name, kw in (("gauss", dict(z_prior="gaussian", truncation_factor=-1.0, y_sampler="totally_random", radius="N/A")),
+                     ("uniform", dict(z_prior="uniform", truncation_factor=-1.0, y_sampler="totally_random", radius="N/A")),
+                     ("eps", dict(z_prior="gaussian", truncation_factor=-1.0, y_sampler="totally_random", radius=0.5)),
+                     ("trunc", dict(z_prior="gaussian", truncation_factor=0.7, y_sampler="totally_random", radius="N/A")),
+                     ("some", dict(z_prior="gaussian", truncation_factor=-1.0, y_sampler="acending_some", radius="N/A")),
+                     ("all", dict(z_prior="gaussian", truncation_factor=-1.0, y_sampler="acending_all", radius="N/A")),
+                     ("fixed", dict(z_prior="gaussian", truncation_factor=-1.0, y_sampler=3, radius="N/A"))):
+        torch.manual_seed(2718)
+        np.random.seed(31)
+        zs, y, zs_eps = sample.sample_zy(batch_size=16, z_dim=12, num_classes=7, device="cpu", **kw)
+        assert np.array_equal(y.numpy(), g[name + "_y"]), name            # integer path: bit exact
+        assert np.array_equal(zs.numpy(), g[name + "_z"]), name           # same generator, same order: bit exact
+        if name + "_zeps" in g.files:
+            assert np.array_equal(zs_eps.numpy(), g[name + "_zeps"]), name

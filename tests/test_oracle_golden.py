@@ -87,6 +87,21 @@ def test_metrics_and_losses(golden_dir):
     assert np.array_equal(O.quantize_images(torch.from_numpy(g["q_in"])), g["q_out"])            # integer path: bit exact
     rs = O.resize_legacy(g["q_out"], 19).numpy()
     np.testing.assert_allclose(rs, g["resize_legacy_19"].transpose(0, 3, 1, 2), rtol=0, atol=1e-4)
+    # "friendly" = PIL 'F'-mode bilinear (reference golden): up-scaling 8 -> 19 and anti-aliased down-scaling 20 -> 13.
+    # float64 sums rounded to float32: the restatement may differ from Pillow's C loop by the summation order only (1 ulp)
+    fr = O.resize_friendly(g["q_out"], 19).numpy()
+    np.testing.assert_allclose(fr, g["resize_friendly_19"].transpose(0, 3, 1, 2), rtol=2e-7, atol=2e-5)
+    q20 = O.quantize_images(torch.from_numpy(g["q20_in"]))
+    fr13 = O.resize_friendly(q20, 13).numpy()
+    np.testing.assert_allclose(fr13, g["resize_friendly_20to13"].transpose(0, 3, 1, 2), rtol=2e-7, atol=2e-5)
+    # and directly against Pillow at the evaluation size (32 -> 299, 300 -> 299)
+    from PIL import Image
+    rs_ = np.random.RandomState(9)
+    for S in (32, 300):
+        ch = rs_.randint(0, 256, size=(S, S)).astype(np.float32)
+        ref = np.asarray(Image.fromarray(ch, mode="F").resize((299, 299), resample=Image.BILINEAR))
+        got = O.resize_friendly(ch[None, None], 299).numpy()[0, 0]
+        np.testing.assert_allclose(got, ref, rtol=2e-7, atol=2e-5)
     mu1, s1 = O.moments(g["feat_fake"])
     mu2, s2 = O.moments(g["feat_real"])
     np.testing.assert_allclose(O.frechet_distance(mu1, s1, mu2, s2), g["fid"], rtol=1e-9)
