@@ -265,6 +265,30 @@ int sgb_bn_tangent_bwd_apply(const void* x, int64_t x_cstride, const void* a, in
                              const float* sums, float count, int32_t use_batch_stats, void* dx, int64_t dx_cstride, void* da,
                              int64_t da_cstride, sgb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Evaluation metrics in fp64 on the device (csrc/metrics.cu).
+ * Replaces: fid.calculate_moments / np.mean + np.cov (src/metrics/fid.py:65-98) and prdc.compute_prdc's three
+ *   sklearn pairwise_distances matrices + argpartition (src/metrics/prdc.py:87-168).
+ * ------------------------------------------------------------------------------------------ */
+/* sum[D] += sum_r f[r], outer[D][D] (upper-triangular 64x64 blocks only) += sum_r f[r] f[r]^T for a batch of n fp32
+ * feature rows; sum / outer are caller-zeroed fp64 accumulators (the cross-rank reduction point of SURVEY 8e). */
+int sgb_feat_moments_accumulate(const float* feats, int32_t n, int32_t D, double* sum, double* outer, sgb_stream_t stream);
+/* mu = sum / n, sigma = (outer - n mu mu^T) / (n - 1) as a full symmetric matrix (np.cov(rowvar=False)). */
+int sgb_feat_moments_finalize(const double* sum, const double* outer, double n, int32_t D, double* mu, double* sigma,
+                              sgb_stream_t stream);
+/* radii[i] = distance from x_i to its nearest_k-th neighbour among the rows of x (self counted as the 0-th):
+ * prdc.compute_nearest_neighbour_distances (src/metrics/prdc.py:115-126).  x: fp64 [n][D]; sqnorm_ws: fp64 [n], receives
+ * the squared row norms (re-used by sgb_prdc_cross); nearest_k <= 7. */
+int sgb_prdc_radii(const double* x, int32_t n, int32_t D, int32_t nearest_k, double* sqnorm_ws, double* radii,
+                   sgb_stream_t stream);
+/* Real-to-fake distance tiles reduced on the fly (src/metrics/prdc.py:129-168):
+ *   col_count[j] = #{i : d(real_i, fake_j) < radii_real[i]}   -> precision = mean(col_count > 0), density = mean(col_count) / k
+ *   row_any[i]   = any_j d(real_i, fake_j) < radii_fake[j]    -> recall
+ *   row_cov[i]   = min_j d(real_i, fake_j) < radii_real[i]    -> coverage */
+int sgb_prdc_cross(const double* real, const double* real_sqnorm, const double* fake, const double* fake_sqnorm,
+                   const double* radii_real, const double* radii_fake, int32_t n_real, int32_t n_fake, int32_t D,
+                   int32_t* col_count, uint8_t* row_any, uint8_t* row_cov, sgb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

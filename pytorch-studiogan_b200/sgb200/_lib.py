@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsgb200.so")
 c_int = ctypes.c_int32
 c_i64 = ctypes.c_int64
 c_f = ctypes.c_float
+c_d = ctypes.c_double
 c_p = ctypes.c_void_p
 
 
@@ -98,6 +99,10 @@ SIGNATURES = {
     "sgb_gp_interpolate": (c_int, [c_p, c_p, c_p, c_p, c_int, c_i64, c_p]),
     "sgb_gp_sumsq": (c_int, [c_p, c_p, c_int, c_i64, c_p]),
     "sgb_gp_seed": (c_int, [c_p, c_p, c_p, c_int, c_i64, c_p]),
+    "sgb_feat_moments_accumulate": (c_int, [c_p, c_int, c_int, c_p, c_p, c_p]),
+    "sgb_feat_moments_finalize": (c_int, [c_p, c_p, c_d, c_int, c_p, c_p, c_p]),
+    "sgb_prdc_radii": (c_int, [c_p, c_int, c_int, c_int, c_p, c_p, c_p]),
+    "sgb_prdc_cross": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p, c_p, c_p]),
     "sgb_bn_tangent_bwd_reduce": (c_int, [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i64, c_int, c_p, c_p, c_p, c_p]),
     "sgb_bn_tangent_bwd_apply": (c_int, [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i64, c_int, c_p, c_p, c_p, c_p, c_f, c_int,
                                          c_p, c_i64, c_p, c_i64, c_p]),

@@ -10,7 +10,10 @@ from ..utils import losses, sample
 def generate_images_and_stack_features(generator, discriminator, eval_model, num_generate, y_sampler, batch_size, z_prior,
                                        truncation_factor, z_dim, num_classes, LOSS, RUN, MODEL, is_stylegan=False,
                                        generator_mapping=None, generator_synthesis=None, quantize=True, world_size=1, DDP=False,
-                                       device="cuda", logger=None, disable_tqdm=True):
+                                       device="cuda", logger=None, disable_tqdm=True, moments=None):
+    """``moments`` (metrics.fid.MomentsAccumulator, optional): every batch's features are also folded into the running
+    [sum f, sum f f^T]; only the rows that survive the reference's ``[:num_generate]`` truncation of the rank-major
+    gathered matrix are counted, so the statistics are those of exactly the same feature set."""
     eval_model.eval()
     feature_holder, prob_holder, fake_label_holder = [], [], []
     if device == 0 and logger is not None:
@@ -18,6 +21,11 @@ def generate_images_and_stack_features(generator, discriminator, eval_model, num
     num_batches = int(math.ceil(float(num_generate) / float(batch_size)))
     if DDP:
         num_batches = num_batches // world_size + 1
+    rank = 0
+    if DDP:
+        import torch.distributed as dist
+        rank = dist.get_rank()
+    first_row, done = rank * num_batches * batch_size, 0          # this rank's rows in the gathered (rank-major) matrix
     for _ in range(num_batches):
         fake_images, fake_labels, _, _, _, _, _ = sample.generate_images(
             z_prior=z_prior, truncation_factor=truncation_factor, batch_size=batch_size, z_dim=z_dim, num_classes=num_classes,
@@ -26,6 +34,10 @@ def generate_images_and_stack_features(generator, discriminator, eval_model, num
         with torch.no_grad():
             features, logits = eval_model.get_outputs(fake_images, quantize=quantize)
             probs = torch.nn.functional.softmax(logits, dim=1)
+        if moments is not None:
+            keep = max(0, min(features.shape[0], num_generate - (first_row + done)))
+            moments.update(features[:keep])
+            done += features.shape[0]
         feature_holder.append(features)
         prob_holder.append(probs)
         fake_label_holder.append(fake_labels)

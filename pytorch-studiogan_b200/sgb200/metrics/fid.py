@@ -26,8 +26,50 @@ def frechet_inception_distance(mu1, sigma1, mu2, sigma2, eps=1e-6):
     return diff.dot(diff) + np.trace(sigma1) + np.trace(sigma2) - 2 * np.trace(covmean)
 
 
+class MomentsAccumulator(object):
+    """Running [sum f, sum f f^T] in fp64 on the device (sgb_feat_moments_accumulate): features are folded in batch by batch
+    as the Inception pipeline produces them, the [N, 2048] matrix is never needed for FID, and under DDP the two
+    accumulators (33.5 MB) are all-reduced instead of gathering the features.  ``finalize`` returns the mean
+    and np.cov(rowvar=False) (src/metrics/fid.py:65-98)."""
+
+    def __init__(self, dim, device):
+        self.dim, self.n = dim, 0
+        self.sum = torch.zeros(dim, dtype=torch.float64, device=device)
+        self.outer = torch.zeros((dim, dim), dtype=torch.float64, device=device)
+
+    def update(self, feats):
+        from .. import _lib as L
+        f = feats.detach().to(torch.float32).contiguous()
+        assert f.dim() == 2 and f.shape[1] == self.dim
+        if f.shape[0] == 0:
+            return
+        L.call("sgb_feat_moments_accumulate", L.ptr(f), f.shape[0], self.dim, L.ptr(self.sum), L.ptr(self.outer), L.stream_ptr())
+        self.n += f.shape[0]
+
+    def all_reduce(self, group=None):
+        import torch.distributed as dist
+        n = torch.tensor([float(self.n)], dtype=torch.float64, device=self.sum.device)
+        for t in (self.sum, self.outer, n):
+            dist.all_reduce(t, group=group)
+        self.n = int(n.item())
+
+    def finalize(self):
+        from .. import _lib as L
+        mu = torch.empty_like(self.sum)
+        sigma = torch.empty_like(self.outer)
+        L.call("sgb_feat_moments_finalize", L.ptr(self.sum), L.ptr(self.outer), float(self.n), self.dim, L.ptr(mu), L.ptr(sigma),
+               L.stream_ptr())
+        return mu, sigma
+
+
 def calculate_moments(feats):
-    """mean and unbiased covariance (np.cov(rowvar=False)) of an [N, D] feature tensor, fp64 on its device."""
+    """mean and unbiased covariance (np.cov(rowvar=False)) of an [N, D] feature tensor, fp64 on its device: the moment
+    kernels on CUDA tensors (in row blocks of 4096), plain tensor algebra on the host (CPU tests / oracle comparisons)."""
+    if feats.is_cuda:
+        acc = MomentsAccumulator(feats.shape[1], feats.device)
+        for s in range(0, feats.shape[0], 4096):
+            acc.update(feats[s:s + 4096])
+        return acc.finalize()
     f = feats.to(torch.float64)
     n = f.shape[0]
     mu = f.mean(0)

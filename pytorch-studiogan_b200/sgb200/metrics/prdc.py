@@ -1,8 +1,9 @@
 """Improved precision / recall and density / coverage (reference ``src/metrics/prdc.py:129-168``) on the device.
 
 The reference materialises three N x N fp64 distance matrices on the host (20 GB each at N = 50 000).  Here distances are
-produced in row tiles ( |a|^2 + |b|^2 - 2 a.b in fp64 ), reduced immediately to what the four metrics need (k-th smallest
-per row, per-column "any"/count, per-row minimum), and never stored."""
+produced in tiles ( |a|^2 + |b|^2 - 2 a.b in fp64 ), reduced immediately to what the four metrics need (k-th smallest per
+row, per-column count, per-row any / minimum), and never stored: on CUDA tensors by the hand-written tile kernels of
+csrc/metrics.cu, on host tensors (CPU tests) by the same algebra in tensor ops."""
 import torch
 
 
@@ -26,9 +27,32 @@ def kth_nn_distances(x, k, tile=4096):
     return out
 
 
+def _compute_prdc_cuda(real, fake, nearest_k):
+    """The tile kernels of csrc/metrics.cu: two radii passes (real-real, fake-fake) and one real-fake pass, every distance
+    tile reduced in registers / shared memory; nothing of size N x N is ever written."""
+    from .. import _lib as L
+    real, fake = real.contiguous(), fake.contiguous()
+    nr, D = real.shape
+    nf = fake.shape[0]
+    dev = real.device
+    rn, fn = torch.empty(nr, dtype=torch.float64, device=dev), torch.empty(nf, dtype=torch.float64, device=dev)
+    r_real, r_fake = torch.empty_like(rn), torch.empty_like(fn)
+    L.call("sgb_prdc_radii", L.ptr(real), nr, D, nearest_k, L.ptr(rn), L.ptr(r_real), L.stream_ptr())
+    L.call("sgb_prdc_radii", L.ptr(fake), nf, D, nearest_k, L.ptr(fn), L.ptr(r_fake), L.stream_ptr())
+    col_count = torch.empty(nf, dtype=torch.int32, device=dev)
+    row_any = torch.empty(nr, dtype=torch.uint8, device=dev)
+    row_cov = torch.empty(nr, dtype=torch.uint8, device=dev)
+    L.call("sgb_prdc_cross", L.ptr(real), L.ptr(rn), L.ptr(fake), L.ptr(fn), L.ptr(r_real), L.ptr(r_fake), nr, nf, D,
+           L.ptr(col_count), L.ptr(row_any), L.ptr(row_cov), L.stream_ptr())
+    return dict(precision=float((col_count > 0).double().mean()), recall=float(row_any.double().mean()),
+                density=float(col_count.double().mean() / float(nearest_k)), coverage=float(row_cov.double().mean()))
+
+
 def compute_prdc(real_features, fake_features, nearest_k, tile=4096):
     real = torch.as_tensor(real_features, dtype=torch.float64)
     fake = torch.as_tensor(fake_features, dtype=torch.float64, device=real.device)
+    if real.is_cuda and nearest_k + 1 <= 8:
+        return _compute_prdc_cuda(real, fake, nearest_k)
     r_real = kth_nn_distances(real, nearest_k, tile)
     r_fake = kth_nn_distances(fake, nearest_k, tile)
     real2, fake2 = (real * real).sum(1), (fake * fake).sum(1)

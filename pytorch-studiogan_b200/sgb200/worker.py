@@ -253,18 +253,25 @@ def _evaluate(self, step, metrics, writing=True, training=False):
         elif getattr(self.RUN, "batch_statistics", False):
             generator.apply(misc.set_bn_trainable)
             generator.apply(misc.untrack_bn_statistics)
+        # FID statistics are accumulated on the fly ([sum f, sum f f^T], fp64) and, under DDP, all-reduced (33.5 MB) --
+        # the gathered [N, 2048] feature matrix is only needed by PRDC
+        moments = fid.MomentsAccumulator(2048, self.local_rank) if "fid" in metrics else None
         fake_feats, fake_probs, fake_labels = features.generate_images_and_stack_features(
             generator=generator, discriminator=self.Dis, eval_model=self.eval_model, num_generate=num_eval,
             y_sampler="totally_random", batch_size=self.OPTIMIZATION.batch_size, z_prior=self.MODEL.z_prior,
             truncation_factor=self.RUN.truncation_factor, z_dim=self.MODEL.z_dim, num_classes=self.DATA.num_classes, LOSS=self.LOSS,
             RUN=self.RUN, MODEL=self.MODEL, quantize=True, world_size=getattr(self.OPTIMIZATION, "world_size", 1), DDP=self.DDP,
-            device=self.local_rank, logger=self.logger)
+            device=self.local_rank, logger=self.logger, moments=moments)
         if "is" in metrics:
             kl_score, kl_std, top1, top5 = ins.eval_features(probs=fake_probs, labels=fake_labels, data_loader=self.eval_dataloader,
                                                              num_features=num_eval, split=num_splits, is_acc=is_acc)
             metric_dict.update({"IS": float(kl_score), "Top1_acc": top1, "Top5_acc": top5})
         if "fid" in metrics:
-            fid_score, m1, c1 = fid.calculate_fid(fake_feats, self.mu, self.sigma, num_eval)
+            if self.DDP:
+                moments.all_reduce(getattr(self.Gen, "sgb_group", None))
+            m1, c1 = moments.finalize()
+            fid_score = fid.frechet_distance_device(m1, c1, torch.as_tensor(self.mu, device=m1.device),
+                                                    torch.as_tensor(self.sigma, device=m1.device))
             if self.best_fid is None or fid_score <= self.best_fid:
                 self.best_fid, self.best_step, is_best = fid_score, step, True
             metric_dict.update({"FID": fid_score})

@@ -183,3 +183,49 @@ def test_worker_evaluate_runs_end_to_end():
     r = w.last_metrics
     assert best is True and np.isfinite(r["FID"]) and r["FID"] > 0 and np.isfinite(r["IS"]) and 0.0 <= r["Coverage"] <= 1.0
     assert Gen.training and Dis.training                       # make_GAN_trainable restored the modes
+
+
+def test_feature_moments_kernel_matches_numpy_cov():
+    """sgb_feat_moments_accumulate / finalize (fp64) against np.mean / np.cov(rowvar=False) (src/metrics/fid.py:65-98) on
+    features folded in over uneven batches; D = 200 exercises ragged 64-wide blocks, D = 2048 the evaluation size."""
+    from sgb200.metrics import fid
+    dev = _cuda()
+    rs = np.random.RandomState(3)
+    for D, sizes in ((200, (37, 64, 1, 130)), (2048, (256, 100))):
+        f = (rs.randn(sum(sizes), D) * (1 + rs.rand(D)) + rs.randn(D)).astype(np.float32)
+        acc = fid.MomentsAccumulator(D, dev)
+        s = 0
+        for n in sizes:
+            acc.update(torch.from_numpy(f[s:s + n]).to(dev))
+            s += n
+        mu, sigma = acc.finalize()
+        f64 = f.astype(np.float64)
+        np.testing.assert_allclose(mu.cpu().numpy(), f64.mean(0), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(sigma.cpu().numpy(), np.cov(f64, rowvar=False), rtol=1e-9, atol=1e-10)
+        mu2, sigma2 = fid.calculate_moments(torch.from_numpy(f).to(dev))
+        assert torch.equal(mu2, mu) and torch.equal(sigma2, sigma)
+
+
+def test_prdc_tile_kernels_match_reference_golden_and_host_path(golden_dir):
+    """csrc/metrics.cu PRDC kernels (radii + cross reductions, fp64 distance tiles never stored) against the reference's
+    compute_prdc golden (tests/golden/metrics.npz: sklearn pairwise_distances + argpartition) -- the four values are
+    ratios of integer counts and must agree exactly -- and against the host tensor path on a larger ragged problem."""
+    from sgb200.metrics import prdc
+    dev = _cuda()
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    real, fake = torch.from_numpy(g["feat_real"][:200]), torch.from_numpy(g["feat_fake"][:180].astype(np.float64))
+    got = prdc.compute_prdc(real.to(dev), fake.to(dev), 5)
+    np.testing.assert_allclose([got["precision"], got["recall"], got["density"], got["coverage"]], g["prdc"], rtol=1e-12, atol=0)
+    rs = np.random.RandomState(4)
+    real = torch.from_numpy(rs.randn(333, 70))
+    fake = torch.from_numpy(rs.randn(401, 70) * 1.05 + 0.1)
+    ref = prdc.compute_prdc(real, fake, 3)
+    got = prdc.compute_prdc(real.to(dev), fake.to(dev), 3)
+    for k in ref:
+        assert abs(ref[k] - got[k]) < 1e-12, (k, ref[k], got[k])
+    # the radii themselves
+    from sgb200 import _lib as L
+    x = real.to(dev).contiguous()
+    rn, rad = torch.empty(333, dtype=torch.float64, device=dev), torch.empty(333, dtype=torch.float64, device=dev)
+    L.call("sgb_prdc_radii", L.ptr(x), 333, 70, 3, L.ptr(rn), L.ptr(rad), L.stream_ptr())
+    np.testing.assert_allclose(rad.cpu().numpy(), prdc.kth_nn_distances(real, 3).numpy(), rtol=1e-9, atol=1e-9)
