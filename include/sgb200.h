@@ -223,6 +223,10 @@ int sgb_col27_bwd(const void* dcol, float* dimg, int32_t B, int32_t H, int32_t W
  * (src/metrics/inception_net.py:86,91,153,178,208,241). */
 int sgb_pool3x3(const void* x, int64_t xs, void* y, int64_t ys, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride,
                 int32_t pad, int32_t mode, sgb_stream_t stream);
+/* out[B][2H][2W][C]: out[b,2h,2w,:] = x[b,h,w,:], zero elsewhere (NHWC bf16): the adjoint of a stride-2 sub-sampling.  With
+ * it DCGAN's ConvTranspose2d / Conv2d (kernel 4, stride 2, padding 1; src/models/deep_conv.py:20,140) run on the stride-1
+ * conv engine: conv_transpose(x) = conv_same_4x4(zero_stuff(x)), and the strided conv's gradients see zero_stuff(dy). */
+int sgb_zero_stuff2(const void* x, int64_t xs, void* y, int64_t ys, int32_t B, int32_t H, int32_t W, int32_t C, sgb_stream_t stream);
 /* uint8 quantisation of generated images, bit-exact with ops.quantize_images (src/utils/ops.py:251-255). */
 int sgb_quantize_u8(const float* img, uint8_t* out, int64_t n, sgb_stream_t stream);
 /* Fused evaluation pre-processing on the device (quantise -> bilinear resize to SxS -> /255 -> (x-0.5)/0.5;

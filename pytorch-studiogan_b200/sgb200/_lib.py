@@ -90,6 +90,7 @@ SIGNATURES = {
     "sgb_col27": (c_int, [c_p, c_int, c_i64, c_p, c_int, c_int, c_int, c_p]),
     "sgb_col27_bwd": (c_int, [c_p, c_p, c_int, c_int, c_int, c_p]),
     "sgb_pool3x3": (c_int, [c_p, c_i64, c_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "sgb_zero_stuff2": (c_int, [c_p, c_i64, c_p, c_i64, c_int, c_int, c_int, c_int, c_p]),
     "sgb_quantize_u8": (c_int, [c_p, c_p, c_i64, c_p]),
     "sgb_quantize_resize_normalize": (c_int, [c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_int, c_p]),
     "sgb_cast_f32_to_bf16": (c_int, [c_p, c_p, c_i64, c_f, c_p]),

@@ -172,7 +172,7 @@ class ConvFn(TFunction):
         res = residual
         y = K.conv_fprop(x, wf, Cout_p, KH, KW, pad, pad, bias=bias if Cout_p == Cout else _pad_bias(bias, Cout_p),
                          residual=res, res_up2=cfg.get("res_up2", False), relu=cfg.get("relu", False),
-                         out_fp32=cfg.get("out_fp32", False))
+                         out_fp32=cfg.get("out_fp32", False), stride=cfg.get("stride", 1))
         if need_dw and sn is not None and cache is None:
             u_saved, v_saved = u.clone(), v.clone()
         ctx.cfg = cfg
@@ -191,6 +191,9 @@ class ConvFn(TFunction):
         dz = _grad_bf16(dy)
         if cfg.get("relu", False) and not cfg.get("premasked", False):
             dz = K.axpby(dz, mask=y)
+        if cfg.get("stride", 1) == 2:
+            # y = conv_same(x)[::2, ::2] (the engine's out_sub store): the gradient on the stride-1 grid is dz zero-stuffed
+            dz = K.zero_stuff2(dz)
         dx = dW = dbias = dres = None
         if ctx.needs_input_grad[0]:
             mask = x if cfg.get("mask_input", False) else None
@@ -236,6 +239,40 @@ class ConvFn(TFunction):
         if t is not None and cfg.get("relu", False):
             t = MaskFn.apply(t, out)
         return t
+
+
+class ConvTranspose4x4s2Fn(TFunction):
+    """nn.ConvTranspose2d(kernel 4, stride 2, padding 1) (DCGAN generator, src/models/deep_conv.py:20) on the stride-1 engine:
+       y = conv_same_4x4(zero_stuff(x), W~) with W~[co][ci][kh][kw] = W[ci][co][3-kh][3-kw] and tap offsets -2..+1.
+    Reading the [Cin, Cout, 4, 4] module weight as a conv weight V ("Cout" = Cin), the DGRAD pack of V is exactly the fprop
+    pack of W~ and the FPROP pack of V its dgrad pack, so no new pack kernel is needed.  Backward: dx = the even positions of
+    the 4x4 dgrad (the engine's out_sub store); dW~ from the weight-gradient kernel on (zero_stuff(x), dy), re-indexed to W."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        Cin, Cout = weight.shape[0], weight.shape[1]
+        assert tuple(weight.shape[2:]) == (4, 4)
+        xu = K.zero_stuff2(x)
+        v_f, v_d = K.weight_pack(weight, None, Cin, Cout, 16, True, True)      # V = weight as [rows = Cin][cols = Cout][16]
+        y = K.conv_fprop(xu, v_d, Cout, 4, 4, 2, 2, bias=bias)
+        ctx.dims = (Cin, Cout)
+        ctx.save_for_backward(xu, v_f)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xu, v_f = ctx.saved_tensors
+        Cin, Cout = ctx.dims
+        dz = _grad_bf16(dy)
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = K.conv_fprop(dz, v_f, Cin, 4, 4, 1, 1, stride=2)
+        if ctx.needs_input_grad[1] and not SKIP_PARAM_GRADS:
+            G, db = K.conv_wgrad(xu, dz, 4, 4, 2, 2, want_dbias=ctx.needs_input_grad[2])     # dW~ as [Cout][tap][Cin]
+            dW = G.flip(1).permute(2, 0, 1).reshape(Cin, Cout, 4, 4).contiguous()            # dW[ci][co][t] = dW~[co][15 - t][ci]
+        if ctx.needs_input_grad[2] and db is None and not SKIP_PARAM_GRADS:
+            db = K.bn_stats(dz)[0][:Cout]
+        return dx, dW, db
 
 
 class MaskFn(TFunction):

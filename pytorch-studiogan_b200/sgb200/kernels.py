@@ -333,6 +333,14 @@ def col27_bwd(dcol):
     return dimg
 
 
+def zero_stuff2(x):
+    """[B, C, H, W] -> [B, C, 2H, 2W] with x at the even positions and zeros elsewhere (adjoint of ``[::2, ::2]``)."""
+    B, C, H, W, xs = geom(x)
+    y = empty_nhwc(B, C, 2 * H, 2 * W, x.device)
+    L.call("sgb_zero_stuff2", L.ptr(x), xs, L.ptr(y), geom(y)[4], B, H, W, C, _s(), nbytes=_nb(x, y))
+    return y
+
+
 def pool3x3(x, stride, pad, mode, out=None):
     """Inception 3x3 pooling; mode 0 = average (count_include_pad=False), 1 = max."""
     B, C, H, W, xs = geom(x)

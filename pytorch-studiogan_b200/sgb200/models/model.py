@@ -15,7 +15,7 @@ import torch.distributed as dist
 from ..utils import ops
 from ..utils.ema import Ema
 
-BACKBONES = ("big_resnet_deep_legacy", "big_resnet_deep_studiogan", "big_resnet", "resnet")
+BACKBONES = ("big_resnet_deep_legacy", "big_resnet_deep_studiogan", "big_resnet", "resnet", "deep_conv")
 
 
 def load_generator_discriminator(DATA, OPTIMIZATION, MODEL, STYLEGAN, MODULES, RUN, device, logger):

@@ -42,8 +42,10 @@ class _ConvBase(nn.Conv2d):
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True):
         super().__init__(in_channels, out_channels, kernel_size, stride=stride, padding=padding, dilation=dilation,
                          groups=groups, bias=bias)
-        if self.stride != (1, 1) or self.dilation != (1, 1) or self.groups != 1 or self.padding[0] != self.padding[1]:
-            raise NotImplementedError("sgb200 conv engine: stride-1, dilation-1, groups-1 square-padded convolutions only")
+        strided = self.stride == (2, 2) and self.kernel_size == (4, 4) and self.padding == (1, 1)     # DCGAN's down-sampling conv
+        if (self.stride != (1, 1) and not strided) or self.dilation != (1, 1) or self.groups != 1 or self.padding[0] != self.padding[1]:
+            raise NotImplementedError("sgb200 conv engine: stride-1 (or 4x4 / stride-2 / pad-1), dilation-1, groups-1 square-padded "
+                                      "convolutions only")
         if self.spectral:
             _apply_spectral_norm(self)
 
@@ -51,7 +53,7 @@ class _ConvBase(nn.Conv2d):
         if self.in_channels == 3 and self.kernel_size == (3, 3) and self.padding == (1, 1):
             return self._forward_image(x, residual, relu, premasked)
         cfg = {"KH": self.kernel_size[0], "KW": self.kernel_size[1], "pad": self.padding[0], "relu": relu,
-               "premasked": premasked, "mask_input": mask_input, "res_up2": res_up2,
+               "premasked": premasked, "mask_input": mask_input, "res_up2": res_up2, "stride": self.stride[0],
                "sn": getattr(self, "_sn", None), "do_power_iteration": self.training,
                "sn_cache": getattr(self, "_sn_cache", None), "sn_pass": getattr(self, "_sn_pass", None)}
         return A.ConvFn.call(x, _w(self), self.bias, residual, cfg)
@@ -161,11 +163,27 @@ def sn_embedding(num_embeddings, embedding_dim):
     return SNEmbedding(num_embeddings, embedding_dim)
 
 
-def deconv2d(*args, **kwargs):
-    raise NotImplementedError("ConvTranspose2d (DCGAN generator, config 1) is the CPU-only oracle case; no sm_100a kernel")
+class ConvTranspose2d(nn.ConvTranspose2d):
+    """nn.ConvTranspose2d(kernel 4, stride 2, padding 1) of the DCGAN generator on the stride-1 conv engine
+    (autograd_ops.ConvTranspose4x4s2Fn)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=2, padding=0, dilation=1, groups=1, bias=True):
+        super().__init__(in_channels, out_channels, kernel_size, stride=stride, padding=padding, dilation=dilation, groups=groups,
+                         bias=bias)
+        if self.kernel_size != (4, 4) or self.stride != (2, 2) or self.padding != (1, 1) or self.dilation != (1, 1) or \
+                self.groups != 1 or self.output_padding != (0, 0):
+            raise NotImplementedError("sgb200: transposed convolution with kernel 4 / stride 2 / padding 1 only (DCGAN)")
+
+    def forward(self, x):
+        return A.ConvTranspose4x4s2Fn.call(x, self.weight, self.bias)
 
 
-sndeconv2d = deconv2d
+def deconv2d(in_channels, out_channels, kernel_size, stride=2, padding=0, dilation=1, groups=1, bias=True):
+    return ConvTranspose2d(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias)
+
+
+def sndeconv2d(*args, **kwargs):
+    raise NotImplementedError("spectrally-normalised ConvTranspose2d (dim = 1 power iteration) is not on any BASELINE config")
 
 
 class BatchNorm2d(nn.BatchNorm2d):

@@ -196,3 +196,103 @@ def test_two_ranks_reproduce_one_rank_on_the_global_batch():
     assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-2000:]
     out = json.loads(lines[-1][len("MULTIRANK_CHECK "):])
     assert out["ok"], out
+
+
+# ------------------------------------------------------------------------------------------------ DCGAN (BASELINE config 1)
+def test_dcgan_layers_conv_transpose_and_strided_conv():
+    """ConvTranspose2d / Conv2d with kernel 4, stride 2, padding 1 (src/models/deep_conv.py:20,140) through the stride-1
+    engine identities of csrc/resample.cu, forward and every gradient, against torch on the CPU."""
+    from sgb200.utils import ops
+    dev = _cuda()
+    g = torch.Generator().manual_seed(21)
+    # transposed convolution 64 -> 32, 8x8 -> 16x16
+    x = bfr(torch.randn(3, 64, 8, 8, generator=g))
+    ct = ops.deconv2d(64, 32, 4, 2, 1)
+    with torch.no_grad():
+        ct.weight.copy_(torch.randn(64, 32, 4, 4, generator=g) * 0.05)
+        ct.bias.copy_(torch.randn(32, generator=g) * 0.1)
+    dy = bfr(torch.randn(3, 32, 16, 16, generator=g))
+    xr = x.clone().requires_grad_(True)
+    wr, br = ct.weight.detach().clone().requires_grad_(True), ct.bias.detach().clone().requires_grad_(True)
+    yr = F.conv_transpose2d(xr, bfr(wr.detach()) + (wr - wr.detach()), br, stride=2, padding=1)
+    yr.backward(dy)
+    ct = ct.to(dev)
+    xd = to_nhwc(x, dev).requires_grad_(True)
+    y = ct(xd)
+    y.backward(to_nhwc(dy, dev))
+    assert rel_err(y, yr) < 8e-3 and rel_err(xd.grad, xr.grad) < 8e-3
+    assert rel_err(ct.weight.grad, wr.grad) < 2e-3 and rel_err(ct.bias.grad, br.grad) < 2e-3
+    # strided convolution 32 -> 48, 16x16 -> 8x8
+    x = bfr(torch.randn(3, 32, 16, 16, generator=g))
+    cv = ops.conv2d(32, 48, 4, 2, 1)
+    with torch.no_grad():
+        cv.weight.copy_(torch.randn(48, 32, 4, 4, generator=g) * 0.05)
+        cv.bias.copy_(torch.randn(48, generator=g) * 0.1)
+    dy = bfr(torch.randn(3, 48, 8, 8, generator=g))
+    xr = x.clone().requires_grad_(True)
+    wr, br = cv.weight.detach().clone().requires_grad_(True), cv.bias.detach().clone().requires_grad_(True)
+    yr = F.conv2d(xr, bfr(wr.detach()) + (wr - wr.detach()), br, stride=2, padding=1)
+    yr.backward(dy)
+    cv = cv.to(dev)
+    xd = to_nhwc(x, dev).requires_grad_(True)
+    y = cv(xd)
+    assert y.shape == yr.shape
+    y.backward(to_nhwc(dy, dev))
+    assert rel_err(y, yr) < 8e-3 and rel_err(xd.grad, xr.grad) < 8e-3
+    assert rel_err(cv.weight.grad, wr.grad) < 2e-3 and rel_err(cv.bias.grad, br.grad) < 2e-3
+
+
+def test_dcgan_config1_d_and_g_phase_vs_reference_golden(golden_dir):
+    """BASELINE config 1 as a product path: models.deep_conv on the kernel set against the reference's DCGAN golden
+    (tests/golden/dcgan32.npz; weights regenerated from the seed on both sides).  Tolerances of the 32x32 goldens: images /
+    logits 4e-2 relative L2, losses 5e-2, BatchNorm running statistics 1e-2, discriminator-phase gradient norms 1e-1."""
+    import json
+    import os
+    from oracle import studiogan_oracle as O
+    from sgb200 import config as C
+    from sgb200.models import deep_conv
+    from sgb200.utils import losses
+    from test_gpu_parity import l2_err
+    dev = _cuda()
+    g = np.load(os.path.join(golden_dir, "dcgan32.npz"))
+    M = C.make_modules(False, False, "W/O", "deep_conv")
+    MODEL = C._Section(info_type="N/A", g_info_injection="N/A")
+    G = deep_conv.Generator(z_dim=16, g_shared_dim="N/A", img_size=32, g_conv_dim="N/A", apply_attn=False, attn_g_loc=[], g_cond_mtd="W/O",
+                            num_classes=10, g_init="ortho", g_depth="N/A", mixed_precision=False, MODULES=M, MODEL=MODEL)
+    D = deep_conv.Discriminator(img_size=32, d_conv_dim="N/A", apply_d_sn=False, apply_attn=False, attn_d_loc=[], d_cond_mtd="W/O",
+                                aux_cls_type="W/O", d_embed_dim="N/A", normalize_d_embed=False, num_classes=10, d_init="ortho",
+                                d_depth="N/A", mixed_precision=False, MODULES=M, MODEL=MODEL)
+    G.load_state_dict(O.seeded_state(json.loads(str(g["keys_g"])), 101), strict=True)
+    D.load_state_dict(O.seeded_state(json.loads(str(g["keys_d"])), 202), strict=True)
+    G, D = G.to(dev).train(), D.to(dev).train()
+    z, y, real = torch.from_numpy(g["z"]).to(dev), torch.from_numpy(g["y"]).to(dev), torch.from_numpy(g["real"]).to(dev)
+    for p in G.parameters():
+        p.requires_grad_(False)
+    fake = G(z, y)
+    assert l2_err(fake, torch.from_numpy(g["fake"])) < 4e-2
+    rd, fd = D(real, y), D(fake.detach(), y)
+    assert l2_err(rd["adv_output"], torch.from_numpy(g["adv_real"])) < 4e-2
+    assert l2_err(fd["adv_output"], torch.from_numpy(g["adv_fake"])) < 4e-2
+    d_loss = losses.d_vanilla(rd["adv_output"], fd["adv_output"])
+    d_loss.backward()
+    assert abs(float(d_loss) - float(g["d_loss"])) < 5e-2 * abs(float(g["d_loss"]))
+    gmax = max(float(g[k]) for k in g.files if k.startswith("Dgnorm/"))
+    for n, p in D.named_parameters():
+        assert abs(float(p.grad.norm()) - float(g["Dgnorm/" + n])) < 1e-1 * float(g["Dgnorm/" + n]) + 2e-3 * gmax, n
+    for n, b in list(G.named_buffers()) + list(D.named_buffers()):
+        key = ("G1/" if any(b is bb for bb in G.buffers()) else "D1/") + n
+        if "running_" in n:
+            assert rel_err(b, torch.from_numpy(g[key])) < 1e-2, key
+    D.zero_grad(set_to_none=True)
+    for p in G.parameters():
+        p.requires_grad_(True)
+    for p in D.parameters():
+        p.requires_grad_(False)
+    fake2 = G(z, y)
+    assert l2_err(fake2, torch.from_numpy(g["fake2"])) < 4e-2
+    g_loss = losses.g_vanilla(D(fake2, y)["adv_output"])
+    g_loss.backward()
+    assert abs(float(g_loss) - float(g["g_loss"])) < 5e-2 * abs(float(g["g_loss"]))
+    gmax = max(float(g[k]) for k in g.files if k.startswith("Ggnorm/"))
+    for n, p in G.named_parameters():
+        assert abs(float(p.grad.norm()) - float(g["Ggnorm/" + n])) < 0.3 * float(g["Ggnorm/" + n]) + 1e-2 * gmax, n

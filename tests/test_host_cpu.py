@@ -284,3 +284,22 @@ def test_sampler_rng_order_matches_reference_bit_for_bit(golden_dir):
         assert np.array_equal(zs.numpy(), g[name + "_z"]), name           # same generator, same order: bit exact
         if name + "_zeps" in g.files:
             assert np.array_equal(zs_eps.numpy(), g[name + "_zeps"]), name
+
+
+def test_dcgan_state_dict_keys_match_reference(golden_dir):
+    """models.deep_conv (BASELINE config 1): state_dict keys and shapes of generator / discriminator equal the reference's
+    (recorded in tests/golden/dcgan32.npz by the generator script), so reference DCGAN checkpoints load strictly."""
+    import json
+    import numpy as np
+    from sgb200 import config as C
+    from sgb200.models import deep_conv
+    g = np.load(os.path.join(golden_dir, "dcgan32.npz"))
+    M = C.make_modules(False, False, "W/O", "deep_conv")
+    MODEL = C._Section(info_type="N/A", g_info_injection="N/A")
+    G = deep_conv.Generator(z_dim=16, g_shared_dim="N/A", img_size=32, g_conv_dim="N/A", apply_attn=False, attn_g_loc=[], g_cond_mtd="W/O",
+                            num_classes=10, g_init="ortho", g_depth="N/A", mixed_precision=False, MODULES=M, MODEL=MODEL)
+    D = deep_conv.Discriminator(img_size=32, d_conv_dim="N/A", apply_d_sn=False, apply_attn=False, attn_d_loc=[], d_cond_mtd="W/O",
+                                aux_cls_type="W/O", d_embed_dim="N/A", normalize_d_embed=False, num_classes=10, d_init="ortho",
+                                d_depth="N/A", mixed_precision=False, MODULES=M, MODEL=MODEL)
+    assert [[k, list(v.shape)] for k, v in G.state_dict().items()] == json.loads(str(g["keys_g"]))
+    assert [[k, list(v.shape)] for k, v in D.state_dict().items()] == json.loads(str(g["keys_d"]))
