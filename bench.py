@@ -414,13 +414,23 @@ def measure(args, rank, world, device, config_path, steps, warmup, want_e2e, wan
             _lib.PROFILE["enabled"] = False
             res["prof"] = {"error": repr(ex)}
     if want_e2e:
-        host_loader = SyntheticBasketLoader(per_rank, n_items, S, cfgs.DATA.num_classes, 200 + rank, device=None)
+        # the product data path (sgb200/data_util.py): a uint8 NHWC dataset in host memory (synthetic, 3 baskets), baskets gathered
+        # into pinned staging buffers, H2D on a side stream, flip + ToTensor + Normalize on the device; both losses read back
+        from sgb200 import data_util
+        rs = np.random.RandomState(200 + rank)
+        basket = per_rank * n_items
+        ds = data_util.Dataset_.from_arrays(rs.randint(0, 256, size=(3 * basket, S, S, 3), dtype=np.uint8),
+                                            rs.randint(0, cfgs.DATA.num_classes, size=3 * basket), random_flip=True)
+        host_loader = data_util.DeviceBasketLoader(ds, basket, device, shuffle=True, seed=200 + rank)
         worker.train_dataloader, worker.train_iter = host_loader, iter(host_loader)
         run_steps(worker, 1, True)
         ms_e2e, _ = timed(worker, steps, world, True)
         res["e2e"] = {"value": global_batch * opt.acml_steps / (ms_e2e * 1e-3), "unit": "img/s",
-                      "h2d_bytes_per_step": world * per_rank * n_items * (3 * S * S * 4 + 8), "d2h_bytes_per_step": 8 * world,
-                      "ms_per_step": ms_e2e}
+                      "h2d_bytes_per_step": world * host_loader.h2d_bytes, "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e2e,
+                      "input": "uint8 NHWC baskets from pinned host memory (%d B/step/rank), device-side flip + normalise" % host_loader.h2d_bytes}
+        worker.train_dataloader = worker.train_iter = None
+        host_loader.close()
+        del host_loader, ds
     return res
 
 

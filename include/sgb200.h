@@ -236,6 +236,10 @@ int sgb_quantize_u8(const float* img, uint8_t* out, int64_t n, sgb_stream_t stre
  * out_img (optional): NCHW fp32 [B,3,S,S]; out_col (optional): [B,So,So,32] bf16 stride-2 valid 3x3 patches, So=(S-3)/2+1. */
 int sgb_quantize_resize_normalize(const float* img, int32_t quantize, int32_t B, int32_t H, int32_t W, int32_t S, float* out_img,
                                   void* out_col, int32_t resizer, sgb_stream_t stream);
+/* Data path: uint8 NHWC [B,H,W,3] (HDF5 "imgs" / decoded folders, src/data_util.py:59-142, src/utils/hdf5.py) -> NCHW fp32 in
+ * [-1,1], i.e. RandomHorizontalFlip (flip[b] != 0; flip may be NULL) + ToTensor + Normalize(0.5, 0.5) of the reference's
+ * per-sample transform chain, bit-identical, on the device. */
+int sgb_u8_to_img(const uint8_t* u8, const uint8_t* flip, float* img, int32_t B, int32_t H, int32_t W, sgb_stream_t stream);
 int sgb_cast_f32_to_bf16(const float* in, void* out, int64_t n, float scale, sgb_stream_t stream);
 int sgb_cast_bf16_to_f32(const void* in, float* out, int64_t n, sgb_stream_t stream);
 

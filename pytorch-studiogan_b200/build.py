@@ -63,10 +63,12 @@ def build(force=False, selftest=False):
         objs = list(ex.map(_compile, srcs))
     newest = max(os.path.getmtime(o) for o in objs)
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
-        cmd = [NVCC, "-shared", "-cudart", "static", "-o", LIB] + objs
+        tmp = os.path.join(OBJ, "libsgb200.so.link")          # link aside, then rename: the in-tree library is replaced atomically
+        cmd = [NVCC, "-shared", "-cudart", "static", "-o", tmp] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+        os.replace(tmp, LIB)
     if selftest:
         cmd = [NVCC] + FLAGS + [os.path.join(CSRC, "selftest.cu"), "-o", SELFTEST, "-L" + LIBDIR, "-lsgb200",
                                 "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../sgb200/lib"]

@@ -176,12 +176,12 @@ __device__ __forceinline__ bool epi_use_tma(const EpiArgs& p, int BN) {
 __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtensorMap* tmY, uint32_t t_row, int BN, int n0,
                                                   int c1, int c2, int c3, bool valid, long long pix, long long rpix, float alpha,
                                                   uint32_t stage, int team, int row, bool leader, int chunk_stride = 2,
-                                                  const EpiAux* aux = nullptr, uint32_t* sbuf = nullptr) {
+                                                  const EpiAux* aux = nullptr, uint32_t* sbuf = nullptr, int nbuf = 2) {
   const bool res_pre = p.residual != nullptr && !p.res_after;
   const bool res_post = p.residual != nullptr && p.res_after;
   const float rs = p.res_scale;
-  // sbuf != nullptr: the team owns TWO staging tiles (stage, stage + 16 KiB) used alternately, so a chunk only waits for the
-  // store issued two chunks ago -- the latency of the previous tensor store is off the critical path.
+  // sbuf != nullptr: the team owns ``nbuf`` (2..4) staging tiles used round-robin, so a chunk only waits for the store issued
+  // nbuf chunks ago -- the latency of the previous tensor stores is off the critical path and more bytes are in flight.
   const uint32_t sw = (uint32_t)(row & 7);
   const int aux_kind = aux ? aux->kind : 0;                       // 1: residual tile via TMA, 2: mask tile via TMA
   const uint32_t arow_addr = aux ? aux->stage + (uint32_t)aux->arow * 128u : 0u;
@@ -189,12 +189,15 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
   for (int cc = (chunk_stride == 2 ? team : 0); cc * 64 < BN; cc += chunk_stride) {
     const int nbase = n0 + cc * 64;
     if (nbase >= p.Cout) break;
-    const uint32_t stage_cur = stage + (sbuf ? (*sbuf & 1u) * kEpiStageBytes : 0u);
+    const uint32_t stage_cur = stage + (sbuf ? *sbuf * kEpiStageBytes : 0u);
     const uint32_t srow = stage_cur + (uint32_t)row * 128u;
     if (leader) {                                // the store that last used this staging tile has finished reading it
-      if (sbuf) bulk_wait_read1(); else bulk_wait_read0();
+      if (!sbuf) bulk_wait_read0();
+      else if (nbuf == 2) bulk_wait_read1();
+      else if (nbuf == 3) bulk_wait_read2();
+      else bulk_wait_read3();
     }
-    if (sbuf) *sbuf ^= 1u;
+    if (sbuf) *sbuf = (*sbuf + 1u == (uint32_t)nbuf) ? 0u : *sbuf + 1u;
     named_bar_sync(1 + team, 128);
     if (aux_kind) {                              // residual / mask chunk for this tile: one TMA box instead of strided 16-byte loads
       if (leader) {

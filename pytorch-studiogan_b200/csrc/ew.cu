@@ -576,6 +576,22 @@ __global__ void __launch_bounds__(256) resize_norm_kernel(const float* __restric
   }
 }
 
+// Data path (src/data_util.py:59-142): a uint8 NHWC batch as the datasets store it (HDF5 "imgs", decoded image folders)
+// -> what the reference's per-sample CPU transform chain delivers: RandomHorizontalFlip, ToTensor (x / 255), Normalize(0.5, 0.5)
+// ((x - 0.5) / 0.5), as NCHW fp32 in [-1, 1].  Same fp32 operations in the same order => bit-identical values; the host
+// only ships 1 byte per value over PCIe / NVLink-C2C instead of 4.
+__global__ void __launch_bounds__(256) u8_to_img_kernel(const uint8_t* __restrict__ u8, const uint8_t* __restrict__ flip,
+                                                         float* __restrict__ img, int B, int H, int W) {
+  const long long total = (long long)B * 3 * H * W;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int w = (int)(i % W), h = (int)((i / W) % H);
+    const int c = (int)((i / ((long long)W * H)) % 3), b = (int)(i / ((long long)3 * W * H));
+    const int ws = (flip && flip[b]) ? W - 1 - w : w;
+    const float v = (float)u8[(((long long)b * H + h) * W + ws) * 3 + c];
+    img[i] = (v / 255.0f - 0.5f) / 0.5f;
+  }
+}
+
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n,
                                                              float scale) {
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
@@ -834,6 +850,14 @@ extern "C" int sgb_quantize_resize_normalize(const float* img, int32_t quantize,
   const int So = (S - 3) / 2 + 1;
   const long long work = out_img ? (long long)B * 3 * S * S : (long long)B * So * So;
   resize_norm_kernel<<<ew_blocks(work), 256, 0, stream>>>(img, quantize, B, H, W, S, out_img, (bf16*)out_col, So, resizer);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_u8_to_img(const uint8_t* u8, const uint8_t* flip, float* img, int32_t B, int32_t H, int32_t W, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(u8 && img && B > 0 && H > 0 && W > 0);
+  u8_to_img_kernel<<<ew_blocks((long long)B * 3 * H * W), 256, 0, stream>>>(u8, flip, img, B, H, W);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }

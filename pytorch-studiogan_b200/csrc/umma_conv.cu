@@ -33,7 +33,8 @@ struct FpropArgs {
   int w_mode;                     // 0: shared weights [Cout][taps][Cin]; 1: per-image [B][N][K]; 2: per-image MN-major [B][K][N]
   int stages;
   int use_tma;                    // epilogue through staging tiles + TMA tensor stores
-  int epi_nbuf;                   // staging tiles per epilogue team (2: stores overlap the next chunk's conversion)
+  int epi_nbuf;                   // staging tiles per epilogue team (2..4: stores overlap the next chunks' conversion)
+  int b_resident;                 // 1: every weight tile of this CTA's channel tile stays in shared memory (loaded once)
   int aux_kind, aux_tw, aux_th;   // residual (1) / mask (2) tile staged by TMA; its box is aux_tw x aux_th x nb pixels
   int out_sub;                    // 2: store only even (h, w) outputs at (h/2, w/2) -> stride-2 convolution (Inception reduction blocks)
   uint32_t tmem_cols;
@@ -46,9 +47,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t epi_stage_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // two 16 KiB staging tiles when use_tma
   const uint32_t aux_stage_base = epi_stage_base + (p.use_tma ? 2u * p.epi_nbuf * kEpiStageBytes : 0u);   // + two aux tiles when aux_kind
-  const uint32_t smem_base = aux_stage_base + (p.aux_kind ? 2u * kEpiStageBytes : 0u);
   const uint32_t b_bytes = (uint32_t)p.BN * kBlockK * 2;  // same size for K-major [BN][64] and MN-major (BN/64) x [64][64]
-  const uint32_t stage_bytes = kABytes + b_bytes;  // multiple of 1024 because BN % 8 == 0 -> b_bytes % 1024 == 0
+  const uint32_t bres_base = aux_stage_base + (p.aux_kind ? 2u * kEpiStageBytes : 0u);     // resident weight tiles [tap][kb]
+  const uint32_t smem_base = bres_base + (p.b_resident ? (uint32_t)(p.taps * p.kblocks) * b_bytes : 0u);
+  const uint32_t stage_bytes = kABytes + (p.b_resident ? 0u : b_bytes);  // multiple of 1024 because BN % 8 == 0 -> b_bytes % 1024 == 0
   const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
@@ -56,6 +58,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
   const uint32_t holder = bar_base + 8u * (2 * p.stages + 4);
   auto aux_bar = [&](int t) { return bar_base + 8u * (2 * p.stages + 6 + t); };
+  const uint32_t bres_bar = bar_base + 8u * (2 * p.stages + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -72,6 +75,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(tempty_bar(a), kEpiThreads);
       mbar_init(aux_bar(a), 1);
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
     if (p.use_tma) tma_prefetch_desc(&tmY);
   }
@@ -91,6 +95,12 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       // ------------------------------------------------------------- TMA producer
       uint32_t it = 0;
+      if (p.b_resident) {       // tiles_n == 1: the whole (small) filter is fetched once per CTA instead of once per tile
+        mbar_arrive_expect_tx(bres_bar, (uint32_t)(p.taps * p.kblocks) * b_bytes);
+        for (int tap = 0; tap < p.taps; ++tap)
+          for (int kb = 0; kb < p.kblocks; ++kb)
+            tma_load_3d(bres_base + (uint32_t)(tap * p.kblocks + kb) * b_bytes, &tmB, bres_bar, kb * kBlockK, tap, 0);
+      }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int t = tile;
         const int nt = t % p.tiles_n; t /= p.tiles_n;
@@ -107,7 +117,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_arrive_expect_tx(full_bar(s), stage_bytes);
             const uint32_t sa = smem_base + s * stage_bytes;
             tma_load_4d(sa, &tmA, full_bar(s), kb * kBlockK, w0 + dw, h0 + dh, b0);
-            if (p.w_mode == 0) {
+            if (p.b_resident) {
+            } else if (p.w_mode == 0) {
               tma_load_3d(sa + kABytes, &tmB, full_bar(s), kb * kBlockK, tap, n0);
             } else if (p.w_mode == 1) {
               tma_load_3d(sa + kABytes, &tmB, full_bar(s), kb * kBlockK, b0, n0);
@@ -125,6 +136,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool b_mn = (p.w_mode == 2);
       const uint32_t idesc = make_idesc_bf16(kTileM, p.BN, 0, b_mn ? 1 : 0);
       uint32_t it = 0, tcount = 0;
+      if (p.b_resident) { mbar_wait(bres_bar, 0); tc_fence_after(); }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(tempty_bar(a), aph ^ 1);
@@ -139,7 +151,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint64_t adesc = make_sdesc_sw128(sa, 16, 1024);
           // K-major B: rows = output channels, +32 B per 16-wide K step.
           // MN-major B: (BN/64) atoms of [64 k-rows][64 n] 8 KiB apart (LBO), 8-row groups 1 KiB apart (SBO), +2 KiB per K step.
-          const uint64_t bdesc = b_mn ? make_sdesc_sw128(sa + kABytes, 8192, 1024) : make_sdesc_sw128(sa + kABytes, 16, 1024);
+          const uint32_t sb = p.b_resident ? bres_base + (uint32_t)k * b_bytes : sa + kABytes;     // k = tap * kblocks + kb
+          const uint64_t bdesc = b_mn ? make_sdesc_sw128(sb, 8192, 1024) : make_sdesc_sw128(sb, 16, 1024);
           const uint32_t bstep = b_mn ? 128u : 2u;
 #pragma unroll
           for (int kk = 0; kk < kBlockK / 16; ++kk) {
@@ -204,7 +217,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           aux.n_c3 = u * p.nb;
         }
         epilogue_tile_tma(p.e, &tmY, t_row, p.BN, n0, wt * p.tw, ht * p.th, bt * p.nb, valid, pix, rpix, alpha, stage, team, row,
-                          leader, 2, p.aux_kind ? &aux : nullptr, p.epi_nbuf == 2 ? &sbuf : nullptr);
+                          leader, 2, p.aux_kind ? &aux : nullptr, p.epi_nbuf >= 2 ? &sbuf : nullptr, p.epi_nbuf);
       } else if (team == 0) {
         epilogue_row(p.e, t_row, p.BN, n0, valid, pix, rpix, alpha, vec_ok);
       }
@@ -460,6 +473,16 @@ static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
+// Bring-up switches: read from the environment ONCE per process (a conv launch used to call getenv five times).
+struct EngineSwitches {
+  int conv3x3_rows, rows_base_offset, epi_tma, epi_tma_maxk, epi_aux, epi_nbuf, wgrad3x3, b_resident;
+};
+static const EngineSwitches& switches() {
+  static const EngineSwitches s = {env_int("SGB_CONV3X3_ROWS", 1), env_int("SGB_ROWS_BASE_OFFSET", 0), env_int("SGB_EPI_TMA", 1),
+                                   env_int("SGB_EPI_TMA_MAXK", 640), env_int("SGB_EPI_AUX", 1), env_int("SGB_EPI_NBUF", 2),
+                                   env_int("SGB_WGRAD3X3", 1), env_int("SGB_B_RESIDENT", 1)};
+  return s;
+}
 
 extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -474,9 +497,9 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   SGB_REQUIRE(((uintptr_t)d->bias & 15) == 0 && ((uintptr_t)d->residual & 15) == 0 && ((uintptr_t)d->mask & 15) == 0);
   {
     // wide, few-channel 3x3 layers: halo-row kernel (umma_conv3x3.cu).  SGB_CONV3X3_ROWS=0 forces the generic kernel.
-    static const int use_rows = env_int("SGB_CONV3X3_ROWS", 1);
-    static const int bo_mode = env_int("SGB_ROWS_BASE_OFFSET", 0);
-    if (use_rows && d->Hin <= 0 && d->Win <= 0 && d->out_sub != 2 && conv3x3_rows_eligible(d)) return launch_conv3x3_rows(d, stream, bo_mode, env_int("SGB_EPI_TMA", 1));
+    const EngineSwitches& sw = switches();
+    if (sw.conv3x3_rows && d->Hin <= 0 && d->Win <= 0 && d->out_sub != 2 && conv3x3_rows_eligible(d))
+      return launch_conv3x3_rows(d, stream, sw.rows_base_offset, sw.epi_tma);
   }
   SGB_REQUIRE(((uintptr_t)d->bias & 15) == 0 && ((uintptr_t)d->residual & 15) == 0 && ((uintptr_t)d->mask & 15) == 0);
 
@@ -509,22 +532,28 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   SGB_REQUIRE(p.out_sub == 1 || (!d->residual && !d->mask));
   p.use_tma = (p.out_sub == 1 && !d->y_fp32 && BN % 64 == 0 && d->Cout % 8 == 0 && d->y_cstride % 8 == 0 &&
                (!d->residual || d->res_cstride % 8 == 0) && (!d->mask || d->mask_cstride % 8 == 0) &&
-               p.taps * d->Cin <= env_int("SGB_EPI_TMA_MAXK", 640) && env_int("SGB_EPI_TMA", 1)) ? 1 : 0;   // output-heavy layers only
+               p.taps * d->Cin <= switches().epi_tma_maxk && switches().epi_tma) ? 1 : 0;   // output-heavy layers only
   // auxiliary epilogue operand through TMA: exactly one of residual / mask, bf16 NHWC with 16-byte aligned channel stride
   p.aux_kind = 0; p.aux_tw = p.tw; p.aux_th = p.th;
-  if (p.use_tma && env_int("SGB_EPI_AUX", 1) && (d->residual != nullptr || d->mask != nullptr)) {
+  if (p.use_tma && switches().epi_aux && (d->residual != nullptr || d->mask != nullptr)) {
     // one operand rides TMA: the mask when both are present (full-resolution tile; the residual of such launches is the
     // quarter-size pooled-skip gradient, whose direct 16-byte loads are shared by 2x2 pixel neighbours through L1)
     if (d->mask) p.aux_kind = 2;
     else if (!d->res_up2) p.aux_kind = 1;
     else if (p.tw >= 2) { p.aux_kind = 1; p.aux_tw = p.tw / 2; p.aux_th = p.th >= 2 ? p.th / 2 : 1; }
   }
-  const uint32_t stage_bytes = kABytes + BN * kBlockK * 2;
-  // short-K layers (one or two K blocks per tile) are epilogue / store bound: give each team a second staging tile
-  p.epi_nbuf = (p.use_tma && p.taps * p.kblocks <= 2 && env_int("SGB_EPI_NBUF", 2) == 2) ? 2 : 1;
-  int stages = (int)(((200 - (p.use_tma ? 32 * p.epi_nbuf : 0) - (p.aux_kind ? 32 : 0)) * 1024) / stage_bytes);
+  // short-K layers (one or two K blocks per tile) are store bound: their (small) filter stays resident in shared memory and the
+  // space of the B halves of the ring buys more staging tiles per epilogue team = more store bytes in flight
+  const uint32_t b_tile = (uint32_t)BN * kBlockK * 2;
+  const int kt = p.taps * p.kblocks;
+  p.b_resident = (switches().b_resident && d->w_mode == 0 && p.tiles_n == 1 && kt <= 2 && kt * b_tile <= 64u * 1024u) ? 1 : 0;
+  const uint32_t stage_bytes = kABytes + (p.b_resident ? 0u : b_tile);
+  const int nbuf_want = switches().epi_nbuf < 1 ? 1 : (switches().epi_nbuf > 4 ? 4 : switches().epi_nbuf);
+  p.epi_nbuf = (p.use_tma && kt <= 2) ? nbuf_want : 1;
+  auto ring_kb = [&](int nbuf) { return (kt <= 2 ? 216 : 200) - (p.use_tma ? 32 * nbuf : 0) - (p.aux_kind ? 32 : 0) - (p.b_resident ? (int)(kt * b_tile / 1024) : 0); };
+  while (p.epi_nbuf > 1 && ring_kb(p.epi_nbuf) * 1024 < (int)(3 * stage_bytes)) --p.epi_nbuf;     // keep >= 3 ring stages
+  int stages = ring_kb(p.epi_nbuf) * 1024 / (int)stage_bytes;
   if (stages > 8) stages = 8;
-  if (stages < 2) { p.epi_nbuf = 1; stages = (int)(((200 - (p.use_tma ? 32 : 0) - (p.aux_kind ? 32 : 0)) * 1024) / stage_bytes); }
   if (stages < 2) stages = 2;
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * BN);
@@ -564,7 +593,7 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
     if (rc) return rc;
   }
   const size_t smem = (size_t)stages * stage_bytes + (p.use_tma ? 2 * p.epi_nbuf * kEpiStageBytes : 0) + (p.aux_kind ? 2 * kEpiStageBytes : 0) +
-                      1024 + 8 * (2 * stages + 8) + 16;
+                      (p.b_resident ? (size_t)kt * b_tile : 0) + 1024 + 8 * (2 * stages + 9) + 16;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     SGB_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -578,7 +607,7 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
 
 extern "C" int sgb_conv_wgrad_fuses_dbias(const sgb_wgrad_desc* d) {
   if (!d) return 0;
-  if (env_int("SGB_WGRAD3X3", 1) && wgrad3x3_c64_eligible(d)) return 1;
+  if (switches().wgrad3x3 && wgrad3x3_c64_eligible(d)) return 1;
   return d->per_image ? 0 : 1;          // generic kernel: constant-ones B operand on its (first channel tile, first tap) items
 }
 
@@ -588,7 +617,7 @@ extern "C" int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream_) {
   SGB_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0 && d->KH > 0 && d->KW > 0);
   SGB_REQUIRE(d->Cin % 8 == 0 && d->x_cstride % 8 == 0 && d->Cout % 8 == 0 && d->dy_cstride % 8 == 0);
   SGB_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->dy & 15) == 0);
-  if (env_int("SGB_WGRAD3X3", 1) && wgrad3x3_c64_eligible(d)) return launch_wgrad3x3_c64(d, stream);
+  if (switches().wgrad3x3 && wgrad3x3_c64_eligible(d)) return launch_wgrad3x3_c64(d, stream);
   SGB_REQUIRE(d->dbias == nullptr || !d->per_image);
 
   WgradArgs p;

@@ -93,6 +93,7 @@ SIGNATURES = {
     "sgb_zero_stuff2": (c_int, [c_p, c_i64, c_p, c_i64, c_int, c_int, c_int, c_int, c_p]),
     "sgb_quantize_u8": (c_int, [c_p, c_p, c_i64, c_p]),
     "sgb_quantize_resize_normalize": (c_int, [c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_int, c_p]),
+    "sgb_u8_to_img": (c_int, [c_p, c_p, c_p, c_int, c_int, c_int, c_p]),
     "sgb_cast_f32_to_bf16": (c_int, [c_p, c_p, c_i64, c_f, c_p]),
     "sgb_cast_bf16_to_f32": (c_int, [c_p, c_p, c_i64, c_p]),
     "sgb_adam_ema_step": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_f, c_f, c_f, c_f, c_int, c_p, c_p, c_f, c_f, c_p]),

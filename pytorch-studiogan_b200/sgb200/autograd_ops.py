@@ -106,7 +106,7 @@ def _direct_grad_ptr(p):
     return g.data_ptr()
 
 
-def conv_param_grads(x, dz, weight, need_w, need_b, KH, KW, pad, dims, sigma, u_saved, v_saved, perm_S=1, sn_pass=None):
+def conv_param_grads(x, dz, weight, need_w, need_b, KH, KW, pad, dims, sigma, u_saved, v_saved, perm_S=1, sn_pass=None, bias=None):
     """Weight and bias gradient of y = conv(x, W / sigma) + b given dz = dL/dy (NHWC bf16): tcgen05 weight-gradient kernel,
     then the spectral-norm chain rule (sgb_sn_backward).  The weight gradient is added straight into the flat gradient
     arena when the parameter opted in (returns None for it then).  The bias gradient rides on the weight-gradient launch
@@ -118,7 +118,13 @@ def conv_param_grads(x, dz, weight, need_w, need_b, KH, KW, pad, dims, sigma, u_
         # batched path: accumulate the raw weight gradient into this forward pass's flat buffer; the spectral-norm chain
         # rule of ALL layers runs as one launch pair when the backward pass ends (snbatch._Pass.flush)
         G = sn_pass[0].g_slice(sn_pass[1])
-        if need_b:
+        btgt = _direct_grad(bias) if (need_b and bias is not None and dz.shape[1] == Cout) else None
+        if btgt is not None:
+            # the bias gradient is added straight into the gradient arena by the same launch (no tensor, no accumulate kernel)
+            _, done = K.conv_wgrad(x, dz, KH, KW, pad, pad, dw=G, accumulate=True, dbias_acc=btgt)
+            if done:
+                need_b = False
+        elif need_b:
             _, dbias = K.conv_wgrad(x, dz, KH, KW, pad, pad, dw=G, accumulate=True, want_dbias=True)
             if dbias is not None:
                 dbias = dbias[:Cout]
@@ -177,6 +183,7 @@ class ConvFn(TFunction):
             u_saved, v_saved = u.clone(), v.clone()
         ctx.cfg = cfg
         ctx.dims = (Cout, Cin, taps)
+        ctx.bias_ref = bias                          # the parameter object (arena-backed .grad), not a saved activation
         ctx.has_res = residual is not None
         ctx.res_shape = residual.shape if residual is not None else None
         ctx.save_for_backward(x, weight, wd, sigma, u_saved, v_saved, y if cfg.get("relu", False) else None)
@@ -210,7 +217,7 @@ class ConvFn(TFunction):
                 dx = dx[:, :x.shape[1]]
         if not SKIP_PARAM_GRADS:
             dW, dbias = conv_param_grads(x, dz, weight, ctx.needs_input_grad[1], ctx.needs_input_grad[2], KH, KW, pad, ctx.dims,
-                                         sigma, u_saved, v_saved, cfg.get("perm_S", 1), cfg.get("sn_pass"))
+                                         sigma, u_saved, v_saved, cfg.get("perm_S", 1), cfg.get("sn_pass"), ctx.bias_ref)
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = K.pool2_fwd(dz, 2) if cfg.get("res_up2", False) else dz
             rc = ctx.res_shape[1]
@@ -594,6 +601,7 @@ class DEntryConvFn(TFunction):
             px = a0.view_as(a0)
         ctx.cfg = cfg
         ctx.dims = (hid, Cin, 1)
+        ctx.bias_ref = bias
         ctx.save_for_backward(a0, weight, wd, sigma, us, vs)
         return h1, px
 
@@ -610,7 +618,7 @@ class DEntryConvFn(TFunction):
                               res_up2=down, res_scale=0.25 if down else 1.0)
         if not SKIP_PARAM_GRADS:
             dW, db = conv_param_grads(a0, dz, weight, ctx.needs_input_grad[1], ctx.needs_input_grad[2], 1, 1, 0, ctx.dims,
-                                      sigma, us, vs, 1, cfg.get("sn_pass"))
+                                      sigma, us, vs, 1, cfg.get("sn_pass"), ctx.bias_ref)
         return dx, dW, db, None
 
 
@@ -643,6 +651,7 @@ class ConcatSkipFn(TFunction):
             u_saved, v_saved = u.clone(), v.clone()
         ctx.cfg = cfg
         ctx.dims = (Cextra, Cin)
+        ctx.bias_ref = bias
         ctx.save_for_backward(px, weight, wd, sigma, u_saved, v_saved)
         return skip
 
@@ -657,7 +666,7 @@ class ConcatSkipFn(TFunction):
             dpx = K.conv_fprop(d_hi, wd, Cin, 1, 1, 0, 0, residual=d_lo)
         if not SKIP_PARAM_GRADS:
             dW, dbias = conv_param_grads(px, d_hi, weight, ctx.needs_input_grad[1], ctx.needs_input_grad[2], 1, 1, 0,
-                                         (Cextra, Cin, 1), sigma, u_saved, v_saved, 1, ctx.cfg.get("sn_pass"))
+                                         (Cextra, Cin, 1), sigma, u_saved, v_saved, 1, ctx.cfg.get("sn_pass"), ctx.bias_ref)
         return dpx, dW, dbias, None
 
     @staticmethod

@@ -97,10 +97,11 @@ def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_u
     return out
 
 
-def conv_wgrad(x, dy, KH, KW, pad_h, pad_w, dw=None, accumulate=False, per_image=False, want_dbias=False):
+def conv_wgrad(x, dy, KH, KW, pad_h, pad_w, dw=None, accumulate=False, per_image=False, want_dbias=False, dbias_acc=None):
     """fp32 weight gradient in the fprop-pack layout [Cout][KH*KW][Cin] (or [B][...] when per_image).
     want_dbias: returns (dw, dbias) where dbias is the fp32 [Cout] bias gradient if this launch can produce it for free,
-    else None (the caller then reduces dy itself)."""
+    else None (the caller then reduces dy itself).  dbias_acc (with accumulate=True): an fp32 [Cout] tensor the launch ADDS
+    the bias gradient to (a view of the gradient arena); returns (dw, True) when it did."""
     B, Cin, H, W, xcs = geom(x)
     _, Cout, _, _, dcs = geom(dy)
     if dw is None:
@@ -114,7 +115,13 @@ def conv_wgrad(x, dy, KH, KW, pad_h, pad_w, dw=None, accumulate=False, per_image
     d.dy, d.dy_cstride = dy.data_ptr(), dcs
     d.dw, d.accumulate, d.per_image = dw.data_ptr(), 1 if accumulate else 0, 1 if per_image else 0
     dbias = None
-    if want_dbias and L.load().sgb_conv_wgrad_fuses_dbias(ctypes.byref(d)):
+    if dbias_acc is not None:
+        assert accumulate and dbias_acc.dtype == torch.float32 and dbias_acc.numel() == Cout and dbias_acc.is_contiguous()
+        if L.load().sgb_conv_wgrad_fuses_dbias(ctypes.byref(d)):
+            d.dbias = dbias_acc.data_ptr()
+            dbias = True
+        want_dbias = True
+    elif want_dbias and L.load().sgb_conv_wgrad_fuses_dbias(ctypes.byref(d)):
         # accumulate: the launch zeroes neither dw nor dbias, so dbias starts from zeros here
         dbias = (torch.zeros if accumulate else torch.empty)(Cout, device=x.device, dtype=torch.float32)
         d.dbias = dbias.data_ptr()
@@ -370,6 +377,16 @@ def quantize_resize_normalize(img, S=299, quantize=True, want_image=False, want_
     L.call("sgb_quantize_resize_normalize", L.ptr(img), 1 if quantize else 0, B, H, W, S, L.ptr(out_img), L.ptr(out_col),
            {"legacy": 0, "friendly": 1}[resizer], _s())
     return out_img, out_col
+
+
+def u8_to_img(u8, flip=None, out=None):
+    """uint8 NHWC [B,H,W,3] device tensor (+ optional uint8 [B] flip flags) -> NCHW fp32 in [-1,1]."""
+    B, H, W, C = u8.shape
+    assert C == 3 and u8.dtype == torch.uint8 and u8.is_contiguous()
+    if out is None:
+        out = torch.empty((B, 3, H, W), device=u8.device, dtype=torch.float32)
+    L.call("sgb_u8_to_img", L.ptr(u8), L.ptr(flip), L.ptr(out), B, H, W, _s())
+    return out
 
 
 def cast_f32_to_bf16(x, scale=1.0, out=None):

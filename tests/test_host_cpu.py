@@ -303,3 +303,23 @@ def test_dcgan_state_dict_keys_match_reference(golden_dir):
                                 d_depth="N/A", mixed_precision=False, MODULES=M, MODEL=MODEL)
     assert [[k, list(v.shape)] for k, v in G.state_dict().items()] == json.loads(str(g["keys_g"]))
     assert [[k, list(v.shape)] for k, v in D.state_dict().items()] == json.loads(str(g["keys_d"]))
+
+
+def test_uint8_dataset_matches_reference_transform_chain(tmp_path):
+    """data_util.Dataset_ (src/data_util.py:59-142): an .npz / HDF5-style uint8 NHWC store; ``__getitem__`` equals the
+    reference's ToTensor + Normalize(0.5, 0.5) chain bit for bit, the batched ``gather`` returns the stored bytes."""
+    import numpy as np
+    from sgb200 import data_util
+    rs = np.random.RandomState(0)
+    imgs = rs.randint(0, 256, size=(10, 6, 5, 3)).astype(np.uint8)
+    labels = rs.randint(0, 4, size=10)
+    path = str(tmp_path / "toy.npz")
+    np.savez(path, imgs=imgs, labels=labels)
+    ds = data_util.Dataset_("toy", None, True, hdf5_path=path, random_flip=False)
+    assert len(ds) == 10
+    x, y = ds[3]
+    ref = (torch.from_numpy(imgs[3]).permute(2, 0, 1).float().div(255) - 0.5) / 0.5
+    assert torch.equal(x, ref) and y == int(labels[3])
+    out_i, out_l = torch.empty((4, 6, 5, 3), dtype=torch.uint8), torch.empty(4, dtype=torch.int64)
+    ds.gather([7, 0, 2, 2], out_i, out_l)
+    assert np.array_equal(out_i.numpy(), imgs[[7, 0, 2, 2]]) and out_l.tolist() == labels[[7, 0, 2, 2]].tolist()
