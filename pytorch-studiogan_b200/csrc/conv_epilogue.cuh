@@ -170,20 +170,42 @@ __device__ __forceinline__ bool epi_use_tma(const EpiArgs& p, int BN) {
   return !p.y_fp32 && (BN % 64 == 0) && epi_vec_ok(p);
 }
 
+// Compile-time epilogue variants.  The per-piece loop below runs on 2 warps per scheduler with little latency hiding, so
+// every run-time test of "is there a bias / residual / mask / ragged channel tail" costs issue slots on the critical path of
+// the memory-bound layers (ncu, r01: ~150 SASS instructions per 16-column piece).  F >= 0 fixes those questions at compile
+// time (bit 0 bias, 1 ReLU, 2 residual before the activation, 3 residual after the mask, 4 mask, 5 Cout % 64 == 0 and every
+// 16-byte alignment holds); F < 0 is the fully general run-time version.
+static constexpr int kEpiBias = 1, kEpiRelu = 2, kEpiResPre = 4, kEpiResPost = 8, kEpiMask = 16, kEpiFull = 32;
+
+__host__ __device__ inline int epi_flags_of(const EpiArgs& p) {
+  int f = 0;
+  if (p.bias) f |= kEpiBias;
+  if (p.relu) f |= kEpiRelu;
+  if (p.residual) f |= p.res_after ? kEpiResPost : kEpiResPre;
+  if (p.mask) f |= kEpiMask;
+  if (p.Cout % 64 == 0) f |= kEpiFull;
+  return f;
+}
+
 // t_row : TMEM address (lane quadrant of this warp, first column of the accumulator).
 // c1..c3: box coordinates (w0, h0, b0) of the tile in the output tensor map; channel coordinate = n0 + chunk * 64.
 // stage : this team's staging buffer (1024-byte aligned).  team in {0,1}; row = accumulator row of this thread.
+template <int F>
 __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtensorMap* tmY, uint32_t t_row, int BN, int n0,
                                                   int c1, int c2, int c3, bool valid, long long pix, long long rpix, float alpha,
                                                   uint32_t stage, int team, int row, bool leader, int chunk_stride = 2,
                                                   const EpiAux* aux = nullptr, uint32_t* sbuf = nullptr, int nbuf = 2) {
-  const bool res_pre = p.residual != nullptr && !p.res_after;
-  const bool res_post = p.residual != nullptr && p.res_after;
+  const bool has_bias = F < 0 ? p.bias != nullptr : (F & kEpiBias) != 0;
+  const bool do_relu = F < 0 ? p.relu != 0 : (F & kEpiRelu) != 0;
+  const bool res_pre = F < 0 ? (p.residual != nullptr && !p.res_after) : (F & kEpiResPre) != 0;
+  const bool res_post = F < 0 ? (p.residual != nullptr && p.res_after) : (F & kEpiResPost) != 0;
+  const bool has_mask = F < 0 ? p.mask != nullptr : (F & kEpiMask) != 0;
+  const bool full_c = F >= 0 && (F & kEpiFull) != 0;       // no channel-tail tests
   const float rs = p.res_scale;
   // sbuf != nullptr: the team owns ``nbuf`` (2..4) staging tiles used round-robin, so a chunk only waits for the store issued
   // nbuf chunks ago -- the latency of the previous tensor stores is off the critical path and more bytes are in flight.
   const uint32_t sw = (uint32_t)(row & 7);
-  const int aux_kind = aux ? aux->kind : 0;                       // 1: residual tile via TMA, 2: mask tile via TMA
+  const int aux_kind = (aux && (res_pre || res_post || has_mask)) ? aux->kind : 0;   // 1: residual tile via TMA, 2: mask tile via TMA
   const uint32_t arow_addr = aux ? aux->stage + (uint32_t)aux->arow * 128u : 0u;
   const uint32_t asw = aux ? (uint32_t)(aux->arow & 7) : 0u;
   for (int cc = (chunk_stride == 2 ? team : 0); cc * 64 < BN; cc += chunk_stride) {
@@ -210,77 +232,86 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
       mbar_wait(aux->bar, *aux->phase);
       *aux->phase ^= 1u;
     }
-#pragma unroll 1
-    for (int s = 0; s < 4; ++s) {
-      uint32_t v[16];
-      __syncwarp();
-      tmem_ld16(t_row + cc * 64 + s * 16, v);
-      tmem_ld_wait();
-      const int n = nbase + s * 16;
-      float f[16];
+    // compile-time variants handle two 16-column pieces per iteration: both TMEM loads are in flight before the single wait
+    // (the variants use ~77 registers, the general version 102), which hides part of the LDTM latency that two warps per
+    // scheduler cannot hide by themselves
+    constexpr int NP = F >= 0 ? 2 : 1;
+    auto piece = [&](const int s, const uint32_t (&v)[16]) {
+        const int n = nbase + s * 16;
+        float f[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * alpha;
-      const int nvalid = p.Cout - n;               // channels of this 16-wide piece inside the tensor: >= 16, 8 (Cout % 16 == 8) or <= 0
-      const bool in_c = nvalid > 0;
-      if (in_c && p.bias) {
-        const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * alpha;
+        const int nvalid = full_c ? 16 : p.Cout - n;   // channels of this 16-wide piece inside the tensor: >= 16, 8 (Cout % 16 == 8) or <= 0
+        const bool in_c = full_c || nvalid > 0;
+        if (has_bias && in_c) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (4 * j < nvalid) {
-            const float4 bb = __ldg(bp + j);
-            f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+          for (int j = 0; j < 4; ++j) {
+            if (full_c || 4 * j < nvalid) {
+              const float4 bb = __ldg(bp + j);
+              f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+            }
           }
         }
-      }
-      if (in_c && valid && res_pre) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.res_cstride + n);
+        if (res_pre && in_c && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.res_cstride + n);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const uint4 r = (aux_kind == 1) ? ld_shared_v4(arow_addr + (((uint32_t)(2 * s + j) ^ asw) << 4))
-                                          : (8 * j < nvalid ? __ldg(rp + j) : make_uint4(0u, 0u, 0u, 0u));
-          f[8 * j + 0] = fmaf(bf16_bits_lo(r.x), rs, f[8 * j + 0]); f[8 * j + 1] = fmaf(bf16_bits_hi(r.x), rs, f[8 * j + 1]);
-          f[8 * j + 2] = fmaf(bf16_bits_lo(r.y), rs, f[8 * j + 2]); f[8 * j + 3] = fmaf(bf16_bits_hi(r.y), rs, f[8 * j + 3]);
-          f[8 * j + 4] = fmaf(bf16_bits_lo(r.z), rs, f[8 * j + 4]); f[8 * j + 5] = fmaf(bf16_bits_hi(r.z), rs, f[8 * j + 5]);
-          f[8 * j + 6] = fmaf(bf16_bits_lo(r.w), rs, f[8 * j + 6]); f[8 * j + 7] = fmaf(bf16_bits_hi(r.w), rs, f[8 * j + 7]);
+          for (int j = 0; j < 2; ++j) {
+            const uint4 r = (aux_kind == 1) ? ld_shared_v4(arow_addr + (((uint32_t)(2 * s + j) ^ asw) << 4))
+                                            : ((full_c || 8 * j < nvalid) ? __ldg(rp + j) : make_uint4(0u, 0u, 0u, 0u));
+            f[8 * j + 0] = fmaf(bf16_bits_lo(r.x), rs, f[8 * j + 0]); f[8 * j + 1] = fmaf(bf16_bits_hi(r.x), rs, f[8 * j + 1]);
+            f[8 * j + 2] = fmaf(bf16_bits_lo(r.y), rs, f[8 * j + 2]); f[8 * j + 3] = fmaf(bf16_bits_hi(r.y), rs, f[8 * j + 3]);
+            f[8 * j + 4] = fmaf(bf16_bits_lo(r.z), rs, f[8 * j + 4]); f[8 * j + 5] = fmaf(bf16_bits_hi(r.z), rs, f[8 * j + 5]);
+            f[8 * j + 6] = fmaf(bf16_bits_lo(r.w), rs, f[8 * j + 6]); f[8 * j + 7] = fmaf(bf16_bits_hi(r.w), rs, f[8 * j + 7]);
+          }
         }
-      }
-      if (p.relu) {
+        if (do_relu) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-      }
-      if (in_c && valid && p.mask) {
-        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_cstride + n);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const uint4 m = (aux_kind == 2) ? ld_shared_v4(arow_addr + (((uint32_t)(2 * s + j) ^ asw) << 4))
-                                          : (8 * j < nvalid ? __ldg(mp + j) : make_uint4(0u, 0u, 0u, 0u));
-          f[8 * j + 0] = bf16_bits_lo(m.x) > 0.f ? f[8 * j + 0] : 0.f;
-          f[8 * j + 1] = bf16_bits_hi(m.x) > 0.f ? f[8 * j + 1] : 0.f;
-          f[8 * j + 2] = bf16_bits_lo(m.y) > 0.f ? f[8 * j + 2] : 0.f;
-          f[8 * j + 3] = bf16_bits_hi(m.y) > 0.f ? f[8 * j + 3] : 0.f;
-          f[8 * j + 4] = bf16_bits_lo(m.z) > 0.f ? f[8 * j + 4] : 0.f;
-          f[8 * j + 5] = bf16_bits_hi(m.z) > 0.f ? f[8 * j + 5] : 0.f;
-          f[8 * j + 6] = bf16_bits_lo(m.w) > 0.f ? f[8 * j + 6] : 0.f;
-          f[8 * j + 7] = bf16_bits_hi(m.w) > 0.f ? f[8 * j + 7] : 0.f;
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-      }
-      if (in_c && valid && res_post) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.res_cstride + n);
+        if (has_mask && in_c && valid) {
+          const uint4* mp = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_cstride + n);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const uint4 r = (aux_kind == 1) ? ld_shared_v4(arow_addr + (((uint32_t)(2 * s + j) ^ asw) << 4))
-                                          : (8 * j < nvalid ? __ldg(rp + j) : make_uint4(0u, 0u, 0u, 0u));
-          f[8 * j + 0] = fmaf(bf16_bits_lo(r.x), rs, f[8 * j + 0]); f[8 * j + 1] = fmaf(bf16_bits_hi(r.x), rs, f[8 * j + 1]);
-          f[8 * j + 2] = fmaf(bf16_bits_lo(r.y), rs, f[8 * j + 2]); f[8 * j + 3] = fmaf(bf16_bits_hi(r.y), rs, f[8 * j + 3]);
-          f[8 * j + 4] = fmaf(bf16_bits_lo(r.z), rs, f[8 * j + 4]); f[8 * j + 5] = fmaf(bf16_bits_hi(r.z), rs, f[8 * j + 5]);
-          f[8 * j + 6] = fmaf(bf16_bits_lo(r.w), rs, f[8 * j + 6]); f[8 * j + 7] = fmaf(bf16_bits_hi(r.w), rs, f[8 * j + 7]);
+          for (int j = 0; j < 2; ++j) {
+            const uint4 m = (aux_kind == 2) ? ld_shared_v4(arow_addr + (((uint32_t)(2 * s + j) ^ asw) << 4))
+                                            : ((full_c || 8 * j < nvalid) ? __ldg(mp + j) : make_uint4(0u, 0u, 0u, 0u));
+            f[8 * j + 0] = bf16_bits_lo(m.x) > 0.f ? f[8 * j + 0] : 0.f;
+            f[8 * j + 1] = bf16_bits_hi(m.x) > 0.f ? f[8 * j + 1] : 0.f;
+            f[8 * j + 2] = bf16_bits_lo(m.y) > 0.f ? f[8 * j + 2] : 0.f;
+            f[8 * j + 3] = bf16_bits_hi(m.y) > 0.f ? f[8 * j + 3] : 0.f;
+            f[8 * j + 4] = bf16_bits_lo(m.z) > 0.f ? f[8 * j + 4] : 0.f;
+            f[8 * j + 5] = bf16_bits_hi(m.z) > 0.f ? f[8 * j + 5] : 0.f;
+            f[8 * j + 6] = bf16_bits_lo(m.w) > 0.f ? f[8 * j + 6] : 0.f;
+            f[8 * j + 7] = bf16_bits_hi(m.w) > 0.f ? f[8 * j + 7] : 0.f;
+          }
         }
-      }
-      // 16 channels = two 16-byte units (2s, 2s+1) of this row's 128-byte line; unit u lives at (u ^ (row & 7))
-      st_shared_v4(srow + (((uint32_t)(2 * s) ^ sw) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                   pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-      st_shared_v4(srow + (((uint32_t)(2 * s + 1) ^ sw) << 4), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
-                   pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+        if (res_post && in_c && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.res_cstride + n);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint4 r = (aux_kind == 1) ? ld_shared_v4(arow_addr + (((uint32_t)(2 * s + j) ^ asw) << 4))
+                                            : ((full_c || 8 * j < nvalid) ? __ldg(rp + j) : make_uint4(0u, 0u, 0u, 0u));
+            f[8 * j + 0] = fmaf(bf16_bits_lo(r.x), rs, f[8 * j + 0]); f[8 * j + 1] = fmaf(bf16_bits_hi(r.x), rs, f[8 * j + 1]);
+            f[8 * j + 2] = fmaf(bf16_bits_lo(r.y), rs, f[8 * j + 2]); f[8 * j + 3] = fmaf(bf16_bits_hi(r.y), rs, f[8 * j + 3]);
+            f[8 * j + 4] = fmaf(bf16_bits_lo(r.z), rs, f[8 * j + 4]); f[8 * j + 5] = fmaf(bf16_bits_hi(r.z), rs, f[8 * j + 5]);
+            f[8 * j + 6] = fmaf(bf16_bits_lo(r.w), rs, f[8 * j + 6]); f[8 * j + 7] = fmaf(bf16_bits_hi(r.w), rs, f[8 * j + 7]);
+          }
+        }
+        // 16 channels = two 16-byte units (2s, 2s+1) of this row's 128-byte line; unit u lives at (u ^ (row & 7))
+        st_shared_v4(srow + (((uint32_t)(2 * s) ^ sw) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                     pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        st_shared_v4(srow + (((uint32_t)(2 * s + 1) ^ sw) << 4), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                     pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+    };
+#pragma unroll 1
+    for (int s0 = 0; s0 < 4; s0 += NP) {
+      uint32_t v[NP][16];
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < NP; ++q) tmem_ld16(t_row + cc * 64 + (s0 + q) * 16, v[q]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < NP; ++q) piece(s0 + q, v[q]);
     }
     fence_proxy_async_smem();                    // generic-proxy smem writes -> visible to the TMA (async proxy)
     named_bar_sync(1 + team, 128);

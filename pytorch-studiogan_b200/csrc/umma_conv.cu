@@ -41,6 +41,7 @@ struct FpropArgs {
   EpiArgs e;
 };
 
+template <int F>      // epilogue variant (conv_epilogue.cuh: kEpi* bits fixed at compile time; -1 = run-time flags)
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmAux, const FpropArgs p) {
@@ -216,7 +217,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           aux.n_c2 = aux_half ? (ht2 * p.th) >> 1 : ht2 * p.th;
           aux.n_c3 = u * p.nb;
         }
-        epilogue_tile_tma(p.e, &tmY, t_row, p.BN, n0, wt * p.tw, ht * p.th, bt * p.nb, valid, pix, rpix, alpha, stage, team, row,
+        epilogue_tile_tma<F>(p.e, &tmY, t_row, p.BN, n0, wt * p.tw, ht * p.th, bt * p.nb, valid, pix, rpix, alpha, stage, team, row,
                           leader, 2, p.aux_kind ? &aux : nullptr, p.epi_nbuf >= 2 ? &sbuf : nullptr, p.epi_nbuf);
       } else if (team == 0) {
         epilogue_row(p.e, t_row, p.BN, n0, valid, pix, rpix, alpha, vec_ok);
@@ -484,6 +485,19 @@ static const EngineSwitches& switches() {
   return s;
 }
 
+template <int F>
+static int launch_fprop(int grid, size_t smem, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+                        const CUtensorMap& tmAux, const FpropArgs& p) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SGB_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_fprop_kernel<F><<<grid, kThreads, smem, stream>>>(tmA, tmB, tmY, tmAux, p);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
 extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SGB_REQUIRE(d && d->x && d->w && d->y);
@@ -594,15 +608,21 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   }
   const size_t smem = (size_t)stages * stage_bytes + (p.use_tma ? 2 * p.epi_nbuf * kEpiStageBytes : 0) + (p.aux_kind ? 2 * kEpiStageBytes : 0) +
                       (p.b_resident ? (size_t)kt * b_tile : 0) + 1024 + 8 * (2 * stages + 9) + 16;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    SGB_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    smem_set = 227 * 1024;
-  }
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  conv_fprop_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmY, tmAux, p);
-  SGB_LAUNCH_CHECK();
-  return SGB_OK;
+  // the hot epilogue shapes of the training step get compile-time variants; everything else takes the general kernel
+  const int f = p.use_tma ? epi_flags_of(p.e) : -1;
+  switch (f) {
+    case kEpiFull: return launch_fprop<kEpiFull>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);                                             // dgrad / attention GEMMs
+    case kEpiFull | kEpiBias: return launch_fprop<kEpiFull | kEpiBias>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);                       // generator convs
+    case kEpiFull | kEpiBias | kEpiRelu: return launch_fprop<kEpiFull | kEpiBias | kEpiRelu>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);   // discriminator convs
+    case kEpiFull | kEpiResPre: return launch_fprop<kEpiFull | kEpiResPre>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);                   // concat-skip dgrad
+    case kEpiFull | kEpiBias | kEpiResPre: return launch_fprop<kEpiFull | kEpiBias | kEpiResPre>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);   // block output + skip
+    case kEpiFull | kEpiBias | kEpiRelu | kEpiResPre:
+      return launch_fprop<kEpiFull | kEpiBias | kEpiRelu | kEpiResPre>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);                       // ... with the next block's ReLU
+    case kEpiFull | kEpiMask: return launch_fprop<kEpiFull | kEpiMask>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);                       // dgrad through a ReLU
+    case kEpiFull | kEpiMask | kEpiResPre: return launch_fprop<kEpiFull | kEpiMask | kEpiResPre>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);   // fused block entry
+    default: return launch_fprop<-1>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);
+  }
 }
 
 extern "C" int sgb_conv_wgrad_fuses_dbias(const sgb_wgrad_desc* d) {

@@ -36,6 +36,7 @@ __device__ __forceinline__ uint64_t sdesc_rows(uint32_t addr, int bo_mode) {
   return d;
 }
 
+template <int F>      // epilogue variant, see conv_epilogue.cuh
 __global__ void __launch_bounds__(kRowsThreads, 1)
 conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const RowsArgs p) {
@@ -219,7 +220,7 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (p.epi_bufs == 2 || team == 0) {
               const uint32_t stage = epi_stage_base + ((p.epi_bufs == 2) ? team : 0) * kEpiStageBytes;
               // one team covers every chunk of its row: run the chunk loop for both parities on the team's own barrier
-              epilogue_tile_tma(p.e, &tmY, t_row, p.BN, nt * p.BN, ws * 128, h, b, true, pix, rpix, alpha, stage, team, row, leader, 1);
+              epilogue_tile_tma<F>(p.e, &tmY, t_row, p.BN, nt * p.BN, ws * 128, h, b, true, pix, rpix, alpha, stage, team, row, leader, 1);
             } else {
               epilogue_row(p.e, t_row, p.BN, nt * p.BN, true, pix, rpix, alpha, vec_ok);
             }
@@ -243,6 +244,19 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 void fill_epi(EpiArgs& e, const sgb_conv_desc* d);
+
+template <int F>
+static int launch_rows(int grid, size_t smem, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+                       const RowsArgs& p) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SGB_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv3x3_rows_kernel<F><<<grid, kRowsThreads, smem, stream>>>(tmA, tmB, tmY, p);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
 
 bool conv3x3_rows_eligible(const sgb_conv_desc* d) {
   return d->KH == 3 && d->KW == 3 && d->pad_h == 1 && d->pad_w == 1 && d->w_mode == 0 && d->W % 128 == 0 && d->H % 2 == 0 &&
@@ -313,15 +327,15 @@ int launch_conv3x3_rows(const sgb_conv_desc* d, cudaStream_t stream, int bo_mode
   const size_t smem = (size_t)p.a_stages * a_stage + (p.resident ? resident_bytes : p.b_stages * b_tile) +
                       (p.use_tma ? p.epi_bufs * kEpiStageBytes : 0) + 1024 +
                       8 * (2 * p.a_stages + 2 * nb + 4) + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SGB_CUDA(cudaFuncSetAttribute(conv3x3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  conv3x3_rows_kernel<<<grid, kRowsThreads, smem, stream>>>(tmA, tmB, tmY, p);
-  SGB_LAUNCH_CHECK();
-  return SGB_OK;
+  const int f = p.use_tma ? epi_flags_of(p.e) : -1;
+  switch (f) {
+    case kEpiFull | kEpiBias: return launch_rows<kEpiFull | kEpiBias>(grid, smem, stream, tmA, tmB, tmY, p);                        // generator 3x3
+    case kEpiFull | kEpiBias | kEpiRelu: return launch_rows<kEpiFull | kEpiBias | kEpiRelu>(grid, smem, stream, tmA, tmB, tmY, p);    // discriminator 3x3
+    case kEpiFull | kEpiMask: return launch_rows<kEpiFull | kEpiMask>(grid, smem, stream, tmA, tmB, tmY, p);                        // dgrad through a ReLU
+    case kEpiFull: return launch_rows<kEpiFull>(grid, smem, stream, tmA, tmB, tmY, p);                                              // plain dgrad
+    default: return launch_rows<-1>(grid, smem, stream, tmA, tmB, tmY, p);
+  }
 }
 
 }  // namespace sgb
