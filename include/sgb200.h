@@ -274,6 +274,22 @@ int sgb_bn_tangent_bwd_apply(const void* x, int64_t x_cstride, const void* a, in
                              int64_t da_cstride, sgb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Augmentations on NCHW fp32 images (csrc/augment.cu).
+ * Replaces: diffaug.apply_diffaug, policy "color,translation,cutout" (src/utils/diffaug.py:37-100) -- seven tensor-op passes in
+ *   the reference, one gather kernel here -- and cr.apply_cr_aug (src/utils/cr.py:13-50).
+ * params: fp32 [B][7] = {brightness offset, saturation factor, contrast factor, shift_h, shift_w, cutout_h0, cutout_w0}.
+ * ------------------------------------------------------------------------------------------ */
+int sgb_sample_mean(const float* x, int32_t B, int64_t n_per, float* out, sgb_stream_t stream);
+int sgb_diffaug_fwd(const float* x, const float* params, const float* mean_x, float* y, int32_t B, int32_t H, int32_t W,
+                    int32_t do_color, int32_t do_translation, int32_t do_cutout, sgb_stream_t stream);
+/* adjoint of sgb_diffaug_fwd; mean_ws: fp32 [B] scratch. */
+int sgb_diffaug_bwd(const float* dy, const float* params, float* dx, float* mean_ws, int32_t B, int32_t H, int32_t W,
+                    int32_t do_color, int32_t do_translation, int32_t do_cutout, sgb_stream_t stream);
+/* y[b,c,h,w] = xf[b,c,reflect(h + tx[b]),reflect(w + ty[b])], xf = x mirrored along w where flip[b] (any of the three may be NULL). */
+int sgb_cr_aug(const float* x, const uint8_t* flip, const int32_t* tx, const int32_t* ty, float* y, int32_t B, int32_t C, int32_t H,
+               int32_t W, sgb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Evaluation metrics in fp64 on the device (csrc/metrics.cu).
  * Replaces: fid.calculate_moments / np.mean + np.cov (src/metrics/fid.py:65-98) and prdc.compute_prdc's three
  *   sklearn pairwise_distances matrices + argpartition (src/metrics/prdc.py:87-168).

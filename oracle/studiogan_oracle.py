@@ -657,6 +657,52 @@ def dcgan_discriminator(sd, x, label=None, training=True):
     return torch.squeeze(linear(sd, "linear1.", h, training)), h
 
 
+def diffaug_closed_form(x, params, color=True, translation=True, cutout=True):
+    """DiffAugment "color,translation,cutout" (src/utils/diffaug.py:47-100) for given per-sample parameters
+    params[b] = (brightness offset, saturation factor, contrast factor, shift_h, shift_w, cut_h0, cut_w0): the reference's seven
+    passes restated as the closed form the device kernel evaluates (differentiable w.r.t. x through torch autograd)."""
+    B, C, H, W = x.shape
+    p = params.to(x.dtype)
+    y = x
+    if color:
+        y = y + p[:, 0].view(B, 1, 1, 1)
+        m1 = y.mean(dim=1, keepdim=True)
+        y = (y - m1) * p[:, 1].view(B, 1, 1, 1) + m1
+        m2 = y.mean(dim=[1, 2, 3], keepdim=True)
+        y = (y - m2) * p[:, 2].view(B, 1, 1, 1) + m2
+    hh = torch.arange(H).view(1, H, 1)
+    ww = torch.arange(W).view(1, 1, W)
+    if translation:
+        hs = hh + p[:, 3].long().view(B, 1, 1)
+        ws = ww + p[:, 4].long().view(B, 1, 1)
+        inside = ((hs >= 0) & (hs < H) & (ws >= 0) & (ws < W)).unsqueeze(1)
+        idx_b = torch.arange(B).view(B, 1, 1).expand(B, H, W)
+        g = y.permute(0, 2, 3, 1)[idx_b, hs.clamp(0, H - 1).expand(B, H, W), ws.clamp(0, W - 1).expand(B, H, W)].permute(0, 3, 1, 2)
+        y = g * inside.to(x.dtype)
+    if cutout:
+        ch, cw = int(H * 0.5 + 0.5), int(W * 0.5 + 0.5)
+        h0 = (p[:, 5].long() - ch // 2).view(B, 1, 1)
+        w0 = (p[:, 6].long() - cw // 2).view(B, 1, 1)
+        box = (hh >= h0.clamp(min=0)) & (hh <= (h0 + ch - 1).clamp(max=H - 1)) & (ww >= w0.clamp(min=0)) & (ww <= (w0 + cw - 1).clamp(max=W - 1))
+        y = y * (~box).unsqueeze(1).to(x.dtype)
+    return y
+
+
+def cr_aug_closed_form(x, flip, tx, ty):
+    """cr.apply_cr_aug (src/utils/cr.py:13-50) for given draws: mirror along w where ``flip``, then read at
+    (reflect(h + tx), reflect(w + ty))."""
+    B, C, H, W = x.shape
+
+    def refl(i, n):
+        i = i.abs()
+        return torch.where(i >= n, 2 * (n - 1) - i, i)
+    xf = torch.where(flip.view(B, 1, 1, 1).bool(), x.flip(3), x)
+    hs = refl(torch.arange(H).view(1, H, 1) + tx.long().view(B, 1, 1), H).expand(B, H, W)
+    ws = refl(torch.arange(W).view(1, 1, W) + ty.long().view(B, 1, 1), W).expand(B, H, W)
+    idx_b = torch.arange(B).view(B, 1, 1).expand(B, H, W)
+    return xf.permute(0, 2, 3, 1)[idx_b, hs, ws].permute(0, 3, 1, 2)
+
+
 def seeded_state(keys_shapes, seed):
     """Deterministic weights for a (key, shape) list: used for the DCGAN fixture, whose 6.4 M parameters are regenerated
     from the seed on both sides instead of being stored (conv / linear weights ~ N(0, 0.05^2), BN weight 1 + 0.1 N,

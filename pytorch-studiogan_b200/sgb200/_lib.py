@@ -101,6 +101,10 @@ SIGNATURES = {
     "sgb_gp_interpolate": (c_int, [c_p, c_p, c_p, c_p, c_int, c_i64, c_p]),
     "sgb_gp_sumsq": (c_int, [c_p, c_p, c_int, c_i64, c_p]),
     "sgb_gp_seed": (c_int, [c_p, c_p, c_p, c_int, c_i64, c_p]),
+    "sgb_sample_mean": (c_int, [c_p, c_int, c_i64, c_p, c_p]),
+    "sgb_diffaug_fwd": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "sgb_diffaug_bwd": (c_int, [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p]),
+    "sgb_cr_aug": (c_int, [c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p]),
     "sgb_feat_moments_accumulate": (c_int, [c_p, c_int, c_int, c_p, c_p, c_p]),
     "sgb_feat_moments_finalize": (c_int, [c_p, c_p, c_d, c_int, c_p, c_p, c_p]),
     "sgb_prdc_radii": (c_int, [c_p, c_int, c_int, c_int, c_p, c_p, c_p]),

@@ -40,7 +40,8 @@ def _defaults():
         momentum="N/A", nesterov="N/A", alpha="N/A", beta1=0.5, beta2=0.999, d_first=True, g_updates_per_step=1,
         d_updates_per_step=5, total_steps=100000)
     c["PRE"] = _Section(apply_rflip=True)
-    c["AUG"] = _Section(apply_diffaug=False, apply_ada=False, apply_apa=False)
+    c["AUG"] = _Section(apply_diffaug=False, apply_ada=False, apply_apa=False, cr_aug_type="W/O", bcr_aug_type="W/O",
+                        diffaug_type="W/O")
     c["STYLEGAN"] = _Section()
     c["RUN"] = _Section(mixed_precision=False, distributed_data_parallel=False, synchronized_bn=False, batch_statistics=False,
                         standing_statistics=False, standing_step=-1, standing_max_batch=-1, freezeD=-1, cuda_graphs=False, langevin_sampling=False,
@@ -60,6 +61,7 @@ class Configurations(object):
             self._overwrite_cfgs(cfg_file)
         self.define_modules()
         self.define_losses()
+        self.define_augments()
 
     def update_cfgs(self, cfgs, super="RUN"):
         for attr, value in cfgs.items():
@@ -84,6 +86,29 @@ class Configurations(object):
                     "hinge": losses.d_hinge, "wasserstein": losses.d_wasserstein}
         self.LOSS.g_loss = g_losses[self.LOSS.adv_loss]
         self.LOSS.d_loss = d_losses[self.LOSS.adv_loss]
+
+    def define_augments(self, device=None):
+        """``AUG.series_augment`` (applied to every image the discriminator sees, src/worker.py:276-285,549) and
+        ``AUG.parallel_augment`` (the CR / bCR copy, :326-355) as in src/config.py:567-629, for the augmentation types built on
+        this path: DiffAugment ("diffaug") and the CR augmentation ("cr" / "bcr").  ADA / APA / SimCLR types raise."""
+        from .utils import cr, diffaug, misc
+        self.AUG.series_augment = misc.identity
+        self.AUG.parallel_augment = misc.identity
+        table = {"diffaug": diffaug.apply_diffaug, "cr": cr.apply_cr_aug, "bcr": cr.apply_cr_aug}
+        if self.AUG.apply_ada or self.AUG.apply_apa:
+            raise NotImplementedError("AUG.apply_ada / apply_apa are outside the sgb200 hot-path scope")
+        if self.AUG.apply_diffaug:
+            if self.AUG.diffaug_type not in ("cr", "diffaug"):
+                raise NotImplementedError("AUG.diffaug_type '%s' (built: 'diffaug', 'cr')" % self.AUG.diffaug_type)
+            self.AUG.series_augment = table[self.AUG.diffaug_type]
+        if self.LOSS.apply_cr:
+            if self.AUG.cr_aug_type not in ("cr", "diffaug"):
+                raise NotImplementedError("AUG.cr_aug_type '%s' (built: 'cr', 'diffaug')" % self.AUG.cr_aug_type)
+            self.AUG.parallel_augment = table[self.AUG.cr_aug_type]
+        if self.LOSS.apply_bcr:
+            if self.AUG.bcr_aug_type not in ("bcr", "diffaug"):
+                raise NotImplementedError("AUG.bcr_aug_type '%s' (built: 'bcr', 'diffaug')" % self.AUG.bcr_aug_type)
+            self.AUG.parallel_augment = table[self.AUG.bcr_aug_type]
 
     def define_modules(self):
         return make_modules(self.MODEL.apply_g_sn, self.MODEL.apply_d_sn, self.MODEL.g_cond_mtd, self.MODEL.backbone,

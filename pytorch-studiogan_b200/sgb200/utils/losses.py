@@ -150,3 +150,8 @@ def make_cond_loss(d_cond_mtd, num_classes, LOSS, DDP):
     if d_cond_mtd == "D2DCE":
         return Data2DataCrossEntropyLoss(num_classes=num_classes, temperature=LOSS.temperature, m_p=LOSS.m_p, DDP=DDP)
     return None
+
+
+def lecam_reg(d_logit_real, d_logit_fake, ema):
+    """LeCam regulariser (src/utils/losses.py:262-265): mean relu(D(real) - ema.D_fake)^2 + mean relu(ema.D_real - D(fake))^2."""
+    return torch.mean(F.relu(d_logit_real - ema.D_fake).pow(2)) + torch.mean(F.relu(ema.D_real - d_logit_fake).pow(2))

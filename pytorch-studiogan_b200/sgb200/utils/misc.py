@@ -127,3 +127,7 @@ def apply_standing_statistics(generator, standing_max_batch, standing_step, DATA
                                    num_classes=DATA.num_classes, y_sampler="totally_random", radius="N/A", generator=generator,
                                    discriminator=None, is_train=True, LOSS=LOSS, RUN=RUN, MODEL=MODEL, device=device)
     generator.eval()
+
+
+def identity(x):
+    return x

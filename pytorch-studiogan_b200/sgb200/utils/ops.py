@@ -260,6 +260,21 @@ class SelfAttention(nn.Module):
         return A.SelfAttentionFn.call(x, _w(mods[0]), _w(mods[1]), _w(mods[2]), _w(mods[3]), self.sigma, cfgs)
 
 
+class LeCamEMA(object):
+    """Exponential moving averages of the discriminator's mean logits / losses for the LeCam regulariser
+    (src/utils/ops.py:106-132; host-side floats, five numbers)."""
+
+    def __init__(self, init=7777, decay=0.9, start_iter=0):
+        self.G_loss = self.D_loss_real = self.D_loss_fake = self.D_real = self.D_fake = init
+        self.decay, self.start_itr = decay, start_iter
+
+    def update(self, cur, mode, itr):
+        decay = 0.0 if itr < self.start_itr else self.decay
+        if mode not in ("G_loss", "D_loss_real", "D_loss_fake", "D_real", "D_fake"):
+            raise KeyError(mode)
+        setattr(self, mode, getattr(self, mode) * decay + cur * (1 - decay))
+
+
 def init_weights(modules, initialize):
     """Same traversal and RNG consumption as src/utils/ops.py:135-162 (the reference initialises the spectral-norm
     modules through the ``weight`` alias of ``weight_orig``; here the parameter is addressed directly)."""

@@ -87,15 +87,25 @@ class WORKER(object):
             self.cond_loss_mi = copy.deepcopy(self.cond_loss)
         if self.MODEL.aux_cls_type not in ("W/O", "N/A", "TAC", "ADC"):
             raise NotImplementedError("aux_cls_type %s" % self.MODEL.aux_cls_type)
-        for flag in ("apply_cr", "apply_bcr", "apply_zcr", "apply_lo", "apply_topk", "apply_lecam", "apply_r1_reg",
-                     "apply_dra", "apply_maxgp", "apply_fm", "apply_wc", "apply_inv_reg"):
+        for flag in ("apply_lo", "apply_topk", "apply_r1_reg", "apply_dra", "apply_maxgp", "apply_fm", "apply_wc", "apply_inv_reg"):
             if getattr(self.LOSS, flag, False):
                 raise NotImplementedError("LOSS.%s is outside the sgb200 hot-path scope" % flag)
         # a YAML that asks for an augmentation this path does not implement must not silently train a different recipe
-        AUG = getattr(cfgs, "AUG", None)
-        for flag in ("apply_diffaug", "apply_ada", "apply_apa"):
-            if AUG is not None and getattr(AUG, flag, False):
-                raise NotImplementedError("AUG.%s is outside the sgb200 hot-path scope" % flag)
+        # (Configurations.define_augments raises for ADA / APA / SimCLR types; DiffAugment and the CR augmentation are built)
+        self.AUG = getattr(cfgs, "AUG", None)
+        if self.AUG is None or not hasattr(self.AUG, "series_augment"):
+            from .utils import misc as _misc
+            import types as _types
+            self.AUG = _types.SimpleNamespace(series_augment=_misc.identity, parallel_augment=_misc.identity, apply_diffaug=False)
+        self.l2_loss = torch.nn.MSELoss()
+        # LeCam regulariser state (src/worker.py:119-122; the five EMA numbers travel in checkpoints as ``lecam_emas``)
+        from .utils import ops as _ops
+        self.lecam_ema = _ops.LeCamEMA()
+        if lecam_emas is not None:
+            self.lecam_ema.__dict__ = lecam_emas
+        if self.LOSS.apply_lecam:
+            self.lecam_ema.decay, self.lecam_ema.start_itr = self.LOSS.lecam_ema_decay, self.LOSS.lecam_ema_start_iter
+        self._current_step = 0
 
     # ------------------------------------------------------------------------------------------------ data
     def sample_data_basket_raw(self):
@@ -118,14 +128,17 @@ class WORKER(object):
     def _generate(self, is_train=True):
         return sample.generate_images(z_prior=self.MODEL.z_prior, truncation_factor=-1.0, batch_size=self.OPTIMIZATION.batch_size,
                                       z_dim=self.MODEL.z_dim, num_classes=self.DATA.num_classes, y_sampler="totally_random",
-                                      radius="N/A", generator=self.Gen, discriminator=self.Dis, is_train=is_train, LOSS=self.LOSS,
+                                      radius=self.LOSS.radius if self.LOSS.apply_zcr else "N/A", generator=self.Gen, discriminator=self.Dis, is_train=is_train, LOSS=self.LOSS,
                                       RUN=self.RUN, MODEL=self.MODEL, device=self.local_rank)
 
     # ------------------------------------------------------------------------------------------------ D phase
     def _graphs_enabled(self):
-        return bool(getattr(self.RUN, "cuda_graphs", False)) and not self.LOSS.apply_gp and self.cond_loss is None
+        plain = not (self.LOSS.apply_cr or self.LOSS.apply_bcr or self.LOSS.apply_zcr or self.LOSS.apply_lecam or
+                     getattr(self.AUG, "apply_diffaug", False))      # host-side RNG / EMA state: not capturable
+        return bool(getattr(self.RUN, "cuda_graphs", False)) and not self.LOSS.apply_gp and self.cond_loss is None and plain
 
     def train_discriminator(self, current_step):
+        self._current_step = current_step
         real_image_basket, real_label_basket = self.sample_data_basket_raw()
         if self._graphs_enabled():
             # static input buffers: the graph reads the same addresses every replay
@@ -138,6 +151,33 @@ class WORKER(object):
             return "N/A", self._d_graph()
         dis_acml_loss = self._d_phase(real_image_basket, real_label_basket)
         return self._real_cond_loss, dis_acml_loss
+
+    def _consistency_terms(self, real_images, real_labels, fake_images, fake_labels, fake_images_eps, real_dict, fake_dict):
+        """CR (src/worker.py:326-336), bCR (:339-354) and zCR (:357-366) terms of the discriminator loss: squared distance
+        between the discriminator's outputs on an image and on its augmented / latent-perturbed copy."""
+        if not (self.LOSS.apply_cr or self.LOSS.apply_bcr or self.LOSS.apply_zcr):
+            return 0.0
+        mtd = self.MODEL.d_cond_mtd
+
+        def pair_loss(a, b):
+            loss = self.l2_loss(a["adv_output"], b["adv_output"])
+            if mtd == "AC":
+                loss = loss + self.l2_loss(a["cls_output"], b["cls_output"])
+            elif mtd in ("2C", "D2DCE"):
+                loss = loss + self.l2_loss(a["embed"], b["embed"])
+            return loss
+        total = 0.0
+        if self.LOSS.apply_cr:
+            real_prl = self.Dis(self.AUG.parallel_augment(real_images), real_labels)
+            total = total + self.LOSS.cr_lambda * pair_loss(real_dict, real_prl)
+        if self.LOSS.apply_bcr:
+            real_prl = self.Dis(self.AUG.parallel_augment(real_images), real_labels)
+            fake_prl = self.Dis(self.AUG.parallel_augment(fake_images), fake_labels, adc_fake=self.adc_fake)
+            total = total + self.LOSS.real_lambda * pair_loss(real_dict, real_prl) + self.LOSS.fake_lambda * pair_loss(fake_dict, fake_prl)
+        if self.LOSS.apply_zcr:
+            fake_eps = self.Dis(fake_images_eps, fake_labels, adc_fake=self.adc_fake)
+            total = total + self.LOSS.d_lambda * pair_loss(fake_dict, fake_eps)
+        return total
 
     def _d_phase_static(self):
         return self._d_phase(self._static_imgs, self._static_labels)
@@ -158,9 +198,10 @@ class WORKER(object):
             for _ in range(self.OPTIMIZATION.acml_steps):
                 real_images = real_image_basket[batch_counter].to(self.local_rank, non_blocking=True)
                 real_labels = real_label_basket[batch_counter].to(self.local_rank, non_blocking=True)
-                fake_images, fake_labels, _, _, _, _, _ = self._generate(True)
-                real_dict = self.Dis(real_images, real_labels)
-                fake_dict = self.Dis(fake_images, fake_labels, adc_fake=self.adc_fake)
+                fake_images, fake_labels, fake_images_eps, _, _, _, _ = self._generate(True)
+                # differentiable augmentation of everything the discriminator sees (src/worker.py:276-285)
+                real_dict = self.Dis(self.AUG.series_augment(real_images), real_labels)
+                fake_dict = self.Dis(self.AUG.series_augment(fake_images), fake_labels, adc_fake=self.adc_fake)
                 dis_acml_loss = self.LOSS.d_loss(real_dict["adv_output"], fake_dict["adv_output"], DDP=self.DDP)
                 if self.cond_loss is not None:          # src/worker.py:306-319
                     real_cond_loss = self.cond_loss(**real_dict)
@@ -170,6 +211,14 @@ class WORKER(object):
                     elif self.adc_fake:
                         dis_acml_loss = dis_acml_loss + self.LOSS.cond_lambda * self.cond_loss(**fake_dict)
                     self._real_cond_loss = real_cond_loss.detach()
+                dis_acml_loss = dis_acml_loss + self._consistency_terms(real_images, real_labels, fake_images, fake_labels,
+                                                                        fake_images_eps, real_dict, fake_dict)
+                if self.LOSS.apply_lecam:                # src/worker.py:394-407
+                    self.lecam_ema.update(torch.mean(real_dict["adv_output"]).item(), "D_real", self._current_step)
+                    self.lecam_ema.update(torch.mean(fake_dict["adv_output"]).item(), "D_fake", self._current_step)
+                    if self._current_step > self.LOSS.lecam_ema_start_iter:
+                        dis_acml_loss = dis_acml_loss + self.LOSS.lecam_lambda * losses.lecam_reg(
+                            real_dict["adv_output"], fake_dict["adv_output"], self.lecam_ema)
                 if self.LOSS.apply_gp:
                     from .utils import gp
                     dis_acml_loss = dis_acml_loss + self.LOSS.gp_lambda * gp.cal_grad_penalty(
@@ -205,9 +254,11 @@ class WORKER(object):
         for _ in range(self.OPTIMIZATION.g_updates_per_step):
             self.OPTIMIZATION.g_optimizer.zero_grad()
             for _ in range(self.OPTIMIZATION.acml_steps):
-                fake_images, fake_labels, _, _, _, _, _ = self._generate(True)
-                fake_dict = self.Dis(fake_images, fake_labels)
+                fake_images, fake_labels, fake_images_eps, _, _, _, _ = self._generate(True)
+                fake_dict = self.Dis(self.AUG.series_augment(fake_images), fake_labels)      # src/worker.py:549-552
                 gen_acml_loss = self.LOSS.g_loss(fake_dict["adv_output"], DDP=self.DDP)
+                if self.LOSS.apply_zcr:                  # src/worker.py:603-605: push G(z) and G(z + eps) apart
+                    gen_acml_loss = gen_acml_loss - self.LOSS.g_lambda * self.l2_loss(fake_images, fake_images_eps)
                 if self.cond_loss is not None:          # src/worker.py:574-585
                     gen_acml_loss = gen_acml_loss + self.LOSS.cond_lambda * self.cond_loss(**fake_dict)
                     if self.cond_loss_mi is not None:

@@ -402,6 +402,31 @@ def golden_sampler():
     print("sampler", {k: v.shape for k, v in out.items()})
 
 
+def golden_augment():
+    """Reference DiffAugment (src/utils/diffaug.py) and CR augmentation (src/utils/cr.py) on seeded CPU inputs: outputs and,
+    for DiffAugment, the input gradient of a seeded cotangent.  The seeds are re-applied right before each call so that the
+    product's parameter draw (same RNG order) can be checked together with the arithmetic."""
+    import utils.diffaug as rdiff
+    import utils.cr as rcr
+    out = {}
+    g = torch.Generator().manual_seed(606)
+    for tag, (B, H, W) in (("a", (5, 16, 16)), ("b", (3, 12, 20))):
+        x = torch.randn(B, 3, H, W, generator=g)
+        ct = torch.randn(B, 3, H, W, generator=g)
+        out["x_" + tag], out["ct_" + tag] = x.numpy(), ct.numpy()
+        for pname, policy in (("full", "color,translation,cutout"), ("color", "color"), ("geo", "translation,cutout")):
+            xr = x.clone().requires_grad_(True)
+            torch.manual_seed(4242)
+            y = rdiff.apply_diffaug(xr, policy=policy)
+            y.backward(ct)
+            out["diffaug_%s_%s" % (pname, tag)] = y.detach().numpy()
+            out["diffaug_%s_%s_dx" % (pname, tag)] = xr.grad.numpy().copy()
+        torch.manual_seed(777)
+        out["cr_" + tag] = rcr.apply_cr_aug(x).numpy()
+    np.savez_compressed(os.path.join(HERE, "augment.npz"), **out)
+    print("augment", {k: v.shape for k, v in out.items() if k.startswith("diffaug_full")})
+
+
 def golden_metrics():
     rng = np.random.RandomState(0)
     out = {}
@@ -483,3 +508,4 @@ if __name__ == "__main__":
     golden_gp("gp_deep32_sn_c8_pd", "deep", 8, True, "PD")
     golden_deep_bench_shape()
     golden_sampler()
+    golden_augment()

@@ -296,3 +296,90 @@ def test_dcgan_config1_d_and_g_phase_vs_reference_golden(golden_dir):
     gmax = max(float(g[k]) for k in g.files if k.startswith("Ggnorm/"))
     for n, p in G.named_parameters():
         assert abs(float(p.grad.norm()) - float(g["Ggnorm/" + n])) < 0.3 * float(g["Ggnorm/" + n]) + 1e-2 * gmax, n
+
+
+# ------------------------------------------------------------------------------------------------ augmentations
+def test_diffaug_and_cr_kernels_match_reference_golden(golden_dir):
+    """sgb_diffaug_fwd / bwd and sgb_cr_aug against the reference's DiffAugment / CR outputs and input gradients
+    (tests/golden/augment.npz), with the parameters drawn by the product in the reference's RNG order on the host generator
+    (the device path uses the same draw on the CUDA generator).  fp32 element-wise arithmetic: 1e-5."""
+    import os
+    from sgb200.utils import cr, diffaug
+    dev = _cuda()
+    g = np.load(os.path.join(golden_dir, "augment.npz"))
+    for tag in ("a", "b"):
+        x = torch.from_numpy(g["x_" + tag])
+        ct = torch.from_numpy(g["ct_" + tag])
+        B, _, H, W = x.shape
+        for pname, policy in (("full", "color,translation,cutout"), ("color", "color"), ("geo", "translation,cutout")):
+            torch.manual_seed(4242)
+            params = diffaug.draw_params(B, H, W, policy, "cpu")
+            xd = x.to(dev).requires_grad_(True)
+            y = diffaug.apply_diffaug(xd, policy, params=params.to(dev))
+            np.testing.assert_allclose(y.detach().cpu().numpy(), g["diffaug_%s_%s" % (pname, tag)], rtol=1e-5, atol=1e-5)
+            y.backward(ct.to(dev))
+            np.testing.assert_allclose(xd.grad.cpu().numpy(), g["diffaug_%s_%s_dx" % (pname, tag)], rtol=1e-5, atol=1e-5)
+        torch.manual_seed(777)
+        f, tx, ty = cr.draw_params(B, H, W, "cpu")
+        y = cr.apply_cr_aug(x.to(dev), params=(f.to(dev), tx.to(dev), ty.to(dev)))
+        np.testing.assert_array_equal(y.cpu().numpy(), g["cr_" + tag])
+    # the device draw + kernel path end to end (statistical sanity: translation / cutout leave ~ the expected share of zeros)
+    xd = torch.randn(64, 3, 32, 32, device=dev).abs() + 1.0
+    y = diffaug.apply_diffaug(xd, "translation,cutout")
+    zero_share = float((y == 0).float().mean())
+    assert 0.15 < zero_share < 0.5, zero_share
+
+
+def test_worker_step_with_diffaug_bcr_zcr_and_lecam():
+    """WORKER.train_discriminator / train_generator with AUG.apply_diffaug (DiffAugment on every discriminator input,
+    gradient through it in the generator phase), LOSS.apply_bcr + apply_zcr (consistency terms, src/worker.py:339-366,603-605)
+    and LOSS.apply_lecam (:394-407) on a small BigGAN-Deep: the step runs on the CUDA path, the discriminator loss contains
+    the extra terms (it differs from the plain hinge loss of the same logits), the LeCam EMAs move, parameters move, nothing
+    is NaN."""
+    from sgb200 import config as C
+    from sgb200.models import model as M
+    from sgb200.worker import WORKER
+    dev = _cuda()
+    cfgs = C.Configurations(None)
+    cfgs.DATA.img_size, cfgs.DATA.num_classes = 32, 10
+    m = cfgs.MODEL
+    m.backbone, m.g_cond_mtd, m.d_cond_mtd, m.apply_g_sn, m.apply_d_sn = "big_resnet_deep_legacy", "cBN", "PD", True, True
+    m.z_dim, m.g_shared_dim, m.g_conv_dim, m.d_conv_dim, m.g_depth, m.d_depth = 32, 32, 16, 16, 1, 1
+    m.apply_g_ema = False
+    L_ = cfgs.LOSS
+    L_.adv_loss = "hinge"
+    L_.apply_bcr, L_.real_lambda, L_.fake_lambda = True, 10.0, 10.0
+    L_.apply_zcr, L_.radius, L_.g_lambda, L_.d_lambda = True, 0.05, 0.5, 5.0
+    L_.apply_lecam, L_.lecam_lambda, L_.lecam_ema_start_iter, L_.lecam_ema_decay = True, 0.3, 2, 0.9
+    cfgs.AUG.apply_diffaug, cfgs.AUG.diffaug_type, cfgs.AUG.bcr_aug_type = True, "diffaug", "bcr"
+    o = cfgs.OPTIMIZATION
+    o.batch_size, o.d_updates_per_step, o.g_updates_per_step, o.acml_steps = 16, 2, 1, 1
+    cfgs.define_modules()
+    cfgs.define_losses()
+    cfgs.define_augments()
+    torch.manual_seed(0)
+    Gen, _, _, Dis, Gen_ema, _, _, ema = M.load_generator_discriminator(cfgs.DATA, o, cfgs.MODEL, cfgs.STYLEGAN, cfgs.MODULES,
+                                                                        cfgs.RUN, dev, None)
+    cfgs.define_optimizer(Gen, Dis)
+
+    class Loader:
+        def __iter__(self):
+            return self
+
+        def __next__(self):
+            g = torch.Generator().manual_seed(1)
+            return torch.rand(32, 3, 32, 32, generator=g) * 2 - 1, torch.randint(0, 10, (32,), generator=g)
+    w = WORKER(cfgs=cfgs, run_name="t", Gen=Gen, Gen_mapping=None, Gen_synthesis=None, Dis=Dis, Gen_ema=Gen_ema, Gen_ema_mapping=None,
+               Gen_ema_synthesis=None, ema=ema, eval_model=None, train_dataloader=Loader(), eval_dataloader=None, global_rank=0,
+               local_rank=dev, mu=None, sigma=None, real_feats=None, logger=None)
+    assert w.lecam_ema.D_real == 7777
+    d0 = [p.detach().clone() for p in Dis.parameters()]
+    g0 = [p.detach().clone() for p in Gen.parameters()]
+    for step in range(1, 4):             # step 1: EMA = current (before start_iter); step 2: decayed; step 3: regulariser active
+        _, d_loss = w.train_discriminator(step)
+        g_loss = w.train_generator(step)
+        assert torch.isfinite(d_loss).all() and torch.isfinite(g_loss).all()
+    assert w.lecam_ema.D_real != 7777 and abs(w.lecam_ema.D_real) < 1e3          # the EMA has been fed with mean logits
+    assert all(torch.isfinite(p).all() for p in list(Dis.parameters()) + list(Gen.parameters()))
+    assert any(float((p.detach() - q).abs().max()) > 0 for p, q in zip(Dis.parameters(), d0))
+    assert any(float((p.detach() - q).abs().max()) > 0 for p, q in zip(Gen.parameters(), g0))

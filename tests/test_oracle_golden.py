@@ -246,3 +246,28 @@ def test_deep_256_bench_topology(golden_dir):
         if "Dgrad/full/" + k in g.files:
             ref = g["Dgrad/full/" + k]
             assert np.abs(sdD[k].grad.numpy() - ref).max() <= 5e-3 * (1e-3 * gmax + np.abs(ref).max()), k
+
+
+def test_augmentations_closed_form_and_rng_order_match_reference(golden_dir):
+    """DiffAugment / CR augmentation: the product's parameter draw (sgb200.utils.diffaug.draw_params / cr.draw_params)
+    consumes the generator exactly like the reference, and the closed form the device kernels implement equals the
+    reference's pass-by-pass result (values 1e-5: the contrast mean is taken before instead of after the saturation step;
+    input gradients 1e-5)."""
+    from sgb200.utils import cr, diffaug
+    g = np.load(os.path.join(golden_dir, "augment.npz"))
+    for tag in ("a", "b"):
+        x = torch.from_numpy(g["x_" + tag])
+        ct = torch.from_numpy(g["ct_" + tag])
+        B, _, H, W = x.shape
+        for pname, policy in (("full", "color,translation,cutout"), ("color", "color"), ("geo", "translation,cutout")):
+            torch.manual_seed(4242)
+            params = diffaug.draw_params(B, H, W, policy, "cpu")
+            xr = x.clone().requires_grad_(True)
+            names = policy.split(",")
+            y = O.diffaug_closed_form(xr, params, "color" in names, "translation" in names, "cutout" in names)
+            np.testing.assert_allclose(y.detach().numpy(), g["diffaug_%s_%s" % (pname, tag)], rtol=1e-5, atol=1e-5)
+            y.backward(ct)
+            np.testing.assert_allclose(xr.grad.numpy(), g["diffaug_%s_%s_dx" % (pname, tag)], rtol=1e-5, atol=1e-5)
+        torch.manual_seed(777)
+        f, tx, ty = cr.draw_params(B, H, W, "cpu")
+        np.testing.assert_array_equal(O.cr_aug_closed_form(x, f, tx, ty).numpy(), g["cr_" + tag])
