@@ -260,3 +260,43 @@ def test_device_basket_loader_is_bit_identical_to_the_cpu_transform_chain(tmp_pa
         ref = torch.where(flip[:, None, None, None], ref.flip(3), ref)
         assert x.shape == (24, 3, 16, 12) and x.dtype == torch.float32
         assert torch.equal(x.cpu(), ref) and y.cpu().tolist() == labels[idx].tolist()
+
+
+def test_folder_evaluator_matches_feature_level_metrics(tmp_path):
+    """sgb200.evaluate (src/evaluate.py:112-288, folder mode): two PNG folders -> IS / FID / PRDC.  Checked against the same
+    metrics computed from features extracted directly from the in-memory uint8 arrays (PNG is lossless, so the folder path
+    must reproduce them exactly), plus the pre-computed ``dset1_moments`` / ``dset1_feats`` entry points."""
+    from PIL import Image
+    from sgb200 import evaluate as E
+    from sgb200.metrics import fid, prdc
+    from sgb200.metrics.preparation import LoadEvalModel
+    dev = _cuda()
+    rs = np.random.RandomState(7)
+    sets = {}
+    for name, n, shift in (("a", 24, 0), ("b", 20, 40)):
+        arr = np.clip(rs.randint(0, 216, size=(n, 32, 32, 3)) + shift, 0, 255).astype(np.uint8)
+        os.makedirs(tmp_path / name / "cls0")
+        os.makedirs(tmp_path / name / "cls1")
+        for i in range(n):
+            Image.fromarray(arr[i]).save(str(tmp_path / name / ("cls%d" % (i % 2)) / ("%03d.png" % i)))
+        # ImageFolder order: all of cls0 (even i) then all of cls1 (odd i)
+        sets[name] = np.concatenate([arr[0::2], arr[1::2]], 0)
+    res = E.evaluate(str(tmp_path / "a"), str(tmp_path / "b"), batch_size=16, device=dev)
+    assert res["dset1_size"] == 24 and res["dset2_size"] == 20
+    ev = LoadEvalModel("InceptionV3_tf", "legacy", 1, False, dev)
+    feats = {}
+    for name, arr in sets.items():
+        f, _ = ev.get_outputs(torch.from_numpy(arr).permute(0, 3, 1, 2).float().to(dev), quantize=False)
+        feats[name] = f
+    m1, s1 = fid.calculate_moments(feats["a"])
+    m2, s2 = fid.calculate_moments(feats["b"])
+    ref_fid = fid.frechet_distance_device(m1, s1, m2, s2)
+    assert abs(res["FID"] - ref_fid) <= 1e-6 * max(1.0, abs(ref_fid))
+    ref_pr = prdc.compute_prdc(feats["a"].double(), feats["b"].double(), 5)
+    assert abs(res["Improved_Precision"] - ref_pr["precision"]) < 1e-12 and abs(res["Coverage"] - ref_pr["coverage"]) < 1e-12
+    # pre-computed statistics of dset1 instead of the folder
+    np.savez(str(tmp_path / "m.npz"), mu=m1.cpu().numpy(), sigma=s1.cpu().numpy())
+    np.savez(str(tmp_path / "f.npz"), real_feats=feats["a"].double().cpu().numpy())
+    res2 = E.evaluate(None, str(tmp_path / "b"), dset1_moments=str(tmp_path / "m.npz"), dset1_feats=str(tmp_path / "f.npz"),
+                      batch_size=16, device=dev)
+    assert abs(res2["FID"] - res["FID"]) <= 1e-6 * max(1.0, abs(res["FID"])) and res2["Density"] == res["Density"]
