@@ -19,6 +19,8 @@ class _GraphedPhase:
     live in static device buffers filled before each replay; z / labels come from the device RNG inside the graph; the
     Adam step counters live on the device (ArenaAdam.step_t).  Any capture failure falls back to eager execution."""
 
+    POOL = None                                   # one memory pool for every captured phase: they never replay concurrently
+
     def __init__(self, fn, warmup=2):
         self.fn, self.warmup = fn, warmup
         self.calls = 0
@@ -26,11 +28,16 @@ class _GraphedPhase:
         self.failed = False
         self.launches = 0                         # library launches recorded in the graph (re-issued by every replay)
 
+    def _result(self):
+        """The phase's result copied out of the graph pool: the pool is shared between the phases, so the next replay of the
+        OTHER phase may reuse the memory the captured result lives in."""
+        return self.out.clone() if torch.is_tensor(self.out) else self.out
+
     def __call__(self):
         if self.graph is not None:
             self.graph.replay()
             _lib.LAUNCHES[0] += self.launches
-            return self.out
+            return self._result()
         self.calls += 1
         if self.failed or self.calls <= self.warmup:
             return self.fn()
@@ -39,12 +46,14 @@ class _GraphedPhase:
             torch.cuda.empty_cache()
             g = torch.cuda.CUDAGraph()
             n0 = _lib.LAUNCHES[0]
-            with torch.cuda.graph(g):
+            if _GraphedPhase.POOL is None:
+                _GraphedPhase.POOL = torch.cuda.graph_pool_handle()
+            with torch.cuda.graph(g, pool=_GraphedPhase.POOL):     # D-phase and G-phase graphs share their activation memory
                 out = self.fn()
             self.launches = _lib.LAUNCHES[0] - n0
             self.graph, self.out = g, out
             g.replay()
-            return out
+            return self._result()
         except Exception as ex:  # noqa: BLE001 - keep training alive, eagerly
             self.failed = True
             self.graph = None
