@@ -187,6 +187,89 @@ __host__ __device__ inline int epi_flags_of(const EpiArgs& p) {
   return f;
 }
 
+// Direct-store epilogue of a compile-time variant F >= 0 (bf16 output, Cout % 64 == 0, 16-byte aligned operands): the same
+// arithmetic as epilogue_row without its run-time case analysis, two 16-column pieces per TMEM wait.  Used by the halo-row
+// kernel's second output row at C = 64 (no room for a second staging tile): one full 128-byte line per thread and piece pair.
+template <int F>
+__device__ __forceinline__ void epilogue_row_fast(const EpiArgs& p, uint32_t t_row, int BN, int n0, bool valid, long long pix,
+                                                  long long rpix, float alpha) {
+  static_assert(F >= 0 && (F & kEpiFull), "compile-time variant with a full channel tile");
+  constexpr bool has_bias = (F & kEpiBias) != 0, do_relu = (F & kEpiRelu) != 0, res_pre = (F & kEpiResPre) != 0,
+                 res_post = (F & kEpiResPost) != 0, has_mask = (F & kEpiMask) != 0;
+  const float rs = p.res_scale;
+  bf16* yrow = reinterpret_cast<bf16*>(p.y) + pix * p.y_cstride;
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t v[2][16];
+    __syncwarp();
+    tmem_ld16(t_row + c0, v[0]);
+    tmem_ld16(t_row + c0 + 16, v[1]);
+    tmem_ld_wait();
+    if (!valid || n0 + c0 >= p.Cout) continue;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int n = n0 + c0 + q * 16;
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[q][j]) * alpha;
+      if (has_bias) {
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 bb = __ldg(bp + j);
+          f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+        }
+      }
+      if (res_pre || res_post) {
+        // (residual variants are not instantiated for this path today; kept for completeness of the flag set)
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.res_cstride + n);
+        if (res_pre) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint4 r = __ldg(rp + j);
+            f[8 * j + 0] = fmaf(bf16_bits_lo(r.x), rs, f[8 * j + 0]); f[8 * j + 1] = fmaf(bf16_bits_hi(r.x), rs, f[8 * j + 1]);
+            f[8 * j + 2] = fmaf(bf16_bits_lo(r.y), rs, f[8 * j + 2]); f[8 * j + 3] = fmaf(bf16_bits_hi(r.y), rs, f[8 * j + 3]);
+            f[8 * j + 4] = fmaf(bf16_bits_lo(r.z), rs, f[8 * j + 4]); f[8 * j + 5] = fmaf(bf16_bits_hi(r.z), rs, f[8 * j + 5]);
+            f[8 * j + 6] = fmaf(bf16_bits_lo(r.w), rs, f[8 * j + 6]); f[8 * j + 7] = fmaf(bf16_bits_hi(r.w), rs, f[8 * j + 7]);
+          }
+        }
+      }
+      if (do_relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      if (has_mask) {
+        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_cstride + n);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint4 m = __ldg(mp + j);
+          f[8 * j + 0] = bf16_bits_lo(m.x) > 0.f ? f[8 * j + 0] : 0.f;
+          f[8 * j + 1] = bf16_bits_hi(m.x) > 0.f ? f[8 * j + 1] : 0.f;
+          f[8 * j + 2] = bf16_bits_lo(m.y) > 0.f ? f[8 * j + 2] : 0.f;
+          f[8 * j + 3] = bf16_bits_hi(m.y) > 0.f ? f[8 * j + 3] : 0.f;
+          f[8 * j + 4] = bf16_bits_lo(m.z) > 0.f ? f[8 * j + 4] : 0.f;
+          f[8 * j + 5] = bf16_bits_hi(m.z) > 0.f ? f[8 * j + 5] : 0.f;
+          f[8 * j + 6] = bf16_bits_lo(m.w) > 0.f ? f[8 * j + 6] : 0.f;
+          f[8 * j + 7] = bf16_bits_hi(m.w) > 0.f ? f[8 * j + 7] : 0.f;
+        }
+      }
+      if (res_post) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.res_cstride + n);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint4 r = __ldg(rp + j);
+          f[8 * j + 0] = fmaf(bf16_bits_lo(r.x), rs, f[8 * j + 0]); f[8 * j + 1] = fmaf(bf16_bits_hi(r.x), rs, f[8 * j + 1]);
+          f[8 * j + 2] = fmaf(bf16_bits_lo(r.y), rs, f[8 * j + 2]); f[8 * j + 3] = fmaf(bf16_bits_hi(r.y), rs, f[8 * j + 3]);
+          f[8 * j + 4] = fmaf(bf16_bits_lo(r.z), rs, f[8 * j + 4]); f[8 * j + 5] = fmaf(bf16_bits_hi(r.z), rs, f[8 * j + 5]);
+          f[8 * j + 6] = fmaf(bf16_bits_lo(r.w), rs, f[8 * j + 6]); f[8 * j + 7] = fmaf(bf16_bits_hi(r.w), rs, f[8 * j + 7]);
+        }
+      }
+      uint4* yp = reinterpret_cast<uint4*>(yrow + n);
+      yp[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      yp[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+    }
+  }
+}
+
 // t_row : TMEM address (lane quadrant of this warp, first column of the accumulator).
 // c1..c3: box coordinates (w0, h0, b0) of the tile in the output tensor map; channel coordinate = n0 + chunk * 64.
 // stage : this team's staging buffer (1024-byte aligned).  team in {0,1}; row = accumulator row of this thread.

@@ -222,7 +222,8 @@ conv3x3_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               // one team covers every chunk of its row: run the chunk loop for both parities on the team's own barrier
               epilogue_tile_tma<F>(p.e, &tmY, t_row, p.BN, nt * p.BN, ws * 128, h, b, true, pix, rpix, alpha, stage, team, row, leader, 1);
             } else {
-              epilogue_row(p.e, t_row, p.BN, nt * p.BN, true, pix, rpix, alpha, vec_ok);
+              if constexpr (F >= 0) epilogue_row_fast<F>(p.e, t_row, p.BN, nt * p.BN, true, pix, rpix, alpha);
+              else epilogue_row(p.e, t_row, p.BN, nt * p.BN, true, pix, rpix, alpha, vec_ok);
             }
           }
         } else if (team == 0) {
