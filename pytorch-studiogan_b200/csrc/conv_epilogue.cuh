@@ -142,21 +142,16 @@ __device__ __forceinline__ void epilogue_row(const EpiArgs& p, uint32_t t_row, i
 static constexpr int kEpiThreads = 256;           // 8 epilogue warps
 
 // Optional auxiliary operand of the epilogue (the residual OR the ReLU-mask tensor) staged by TMA: one SWIZZLE_128B box of
-// the same pixels (or of the half-resolution source pixels for the nearest-x2 residual) per 64-channel chunk.
+// the same pixels (or of the half-resolution source pixels for the nearest-x2 residual) per 64-channel chunk.  The boxes are
+// fetched by a dedicated producer warp into a per-team ring of ``depth`` tiles (full / empty mbarriers), in the order the team
+// consumes its chunks, so their ~1-2 us latency under load overlaps ``depth`` chunks of epilogue work instead of one.
 struct EpiAux {
   int kind;                 // 1 residual, 2 mask
-  const CUtensorMap* tm;
-  uint32_t stage;           // 1024-byte aligned staging tile of this team
-  uint32_t bar;             // mbarrier (count 1)
-  uint32_t* phase;          // per-thread phase bit, toggled per chunk
-  uint32_t bytes;           // bytes of one box
-  int c1, c2, c3;           // box coordinates (w, h, b) in the auxiliary tensor
-  int arow;                 // staging-tile row this thread reads
-  // Prefetch: the box of the NEXT chunk (same tile, or this team's first chunk of the CTA's next tile) is requested as soon
-  // as the current chunk's staging tile has been consumed, so its ~1 us latency hides behind the store / the next MMAs.
-  uint32_t* primed;         // leader-only flag: the load for the upcoming chunk is already in flight
-  int has_next;             // next tile exists and has a chunk for this team
-  int n_nbase, n_c1, n_c2, n_c3;
+  uint32_t ring;            // this team's first aux tile (1024-byte aligned), tiles 16 KiB apart
+  uint32_t full0, empty0;   // this team's first full / empty mbarrier (8 bytes apart per slot)
+  int depth;                // ring slots per team
+  uint32_t* cnt;            // per-thread count of chunks consumed by this team
+  int arow;                 // aux-tile row this thread reads
 };
 
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
@@ -289,7 +284,6 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
   // nbuf chunks ago -- the latency of the previous tensor stores is off the critical path and more bytes are in flight.
   const uint32_t sw = (uint32_t)(row & 7);
   const int aux_kind = (aux && (res_pre || res_post || has_mask)) ? aux->kind : 0;   // 1: residual tile via TMA, 2: mask tile via TMA
-  const uint32_t arow_addr = aux ? aux->stage + (uint32_t)aux->arow * 128u : 0u;
   const uint32_t asw = aux ? (uint32_t)(aux->arow & 7) : 0u;
   for (int cc = (chunk_stride == 2 ? team : 0); cc * 64 < BN; cc += chunk_stride) {
     const int nbase = n0 + cc * 64;
@@ -304,16 +298,12 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
     }
     if (sbuf) *sbuf = (*sbuf + 1u == (uint32_t)nbuf) ? 0u : *sbuf + 1u;
     named_bar_sync(1 + team, 128);
-    if (aux_kind) {                              // residual / mask chunk for this tile: one TMA box instead of strided 16-byte loads
-      if (leader) {
-        if (!*aux->primed) {
-          mbar_arrive_expect_tx(aux->bar, aux->bytes);
-          tma_load_4d(aux->stage, aux->tm, aux->bar, nbase, aux->c1, aux->c2, aux->c3);
-        }
-        *aux->primed = 0u;
-      }
-      mbar_wait(aux->bar, *aux->phase);
-      *aux->phase ^= 1u;
+    uint32_t arow_addr = 0u, aslot = 0u;
+    if (aux_kind) {                              // residual / mask chunk: one TMA box (fetched ahead by the aux producer warp)
+      aslot = *aux->cnt % (uint32_t)aux->depth;
+      mbar_wait(aux->full0 + 8u * aslot, (*aux->cnt / (uint32_t)aux->depth) & 1u);
+      arow_addr = aux->ring + aslot * kEpiStageBytes + (uint32_t)aux->arow * 128u;
+      *aux->cnt += 1u;
     }
     // compile-time variants handle two 16-column pieces per iteration: both TMEM loads are in flight before the single wait
     // (the variants use ~77 registers, the general version 102), which hides part of the LDTM latency that two warps per
@@ -401,18 +391,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
     if (leader) {
       tma_store_4d(tmY, stage_cur, nbase, c1, c2, c3);
       bulk_commit();
-      if (aux_kind) {                            // every thread of the team is past its last read of the aux tile (barrier above)
-        const int cc2 = cc + chunk_stride;
-        if (cc2 * 64 < BN && n0 + cc2 * 64 < p.Cout) {
-          mbar_arrive_expect_tx(aux->bar, aux->bytes);
-          tma_load_4d(aux->stage, aux->tm, aux->bar, n0 + cc2 * 64, aux->c1, aux->c2, aux->c3);
-          *aux->primed = 1u;
-        } else if (aux->has_next) {
-          mbar_arrive_expect_tx(aux->bar, aux->bytes);
-          tma_load_4d(aux->stage, aux->tm, aux->bar, aux->n_nbase, aux->n_c1, aux->n_c2, aux->n_c3);
-          *aux->primed = 1u;
-        }
-      }
+      if (aux_kind) mbar_arrive(aux->empty0 + 8u * aslot);   // every thread of the team is past its last read of the aux tile (barrier above)
     }
   }
 }

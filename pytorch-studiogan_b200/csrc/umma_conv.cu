@@ -36,6 +36,7 @@ struct FpropArgs {
   int epi_nbuf;                   // staging tiles per epilogue team (2..4: stores overlap the next chunks' conversion)
   int b_resident;                 // 1: every weight tile of this CTA's channel tile stays in shared memory (loaded once)
   int aux_kind, aux_tw, aux_th;   // residual (1) / mask (2) tile staged by TMA; its box is aux_tw x aux_th x nb pixels
+  int aux_depth;                  // aux tiles per epilogue team (ring filled by the aux producer warp)
   int out_sub;                    // 2: store only even (h, w) outputs at (h/2, w/2) -> stride-2 convolution (Inception reduction blocks)
   uint32_t tmem_cols;
   EpiArgs e;
@@ -49,7 +50,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t epi_stage_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // two 16 KiB staging tiles when use_tma
   const uint32_t aux_stage_base = epi_stage_base + (p.use_tma ? 2u * p.epi_nbuf * kEpiStageBytes : 0u);   // + two aux tiles when aux_kind
   const uint32_t b_bytes = (uint32_t)p.BN * kBlockK * 2;  // same size for K-major [BN][64] and MN-major (BN/64) x [64][64]
-  const uint32_t bres_base = aux_stage_base + (p.aux_kind ? 2u * kEpiStageBytes : 0u);     // resident weight tiles [tap][kb]
+  const uint32_t bres_base = aux_stage_base + (p.aux_kind ? 2u * p.aux_depth * kEpiStageBytes : 0u);     // resident weight tiles [tap][kb]
   const uint32_t smem_base = bres_base + (p.b_resident ? (uint32_t)(p.taps * p.kblocks) * b_bytes : 0u);
   const uint32_t stage_bytes = kABytes + (p.b_resident ? 0u : b_bytes);  // multiple of 1024 because BN % 8 == 0 -> b_bytes % 1024 == 0
   const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
@@ -58,8 +59,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
   const uint32_t holder = bar_base + 8u * (2 * p.stages + 4);
-  auto aux_bar = [&](int t) { return bar_base + 8u * (2 * p.stages + 6 + t); };
-  const uint32_t bres_bar = bar_base + 8u * (2 * p.stages + 8);
+  const uint32_t bres_bar = bar_base + 8u * (2 * p.stages + 6);
+  auto aux_full = [&](int team, int slot) { return bar_base + 8u * (2 * p.stages + 8 + team * p.aux_depth + slot); };
+  auto aux_empty = [&](int team, int slot) { return bar_base + 8u * (2 * p.stages + 8 + (2 + team) * p.aux_depth + slot); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -74,7 +76,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kEpiThreads);
-      mbar_init(aux_bar(a), 1);
+      for (int sl = 0; sl < p.aux_depth; ++sl) { mbar_init(aux_full(a, sl), 1); mbar_init(aux_empty(a, sl), 1); }
     }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
@@ -165,6 +167,31 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         umma_commit(tfull_bar(a));    // accumulator complete
       }
     }
+  } else if (warp == 2) {
+    if (lane == 0 && p.aux_kind) {
+      // ------------------------------------------------------------- aux producer: residual / mask boxes, in the order the
+      // two epilogue teams consume their chunks (team = chunk & 1), up to aux_depth boxes ahead per team
+      const bool half = p.aux_kind == 1 && p.e.res_up2;
+      const uint32_t bytes = (uint32_t)(p.aux_tw * p.aux_th * p.nb) * 128u;
+      uint32_t cnt[2] = {0u, 0u};
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int nt = t % p.tiles_n; t /= p.tiles_n;
+        const int wt = t % p.tiles_w; t /= p.tiles_w;
+        const int ht = t % p.tiles_h; t /= p.tiles_h;
+        const int c1 = half ? (wt * p.tw) >> 1 : wt * p.tw, c2 = half ? (ht * p.th) >> 1 : ht * p.th, c3 = t * p.nb;
+        for (int cc = 0; cc * 64 < p.BN; ++cc) {
+          const int nbase = nt * p.BN + cc * 64;
+          if (nbase >= p.e.Cout) break;
+          const int team = cc & 1;
+          const uint32_t slot = cnt[team] % (uint32_t)p.aux_depth;
+          mbar_wait(aux_empty(team, slot), ((cnt[team] / (uint32_t)p.aux_depth) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(aux_full(team, slot), bytes);
+          tma_load_4d(aux_stage_base + (uint32_t)(team * p.aux_depth + slot) * kEpiStageBytes, &tmAux, aux_full(team, slot), nbase, c1, c2, c3);
+          ++cnt[team];
+        }
+      }
+    }
   } else if (warp >= 4) {
     // --------------------------------------------------------------- epilogue: 8 warps, TMEM lane quadrant = warp % 4
     const int q = warp & 3;
@@ -175,11 +202,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool vec_ok = epi_vec_ok(p.e);
     const float alpha = p.e.alpha_ptr ? p.e.alpha * __ldg(p.e.alpha_ptr) : p.e.alpha;
     const uint32_t stage = epi_stage_base + team * p.epi_nbuf * kEpiStageBytes;
-    uint32_t aux_phase = 0, aux_primed = 0, sbuf = 0;
+    uint32_t aux_cnt = 0, sbuf = 0;
     EpiAux aux;
-    aux.primed = &aux_primed; aux.has_next = 0; aux.n_nbase = aux.n_c1 = aux.n_c2 = aux.n_c3 = 0;
-    aux.kind = p.aux_kind; aux.tm = &tmAux; aux.stage = aux_stage_base + team * kEpiStageBytes; aux.bar = aux_bar(team);
-    aux.phase = &aux_phase; aux.bytes = (uint32_t)(p.aux_tw * p.aux_th * p.nb) * 128u;
+    aux.kind = p.aux_kind; aux.ring = aux_stage_base + (uint32_t)(team * p.aux_depth) * kEpiStageBytes;
+    aux.full0 = aux_full(team, 0); aux.empty0 = aux_empty(team, 0); aux.depth = p.aux_depth; aux.cnt = &aux_cnt;
     const bool aux_half = p.aux_kind == 1 && p.e.res_up2;
     aux.arow = aux_half ? ((bi * p.aux_th + (p.aux_th == p.th ? hi : (hi >> 1))) * p.aux_tw + (wi >> 1)) : row;
     uint32_t tcount = 0;
@@ -201,22 +227,6 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + a * p.BN;
       if (p.use_tma) {
-        aux.c1 = aux_half ? (wt * p.tw) >> 1 : wt * p.tw;
-        aux.c2 = aux_half ? (ht * p.th) >> 1 : ht * p.th;
-        aux.c3 = bt * p.nb;
-        const int ntile = tile + (int)gridDim.x;       // this CTA's next tile: its first chunk of this team is prefetched
-        aux.has_next = 0;
-        if (p.aux_kind && ntile < p.num_tiles) {
-          int u = ntile;
-          const int nt2 = u % p.tiles_n; u /= p.tiles_n;
-          const int wt2 = u % p.tiles_w; u /= p.tiles_w;
-          const int ht2 = u % p.tiles_h; u /= p.tiles_h;
-          aux.n_nbase = nt2 * p.BN + team * 64;
-          aux.has_next = (team * 64 < p.BN && aux.n_nbase < p.e.Cout) ? 1 : 0;
-          aux.n_c1 = aux_half ? (wt2 * p.tw) >> 1 : wt2 * p.tw;
-          aux.n_c2 = aux_half ? (ht2 * p.th) >> 1 : ht2 * p.th;
-          aux.n_c3 = u * p.nb;
-        }
         epilogue_tile_tma<F>(p.e, &tmY, t_row, p.BN, n0, wt * p.tw, ht * p.th, bt * p.nb, valid, pix, rpix, alpha, stage, team, row,
                           leader, 2, p.aux_kind ? &aux : nullptr, p.epi_nbuf >= 2 ? &sbuf : nullptr, p.epi_nbuf);
       } else if (team == 0) {
@@ -476,12 +486,12 @@ static int env_int(const char* name, int dflt) {
 }
 // Bring-up switches: read from the environment ONCE per process (a conv launch used to call getenv five times).
 struct EngineSwitches {
-  int conv3x3_rows, rows_base_offset, epi_tma, epi_tma_maxk, epi_aux, epi_nbuf, wgrad3x3, b_resident;
+  int conv3x3_rows, rows_base_offset, epi_tma, epi_tma_maxk, epi_aux, epi_nbuf, wgrad3x3, b_resident, aux_depth;
 };
 static const EngineSwitches& switches() {
   static const EngineSwitches s = {env_int("SGB_CONV3X3_ROWS", 1), env_int("SGB_ROWS_BASE_OFFSET", 0), env_int("SGB_EPI_TMA", 1),
                                    env_int("SGB_EPI_TMA_MAXK", 640), env_int("SGB_EPI_AUX", 1), env_int("SGB_EPI_NBUF", 2),
-                                   env_int("SGB_WGRAD3X3", 1), env_int("SGB_B_RESIDENT", 1)};
+                                   env_int("SGB_WGRAD3X3", 1), env_int("SGB_B_RESIDENT", 1), env_int("SGB_AUX_DEPTH", 2)};
   return s;
 }
 
@@ -564,8 +574,11 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   const uint32_t stage_bytes = kABytes + (p.b_resident ? 0u : b_tile);
   const int nbuf_want = switches().epi_nbuf < 1 ? 1 : (switches().epi_nbuf > 4 ? 4 : switches().epi_nbuf);
   p.epi_nbuf = (p.use_tma && kt <= 2) ? nbuf_want : 1;
-  auto ring_kb = [&](int nbuf) { return (kt <= 2 ? 216 : 200) - (p.use_tma ? 32 * nbuf : 0) - (p.aux_kind ? 32 : 0) - (p.b_resident ? (int)(kt * b_tile / 1024) : 0); };
-  while (p.epi_nbuf > 1 && ring_kb(p.epi_nbuf) * 1024 < (int)(3 * stage_bytes)) --p.epi_nbuf;     // keep >= 3 ring stages
+  p.aux_depth = p.aux_kind ? (switches().aux_depth < 1 ? 1 : (switches().aux_depth > 3 ? 3 : switches().aux_depth)) : 1;
+  auto ring_kb = [&](int nbuf) { return 216 - (p.use_tma ? 32 * nbuf : 0) - (p.aux_kind ? 32 * p.aux_depth : 0) - (p.b_resident ? (int)(kt * b_tile / 1024) : 0); };
+  // keep >= 3 operand ring stages: give back aux depth first, then staging tiles
+  while (p.aux_kind && p.aux_depth > 1 && ring_kb(p.epi_nbuf) * 1024 < (int)(3 * stage_bytes)) --p.aux_depth;
+  while (p.epi_nbuf > 1 && ring_kb(p.epi_nbuf) * 1024 < (int)(3 * stage_bytes)) --p.epi_nbuf;
   int stages = ring_kb(p.epi_nbuf) * 1024 / (int)stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
@@ -606,8 +619,8 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
     rc = make_act_tmap(&tmAux, ap, d->B, half ? d->H / 2 : d->H, half ? d->W / 2 : d->W, d->Cout, acs, p.aux_tw, p.aux_th, p.nb);
     if (rc) return rc;
   }
-  const size_t smem = (size_t)stages * stage_bytes + (p.use_tma ? 2 * p.epi_nbuf * kEpiStageBytes : 0) + (p.aux_kind ? 2 * kEpiStageBytes : 0) +
-                      (p.b_resident ? (size_t)kt * b_tile : 0) + 1024 + 8 * (2 * stages + 9) + 16;
+  const size_t smem = (size_t)stages * stage_bytes + (p.use_tma ? 2 * p.epi_nbuf * kEpiStageBytes : 0) + (p.aux_kind ? 2 * p.aux_depth * kEpiStageBytes : 0) +
+                      (p.b_resident ? (size_t)kt * b_tile : 0) + 1024 + 8 * (2 * stages + 8 + 4 * 3) + 16;
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   // the hot epilogue shapes of the training step get compile-time variants; everything else takes the general kernel
   const int f = p.use_tma ? epi_flags_of(p.e) : -1;
