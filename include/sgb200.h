@@ -73,6 +73,11 @@ typedef struct sgb_conv_desc {
   int32_t out_sub;
   float res_scale;     /* residual multiplier (0 is read as 1): 0.25 with res_up2 = the backward of a 2x2 average pooling
                           added in the epilogue (src/models/big_resnet_deep_legacy.py:220-224, the pooled skip branch) */
+  /* ReLU masks as bit planes (Cout % 64 == 0, bf16 output): [B*H*W][Cout/64] 64-bit words, bit j of word c = channel 64c + j.
+   * relu_bits (needs relu = 1): written next to y, bit = (y > 0);  mask_bits: used instead of ``mask`` (1/16 of its bytes) by
+   * the input-gradient launch of the layer that consumed y (the in-place d_act_fn of src/config.py:486 in backward). */
+  const void* mask_bits;
+  void* relu_bits;
 } sgb_conv_desc;
 
 int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream);
@@ -193,7 +198,8 @@ int sgb_axpby(const void* x, int64_t xs, const void* y, int64_t ys, const void* 
 /* 2x2 pooling to [B,Ho,Wo,C]; mode 0 average, 1 max. */
 int sgb_pool2_fwd(const void* x, int64_t xs, void* y, int64_t ys, int32_t B, int32_t Ho, int32_t Wo, int32_t C, int32_t mode,
                   sgb_stream_t stream);
-/* dx = pool2 backward of dy (+ add) (masked by relu_src > 0); x needed for max (first max in scan order wins). */
+/* dx = pool2 backward of dy (+ add) (masked by relu_src > 0); x needed for max (first max in scan order wins).
+ * rs == -1: relu_src holds the bit planes a relu conv epilogue wrote (sgb_conv_desc.relu_bits) instead of the bf16 tensor. */
 /* a0 = relu(x) (full resolution) and y = 2x2 average of a0, one pass: entry of a down-sampling discriminator block
  * (self.activation + self.average_pooling on the skip, src/models/big_resnet_deep_legacy.py:211-224,
  * src/models/big_resnet_deep_studiogan.py:233-249). */

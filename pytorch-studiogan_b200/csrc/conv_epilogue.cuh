@@ -15,7 +15,23 @@ struct EpiArgs {
   const bf16* mask; long long mask_cstride;
   int relu;
   void* y; long long y_cstride; int y_fp32;
+  // ReLU masks as bit planes (Cout % 64 == 0): one 64-bit word per (pixel, 64-channel chunk), bit j = channel 64 * chunk + j.
+  // mask_bits replaces ``mask`` (1/16 of its bytes); relu_bits is written by a relu epilogue for the consumer's backward.
+  const unsigned long long* mask_bits;
+  unsigned long long* relu_bits;
 };
+
+// 16 accumulator values -> 16 mask bits (value > 0)
+__device__ __forceinline__ uint32_t positive_bits16(const float (&f)[16]) {
+  uint32_t b = 0u;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) b |= (f[j] > 0.f) ? (1u << j) : 0u;
+  return b;
+}
+__device__ __forceinline__ void apply_bits16(float (&f)[16], uint32_t mb) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) f[j] = ((mb >> j) & 1u) ? f[j] : 0.f;
+}
 
 __device__ __forceinline__ float bf16_bits_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_bits_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
@@ -69,8 +85,13 @@ __device__ __forceinline__ void epilogue_row(const EpiArgs& p, uint32_t t_row, i
       if (p.relu) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        if (p.relu_bits)
+          reinterpret_cast<unsigned short*>(p.relu_bits)[(pix * (p.Cout >> 6) + (n >> 6)) * 4 + ((n >> 4) & 3)] =
+              (unsigned short)positive_bits16(f);
       }
-      if (p.mask) {
+      if (p.mask_bits) {
+        apply_bits16(f, __ldg(reinterpret_cast<const unsigned short*>(p.mask_bits) + (pix * (p.Cout >> 6) + (n >> 6)) * 4 + ((n >> 4) & 3)));
+      } else if (p.mask) {
         const uint4* mp = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_cstride + n);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -177,7 +198,7 @@ __host__ __device__ inline int epi_flags_of(const EpiArgs& p) {
   if (p.bias) f |= kEpiBias;
   if (p.relu) f |= kEpiRelu;
   if (p.residual) f |= p.res_after ? kEpiResPost : kEpiResPre;
-  if (p.mask) f |= kEpiMask;
+  if (p.mask || p.mask_bits) f |= kEpiMask;
   if (p.Cout % 64 == 0) f |= kEpiFull;
   return f;
 }
@@ -231,8 +252,13 @@ __device__ __forceinline__ void epilogue_row_fast(const EpiArgs& p, uint32_t t_r
       if (do_relu) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        if (p.relu_bits)
+          reinterpret_cast<unsigned short*>(p.relu_bits)[(pix * (p.Cout >> 6) + (n >> 6)) * 4 + ((n >> 4) & 3)] =
+              (unsigned short)positive_bits16(f);
       }
-      if (has_mask) {
+      if (has_mask && p.mask_bits) {
+        apply_bits16(f, __ldg(reinterpret_cast<const unsigned short*>(p.mask_bits) + (pix * (p.Cout >> 6) + (n >> 6)) * 4 + ((n >> 4) & 3)));
+      } else if (has_mask) {
         const uint4* mp = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_cstride + n);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -277,7 +303,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
   const bool do_relu = F < 0 ? p.relu != 0 : (F & kEpiRelu) != 0;
   const bool res_pre = F < 0 ? (p.residual != nullptr && !p.res_after) : (F & kEpiResPre) != 0;
   const bool res_post = F < 0 ? (p.residual != nullptr && p.res_after) : (F & kEpiResPost) != 0;
-  const bool has_mask = F < 0 ? p.mask != nullptr : (F & kEpiMask) != 0;
+  const bool has_mask = F < 0 ? (p.mask != nullptr || p.mask_bits != nullptr) : (F & kEpiMask) != 0;
+  const bool use_mbits = has_mask && p.mask_bits != nullptr;
+  const bool emit_bits = do_relu && p.relu_bits != nullptr;
+  const long long nw = p.Cout >> 6;
   const bool full_c = F >= 0 && (F & kEpiFull) != 0;       // no channel-tail tests
   const float rs = p.res_scale;
   // sbuf != nullptr: the team owns ``nbuf`` (2..4) staging tiles used round-robin, so a chunk only waits for the store issued
@@ -288,6 +317,11 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
   for (int cc = (chunk_stride == 2 ? team : 0); cc * 64 < BN; cc += chunk_stride) {
     const int nbase = n0 + cc * 64;
     if (nbase >= p.Cout) break;
+    uint32_t mlo = 0u, mhi = 0u, olo = 0u, ohi = 0u;
+    if (use_mbits && valid) {                    // 8 bytes instead of a 128-byte line of the bf16 activation
+      const uint2 m = __ldg(reinterpret_cast<const uint2*>(p.mask_bits) + pix * nw + (nbase >> 6));
+      mlo = m.x; mhi = m.y;
+    }
     const uint32_t stage_cur = stage + (sbuf ? *sbuf * kEpiStageBytes : 0u);
     const uint32_t srow = stage_cur + (uint32_t)row * 128u;
     if (leader) {                                // the store that last used this staging tile has finished reading it
@@ -309,7 +343,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
     // (the variants use ~77 registers, the general version 102), which hides part of the LDTM latency that two warps per
     // scheduler cannot hide by themselves
     constexpr int NP = F >= 0 ? 2 : 1;
-    auto piece = [&](const int s, const uint32_t (&v)[16]) {
+    auto piece = [&](const int s, const uint32_t (&v)[16], const uint32_t mb) -> uint32_t {
         const int n = nbase + s * 16;
         float f[16];
 #pragma unroll
@@ -338,11 +372,15 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
             f[8 * j + 6] = fmaf(bf16_bits_lo(r.w), rs, f[8 * j + 6]); f[8 * j + 7] = fmaf(bf16_bits_hi(r.w), rs, f[8 * j + 7]);
           }
         }
+        uint32_t ob = 0u;
         if (do_relu) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          if (emit_bits) ob = positive_bits16(f);
         }
-        if (has_mask && in_c && valid) {
+        if (use_mbits) {
+          apply_bits16(f, mb);
+        } else if (has_mask && in_c && valid) {
           const uint4* mp = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_cstride + n);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
@@ -375,6 +413,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
                      pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
         st_shared_v4(srow + (((uint32_t)(2 * s + 1) ^ sw) << 4), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
                      pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+        return ob;
     };
 #pragma unroll 1
     for (int s0 = 0; s0 < 4; s0 += NP) {
@@ -384,8 +423,14 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
       for (int q = 0; q < NP; ++q) tmem_ld16(t_row + cc * 64 + (s0 + q) * 16, v[q]);
       tmem_ld_wait();
 #pragma unroll
-      for (int q = 0; q < NP; ++q) piece(s0 + q, v[q]);
+      for (int q = 0; q < NP; ++q) {
+        const int s = s0 + q;
+        const uint32_t ob = piece(s, v[q], ((s < 2 ? mlo : mhi) >> (16 * (s & 1))) & 0xFFFFu);
+        if (s < 2) olo |= ob << (16 * (s & 1));
+        else ohi |= ob << (16 * (s & 1));
+      }
     }
+    if (emit_bits && valid) reinterpret_cast<uint2*>(p.relu_bits)[pix * nw + (nbase >> 6)] = make_uint2(olo, ohi);
     fence_proxy_async_smem();                    // generic-proxy smem writes -> visible to the TMA (async proxy)
     named_bar_sync(1 + team, 128);
     if (leader) {

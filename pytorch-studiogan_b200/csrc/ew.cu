@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(256) relu_pool2_kernel(const bf16* __restrict_
 // Backward of 2x2 pooling, one thread = 8 channels of one OUTPUT-resolution pixel, writes the 4 input-resolution pixels.
 // mode 0 (avg): dx = 0.25*dy; mode 1 (max): dy routed to the first maximum in (h,w) scan order (torch MaxPool2d).
 // Optional: add (same layout as dx) is summed in, relu_src masks the result where relu_src <= 0.
+template <bool BITS>
 __global__ void __launch_bounds__(256) pool2_bwd_kernel(const bf16* __restrict__ dy, long long dys, const bf16* __restrict__ x,
                                                          long long xs, const bf16* __restrict__ add, long long adds,
                                                          const bf16* __restrict__ relu_src, long long rs, bf16* __restrict__ dx,
@@ -163,7 +164,11 @@ __global__ void __launch_bounds__(256) pool2_bwd_kernel(const bf16* __restrict__
 #pragma unroll
       for (int k = 0; k < 4; ++k) ra[k] = __ldg(reinterpret_cast<const uint4*>(add + qs[k] * adds) + g);
     }
-    if (relu_src) {
+    unsigned char rb[4];
+    if (BITS) {                    // bit planes: one byte = these 8 channels of one pixel
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rb[k] = __ldg(reinterpret_cast<const unsigned char*>(relu_src) + qs[k] * VG + g);
+    } else if (relu_src) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) rr[k] = __ldg(reinterpret_cast<const uint4*>(relu_src + qs[k] * rs) + g);
     }
@@ -175,7 +180,10 @@ __global__ void __launch_bounds__(256) pool2_bwd_kernel(const bf16* __restrict__
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[k][j] += t[j];
       }
-      if (relu_src) {
+      if (BITS) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[k][j] = ((rb[k] >> j) & 1) ? o[k][j] : 0.f;
+      } else if (relu_src) {
         float t[8];
         unpack8(rr[k], t);
 #pragma unroll
@@ -721,9 +729,13 @@ extern "C" int sgb_pool2_bwd(const void* dy, int64_t dys, const void* x, int64_t
   cudaStream_t stream = (cudaStream_t)stream_;
   SGB_REQUIRE(dy && dx && B > 0 && Ho > 0 && Wo > 0 && C > 0 && C % 8 == 0 && dys % 8 == 0 && dxs % 8 == 0);
   SGB_REQUIRE(mode == 0 || (x && xs % 8 == 0));
-  SGB_REQUIRE((!add || adds % 8 == 0) && (!relu_src || rs % 8 == 0));
-  pool2_bwd_kernel<<<ew_blocks((long long)B * Ho * Wo * (C / 8)), 256, 0, stream>>>(
-      (const bf16*)dy, dys, (const bf16*)x, xs, (const bf16*)add, adds, (const bf16*)relu_src, rs, (bf16*)dx, dxs, B, Ho, Wo, C, mode);
+  SGB_REQUIRE((!add || adds % 8 == 0) && (!relu_src || rs % 8 == 0 || (rs == -1 && C % 64 == 0)));   // rs == -1: relu_src = bit planes
+  if (relu_src && rs == -1)
+    pool2_bwd_kernel<true><<<ew_blocks((long long)B * Ho * Wo * (C / 8)), 256, 0, stream>>>(
+        (const bf16*)dy, dys, (const bf16*)x, xs, (const bf16*)add, adds, (const bf16*)relu_src, rs, (bf16*)dx, dxs, B, Ho, Wo, C, mode);
+  else
+    pool2_bwd_kernel<false><<<ew_blocks((long long)B * Ho * Wo * (C / 8)), 256, 0, stream>>>(
+        (const bf16*)dy, dys, (const bf16*)x, xs, (const bf16*)add, adds, (const bf16*)relu_src, rs, (bf16*)dx, dxs, B, Ho, Wo, C, mode);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }

@@ -459,6 +459,8 @@ void fill_epi(EpiArgs& e, const sgb_conv_desc* d) {
   e.res_scale = d->res_scale != 0.f ? d->res_scale : 1.f;
   e.mask = (const bf16*)d->mask; e.mask_cstride = d->mask_cstride; e.relu = d->relu;
   e.y = d->y; e.y_cstride = d->y_cstride; e.y_fp32 = d->y_fp32;
+  e.mask_bits = (const unsigned long long*)d->mask_bits;
+  e.relu_bits = (unsigned long long*)d->relu_bits;
 }
 
 static int make_act_tmap(CUtensorMap* m, const void* base, int B, int H, int W, int C, long long cstride, int tw, int th,
@@ -519,6 +521,11 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   SGB_REQUIRE(d->w_mode == 0 || (d->KH == 1 && d->KW == 1 && d->H * d->W >= 128));
   SGB_REQUIRE(d->w_mode != 2 || d->Cout % 8 == 0);
   SGB_REQUIRE(((uintptr_t)d->bias & 15) == 0 && ((uintptr_t)d->residual & 15) == 0 && ((uintptr_t)d->mask & 15) == 0);
+  // bit-plane ReLU masks: whole 64-channel words, vector epilogue paths only
+  SGB_REQUIRE(!d->mask_bits || (!d->mask && d->Cout % 64 == 0 && !d->y_fp32 && d->out_sub != 2 && ((uintptr_t)d->mask_bits & 7) == 0));
+  SGB_REQUIRE(!d->relu_bits || (d->relu && d->Cout % 64 == 0 && !d->y_fp32 && d->out_sub != 2 && d->y_cstride % 8 == 0 &&
+                                ((uintptr_t)d->relu_bits & 7) == 0));
+  SGB_REQUIRE(!(d->mask_bits || d->relu_bits) || ((!d->residual || d->res_cstride % 8 == 0) && d->y_cstride % 8 == 0));
   {
     // wide, few-channel 3x3 layers: halo-row kernel (umma_conv3x3.cu).  SGB_CONV3X3_ROWS=0 forces the generic kernel.
     const EngineSwitches& sw = switches();
@@ -559,10 +566,11 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
                p.taps * d->Cin <= switches().epi_tma_maxk && switches().epi_tma) ? 1 : 0;   // output-heavy layers only
   // auxiliary epilogue operand through TMA: exactly one of residual / mask, bf16 NHWC with 16-byte aligned channel stride
   p.aux_kind = 0; p.aux_tw = p.tw; p.aux_th = p.th;
-  if (p.use_tma && switches().epi_aux && (d->residual != nullptr || d->mask != nullptr)) {
+  if (p.use_tma && switches().epi_aux && (d->residual != nullptr || d->mask != nullptr)) {   // (mask_bits are 8-byte direct loads)
     // one operand rides TMA: the mask when both are present (full-resolution tile; the residual of such launches is the
     // quarter-size pooled-skip gradient, whose direct 16-byte loads are shared by 2x2 pixel neighbours through L1)
     if (d->mask) p.aux_kind = 2;
+    else if (!d->residual) p.aux_kind = 0;                       // bit-plane mask only: nothing to stage
     else if (!d->res_up2) p.aux_kind = 1;
     else if (p.tw >= 2) { p.aux_kind = 1; p.aux_tw = p.tw / 2; p.aux_th = p.th >= 2 ? p.th / 2 : 1; }
   }

@@ -36,6 +36,7 @@ class ConvDesc(ctypes.Structure):
         ("y", c_p), ("y_cstride", c_i64), ("y_fp32", c_int),
         ("Hin", c_int), ("Win", c_int), ("out_sub", c_int),
         ("res_scale", c_f),
+        ("mask_bits", c_p), ("relu_bits", c_p),
     ]
 
 

@@ -178,7 +178,9 @@ class ConvFn(TFunction):
         res = residual
         y = K.conv_fprop(x, wf, Cout_p, KH, KW, pad, pad, bias=bias if Cout_p == Cout else _pad_bias(bias, Cout_p),
                          residual=res, res_up2=cfg.get("res_up2", False), relu=cfg.get("relu", False),
-                         out_fp32=cfg.get("out_fp32", False), stride=cfg.get("stride", 1))
+                         out_fp32=cfg.get("out_fp32", False), stride=cfg.get("stride", 1),
+                         want_relu_bits=cfg.get("premasked", False) and any(ctx.needs_input_grad))
+        ctx.x_bits = getattr(x, "_sgb_relu_bits", None) if (need_dx and cfg.get("mask_input", False)) else None
         if need_dw and sn is not None and cache is None:
             u_saved, v_saved = u.clone(), v.clone()
         ctx.cfg = cfg
@@ -204,6 +206,7 @@ class ConvFn(TFunction):
         dx = dW = dbias = dres = None
         if ctx.needs_input_grad[0]:
             mask = x if cfg.get("mask_input", False) else None
+            mbits = ctx.x_bits
             if Cout <= 3 and KH == 3 and KW == 3 and pad == 1 and cfg.get("perm_S", 1) == 1:
                 # C -> 3 image convolution (generator output layer): its input gradient is a 3 -> C convolution of the
                 # 3-channel dz; gather dz's 3x3 patches (K = 27 -> 32) and run it as a 1x1 GEMM instead of a K-padded 3x3.
@@ -212,7 +215,7 @@ class ConvFn(TFunction):
                 wf2, _ = K.weight_pack(wcol, None, Cin, 27, 1, True, False)
                 dx = K.conv_fprop(K.col27(dz), wf2, K.pad8(Cin), 1, 1, 0, 0, mask=mask)
             else:
-                dx = K.conv_fprop(dz, wd, K.pad8(Cin), KH, KW, KH - 1 - pad, KW - 1 - pad, mask=mask)
+                dx = K.conv_fprop(dz, wd, K.pad8(Cin), KH, KW, KH - 1 - pad, KW - 1 - pad, mask=mask, mask_bits=mbits)
             if dx.shape[1] != x.shape[1]:
                 dx = dx[:, :x.shape[1]]
         if not SKIP_PARAM_GRADS:
@@ -498,13 +501,14 @@ class AvgPoolFn(TFunction):
     @staticmethod
     def forward(ctx, x, input_is_relu_out):
         ctx.input_is_relu_out = input_is_relu_out
-        ctx.save_for_backward(x if input_is_relu_out else None)
+        ctx.x_bits = getattr(x, "_sgb_relu_bits", None) if input_is_relu_out else None
+        ctx.save_for_backward(x if (input_is_relu_out and ctx.x_bits is None) else None)
         return K.pool2_fwd(x, 0)
 
     @staticmethod
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
-        return K.pool2_bwd(K.as_nhwc(dy), 0, relu_src=x), None
+        return K.pool2_bwd(K.as_nhwc(dy), 0, relu_src=x, relu_bits=ctx.x_bits), None
 
     @staticmethod
     def tangent(args, out, tan):
@@ -588,7 +592,8 @@ class DEntryConvFn(TFunction):
         B, Cin, H, W, _ = K.geom(a0)
         hid = weight.shape[0]
         wf, wd, sigma, us, vs = _sn_packs(weight, cfg, hid, Cin, 1, True)
-        h1 = K.conv_fprop(a0, wf, hid, 1, 1, 0, 0, bias=bias, relu=True)
+        h1 = K.conv_fprop(a0, wf, hid, 1, 1, 0, 0, bias=bias, relu=True, want_relu_bits=any(ctx.needs_input_grad))
+        ctx.a0_bits = getattr(a0, "_sgb_relu_bits", None) if ctx.needs_input_grad[0] else None
         down = cfg["downsample"]
         if down:
             sc = cfg.get("skip_channels", 0) or Cin
@@ -614,7 +619,7 @@ class DEntryConvFn(TFunction):
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             down = cfg["downsample"]
-            dx = K.conv_fprop(dz, wd, Cin, 1, 1, 0, 0, mask=a0, residual=K.as_nhwc(dpx) if dpx is not None else None,
+            dx = K.conv_fprop(dz, wd, Cin, 1, 1, 0, 0, mask=a0, mask_bits=ctx.a0_bits, residual=K.as_nhwc(dpx) if dpx is not None else None,
                               res_up2=down, res_scale=0.25 if down else 1.0)
         if not SKIP_PARAM_GRADS:
             dW, db = conv_param_grads(a0, dz, weight, ctx.needs_input_grad[1], ctx.needs_input_grad[2], 1, 1, 0, ctx.dims,

@@ -5,10 +5,16 @@ Activation convention: a torch tensor of logical shape [B, C, H, W], dtype bfloa
 current CUDA stream of the tensor's device.
 """
 import ctypes
+import os
 
 import torch
 
 from . import _lib as L
+
+# ReLU masks of the discriminators travel to the backward as bit planes (1/16 of the bf16 bytes); SGB_RELU_BITS=0 reads the
+# stored activations instead (A/B switch, read once).
+RELU_BITS = os.environ.get("SGB_RELU_BITS", "1") != "0"
+BITS_STATS = {"written": 0, "used": 0}
 
 bf16 = torch.bfloat16
 
@@ -56,8 +62,10 @@ def _s():
 # ---------------------------------------------------------------------------------------------- conv engine
 def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_up2=False, res_after_mask=False,
                mask=None, relu=False, alpha=1.0, alpha_ptr=None, out=None, out_fp32=False, w_mode=0, same_size=True, stride=1,
-               res_scale=1.0):
+               res_scale=1.0, mask_bits=None, want_relu_bits=False):
     """y = epilogue(conv(x, w)); see sgb_conv_fprop. ``w`` is a packed bf16 weight (layout by w_mode).
+    want_relu_bits (with relu): also write the (y > 0) bit planes, returned as ``y._sgb_relu_bits`` (uint8 [B, H, W, Cout / 8]);
+    mask_bits: such a tensor, used instead of ``mask`` by the input-gradient launch of the layer that consumed y.
     same_size=False: output grid = Hin + 2*pad - K + 1 ("valid"-style); stride=2 stores its even positions only.
     res_scale: multiplier of the residual (0.25 with res_up2 = average-pool backward added in the epilogue)."""
     B, Cin, Hin, Win, xcs = geom(x)
@@ -82,9 +90,19 @@ def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_u
     d.res_up2 = 1 if res_up2 else 0
     d.res_scale = float(res_scale)
     d.res_after_mask = 1 if res_after_mask else 0
+    if mask_bits is not None:
+        assert mask_bits.dtype == torch.uint8 and mask_bits.numel() == B * H * W * Cout // 8 and Cout % 64 == 0
+        d.mask_bits, mask = mask_bits.data_ptr(), None
+        BITS_STATS["used"] += 1
     if mask is not None:
         d.mask, d.mask_cstride = mask.data_ptr(), geom(mask)[4]
     d.relu = 1 if relu else 0
+    bits = None
+    if want_relu_bits and relu and RELU_BITS and Cout % 64 == 0 and stride == 1 and out.dtype == bf16 and ycs % 8 == 0:
+        bits = torch.empty((B, H, W, Cout // 8), device=x.device, dtype=torch.uint8)
+        d.relu_bits = bits.data_ptr()
+        out._sgb_relu_bits = bits
+        BITS_STATS["written"] += 1
     d.y, d.y_cstride, d.y_fp32 = out.data_ptr(), ycs, 1 if out.dtype == torch.float32 else 0
     # algorithmic bytes: every operand tensor once (the residual at its own resolution), weights once
     nb = 2.0 * B * Hin * Win * Cin + out.element_size() * float(B * Ho * Wo * Cout) + 2.0 * Cout * Cin * KH * KW * (B if w_mode else 1)
@@ -92,7 +110,16 @@ def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_u
         nb += 2.0 * B * H * W * Cout / (4 if res_up2 else 1)
     if mask is not None:
         nb += 2.0 * B * H * W * Cout
-    L.call("sgb_conv_fprop", ctypes.byref(d), _s(), tag="conv_fprop %dx%d %d->%d @%dx%d m%d" % (KH, KW, Cin, Cout, H, W, w_mode),
+    if mask_bits is not None:
+        nb += B * H * W * Cout / 8.0
+    if bits is not None:
+        nb += B * H * W * Cout / 8.0
+    # accounting kind = the kernel the library dispatches (csrc/umma_conv3x3.cu conv3x3_rows_eligible): the halo-row kernel, the
+    # generic kernel on a k x k filter (tensor bound) or on a 1x1 filter (HBM bound at these channel counts)
+    rows = (KH == 3 and KW == 3 and pad_h == 1 and pad_w == 1 and w_mode == 0 and same_size and stride == 1 and W % 128 == 0
+            and H % 2 == 0 and Cin % 64 == 0 and Cin <= 128 and Cout % 8 == 0)
+    kind = "conv3x3_rows" if rows else ("conv_fprop_1x1" if KH * KW == 1 else "conv_fprop_kxk")
+    L.call("sgb_conv_fprop", ctypes.byref(d), _s(), tag="%s %dx%d %d->%d @%dx%d m%d" % (kind, KH, KW, Cin, Cout, H, W, w_mode),
            flops=2.0 * B * H * W * Cout * Cin * KH * KW, nbytes=nb)
     return out
 
@@ -250,12 +277,19 @@ def relu_pool2(x):
     return a0, y
 
 
-def pool2_bwd(dy, mode, x=None, add=None, relu_src=None):
+def pool2_bwd(dy, mode, x=None, add=None, relu_src=None, relu_bits=None):
+    """relu_bits: the bit planes of the post-ReLU input (see conv_fprop), used instead of ``relu_src``."""
     B, C, Ho, Wo, dys = geom(dy)
     dx = empty_nhwc(B, C, 2 * Ho, 2 * Wo, dy.device)
+    if relu_bits is not None:
+        assert relu_bits.dtype == torch.uint8 and relu_bits.numel() == B * 4 * Ho * Wo * C // 8 and C % 64 == 0
+        rsrc, rs = relu_bits.data_ptr(), -1
+        BITS_STATS["used"] += 1
+    else:
+        rsrc, rs = L.ptr(relu_src), geom(relu_src)[4] if relu_src is not None else 0
     L.call("sgb_pool2_bwd", L.ptr(dy), dys, L.ptr(x), geom(x)[4] if x is not None else 0, L.ptr(add),
-           geom(add)[4] if add is not None else 0, L.ptr(relu_src), geom(relu_src)[4] if relu_src is not None else 0, L.ptr(dx),
-           geom(dx)[4], B, Ho, Wo, C, mode, _s(), nbytes=_nb(dy, x, add, relu_src, dx))
+           geom(add)[4] if add is not None else 0, rsrc, rs, L.ptr(dx),
+           geom(dx)[4], B, Ho, Wo, C, mode, _s(), nbytes=_nb(dy, x, add, relu_bits if relu_bits is not None else relu_src, dx))
     return dx
 
 

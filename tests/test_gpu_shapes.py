@@ -383,3 +383,83 @@ def test_worker_step_with_diffaug_bcr_zcr_and_lecam():
     assert all(torch.isfinite(p).all() for p in list(Dis.parameters()) + list(Gen.parameters()))
     assert any(float((p.detach() - q).abs().max()) > 0 for p, q in zip(Dis.parameters(), d0))
     assert any(float((p.detach() - q).abs().max()) > 0 for p, q in zip(Gen.parameters(), g0))
+
+
+# (B, H, W, Cin, Cout, k): epilogue paths that write / read ReLU bit planes
+BIT_SHAPES = [
+    (2, 64, 64, 128, 64, 1),      # generic kernel, TMA-store epilogue, one 64-channel chunk
+    (2, 32, 32, 64, 256, 1),      # ... four chunks, two teams
+    (1, 256, 256, 64, 64, 3),     # halo-row kernel: staging-tile row + direct-store row
+    (1, 128, 128, 128, 128, 3),   # halo-row kernel, two chunks
+    (2, 16, 16, 256, 256, 3),     # generic kernel, direct-store epilogue (K > TMA-store limit)
+    (3, 20, 20, 64, 128, 1),      # ragged pixel tiles (clipped rows)
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", BIT_SHAPES)
+def test_relu_bit_planes_written_and_consumed(B, H, W, Cin, Cout, k):
+    """A relu epilogue's bit planes equal (y > 0) packed little-endian per 64-channel word, and an input-gradient launch
+    masked by those bits equals the launch masked by the bf16 tensor, bit for bit."""
+    from sgb200 import kernels as K
+    dev = _cuda()
+    g = torch.Generator().manual_seed(Cin * 7 + Cout + k)
+    x = to_nhwc(bfr(torch.randn(B, Cin, H, W, generator=g)), dev)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / np.sqrt(Cin * k * k)).to(dev)
+    b = torch.randn(Cout, generator=g).to(dev)
+    wf, wd = K.weight_pack(w, None, Cout, Cin, k * k, True, True)
+    y = K.conv_fprop(x, wf, Cout, k, k, k // 2, k // 2, bias=b, relu=True, want_relu_bits=True)
+    y_plain = K.conv_fprop(x, wf, Cout, k, k, k // 2, k // 2, bias=b, relu=True)
+    bits = y._sgb_relu_bits
+    assert torch.equal(y, y_plain)
+    pos = (y.permute(0, 2, 3, 1).float() > 0).cpu().numpy()                       # [B, H, W, C]
+    expect = np.packbits(pos, axis=-1, bitorder="little")
+    got = bits.cpu().numpy()
+    # a positive accumulator below the smallest bf16 rounds to zero in y but keeps its bit: allow only that direction
+    diff = np.unpackbits(got ^ expect, axis=-1, bitorder="little").astype(bool)
+    assert diff.mean() < 1e-6 and not (diff & pos).any()
+    # consumer: dgrad of a layer whose INPUT was y (mask has Cout_of_dgrad = Cout channels)
+    dz = to_nhwc(bfr(torch.randn(B, Cin, H, W, generator=g)), dev)
+    wt = (torch.randn(Cin, Cout, k, k, generator=g) / np.sqrt(Cout * k * k)).to(dev)   # next layer: Cout -> Cin
+    _, wtd = K.weight_pack(wt, None, Cin, Cout, k * k, True, True)
+    dx_ref = K.conv_fprop(dz, wtd, Cout, k, k, k - 1 - k // 2, k - 1 - k // 2, mask=y)
+    dx_bits = K.conv_fprop(dz, wtd, Cout, k, k, k - 1 - k // 2, k - 1 - k // 2, mask_bits=bits)
+    if diff.any():
+        keep = torch.from_numpy(~diff).to(dev).permute(0, 3, 1, 2)
+        assert torch.equal(dx_ref * keep, dx_bits * keep)
+    else:
+        assert torch.equal(dx_ref, dx_bits)
+    # with a half-resolution residual on top (fused discriminator block entry)
+    if H % 2 == 0 and k == 1:
+        r = to_nhwc(bfr(torch.randn(B, Cout, H // 2, W // 2, generator=g)), dev)
+        a = K.conv_fprop(dz, wtd, Cout, 1, 1, 0, 0, mask=y, residual=r, res_up2=True, res_scale=0.25)
+        c = K.conv_fprop(dz, wtd, Cout, 1, 1, 0, 0, mask_bits=bits, residual=r, res_up2=True, res_scale=0.25)
+        assert diff.any() or torch.equal(a, c)
+
+
+def test_pool2_bwd_with_bit_planes_and_d_block_uses_them():
+    from sgb200 import kernels as K
+    dev = _cuda()
+    g = torch.Generator().manual_seed(3)
+    B, C, H, W = 2, 128, 32, 32
+    x = to_nhwc(bfr(torch.randn(B, 64, H, W, generator=g)), dev)
+    w = (torch.randn(C, 64, 1, 1, generator=g) / 8).to(dev)
+    wf, _ = K.weight_pack(w, None, C, 64, 1, True, False)
+    y = K.conv_fprop(x, wf, C, 1, 1, 0, 0, relu=True, want_relu_bits=True)
+    dy = to_nhwc(bfr(torch.randn(B, C, H // 2, W // 2, generator=g)), dev)
+    assert torch.equal(K.pool2_bwd(dy, 0, relu_src=y), K.pool2_bwd(dy, 0, relu_bits=y._sgb_relu_bits))
+    # the discriminator block hands bit planes from producer to consumer (no silent fallback to the bf16 masks)
+    import importlib
+    from sgb200 import config as Cfg
+    deep = importlib.import_module("sgb200.models.big_resnet_deep_legacy")
+    M = Cfg.make_modules(True, True, "cBN", "big_resnet_deep_legacy")
+    MODEL = Cfg._Section(info_type="N/A", g_info_injection="N/A")
+    torch.manual_seed(0)
+    D = deep.Discriminator(img_size=32, d_conv_dim=64, apply_d_sn=True, apply_attn=False, attn_d_loc=[1], d_cond_mtd="PD",
+                           aux_cls_type="W/O", d_embed_dim="N/A", normalize_d_embed=False, num_classes=5, d_init="ortho",
+                           d_depth=1, mixed_precision=False, MODULES=M, MODEL=MODEL).to(dev).train()
+    img = (torch.rand(4, 3, 32, 32, generator=g) * 2 - 1).to(dev).requires_grad_(True)
+    lab = torch.randint(0, 5, (4,), generator=g).to(dev)
+    K.BITS_STATS.update(written=0, used=0)
+    D(img, lab)["adv_output"].sum().backward()
+    if K.RELU_BITS:
+        assert K.BITS_STATS["written"] > 0 and K.BITS_STATS["used"] >= K.BITS_STATS["written"] - 1, K.BITS_STATS   # (the head reads the last tensor itself)
