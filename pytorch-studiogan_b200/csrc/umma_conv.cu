@@ -677,11 +677,25 @@ extern "C" int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream_) {
   p.tiles_per_group = p.pix_tiles / p.groups;
   p.dw_group_stride = (long long)d->Cout * p.taps * d->Cin;
   const int base_items = p.tiles_m * p.tiles_n * p.taps * p.groups;
-  int splits = (2 * sm_count() + base_items - 1) / base_items;
-  if (splits > p.tiles_per_group) splits = p.tiles_per_group;
-  if (splits < 1) splits = 1;
-  p.tiles_per_split = (p.tiles_per_group + splits - 1) / splits;
-  p.splits = (p.tiles_per_group + p.tiles_per_split - 1) / p.tiles_per_split;
+  // K-splits: the persistent grid runs ceil(items / SMs) rounds of one item (= tiles_per_split pixel tiles + a drain) each, so
+  // pick the split count that minimises rounds x (tiles_per_split + drain); r02 ncu: 9 taps x 33 splits = 297 items ran as
+  // 148 + 148 + 1 and left the SMs idle for a third of the launch.
+  {
+    const int sms = sm_count();
+    const int max_splits = p.tiles_per_group < (4 * sms + base_items - 1) / base_items ? p.tiles_per_group : (4 * sms + base_items - 1) / base_items;
+    const long long drain = 2;                      // accumulator drain (fp32 red.add of a 128 x BN block) in pixel-tile units
+    long long best_cost = -1;
+    int best = 1;
+    for (int s = 1; s <= (max_splits < 1 ? 1 : max_splits); ++s) {
+      const int tps = (p.tiles_per_group + s - 1) / s;
+      const int eff = (p.tiles_per_group + tps - 1) / tps;
+      const long long rounds = ((long long)base_items * eff + sms - 1) / sms;
+      const long long cost = rounds * (tps + drain);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+    }
+    p.tiles_per_split = (p.tiles_per_group + best - 1) / best;
+    p.splits = (p.tiles_per_group + p.tiles_per_split - 1) / p.tiles_per_split;
+  }
   p.num_items = base_items * p.splits;
   const uint32_t stage_bytes = 2 * kABytes + (p.BN / 64) * kABytes;
   int stages = (int)(((d->dbias ? 224 - 16 : 200) * 1024) / stage_bytes);   // the ones slab must not cost a pipeline stage
