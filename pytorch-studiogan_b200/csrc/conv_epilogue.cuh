@@ -192,6 +192,11 @@ __device__ __forceinline__ bool epi_use_tma(const EpiArgs& p, int BN) {
 // time (bit 0 bias, 1 ReLU, 2 residual before the activation, 3 residual after the mask, 4 mask, 5 Cout % 64 == 0 and every
 // 16-byte alignment holds); F < 0 is the fully general run-time version.
 static constexpr int kEpiBias = 1, kEpiRelu = 2, kEpiResPre = 4, kEpiResPost = 8, kEpiMask = 16, kEpiFull = 32;
+// ... bit 6: the mask is a bit plane (mask_bits), 7 / 8: the residual / the bf16 mask tile arrives through the aux TMA ring,
+// 9: the ReLU epilogue also writes its bit plane (relu_bits).  r02 ncu of the fused block-entry dgrad (mask + residual): with these
+// three questions left to run time the compiler if-converts both sides of each and the piece loop issues 12 instructions per
+// output element (the bias-only variant: 2).
+static constexpr int kEpiMaskBits = 64, kEpiAuxRes = 128, kEpiAuxMask = 256, kEpiBitsOut = 512;
 
 __host__ __device__ inline int epi_flags_of(const EpiArgs& p) {
   int f = 0;
@@ -199,6 +204,8 @@ __host__ __device__ inline int epi_flags_of(const EpiArgs& p) {
   if (p.relu) f |= kEpiRelu;
   if (p.residual) f |= p.res_after ? kEpiResPost : kEpiResPre;
   if (p.mask || p.mask_bits) f |= kEpiMask;
+  if (p.mask_bits) f |= kEpiMaskBits;
+  if (p.relu && p.relu_bits) f |= kEpiBitsOut;
   if (p.Cout % 64 == 0) f |= kEpiFull;
   return f;
 }
@@ -252,13 +259,13 @@ __device__ __forceinline__ void epilogue_row_fast(const EpiArgs& p, uint32_t t_r
       if (do_relu) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-        if (p.relu_bits)
+        if constexpr ((F & kEpiBitsOut) != 0)
           reinterpret_cast<unsigned short*>(p.relu_bits)[(pix * (p.Cout >> 6) + (n >> 6)) * 4 + ((n >> 4) & 3)] =
               (unsigned short)positive_bits16(f);
       }
-      if (has_mask && p.mask_bits) {
+      if constexpr (has_mask && (F & kEpiMaskBits) != 0) {
         apply_bits16(f, __ldg(reinterpret_cast<const unsigned short*>(p.mask_bits) + (pix * (p.Cout >> 6) + (n >> 6)) * 4 + ((n >> 4) & 3)));
-      } else if (has_mask) {
+      } else if constexpr (has_mask) {
         const uint4* mp = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_cstride + n);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -294,33 +301,44 @@ __device__ __forceinline__ void epilogue_row_fast(const EpiArgs& p, uint32_t t_r
 // t_row : TMEM address (lane quadrant of this warp, first column of the accumulator).
 // c1..c3: box coordinates (w0, h0, b0) of the tile in the output tensor map; channel coordinate = n0 + chunk * 64.
 // stage : this team's staging buffer (1024-byte aligned).  team in {0,1}; row = accumulator row of this thread.
-template <int F>
+// NH: warps per (team, lane quadrant).  1: a thread converts all four 16-column pieces of its row of the chunk; 2: two warps share
+// the row (``half`` 0 / 1 takes pieces 0-1 / 2-3), a team is 8 warps -- twice the warps per scheduler to hide the TMEM-load /
+// shared-memory latencies of the per-piece chain (r02 ncu of a 1x1 launch: 3 warps per scheduler, one eligible 46 % of cycles).
+template <int F, int NH = 1>
 __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtensorMap* tmY, uint32_t t_row, int BN, int n0,
                                                   int c1, int c2, int c3, bool valid, long long pix, long long rpix, float alpha,
                                                   uint32_t stage, int team, int row, bool leader, int chunk_stride = 2,
-                                                  const EpiAux* aux = nullptr, uint32_t* sbuf = nullptr, int nbuf = 2) {
+                                                  const EpiAux* aux = nullptr, uint32_t* sbuf = nullptr, int nbuf = 2, int half = 0) {
+  constexpr int kTeamThreads = 128 * NH;
+  const int sbeg = half * (4 / NH), send = sbeg + 4 / NH;
   const bool has_bias = F < 0 ? p.bias != nullptr : (F & kEpiBias) != 0;
   const bool do_relu = F < 0 ? p.relu != 0 : (F & kEpiRelu) != 0;
   const bool res_pre = F < 0 ? (p.residual != nullptr && !p.res_after) : (F & kEpiResPre) != 0;
   const bool res_post = F < 0 ? (p.residual != nullptr && p.res_after) : (F & kEpiResPost) != 0;
   const bool has_mask = F < 0 ? (p.mask != nullptr || p.mask_bits != nullptr) : (F & kEpiMask) != 0;
-  const bool use_mbits = has_mask && p.mask_bits != nullptr;
-  const bool emit_bits = do_relu && p.relu_bits != nullptr;
+  const bool use_mbits = F < 0 ? (has_mask && p.mask_bits != nullptr) : (F & kEpiMaskBits) != 0;
+  const bool emit_bits = F < 0 ? (do_relu && p.relu_bits != nullptr) : (F & kEpiBitsOut) != 0;
   const long long nw = p.Cout >> 6;
   const bool full_c = F >= 0 && (F & kEpiFull) != 0;       // no channel-tail tests
   const float rs = p.res_scale;
   // sbuf != nullptr: the team owns ``nbuf`` (2..4) staging tiles used round-robin, so a chunk only waits for the store issued
   // nbuf chunks ago -- the latency of the previous tensor stores is off the critical path and more bytes are in flight.
   const uint32_t sw = (uint32_t)(row & 7);
-  const int aux_kind = (aux && (res_pre || res_post || has_mask)) ? aux->kind : 0;   // 1: residual tile via TMA, 2: mask tile via TMA
+  // 1: residual tile via TMA, 2: mask tile via TMA (compile-time for F >= 0: the host sets the aux bits iff it passes ``aux``)
+  const int aux_kind = F < 0 ? ((aux && (res_pre || res_post || has_mask)) ? aux->kind : 0)
+                             : ((F & kEpiAuxRes) ? 1 : ((F & kEpiAuxMask) ? 2 : 0));
   const uint32_t asw = aux ? (uint32_t)(aux->arow & 7) : 0u;
   for (int cc = (chunk_stride == 2 ? team : 0); cc * 64 < BN; cc += chunk_stride) {
     const int nbase = n0 + cc * 64;
     if (nbase >= p.Cout) break;
     uint32_t mlo = 0u, mhi = 0u, olo = 0u, ohi = 0u;
     if (use_mbits && valid) {                    // 8 bytes instead of a 128-byte line of the bf16 activation
-      const uint2 m = __ldg(reinterpret_cast<const uint2*>(p.mask_bits) + pix * nw + (nbase >> 6));
-      mlo = m.x; mhi = m.y;
+      if (NH == 1) {
+        const uint2 m = __ldg(reinterpret_cast<const uint2*>(p.mask_bits) + pix * nw + (nbase >> 6));
+        mlo = m.x; mhi = m.y;
+      } else {
+        mlo = mhi = __ldg(reinterpret_cast<const uint32_t*>(p.mask_bits) + (pix * nw + (nbase >> 6)) * 2 + half);
+      }
     }
     const uint32_t stage_cur = stage + (sbuf ? *sbuf * kEpiStageBytes : 0u);
     const uint32_t srow = stage_cur + (uint32_t)row * 128u;
@@ -331,7 +349,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
       else bulk_wait_read3();
     }
     if (sbuf) *sbuf = (*sbuf + 1u == (uint32_t)nbuf) ? 0u : *sbuf + 1u;
-    named_bar_sync(1 + team, 128);
+    named_bar_sync(1 + team, kTeamThreads);
     uint32_t arow_addr = 0u, aslot = 0u;
     if (aux_kind) {                              // residual / mask chunk: one TMA box (fetched ahead by the aux producer warp)
       aslot = *aux->cnt % (uint32_t)aux->depth;
@@ -416,7 +434,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
         return ob;
     };
 #pragma unroll 1
-    for (int s0 = 0; s0 < 4; s0 += NP) {
+    for (int s0 = sbeg; s0 < send; s0 += NP) {
       uint32_t v[NP][16];
       __syncwarp();
 #pragma unroll
@@ -430,9 +448,12 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
         else ohi |= ob << (16 * (s & 1));
       }
     }
-    if (emit_bits && valid) reinterpret_cast<uint2*>(p.relu_bits)[pix * nw + (nbase >> 6)] = make_uint2(olo, ohi);
+    if (emit_bits && valid) {
+      if (NH == 1) reinterpret_cast<uint2*>(p.relu_bits)[pix * nw + (nbase >> 6)] = make_uint2(olo, ohi);
+      else reinterpret_cast<uint32_t*>(p.relu_bits)[(pix * nw + (nbase >> 6)) * 2 + half] = half ? ohi : olo;
+    }
     fence_proxy_async_smem();                    // generic-proxy smem writes -> visible to the TMA (async proxy)
-    named_bar_sync(1 + team, 128);
+    named_bar_sync(1 + team, kTeamThreads);
     if (leader) {
       tma_store_4d(tmY, stage_cur, nbase, c1, c2, c3);
       bulk_commit();

@@ -19,7 +19,8 @@
 namespace sgb {
 
 static constexpr int kWgradThreads = 192;                // wgrad: warps 0 producer, 1 MMA, 2..5 epilogue
-static constexpr int kThreads = 128 + kEpiThreads;  // warps 0..3: producer / MMA / (idle), warps 4..11: epilogue teams
+static constexpr int kFpropEpiThreads = 512;       // 16 epilogue warps: 2 teams x 4 lane quadrants x 2 column halves
+static constexpr int kThreads = 128 + kFpropEpiThreads;  // warps 0..3: producer / MMA / aux producer / (idle), warps 4..19: epilogue teams
 static constexpr int kTileM = 128;          // pixels (fprop) or output channels (wgrad) per tile = TMEM lanes
 static constexpr int kBlockK = 64;          // bf16 elements per 128-byte swizzle row
 static constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB
@@ -75,7 +76,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiThreads);
+      mbar_init(tempty_bar(a), kFpropEpiThreads);
       for (int sl = 0; sl < p.aux_depth; ++sl) { mbar_init(aux_full(a, sl), 1); mbar_init(aux_empty(a, sl), 1); }
     }
     mbar_init(bres_bar, 1);
@@ -193,11 +194,13 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp >= 4) {
-    // --------------------------------------------------------------- epilogue: 8 warps, TMEM lane quadrant = warp % 4
+    // --------------------------------------------------------------- epilogue: 16 warps, TMEM lane quadrant = warp % 4;
+    // team = which 64-channel chunks (even / odd), half = which two of the four 16-column pieces of a chunk
     const int q = warp & 3;
-    const int team = (warp - 4) >> 2;
+    const int team = ((warp - 4) >> 2) & 1;
+    const int half = (warp - 4) >> 3;
     const int row = q * 32 + lane;
-    const bool leader = (q == 0) && (lane == 0);
+    const bool leader = (q == 0) && (lane == 0) && (half == 0);
     const int wi = row % p.tw, hi = (row / p.tw) % p.th, bi = row / (p.tw * p.th);
     const bool vec_ok = epi_vec_ok(p.e);
     const float alpha = p.e.alpha_ptr ? p.e.alpha * __ldg(p.e.alpha_ptr) : p.e.alpha;
@@ -227,9 +230,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + a * p.BN;
       if (p.use_tma) {
-        epilogue_tile_tma<F>(p.e, &tmY, t_row, p.BN, n0, wt * p.tw, ht * p.th, bt * p.nb, valid, pix, rpix, alpha, stage, team, row,
-                          leader, 2, p.aux_kind ? &aux : nullptr, p.epi_nbuf >= 2 ? &sbuf : nullptr, p.epi_nbuf);
-      } else if (team == 0) {
+        epilogue_tile_tma<F, 2>(p.e, &tmY, t_row, p.BN, n0, wt * p.tw, ht * p.th, bt * p.nb, valid, pix, rpix, alpha, stage, team, row,
+                             leader, 2, p.aux_kind ? &aux : nullptr, p.epi_nbuf >= 2 ? &sbuf : nullptr, p.epi_nbuf, half);
+      } else if (team == 0 && half == 0) {
         epilogue_row(p.e, t_row, p.BN, n0, valid, pix, rpix, alpha, vec_ok);
       }
       tc_fence_before();
@@ -631,19 +634,27 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
                       (p.b_resident ? (size_t)kt * b_tile : 0) + 1024 + 8 * (2 * stages + 8 + 4 * 3) + 16;
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   // the hot epilogue shapes of the training step get compile-time variants; everything else takes the general kernel
-  const int f = p.use_tma ? epi_flags_of(p.e) : -1;
+  int f = p.use_tma ? epi_flags_of(p.e) : -1;
+  if (f >= 0 && p.aux_kind == 1) f |= kEpiAuxRes;
+  if (f >= 0 && p.aux_kind == 2) f |= kEpiAuxMask;
+#define SGB_FPROP_CASE(FLAGS) \
+  case (FLAGS): return launch_fprop<(FLAGS)>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);
   switch (f) {
-    case kEpiFull: return launch_fprop<kEpiFull>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);                                             // dgrad / attention GEMMs
-    case kEpiFull | kEpiBias: return launch_fprop<kEpiFull | kEpiBias>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);                       // generator convs
-    case kEpiFull | kEpiBias | kEpiRelu: return launch_fprop<kEpiFull | kEpiBias | kEpiRelu>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);   // discriminator convs
-    case kEpiFull | kEpiResPre: return launch_fprop<kEpiFull | kEpiResPre>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);                   // concat-skip dgrad
-    case kEpiFull | kEpiBias | kEpiResPre: return launch_fprop<kEpiFull | kEpiBias | kEpiResPre>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);   // block output + skip
-    case kEpiFull | kEpiBias | kEpiRelu | kEpiResPre:
-      return launch_fprop<kEpiFull | kEpiBias | kEpiRelu | kEpiResPre>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);                       // ... with the next block's ReLU
-    case kEpiFull | kEpiMask: return launch_fprop<kEpiFull | kEpiMask>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);                       // dgrad through a ReLU
-    case kEpiFull | kEpiMask | kEpiResPre: return launch_fprop<kEpiFull | kEpiMask | kEpiResPre>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);   // fused block entry
+    SGB_FPROP_CASE(kEpiFull)                                                          // dgrad / attention GEMMs
+    SGB_FPROP_CASE(kEpiFull | kEpiBias)                                               // generator convs
+    SGB_FPROP_CASE(kEpiFull | kEpiBias | kEpiRelu)                                    // discriminator convs (no backward expected)
+    SGB_FPROP_CASE(kEpiFull | kEpiBias | kEpiRelu | kEpiBitsOut)                      // ... writing the ReLU bit plane
+    SGB_FPROP_CASE(kEpiFull | kEpiResPre | kEpiAuxRes)                                // concat-skip dgrad
+    SGB_FPROP_CASE(kEpiFull | kEpiBias | kEpiResPre | kEpiAuxRes)                     // block output + skip
+    SGB_FPROP_CASE(kEpiFull | kEpiBias | kEpiRelu | kEpiResPre | kEpiAuxRes)          // ... with the next block's ReLU
+    SGB_FPROP_CASE(kEpiFull | kEpiBias | kEpiRelu | kEpiResPre | kEpiAuxRes | kEpiBitsOut)
+    SGB_FPROP_CASE(kEpiFull | kEpiMask | kEpiMaskBits)                                // dgrad through a ReLU (bit plane)
+    SGB_FPROP_CASE(kEpiFull | kEpiMask | kEpiMaskBits | kEpiResPre | kEpiAuxRes)      // fused block entry (bit plane + pooled-skip gradient)
+    SGB_FPROP_CASE(kEpiFull | kEpiMask | kEpiAuxMask)                                 // dgrad through a ReLU (bf16 mask tile)
+    SGB_FPROP_CASE(kEpiFull | kEpiMask | kEpiResPre | kEpiAuxMask)                    // fused block entry (bf16 mask tile)
     default: return launch_fprop<-1>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);
   }
+#undef SGB_FPROP_CASE
 }
 
 extern "C" int sgb_conv_wgrad_fuses_dbias(const sgb_wgrad_desc* d) {
@@ -692,6 +703,15 @@ extern "C" int sgb_conv_wgrad(const sgb_wgrad_desc* d, sgb_stream_t stream_) {
       const long long rounds = ((long long)base_items * eff + sms - 1) / sms;
       const long long cost = rounds * (tps + drain);
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+    }
+    // near-ties go to MORE splits: concurrent items of one split read the same dY / X tiles at the same moment (36 CTAs on
+    // one set of L2 lines for a 256 -> 256 filter), more splits = more distinct streams and drains hidden behind the next item
+    // (r02: 3x3 512->512 @16x16 ran 807 TF/s with 1 split x 144 items and 968 TF/s with 3 x 144)
+    for (int s = best + 1; s <= (max_splits < 1 ? 1 : max_splits); ++s) {
+      const int tps = (p.tiles_per_group + s - 1) / s;
+      const int eff = (p.tiles_per_group + tps - 1) / tps;
+      const long long rounds = ((long long)base_items * eff + sms - 1) / sms;
+      if (50 * rounds * (tps + drain) <= 51 * best_cost) best = s;
     }
     p.tiles_per_split = (p.tiles_per_group + best - 1) / best;
     p.splits = (p.tiles_per_group + p.tiles_per_split - 1) / p.tiles_per_split;

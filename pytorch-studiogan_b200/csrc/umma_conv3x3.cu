@@ -333,7 +333,11 @@ int launch_conv3x3_rows(const sgb_conv_desc* d, cudaStream_t stream, int bo_mode
   switch (f) {
     case kEpiFull | kEpiBias: return launch_rows<kEpiFull | kEpiBias>(grid, smem, stream, tmA, tmB, tmY, p);                        // generator 3x3
     case kEpiFull | kEpiBias | kEpiRelu: return launch_rows<kEpiFull | kEpiBias | kEpiRelu>(grid, smem, stream, tmA, tmB, tmY, p);    // discriminator 3x3
-    case kEpiFull | kEpiMask: return launch_rows<kEpiFull | kEpiMask>(grid, smem, stream, tmA, tmB, tmY, p);                        // dgrad through a ReLU
+    case kEpiFull | kEpiBias | kEpiRelu | kEpiBitsOut:
+      return launch_rows<kEpiFull | kEpiBias | kEpiRelu | kEpiBitsOut>(grid, smem, stream, tmA, tmB, tmY, p);                         // ... writing the ReLU bit plane
+    case kEpiFull | kEpiMask: return launch_rows<kEpiFull | kEpiMask>(grid, smem, stream, tmA, tmB, tmY, p);                        // dgrad through a ReLU (bf16 mask)
+    case kEpiFull | kEpiMask | kEpiMaskBits:
+      return launch_rows<kEpiFull | kEpiMask | kEpiMaskBits>(grid, smem, stream, tmA, tmB, tmY, p);                                   // dgrad through a ReLU (bit plane)
     case kEpiFull: return launch_rows<kEpiFull>(grid, smem, stream, tmA, tmB, tmY, p);                                              // plain dgrad
     default: return launch_rows<-1>(grid, smem, stream, tmA, tmB, tmY, p);
   }
