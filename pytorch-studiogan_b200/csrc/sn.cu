@@ -264,34 +264,56 @@ __global__ void __launch_bounds__(256) sn_wv_batch_kernel(const sgb_sn_layer* __
   }
 }
 
-__global__ void __launch_bounds__(256) sn_pack_batch_kernel(const sgb_sn_layer* __restrict__ table, const float* __restrict__ sigma_all,
-                                                             bf16* __restrict__ pack_f, bf16* __restrict__ pack_d) {
+__global__ void __launch_bounds__(256) sn_pack_batch_kernel(const sgb_sn_layer* __restrict__ table, int n_layers, int total_tiles,
+                                                             const float* __restrict__ sigma_all, bf16* __restrict__ pack_f,
+                                                             bf16* __restrict__ pack_d) {
   // Tile = 32 output channels x 32 input channels x all taps, staged in shared memory so that the fp32 reads (one run of
   // 32*taps floats per output channel) AND both bf16 writes are contiguous: the fprop pack [co][tap][ci] in runs of 32 ci,
   // the dgrad pack [ci][taps-1-tap][co] in runs of 32 co.  (The element-wise version scattered 2-byte stores: 0.5 ms/call.)
+  // Work decomposition: ONE global tile index over all layers (table[l].tile_start = tiles of the layers before l; layers
+  // with more than 9 taps count 4096-element pseudo tiles); a block owns a contiguous range of it.  The former
+  // (max tiles) x (layers) grid launched ~300 k blocks of which most returned at once: 0.49 ms per call (r02 launch list).
   constexpr int kT = 32, kMaxTaps = 9;
   __shared__ bf16 tile[kT][kT * kMaxTaps + 2];
-  const sgb_sn_layer L = table[blockIdx.y];
-  const int Cout = L.Cout, Cin = L.Cin, taps = L.taps, perm_S = L.perm_S;
-  const float inv = 1.f / __ldcg(sigma_all + blockIdx.y);
-  bf16* wf = pack_f ? pack_f + L.off_f : nullptr;
-  bf16* wd = pack_d ? pack_d + L.off_d : nullptr;
-  if (taps > kMaxTaps) {                          // generic fallback (no such layer on the hot path)
-    const size_t total = (size_t)Cout * Cin * taps;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-      const int tap = (int)(i % taps);
-      const int ci = (int)((i / taps) % Cin);
-      int co = (int)(i / ((size_t)taps * Cin));
-      const bf16 v = __float2bfloat16_rn(__ldg(L.W + i) * inv);
-      if (perm_S > 1) { const int C = Cout / perm_S; co = (co % perm_S) * C + co / perm_S; }
-      if (wf) wf[((size_t)co * taps + tap) * L.Cin_p + ci] = v;
-      if (wd) wd[((size_t)ci * taps + (taps - 1 - tap)) * L.Cout_p + co] = v;
-    }
-    return;
+  const int t0 = (int)((long long)total_tiles * blockIdx.x / gridDim.x);
+  const int t1 = (int)((long long)total_tiles * (blockIdx.x + 1) / gridDim.x);
+  if (t0 >= t1) return;
+  int lo = 0, hi = n_layers - 1;
+  while (lo < hi) {                                // last layer whose first tile is <= t0
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].tile_start <= t0) lo = mid; else hi = mid - 1;
   }
-  const int tiles_ci = (Cin + kT - 1) / kT, tiles_co = (Cout + kT - 1) / kT;
-  const int run = kT * taps;                      // source elements per output channel inside one tile
-  for (int t = blockIdx.x; t < tiles_ci * tiles_co; t += gridDim.x) {
+  int l = lo;
+  sgb_sn_layer L = table[l];
+  int next_start = (l + 1 < n_layers) ? table[l + 1].tile_start : total_tiles;
+  float inv = 1.f / __ldcg(sigma_all + l);
+  for (int tg = t0; tg < t1; ++tg) {
+    while (tg >= next_start) {                     // (layers without tiles are skipped here)
+      ++l;
+      L = table[l];
+      next_start = (l + 1 < n_layers) ? table[l + 1].tile_start : total_tiles;
+      inv = 1.f / __ldcg(sigma_all + l);
+    }
+    const int t = tg - L.tile_start;
+    const int Cout = L.Cout, Cin = L.Cin, taps = L.taps, perm_S = L.perm_S;
+    bf16* wf = pack_f ? pack_f + L.off_f : nullptr;
+    bf16* wd = pack_d ? pack_d + L.off_d : nullptr;
+    if (taps > kMaxTaps) {                          // element-wise pseudo tile (4x4 filters of the DCGAN generator)
+      const unsigned total = (unsigned)Cout * Cin * taps;
+      const unsigned e0 = (unsigned)t * 4096u, e1 = min(e0 + 4096u, total);
+      for (unsigned i = e0 + threadIdx.x; i < e1; i += 256) {
+        const int tap = (int)(i % taps);
+        const int ci = (int)((i / taps) % Cin);
+        int co = (int)(i / ((unsigned)taps * Cin));
+        const bf16 v = __float2bfloat16_rn(__ldg(L.W + i) * inv);
+        if (perm_S > 1) { const int C = Cout / perm_S; co = (co % perm_S) * C + co / perm_S; }
+        if (wf) wf[((size_t)co * taps + tap) * L.Cin_p + ci] = v;
+        if (wd) wd[((size_t)ci * taps + (taps - 1 - tap)) * L.Cout_p + co] = v;
+      }
+      continue;
+    }
+    const int tiles_ci = (Cin + kT - 1) / kT;
+    const int run = kT * taps;                      // source elements per output channel inside one tile
     const int co0 = (t / tiles_ci) * kT, ci0 = (t % tiles_ci) * kT;
     const int nci = min(kT, Cin - ci0), nco = min(kT, Cout - co0);
     __syncthreads();
@@ -333,20 +355,45 @@ __global__ void __launch_bounds__(256) sn_pack_batch_kernel(const sgb_sn_layer* 
 // sigma are the copies taken at that forward pass (flat arenas, per-layer offsets in the table).  Layers that produced no
 // weight gradient in this pass hold zeros in g_flat and add zero.
 // ---------------------------------------------------------------------------------------------------------------------
+// Both kernels walk a layer row by row (row = one output channel: Cin * taps contiguous floats of W / dW, and the
+// contiguous [taps][Cin_p] block of G).  For taps > 1 the G row is staged in shared memory so that the global reads of G, W and
+// the read-modify-write of dW are all coalesced (the element-wise version read G with a stride of Cin_p floats and did three
+// 64-bit divisions per element: 0.25 ms per kernel and call).
+static constexpr int kSnRowFloats = 8192;          // 32 KiB: 512 channels x 16 taps
+
+__device__ __forceinline__ int sn_g_row(const sgb_snbwd_layer& L, int co_orig) {
+  if (L.perm_S > 1) { const int C = L.Cout / L.perm_S; return (co_orig % L.perm_S) * C + co_orig / L.perm_S; }
+  return co_orig;
+}
+
 __global__ void __launch_bounds__(256) sn_bwd_dot_batch_kernel(const sgb_snbwd_layer* __restrict__ table,
                                                                 const float* __restrict__ g_flat, float* __restrict__ dots) {
   __shared__ float sh[32];
+  __shared__ float grow[kSnRowFloats];
   const sgb_snbwd_layer L = table[blockIdx.y];
   if (!L.has_sn || !L.dW) return;
-  const float* G = g_flat + L.off_g;
-  const size_t total = (size_t)L.Cout * L.Cin * L.taps;
+  const int taps = L.taps, Cin = L.Cin, K = Cin * taps, GK = taps * L.Cin_p;
+  const bool staged = taps > 1 && GK <= kSnRowFloats;
   float acc = 0.f;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-    const int tap = (int)(i % L.taps);
-    const int ci = (int)((i / L.taps) % L.Cin);
-    int co = (int)(i / ((size_t)L.taps * L.Cin));
-    if (L.perm_S > 1) { const int C = L.Cout / L.perm_S; co = (co % L.perm_S) * C + co / L.perm_S; }
-    acc = fmaf(__ldg(G + ((size_t)co * L.taps + tap) * L.Cin_p + ci), __ldg(L.W + i), acc);
+  for (int r = blockIdx.x; r < L.Cout; r += gridDim.x) {
+    const float* G = g_flat + L.off_g + (size_t)sn_g_row(L, r) * GK;
+    const float* W = L.W + (size_t)r * K;
+    if (taps == 1) {
+      for (int k = threadIdx.x; k < K; k += 256) acc = fmaf(__ldg(G + k), __ldg(W + k), acc);
+    } else if (staged) {
+      __syncthreads();
+      for (int k = threadIdx.x; k < GK; k += 256) grow[k] = __ldg(G + k);
+      __syncthreads();
+      for (int k = threadIdx.x; k < K; k += 256) {
+        const int ci = k / taps, tap = k - ci * taps;
+        acc = fmaf(grow[tap * L.Cin_p + ci], __ldg(W + k), acc);
+      }
+    } else {
+      for (int k = threadIdx.x; k < K; k += 256) {
+        const int ci = k / taps, tap = k - ci * taps;
+        acc = fmaf(__ldg(G + (size_t)tap * L.Cin_p + ci), __ldg(W + k), acc);
+      }
+    }
   }
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0 && acc != 0.f) atomicAdd(dots + blockIdx.y, acc);
@@ -356,10 +403,11 @@ __global__ void __launch_bounds__(256) sn_bwd_apply_batch_kernel(const sgb_snbwd
                                                                   const float* __restrict__ g_flat, const float* __restrict__ dots,
                                                                   const float* __restrict__ sigma_all, const float* __restrict__ u_flat,
                                                                   const float* __restrict__ v_flat) {
+  __shared__ float grow[kSnRowFloats];
   const sgb_snbwd_layer L = table[blockIdx.y];
   if (!L.dW) return;
-  const float* G = g_flat + L.off_g;
-  const size_t total = (size_t)L.Cout * L.Cin * L.taps;
+  const int taps = L.taps, Cin = L.Cin, K = Cin * taps, GK = taps * L.Cin_p;
+  const bool staged = taps > 1 && GK <= kSnRowFloats;
   float inv = 1.f, coef = 0.f;
   const float* u = nullptr;
   const float* v = nullptr;
@@ -369,15 +417,26 @@ __global__ void __launch_bounds__(256) sn_bwd_apply_batch_kernel(const sgb_snbwd
     u = u_flat + L.off_u;
     v = v_flat + L.off_v;
   }
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-    const int tap = (int)(i % L.taps);
-    const int ci = (int)((i / L.taps) % L.Cin);
-    const int co_orig = (int)(i / ((size_t)L.taps * L.Cin));
-    int co = co_orig;
-    if (L.perm_S > 1) { const int C = L.Cout / L.perm_S; co = (co % L.perm_S) * C + co / L.perm_S; }
-    float g = __ldg(G + ((size_t)co * L.taps + tap) * L.Cin_p + ci);
-    if (L.has_sn) g = (g - coef * __ldg(u + co_orig) * __ldg(v + (size_t)ci * L.taps + tap)) * inv;
-    L.dW[i] += g;
+  for (int r = blockIdx.x; r < L.Cout; r += gridDim.x) {
+    const float* G = g_flat + L.off_g + (size_t)sn_g_row(L, r) * GK;
+    float* dW = L.dW + (size_t)r * K;
+    const float cu = L.has_sn ? coef * __ldg(u + r) : 0.f;
+    if (staged) {
+      __syncthreads();
+      for (int k = threadIdx.x; k < GK; k += 256) grow[k] = __ldg(G + k);
+      __syncthreads();
+    }
+    for (int k = threadIdx.x; k < K; k += 256) {
+      float g;
+      if (taps == 1) {
+        g = __ldg(G + k);
+      } else {
+        const int ci = k / taps, tap = k - ci * taps;
+        g = staged ? grow[tap * L.Cin_p + ci] : __ldg(G + (size_t)tap * L.Cin_p + ci);
+      }
+      if (L.has_sn) g = (g - cu * __ldg(v + k)) * inv;
+      dW[k] += g;
+    }
   }
 }
 
@@ -410,7 +469,10 @@ extern "C" int sgb_sn_batch(const sgb_sn_layer* table, int32_t n_layers, float* 
   sn_wv_batch_kernel<<<dim3(max_blocks_wv, n_layers), 256, 0, stream>>>(table, sigma_all, eps, do_power_iteration);
   SGB_LAUNCH_CHECK();
   if (pack_f || pack_d) {
-    sn_pack_batch_kernel<<<dim3(max_blocks_pack, n_layers), 256, 0, stream>>>(table, sigma_all, (bf16*)pack_f, (bf16*)pack_d);
+    // max_blocks_pack carries the total tile count of the table (sum over layers, see sgb_sn_layer.tile_start)
+    const int total_tiles = max_blocks_pack;
+    const int blocks = total_tiles < 8 * sm_count() ? total_tiles : 8 * sm_count();
+    sn_pack_batch_kernel<<<blocks, 256, 0, stream>>>(table, n_layers, total_tiles, sigma_all, (bf16*)pack_f, (bf16*)pack_d);
     SGB_LAUNCH_CHECK();
   }
   return SGB_OK;

@@ -19,7 +19,11 @@
 namespace sgb {
 
 static constexpr int kWgradThreads = 192;                // wgrad: warps 0 producer, 1 MMA, 2..5 epilogue
-static constexpr int kFpropEpiThreads = 512;       // 16 epilogue warps: 2 teams x 4 lane quadrants x 2 column halves
+#ifndef SGB_FPROP_NH
+#define SGB_FPROP_NH 1                               // warps per (team, lane quadrant) in the epilogue; 2 = 16 epilogue warps (A/B on one box, r02: 565.1 vs 563.2 ms/step -- no gain, the 1x1 launches sit on the HBM read/write mix, not on epilogue latency)
+#endif
+static constexpr int kFpropNH = SGB_FPROP_NH;
+static constexpr int kFpropEpiThreads = 256 * kFpropNH;   // 2 teams x 4 lane quadrants x NH column halves
 static constexpr int kThreads = 128 + kFpropEpiThreads;  // warps 0..3: producer / MMA / aux producer / (idle), warps 4..19: epilogue teams
 static constexpr int kTileM = 128;          // pixels (fprop) or output channels (wgrad) per tile = TMEM lanes
 static constexpr int kBlockK = 64;          // bf16 elements per 128-byte swizzle row
@@ -230,7 +234,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + a * p.BN;
       if (p.use_tma) {
-        epilogue_tile_tma<F, 2>(p.e, &tmY, t_row, p.BN, n0, wt * p.tw, ht * p.th, bt * p.nb, valid, pix, rpix, alpha, stage, team, row,
+        epilogue_tile_tma<F, kFpropNH>(p.e, &tmY, t_row, p.BN, n0, wt * p.tw, ht * p.th, bt * p.nb, valid, pix, rpix, alpha, stage, team, row,
                              leader, 2, p.aux_kind ? &aux : nullptr, p.epi_nbuf >= 2 ? &sbuf : nullptr, p.epi_nbuf, half);
       } else if (team == 0 && half == 0) {
         epilogue_row(p.e, t_row, p.BN, n0, valid, pix, rpix, alpha, vec_ok);
@@ -550,10 +554,12 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   else if (d->Cout <= 64) BN = 64;
   else if (d->Cout <= 128 || d->Cout % 256 != 0) BN = 128;
   else BN = 256;
-  // keep enough tiles in flight: prefer 128-wide N tiles when the grid would otherwise underfill the SMs
+  // 128-wide N tiles only when both halves of every 256-wide tile find an idle SM: an N = 128 tile takes nearly as long as an
+  // N = 256 one (the MMA is bound by the shared-memory fetch of the A tile: 712 vs 1381 TFLOP/s on 3x3 128 / 256 channels), so
+  // splitting pays only while tiles256 <= SMs / 2 (r02, B = 32: 3x3 256->256 @32x32 ran 557 TFLOP/s as 512 N = 128 tiles)
   {
     long long tiles256 = (long long)p.tiles_w * p.tiles_h * p.tiles_b * ((d->Cout + 255) / 256);
-    if (BN == 256 && tiles256 < 2LL * sm_count()) BN = 128;
+    if (BN == 256 && 2LL * tiles256 <= sm_count()) BN = 128;
   }
   if (d->w_mode == 2 && BN < 64) BN = 64;  // MN-major B is staged in 64-wide atoms
   p.BN = BN;

@@ -11,7 +11,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsgb200.so")
+LIB_PATH = os.environ.get("SGB_LIB") or os.path.join(_HERE, "lib", "libsgb200.so")   # SGB_LIB: A/B builds of the same ABI
 
 c_int = ctypes.c_int32
 c_i64 = ctypes.c_int64

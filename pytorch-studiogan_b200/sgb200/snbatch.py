@@ -20,7 +20,7 @@ from .utils import ops
 
 LAYER_DTYPE = np.dtype([("W", "<u8"), ("u", "<u8"), ("v", "<u8"), ("ws", "<u8"), ("R", "<i4"), ("K", "<i4"),
                         ("Cout", "<i4"), ("Cin", "<i4"), ("taps", "<i4"), ("perm_S", "<i4"), ("Cout_p", "<i4"), ("Cin_p", "<i4"),
-                        ("off_f", "<i8"), ("off_d", "<i8"), ("has_sn", "<i4"), ("reserved", "<i4")])
+                        ("off_f", "<i8"), ("off_d", "<i8"), ("has_sn", "<i4"), ("tile_start", "<i4")])
 assert LAYER_DTYPE.itemsize == 88
 BWD_DTYPE = np.dtype([("W", "<u8"), ("dW", "<u8"), ("off_g", "<i8"), ("off_u", "<i8"), ("off_v", "<i8"), ("Cout", "<i4"),
                       ("Cin", "<i4"), ("taps", "<i4"), ("perm_S", "<i4"), ("Cin_p", "<i4"), ("has_sn", "<i4")])
@@ -88,7 +88,8 @@ class SNBatch:
         ou = ov = ows = 0
         off_f = off_d = 0
         self.slices = []
-        mb1 = mb2 = mb3 = 1
+        mb1 = mb2 = 1
+        tiles = 0
         for i, m in enumerate(mods):
             W = ops._w(m)
             Cout = W.shape[0]
@@ -119,13 +120,14 @@ class SNBatch:
                 ows += R + Kd + 4
                 mb1 = max(mb1, ((Kd + 255) // 256) * ((R + 63) // 64))
                 mb2 = max(mb2, (R + 7) // 8)
-            mb3 = max(mb3, (Cout * Cin * taps + 255) // 256)
+            e["tile_start"] = tiles
+            tiles += ((Cout + 31) // 32) * ((Cin + 31) // 32) if taps <= 9 else (Cout * Cin * taps + 4095) // 4096
             self.slices.append((off_f, off_d, nf, (Cout_p, taps, Cin_p), (Cin_p, taps, Cout_p), su, sv))
             off_f += (nf + 63) // 64 * 64            # keep every pack 128-byte aligned (TMA base alignment)
             off_d += (nf + 63) // 64 * 64
         self.total_f, self.total_d = off_f, off_d
         self.table = torch.from_numpy(table.view(np.uint8).copy()).to(device)
-        self.max_blocks = (min(mb1, 4096), min(mb2, 1024), min(mb3, 2048))
+        self.max_blocks = (min(mb1, 4096), min(mb2, 1024), tiles)     # (wtu grid, wv grid, total pack tiles)
         self.mods = mods
         self.device = device
         self.params = [ops._w(m) for m in mods]
