@@ -138,11 +138,11 @@ typedef struct sgb_sn_layer {
   int32_t Cout, Cin, taps, perm_S, Cout_p, Cin_p;
   int64_t off_f, off_d;
   int32_t has_sn;
-  int32_t tile_start;  /* pack tiles of the layers before this one: ceil(Cout/32)*ceil(Cin/32) per layer (taps <= 9), else
-                          ceil(Cout*Cin*taps/4096) */
+  int32_t tile_start;  /* pack work units (~1024 weights) of the layers before this one: taps*ceil(Cout/32)*ceil(Cin/32) per
+                          layer (taps <= 9), else 4*ceil(Cout*Cin*taps/4096) */
 } sgb_sn_layer;
 /* max_blocks_wtu / max_blocks_wv: grid width of the two power-iteration launches; total_pack_tiles: sum of the table's pack
- * tiles (the pack launch walks one global tile index, see tile_start). */
+ * work units (the pack launch walks one global unit index, see tile_start). */
 int sgb_sn_batch(const sgb_sn_layer* table, int32_t n_layers, float* sigma_all, void* pack_f, void* pack_d, float eps,
                  int32_t do_power_iteration, int32_t max_blocks_wtu, int32_t max_blocks_wv, int32_t total_pack_tiles,
                  sgb_stream_t stream);

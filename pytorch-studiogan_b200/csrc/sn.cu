@@ -275,26 +275,34 @@ __global__ void __launch_bounds__(256) sn_pack_batch_kernel(const sgb_sn_layer* 
   // (max tiles) x (layers) grid launched ~300 k blocks of which most returned at once: 0.49 ms per call (r02 launch list).
   constexpr int kT = 32, kMaxTaps = 9;
   __shared__ bf16 tile[kT][kT * kMaxTaps + 2];
-  const int t0 = (int)((long long)total_tiles * blockIdx.x / gridDim.x);
-  const int t1 = (int)((long long)total_tiles * (blockIdx.x + 1) / gridDim.x);
-  if (t0 >= t1) return;
+  // (total_tiles / tile_start count WORK UNITS of ~1024 weights: a tile of a k-tap layer is k units, a pseudo tile 4, so
+  //  that contiguous unit ranges are balanced; a tile belongs to the block whose range holds its first unit)
+  const int u0 = (int)((long long)total_tiles * blockIdx.x / gridDim.x);
+  const int u1 = (int)((long long)total_tiles * (blockIdx.x + 1) / gridDim.x);
+  if (u0 >= u1) return;
   int lo = 0, hi = n_layers - 1;
-  while (lo < hi) {                                // last layer whose first tile is <= t0
+  while (lo < hi) {                                // last layer whose first unit is <= u0
     const int mid = (lo + hi + 1) >> 1;
-    if (table[mid].tile_start <= t0) lo = mid; else hi = mid - 1;
+    if (table[mid].tile_start <= u0) lo = mid; else hi = mid - 1;
   }
   int l = lo;
   sgb_sn_layer L = table[l];
   int next_start = (l + 1 < n_layers) ? table[l + 1].tile_start : total_tiles;
   float inv = 1.f / __ldcg(sigma_all + l);
-  for (int tg = t0; tg < t1; ++tg) {
-    while (tg >= next_start) {                     // (layers without tiles are skipped here)
+  int upt = L.taps > kMaxTaps ? 4 : L.taps;        // units per tile of the current layer
+  int t = (u0 - L.tile_start + upt - 1) / upt;     // first tile starting at or after u0
+  for (;;) {
+    int ustart = L.tile_start + t * upt;
+    while (ustart >= next_start && l + 1 < n_layers) {   // next layer (layers without tiles are skipped here)
       ++l;
       L = table[l];
       next_start = (l + 1 < n_layers) ? table[l + 1].tile_start : total_tiles;
       inv = 1.f / __ldcg(sigma_all + l);
+      upt = L.taps > kMaxTaps ? 4 : L.taps;
+      t = 0;
+      ustart = L.tile_start;
     }
-    const int t = tg - L.tile_start;
+    if (ustart >= u1 || ustart >= next_start) break;
     const int Cout = L.Cout, Cin = L.Cin, taps = L.taps, perm_S = L.perm_S;
     bf16* wf = pack_f ? pack_f + L.off_f : nullptr;
     bf16* wd = pack_d ? pack_d + L.off_d : nullptr;
@@ -310,6 +318,7 @@ __global__ void __launch_bounds__(256) sn_pack_batch_kernel(const sgb_sn_layer* 
         if (wf) wf[((size_t)co * taps + tap) * L.Cin_p + ci] = v;
         if (wd) wd[((size_t)ci * taps + (taps - 1 - tap)) * L.Cout_p + co] = v;
       }
+      ++t;
       continue;
     }
     const int tiles_ci = (Cin + kT - 1) / kT;
@@ -346,6 +355,7 @@ __global__ void __launch_bounds__(256) sn_pack_batch_kernel(const sgb_sn_layer* 
         }
       }
     }
+    ++t;
   }
 }
 
@@ -471,7 +481,7 @@ extern "C" int sgb_sn_batch(const sgb_sn_layer* table, int32_t n_layers, float* 
   if (pack_f || pack_d) {
     // max_blocks_pack carries the total tile count of the table (sum over layers, see sgb_sn_layer.tile_start)
     const int total_tiles = max_blocks_pack;
-    const int blocks = total_tiles < 8 * sm_count() ? total_tiles : 8 * sm_count();
+    const int blocks = total_tiles < 32 * sm_count() ? total_tiles : 32 * sm_count();   // 4 waves of resident blocks: dynamic balance
     sn_pack_batch_kernel<<<blocks, 256, 0, stream>>>(table, n_layers, total_tiles, sigma_all, (bf16*)pack_f, (bf16*)pack_d);
     SGB_LAUNCH_CHECK();
   }

@@ -121,7 +121,8 @@ class SNBatch:
                 mb1 = max(mb1, ((Kd + 255) // 256) * ((R + 63) // 64))
                 mb2 = max(mb2, (R + 7) // 8)
             e["tile_start"] = tiles
-            tiles += ((Cout + 31) // 32) * ((Cin + 31) // 32) if taps <= 9 else (Cout * Cin * taps + 4095) // 4096
+            # work units of ~1024 weights: a 32 x 32 tile of a k-tap layer counts k, a 4096-element pseudo tile (k > 9) counts 4
+            tiles += ((Cout + 31) // 32) * ((Cin + 31) // 32) * taps if taps <= 9 else 4 * ((Cout * Cin * taps + 4095) // 4096)
             self.slices.append((off_f, off_d, nf, (Cout_p, taps, Cin_p), (Cin_p, taps, Cout_p), su, sv))
             off_f += (nf + 63) // 64 * 64            # keep every pack 128-byte aligned (TMA base alignment)
             off_d += (nf + 63) // 64 * 64
