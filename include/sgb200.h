@@ -78,6 +78,17 @@ typedef struct sgb_conv_desc {
    * the input-gradient launch of the layer that consumed y (the in-place d_act_fn of src/config.py:486 in backward). */
   const void* mask_bits;
   void* relu_bits;
+  /* Row softmax of the attention map (src/utils/ops.py:93-97) inside the GEMM epilogue, 1x1 / w_mode 1 launches with
+   * Cout = keys (multiple of 64), bf16 output, no other epilogue operand:
+   *   sm_mode 1: statistics pass -- nothing is stored to y; sm_stats[row][part] = (max, sum exp(. - max)) over the columns of one
+   *              (channel tile, epilogue team) pair; parts per row = sgb_conv_softmax_parts(desc)
+   *   sm_mode 2: y = exp(acc - m_row) / l_row with (m, l) merged from sm_stats (the same GEMM launched a second time)
+   *   sm_mode 3: y = sm_p * (acc - sm_delta[row]): softmax backward dS = P * (dP - delta), delta = rowsum(dO * O) */
+  int32_t sm_mode;
+  float* sm_stats;
+  const float* sm_delta;
+  const void* sm_p;     /* bf16 NHWC, same shape as y */
+  int64_t sm_p_cstride;
 } sgb_conv_desc;
 
 int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream);
@@ -141,6 +152,10 @@ typedef struct sgb_sn_layer {
   int32_t tile_start;  /* pack work units (~1024 weights) of the layers before this one: taps*ceil(Cout/32)*ceil(Cin/32) per
                           layer (taps <= 9), else 4*ceil(Cout*Cin*taps/4096) */
 } sgb_sn_layer;
+/* Partials per row the softmax statistics pass of sgb_conv_fprop writes for this problem size (2 x channel tiles). */
+int sgb_conv_softmax_parts(const sgb_conv_desc* d);
+/* out[r] = sum_c x[r][c] * y[r][c] (bf16 rows of C channels, fp32 out): delta of the softmax backward. */
+int sgb_rowdot(const void* x, int64_t xs, const void* y, int64_t ys, int64_t rows, int32_t C, float* out, sgb_stream_t stream);
 /* max_blocks_wtu / max_blocks_wv: grid width of the two power-iteration launches; total_pack_tiles: sum of the table's pack
  * work units (the pack launch walks one global unit index, see tile_start). */
 int sgb_sn_batch(const sgb_sn_layer* table, int32_t n_layers, float* sigma_all, void* pack_f, void* pack_d, float eps,

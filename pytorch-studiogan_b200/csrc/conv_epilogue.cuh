@@ -19,6 +19,13 @@ struct EpiArgs {
   // mask_bits replaces ``mask`` (1/16 of its bytes); relu_bits is written by a relu epilogue for the consumer's backward.
   const unsigned long long* mask_bits;
   unsigned long long* relu_bits;
+  // Row softmax of the attention map inside the GEMM epilogues (one thread = one query row of the tile):
+  //   sm_mode 1: no output; per row and per (channel tile, team) the partial (max, sum exp) of its columns -> sm_stats
+  //   sm_mode 2: y = exp(acc - m) / l with (m, l) merged from the row's sm_parts partials
+  //   sm_mode 3: y = P * (acc - delta[row]) (softmax backward; P arrives through the aux TMA ring, kind 3)
+  int sm_mode, sm_parts;
+  float* sm_stats;            // [rows][sm_parts][2]
+  const float* sm_delta;      // [rows]
 };
 
 // 16 accumulator values -> 16 mask bits (value > 0)
@@ -197,6 +204,8 @@ static constexpr int kEpiBias = 1, kEpiRelu = 2, kEpiResPre = 4, kEpiResPost = 8
 // three questions left to run time the compiler if-converts both sides of each and the piece loop issues 12 instructions per
 // output element (the bias-only variant: 2).
 static constexpr int kEpiMaskBits = 64, kEpiAuxRes = 128, kEpiAuxMask = 256, kEpiBitsOut = 512;
+// attention: bit 10 softmax statistics (no store), 11 softmax apply, 12 softmax backward (P tile through the aux ring)
+static constexpr int kEpiSmStats = 1024, kEpiSmApply = 2048, kEpiSmBwd = 4096;
 
 __host__ __device__ inline int epi_flags_of(const EpiArgs& p) {
   int f = 0;
@@ -207,7 +216,46 @@ __host__ __device__ inline int epi_flags_of(const EpiArgs& p) {
   if (p.mask_bits) f |= kEpiMaskBits;
   if (p.relu && p.relu_bits) f |= kEpiBitsOut;
   if (p.Cout % 64 == 0) f |= kEpiFull;
+  if (p.sm_mode == 1) f |= kEpiSmStats;
+  if (p.sm_mode == 2) f |= kEpiSmApply;
+  if (p.sm_mode == 3) f |= kEpiSmBwd;
   return f;
+}
+
+// Softmax statistics of one accumulator tile (sm_mode 1): this thread's row, the 64-column chunks of its team; the running
+// (max, sum exp) pair is kept in registers and stored once -- nothing else leaves the SM.
+__device__ __forceinline__ void epilogue_tile_smstats(const EpiArgs& p, uint32_t t_row, int BN, int n0, bool valid, long long pix,
+                                                      float alpha, int team, int part) {
+  float m = -INFINITY, l = 0.f;
+  constexpr float kLog2e = 1.4426950408889634f;
+  for (int cc = team; cc * 64 < BN; cc += 2) {
+    if (n0 + cc * 64 >= p.Cout) break;
+#pragma unroll 1
+    for (int s0 = 0; s0 < 4; s0 += 2) {
+      uint32_t v[2][16];
+      __syncwarp();
+      tmem_ld16(t_row + cc * 64 + s0 * 16, v[0]);
+      tmem_ld16(t_row + cc * 64 + (s0 + 1) * 16, v[1]);
+      tmem_ld_wait();
+      float pm = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pm = fmaxf(pm, __uint_as_float(v[q][j]) * alpha);
+      const float mn = fmaxf(m, pm);
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc += exp2f((__uint_as_float(v[q][j]) * alpha - mn) * kLog2e);
+      l = l * exp2f((m - mn) * kLog2e) + acc;
+      m = mn;
+    }
+  }
+  if (valid) {
+    float2* dst = reinterpret_cast<float2*>(p.sm_stats) + pix * p.sm_parts + part;
+    *dst = make_float2(m, l);
+  }
 }
 
 // Direct-store epilogue of a compile-time variant F >= 0 (bf16 output, Cout % 64 == 0, 16-byte aligned operands): the same
@@ -311,6 +359,18 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
                                                   const EpiAux* aux = nullptr, uint32_t* sbuf = nullptr, int nbuf = 2, int half = 0) {
   constexpr int kTeamThreads = 128 * NH;
   const int sbeg = half * (4 / NH), send = sbeg + 4 / NH;
+  constexpr bool sm_apply = F >= 0 && (F & kEpiSmApply) != 0, sm_bwd = F >= 0 && (F & kEpiSmBwd) != 0;
+  constexpr float kLog2e = 1.4426950408889634f;
+  float sm_a = 0.f, sm_b = 1.f;                    // apply: (row max, 1 / row sum); backward: (delta, -)
+  if (sm_apply && valid) {
+    const float2* st = reinterpret_cast<const float2*>(p.sm_stats) + pix * p.sm_parts;
+    float m = -INFINITY;
+    for (int i = 0; i < p.sm_parts; ++i) m = fmaxf(m, __ldcg(&st[i].x));
+    float l = 0.f;
+    for (int i = 0; i < p.sm_parts; ++i) { const float2 t = __ldcg(&st[i]); l += t.y * exp2f((t.x - m) * kLog2e); }
+    sm_a = m; sm_b = 1.f / l;
+  }
+  if (sm_bwd && valid) sm_a = __ldg(p.sm_delta + pix);
   const bool has_bias = F < 0 ? p.bias != nullptr : (F & kEpiBias) != 0;
   const bool do_relu = F < 0 ? p.relu != 0 : (F & kEpiRelu) != 0;
   const bool res_pre = F < 0 ? (p.residual != nullptr && !p.res_after) : (F & kEpiResPre) != 0;
@@ -326,7 +386,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
   const uint32_t sw = (uint32_t)(row & 7);
   // 1: residual tile via TMA, 2: mask tile via TMA (compile-time for F >= 0: the host sets the aux bits iff it passes ``aux``)
   const int aux_kind = F < 0 ? ((aux && (res_pre || res_post || has_mask)) ? aux->kind : 0)
-                             : ((F & kEpiAuxRes) ? 1 : ((F & kEpiAuxMask) ? 2 : 0));
+                             : ((F & kEpiAuxRes) ? 1 : ((F & kEpiAuxMask) ? 2 : (sm_bwd ? 3 : 0)));
   const uint32_t asw = aux ? (uint32_t)(aux->arow & 7) : 0u;
   for (int cc = (chunk_stride == 2 ? team : 0); cc * 64 < BN; cc += chunk_stride) {
     const int nbase = n0 + cc * 64;
@@ -368,6 +428,20 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
         for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * alpha;
         const int nvalid = full_c ? 16 : p.Cout - n;   // channels of this 16-wide piece inside the tensor: >= 16, 8 (Cout % 16 == 8) or <= 0
         const bool in_c = full_c || nvalid > 0;
+        if (sm_apply) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = exp2f((f[j] - sm_a) * kLog2e) * sm_b;
+        }
+        if (sm_bwd) {                                // dS = P * (dP - delta); P: this row of the aux tile
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint4 r = ld_shared_v4(arow_addr + (((uint32_t)(2 * s + j) ^ asw) << 4));
+            f[8 * j + 0] = bf16_bits_lo(r.x) * (f[8 * j + 0] - sm_a); f[8 * j + 1] = bf16_bits_hi(r.x) * (f[8 * j + 1] - sm_a);
+            f[8 * j + 2] = bf16_bits_lo(r.y) * (f[8 * j + 2] - sm_a); f[8 * j + 3] = bf16_bits_hi(r.y) * (f[8 * j + 3] - sm_a);
+            f[8 * j + 4] = bf16_bits_lo(r.z) * (f[8 * j + 4] - sm_a); f[8 * j + 5] = bf16_bits_hi(r.z) * (f[8 * j + 5] - sm_a);
+            f[8 * j + 6] = bf16_bits_lo(r.w) * (f[8 * j + 6] - sm_a); f[8 * j + 7] = bf16_bits_hi(r.w) * (f[8 * j + 7] - sm_a);
+          }
+        }
         if (has_bias && in_c) {
           const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll

@@ -194,6 +194,27 @@ __global__ void __launch_bounds__(256) pool2_bwd_kernel(const bf16* __restrict__
   }
 }
 
+// out[row] = sum_c x[row][c] * y[row][c]: delta = rowsum(dO * O) of the softmax backward; one warp per row.
+__global__ void __launch_bounds__(256) rowdot_kernel(const bf16* __restrict__ x, long long xs, const bf16* __restrict__ y, long long ys,
+                                                     long long rows, int C, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const uint4* xp = reinterpret_cast<const uint4*>(x + row * xs);
+  const uint4* yp = reinterpret_cast<const uint4*>(y + row * ys);
+  float acc = 0.f;
+  for (int i = lane; i < (C >> 3); i += 32) {
+    float a[8], b[8];
+    unpack8(__ldg(xp + i), a);
+    unpack8(__ldg(yp + i), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(a[j], b[j], acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[row] = acc;
+}
+
 // Row softmax over the last dim (bf16 in/out, fp32 math), one warp per row, in place allowed.
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const bf16* __restrict__ s, bf16* __restrict__ p, long long rows, int n) {
   const int lane = threadIdx.x & 31;
@@ -736,6 +757,14 @@ extern "C" int sgb_pool2_bwd(const void* dy, int64_t dys, const void* x, int64_t
   else
     pool2_bwd_kernel<false><<<ew_blocks((long long)B * Ho * Wo * (C / 8)), 256, 0, stream>>>(
         (const bf16*)dy, dys, (const bf16*)x, xs, (const bf16*)add, adds, (const bf16*)relu_src, rs, (bf16*)dx, dxs, B, Ho, Wo, C, mode);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_rowdot(const void* x, int64_t xs, const void* y, int64_t ys, int64_t rows, int32_t C, float* out, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(x && y && out && rows > 0 && C > 0 && C % 8 == 0 && xs % 8 == 0 && ys % 8 == 0);
+  rowdot_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>((const bf16*)x, xs, (const bf16*)y, ys, rows, C, out);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }

@@ -233,7 +233,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + a * p.BN;
-      if (p.use_tma) {
+      if constexpr (F >= 0 && (F & kEpiSmStats) != 0) {
+        if (half == 0) epilogue_tile_smstats(p.e, t_row, p.BN, n0, valid, pix, alpha, team, nt * 2 + team);
+      } else if (p.use_tma) {
         epilogue_tile_tma<F, kFpropNH>(p.e, &tmY, t_row, p.BN, n0, wt * p.tw, ht * p.th, bt * p.nb, valid, pix, rpix, alpha, stage, team, row,
                              leader, 2, p.aux_kind ? &aux : nullptr, p.epi_nbuf >= 2 ? &sbuf : nullptr, p.epi_nbuf, half);
       } else if (team == 0 && half == 0) {
@@ -468,6 +470,7 @@ void fill_epi(EpiArgs& e, const sgb_conv_desc* d) {
   e.y = d->y; e.y_cstride = d->y_cstride; e.y_fp32 = d->y_fp32;
   e.mask_bits = (const unsigned long long*)d->mask_bits;
   e.relu_bits = (unsigned long long*)d->relu_bits;
+  e.sm_mode = d->sm_mode; e.sm_parts = 0; e.sm_stats = d->sm_stats; e.sm_delta = d->sm_delta;
 }
 
 static int make_act_tmap(CUtensorMap* m, const void* base, int B, int H, int W, int C, long long cstride, int tw, int th,
@@ -517,6 +520,33 @@ static int launch_fprop(int grid, size_t smem, cudaStream_t stream, const CUtens
   return SGB_OK;
 }
 
+static int pick_bn(const sgb_conv_desc* d, long long pixel_tiles) {
+  int BN;
+  if (d->Cout <= 16) BN = 16;
+  else if (d->Cout <= 32) BN = 32;
+  else if (d->Cout <= 64) BN = 64;
+  else if (d->Cout <= 128 || d->Cout % 256 != 0) BN = 128;
+  else BN = 256;
+  // 128-wide N tiles only when both halves of every 256-wide tile find an idle SM: an N = 128 tile takes nearly as long as an
+  // N = 256 one (the MMA is bound by the shared-memory fetch of the A tile: 712 vs 1381 TFLOP/s on 3x3 128 / 256 channels), so
+  // splitting pays only while tiles256 <= SMs / 2 (r02, B = 32: 3x3 256->256 @32x32 ran 557 TFLOP/s as 512 N = 128 tiles)
+  {
+    long long tiles256 = pixel_tiles * ((d->Cout + 255) / 256);
+    if (BN == 256 && 2LL * tiles256 <= sm_count()) BN = 128;
+  }
+  if (d->w_mode == 2 && BN < 64) BN = 64;  // MN-major B is staged in 64-wide atoms
+  return BN;
+}
+
+extern "C" int sgb_conv_softmax_parts(const sgb_conv_desc* d) {
+  if (!d || d->Cout <= 0) return 0;
+  int tw, th, nb;
+  pick_tile(d->H, d->W, d->B, tw, th, nb);
+  const long long pixel_tiles = (long long)((d->W + tw - 1) / tw) * ((d->H + th - 1) / th) * ((d->B + nb - 1) / nb);
+  const int BN = pick_bn(d, pixel_tiles);
+  return 2 * ((d->Cout + BN - 1) / BN);
+}
+
 extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SGB_REQUIRE(d && d->x && d->w && d->y);
@@ -533,6 +563,13 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   SGB_REQUIRE(!d->relu_bits || (d->relu && d->Cout % 64 == 0 && !d->y_fp32 && d->out_sub != 2 && d->y_cstride % 8 == 0 &&
                                 ((uintptr_t)d->relu_bits & 7) == 0));
   SGB_REQUIRE(!(d->mask_bits || d->relu_bits) || ((!d->residual || d->res_cstride % 8 == 0) && d->y_cstride % 8 == 0));
+  // attention softmax inside the epilogue: plain bf16 GEMM tiles only
+  SGB_REQUIRE(d->sm_mode >= 0 && d->sm_mode <= 3);
+  SGB_REQUIRE(!d->sm_mode || (d->Cout % 64 == 0 && !d->y_fp32 && d->out_sub != 2 && !d->bias && !d->residual && !d->mask && !d->mask_bits &&
+                              !d->relu && d->KH == 1 && d->KW == 1 && d->Cin <= 640 && d->y_cstride % 8 == 0));
+  SGB_REQUIRE(d->sm_mode != 1 || d->sm_stats);
+  SGB_REQUIRE(d->sm_mode != 2 || d->sm_stats);
+  SGB_REQUIRE(d->sm_mode != 3 || (d->sm_delta && d->sm_p && d->sm_p_cstride % 8 == 0 && ((uintptr_t)d->sm_p & 15) == 0));
   {
     // wide, few-channel 3x3 layers: halo-row kernel (umma_conv3x3.cu).  SGB_CONV3X3_ROWS=0 forces the generic kernel.
     const EngineSwitches& sw = switches();
@@ -548,20 +585,7 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   p.tiles_w = (d->W + p.tw - 1) / p.tw;
   p.tiles_h = (d->H + p.th - 1) / p.th;
   p.tiles_b = (d->B + p.nb - 1) / p.nb;
-  int BN;
-  if (d->Cout <= 16) BN = 16;
-  else if (d->Cout <= 32) BN = 32;
-  else if (d->Cout <= 64) BN = 64;
-  else if (d->Cout <= 128 || d->Cout % 256 != 0) BN = 128;
-  else BN = 256;
-  // 128-wide N tiles only when both halves of every 256-wide tile find an idle SM: an N = 128 tile takes nearly as long as an
-  // N = 256 one (the MMA is bound by the shared-memory fetch of the A tile: 712 vs 1381 TFLOP/s on 3x3 128 / 256 channels), so
-  // splitting pays only while tiles256 <= SMs / 2 (r02, B = 32: 3x3 256->256 @32x32 ran 557 TFLOP/s as 512 N = 128 tiles)
-  {
-    long long tiles256 = (long long)p.tiles_w * p.tiles_h * p.tiles_b * ((d->Cout + 255) / 256);
-    if (BN == 256 && 2LL * tiles256 <= sm_count()) BN = 128;
-  }
-  if (d->w_mode == 2 && BN < 64) BN = 64;  // MN-major B is staged in 64-wide atoms
+  const int BN = pick_bn(d, p.tiles_w * p.tiles_h * p.tiles_b);
   p.BN = BN;
   p.w_mode = d->w_mode;
   p.tiles_n = (d->Cout + BN - 1) / BN;
@@ -583,6 +607,10 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
     else if (!d->res_up2) p.aux_kind = 1;
     else if (p.tw >= 2) { p.aux_kind = 1; p.aux_tw = p.tw / 2; p.aux_th = p.th >= 2 ? p.th / 2 : 1; }
   }
+  if (d->sm_mode) {
+    SGB_REQUIRE(p.use_tma);                                            // (the softmax variants exist only for the staged-store epilogue)
+    if (d->sm_mode == 3) p.aux_kind = 3;                               // P tile of the softmax backward
+  }
   // short-K layers (one or two K blocks per tile) are store bound: their (small) filter stays resident in shared memory and the
   // space of the B halves of the ring buys more staging tiles per epilogue team = more store bytes in flight
   const uint32_t b_tile = (uint32_t)BN * kBlockK * 2;
@@ -602,6 +630,7 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   p.stages = stages;
   p.tmem_cols = pow2_cols(2 * BN);
   fill_epi(p.e, d);
+  p.e.sm_parts = 2 * p.tiles_n;
 
   CUtensorMap tmA, tmB;
   int rc = make_act_tmap(&tmA, d->x, d->B, Hin, Win, d->Cin, d->x_cstride, p.tw, p.th, p.nb);
@@ -631,8 +660,8 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   CUtensorMap tmAux = tmA;
   if (p.aux_kind) {
     const bool half = (p.aux_kind == 1 && d->res_up2);
-    const void* ap = p.aux_kind == 1 ? d->residual : d->mask;
-    const long long acs = p.aux_kind == 1 ? d->res_cstride : d->mask_cstride;
+    const void* ap = p.aux_kind == 1 ? d->residual : (p.aux_kind == 3 ? d->sm_p : d->mask);
+    const long long acs = p.aux_kind == 1 ? d->res_cstride : (p.aux_kind == 3 ? d->sm_p_cstride : d->mask_cstride);
     rc = make_act_tmap(&tmAux, ap, d->B, half ? d->H / 2 : d->H, half ? d->W / 2 : d->W, d->Cout, acs, p.aux_tw, p.aux_th, p.nb);
     if (rc) return rc;
   }
@@ -641,6 +670,7 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   // the hot epilogue shapes of the training step get compile-time variants; everything else takes the general kernel
   int f = p.use_tma ? epi_flags_of(p.e) : -1;
+  SGB_REQUIRE(!d->sm_mode || f == (kEpiFull | (d->sm_mode == 1 ? kEpiSmStats : d->sm_mode == 2 ? kEpiSmApply : kEpiSmBwd)));
   if (f >= 0 && p.aux_kind == 1) f |= kEpiAuxRes;
   if (f >= 0 && p.aux_kind == 2) f |= kEpiAuxMask;
 #define SGB_FPROP_CASE(FLAGS) \
@@ -658,6 +688,9 @@ extern "C" int sgb_conv_fprop(const sgb_conv_desc* d, sgb_stream_t stream_) {
     SGB_FPROP_CASE(kEpiFull | kEpiMask | kEpiMaskBits | kEpiResPre | kEpiAuxRes)      // fused block entry (bit plane + pooled-skip gradient)
     SGB_FPROP_CASE(kEpiFull | kEpiMask | kEpiAuxMask)                                 // dgrad through a ReLU (bf16 mask tile)
     SGB_FPROP_CASE(kEpiFull | kEpiMask | kEpiResPre | kEpiAuxMask)                    // fused block entry (bf16 mask tile)
+    SGB_FPROP_CASE(kEpiFull | kEpiSmStats)                                            // attention: row (max, sum exp) partials of theta . phi^T
+    SGB_FPROP_CASE(kEpiFull | kEpiSmApply)                                            // attention: P = softmax(theta . phi^T) written directly
+    SGB_FPROP_CASE(kEpiFull | kEpiSmBwd)                                              // attention: dS = P * (do . g^T - delta)
     default: return launch_fprop<-1>(grid, smem, stream, tmA, tmB, tmY, tmAux, p);
   }
 #undef SGB_FPROP_CASE

@@ -37,6 +37,7 @@ class ConvDesc(ctypes.Structure):
         ("Hin", c_int), ("Win", c_int), ("out_sub", c_int),
         ("res_scale", c_f),
         ("mask_bits", c_p), ("relu_bits", c_p),
+        ("sm_mode", c_int), ("sm_stats", c_p), ("sm_delta", c_p), ("sm_p", c_p), ("sm_p_cstride", c_i64),
     ]
 
 
@@ -81,6 +82,8 @@ SIGNATURES = {
     "sgb_pool2_bwd": (c_int, [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_int, c_int, c_int, c_int,
                               c_int, c_p]),
     "sgb_softmax_rows": (c_int, [c_p, c_p, c_i64, c_int, c_p]),
+    "sgb_rowdot": (c_int, [c_p, c_i64, c_p, c_i64, c_i64, c_int, c_p, c_p]),
+    "sgb_conv_softmax_parts": (c_int, [ctypes.POINTER(ConvDesc)]),
     "sgb_softmax_bwd_rows": (c_int, [c_p, c_p, c_p, c_i64, c_int, c_p]),
     "sgb_dot": (c_int, [c_p, c_p, c_i64, c_p, c_p]),
     "sgb_sum_hw": (c_int, [c_p, c_i64, c_int, c_int, c_int, c_int, c_p, c_p]),

@@ -7,6 +7,7 @@ Conventions
   (the consumer's dgrad epilogue does it for free via ``mask_input=True``).  That gradient is therefore the
   gradient w.r.t. the pre-activation and is used as is.
 """
+import os
 import torch
 import torch.distributed as dist
 from torch.autograd import Function
@@ -783,6 +784,9 @@ class ImageOutFn(TFunction):
         return K.img_grad_to_nhwc(dimg, img, ctx.Cp), None
 
 
+FUSED_SOFTMAX = os.environ.get("SGB_ATTN_FUSED_SOFTMAX", "1") != "0"   # A/B switch, read once
+
+
 class SelfAttentionFn(TFunction):
     """ops.SelfAttention.forward (src/utils/ops.py:83-103) with the attention map materialised in bf16:
        theta = conv(x), phi = maxpool(conv(x)), g = maxpool(conv(x)); P = softmax(theta . phi^T); o = P . g;
@@ -816,8 +820,14 @@ class SelfAttentionFn(TFunction):
         g_f = K.conv_fprop(x, packs[2][0], c2, 1, 1, 0, 0)
         phi = K.pool2_fwd(phi_f, 1)                                               # [B, c8, H/2, W/2]  keys  [M][c8]
         g = K.pool2_fwd(g_f, 1)                                                   # [B, c2, H/2, W/2]  values [M][c2]
-        S = K.conv_fprop(theta, phi, M, 1, 1, 0, 0, w_mode=1)                     # [B, M, H, W] == [B][N][M]
-        K.softmax_rows(S, M, out=S)                                               # P in place
+        if FUSED_SOFTMAX and M % 64 == 0:
+            # the score GEMM runs twice (K = C/8 is tiny): a statistics pass that stores nothing, then the pass whose epilogue
+            # writes P = softmax(theta . phi^T) directly -- the score matrix S never exists in memory
+            S, stats = K.conv_fprop(theta, phi, M, 1, 1, 0, 0, w_mode=1, sm_mode=1)
+            K.conv_fprop(theta, phi, M, 1, 1, 0, 0, w_mode=1, sm_mode=2, sm_stats=stats, out=S)
+        else:
+            S = K.conv_fprop(theta, phi, M, 1, 1, 0, 0, w_mode=1)                 # [B, M, H, W] == [B][N][M]
+            K.softmax_rows(S, M, out=S)                                           # P in place
         o = K.conv_fprop(S, g, c2, 1, 1, 0, 0, w_mode=2)                          # [B, c2, H, W]
         t = K.conv_fprop(o, packs[3][0], C, 1, 1, 0, 0)                           # conv1x1_attn
         out = K.axpby(t, x, a=1.0, a_dev=sigma, b=1.0)
@@ -839,9 +849,13 @@ class SelfAttentionFn(TFunction):
         do = K.conv_fprop(dt, packs[3][1], c2, 1, 1, 0, 0)
         G_o = K.conv_wgrad(o, dt, 1, 1, 0, 0)
         # o = P . g   ->  dP = do . g^T (keys as output channels), dg = P^T . do (per image)
-        dP = K.conv_fprop(do, g, M, 1, 1, 0, 0, w_mode=1)                         # g as [B][M][c2] K-major operand
         dg_pool = K.conv_wgrad(do, P, 1, 1, 0, 0, per_image=True)                 # [B][M][1][c2] fp32
-        dS = K.softmax_bwd_rows(P, dP, M, out=dP)
+        if FUSED_SOFTMAX and M % 64 == 0:
+            # dS = P * (dP - delta) in the epilogue of the dP GEMM, delta = rowsum(dP * P) = rowsum(do * o): dP never exists
+            dS = K.conv_fprop(do, g, M, 1, 1, 0, 0, w_mode=1, sm_mode=3, sm_delta=K.rowdot(do, o), sm_p=P)
+        else:
+            dP = K.conv_fprop(do, g, M, 1, 1, 0, 0, w_mode=1)                     # g as [B][M][c2] K-major operand
+            dS = K.softmax_bwd_rows(P, dP, M, out=dP)
         # S = theta . phi^T -> dtheta = dS . phi (phi as [B][K=M][N=c8] MN-major), dphi = dS^T . theta (per image)
         dtheta = K.conv_fprop(dS, phi, c8, 1, 1, 0, 0, w_mode=2)
         dphi_pool = K.conv_wgrad(theta, dS, 1, 1, 0, 0, per_image=True)           # [B][M][1][c8] fp32

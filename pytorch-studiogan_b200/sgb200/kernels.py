@@ -62,7 +62,7 @@ def _s():
 # ---------------------------------------------------------------------------------------------- conv engine
 def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_up2=False, res_after_mask=False,
                mask=None, relu=False, alpha=1.0, alpha_ptr=None, out=None, out_fp32=False, w_mode=0, same_size=True, stride=1,
-               res_scale=1.0, mask_bits=None, want_relu_bits=False):
+               res_scale=1.0, mask_bits=None, want_relu_bits=False, sm_mode=0, sm_stats=None, sm_delta=None, sm_p=None):
     """y = epilogue(conv(x, w)); see sgb_conv_fprop. ``w`` is a packed bf16 weight (layout by w_mode).
     want_relu_bits (with relu): also write the (y > 0) bit planes, returned as ``y._sgb_relu_bits`` (uint8 [B, H, W, Cout / 8]);
     mask_bits: such a tensor, used instead of ``mask`` by the input-gradient launch of the layer that consumed y.
@@ -104,6 +104,15 @@ def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_u
         out._sgb_relu_bits = bits
         BITS_STATS["written"] += 1
     d.y, d.y_cstride, d.y_fp32 = out.data_ptr(), ycs, 1 if out.dtype == torch.float32 else 0
+    if sm_mode:
+        d.sm_mode = sm_mode
+        if sm_mode in (1, 2):
+            if sm_stats is None:
+                parts = L.load().sgb_conv_softmax_parts(ctypes.byref(d))
+                sm_stats = torch.empty(B * H * W * parts * 2, device=x.device, dtype=torch.float32)
+            d.sm_stats = sm_stats.data_ptr()
+        else:
+            d.sm_delta, d.sm_p, d.sm_p_cstride = sm_delta.data_ptr(), sm_p.data_ptr(), geom(sm_p)[4]
     # algorithmic bytes: every operand tensor once (the residual at its own resolution), weights once
     nb = 2.0 * B * Hin * Win * Cin + out.element_size() * float(B * Ho * Wo * Cout) + 2.0 * Cout * Cin * KH * KW * (B if w_mode else 1)
     if residual is not None:
@@ -114,6 +123,10 @@ def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_u
         nb += B * H * W * Cout / 8.0
     if bits is not None:
         nb += B * H * W * Cout / 8.0
+    if sm_mode == 1:
+        nb -= out.element_size() * float(B * Ho * Wo * Cout)        # the statistics pass stores no tile
+    if sm_mode == 3:
+        nb += 2.0 * B * H * W * Cout
     # accounting kind = the kernel the library dispatches (csrc/umma_conv3x3.cu conv3x3_rows_eligible): the halo-row kernel, the
     # generic kernel on a k x k filter (tensor bound) or on a 1x1 filter (HBM bound at these channel counts)
     rows = (KH == 3 and KW == 3 and pad_h == 1 and pad_w == 1 and w_mode == 0 and same_size and stride == 1 and W % 128 == 0
@@ -121,6 +134,16 @@ def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_u
     kind = "conv3x3_rows" if rows else ("conv_fprop_1x1" if KH * KW == 1 else "conv_fprop_kxk")
     L.call("sgb_conv_fprop", ctypes.byref(d), _s(), tag="%s %dx%d %d->%d @%dx%d m%d" % (kind, KH, KW, Cin, Cout, H, W, w_mode),
            flops=2.0 * B * H * W * Cout * Cin * KH * KW, nbytes=nb)
+    if sm_mode == 1:
+        return out, sm_stats
+    return out
+
+
+def rowdot(x, y):
+    """fp32 [B*H*W]: sum over channels of x * y (bf16 NHWC tensors of equal shape)."""
+    B, C, H, W, xs = geom(x)
+    out = torch.empty(B * H * W, device=x.device, dtype=torch.float32)
+    L.call("sgb_rowdot", L.ptr(x), xs, L.ptr(y), geom(y)[4], B * H * W, C, L.ptr(out), _s(), nbytes=_nb(x, y))
     return out
 
 

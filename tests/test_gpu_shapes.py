@@ -463,3 +463,40 @@ def test_pool2_bwd_with_bit_planes_and_d_block_uses_them():
     D(img, lab)["adv_output"].sum().backward()
     if K.RELU_BITS:
         assert K.BITS_STATS["written"] > 0 and K.BITS_STATS["used"] >= K.BITS_STATS["written"] - 1, K.BITS_STATS   # (the head reads the last tensor itself)
+
+
+@pytest.mark.parametrize("B,S,c8,c2", [(2, 64, 64, 256), (3, 16, 48, 192), (1, 32, 16, 64)])
+def test_attention_softmax_inside_the_gemm_epilogues(B, S, c8, c2):
+    """P = softmax(theta . phi^T) written by the score GEMM's second pass (statistics pass + apply pass) and
+    dS = P * (do . g^T - rowsum(do * o)) written by the dP GEMM, against fp32 torch on the same bf16 operands
+    (src/utils/ops.py:93-97 and its autograd)."""
+    from sgb200 import kernels as K
+    dev = _cuda()
+    g_ = torch.Generator().manual_seed(S + c8)
+    N, M = S * S, (S // 2) * (S // 2)
+    theta = bfr(torch.randn(B, c8, S, S, generator=g_) * 0.7)
+    phi = bfr(torch.randn(B, c8, S // 2, S // 2, generator=g_) * 0.7)
+    gv = bfr(torch.randn(B, c2, S // 2, S // 2, generator=g_))
+    do = bfr(torch.randn(B, c2, S, S, generator=g_))
+    th, ph, gd, dod = (to_nhwc(t, dev) for t in (theta, phi, gv, do))
+    P, stats = K.conv_fprop(th, ph, M, 1, 1, 0, 0, w_mode=1, sm_mode=1)
+    K.conv_fprop(th, ph, M, 1, 1, 0, 0, w_mode=1, sm_mode=2, sm_stats=stats, out=P)
+    q = theta.reshape(B, c8, N).transpose(1, 2)                      # [B, N, c8]
+    k = phi.reshape(B, c8, M)                                        # [B, c8, M]
+    Pr = torch.softmax(torch.bmm(q, k), -1)                          # [B, N, M]
+    Pg = P.permute(0, 2, 3, 1).reshape(B, N, M).float().cpu()
+    assert float((Pg - Pr).abs().max()) < 8e-3 * float(Pr.max()) + 1e-6
+    assert float((Pg.sum(-1) - 1).abs().max()) < 2e-2
+    # same result as the two-kernel path (score GEMM rounded to bf16, then the row-softmax kernel) up to that rounding
+    S2 = K.conv_fprop(th, ph, M, 1, 1, 0, 0, w_mode=1)
+    K.softmax_rows(S2, M, out=S2)
+    assert rel_err(P, S2.float().cpu()) < 2e-2
+    # backward
+    o = K.conv_fprop(P, gd, c2, 1, 1, 0, 0, w_mode=2)
+    dS = K.conv_fprop(dod, gd, M, 1, 1, 0, 0, w_mode=1, sm_mode=3, sm_delta=K.rowdot(dod, o), sm_p=P)
+    v = gv.reshape(B, c2, M)                                          # [B, c2, M]
+    dP = torch.bmm(do.reshape(B, c2, N).transpose(1, 2), v)          # [B, N, M]
+    Pb = Pg                                                          # the bf16 P the kernels used
+    dSr = Pb * (dP - (Pb * dP).sum(-1, keepdim=True))
+    dSg = dS.permute(0, 2, 3, 1).reshape(B, N, M).float().cpu()
+    assert float((dSg - dSr).norm() / dSr.norm()) < 1.5e-2
