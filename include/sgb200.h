@@ -154,6 +154,15 @@ typedef struct sgb_sn_layer {
 } sgb_sn_layer;
 /* Partials per row the softmax statistics pass of sgb_conv_fprop writes for this problem size (2 x channel tiles). */
 int sgb_conv_softmax_parts(const sgb_conv_desc* d);
+/* Discriminator head on the fp32 sum-pooled features h [B][C] (src/models/big_resnet_deep_legacy.py:346-349,366-368; identical
+ * in big_resnet.py / resnet.py): adv[b] = <h_b, w1> / sigma1 + b1 + <h_b, E[labels[b]]> / sigmaE.  sigma1 / sigmaE / b1: device
+ * scalars or NULL; E NULL: unconditional head.  Backward: dh [B][C]; gw1 [C] and gE [n_cls][C] are the gradients of the
+ * EFFECTIVE (spectrally normalised) weights -- gE is ADDED to (zero it first), gw1 / db1 are overwritten -- and go through
+ * sgb_sn_backward like every other layer's. */
+int sgb_dhead_fwd(const float* h, const float* w1, const float* sigma1, const float* b1, const float* E, const float* sigmaE,
+                  const int64_t* labels, int32_t B, int32_t C, float* adv, sgb_stream_t stream);
+int sgb_dhead_bwd(const float* dadv, const float* h, const float* w1, const float* sigma1, const float* E, const float* sigmaE,
+                  const int64_t* labels, int32_t B, int32_t C, float* dh, float* gw1, float* gE, float* db1, sgb_stream_t stream);
 /* out[r] = sum_c x[r][c] * y[r][c] (bf16 rows of C channels, fp32 out): delta of the softmax backward. */
 int sgb_rowdot(const void* x, int64_t xs, const void* y, int64_t ys, int64_t rows, int32_t C, float* out, sgb_stream_t stream);
 /* max_blocks_wtu / max_blocks_wv: grid width of the two power-iteration launches; total_pack_tiles: sum of the table's pack

@@ -194,6 +194,70 @@ __global__ void __launch_bounds__(256) pool2_bwd_kernel(const bf16* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Discriminator head (src/models/big_resnet_deep_legacy.py:346-349,366-368; the same lines close big_resnet.py and
+// resnet.py): adv[b] = <h_b, w1> / sigma1 + b1 + <h_b, E[y_b]> / sigmaE on the fp32 sum-pooled features.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dhead_fwd_kernel(const float* __restrict__ h, const float* __restrict__ w1,
+                                                        const float* __restrict__ sigma1, const float* __restrict__ b1,
+                                                        const float* __restrict__ E, const float* __restrict__ sigmaE,
+                                                        const long long* __restrict__ labels, int B, int C, float* __restrict__ adv) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float* hp = h + (size_t)b * C;
+  const float* ep = E ? E + (size_t)labels[b] * C : nullptr;
+  float a1 = 0.f, a2 = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float hv = __ldg(hp + c);
+    a1 = fmaf(hv, __ldg(w1 + c), a1);
+    if (ep) a2 = fmaf(hv, __ldg(ep + c), a2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+  if (lane == 0) {
+    float r = sigma1 ? a1 / __ldg(sigma1) : a1;
+    if (b1) r += __ldg(b1);
+    if (ep) r += sigmaE ? a2 / __ldg(sigmaE) : a2;
+    adv[b] = r;
+  }
+}
+
+// dh[b][c] = dadv[b] * (w1[c] / sigma1 + E[y_b][c] / sigmaE); gE[y_b][c] += dadv[b] * h[b][c] (gradient of the EFFECTIVE table)
+__global__ void __launch_bounds__(256) dhead_bwd_rows_kernel(const float* __restrict__ dadv, const float* __restrict__ h,
+                                                             const float* __restrict__ w1, const float* __restrict__ sigma1,
+                                                             const float* __restrict__ E, const float* __restrict__ sigmaE,
+                                                             const long long* __restrict__ labels, int B, int C,
+                                                             float* __restrict__ dh, float* __restrict__ gE) {
+  const int b = blockIdx.y;
+  const float d = __ldg(dadv + b);
+  const float i1 = sigma1 ? 1.f / __ldg(sigma1) : 1.f;
+  const float iE = sigmaE ? 1.f / __ldg(sigmaE) : 1.f;
+  const long long y = E ? labels[b] : 0;
+  for (int c = blockIdx.x * 256 + threadIdx.x; c < C; c += gridDim.x * 256) {
+    float w = __ldg(w1 + c) * i1;
+    if (E) w = fmaf(__ldg(E + (size_t)y * C + c), iE, w);
+    if (dh) dh[(size_t)b * C + c] = d * w;
+    if (E && gE) atomicAdd(gE + (size_t)y * C + c, d * __ldg(h + (size_t)b * C + c));
+  }
+}
+
+// gw1[c] = sum_b dadv[b] * h[b][c] (gradient of the effective weight row), db1 = sum_b dadv[b]
+__global__ void __launch_bounds__(256) dhead_bwd_w_kernel(const float* __restrict__ dadv, const float* __restrict__ h, int B, int C,
+                                                          float* __restrict__ gw1, float* __restrict__ db1) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc = fmaf(__ldg(dadv + b), __ldg(h + (size_t)b * C + c), acc);
+    gw1[c] = acc;
+  }
+  if (db1 && blockIdx.x == 0 && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += __ldg(dadv + b);
+    *db1 = s;
+  }
+}
+
 // out[row] = sum_c x[row][c] * y[row][c]: delta = rowsum(dO * O) of the softmax backward; one warp per row.
 __global__ void __launch_bounds__(256) rowdot_kernel(const bf16* __restrict__ x, long long xs, const bf16* __restrict__ y, long long ys,
                                                      long long rows, int C, float* __restrict__ out) {
@@ -758,6 +822,32 @@ extern "C" int sgb_pool2_bwd(const void* dy, int64_t dys, const void* x, int64_t
     pool2_bwd_kernel<false><<<ew_blocks((long long)B * Ho * Wo * (C / 8)), 256, 0, stream>>>(
         (const bf16*)dy, dys, (const bf16*)x, xs, (const bf16*)add, adds, (const bf16*)relu_src, rs, (bf16*)dx, dxs, B, Ho, Wo, C, mode);
   SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_dhead_fwd(const float* h, const float* w1, const float* sigma1, const float* b1, const float* E,
+                             const float* sigmaE, const int64_t* labels, int32_t B, int32_t C, float* adv, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(h && w1 && adv && B > 0 && C > 0 && (!E || labels));
+  dhead_fwd_kernel<<<(B + 7) / 8, 256, 0, stream>>>(h, w1, sigma1, b1, E, sigmaE, (const long long*)labels, B, C, adv);
+  SGB_LAUNCH_CHECK();
+  return SGB_OK;
+}
+
+extern "C" int sgb_dhead_bwd(const float* dadv, const float* h, const float* w1, const float* sigma1, const float* E,
+                             const float* sigmaE, const int64_t* labels, int32_t B, int32_t C, float* dh, float* gw1, float* gE,
+                             float* db1, sgb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SGB_REQUIRE(dadv && h && w1 && B > 0 && C > 0 && (!E || labels));
+  if (dh || (E && gE)) {
+    dhead_bwd_rows_kernel<<<dim3((C + 255) / 256, B), 256, 0, stream>>>(dadv, h, w1, sigma1, E, sigmaE, (const long long*)labels, B, C,
+                                                                        dh, gE);
+    SGB_LAUNCH_CHECK();
+  }
+  if (gw1) {
+    dhead_bwd_w_kernel<<<(C + 255) / 256, 256, 0, stream>>>(dadv, h, B, C, gw1, db1);
+    SGB_LAUNCH_CHECK();
+  }
   return SGB_OK;
 }
 

@@ -82,6 +82,8 @@ SIGNATURES = {
     "sgb_pool2_bwd": (c_int, [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_int, c_int, c_int, c_int,
                               c_int, c_p]),
     "sgb_softmax_rows": (c_int, [c_p, c_p, c_i64, c_int, c_p]),
+    "sgb_dhead_fwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_p, c_p]),
+    "sgb_dhead_bwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_p, c_p, c_p, c_p, c_p]),
     "sgb_rowdot": (c_int, [c_p, c_i64, c_p, c_i64, c_i64, c_int, c_p, c_p]),
     "sgb_conv_softmax_parts": (c_int, [ctypes.POINTER(ConvDesc)]),
     "sgb_softmax_bwd_rows": (c_int, [c_p, c_p, c_p, c_i64, c_int, c_p]),

@@ -708,6 +708,61 @@ class SumHWFn(TFunction):
         return SumHWFn.apply(MaskFn.apply(tx, x) if relu else tx, False)
 
 
+class DHeadFn(TFunction):
+    """Discriminator head on the sum-pooled features (src/models/big_resnet_deep_legacy.py:346-349,366-368; the same lines in
+    big_resnet.py / resnet.py):  adv = <h, W1 / sigma1> + b1 [+ <h, E[y] / sigmaE>]  (projection discriminator or unconditional),
+    one launch forward, two backward; the spectral-norm power iteration and chain rule use the same kernels as every layer.
+    cfg: sn1 / snE (SpectralNormState | None), training, no_bias, reuse = the (sigma1, u1, v1, sigmaE, uE, vE) of an earlier call
+    (tangent pass: same effective weights, no new power iteration); the call leaves its own tuple in cfg["saved"]."""
+
+    @staticmethod
+    def forward(ctx, h, w1, b1, E, labels, cfg):
+        h = h.contiguous()
+        reuse = cfg.get("reuse")
+        if reuse is not None:
+            s1, u1, v1, sE, uE, vE = reuse
+        else:
+            def power(w, sn):
+                if sn is None:
+                    return None, None, None
+                u, v, ws = sn.tensors()
+                sg = torch.empty(1, device=w.device, dtype=torch.float32)
+                K.sn_power_iter(w.detach(), u, v, sg, ws, sn.eps, cfg.get("training", True))
+                return sg, u.clone(), v.clone()
+            s1, u1, v1 = power(w1, cfg.get("sn1"))
+            sE, uE, vE = power(E, cfg.get("snE")) if E is not None else (None, None, None)
+        cfg["saved"] = (s1, u1, v1, sE, uE, vE)
+        adv = K.dhead_fwd(h, w1, s1, None if cfg.get("no_bias", False) else b1, E, sE, labels)
+        ctx.has_E = E is not None
+        ctx.has_b = b1 is not None and not cfg.get("no_bias", False)
+        ctx.save_for_backward(h, w1, E, labels, s1, u1, v1, sE, uE, vE)
+        return adv
+
+    @staticmethod
+    def backward(ctx, dadv):
+        h, w1, E, labels, s1, u1, v1, sE, uE, vE = ctx.saved_tensors
+        need_dh = ctx.needs_input_grad[0]
+        need_w = ctx.needs_input_grad[1] or (ctx.has_E and ctx.needs_input_grad[3])
+        dh, gw1, gE, db1 = K.dhead_bwd(dadv.contiguous().float(), h, w1, s1, E, sE, labels, need_dh, need_w and not SKIP_PARAM_GRADS)
+        dW1 = dE = db = None
+        if gw1 is not None and ctx.needs_input_grad[1]:
+            C = h.shape[1]
+            dW1 = K.sn_backward(gw1, w1, u1, v1, s1, 1, C, 1)
+            if ctx.has_b and ctx.needs_input_grad[2]:
+                db = db1
+        if gE is not None and ctx.needs_input_grad[3]:
+            dE = K.sn_backward(gE, E, uE, vE, sE, E.shape[0], E.shape[1], 1)
+        return dh, dW1, db, dE, None, None
+
+    @staticmethod
+    def tangent(args, out, tan):
+        h, w1, b1, E, labels, cfg = args
+        th = tan(h)
+        if th is None:
+            return None
+        return DHeadFn.apply(th, w1, None, E, labels, {"reuse": cfg["saved"], "no_bias": True})
+
+
 class ToBF16Fn(TFunction):
     """[B, K] fp32 -> [B, Kp, 1, 1] bf16 activation (input of the linear layers); K is zero-padded to a multiple of 8
     (TMA stride granularity), e.g. the 10-way one-hot cBN input of ResNetGAN or BigGAN's 148-wide [embedding, z-chunk]."""

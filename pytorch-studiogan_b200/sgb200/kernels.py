@@ -139,6 +139,26 @@ def conv_fprop(x, w, Cout, KH, KW, pad_h, pad_w, bias=None, residual=None, res_u
     return out
 
 
+def dhead_fwd(h, w1, sigma1, b1, E, sigmaE, labels):
+    """adv [B] of the discriminator head (see sgb_dhead_fwd); h fp32 [B, C] contiguous."""
+    B, C = h.shape
+    adv = torch.empty(B, device=h.device, dtype=torch.float32)
+    L.call("sgb_dhead_fwd", L.ptr(h), L.ptr(w1), L.ptr(sigma1), L.ptr(b1), L.ptr(E), L.ptr(sigmaE), L.ptr(labels), B, C, L.ptr(adv), _s())
+    return adv
+
+
+def dhead_bwd(dadv, h, w1, sigma1, E, sigmaE, labels, need_dh=True, need_w=True):
+    """(dh [B, C] | None, gw1 [1, C] | None, gE [n_cls, C] | None, db1 [1] | None): gradients of the EFFECTIVE head weights."""
+    B, C = h.shape
+    dh = torch.empty_like(h) if need_dh else None
+    gw1 = torch.empty((1, C), device=h.device, dtype=torch.float32) if need_w else None
+    db1 = torch.empty(1, device=h.device, dtype=torch.float32) if need_w else None
+    gE = torch.zeros_like(E) if (need_w and E is not None) else None
+    L.call("sgb_dhead_bwd", L.ptr(dadv), L.ptr(h), L.ptr(w1), L.ptr(sigma1), L.ptr(E), L.ptr(sigmaE), L.ptr(labels), B, C,
+           L.ptr(dh), L.ptr(gw1), L.ptr(gE), L.ptr(db1), _s())
+    return dh, gw1, gE, db1
+
+
 def rowdot(x, y):
     """fp32 [B*H*W]: sum over channels of x * y (bf16 NHWC tensors of equal shape)."""
     B, C, H, W, xs = geom(x)

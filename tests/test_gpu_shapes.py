@@ -500,3 +500,47 @@ def test_attention_softmax_inside_the_gemm_epilogues(B, S, c8, c2):
     dSr = Pb * (dP - (Pb * dP).sum(-1, keepdim=True))
     dSg = dS.permute(0, 2, 3, 1).reshape(B, N, M).float().cpu()
     assert float((dSg - dSr).norm() / dSr.norm()) < 1.5e-2
+
+
+@pytest.mark.parametrize("mtd,sn", [("PD", True), ("W/O", True), ("PD", False)])
+def test_discriminator_head_kernels_match_the_eager_head(mtd, sn):
+    """sgb_dhead_fwd / sgb_dhead_bwd (+ the spectral-norm chain rule) against the same head written as tensor arithmetic
+    (src/models/big_resnet_deep_legacy.py:346-349,366-368): logits, feature gradient and parameter gradients."""
+    import copy
+    import importlib
+    from sgb200 import config as Cfg
+    from sgb200.utils import ops
+    dev = _cuda()
+    deep = importlib.import_module("sgb200.models.big_resnet_deep_legacy")
+    M = Cfg.make_modules(True, sn, "cBN", "big_resnet_deep_legacy")
+    MODEL = Cfg._Section(info_type="N/A", g_info_injection="N/A")
+    torch.manual_seed(3)
+    D1 = deep.Discriminator(img_size=32, d_conv_dim=16, apply_d_sn=sn, apply_attn=False, attn_d_loc=[1], d_cond_mtd=mtd,
+                            aux_cls_type="W/O", d_embed_dim="N/A", normalize_d_embed=False, num_classes=7, d_init="ortho",
+                            d_depth=1, mixed_precision=False, MODULES=M, MODEL=MODEL).to(dev).train()
+    D2 = copy.deepcopy(D1)
+    for m in D2.modules():
+        if hasattr(m, "_sn"):
+            m._sn.module, m._sn.ws = m, None
+    g = torch.Generator().manual_seed(1)
+    C = D1.linear1.in_features
+    h0 = (torch.rand(6, C, generator=g) * 3).to(dev)
+    lab = torch.randint(0, 7, (6,), generator=g).to(dev)
+    res = []
+    for D, fused in ((D1, True), (D2, False)):
+        ops.DHEAD_FUSED = fused
+        try:
+            h = h0.clone().requires_grad_(True)
+            adv = ops.discriminator_head(D, h, lab)["adv_output"]
+            (adv * torch.arange(1, 7, device=dev).float()).sum().backward()
+        finally:
+            ops.DHEAD_FUSED = True
+        pg = {n: p.grad.clone() for n, p in D.named_parameters() if p.grad is not None}
+        res.append((adv.detach(), h.grad.clone(), pg))
+    (a1, dh1, g1), (a2, dh2, g2) = res
+    assert rel_err(a1, a2.cpu()) < 1e-5 and rel_err(dh1, dh2.cpu()) < 1e-5
+    assert set(g1) == set(g2) and len(g1) >= (3 if mtd == "PD" else 2)
+    for n in g1:
+        assert rel_err(g1[n], g2[n].cpu()) < 1e-4, n
+    if sn:   # both heads ran one power iteration from the same state
+        assert rel_err(D1.linear1.weight_u, D2.linear1.weight_u.cpu()) < 1e-6
