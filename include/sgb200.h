@@ -200,7 +200,8 @@ int sgb_bn_stats(const void* x, int64_t npix, int32_t C, int64_t x_cstride, floa
 int sgb_bn_finalize(const float* sum, const float* sumsq, float count, float* running_mean, float* running_var,
                     float momentum, float eps, int32_t use_batch_stats, int32_t track, int32_t mode, const float* gain,
                     const float* bias, int32_t nb, int32_t C, float* mean, float* rstd, float* scale, float* shift,
-                    sgb_stream_t stream);
+                    int64_t affine_ld, sgb_stream_t stream);   /* affine_ld: floats between the rows of the per-image gain / bias
+                                                                  (0 = C; > C when they are column slices of one batched GEMM output) */
 /* y = [relu](x*scale + shift); per_image: scale/shift are [B][C] else [C]; up2: y is the nearest x2 upsample. */
 int sgb_scale_shift_act(const void* x, int32_t B, int32_t H, int32_t W, int32_t C, int64_t x_cstride, const float* scale,
                         const float* shift, int32_t per_image, int32_t relu, int32_t up2, void* y, int64_t y_cstride,

@@ -85,7 +85,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, int use_batch_stats, int track, int mode, const float* __restrict__ gain,
                                    const float* __restrict__ bias, int nb, int C, float* __restrict__ mean_out,
-                                   float* __restrict__ rstd_out, float* __restrict__ scale, float* __restrict__ shift) {
+                                   float* __restrict__ rstd_out, float* __restrict__ scale, float* __restrict__ shift, long long affine_ld) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float mean, var;
@@ -108,7 +108,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
   }
   for (int b = blockIdx.y; b < nb; b += gridDim.y) {   // images spread over blockIdx.y: no 256-deep serial loop for cBN
     float g = 1.f, be = 0.f;
-    if (mode == 0) { g = 1.f + gain[(size_t)b * C + c]; be = bias[(size_t)b * C + c]; }
+    if (mode == 0) { g = 1.f + gain[(size_t)b * affine_ld + c]; be = bias[(size_t)b * affine_ld + c]; }
     else if (mode == 1) { g = gain[c]; be = bias[c]; }
     const float sc = rstd * g;
     scale[(size_t)b * C + c] = sc;
@@ -544,14 +544,14 @@ extern "C" int sgb_bn_stats(const void* x, int64_t npix, int32_t C, int64_t x_cs
 extern "C" int sgb_bn_finalize(const float* sum, const float* sumsq, float count, float* running_mean, float* running_var,
                                float momentum, float eps, int32_t use_batch_stats, int32_t track, int32_t mode,
                                const float* gain, const float* bias, int32_t nb, int32_t C, float* mean, float* rstd,
-                               float* scale, float* shift, sgb_stream_t stream_) {
+                               float* scale, float* shift, int64_t affine_ld, sgb_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  SGB_REQUIRE(C > 0 && nb > 0 && mean && rstd && scale && shift);
+  SGB_REQUIRE(C > 0 && nb > 0 && mean && rstd && scale && shift && (affine_ld == 0 || affine_ld >= C));
   SGB_REQUIRE(use_batch_stats ? (sum && sumsq && count > 0.f) : (running_mean && running_var));
   SGB_REQUIRE(mode == 2 || (gain && bias));
   bn_finalize_kernel<<<dim3((C + 127) / 128, nb < 128 ? nb : 128), 128, 0, stream>>>(sum, sumsq, count, running_mean, running_var, momentum, eps,
                                                           use_batch_stats, track, mode, gain, bias, nb, C, mean, rstd, scale,
-                                                          shift);
+                                                          shift, affine_ld > 0 ? affine_ld : C);
   SGB_LAUNCH_CHECK();
   return SGB_OK;
 }

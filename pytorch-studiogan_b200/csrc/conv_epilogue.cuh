@@ -222,6 +222,14 @@ __host__ __device__ inline int epi_flags_of(const EpiArgs& p) {
   return f;
 }
 
+// 2^x on the SFU (ex2.approx: 2^-22 relative error, far below the bf16 rounding of the softmax output); the accurate exp2f
+// costs ~10 instructions per element and made the softmax epilogues issue bound (r02: 0.88 ms per score-GEMM pass)
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Softmax statistics of one accumulator tile (sm_mode 1): this thread's row, the 64-column chunks of its team; the running
 // (max, sum exp) pair is kept in registers and stored once -- nothing else leaves the SM.
 __device__ __forceinline__ void epilogue_tile_smstats(const EpiArgs& p, uint32_t t_row, int BN, int n0, bool valid, long long pix,
@@ -245,10 +253,11 @@ __device__ __forceinline__ void epilogue_tile_smstats(const EpiArgs& p, uint32_t
       const float mn = fmaxf(m, pm);
       float acc = 0.f;
 #pragma unroll
+      const float a2 = alpha * kLog2e, mn2 = -mn * kLog2e;
       for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc += exp2f((__uint_as_float(v[q][j]) * alpha - mn) * kLog2e);
-      l = l * exp2f((m - mn) * kLog2e) + acc;
+        for (int j = 0; j < 16; ++j) acc += fast_ex2(fmaf(__uint_as_float(v[q][j]), a2, mn2));
+      l = l * fast_ex2((m - mn) * kLog2e) + acc;
       m = mn;
     }
   }
@@ -367,8 +376,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
     float m = -INFINITY;
     for (int i = 0; i < p.sm_parts; ++i) m = fmaxf(m, __ldcg(&st[i].x));
     float l = 0.f;
-    for (int i = 0; i < p.sm_parts; ++i) { const float2 t = __ldcg(&st[i]); l += t.y * exp2f((t.x - m) * kLog2e); }
-    sm_a = m; sm_b = 1.f / l;
+    for (int i = 0; i < p.sm_parts; ++i) { const float2 t = __ldcg(&st[i]); l += t.y * fast_ex2((t.x - m) * kLog2e); }
+    sm_a = -m * kLog2e; sm_b = 1.f / l;          // exponent offset in base-2 units
   }
   if (sm_bwd && valid) sm_a = __ldg(p.sm_delta + pix);
   const bool has_bias = F < 0 ? p.bias != nullptr : (F & kEpiBias) != 0;
@@ -430,7 +439,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
         const bool in_c = full_c || nvalid > 0;
         if (sm_apply) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = exp2f((f[j] - sm_a) * kLog2e) * sm_b;
+          for (int j = 0; j < 16; ++j) f[j] = fast_ex2(fmaf(f[j], kLog2e, sm_a)) * sm_b;
         }
         if (sm_bwd) {                                // dS = P * (dP - delta); P: this row of the aux tile
 #pragma unroll

@@ -70,7 +70,7 @@ SIGNATURES = {
     "sgb_sn_backward_batch": (c_int, [c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_int, c_p]),
     "sgb_bn_stats": (c_int, [c_p, c_i64, c_int, c_i64, c_p, c_p, c_p]),
     "sgb_bn_finalize": (c_int, [c_p, c_p, c_f, c_p, c_p, c_f, c_f, c_int, c_int, c_int, c_p, c_p, c_int, c_int,
-                                c_p, c_p, c_p, c_p, c_p]),
+                                c_p, c_p, c_p, c_p, c_i64, c_p]),
     "sgb_scale_shift_act": (c_int, [c_p, c_int, c_int, c_int, c_int, c_i64, c_p, c_p, c_int, c_int, c_int, c_p, c_i64, c_p]),
     "sgb_bn_bwd_reduce": (c_int, [c_p, c_i64, c_p, c_i64, c_int, c_int, c_int, c_int, c_p, c_p, c_int, c_p, c_p, c_int,
                                   c_int, c_p, c_p, c_p, c_p, c_p]),

@@ -329,9 +329,10 @@ class BNActFn(TFunction):
         nb = B if mode == 0 else 1
         g = gain.reshape(nb, C) if gain is not None else None
         b = bias.reshape(nb, C) if bias is not None else None
-        if g is not None and not g.is_contiguous():
+        rows_ok = lambda t: t.dim() == 2 and t.stride(1) == 1      # column slice of the batched affine GEMM: row stride > C
+        if g is not None and not g.is_contiguous() and not (rows_ok(g) and b is not None and rows_ok(b) and g.stride(0) == b.stride(0)):
             g = g.contiguous()
-        if b is not None and not b.is_contiguous():
+        if b is not None and not b.is_contiguous() and not (g is not None and rows_ok(g) and rows_ok(b) and g.stride(0) == b.stride(0)):
             b = b.contiguous()
         mean, rstd, scale, shift = K.bn_finalize(stats, count, running_mean, running_var, cfg["momentum"], cfg["eps"],
                                                  (2 if cfg.get("clamp_eps") else 1) if cfg["use_batch_stats"] else 0,

@@ -258,8 +258,18 @@ def bn_finalize(stats, count, running_mean, running_var, momentum, eps, use_batc
     shift = torch.empty((nb, C), device=device, dtype=torch.float32)
     L.call("sgb_bn_finalize", L.ptr(stats[0]) if stats is not None else None, L.ptr(stats[1]) if stats is not None else None,
            float(count), L.ptr(running_mean), L.ptr(running_var), float(momentum), float(eps), int(use_batch_stats),
-           1 if track else 0, mode, L.ptr(gain), L.ptr(bias), nb, C, L.ptr(mean), L.ptr(rstd), L.ptr(scale), L.ptr(shift), _s())
+           1 if track else 0, mode, L.ptr(gain), L.ptr(bias), nb, C, L.ptr(mean), L.ptr(rstd), L.ptr(scale), L.ptr(shift),
+           _affine_ld(gain, bias, mode, C), _s())
     return mean, rstd, scale, shift
+
+
+def _affine_ld(gain, bias, mode, C):
+    """Row stride of the per-image gain / bias of a conditional batch norm: C, or the width of the batched affine GEMM output
+    they are column slices of (snbatch.cbn_affine_all)."""
+    if mode != 0 or gain is None or gain.dim() != 2 or gain.stride(0) == C:
+        return 0
+    assert gain.stride(1) == 1 and bias.stride(1) == 1 and gain.stride(0) == bias.stride(0)
+    return gain.stride(0)
 
 
 def scale_shift_act(x, scale, shift, per_image, relu, up2):

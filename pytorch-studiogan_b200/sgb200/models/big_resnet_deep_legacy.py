@@ -118,6 +118,8 @@ class Generator(nn.Module):
         if parts:
             z = torch.cat(parts + [z], 1)
         affine = A.ToBF16Fn.call(z)                                  # [B, K, 1, 1] bf16, shared by every cBN
+        if self.g_cond_mtd == "cBN":
+            self._snb.cbn_affine_all(affine)                         # gradient-free passes: all 96 gain / bias maps as one GEMM
         S = self.bottom * self.bottom
         act = self.linear0(affine, perm_S=S)                          # [B, S*C0, 1, 1], features already in (s, c) order
         B = act.shape[0]

@@ -78,6 +78,7 @@ class SNBatch:
 
     def _build(self, device):
         mods = [m for m in self.net.modules() if _eligible(m)]
+        mods.sort(key=lambda m: 0 if getattr(m, "_cbn_affine", False) else 1)     # (stable) cBN gain / bias packs first, contiguous
         nu = sum(ops._w(m).shape[0] for m in mods if hasattr(m, "_sn"))
         nv = sum(ops._w(m).numel() // ops._w(m).shape[0] for m in mods if hasattr(m, "_sn"))
         self.u_flat = torch.empty(max(nu, 1), device=device, dtype=torch.float32)
@@ -142,6 +143,21 @@ class SNBatch:
             if su is not None:
                 e["has_sn"], e["off_u"], e["off_v"] = 1, su[0], sv[0]
         self._bwd_host = bt
+        # conditional-BN affine maps as ONE GEMM in gradient-free passes (cbn_affine_all): the leading packs form one [rows][K] matrix
+        self.cbn = None
+        n = sum(1 for m in mods if getattr(m, "_cbn_affine", False))
+        if n >= 2:
+            Kp = int(table[0]["Cin_p"])
+            rows, ok, spans = 0, True, []
+            for i in range(n):
+                e = table[i]
+                ok = ok and int(e["taps"]) == 1 and int(e["Cin_p"]) == Kp and int(e["perm_S"]) == 1 and \
+                    self.slices[i][0] == self.slices[0][0] + rows * Kp
+                spans.append((rows, int(e["Cout"])))
+                rows += int(e["Cout_p"])
+            if ok:
+                self.cbn = (n, rows, Kp, self.slices[0][0], spans)
+        self._pf = None
 
     def bwd_table(self):
         """Device table for sgb_sn_backward_batch, valid while every layer's ``.grad`` is its view of the flat gradient arena
@@ -176,6 +192,7 @@ class SNBatch:
         us = self.u_flat.clone() if need_grad else None
         vs = self.v_flat.clone() if need_grad else None
         cur = _Pass(self, sigma, us, vs) if need_grad else None
+        self._pf = pf
         for i, (m, (of, od, nf, shf, shd, su, sv)) in enumerate(zip(self.mods, self.slices)):
             m._sn_pass = (cur, i) if cur is not None else None
             wf = pf[of:of + nf].view(shf)
@@ -185,8 +202,27 @@ class SNBatch:
                            us[su[0]:su[1]] if (has_sn and us is not None) else None,
                            vs[sv[0]:sv[1]] if (has_sn and vs is not None) else None)
 
+    def cbn_affine_all(self, y):
+        """Gradient-free passes of a generator whose conditional batch norms all take the same conditioning vector ``y``
+        ([B, K, 1, 1] bf16): every gain(y) / bias(y) (src/utils/ops.py:24-28, 2 x 48 small GEMMs per BigGAN-Deep forward) as ONE
+        GEMM against the contiguous packs; each layer then reads its column slice (``module._pre_out``)."""
+        if self.cbn is None or self._pf is None or torch.is_grad_enabled():
+            return False
+        n, rows, Kp, of0, spans = self.cbn
+        if y.shape[1] != Kp:
+            return False
+        w = self._pf[of0:of0 + rows * Kp].view(rows, 1, Kp)
+        out = K.conv_fprop(y, w, rows, 1, 1, 0, 0, out_fp32=True)
+        out2 = out.permute(0, 2, 3, 1).reshape(y.shape[0], rows)
+        for m, (r0, c) in zip(self.mods[:n], spans):
+            m._pre_out = out2[:, r0:r0 + c]
+        return True
+
     def clear(self):
+        self._pf = None
         if self.mods:
             for m in self.mods:
                 m._sn_cache = None
                 m._sn_pass = None
+                if getattr(m, "_cbn_affine", False):
+                    m._pre_out = None

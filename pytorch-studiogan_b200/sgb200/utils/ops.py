@@ -229,8 +229,14 @@ class ConditionalBatchNorm2d(nn.Module):
         self.bn = batchnorm_2d(out_features, eps=1e-4, momentum=0.1, affine=False)
         self.gain = MODULES.g_linear(in_features=in_features, out_features=out_features, bias=False)
         self.bias = MODULES.g_linear(in_features=in_features, out_features=out_features, bias=False)
+        self.gain._cbn_affine = self.bias._cbn_affine = True        # snbatch keeps these packs contiguous (cbn_affine_all)
 
     def forward(self, x, y, relu=False, up2=False):
+        pre_g, pre_b = getattr(self.gain, "_pre_out", None), getattr(self.bias, "_pre_out", None)
+        if pre_g is not None and pre_b is not None and not torch.is_grad_enabled():
+            # gradient-free pass of a generator whose cBN layers all see the same y: their affine maps were computed by ONE GEMM
+            self.gain._pre_out = self.bias._pre_out = None
+            return self.bn(x, relu=relu, up2=up2, gain=pre_g, bias=pre_b)
         gain = self.gain(y, out_fp32=True)
         bias = self.bias(y, out_fp32=True)
         return self.bn(x, relu=relu, up2=up2, gain=gain, bias=bias)

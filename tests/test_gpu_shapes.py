@@ -544,3 +544,45 @@ def test_discriminator_head_kernels_match_the_eager_head(mtd, sn):
         assert rel_err(g1[n], g2[n].cpu()) < 1e-4, n
     if sn:   # both heads ran one power iteration from the same state
         assert rel_err(D1.linear1.weight_u, D2.linear1.weight_u.cpu()) < 1e-6
+
+
+def test_batched_cbn_affine_gemm_matches_per_layer_linears():
+    """Gradient-free generator passes compute every cBN gain(y) / bias(y) with one GEMM over the contiguous packs
+    (snbatch.cbn_affine_all); the image must equal the per-layer path (grad-enabled pass of an identical copy)."""
+    import copy
+    import importlib
+    from sgb200 import config as Cfg
+    from sgb200 import kernels as K
+    dev = _cuda()
+    deep = importlib.import_module("sgb200.models.big_resnet_deep_legacy")
+    M = Cfg.make_modules(True, True, "cBN", "big_resnet_deep_legacy")
+    MODEL = Cfg._Section(info_type="N/A", g_info_injection="N/A")
+    torch.manual_seed(11)
+    G1 = deep.Generator(z_dim=24, g_shared_dim=16, img_size=32, g_conv_dim=16, apply_attn=False, attn_g_loc=[2], g_cond_mtd="cBN",
+                        num_classes=9, g_init="ortho", g_depth=2, mixed_precision=False, MODULES=M, MODEL=MODEL).to(dev).train()
+    G2 = copy.deepcopy(G1)
+    for net in (G2,):
+        for m in net.modules():
+            if hasattr(m, "_sn"):
+                m._sn.module, m._sn.ws = m, None
+        net._snb.net, net._snb.mods = net, None
+    g = torch.Generator().manual_seed(2)
+    z = torch.randn(5, 24, generator=g).to(dev)
+    y = torch.randint(0, 9, (5,), generator=g).to(dev)
+    calls = []
+    orig = K.conv_fprop
+    K.conv_fprop = lambda *a, **k: (calls.append(a[2]), orig(*a, **k))[1]
+    try:
+        with torch.no_grad():
+            img1 = G1(z, y)
+        n1 = len(calls)
+        calls.clear()
+        img2 = G2(z, y)
+        n2 = len(calls)
+    finally:
+        K.conv_fprop = orig
+    assert G1._snb.cbn is not None and n1 < n2 - 10, (n1, n2)            # dozens of tiny GEMMs became one
+    assert rel_err(img1, img2.detach().float().cpu()) < 2e-3
+    for (n, b1), (_, b2) in zip(G1.named_buffers(), G2.named_buffers()):
+        if "running_" in n or n.endswith("weight_u"):
+            assert rel_err(b1, b2.cpu()) < 1e-4, n
