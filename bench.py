@@ -520,14 +520,14 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained"
     step_flop = STEP_GFLOP_PER_IMAGE.get(workload, 0.0) * 1e9 * global_batch
-    # roofline.traffic: DRAM bytes per launch of the dominant kernel from this round's committed `ncu --set full` capture
-    # (profiles/r02_ncu_traffic.json, written by profiles/summarize_ncu.py); null when no capture of the current kernel exists
-    traffic, traffic_note = None, "no ncu capture of the current kernel committed"
+    # roofline.traffic: DRAM bytes per launch of the dominant kernel from this round's committed `ncu --set full` captures
+    # (profiles/r02_ncu_traffic.json, one record per conv kernel kind, written from the .ncu-rep files of profiles/ncu_target.py)
+    traffic_db = {}
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
-        traffic, traffic_note = t["dram_bytes_per_launch"], t["note"]
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
     except Exception:
         pass
+    traffic, traffic_note = None, "no ncu capture of the current kernel committed"
     roof = {"bound": "tensor", "unit": "TFLOP/s", "peak": peak_tf, "peak_source": peak_src, "traffic": traffic, "traffic_note": traffic_note,
             "step_algorithmic_tflop": step_flop * 1e-12,
             "step_achieved": step_flop / (ms_step * 1e-3) * 1e-12 / world,
@@ -535,20 +535,26 @@ def main():
     CONV_KINDS = ("conv3x3_rows", "conv_fprop_kxk", "conv_fprop_1x1", "conv_wgrad")
     if isinstance(prof, dict) and any(kk in prof for kk in CONV_KINDS):
         hbm = peaks.get("hbm_gbs", 6500.0)
-        # the dominant kernel = the tensor-core kernel with the most time in the accounting step (the halo-row 3x3 kernel for
-        # the 256x256 workloads); the other conv kernels are listed beside it with both of their rates, because the 1x1
-        # launches of the generic kernel are HBM bound, not tensor bound
+        # every conv kernel class is listed under roofline.kernels with both of its rates (TFLOP/s and GB/s) and its share of the step
         kname = {"conv3x3_rows": "conv3x3_rows_kernel (3x3 fprop + dgrad, halo rows, tcgen05)",
                  "conv_fprop_kxk": "conv_fprop_kernel on k x k filters (fprop + dgrad, tcgen05)",
                  "conv_fprop_1x1": "conv_fprop_kernel on 1x1 filters / GEMMs (fprop + dgrad, tcgen05; HBM bound)",
                  "conv_wgrad": "conv_wgrad_kernel + wgrad3x3_c64_kernel (weight gradients, tcgen05)"}
-        tensor_kinds = [kk for kk in ("conv3x3_rows", "conv_fprop_kxk", "conv_wgrad") if kk in prof]
-        dom = max(tensor_kinds, key=lambda kk: prof[kk]["ms"]) if tensor_kinds else "conv_fprop_1x1"
+        # dominant = the conv kernel class with the most time in the accounting step.  The 1x1 launches of conv_fprop_kernel are
+        # HBM bound (K = 32..128 channels: a few FLOP per byte), the others tensor bound; the roofline is reported accordingly.
+        dom = max((kk for kk in CONV_KINDS if kk in prof), key=lambda kk: prof[kk]["ms"])
         k = prof[dom]
+        if dom in traffic_db:
+            traffic, traffic_note = traffic_db[dom]["dram_bytes_per_launch"], traffic_db[dom]["note"]
+            roof["traffic_algorithmic_bytes_of_that_launch"] = traffic_db[dom]["algorithmic_bytes"]
+        roof["traffic"], roof["traffic_note"] = traffic, traffic_note
+        if dom == "conv_fprop_1x1":
+            roof.update({"bound": "hbm", "unit": "GB/s", "peak": hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy)"})
         ew = {kk: vv for kk, vv in prof.items() if kk not in CONV_KINDS and vv.get("gbytes")}
         ew_ms = sum(v["ms"] for v in ew.values())
         ew_gb = sum(v["gbytes"] for v in ew.values())
-        roof.update({"kernel": kname[dom], "achieved": k["tflops"], "frac": k["tflops"] / peak_tf,
+        ach = k["gb_per_s"] if roof["bound"] == "hbm" else k["tflops"]
+        roof.update({"kernel": kname[dom], "achieved": ach, "frac": ach / roof["peak"],
                      "kernel_ms_per_step": k["ms"], "kernel_share_of_step": k["ms"] / ms_step,
                      "kernel_algorithmic_gbytes_per_step": k["gbytes"], "kernel_gb_per_s": k["gb_per_s"],
                      "kernels": {kname[kk]: dict(prof[kk], frac_of_tensor_peak=(prof[kk]["tflops"] or 0.0) / peak_tf,
