@@ -200,6 +200,9 @@ def fid_eval_seconds(worker, cfgs, device, num_eval, batch, world=1):
             n = min(batch, max(0, num_eval - i - batch * (dist.get_rank() if world > 1 else 0)))
             if n > 0:
                 yield torch.randint(0, 256, (n, 3, S, S), generator=gen, device=device).float()
+    # load cuSOLVER (the Frechet distance's two symmetric eigendecompositions) before anything is timed: on a fresh box the first
+    # call pages the library in from disk, measured at 0.2 s to 30 s for the same code (profiles/r02_fid_n2_eval_phases.txt)
+    torch.linalg.eigvalsh(torch.eye(64, dtype=torch.float64, device=device))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

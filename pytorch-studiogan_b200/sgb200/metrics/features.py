@@ -1,10 +1,27 @@
 """Feature stacking for evaluation (reference ``src/metrics/features.py:17-65``): generate ceil(N/B) batches with the
 generator, run the evaluation model on each, concatenate, all-gather across ranks."""
 import math
+import os
+import sys
+import time
 
 import torch
 
 from ..utils import losses, sample
+
+
+_T0 = [None]
+
+
+def _tick(what, device):
+    """SGB_EVAL_TIMING=1: wall seconds of the evaluation phases on stderr (synchronising; diagnostics only)."""
+    if os.environ.get("SGB_EVAL_TIMING", "0") == "0":
+        return
+    torch.cuda.synchronize()
+    now = time.perf_counter()
+    if _T0[0] is not None and what:
+        sys.stderr.write("[sgb200 eval] %-52s %.3f s\n" % (what, now - _T0[0]))
+    _T0[0] = now
 
 
 def generate_images_and_stack_features(generator, discriminator, eval_model, num_generate, y_sampler, batch_size, z_prior,
@@ -15,6 +32,7 @@ def generate_images_and_stack_features(generator, discriminator, eval_model, num
     [sum f, sum f f^T]; only the rows that survive the reference's ``[:num_generate]`` truncation of the rank-major
     gathered matrix are counted, so the statistics are those of exactly the same feature set."""
     eval_model.eval()
+    _tick(None, device)
     feature_holder, prob_holder, fake_label_holder = [], [], []
     if device == 0 and logger is not None:
         logger.info("generate images and stack features ({} images).".format(num_generate))
@@ -44,10 +62,12 @@ def generate_images_and_stack_features(generator, discriminator, eval_model, num
     feature_holder = torch.cat(feature_holder, 0)
     prob_holder = torch.cat(prob_holder, 0)
     fake_label_holder = torch.cat(fake_label_holder, 0)
+    _tick("generate + extract (%d batches of %d)" % (num_batches, batch_size), device)
     if DDP:
         feature_holder = torch.cat(losses.GatherLayer.apply(feature_holder), dim=0)
         prob_holder = torch.cat(losses.GatherLayer.apply(prob_holder), dim=0)
         fake_label_holder = torch.cat(losses.GatherLayer.apply(fake_label_holder), dim=0)
+        _tick("gather features / probabilities / labels", device)
     return feature_holder, prob_holder, list(fake_label_holder.detach().cpu().numpy())
 
 

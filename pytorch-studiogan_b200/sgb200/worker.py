@@ -323,18 +323,22 @@ def _evaluate(self, step, metrics, writing=True, training=False):
             RUN=self.RUN, MODEL=self.MODEL, quantize=True, world_size=getattr(self.OPTIMIZATION, "world_size", 1), DDP=self.DDP,
             device=self.local_rank, logger=self.logger, moments=moments)
         if "is" in metrics:
+            features._tick(None, self.local_rank)
             kl_score, kl_std, top1, top5 = ins.eval_features(probs=fake_probs, labels=fake_labels, data_loader=self.eval_dataloader,
                                                              num_features=num_eval, split=num_splits, is_acc=is_acc)
             metric_dict.update({"IS": float(kl_score), "Top1_acc": top1, "Top5_acc": top5})
+            features._tick("inception score", self.local_rank)
         if "fid" in metrics:
             if self.DDP:
                 moments.all_reduce(getattr(self.Gen, "sgb_group", None))
+                features._tick("moments all-reduce", self.local_rank)
             m1, c1 = moments.finalize()
             fid_score = fid.frechet_distance_device(m1, c1, torch.as_tensor(self.mu, device=m1.device),
                                                     torch.as_tensor(self.sigma, device=m1.device))
             if self.best_fid is None or fid_score <= self.best_fid:
                 self.best_fid, self.best_step, is_best = fid_score, step, True
             metric_dict.update({"FID": fid_score})
+            features._tick("moments finalize + Frechet distance", self.local_rank)
         if "prdc" in metrics:
             pr = prdc.compute_prdc(real_features=torch.as_tensor(self.real_feats, dtype=torch.float64, device=fake_feats.device),
                                    fake_features=fake_feats[:num_eval].to(torch.float64), nearest_k=nearest_k)
