@@ -202,7 +202,11 @@ def fid_eval_seconds(worker, cfgs, device, num_eval, batch, world=1):
                 yield torch.randint(0, 256, (n, 3, S, S), generator=gen, device=device).float()
     # load cuSOLVER (the Frechet distance's two symmetric eigendecompositions) before anything is timed: on a fresh box the first
     # call pages the library in from disk, measured at 0.2 s to 30 s for the same code (profiles/r02_fid_n2_eval_phases.txt)
-    torch.linalg.eigvalsh(torch.eye(64, dtype=torch.float64, device=device))
+    _a = torch.randn(2048, 2048, dtype=torch.float64, device=device)
+    _a = _a @ _a.t()
+    torch.linalg.eigh(_a)
+    torch.linalg.eigvalsh(_a)
+    del _a
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
