@@ -35,6 +35,20 @@ __device__ __forceinline__ uint32_t positive_bits16(const float (&f)[16]) {
   for (int j = 0; j < 16; ++j) b |= (f[j] > 0.f) ? (1u << j) : 0u;
   return b;
 }
+// The same 16 bits from the PACKED bf16 pairs of a post-ReLU piece (every half is +0 or a positive value <= 0x7F80): adding
+// 0x7FFF to a half sets its bit 15 iff it is non-zero without carrying into its neighbour; PRMT gathers the four flag bytes of
+// two words, one multiply moves the four flags into a nibble.  27 integer instructions per piece instead of 40
+// (FSETP + SEL per element + adds) -- the bit plane is paid for by write-bound layers (r02: 1x1 32->128 @256x256 +1.2 ms).
+__device__ __forceinline__ uint32_t positive_bits16_packed(const uint32_t (&w)[8]) {
+  uint32_t bits = 0u;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t ta = w[2 * k] + 0x7FFF7FFFu, tb = w[2 * k + 1] + 0x7FFF7FFFu;
+    const uint32_t flags = __byte_perm(ta, tb, 0x7531) & 0x80808080u;      // bits 7 / 15 / 23 / 31 = elements 4k .. 4k+3
+    bits |= ((flags * 0x00204081u) >> 28) << (4 * k);
+  }
+  return bits;
+}
 __device__ __forceinline__ void apply_bits16(float (&f)[16], uint32_t mb) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) f[j] = ((mb >> j) & 1u) ? f[j] : 0.f;
@@ -387,6 +401,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
   const bool has_mask = F < 0 ? (p.mask != nullptr || p.mask_bits != nullptr) : (F & kEpiMask) != 0;
   const bool use_mbits = F < 0 ? (has_mask && p.mask_bits != nullptr) : (F & kEpiMaskBits) != 0;
   const bool emit_bits = F < 0 ? (do_relu && p.relu_bits != nullptr) : (F & kEpiBitsOut) != 0;
+  // the ReLU is the last arithmetic of the piece (no mask, no post-mask residual): take the bits from the packed output words
+  constexpr bool bits_from_packed = F >= 0 && (F & kEpiBitsOut) != 0 && (F & (kEpiMask | kEpiResPost)) == 0;
   const long long nw = p.Cout >> 6;
   const bool full_c = F >= 0 && (F & kEpiFull) != 0;       // no channel-tail tests
   const float rs = p.res_scale;
@@ -477,7 +493,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
         if (do_relu) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-          if (emit_bits) ob = positive_bits16(f);
+          if (emit_bits && !bits_from_packed) ob = positive_bits16(f);
         }
         if (use_mbits) {
           apply_bits16(f, mb);
@@ -510,10 +526,12 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& p, const CUtens
           }
         }
         // 16 channels = two 16-byte units (2s, 2s+1) of this row's 128-byte line; unit u lives at (u ^ (row & 7))
-        st_shared_v4(srow + (((uint32_t)(2 * s) ^ sw) << 4), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                     pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-        st_shared_v4(srow + (((uint32_t)(2 * s + 1) ^ sw) << 4), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
-                     pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+        if (bits_from_packed) ob = positive_bits16_packed(w);
+        st_shared_v4(srow + (((uint32_t)(2 * s) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+        st_shared_v4(srow + (((uint32_t)(2 * s + 1) ^ sw) << 4), w[4], w[5], w[6], w[7]);
         return ob;
     };
 #pragma unroll 1
