@@ -323,3 +323,38 @@ def test_uint8_dataset_matches_reference_transform_chain(tmp_path):
     out_i, out_l = torch.empty((4, 6, 5, 3), dtype=torch.uint8), torch.empty(4, dtype=torch.int64)
     ds.gather([7, 0, 2, 2], out_i, out_l)
     assert np.array_equal(out_i.numpy(), imgs[[7, 0, 2, 2]]) and out_l.tolist() == labels[[7, 0, 2, 2]].tolist()
+
+
+def test_spectral_norm_table_orders_cbn_packs_contiguously_and_counts_pack_units():
+    """Host logic of snbatch: the conditional-BN gain / bias linears lead the layer table so that their bf16 packs form ONE
+    [rows][K] matrix (snbatch.cbn_affine_all: all cBN affine maps of a gradient-free pass as one GEMM), every layer keeps its
+    own u / v slices, and tile_start counts the pack kernel's work units (include/sgb200.h, sgb_sn_layer)."""
+    from sgb200 import snbatch
+    from sgb200.utils import ops
+    G, D = _build(dict(conv_dim=16, depth=2, attn=True))
+    for net in (G, D):
+        sb = net._snb
+        sb._build(torch.device("cpu"))
+        t = np.frombuffer(sb.table.numpy().tobytes(), dtype=snbatch.LAYER_DTYPE)
+        assert len(t) == len(sb.mods) and len({id(m) for m in sb.mods}) == len(sb.mods)
+        # work units: cumulative, taps * ceil(Cout/32) * ceil(Cin/32) per layer (no layer of these networks has more than 9 taps)
+        units = 0
+        for e in t:
+            assert int(e["tile_start"]) == units
+            units += int(e["taps"]) * ((int(e["Cout"]) + 31) // 32) * ((int(e["Cin"]) + 31) // 32)
+        assert sb.max_blocks[2] == units
+        # packs: 128-byte aligned, non-overlapping, in table order
+        end = 0
+        for (of, od, nf, shf, shd, su, sv), e in zip(sb.slices, t):
+            assert of % 64 == 0 and of >= end and nf == int(e["Cout_p"]) * int(e["taps"]) * int(e["Cin_p"])
+            end = of + nf
+    cbn_lin = [m for mod in G.modules() if isinstance(mod, ops.ConditionalBatchNorm2d) for m in (mod.gain, mod.bias)]
+    n, rows, Kp, of0, spans = G._snb.cbn
+    assert n == len(cbn_lin) >= 16 and set(map(id, G._snb.mods[:n])) == set(map(id, cbn_lin))
+    assert all(getattr(m, "_cbn_affine", False) for m in G._snb.mods[:n]) and not any(getattr(m, "_cbn_affine", False) for m in G._snb.mods[n:])
+    r = 0
+    for m, (r0, c), sl in zip(G._snb.mods[:n], spans, G._snb.slices):
+        assert r0 == r and c == m.out_features and sl[0] == of0 + r0 * Kp and m.in_features <= Kp
+        r += (c + 7) // 8 * 8
+    assert r == rows
+    assert D._snb.cbn is None                                   # no conditional batch norm in the discriminator
