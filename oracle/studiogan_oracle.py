@@ -96,6 +96,33 @@ def self_attention(sd, prefix, x, training=True):
     return x + sd[prefix + "sigma"] * attn_g
 
 
+def softmax_from_partials(scores, part_width):
+    """nn.Softmax(dim=-1) of src/utils/ops.py:95 computed the way the GEMM epilogues do (csrc/conv_epilogue.cuh, sm_mode 1 / 2):
+    the key axis is cut into parts of ``part_width`` columns, every part keeps (max, sum exp(. - max)) of its columns, and the
+    second pass merges the partials of a row into (m, l) and writes exp(s - m) / l.  Algebraically identical to the softmax."""
+    N, M = scores.shape[-2:]
+    parts = scores.split(part_width, dim=-1)
+    m_t = torch.stack([p.max(-1).values for p in parts], -1)                       # [..., N, parts]
+    l_t = torch.stack([(p - p.max(-1, keepdim=True).values).exp().sum(-1) for p in parts], -1)
+    m = m_t.max(-1, keepdim=True).values
+    l = (l_t * (m_t - m).exp()).sum(-1, keepdim=True)
+    return (scores - m).exp() / l
+
+
+def softmax_backward_with_delta(P, dO, V):
+    """Backward of ``P = softmax(S); O = P @ V`` w.r.t. S as the dP GEMM's epilogue forms it (sm_mode 3):
+    dS = P * (dP - delta) with dP = dO @ V^T and delta = rowsum(dO * O) -- equal to rowsum(P * dP), so dP need not exist."""
+    O = P @ V
+    delta = (dO * O).sum(-1, keepdim=True)
+    return P * (dO @ V.transpose(-1, -2) - delta)
+
+
+def relu_bit_planes(y_nhwc):
+    """(y > 0) of a post-ReLU NHWC tensor as the conv epilogues store it (sgb_conv_desc.relu_bits): one little-endian 64-bit word
+    per (pixel, 64-channel chunk), bit j = channel 64 * chunk + j, i.e. numpy's packbits(bitorder='little') over the channels."""
+    return np.packbits(np.asarray(y_nhwc) > 0, axis=-1, bitorder="little")
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # BigGAN-Deep (legacy)  (src/models/big_resnet_deep_legacy.py)
 # ---------------------------------------------------------------------------------------------------------------------

@@ -271,3 +271,27 @@ def test_augmentations_closed_form_and_rng_order_match_reference(golden_dir):
         torch.manual_seed(777)
         f, tx, ty = cr.draw_params(B, H, W, "cpu")
         np.testing.assert_array_equal(O.cr_aug_closed_form(x, f, tx, ty).numpy(), g["cr_" + tag])
+
+
+def test_epilogue_algorithms_equal_the_reference_operators():
+    """The restatements of what the GEMM epilogues compute (two-pass softmax from per-part (max, sum exp) partials, softmax
+    backward through delta = rowsum(dO * O), ReLU bit planes) against torch's own softmax / autograd and numpy (fp64)."""
+    g = torch.Generator().manual_seed(7)
+    S = torch.randn(3, 40, 256, generator=g, dtype=torch.float64) * 4
+    for width in (64, 128, 256):
+        P = O.softmax_from_partials(S, width)
+        assert torch.allclose(P, torch.softmax(S, -1), rtol=1e-12, atol=1e-15)
+    # backward: d/dS of <dO, softmax(S) @ V>
+    V = torch.randn(3, 256, 32, generator=g, dtype=torch.float64)
+    dO = torch.randn(3, 40, 32, generator=g, dtype=torch.float64)
+    Sg = S.clone().requires_grad_(True)
+    (torch.softmax(Sg, -1) @ V * dO).sum().backward()
+    dS = O.softmax_backward_with_delta(torch.softmax(S, -1), dO, V)
+    assert torch.allclose(dS, Sg.grad, rtol=1e-10, atol=1e-13)
+    # bit planes: word c of a pixel = channels 64c .. 64c+63, little-endian
+    y = torch.relu(torch.randn(2, 3, 3, 128, generator=g)).numpy()
+    bits = O.relu_bit_planes(y)
+    assert bits.shape == (2, 3, 3, 16) and bits.dtype == np.uint8
+    words = bits.view(np.uint64).reshape(2, 3, 3, 2)
+    for c in (0, 5, 63, 64, 100, 127):
+        assert np.array_equal((words[..., c // 64] >> np.uint64(c % 64)) & np.uint64(1), (y[..., c] > 0).astype(np.uint64))
